@@ -1,0 +1,144 @@
+/* spp_rl_b200 -- C ABI of the B200-native SPP-RL hot path.
+ *
+ * The reference (raznem/spp-rl, package rltoolkit) is pure Python and has no FFI: every seam on
+ * the hot path is a Python method.  This header declares the entry points a rltoolkit maintainer
+ * would bind (ctypes stub in INTEGRATION.md) to replace those method bodies.  Each entry point
+ * cites the reference method it replaces.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - A `spp_population` holds P independent agents (the reference runs them as OS processes,
+ *     train/spp_sac_hopper.py:115); agent index `a` in [0, P).  `a = -1` means "all agents".
+ *   - Host arrays are dense row-major float32 unless stated; the library owns all device memory.
+ *   - Return value: SPP_OK (0) or a negative error class; text via spp_last_error() (thread local).
+ *   - Calls on one population must come from one host thread at a time; populations are independent.
+ *   - Entry points ending in `_device` take DEVICE pointers and are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*; NULL = default stream).  All others are synchronous.
+ */
+#ifndef SPP_RL_B200_H
+#define SPP_RL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPP_ABI_VERSION 1
+
+enum { SPP_OK = 0, SPP_ERR_ARG = -1, SPP_ERR_CUDA = -2, SPP_ERR_STATE = -3, SPP_ERR_UNSUPPORTED = -4 };
+enum { SPP_ALGO_SAC = 0, SPP_ALGO_DDPG = 1 };
+enum { SPP_ACM_MLP = 0 /* rltoolkit/basic_model.py:108-132 */, SPP_ACM_BASIC = 1 /* rltoolkit/acm/models/basic_acm.py:11-32 */ };
+/* nets of an agent (DDPG uses CRITIC_1 / CRITIC_1_TARG as critic / critic_targ) */
+enum {
+    SPP_NET_ACTOR = 0, SPP_NET_CRITIC_1 = 1, SPP_NET_CRITIC_2 = 2, SPP_NET_ACM = 3,
+    SPP_NET_CRITIC_1_TARG = 4, SPP_NET_CRITIC_2_TARG = 5, SPP_NET_ACTOR_TARG = 6
+};
+/* slots of one row of the loss output (8 floats per agent per update step) */
+enum {
+    SPP_LOSS_CRITIC_1 = 0, SPP_LOSS_CRITIC_2 = 1, SPP_LOSS_ACTOR = 2, SPP_LOSS_PI = 3 /* "sac"/"ddpg" */,
+    SPP_LOSS_DIST = 4, SPP_LOSS_ALPHA = 5, SPP_LOSS_ALPHA_VALUE = 6, SPP_LOSS_COUNT = 8
+};
+
+typedef struct spp_population spp_population;
+
+/* Hyper-parameters of the update path; names follow the reference constructor kwargs
+ * (rltoolkit/algorithms/ddpg/ddpg.py:19-33, sac/sac.py:17-26, acm/acm.py:16-37,
+ *  acm/off_policy/off_policy.py:9-15, acm/off_policy/ddpg_acm.py:11-13). */
+typedef struct spp_config {
+    int32_t algo;                 /* SPP_ALGO_* */
+    int32_t ob_dim, ac_dim;       /* observation / env-action dims; state-target dim == ob_dim */
+    int32_t acm_kind;             /* SPP_ACM_* */
+    int32_t acm_critic;           /* critic sees the ACM's env action (1) or the state target (0) */
+    int32_t norm_closs;           /* custom loss in normalised space */
+    int32_t min_max_denormalize;  /* min-max (1) or mean-std (0) (de)normalisation */
+    int32_t update_batch_size;    /* B */
+    int32_t acm_batch_size;
+    int32_t store_actions;        /* keep the state-target action column of the ring (needed if !acm_critic) */
+    int64_t buffer_size;          /* replay ring capacity per agent */
+    double gamma, tau, actor_lr, critic_lr, alpha_lr, acm_lr, custom_loss, alpha, target_entropy;
+} spp_config;
+
+int spp_abi_version(void);
+const char* spp_last_error(void);
+
+int spp_population_create(const spp_config* cfg, int population, int device, spp_population** out);
+int spp_population_destroy(spp_population* p);
+int spp_sync(spp_population* p);
+
+/* ---- limits and normalisation statistics ------------------------------------------------------
+ * actor_lim[ob]: AcMTrainer.actor_ac_lim (rltoolkit/acm/acm.py:102-108) broadcast to ob entries;
+ * acm_lim[ac]:   MetaLearner.ac_lim (rltoolkit/rl.py:53).
+ * stats: replay_buffer.min_obs/max_obs/obs_mean/obs_std (rltoolkit/buffer/memory.py:76-127); any
+ * pointer may be NULL = unset (identity, as the reference does for None). */
+int spp_set_limits(spp_population* p, const float* actor_lim, const float* acm_lim);
+int spp_set_norm_stats(spp_population* p, int a, const float* min_obs, const float* max_obs,
+                       const float* obs_mean, const float* obs_std);
+
+/* ---- parameters: state_dict() / load_state_dict() of the reference nn.Modules -------------------
+ * Tensors are enumerated per net in the reference's state_dict order with the reference's names
+ * (e.g. "fc1.weight", "fc_prob.bias", "t1"); shapes are the reference's [rows, cols]. */
+int spp_net_tensor_count(spp_population* p, int net);
+int spp_net_tensor_info(spp_population* p, int net, int t, char* name, int name_cap, int* rows, int* cols);
+int spp_params_upload(spp_population* p, int a, int net, int t, const float* host);
+int spp_params_download(spp_population* p, int a, int net, int t, float* host);
+/* Adam moments / step of a trainable tensor (torch.optim.Adam state; rltoolkit/rl.py:62). */
+int spp_adam_download(spp_population* p, int a, int net, int t, float* exp_avg, float* exp_avg_sq, int* step);
+int spp_adam_reset(spp_population* p, int a, int net);
+/* target <- online deep copy (DDPG.critic setter, rltoolkit/algorithms/ddpg/ddpg.py:150-157;
+ * SAC.critic_1 setter, rltoolkit/algorithms/sac/sac.py:124-136). */
+int spp_sync_targets(spp_population* p, int a);
+/* SAC temperature: log_alpha (float64, rltoolkit/algorithms/sac/sac.py:107-110). */
+int spp_alpha_get(spp_population* p, int a, double* log_alpha, double* alpha);
+int spp_alpha_set(spp_population* p, int a, double log_alpha);
+
+/* ---- replay ring: BufferAcMOffPolicy (rltoolkit/buffer/replay_buffer.py:303-401) ----------------
+ * add_obs :56-60, add_timestep :65-75 + ReplayBuffer.addition :133-137, add_acm_action :332-333.
+ * The cursor state machine runs on the host (bit-exact), rows are written to device memory. */
+int spp_ring_add_obs(spp_population* p, int a, const float* obs, int64_t* out_idx);
+int spp_ring_add_acm_action(spp_population* p, int a, const float* acm_action);
+int spp_ring_add_timestep(spp_population* p, int a, int64_t obs_idx, int64_t next_obs_idx,
+                          const float* action, float reward, int done, int end);
+int spp_ring_reset(spp_population* p, int a);
+/* cursors: out[0] = obs cursor, out[1] = timestep cursor, out[2] = current_len (== len(buffer)) */
+int spp_ring_state(spp_population* p, int a, int64_t out[3]);
+/* sample_batch :385-398 for given indices (np.random.randint stays on the caller's side so index
+ * streams are the reference's): two-level gather on the device, results to host arrays.
+ * action may be NULL.  done is int8 like the reference. */
+int spp_ring_sample_batch(spp_population* p, int a, const int64_t* idx, int n, float* obs, float* next_obs,
+                          float* action, float* reward, int8_t* done, float* acm_action);
+/* Synthetic prefill for benchmarks: n transitions per agent in episodes of
+ * `episode_len`, obs ~ U(min_obs,max_obs), next = obs + 0.02 N(0,1), reward ~ N(0,1), done ~ Bern(1e-3). */
+int spp_ring_fill_synthetic(spp_population* p, uint64_t seed, int64_t n, int episode_len);
+/* Device-resident gather of n_batches minibatches per agent (indices drawn on device): measures the
+ * HBM path of sample_batch in isolation.  bytes_out = algorithmic bytes moved per call. */
+int spp_ring_gather_bench_device(spp_population* p, int n_batches, uint64_t seed, double* bytes_out, void* stream);
+
+/* ---- the update step: SAC_AcM.update (rltoolkit/acm/off_policy/sac_acm.py:89-162) /
+ *      DDPG_AcM.update (rltoolkit/acm/off_policy/ddpg_acm.py:147-201), `grad_steps` in a row as
+ *      DDPG.make_update does (rltoolkit/algorithms/ddpg/ddpg.py:231-237). ---------------------------
+ * Host-batch form = the reference's update(obs, next_obs, action, reward, done, acm_action):
+ *   obs, next_obs [P][G][B][ob]; action [P][G][B][ob] (NULL allowed when acm_critic); reward [P][G][B];
+ *   done int8 [P][G][B]; acm_action [P][G][B][ac];
+ *   eps [P][G][2][B][ob]: the N(0,1) draws of Normal.rsample, target pass first then policy pass
+ *   (rltoolkit/algorithms/sac/models.py:45); NULL -> drawn on device (Philox, `seed`).  Ignored for DDPG.
+ *   losses [P][G][8] (may be NULL).  Copies H2D, runs one fused kernel, copies losses D2H. */
+int spp_update_host(spp_population* p, int grad_steps, const float* obs, const float* next_obs,
+                    const float* action, const float* reward, const int8_t* done, const float* acm_action,
+                    const float* eps, uint64_t seed, float* losses);
+/* Ring form = sample_batch + update: idx int64 [P][G][B] host indices (NULL -> device sampler). */
+int spp_update_ring(spp_population* p, int grad_steps, const int64_t* idx, const float* eps, uint64_t seed,
+                    float* losses);
+/* Fully device-resident form (no host traffic): device sampler + device noise; losses_dev may be NULL. */
+int spp_update_ring_device(spp_population* p, int grad_steps, uint64_t seed, float* losses_dev, void* stream);
+
+/* ---- introspection for tests ------------------------------------------------------------------ */
+/* copy a named scratch buffer of agent a to host ("xo","xn","xc","xcp","xm","ha1","ha2","ml","hc1_0",...);
+ * rows/ld describe the returned dense [rows x ld] block. */
+int spp_debug_scratch(spp_population* p, int a, const char* name, float* host, int cap, int* rows, int* ld);
+int spp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_cap);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t spp_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPP_RL_B200_H */

@@ -1,0 +1,693 @@
+// C ABI of spp_rl_b200 (see include/spp_rl_b200.h): handle, device memory, parameter I/O, replay ring
+// host state machine, and the launchers of the fused update kernels.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/spp_rl_b200.h"
+#include "layout.h"
+#include "ring_kernels.h"
+#include "update_kernel.cuh"
+
+namespace spp {
+cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream);
+}
+
+using namespace spp;
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(SPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+struct TensorMap {
+    std::string name;
+    int layer;      // index into NetDesc::L
+    int is_bias;    // 0: rows of W, 1: bias vector, 2: gain row of the BasicAcM pseudo layer
+    int row0;       // first row inside the layer (heads: fc_prob rows [0,ob), fc_scale rows [ob,2ob))
+    int rows, cols; // reference shape
+    int col0;       // gains: first column inside the pseudo layer
+};
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct spp_population {
+    spp_config cfg;
+    int P = 0, device = 0, sm_count = 0;
+    Layout L;
+    Hyper h;
+    float *params = nullptr, *mom_m = nullptr, *mom_v = nullptr, *scratch = nullptr, *norm = nullptr, *acm_lim = nullptr;
+    int* steps = nullptr;
+    double* alpha_state = nullptr;
+    // ring
+    int64_t S = 0;
+    float *r_obs = nullptr, *r_act = nullptr, *r_rew = nullptr, *r_aacm = nullptr;
+    int32_t *r_oidx = nullptr, *r_nidx = nullptr;
+    uint8_t *r_done = nullptr, *r_end = nullptr;
+    int64_t* r_len = nullptr;    // device copy of current_len per agent
+    std::vector<int64_t> obs_cur, ts_cur, cur_len;
+    bool len_dirty = true;
+    // staging
+    DevBuf d_obs, d_nobs, d_act, d_rew, d_done, d_aacm, d_eps, d_idx, d_losses, d_tmp;
+    cudaStream_t stream = nullptr;
+    uint64_t seq = 0;
+    std::vector<TensorMap> tensors[NET_COUNT];
+};
+
+static const NetDesc& net_desc(const spp_population* p, int net) {
+    switch (net) {
+        case NET_ACTOR: case NET_ACTOR_TARG: return p->L.actor;
+        case NET_ACM: return p->L.acm;
+        default: return p->L.critic;
+    }
+}
+
+static void build_tensor_maps(spp_population* p) {
+    const Layout& L = p->L;
+    auto lin = [](std::vector<TensorMap>& v, const char* nm, int layer, int row0, int rows, int cols) {
+        v.push_back({std::string(nm) + ".weight", layer, 0, row0, rows, cols, 0});
+        v.push_back({std::string(nm) + ".bias", layer, 1, row0, rows, 1, 0});
+    };
+    for (int net : {NET_ACTOR, NET_ACTOR_TARG}) {
+        auto& v = p->tensors[net];
+        lin(v, "fc1", 0, 0, kHidden, L.ob);
+        lin(v, "fc2", 1, 0, kHidden, kHidden);
+        if (L.algo == ALGO_SAC) {
+            lin(v, "fc_prob", 2, 0, L.ob, kHidden);
+            lin(v, "fc_scale", 2, L.ob, L.ob, kHidden);
+        } else {
+            lin(v, "fc3", 2, 0, L.ob, kHidden);
+        }
+    }
+    for (int net : {NET_CRITIC_1, NET_CRITIC_2, NET_CRITIC_1_TARG, NET_CRITIC_2_TARG}) {
+        auto& v = p->tensors[net];
+        lin(v, "fc1", 0, 0, kHidden, L.ob + L.act_dim);
+        lin(v, "fc2", 1, 0, kHidden, kHidden);
+        lin(v, "fc3", 2, 0, 1, kHidden);
+    }
+    {
+        auto& v = p->tensors[NET_ACM];
+        if (L.acm_kind == ACM_BASIC) {   // state_dict order of BasicAcM: t, t1, fc1, fc2, fc21, fc3
+            v.push_back({"t", 4, 2, 0, 1, 1, 0});
+            v.push_back({"t1", 4, 2, 0, L.ac, 1, 4});
+            lin(v, "fc1", 0, 0, L.hm1, 2 * L.ob);
+            lin(v, "fc2", 1, 0, L.hm2, L.hm1);
+            lin(v, "fc21", 3, 0, L.hm2, 2 * L.ob);
+            lin(v, "fc3", 2, 0, L.ac, L.hm2);
+        } else {
+            lin(v, "fc1", 0, 0, L.hm1, 2 * L.ob);
+            lin(v, "fc2", 1, 0, L.hm2, L.hm1);
+            lin(v, "fc3", 2, 0, L.ac, L.hm2);
+        }
+    }
+}
+
+static inline int map_col(const LayerDesc& l, int c) { return (l.split > 0 && c >= l.split) ? pad4(l.split) + (c - l.split) : c; }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int spp_abi_version(void) { return SPP_ABI_VERSION; }
+const char* spp_last_error(void) { return g_err.c_str(); }
+int64_t spp_kernel_launches(void) { return g_launches.load(); }
+
+int spp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_cap) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name && name_cap > 0) { strncpy(name, prop.name, name_cap - 1); name[name_cap - 1] = 0; }
+    return SPP_OK;
+}
+
+int spp_population_destroy(spp_population* p) {
+    if (!p) return SPP_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (void* q : {(void*)p->params, (void*)p->mom_m, (void*)p->mom_v, (void*)p->scratch, (void*)p->norm, (void*)p->acm_lim,
+                    (void*)p->steps, (void*)p->alpha_state, (void*)p->r_obs, (void*)p->r_act, (void*)p->r_rew, (void*)p->r_aacm,
+                    (void*)p->r_oidx, (void*)p->r_nidx, (void*)p->r_done, (void*)p->r_end, (void*)p->r_len})
+        if (q) cudaFree(q);
+    for (DevBuf* b : {&p->d_obs, &p->d_nobs, &p->d_act, &p->d_rew, &p->d_done, &p->d_aacm, &p->d_eps, &p->d_idx, &p->d_losses, &p->d_tmp})
+        b->release();
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return SPP_OK;
+}
+
+int spp_population_create(const spp_config* cfg, int population, int device, spp_population** out) {
+    if (!cfg || !out || population < 1) return fail(SPP_ERR_ARG, "spp_population_create: null argument or population < 1");
+    if (cfg->ob_dim < 1 || cfg->ob_dim > 128 || cfg->ac_dim < 1 || cfg->ac_dim > 32)
+        return fail(SPP_ERR_ARG, "spp_population_create: ob_dim must be in [1,128], ac_dim in [1,32]");
+    if (cfg->update_batch_size < 1 || cfg->update_batch_size > 4096) return fail(SPP_ERR_ARG, "update_batch_size must be in [1,4096]");
+    if (cfg->algo != SPP_ALGO_SAC && cfg->algo != SPP_ALGO_DDPG) return fail(SPP_ERR_ARG, "unknown algo");
+    if (cfg->acm_kind != SPP_ACM_MLP && cfg->acm_kind != SPP_ACM_BASIC) return fail(SPP_ERR_ARG, "unknown acm_kind");
+    if (!cfg->acm_critic && !cfg->store_actions && cfg->buffer_size > 0)
+        return fail(SPP_ERR_ARG, "acm_critic=0 needs store_actions=1 (the critic reads the state-target action)");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(SPP_ERR_ARG, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(SPP_ERR_UNSUPPORTED, "spp_rl_b200 is built for sm_100a (B200) only");
+
+    spp_population* p = new spp_population();
+    p->cfg = *cfg; p->P = population; p->device = device; p->sm_count = prop.multiProcessorCount;
+    p->L = make_layout(cfg->algo, cfg->ob_dim, cfg->ac_dim, cfg->acm_kind, cfg->acm_critic ? 1 : 0, cfg->update_batch_size);
+    Hyper& h = p->h;
+    h.gamma = (float)cfg->gamma; h.tau = (float)cfg->tau; h.one_minus_tau = (float)(1.0 - cfg->tau);
+    h.custom_loss = (float)cfg->custom_loss; h.target_entropy = (float)cfg->target_entropy;
+    h.actor_lr = cfg->actor_lr; h.critic_lr = cfg->critic_lr; h.alpha_lr = cfg->alpha_lr;
+    h.norm_closs = cfg->norm_closs ? 1 : 0; h.norm_clamp = cfg->min_max_denormalize ? 0 : 1;
+    build_tensor_maps(p);
+    const Layout& L = p->L;
+    const size_t P = (size_t)population;
+    auto alloc = [&](void** q, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(q, bytes ? bytes : 16);
+        if (e == cudaSuccess) e = cudaMemset(*q, 0, bytes ? bytes : 16);
+        return e;
+    };
+#define ALLOC(ptr, bytes)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = alloc((void**)&(ptr), (bytes));                                           \
+        if (e_ != cudaSuccess) {                                                                   \
+            std::string m = std::string("cudaMalloc(" #ptr "): ") + cudaGetErrorString(e_);        \
+            spp_population_destroy(p);                                                             \
+            return fail(SPP_ERR_CUDA, m);                                                          \
+        }                                                                                          \
+    } while (0)
+    ALLOC(p->params, P * L.params_size * sizeof(float));
+    ALLOC(p->mom_m, P * L.train_size * sizeof(float));
+    ALLOC(p->mom_v, P * L.train_size * sizeof(float));
+    ALLOC(p->scratch, P * L.s.size * sizeof(float));
+    ALLOC(p->norm, P * NORM_COUNT * L.ldo * sizeof(float));
+    ALLOC(p->acm_lim, 32 * sizeof(float));
+    ALLOC(p->steps, P * 4 * sizeof(int));
+    ALLOC(p->alpha_state, P * 4 * sizeof(double));
+    p->S = cfg->buffer_size;
+    if (p->S > 0) {
+        if (p->S > 2000000000LL) { spp_population_destroy(p); return fail(SPP_ERR_ARG, "buffer_size too large"); }
+        ALLOC(p->r_obs, P * p->S * L.ldo * sizeof(float));
+        if (cfg->store_actions) ALLOC(p->r_act, P * p->S * L.ldo * sizeof(float));
+        ALLOC(p->r_rew, P * p->S * sizeof(float));
+        ALLOC(p->r_aacm, P * p->S * L.lda * sizeof(float));
+        ALLOC(p->r_oidx, P * p->S * sizeof(int32_t));
+        ALLOC(p->r_nidx, P * p->S * sizeof(int32_t));
+        ALLOC(p->r_done, P * p->S);
+        ALLOC(p->r_end, P * p->S);
+    }
+    ALLOC(p->r_len, P * sizeof(int64_t));
+#undef ALLOC
+    p->obs_cur.assign(P, 0); p->ts_cur.assign(P, 0); p->cur_len.assign(P, 0);
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        spp_population_destroy(p);
+        return fail(SPP_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    // defaults: limits 1, identity (de)normalisation, log_alpha = log(alpha)
+    std::vector<float> ones(128, 1.f);
+    *out = p;
+    int rc = spp_set_limits(p, ones.data(), ones.data());
+    if (rc == SPP_OK) rc = spp_set_norm_stats(p, -1, nullptr, nullptr, nullptr, nullptr);
+    if (rc == SPP_OK && cfg->algo == SPP_ALGO_SAC) rc = spp_alpha_set(p, -1, std::log(cfg->alpha > 0 ? cfg->alpha : 0.2));
+    if (rc != SPP_OK) { std::string m = g_err; spp_population_destroy(p); *out = nullptr; return fail(rc, m); }
+    return SPP_OK;
+}
+
+int spp_sync(spp_population* p) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaDeviceSynchronize());
+    return SPP_OK;
+}
+
+int spp_set_limits(spp_population* p, const float* actor_lim, const float* acm_lim) {
+    if (!p || !actor_lim || !acm_lim) return fail(SPP_ERR_ARG, "spp_set_limits: null argument");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    std::vector<float> v(L.ldo, 0.f);
+    for (int j = 0; j < L.ob; ++j) v[j] = actor_lim[j];
+    for (int a = 0; a < p->P; ++a)
+        CK(cudaMemcpy(p->norm + ((size_t)a * NORM_COUNT + NORM_LIM) * L.ldo, v.data(), L.ldo * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> m(32, 0.f);
+    for (int j = 0; j < L.ac; ++j) m[j] = acm_lim[j];
+    CK(cudaMemcpy(p->acm_lim, m.data(), 32 * sizeof(float), cudaMemcpyHostToDevice));
+    return SPP_OK;
+}
+
+int spp_set_norm_stats(spp_population* p, int a, const float* min_obs, const float* max_obs, const float* obs_mean,
+                       const float* obs_std) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    if (a < -1 || a >= p->P) return fail(SPP_ERR_ARG, "agent index out of range");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    std::vector<float> v(4 * (size_t)L.ldo, 0.f);
+    float* doff = v.data(); float* dsc = doff + L.ldo; float* nsub = dsc + L.ldo; float* ndiv = nsub + L.ldo;
+    for (int j = 0; j < L.ldo; ++j) { doff[j] = 0.f; dsc[j] = (j < L.ob) ? 1.f : 0.f; nsub[j] = 0.f; ndiv[j] = 1.f; }
+    if (p->cfg.min_max_denormalize) {
+        if (min_obs && max_obs)
+            for (int j = 0; j < L.ob; ++j) {   // memory.py:80-82 and :119-121, evaluated in float32 like torch
+                const float mean = (max_obs[j] + min_obs[j]) / 2.f;
+                doff[j] = mean;
+                dsc[j] = (max_obs[j] - min_obs[j]) / 2.f;
+                nsub[j] = mean;
+                ndiv[j] = (max_obs[j] - mean) + 1e-8f;
+            }
+    } else if (obs_mean && obs_std) {
+        for (int j = 0; j < L.ob; ++j) {       // memory.py:123 and utils.py:70
+            doff[j] = obs_mean[j];
+            dsc[j] = obs_std[j] + 1e-8f;
+            nsub[j] = obs_mean[j];
+            ndiv[j] = obs_std[j] + 1e-8f;
+        }
+    }
+    for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i)
+        CK(cudaMemcpy(p->norm + (size_t)i * NORM_COUNT * L.ldo, v.data(), 4 * (size_t)L.ldo * sizeof(float), cudaMemcpyHostToDevice));
+    return SPP_OK;
+}
+
+// ---- parameters ------------------------------------------------------------------------------------
+int spp_net_tensor_count(spp_population* p, int net) {
+    if (!p || net < 0 || net >= NET_COUNT) return fail(SPP_ERR_ARG, "bad net id");
+    return (int)p->tensors[net].size();
+}
+
+int spp_net_tensor_info(spp_population* p, int net, int t, char* name, int name_cap, int* rows, int* cols) {
+    if (!p || net < 0 || net >= NET_COUNT || t < 0 || t >= (int)p->tensors[net].size()) return fail(SPP_ERR_ARG, "bad net/tensor id");
+    const TensorMap& m = p->tensors[net][t];
+    if (name && name_cap > 0) { strncpy(name, m.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (rows) *rows = m.rows;
+    if (cols) *cols = m.cols;
+    return SPP_OK;
+}
+
+// direction: 0 upload params, 1 download params, 2 download m, 3 download v
+static int tensor_io(spp_population* p, int a, int net, int t, float* host, int dir) {
+    if (!p || !host) return fail(SPP_ERR_ARG, "null argument");
+    if (net < 0 || net >= NET_COUNT || t < 0 || t >= (int)p->tensors[net].size()) return fail(SPP_ERR_ARG, "bad net/tensor id");
+    if (a < (dir == 0 ? -1 : 0) || a >= p->P) return fail(SPP_ERR_ARG, "agent index out of range");
+    if (dir >= 2 && net > NET_ACM) return fail(SPP_ERR_ARG, "target nets have no optimiser state");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    const TensorMap& m = p->tensors[net][t];
+    const LayerDesc& l = net_desc(p, net).L[m.layer];
+    const size_t stride = (dir >= 2) ? L.train_size : L.params_size;
+    float* arena = dir == 2 ? p->mom_m : dir == 3 ? p->mom_v : p->params;
+    size_t off; int n_dev;            // contiguous device span [off, off + n_dev)
+    if (m.is_bias == 0) { off = l.off_w + (size_t)m.row0 * l.ld; n_dev = m.rows * l.ld; }
+    else if (m.is_bias == 1) { off = l.off_b + m.row0; n_dev = m.rows; }
+    else { off = l.off_w + m.col0; n_dev = m.rows; }
+    std::vector<float> stage(n_dev, 0.f);
+    for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i) {
+        float* dev = arena + (size_t)i * stride + L.net_off[net] + off;
+        if (dir == 0) {
+            if (m.is_bias == 0)
+                for (int r = 0; r < m.rows; ++r)
+                    for (int c = 0; c < m.cols; ++c) stage[(size_t)r * l.ld + map_col(l, c)] = host[(size_t)r * m.cols + c];
+            else
+                for (int r = 0; r < m.rows; ++r) stage[r] = host[r];
+            CK(cudaMemcpy(dev, stage.data(), n_dev * sizeof(float), cudaMemcpyHostToDevice));
+        } else {
+            CK(cudaStreamSynchronize(p->stream));
+            CK(cudaMemcpy(stage.data(), dev, n_dev * sizeof(float), cudaMemcpyDeviceToHost));
+            if (m.is_bias == 0)
+                for (int r = 0; r < m.rows; ++r)
+                    for (int c = 0; c < m.cols; ++c) host[(size_t)r * m.cols + c] = stage[(size_t)r * l.ld + map_col(l, c)];
+            else
+                for (int r = 0; r < m.rows; ++r) host[r] = stage[r];
+        }
+    }
+    return SPP_OK;
+}
+
+int spp_params_upload(spp_population* p, int a, int net, int t, const float* host) { return tensor_io(p, a, net, t, const_cast<float*>(host), 0); }
+int spp_params_download(spp_population* p, int a, int net, int t, float* host) { return tensor_io(p, a, net, t, host, 1); }
+
+int spp_adam_download(spp_population* p, int a, int net, int t, float* exp_avg, float* exp_avg_sq, int* step) {
+    int rc = SPP_OK;
+    if (exp_avg) rc = tensor_io(p, a, net, t, exp_avg, 2);
+    if (rc == SPP_OK && exp_avg_sq) rc = tensor_io(p, a, net, t, exp_avg_sq, 3);
+    if (rc == SPP_OK && step) {
+        if (!p || net < 0 || net > NET_ACM || a < 0 || a >= p->P) return fail(SPP_ERR_ARG, "bad net/agent");
+        CK(cudaStreamSynchronize(p->stream));
+        CK(cudaMemcpy(step, p->steps + (size_t)a * 4 + net, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return rc;
+}
+
+int spp_adam_reset(spp_population* p, int a, int net) {
+    if (!p || net < 0 || net > NET_ACM || a < -1 || a >= p->P) return fail(SPP_ERR_ARG, "bad net/agent");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    const Layout& L = p->L;
+    const size_t n = net_desc(p, net).size;
+    for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i) {
+        CK(cudaMemset(p->mom_m + (size_t)i * L.train_size + L.net_off[net], 0, n * sizeof(float)));
+        CK(cudaMemset(p->mom_v + (size_t)i * L.train_size + L.net_off[net], 0, n * sizeof(float)));
+        CK(cudaMemset(p->steps + (size_t)i * 4 + net, 0, sizeof(int)));
+    }
+    return SPP_OK;
+}
+
+int spp_sync_targets(spp_population* p, int a) {
+    if (!p || a < -1 || a >= p->P) return fail(SPP_ERR_ARG, "bad agent");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    const Layout& L = p->L;
+    for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i) {
+        float* base = p->params + (size_t)i * L.params_size;
+        CK(cudaMemcpy(base + L.net_off[NET_CRITIC_1_TARG], base + L.net_off[NET_CRITIC_1], L.critic.size * sizeof(float), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(base + L.net_off[NET_CRITIC_2_TARG], base + L.net_off[NET_CRITIC_2], L.critic.size * sizeof(float), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(base + L.net_off[NET_ACTOR_TARG], base + L.net_off[NET_ACTOR], L.actor.size * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+    return SPP_OK;
+}
+
+int spp_alpha_get(spp_population* p, int a, double* log_alpha, double* alpha) {
+    if (!p || a < 0 || a >= p->P) return fail(SPP_ERR_ARG, "bad agent");
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    double la = 0;
+    CK(cudaMemcpy(&la, p->alpha_state + (size_t)a * 4, sizeof(double), cudaMemcpyDeviceToHost));
+    if (log_alpha) *log_alpha = la;
+    if (alpha) *alpha = std::exp(la);
+    return SPP_OK;
+}
+
+int spp_alpha_set(spp_population* p, int a, double log_alpha) {
+    if (!p || a < -1 || a >= p->P) return fail(SPP_ERR_ARG, "bad agent");
+    CK(cudaSetDevice(p->device));
+    const double st[4] = {log_alpha, 0.0, 0.0, 0.0};
+    for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i)
+        CK(cudaMemcpy(p->alpha_state + (size_t)i * 4, st, sizeof(st), cudaMemcpyHostToDevice));
+    return SPP_OK;
+}
+
+// ---- replay ring -----------------------------------------------------------------------------------
+static int ring_check(spp_population* p, int a) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    if (a < 0 || a >= p->P) return fail(SPP_ERR_ARG, "agent index out of range");
+    if (p->S <= 0) return fail(SPP_ERR_STATE, "population was created without a replay ring (buffer_size = 0)");
+    return SPP_OK;
+}
+
+int spp_ring_add_obs(spp_population* p, int a, const float* obs, int64_t* out_idx) {
+    int rc = ring_check(p, a); if (rc) return rc;
+    if (!obs) return fail(SPP_ERR_ARG, "null obs");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    const int64_t i = p->obs_cur[a];
+    CK(cudaMemcpy(p->r_obs + ((size_t)a * p->S + i) * L.ldo, obs, L.ob * sizeof(float), cudaMemcpyHostToDevice));
+    p->obs_cur[a] = (i + 1) % p->S;                        // replay_buffer.py:56-60
+    if (out_idx) *out_idx = i;
+    return SPP_OK;
+}
+
+int spp_ring_add_acm_action(spp_population* p, int a, const float* acm_action) {
+    int rc = ring_check(p, a); if (rc) return rc;
+    if (!acm_action) return fail(SPP_ERR_ARG, "null acm_action");
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpy(p->r_aacm + ((size_t)a * p->S + p->ts_cur[a]) * p->L.lda, acm_action, p->L.ac * sizeof(float), cudaMemcpyHostToDevice));
+    return SPP_OK;                                         // replay_buffer.py:332-333
+}
+
+int spp_ring_add_timestep(spp_population* p, int a, int64_t obs_idx, int64_t next_obs_idx, const float* action,
+                          float reward, int done, int end) {
+    int rc = ring_check(p, a); if (rc) return rc;
+    if (obs_idx < 0 || obs_idx >= p->S || next_obs_idx < 0 || next_obs_idx >= p->S) return fail(SPP_ERR_ARG, "obs index out of range");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    const int64_t ts = p->ts_cur[a];
+    const size_t row = (size_t)a * p->S + ts;
+    const int32_t oi = (int32_t)obs_idx, ni = (int32_t)next_obs_idx;
+    const uint8_t d = done ? 1 : 0, e = end ? 1 : 0;
+    CK(cudaMemcpy(p->r_oidx + row, &oi, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->r_nidx + row, &ni, 4, cudaMemcpyHostToDevice));
+    if (action && p->r_act) CK(cudaMemcpy(p->r_act + row * L.ldo, action, L.ob * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->r_rew + row, &reward, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->r_done + row, &d, 1, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->r_end + row, &e, 1, cudaMemcpyHostToDevice));
+    // replay_buffer.py:70-75
+    if (next_obs_idx < ts) { p->cur_len[a] = ts + 1; p->ts_cur[a] = 0; }
+    else p->ts_cur[a] = ts + 1;
+    p->cur_len[a] = p->ts_cur[a] > p->cur_len[a] ? p->ts_cur[a] : p->cur_len[a];
+    p->len_dirty = true;
+    return SPP_OK;
+}
+
+int spp_ring_reset(spp_population* p, int a) {
+    if (!p || a < -1 || a >= p->P) return fail(SPP_ERR_ARG, "bad agent");
+    for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i) { p->obs_cur[i] = 0; p->ts_cur[i] = 0; p->cur_len[i] = 0; }
+    p->len_dirty = true;
+    return SPP_OK;
+}
+
+int spp_ring_state(spp_population* p, int a, int64_t out[3]) {
+    if (!p || a < 0 || a >= p->P || !out) return fail(SPP_ERR_ARG, "bad argument");
+    out[0] = p->obs_cur[a]; out[1] = p->ts_cur[a]; out[2] = p->cur_len[a];
+    return SPP_OK;
+}
+
+static RingView ring_view(const spp_population* p) {
+    RingView R{p->r_obs, p->r_oidx, p->r_nidx, p->r_act, p->r_rew, p->r_done, p->r_aacm, p->S, p->L.ob, p->L.ac, p->L.ldo, p->L.lda};
+    return R;
+}
+
+static int push_ring_len(spp_population* p) {
+    if (!p->len_dirty) return SPP_OK;
+    CK(cudaMemcpyAsync(p->r_len, p->cur_len.data(), p->P * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->len_dirty = false;
+    return SPP_OK;
+}
+
+int spp_ring_sample_batch(spp_population* p, int a, const int64_t* idx, int n, float* obs, float* next_obs, float* action,
+                          float* reward, int8_t* done, float* acm_action) {
+    int rc = ring_check(p, a); if (rc) return rc;
+    if (!idx || n < 0 || !obs || !next_obs || !reward || !done || !acm_action) return fail(SPP_ERR_ARG, "null argument");
+    if (n == 0) return SPP_OK;
+    for (int i = 0; i < n; ++i)
+        if (idx[i] < 0 || idx[i] >= p->cur_len[a]) return fail(SPP_ERR_ARG, "sample index outside [0, len(buffer))");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    const size_t fo = (size_t)n * L.ob, fa = (size_t)n * L.ac;
+    const size_t bytes = (3 * fo + fa + n) * sizeof(float) + n + 64;
+    CK(p->d_tmp.ensure(bytes));
+    CK(p->d_idx.ensure((size_t)n * sizeof(int64_t)));
+    float* d = (float*)p->d_tmp.p;
+    GatherOut o{d, d + fo, (action && p->r_act) ? d + 2 * fo : nullptr, d + 3 * fo + fa, (int8_t*)(d + 3 * fo + fa + n), d + 3 * fo};
+    CK(cudaMemcpyAsync(p->d_idx.p, idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
+    CK(launch_ring_gather(ring_view(p), a, (const int64_t*)p->d_idx.p, n, o, p->stream));
+    g_launches++;
+    CK(cudaMemcpyAsync(obs, o.obs, fo * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(next_obs, o.nobs, fo * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    if (action) {
+        if (o.act) CK(cudaMemcpyAsync(action, o.act, fo * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+        else memset(action, 0, fo * sizeof(float));
+    }
+    CK(cudaMemcpyAsync(acm_action, o.aacm, fa * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(reward, o.rew, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(done, o.done, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return SPP_OK;
+}
+
+int spp_ring_fill_synthetic(spp_population* p, uint64_t seed, int64_t n, int episode_len) {
+    if (!p || p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
+    if (n < 1 || episode_len < 1) return fail(SPP_ERR_ARG, "n and episode_len must be positive");
+    const int64_t n_eps = (n + episode_len - 1) / episode_len;
+    if (n + n_eps > p->S) return fail(SPP_ERR_ARG, "n transitions plus one terminal observation per episode must fit buffer_size");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    CK(launch_ring_fill(ring_view(p), p->r_obs, p->r_oidx, p->r_nidx, p->r_act, p->r_rew, p->r_done, p->r_end, p->r_aacm, p->P, n,
+                        episode_len, seed, p->norm, NORM_COUNT * L.ldo, p->sm_count * 8, p->stream));
+    g_launches++;
+    CK(cudaStreamSynchronize(p->stream));
+    for (int a = 0; a < p->P; ++a) { p->obs_cur[a] = (n + n_eps) % p->S; p->ts_cur[a] = n % p->S; p->cur_len[a] = n; }
+    p->len_dirty = true;
+    return SPP_OK;
+}
+
+int spp_ring_gather_bench_device(spp_population* p, int n_batches, uint64_t seed, double* bytes_out, void* stream) {
+    if (!p || p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
+    if (n_batches < 1) return fail(SPP_ERR_ARG, "n_batches must be positive");
+    CK(cudaSetDevice(p->device));
+    int rc = push_ring_len(p); if (rc) return rc;
+    const Layout& L = p->L;
+    const size_t rows = (size_t)p->P * n_batches * L.B;
+    const size_t bytes = rows * ((2 * (size_t)L.ldo + L.lda + 1) * sizeof(float) + 1) + 256;
+    CK(p->d_tmp.ensure(bytes));
+    float* o_obs = (float*)p->d_tmp.p; float* o_nobs = o_obs + rows * L.ldo; float* o_aacm = o_nobs + rows * L.ldo;
+    float* o_rew = o_aacm + rows * L.lda; uint8_t* o_done = (uint8_t*)(o_rew + rows);
+    cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
+    CK(launch_ring_gather_bench(ring_view(p), p->P, n_batches, L.B, p->r_len, seed, o_obs, o_nobs, o_aacm, o_rew, o_done,
+                                p->sm_count * 8, s));
+    g_launches++;
+    // algorithmic bytes: B * ((2 ob + ac + 1) * 4 + 1) read and the same written, plus 2 index words read
+    if (bytes_out) *bytes_out = (double)rows * (2.0 * ((2.0 * L.ob + L.ac + 1) * 4 + 1) + 8.0);
+    return SPP_OK;
+}
+
+// ---- update ----------------------------------------------------------------------------------------
+static void fill_args(spp_population* p, UpdateArgs& a, int G) {
+    memset(&a, 0, sizeof(a));
+    a.L = p->L; a.h = p->h;
+    a.params = p->params; a.mom_m = p->mom_m; a.mom_v = p->mom_v; a.scratch = p->scratch;
+    a.steps = p->steps; a.alpha_state = p->alpha_state; a.norm = p->norm; a.acm_lim = p->acm_lim;
+    a.ring = RingPtrs{p->r_obs, p->r_oidx, p->r_nidx, p->r_act, p->r_rew, p->r_done, p->r_aacm, p->S};
+    a.ring_len = p->r_len;
+    a.G = G; a.population = p->P;
+    a.seq = p->seq++;
+}
+
+static int grid_for(const spp_population* p) { return p->P < p->sm_count ? p->P : p->sm_count; }
+
+int spp_update_host(spp_population* p, int G, const float* obs, const float* next_obs, const float* action,
+                    const float* reward, const int8_t* done, const float* acm_action, const float* eps, uint64_t seed,
+                    float* losses) {
+    if (!p || !obs || !next_obs || !reward || !done || !acm_action) return fail(SPP_ERR_ARG, "spp_update_host: null batch tensor");
+    if (G < 1) return fail(SPP_ERR_ARG, "grad_steps must be positive");
+    if (!p->cfg.acm_critic && !action) return fail(SPP_ERR_ARG, "acm_critic=0 needs the action tensor");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    const size_t rows = (size_t)p->P * G * L.B;
+    cudaStream_t s = p->stream;
+    CK(p->d_obs.ensure(rows * L.ob * 4)); CK(p->d_nobs.ensure(rows * L.ob * 4));
+    CK(p->d_rew.ensure(rows * 4)); CK(p->d_done.ensure(rows)); CK(p->d_aacm.ensure(rows * L.ac * 4));
+    CK(cudaMemcpyAsync(p->d_obs.p, obs, rows * L.ob * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->d_nobs.p, next_obs, rows * L.ob * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->d_rew.p, reward, rows * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->d_done.p, done, rows, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->d_aacm.p, acm_action, rows * L.ac * 4, cudaMemcpyHostToDevice, s));
+    const bool need_act = !p->cfg.acm_critic;
+    if (need_act) {
+        CK(p->d_act.ensure(rows * L.ob * 4));
+        CK(cudaMemcpyAsync(p->d_act.p, action, rows * L.ob * 4, cudaMemcpyHostToDevice, s));
+    }
+    const bool sac = p->cfg.algo == SPP_ALGO_SAC;
+    if (eps && sac) {
+        CK(p->d_eps.ensure(rows * 2 * L.ob * 4));
+        CK(cudaMemcpyAsync(p->d_eps.p, eps, rows * 2 * L.ob * 4, cudaMemcpyHostToDevice, s));
+    }
+    CK(p->d_losses.ensure((size_t)p->P * G * LOSS_COUNT * 4));
+    UpdateArgs a;
+    fill_args(p, a, G);
+    a.batch = BatchPtrs{(const float*)p->d_obs.p, (const float*)p->d_nobs.p, need_act ? (const float*)p->d_act.p : nullptr,
+                        (const float*)p->d_rew.p, (const int8_t*)p->d_done.p, (const float*)p->d_aacm.p};
+    a.eps = (eps && sac) ? (const float*)p->d_eps.p : nullptr;
+    a.seed = seed;
+    a.losses = (float*)p->d_losses.p;
+    CK(launch_update_burst(a, grid_for(p), s));
+    g_launches++;
+    if (losses) CK(cudaMemcpyAsync(losses, p->d_losses.p, (size_t)p->P * G * LOSS_COUNT * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SPP_OK;
+}
+
+int spp_update_ring(spp_population* p, int G, const int64_t* idx, const float* eps, uint64_t seed, float* losses) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    if (p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
+    if (G < 1) return fail(SPP_ERR_ARG, "grad_steps must be positive");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L;
+    const size_t rows = (size_t)p->P * G * L.B;
+    for (int a = 0; a < p->P; ++a)
+        if (p->cur_len[a] < 1) return fail(SPP_ERR_STATE, "replay ring is empty");
+    cudaStream_t s = p->stream;
+    if (idx) {
+        for (int a = 0; a < p->P; ++a)
+            for (size_t k = 0; k < (size_t)G * L.B; ++k) {
+                const int64_t v = idx[(size_t)a * G * L.B + k];
+                if (v < 0 || v >= p->cur_len[a]) return fail(SPP_ERR_ARG, "sample index outside [0, len(buffer))");
+            }
+        CK(p->d_idx.ensure(rows * sizeof(int64_t)));
+        CK(cudaMemcpyAsync(p->d_idx.p, idx, rows * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    }
+    int rc = push_ring_len(p); if (rc) return rc;
+    const bool sac = p->cfg.algo == SPP_ALGO_SAC;
+    if (eps && sac) {
+        CK(p->d_eps.ensure(rows * 2 * L.ob * 4));
+        CK(cudaMemcpyAsync(p->d_eps.p, eps, rows * 2 * L.ob * 4, cudaMemcpyHostToDevice, s));
+    }
+    CK(p->d_losses.ensure((size_t)p->P * G * LOSS_COUNT * 4));
+    UpdateArgs a;
+    fill_args(p, a, G);
+    a.idx = idx ? (const int64_t*)p->d_idx.p : nullptr;
+    a.eps = (eps && sac) ? (const float*)p->d_eps.p : nullptr;
+    a.seed = seed;
+    a.losses = (float*)p->d_losses.p;
+    CK(launch_update_burst(a, grid_for(p), s));
+    g_launches++;
+    if (losses) CK(cudaMemcpyAsync(losses, p->d_losses.p, (size_t)p->P * G * LOSS_COUNT * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SPP_OK;
+}
+
+int spp_update_ring_device(spp_population* p, int G, uint64_t seed, float* losses_dev, void* stream) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    if (p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
+    if (G < 1) return fail(SPP_ERR_ARG, "grad_steps must be positive");
+    for (int a = 0; a < p->P; ++a)
+        if (p->cur_len[a] < 1) return fail(SPP_ERR_STATE, "replay ring is empty");
+    CK(cudaSetDevice(p->device));
+    int rc = push_ring_len(p); if (rc) return rc;
+    UpdateArgs a;
+    fill_args(p, a, G);
+    a.seed = seed;
+    a.losses = losses_dev;
+    CK(launch_update_burst(a, grid_for(p), stream ? (cudaStream_t)stream : p->stream));
+    g_launches++;
+    return SPP_OK;
+}
+
+// ---- introspection ---------------------------------------------------------------------------------
+int spp_debug_scratch(spp_population* p, int a, const char* name, float* host, int cap, int* rows, int* ld) {
+    if (!p || !name || !host || a < 0 || a >= p->P) return fail(SPP_ERR_ARG, "bad argument");
+    const Layout& L = p->L; const ScratchDesc& s = L.s;
+    struct E { const char* n; int off, rows, ld; };
+    const int B = L.B;
+    const E table[] = {
+        {"xo", s.xo, B, L.ldo}, {"xn", s.xn, B, L.ldo}, {"xc", s.xc, B, L.ldc}, {"xcp", s.xcp, B, L.ldc}, {"xm", s.xm, B, L.ldm},
+        {"ha1", s.ha1, B, kHidden}, {"ha2", s.ha2, B, kHidden}, {"ml", s.ml, B, L.ldh}, {"zt", s.zt, B, L.ldo}, {"epsb", s.epsb, B, L.ldo},
+        {"hc1_0", s.hc1[0], B, kHidden}, {"hc1_1", s.hc1[1], B, kHidden}, {"hc2_0", s.hc2[0], B, kHidden}, {"hc2_1", s.hc2[1], B, kHidden},
+        {"dz2_0", s.dz2[0], B, kHidden}, {"dz2_1", s.dz2[1], B, kHidden}, {"dz1_0", s.dz1[0], B, kHidden}, {"dz1_1", s.dz1[1], B, kHidden},
+        {"hm1", s.hm1, B, L.ldm1}, {"hm2", s.hm2, B, L.ldm2}, {"tm3", s.tm3, B, L.lda}, {"dm3", s.dm3, B, L.lda}, {"dm2", s.dm2, B, L.ldm2},
+        {"dm1", s.dm1, B, L.ldm1}, {"dxc", s.dxc, B, L.ldc}, {"dxm", s.dxm, B, L.ldm}, {"dml", s.dml, B, L.ldh},
+        {"dza2", s.dza2, B, kHidden}, {"dza1", s.dza1, B, kHidden}, {"vec", s.vec, 9, L.Bp}, {"gvec", s.gvec, 8, 512},
+    };
+    for (const E& e : table)
+        if (strcmp(e.n, name) == 0) {
+            if (cap < e.rows * e.ld) return fail(SPP_ERR_ARG, "host buffer too small");
+            CK(cudaSetDevice(p->device));
+            CK(cudaStreamSynchronize(p->stream));
+            CK(cudaMemcpy(host, p->scratch + (size_t)a * s.size + e.off, (size_t)e.rows * e.ld * sizeof(float), cudaMemcpyDeviceToHost));
+            if (rows) *rows = e.rows;
+            if (ld) *ld = e.ld;
+            return SPP_OK;
+        }
+    return fail(SPP_ERR_ARG, std::string("unknown scratch buffer ") + name);
+}
+
+}  // extern "C"

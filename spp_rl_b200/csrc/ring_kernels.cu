@@ -1,0 +1,122 @@
+// Replay-ring kernels: two-level minibatch gather, row writes, synthetic prefill.
+// Reference semantics: rltoolkit/buffer/replay_buffer.py:233-261,385-398 (sample), :56-75,133-137,332-333 (adds).
+#include "common.cuh"
+#include "ring_kernels.h"
+
+namespace spp {
+
+// One warp per sampled row: obs = ring_obs[oidx[i]], next_obs = ring_obs[nidx[i]], plus the per-timestep
+// columns.  Rows are padded to 16 B in the ring; outputs are dense (the reference's tensor shapes).
+__global__ void ring_gather_kernel(RingView R, int agent, const int64_t* __restrict__ idx, int n, GatherOut o) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const size_t base = (size_t)agent * R.S;
+    for (int r = w; r < n; r += nw) {
+        const int64_t i = idx[r];
+        const float* po = R.obs + (base + R.oidx[base + i]) * R.ldo;
+        const float* pn = R.obs + (base + R.nidx[base + i]) * R.ldo;
+        for (int j = lane; j < R.ob; j += 32) {
+            o.obs[(size_t)r * R.ob + j] = po[j];
+            o.nobs[(size_t)r * R.ob + j] = pn[j];
+            if (o.act && R.act) o.act[(size_t)r * R.ob + j] = R.act[(base + i) * R.ldo + j];
+        }
+        for (int j = lane; j < R.ac; j += 32) o.aacm[(size_t)r * R.ac + j] = R.aacm[(base + i) * R.lda + j];
+        if (lane == 0) { o.rew[r] = R.rew[base + i]; o.done[r] = (int8_t)R.done[base + i]; }
+    }
+}
+
+// Population-wide gather benchmark: every warp gathers rows for (agent, batch, row) with device-drawn indices
+// and writes dense minibatches [P][nb][B][...] -- the HBM side of sample_batch with nothing else attached.
+__global__ void ring_gather_bench_kernel(RingView R, int P, int nb, int B, const int64_t* __restrict__ len, uint64_t seed,
+                                         float* __restrict__ out_obs, float* __restrict__ out_nobs,
+                                         float* __restrict__ out_aacm, float* __restrict__ out_rew,
+                                         uint8_t* __restrict__ out_done) {
+    const int lane = threadIdx.x & 31;
+    const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t total = (size_t)P * nb * B;
+    const int ldo4 = R.ldo / 4, lda4 = R.lda / 4;
+    for (size_t t = w; t < total; t += nw) {
+        const int agent = (int)(t / ((size_t)nb * B));
+        const uint4 x = Philox::gen(seed, (uint64_t)agent, (uint64_t)(t % ((size_t)nb * B)));
+        const int64_t i = (int64_t)__umul64hi(((uint64_t)x.x << 32) | x.y, (uint64_t)len[agent]);
+        const size_t base = (size_t)agent * R.S;
+        const int32_t oi = R.oidx[base + i], ni = R.nidx[base + i];
+        const float4* po = reinterpret_cast<const float4*>(R.obs + (base + oi) * R.ldo);
+        const float4* pn = reinterpret_cast<const float4*>(R.obs + (base + ni) * R.ldo);
+        float4* qo = reinterpret_cast<float4*>(out_obs + t * R.ldo);
+        float4* qn = reinterpret_cast<float4*>(out_nobs + t * R.ldo);
+        for (int j = lane; j < ldo4; j += 32) { qo[j] = __ldg(po + j); qn[j] = __ldg(pn + j); }
+        if (lane < lda4)
+            reinterpret_cast<float4*>(out_aacm + t * R.lda)[lane] =
+                __ldg(reinterpret_cast<const float4*>(R.aacm + (base + i) * R.lda) + lane);
+        if (lane == 0) { out_rew[t] = R.rew[base + i]; out_done[t] = R.done[base + i]; }
+    }
+}
+
+// Synthetic prefill: n transitions per agent in episodes of T steps (T+1 obs rows per episode).
+__global__ void ring_fill_kernel(RingView R, float* obs, int32_t* oidx, int32_t* nidx, float* act, float* rew,
+                                 uint8_t* done, uint8_t* end, float* aacm, int P, int64_t n, int T, uint64_t seed,
+                                 const float* __restrict__ norm, int norm_stride) {
+    const size_t total = (size_t)P * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int agent = (int)(t / n);
+        const int64_t i = (int64_t)(t % n);
+        const int64_t ep = i / T, st = i % T;
+        const int64_t orow = ep * (T + 1) + st;
+        const size_t base = (size_t)agent * R.S;
+        oidx[base + i] = (int32_t)orow;
+        nidx[base + i] = (int32_t)(orow + 1);
+        const float* doff = norm + (size_t)agent * norm_stride;          // NORM_DOFF
+        const float* dsc = doff + R.ldo;                                 // NORM_DSCALE
+        for (int j = 0; j < R.ob; j += 2) {
+            const uint4 x = Philox::gen(seed, (uint64_t)agent, (uint64_t)i * 128 + j);
+            const float u0 = (float)(x.x >> 8) * (1.0f / 16777216.0f), u1 = (float)(x.y >> 8) * (1.0f / 16777216.0f);
+            const float o0 = doff[j] + (2.f * u0 - 1.f) * dsc[j];
+            obs[(base + orow) * R.ldo + j] = o0;
+            if (st == T - 1 || i == n - 1) obs[(base + orow + 1) * R.ldo + j] = o0 + 0.02f * normal_from_bits(x.z, x.w);
+            if (act) act[(base + i) * R.ldo + j] = 2.f * u1 - 1.f;
+            if (j + 1 < R.ob) {
+                const float o1 = doff[j + 1] + (2.f * u1 - 1.f) * dsc[j + 1];
+                obs[(base + orow) * R.ldo + j + 1] = o1;
+                if (st == T - 1 || i == n - 1) obs[(base + orow + 1) * R.ldo + j + 1] = o1 + 0.02f * normal_from_bits(x.w, x.z);
+                if (act) act[(base + i) * R.ldo + j + 1] = 2.f * u0 - 1.f;
+            }
+        }
+        const uint4 y = Philox::gen(seed ^ 0xABCDEF12345ull, (uint64_t)agent, (uint64_t)i);
+        rew[base + i] = normal_from_bits(y.x, y.y);
+        done[base + i] = (y.z < 4294967u) ? 1 : 0;      // ~1e-3
+        end[base + i] = (st == T - 1) ? 1 : 0;
+        for (int j = 0; j < R.ac; ++j) {
+            const uint4 z = Philox::gen(seed ^ 0x5555AAAA5555ull, (uint64_t)agent, (uint64_t)i * 16 + j);
+            aacm[(base + i) * R.lda + j] = tanhf(normal_from_bits(z.x, z.y));
+        }
+    }
+}
+
+}  // namespace spp
+
+namespace spp {
+
+cudaError_t launch_ring_gather(const RingView& R, int agent, const int64_t* d_idx, int n, const GatherOut& o, cudaStream_t s) {
+    const int blocks = (n * 32 + 255) / 256;
+    ring_gather_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, s>>>(R, agent, d_idx, n, o);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ring_gather_bench(const RingView& R, int P, int nb, int B, const int64_t* d_len, uint64_t seed,
+                                     float* out_obs, float* out_nobs, float* out_aacm, float* out_rew, uint8_t* out_done,
+                                     int grid, cudaStream_t s) {
+    ring_gather_bench_kernel<<<grid, 256, 0, s>>>(R, P, nb, B, d_len, seed, out_obs, out_nobs, out_aacm, out_rew, out_done);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ring_fill(const RingView& R, float* obs, int32_t* oidx, int32_t* nidx, float* act, float* rew,
+                             uint8_t* done, uint8_t* end, float* aacm, int P, int64_t n, int T, uint64_t seed,
+                             const float* norm, int norm_stride, int grid, cudaStream_t s) {
+    ring_fill_kernel<<<grid, 256, 0, s>>>(R, obs, oidx, nidx, act, rew, done, end, aacm, P, n, T, seed, norm, norm_stride);
+    return cudaGetLastError();
+}
+
+}  // namespace spp

@@ -1,0 +1,306 @@
+// Fused off-policy SPP update burst kernel (SAC_AcM / DDPG_AcM), sm_100a.  See update_kernel.cuh.
+#include "update_kernel.cuh"
+
+namespace spp {
+
+// loss slots in Smem::small
+constexpr int kLossBase = 8;
+
+// ---- actor hidden layers + heads.  X: [B x ldo]
+template <int ALGO>
+__device__ inline void actor_forward(const Ctx& c, const float* X, int actor_net) {
+    const Layout& L = c.a.L;
+    float* S = c.S;
+    const float* net = c.net(actor_net);
+    linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldo, L.ldo, net, L.actor.L[0], S + L.s.ha1, kHidden, L.B);
+    __syncthreads();
+    linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.ha1, kHidden, kHidden, net, L.actor.L[1], S + L.s.ha2, kHidden, L.B);
+    __syncthreads();
+    if (ALGO == ALGO_SAC)
+        linear_fwd<NarrowTile, ACT_NONE, false>(c, S + L.s.ha2, kHidden, kHidden, net, L.actor.L[2], S + L.s.ml, L.ldh, L.B);
+    else   // tanh(fc3) * lim ; tanh kept in zt
+        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.ha2, kHidden, kHidden, net, L.actor.L[2], S + L.s.ml, L.ldh, L.B,
+                                               c.normv(NORM_LIM), S + L.s.zt, L.ldo);
+    __syncthreads();
+}
+
+// ---- backward through the actor heads (warp per row); also custom (distance) loss and the SAC temperature step.
+template <int ALGO>
+__device__ inline void stage_actor_head_bwd(const Ctx& c) {
+    const Layout& L = c.a.L;
+    const Hyper& h = c.a.h;
+    float* S = c.S;
+    const int B = L.B, ob = L.ob, ldo = L.ldo, lane = lane_id(), warp = warp_id();
+    const float* ml = S + L.s.ml; const float* zt = S + L.s.zt; const float* epsb = S + L.s.epsb;
+    const float* xm = S + L.s.xm; const float* xn = S + L.s.xn;
+    const float* din = L.acm_critic ? S + L.s.dxm : S + L.s.dxc;
+    const int ldin = L.acm_critic ? L.ldm : L.ldc;
+    float* dml = S + L.s.dml;
+    const float* lim = c.normv(NORM_LIM); const float* dsc = c.normv(NORM_DSCALE);
+    const float* nsub = c.normv(NORM_NSUB); const float* ndiv = c.normv(NORM_NDIV);
+    const float* lp = c.vec(VEC_LOGP);
+    const float invB = 1.0f / (float)B;
+    const float g = __fmul_rn(c.sm.alpha, invB);
+    const float norm_d = (float)(2.0 / ((double)B * (double)ob));
+    float cb[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float dist_sum = 0.f, term_sum = 0.f, aterm_sum = 0.f;
+    for (int r = warp; r < B; r += kWarps) {
+        int k = 0;
+        for (int j = lane; j < ob; j += 32, ++k) {
+            const float th = zt[r * ldo + j];
+            const float zd = xm[r * L.ldm + ldo + j];
+            float dz = 0.f, dzd = 0.f;
+            if (h.custom_loss != 0.f) {
+                float pred, target;
+                if (h.norm_closs) {
+                    target = __fdiv_rn(__fsub_rn(xn[r * ldo + j], nsub[j]), ndiv[j]);
+                    if (h.norm_clamp) target = fminf(fmaxf(target, -10.f), 10.f);
+                    pred = __fmul_rn(th, lim[j]);
+                } else {
+                    target = xn[r * ldo + j];
+                    pred = zd;
+                }
+                const float diff = __fsub_rn(pred, target);
+                dist_sum = fmaf(diff, diff, dist_sum);
+                const float gd = __fmul_rn(__fmul_rn(norm_d, diff), h.custom_loss);
+                if (h.norm_closs) dz = gd; else dzd = gd;
+            }
+            dzd = __fadd_rn(dzd, din[r * ldin + ldo + j]);
+            dz = __fadd_rn(dz, __fmul_rn(dzd, dsc[j]));
+            if (ALGO == ALGO_SAC) {
+                const float mu = ml[r * L.ldh + j];
+                const float lsr = ml[r * L.ldh + ob + j];
+                const float ls = fminf(fmaxf(lsr, -20.f), 2.f);
+                const float sd = expf(ls);
+                const float e = epsb[r * ldo + j];
+                const float u = __fadd_rn(mu, __fmul_rn(e, sd));
+                const float var = __fmul_rn(sd, sd);
+                const float d = __fsub_rn(u, mu);
+                const float two_var = __fmul_rn(2.f, var);
+                const float ds = __fdiv_rn(-g, two_var);
+                const float dd = __fmul_rn(__fmul_rn(ds, 2.f), d);
+                const float d2var = __fdiv_rn(__fmul_rn(g, __fmul_rn(d, d)), __fmul_rn(two_var, two_var));
+                const float dvar = __fmul_rn(2.f, d2var);
+                float dstd = __fadd_rn(__fmul_rn(__fmul_rn(dvar, 2.f), sd), __fdiv_rn(-g, sd));
+                float du = __fmul_rn(__fmul_rn(dz, lim[j]), __fsub_rn(1.f, __fmul_rn(th, th)));
+                const float sg = 1.f / (1.f + expf(2.f * u));      // sigmoid(-2u)
+                du = __fadd_rn(du, __fmul_rn(__fmul_rn(-g, 2.f), __fadd_rn(-1.f, __fmul_rn(2.f, sg))));
+                du = __fadd_rn(du, dd);
+                const float dmu = __fadd_rn(-dd, du);
+                dstd = __fadd_rn(dstd, __fmul_rn(du, e));
+                const float dls = __fmul_rn(dstd, sd);
+                const float dlsr = (lsr >= -20.f && lsr <= 2.f) ? dls : 0.f;
+                dml[r * L.ldh + j] = dmu;
+                dml[r * L.ldh + ob + j] = dlsr;
+                if (k < 4) { cb[0][k] += dmu; cb[1][k] += dlsr; }
+            } else {
+                const float d3 = __fmul_rn(__fmul_rn(dz, lim[j]), __fsub_rn(1.f, __fmul_rn(th, th)));
+                dml[r * L.ldh + j] = d3;
+                if (k < 4) cb[0][k] += d3;
+            }
+        }
+        if (ALGO == ALGO_SAC && lane == 0) {
+            const float term = __fsub_rn(-lp[r], h.target_entropy);
+            term_sum += __fmul_rn(invB, term);
+            aterm_sum += term;
+        }
+    }
+    // head-bias gradients: cross-warp reduce -> gvec(GV_MISC)[0..heads)
+    __syncthreads();
+    {
+        int k = 0;
+        for (int j = lane; j < ob; j += 32, ++k) {
+            c.sm.red[warp * 512 + j] = cb[0][k];
+            if (ALGO == ALGO_SAC) c.sm.red[warp * 512 + ob + j] = cb[1][k];
+        }
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < L.heads; n += kThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += c.sm.red[w * 512 + n];
+        c.gvec(GV_MISC)[n] = s;
+    }
+    const float dist_tot = block_sum(dist_sum, c.sm.small);
+    __syncthreads();
+    const float term_tot = (ALGO == ALGO_SAC) ? block_sum(term_sum, c.sm.small) : 0.f;
+    __syncthreads();
+    const float aterm_tot = (ALGO == ALGO_SAC) ? block_sum(aterm_sum, c.sm.small) : 0.f;
+    if (threadIdx.x == 0) {
+        float* ls = c.sm.small + kLossBase;
+        const float dist = dist_tot / ((float)B * (float)ob);
+        ls[LOSS_DIST] = dist;
+        ls[LOSS_ACTOR] = (h.custom_loss != 0.f) ? __fadd_rn(ls[LOSS_PI], __fmul_rn(h.custom_loss, dist)) : ls[LOSS_PI];
+        if (ALGO == ALGO_SAC) {
+            // temperature: SAC.compute_alpha_loss (rltoolkit/algorithms/sac/sac.py:201-216) + Adam on the fp64 log_alpha
+            double* as = c.a.alpha_state + (size_t)c.agent * 4;
+            const double la = as[0];
+            const double ea = exp(la);
+            ls[LOSS_ALPHA] = __fmul_rn((float)ea, aterm_tot) * invB;
+            const double gla = (double)term_tot * ea;
+            const int t = (int)as[3] + 1;
+            double m = as[1], v = as[2];
+            m = m + 0.09999999999999998 * (gla - m);
+            v = v * 0.999 + 0.0010000000000000009 * gla * gla;
+            const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+            const double denom = sqrt(v) / sqrt(bc2) + 1e-8;
+            const double la_new = la + (-(h.alpha_lr / bc1) * m) / denom;
+            as[0] = la_new; as[1] = m; as[2] = v; as[3] = (double)t;
+            ls[LOSS_ALPHA_VALUE] = (float)exp(la_new);
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int ALGO>
+__device__ void update_step(const Ctx& c, int g) {
+    const Layout& L = c.a.L;
+    const Hyper& h = c.a.h;
+    float* S = c.S;
+    const int B = L.B;
+    constexpr int ncrit = (ALGO == ALGO_SAC) ? 2 : 1;
+    const int crit[2] = {NET_CRITIC_1, NET_CRITIC_2};
+    const int tcrit[2] = {NET_CRITIC_1_TARG, NET_CRITIC_2_TARG};
+    float* ls = c.sm.small + kLossBase;
+
+    // ---- bookkeeping
+    if (threadIdx.x == 0) {
+        if (ALGO == ALGO_SAC) c.sm.alpha = (float)exp(c.a.alpha_state[(size_t)c.agent * 4]);
+        adam_begin(c, 0, h.actor_lr);
+        for (int i = 0; i < ncrit; ++i) adam_begin(c, 1 + i, h.critic_lr);
+        for (int k = 0; k < LOSS_COUNT; ++k) ls[k] = 0.f;
+    }
+    for (int i = threadIdx.x; i < 4 * 512; i += kThreads) __stcg(c.gvec(0) + i, 0.f);
+    stage_gather(c, g);
+    __syncthreads();
+
+    // ---- Phase A: Q target (sac_acm.py:43-56 / ddpg_acm.py:113-121)
+    actor_forward<ALGO>(c, S + L.s.xn, ALGO == ALGO_SAC ? NET_ACTOR : NET_ACTOR_TARG);
+    if (ALGO == ALGO_SAC) stage_sample(c, g, 0); else stage_ddpg_post(c, 0);
+    __syncthreads();
+    if (L.acm_critic) acm_forward(c);
+    critics_hidden(c, S + L.s.xcp, tcrit, ncrit);
+    stage_qtarget(c, tcrit, ncrit);
+    __syncthreads();
+
+    // ---- Phase B: critic step(s) (sac_acm.py:117-131 / ddpg_acm.py:175-182), Polyak fused (sac.py:186-199)
+    critics_hidden(c, S + L.s.xc, crit, ncrit);
+    stage_critic_head_bwd<0>(c, crit, tcrit, ncrit, ls + LOSS_CRITIC_1);
+    __syncthreads();
+    for (int i = 0; i < ncrit; ++i) {   // dz1 = (dz2 W2) * relu'(hc1); column sums -> d b1
+        const LayerDesc& l = L.critic.L[1];
+        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, c.gvec(GV_CB1_0 + i), 1.f};
+        gemm<BigTile, true, false>(S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+    }
+    __syncthreads();
+    for (int i = 0; i < ncrit; ++i) {
+        float* net = c.net(crit[i]); float* nm = c.net_m(crit[i]); float* nv = c.net_v(crit[i]); float* tn = c.net(tcrit[i]);
+        const AdamScalars as = c.sm.adam[1 + i];
+        {   // fc2.weight: dW2[m,n] = sum_b dz2[b,m] hc1[b,n]
+            const LayerDesc& l = L.critic.L[1];
+            EpiAdam<false, true> epi{net + l.off_w, nm + l.off_w, nv + l.off_w, tn + l.off_w, l.ld, as, h.tau, h.one_minus_tau};
+            gemm<BigTile, false, false>(S + L.s.dz2[i], kHidden, S + L.s.hc1[i], kHidden, kHidden, kHidden, B, c.sm.gemm, epi);
+        }
+        {   // fc1.weight: dW1[m,n] = sum_b dz1[b,m] xc[b,n]
+            const LayerDesc& l = L.critic.L[0];
+            EpiAdam<false, true> epi{net + l.off_w, nm + l.off_w, nv + l.off_w, tn + l.off_w, l.ld, as, h.tau, h.one_minus_tau};
+            gemm<NarrowTile, false, false>(S + L.s.dz1[i], kHidden, S + L.s.xc, L.ldc, kHidden, L.ldc, B, c.sm.gemm, epi);
+            adam_vector(net + l.off_b, nm + l.off_b, nv + l.off_b, tn + l.off_b, c.gvec(GV_CB1_0 + i), kHidden, as, h.tau,
+                        h.one_minus_tau, true);
+        }
+    }
+    __syncthreads();
+
+    // ---- Phase C: policy step against the updated critic(s) (sac_acm.py:133-145,60-87 / ddpg_acm.py:125-145,187-192)
+    actor_forward<ALGO>(c, S + L.s.xo, NET_ACTOR);
+    if (ALGO == ALGO_SAC) stage_sample(c, g, 1); else stage_ddpg_post(c, 1);
+    __syncthreads();
+    if (L.acm_critic) acm_forward(c);
+    critics_hidden(c, S + L.s.xcp, crit, ncrit);
+    stage_critic_head_bwd<1>(c, crit, tcrit, ncrit, ls + LOSS_PI);
+    __syncthreads();
+    for (int i = 0; i < ncrit; ++i) {
+        const LayerDesc& l = L.critic.L[1];
+        EpiMaskStore<MASK_RELU, false, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, nullptr, 1.f};
+        gemm<BigTile, true, false>(S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+    }
+    __syncthreads();
+    {   // dxc = sum_i dz1[i] W1_i     [B x ldc]
+        const LayerDesc& l = L.critic.L[0];
+        EpiMaskStore<MASK_NONE, false, false> e0{S + L.s.dxc, L.ldc, nullptr, 0, nullptr, 1.f};
+        gemm<NarrowTile, true, false>(S + L.s.dz1[0], kHidden, c.net(crit[0]) + l.off_w, l.ld, B, L.ldc, kHidden, c.sm.gemm, e0);
+        if (ncrit == 2) {
+            EpiMaskStore<MASK_NONE, false, true> e1{S + L.s.dxc, L.ldc, nullptr, 0, nullptr, 1.f};
+            gemm<NarrowTile, true, false>(S + L.s.dz1[1], kHidden, c.net(crit[1]) + l.off_w, l.ld, B, L.ldc, kHidden, c.sm.gemm, e1);
+        }
+    }
+    __syncthreads();
+    if (L.acm_critic) acm_backward_dx(c);
+    stage_actor_head_bwd<ALGO>(c);
+    {   // dza2 = (dml Wheads) * relu'(ha2); column sums -> d b2
+        const LayerDesc& l = L.actor.L[2];
+        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza2, kHidden, S + L.s.ha2, kHidden, c.gvec(GV_AB2), 1.f};
+        gemm<BigTile, true, false>(S + L.s.dml, L.ldh, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, L.heads, c.sm.gemm, epi);
+    }
+    __syncthreads();
+    {   // dza1 = (dza2 W2) * relu'(ha1); column sums -> d b1
+        const LayerDesc& l = L.actor.L[1];
+        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza1, kHidden, S + L.s.ha1, kHidden, c.gvec(GV_AB1), 1.f};
+        gemm<BigTile, true, false>(S + L.s.dza2, kHidden, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+    }
+    __syncthreads();
+    {
+        float* net = c.net(NET_ACTOR); float* nm = c.net_m(NET_ACTOR); float* nv = c.net_v(NET_ACTOR);
+        float* tn = (ALGO == ALGO_DDPG) ? c.net(NET_ACTOR_TARG) : nullptr;
+        const AdamScalars as = c.sm.adam[0];
+        constexpr bool PK = (ALGO == ALGO_DDPG);     // DDPG.update_target_nets blends the actor too (ddpg.py:273-284)
+        const LayerDesc& l2 = L.actor.L[2]; const LayerDesc& l1 = L.actor.L[1]; const LayerDesc& l0 = L.actor.L[0];
+        {   // heads (transposed tile): dWh[n, m] = sum_b ha2[b, m] dml[b, n]
+            EpiAdam<true, PK> epi{net + l2.off_w, nm + l2.off_w, nv + l2.off_w, PK ? tn + l2.off_w : nullptr, l2.ld, as, h.tau, h.one_minus_tau};
+            gemm<NarrowTile, false, false>(S + L.s.ha2, kHidden, S + L.s.dml, L.ldh, kHidden, L.heads, B, c.sm.gemm, epi);
+        }
+        {
+            EpiAdam<false, PK> epi{net + l1.off_w, nm + l1.off_w, nv + l1.off_w, PK ? tn + l1.off_w : nullptr, l1.ld, as, h.tau, h.one_minus_tau};
+            gemm<BigTile, false, false>(S + L.s.dza2, kHidden, S + L.s.ha1, kHidden, kHidden, kHidden, B, c.sm.gemm, epi);
+        }
+        {
+            EpiAdam<false, PK> epi{net + l0.off_w, nm + l0.off_w, nv + l0.off_w, PK ? tn + l0.off_w : nullptr, l0.ld, as, h.tau, h.one_minus_tau};
+            gemm<NarrowTile, false, false>(S + L.s.dza1, kHidden, S + L.s.xo, L.ldo, kHidden, L.ldo, B, c.sm.gemm, epi);
+        }
+        adam_vector(net + l2.off_b, nm + l2.off_b, nv + l2.off_b, PK ? tn + l2.off_b : nullptr, c.gvec(GV_MISC), L.heads, as, h.tau, h.one_minus_tau, true);
+        adam_vector(net + l1.off_b, nm + l1.off_b, nv + l1.off_b, PK ? tn + l1.off_b : nullptr, c.gvec(GV_AB2), kHidden, as, h.tau, h.one_minus_tau, true);
+        adam_vector(net + l0.off_b, nm + l0.off_b, nv + l0.off_b, PK ? tn + l0.off_b : nullptr, c.gvec(GV_AB1), kHidden, as, h.tau, h.one_minus_tau, true);
+    }
+    __syncthreads();
+    if (threadIdx.x < LOSS_COUNT && c.a.losses)
+        c.a.losses[((size_t)c.agent * c.a.G + g) * LOSS_COUNT + threadIdx.x] = ls[threadIdx.x];
+    __syncthreads();
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(kThreads, 1) update_burst_kernel(const __grid_constant__ UpdateArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
+        Ctx c(a, agent, sm);
+        for (int g = 0; g < a.G; ++g) update_step<ALGO>(c, g);
+    }
+}
+
+cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream) {
+    const size_t smem = sizeof(Smem);
+    cudaError_t e;
+    if (a.L.algo == ALGO_SAC) {
+        e = cudaFuncSetAttribute(update_burst_kernel<ALGO_SAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        update_burst_kernel<ALGO_SAC><<<grid, kThreads, smem, stream>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(update_burst_kernel<ALGO_DDPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        update_burst_kernel<ALGO_DDPG><<<grid, kThreads, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace spp

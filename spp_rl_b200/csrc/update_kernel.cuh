@@ -1,0 +1,469 @@
+// Fused SPP-SAC / SPP-DDPG update burst: one persistent CTA per agent runs `G` consecutive
+// update steps (replay gather -> Q target -> critic step(s) -> policy step -> Polyak -> temperature)
+// without returning to the host.  Reference semantics: SAC_AcM.update
+// (rltoolkit/acm/off_policy/sac_acm.py:89-162), DDPG_AcM.update
+// (rltoolkit/acm/off_policy/ddpg_acm.py:147-201) driven by DDPG.make_update
+// (rltoolkit/algorithms/ddpg/ddpg.py:231-237) with BufferAcMOffPolicy.sample_batch
+// (rltoolkit/buffer/replay_buffer.py:385-398,233-261).
+#pragma once
+#include "gemm_tile.cuh"
+#include "layout.h"
+
+namespace spp {
+
+struct RingPtrs {
+    const float* obs;        // [P][S][ldo]
+    const int32_t* oidx;     // [P][S]
+    const int32_t* nidx;     // [P][S]
+    const float* act;        // [P][S][ldo]   state-target actions (may be null when acm_critic)
+    const float* rew;        // [P][S]
+    const uint8_t* done;     // [P][S]
+    const float* aacm;       // [P][S][lda]
+    int64_t S;
+};
+
+// explicit minibatches (host-facing update(obs, next_obs, action, reward, done, acm_action))
+struct BatchPtrs {
+    const float* obs;        // [P][G][B][ob]  dense
+    const float* nobs;
+    const float* act;        // [P][G][B][ob]  (may be null when acm_critic)
+    const float* rew;        // [P][G][B]
+    const int8_t* done;      // [P][G][B]
+    const float* aacm;       // [P][G][B][ac]
+};
+
+struct Hyper {
+    float gamma, tau, one_minus_tau, custom_loss, target_entropy;
+    double actor_lr, critic_lr, alpha_lr;
+    int norm_closs;          // custom loss in normalised space (MSE(z, normalize(next_obs)))
+    int norm_clamp;          // mean-std normalize clamps to +-10 (utils.standardize_and_clip)
+};
+
+// per-agent normalisation vectors, each ldo floats: [P][NORM_COUNT][ldo]
+enum { NORM_DOFF = 0, NORM_DSCALE = 1, NORM_NSUB = 2, NORM_NDIV = 3, NORM_LIM = 4, NORM_COUNT = 5 };
+
+struct UpdateArgs {
+    Layout L;
+    Hyper h;
+    float* params;           // [P][params_size]
+    float* mom_m;            // [P][train_size]
+    float* mom_v;            // [P][train_size]
+    float* scratch;          // [P][s.size]
+    int* steps;              // [P][4]   Adam step counters: actor, critic_1, critic_2, acm
+    double* alpha_state;     // [P][4]   log_alpha, m, v, step
+    const float* norm;       // [P][NORM_COUNT][ldo]
+    const float* acm_lim;    // [lda]    env action limit (AcM) -- BasicAcM uses its own t1
+    RingPtrs ring;
+    BatchPtrs batch;
+    const int64_t* idx;      // [P][G][B] ring indices, or null
+    const int64_t* ring_len; // [P] current_len, used when idx == null (device sampler)
+    const float* eps;        // [P][G][2][B][ob] injected N(0,1) draws (target pass, policy pass), or null
+    uint64_t seed;           // Philox key when eps / idx are generated on device
+    uint64_t seq;            // burst sequence number (Philox stream)
+    float* losses;           // [P][G][8] or null
+    int G;
+    int population;
+};
+
+enum { LOSS_CRITIC_1 = 0, LOSS_CRITIC_2 = 1, LOSS_ACTOR = 2, LOSS_PI = 3, LOSS_DIST = 4, LOSS_ALPHA = 5, LOSS_ALPHA_VALUE = 6, LOSS_COUNT = 8 };
+
+struct Smem {
+    float gemm[kGemmSmemFloats];
+    float red[8 * 2 * kHidden];       // cross-warp column partials (8 warps x 512)
+    float vecs[4 * kHidden];          // reduced vectors
+    float small[64];
+    AdamScalars adam[4];
+    float alpha;                      // temperature as fp32 (Python float rounded when it meets fp32 tensors)
+};
+
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+    const UpdateArgs& a;
+    int agent;
+    float* P;      // params of this agent
+    float* Mm;     // moments
+    float* Mv;
+    float* S;      // scratch
+    Smem& sm;
+    __device__ Ctx(const UpdateArgs& a_, int agent_, Smem& sm_) : a(a_), agent(agent_), sm(sm_) {
+        P = a.params + (size_t)agent * a.L.params_size;
+        Mm = a.mom_m + (size_t)agent * a.L.train_size;
+        Mv = a.mom_v + (size_t)agent * a.L.train_size;
+        S = a.scratch + (size_t)agent * a.L.s.size;
+    }
+    __device__ float* net(int id) const { return P + a.L.net_off[id]; }
+    __device__ float* net_m(int id) const { return Mm + a.L.net_off[id]; }
+    __device__ float* net_v(int id) const { return Mv + a.L.net_off[id]; }
+    __device__ const float* normv(int which) const {
+        return a.norm + ((size_t)agent * NORM_COUNT + which) * a.L.ldo;
+    }
+    __device__ float* vec(int which) const { return S + a.L.s.vec + which * a.L.Bp; }
+    __device__ float* gvec(int which) const { return S + a.L.s.gvec + which * 512; }
+};
+
+// ---- Adam bookkeeping: bump the step of optimiser `opt` and publish its scalars (thread 0 only)
+__device__ inline void adam_begin(const Ctx& c, int opt, double lr) {
+    int* st = c.a.steps + (size_t)c.agent * 4 + opt;
+    const int t = *st + 1;
+    *st = t;
+    const double bc1 = 1.0 - pow(0.9, (double)t);
+    const double bc2 = 1.0 - pow(0.999, (double)t);
+    c.sm.adam[opt].lr_over_bc1 = (float)(lr / bc1);
+    c.sm.adam[opt].bc2_sqrt = (float)sqrt(bc2);
+}
+
+// Adam (+ optional Polyak) on a contiguous vector with gradient in shared or global memory.
+__device__ inline void adam_vector(float* W, float* Mo, float* Vo, float* T, const float* grad, int n,
+                                   const AdamScalars& s, float tau, float omt, bool grad_global) {
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+        const float g = grad_global ? __ldcg(grad + i) : grad[i];
+        float m = Mo[i], v = Vo[i];
+        const float wn = adam_element(W[i], g, m, v, s);
+        W[i] = wn; Mo[i] = m; Vo[i] = v;
+        if (T) T[i] = __fadd_rn(__fmul_rn(T[i], omt), __fmul_rn(tau, wn));
+    }
+}
+
+// ---- forward of one Linear through the tile GEMM
+template <class Cfg, int ACT, bool SCALE>
+__device__ inline void linear_fwd(const Ctx& c, const float* X, int ldx, int K, const float* net, const LayerDesc& l,
+                                  float* C, int ldc, int B, const float* scale = nullptr, float* C2 = nullptr,
+                                  int ldc2 = 0) {
+    EpiBiasAct<ACT, SCALE> epi{C, ldc, net + l.off_b, scale, C2, ldc2};
+    gemm<Cfg, true, true>(X, ldx, net + l.off_w, l.ld, B, l.rows, K, c.sm.gemm, epi);
+}
+
+// ---- replay gather (warp per row): fills xo, xn, xc=[obs|action], r, notdone*gamma
+__device__ inline void stage_gather(const Ctx& c, int g) {
+    const Layout& L = c.a.L;
+    const int B = L.B, ob = L.ob, ldo = L.ldo;
+    float* xo = c.S + L.s.xo; float* xn = c.S + L.s.xn; float* xc = c.S + L.s.xc;
+    float* vr = c.vec(VEC_R); float* vnd = c.vec(VEC_ND);
+    const int lane = lane_id();
+    const bool from_ring = (c.a.batch.obs == nullptr);
+    for (int r = warp_id(); r < B; r += kWarps) {
+        const float *po, *pn, *pa; float rew; int done;
+        if (from_ring) {
+            const RingPtrs& R = c.a.ring;
+            int64_t i;
+            if (c.a.idx) {
+                i = c.a.idx[((size_t)c.agent * c.a.G + g) * B + r];
+            } else {   // device sampler: uniform over [0, current_len)
+                const uint4 x = Philox::gen(c.a.seed ^ 0x9E3779B97F4A7C15ull, ((uint64_t)c.agent << 32) | (uint32_t)g,
+                                            (c.a.seq << 20) | (uint32_t)r);
+                i = (int64_t)__umul64hi(((uint64_t)x.x << 32) | x.y, (uint64_t)c.a.ring_len[c.agent]);
+            }
+            const size_t base = (size_t)c.agent * R.S;
+            po = R.obs + (base + R.oidx[base + i]) * ldo;
+            pn = R.obs + (base + R.nidx[base + i]) * ldo;
+            pa = L.acm_critic ? R.aacm + (base + i) * L.lda : R.act + (base + i) * ldo;
+            rew = R.rew[base + i];
+            done = R.done[base + i];
+        } else {
+            const BatchPtrs& Bt = c.a.batch;
+            const size_t row = ((size_t)c.agent * c.a.G + g) * B + r;
+            po = Bt.obs + row * ob; pn = Bt.nobs + row * ob;
+            pa = L.acm_critic ? Bt.aacm + row * L.ac : Bt.act + row * ob;
+            rew = Bt.rew[row];
+            done = Bt.done[row];
+        }
+        for (int j = lane; j < ob; j += 32) {
+            const float o = po[j];
+            xo[r * ldo + j] = o;
+            xn[r * ldo + j] = pn[j];
+            xc[r * L.ldc + j] = o;
+        }
+        for (int j = lane; j < L.act_dim; j += 32) xc[r * L.ldc + ldo + j] = pa[j];
+        if (lane == 0) {
+            vr[r] = rew;
+            vnd[r] = __fmul_rn(c.a.h.gamma, (float)(1 - done));   // gamma * (1 - done)
+        }
+    }
+}
+
+// ---- SAC: sample from the actor heads (warp per row).  pass 0: target pass on next_obs, pass 1: policy pass on obs
+__device__ inline void stage_sample(const Ctx& c, int g, int pass) {
+    const Layout& L = c.a.L;
+    const int B = L.B, ob = L.ob, ldo = L.ldo, lane = lane_id();
+    const float* x = c.S + (pass == 0 ? L.s.xn : L.s.xo);
+    const float* ml = c.S + L.s.ml;
+    float* xm = c.S + L.s.xm; float* xcp = c.S + L.s.xcp;
+    float* zt = c.S + L.s.zt; float* epsb = c.S + L.s.epsb;
+    float* logp_out = c.vec(pass == 0 ? VEC_LOGPN : VEC_LOGP);
+    const float* lim = c.normv(NORM_LIM); const float* doff = c.normv(NORM_DOFF); const float* dsc = c.normv(NORM_DSCALE);
+    const float kLogSqrt2Pi = 0.918938533204672741780329736406f, kLog2 = 0.693147180559945309417232121458f;
+    for (int r = warp_id(); r < B; r += kWarps) {
+        float lp = 0.f, corr = 0.f;
+        for (int j = lane; j < ob; j += 32) {
+            const float mu = ml[r * L.ldh + j];
+            const float ls = fminf(fmaxf(ml[r * L.ldh + ob + j], -20.f), 2.f);
+            const float sd = expf(ls);
+            float e;
+            if (c.a.eps) {
+                e = c.a.eps[((((size_t)c.agent * c.a.G + g) * 2 + pass) * B + r) * ob + j];
+            } else {
+                const uint4 w = Philox::gen(c.a.seed, ((uint64_t)c.agent << 32) | ((uint32_t)g * 2 + pass),
+                                            (c.a.seq << 24) | ((uint32_t)r * ob + j));
+                e = normal_from_bits(w.x, w.y);
+            }
+            const float u = __fadd_rn(mu, __fmul_rn(e, sd));
+            const float var = __fmul_rn(sd, sd);
+            const float d = __fsub_rn(u, mu);
+            lp += __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, var)), logf(sd)), kLogSqrt2Pi);
+            corr += __fsub_rn(__fsub_rn(kLog2, u), softplus_t(-2.f * u));
+            const float th = tanhf(u);
+            const float z = __fmul_rn(th, lim[j]);
+            const float zd = __fadd_rn(doff[j], __fmul_rn(z, dsc[j]));
+            const float xv = x[r * ldo + j];
+            xcp[r * L.ldc + j] = xv;
+            if (L.acm_critic) { xm[r * L.ldm + j] = xv; xm[r * L.ldm + ldo + j] = zd; }
+            else xcp[r * L.ldc + ldo + j] = zd;
+            if (pass == 1) { zt[r * ldo + j] = th; epsb[r * ldo + j] = e; if (!L.acm_critic) xm[r * L.ldm + ldo + j] = zd; }
+        }
+        lp = warp_sum(lp); corr = warp_sum(corr);
+        if (lane == 0) logp_out[r] = __fsub_rn(lp, __fmul_rn(2.f, corr));
+    }
+}
+
+// ---- DDPG: deterministic head post-processing (heads GEMM already applied tanh; zt holds tanh, ml holds tanh*lim)
+__device__ inline void stage_ddpg_post(const Ctx& c, int pass) {
+    const Layout& L = c.a.L;
+    const int B = L.B, ob = L.ob, ldo = L.ldo, lane = lane_id();
+    const float* x = c.S + (pass == 0 ? L.s.xn : L.s.xo);
+    const float* ml = c.S + L.s.ml;
+    float* xm = c.S + L.s.xm; float* xcp = c.S + L.s.xcp;
+    const float* doff = c.normv(NORM_DOFF); const float* dsc = c.normv(NORM_DSCALE);
+    for (int r = warp_id(); r < B; r += kWarps)
+        for (int j = lane; j < ob; j += 32) {
+            const float zd = __fadd_rn(doff[j], __fmul_rn(ml[r * L.ldh + j], dsc[j]));
+            const float xv = x[r * ldo + j];
+            xcp[r * L.ldc + j] = xv;
+            if (L.acm_critic) { xm[r * L.ldm + j] = xv; xm[r * L.ldm + ldo + j] = zd; }
+            else { xcp[r * L.ldc + ldo + j] = zd; if (pass == 1) xm[r * L.ldm + ldo + j] = zd; }
+        }
+}
+
+// ---- ACM forward (AcM: tanh-tanh-tanh*lim; BasicAcM: skip connection and learnable gains).  Writes the action
+//      into the action block of xcp and keeps tanh(fc3) in tm3 for the backward.
+__device__ inline void acm_forward(const Ctx& c) {
+    const Layout& L = c.a.L;
+    const float* acm = c.net(NET_ACM);
+    float* S = c.S;
+    const int B = L.B;
+    if (L.acm_kind == ACM_MLP) {
+        linear_fwd<NarrowTile, ACT_TANH, false>(c, S + L.s.xm, L.ldm, L.ldm, acm, L.acm.L[0], S + L.s.hm1, L.ldm1, B);
+        __syncthreads();
+        linear_fwd<NarrowTile, ACT_TANH, false>(c, S + L.s.hm1, L.ldm1, L.hm1, acm, L.acm.L[1], S + L.s.hm2, L.ldm2, B);
+        __syncthreads();
+        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.hm2, acm, L.acm.L[2], S + L.s.xcp + L.ldo, L.ldc, B,
+                                               c.a.acm_lim, S + L.s.tm3, L.lda);
+        __syncthreads();
+    } else {
+        // h = tanh(fc1 x); s = fc21 x
+        linear_fwd<NarrowTile, ACT_TANH, false>(c, S + L.s.xm, L.ldm, L.ldm, acm, L.acm.L[0], S + L.s.hm1, L.ldm1, B);
+        linear_fwd<NarrowTile, ACT_NONE, false>(c, S + L.s.xm, L.ldm, L.ldm, acm, L.acm.L[3], S + L.s.hms, L.ldm2, B);
+        __syncthreads();
+        // h1 = tanh(fc2 h + t * s)
+        {
+            const LayerDesc& l = L.acm.L[1];
+            EpiBiasAddAct epi{S + L.s.hm2, L.ldm2, acm + l.off_b, S + L.s.hms, L.ldm2, acm[L.acm.L[4].off_w]};
+            gemm<NarrowTile, true, true>(S + L.s.hm1, L.ldm1, acm + l.off_w, l.ld, B, l.rows, L.hm1, c.sm.gemm, epi);
+        }
+        __syncthreads();
+        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.hm2, acm, L.acm.L[2], S + L.s.xcp + L.ldo, L.ldc, B,
+                                               acm + L.acm.L[4].off_w + 4, S + L.s.tm3, L.lda);
+        __syncthreads();
+    }
+}
+
+// ---- ACM backward to its input (frozen ACM: no weight gradients).  In: dxc action block.  Out: dxm.
+__device__ inline void acm_backward_dx(const Ctx& c) {
+    const Layout& L = c.a.L;
+    const float* acm = c.net(NET_ACM);
+    float* S = c.S;
+    const int B = L.B, ac = L.ac;
+    const float* scale = (L.acm_kind == ACM_MLP) ? c.a.acm_lim : acm + L.acm.L[4].off_w + 4;
+    // d3 = da * scale * (1 - t3^2)
+    for (int e = threadIdx.x; e < B * ac; e += kThreads) {
+        const int r = e / ac, j = e % ac;
+        const float t3 = S[L.s.tm3 + r * L.lda + j];
+        const float da = S[L.s.dxc + r * L.ldc + L.ldo + j];
+        S[L.s.dm3 + r * L.lda + j] = __fmul_rn(__fmul_rn(da, scale[j]), __fsub_rn(1.f, __fmul_rn(t3, t3)));
+    }
+    __syncthreads();
+    {   // d2 = (d3 W3) * (1 - h2^2)      [B x hm2], K = ac
+        const LayerDesc& l = L.acm.L[2];
+        EpiMaskStore<MASK_TANH, false, false> epi{S + L.s.dm2, L.ldm2, S + L.s.hm2, L.ldm2, nullptr, 1.f};
+        gemm<NarrowTile, true, false>(S + L.s.dm3, L.lda, acm + l.off_w, l.ld, B, L.hm2, ac, c.sm.gemm, epi);
+    }
+    __syncthreads();
+    if (L.acm_kind == ACM_BASIC) {   // ds = d2 * t
+        const float t = acm[L.acm.L[4].off_w];
+        for (int e = threadIdx.x; e < B * L.hm2; e += kThreads) {
+            const int r = e / L.hm2, j = e % L.hm2;
+            S[L.s.dms + r * L.ldm2 + j] = __fmul_rn(S[L.s.dm2 + r * L.ldm2 + j], t);
+        }
+    }
+    {   // d1 = (d2 W2) * (1 - h1^2)      [B x hm1], K = hm2
+        const LayerDesc& l = L.acm.L[1];
+        EpiMaskStore<MASK_TANH, false, false> epi{S + L.s.dm1, L.ldm1, S + L.s.hm1, L.ldm1, nullptr, 1.f};
+        gemm<NarrowTile, true, false>(S + L.s.dm2, L.ldm2, acm + l.off_w, l.ld, B, L.hm1, L.hm2, c.sm.gemm, epi);
+    }
+    __syncthreads();
+    {   // dx = d1 W1 (+ ds W21)          [B x ldm], K = hm1
+        const LayerDesc& l = L.acm.L[0];
+        EpiMaskStore<MASK_NONE, false, false> epi{S + L.s.dxm, L.ldm, nullptr, 0, nullptr, 1.f};
+        gemm<NarrowTile, true, false>(S + L.s.dm1, L.ldm1, acm + l.off_w, l.ld, B, L.ldm, L.hm1, c.sm.gemm, epi);
+        if (L.acm_kind == ACM_BASIC) {
+            const LayerDesc& l2 = L.acm.L[3];
+            EpiMaskStore<MASK_NONE, false, true> epi2{S + L.s.dxm, L.ldm, nullptr, 0, nullptr, 1.f};
+            gemm<NarrowTile, true, false>(S + L.s.dms, L.ldm2, acm + l2.off_w, l2.ld, B, L.ldm, L.hm2, c.sm.gemm, epi2);
+        }
+    }
+    __syncthreads();
+}
+
+// ---- critic hidden layers for `ncrit` critics: hc1 = relu(fc1 x), hc2 = relu(fc2 hc1)
+__device__ inline void critics_hidden(const Ctx& c, const float* X, const int* nets, int ncrit) {
+    const Layout& L = c.a.L;
+    float* S = c.S;
+    for (int i = 0; i < ncrit; ++i)
+        linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldc, L.ldc, c.net(nets[i]), L.critic.L[0], S + L.s.hc1[i], kHidden, L.B);
+    __syncthreads();
+    for (int i = 0; i < ncrit; ++i)
+        linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.hc1[i], kHidden, kHidden, c.net(nets[i]), L.critic.L[1],
+                                             S + L.s.hc2[i], kHidden, L.B);
+    __syncthreads();
+}
+
+// q[r] = hc2[i][r,:] . w3 + b3 for one row (whole warp)
+__device__ inline float critic_head_row(const float* h2row, const float* w3, float b3) {
+    float s = 0.f;
+#pragma unroll
+    for (int cidx = 0; cidx < kHidden / 32; ++cidx) {
+        const int n = lane_id() + 32 * cidx;
+        s = fmaf(h2row[n], w3[n], s);
+    }
+    return warp_sum(s) + b3;
+}
+
+// ---- Q target: y = r + gamma*(1-done) * (min_i q_i^targ - alpha*logp')      (SAC) / (q^targ) (DDPG)
+__device__ inline void stage_qtarget(const Ctx& c, const int* tnets, int ncrit) {
+    const Layout& L = c.a.L;
+    const float* S = c.S;
+    float* y = c.vec(VEC_Y);
+    const float* vr = c.vec(VEC_R); const float* vnd = c.vec(VEC_ND); const float* lpn = c.vec(VEC_LOGPN);
+    for (int r = warp_id(); r < L.B; r += kWarps) {
+        float q = 0.f;
+        for (int i = 0; i < ncrit; ++i) {
+            const float* net = c.net(tnets[i]);
+            const float qi = critic_head_row(S + L.s.hc2[i] + (size_t)r * kHidden, net + L.critic.L[2].off_w,
+                                             net[L.critic.L[2].off_b]);
+            q = (i == 0) ? qi : fminf(q, qi);
+        }
+        if (lane_id() == 0) {
+            float inner = q;
+            if (L.algo == ALGO_SAC) inner = __fsub_rn(q, __fmul_rn(c.sm.alpha, lpn[r]));
+            y[r] = __fadd_rn(vr[r], __fmul_rn(vnd[r], inner));
+        }
+    }
+}
+
+// ---- critic loss + backward through fc3 (+ Adam on fc3 / b3 / b2 of each critic).
+//      MODE 0: critic update (dq = (2/B)(q - y); accumulates dW3, db3, db2 and applies Adam + Polyak to them)
+//      MODE 1: policy pass   (dq = -1/B routed to argmin_i q_i; no weight gradients)
+template <int MODE>
+__device__ inline void stage_critic_head_bwd(const Ctx& c, const int* nets, const int* tnets, int ncrit, float* loss_out) {
+    const Layout& L = c.a.L;
+    float* S = c.S;
+    const int B = L.B, lane = lane_id(), warp = warp_id();
+    const float* y = c.vec(VEC_Y); const float* lp = c.vec(VEC_LOGP);
+    const float invB = 1.0f / (float)B, norm2 = (float)(2.0 / (double)B);
+    float acc_w3[2][8], acc_b2[2][8], acc_b3[2] = {0.f, 0.f}, lsum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc_w3[i][k] = 0.f; acc_b2[i][k] = 0.f; }
+    for (int r = warp; r < B; r += kWarps) {
+        float q[2] = {0.f, 0.f};
+        for (int i = 0; i < ncrit; ++i) {
+            const float* net = c.net(nets[i]);
+            q[i] = critic_head_row(S + L.s.hc2[i] + (size_t)r * kHidden, net + L.critic.L[2].off_w, net[L.critic.L[2].off_b]);
+        }
+        float dq[2];
+        if (MODE == 0) {
+            for (int i = 0; i < ncrit; ++i) {
+                const float diff = __fsub_rn(q[i], y[r]);
+                dq[i] = __fmul_rn(norm2, diff);
+                lsum[i] += (lane == 0) ? diff * diff : 0.f;
+            }
+        } else {
+            const float gq = -invB;
+            if (ncrit == 2) {
+                const float tie = (q[0] == q[1]) ? 0.5f * gq : 0.f;
+                dq[0] = (q[0] < q[1] ? gq : 0.f) + tie;
+                dq[1] = (q[1] < q[0] ? gq : 0.f) + tie;
+                const float qm = fminf(q[0], q[1]);
+                lsum[0] += (lane == 0) ? (L.algo == ALGO_SAC ? __fsub_rn(__fmul_rn(c.sm.alpha, lp[r]), qm) : -qm) : 0.f;
+            } else {
+                dq[0] = gq;
+                lsum[0] += (lane == 0) ? -q[0] : 0.f;
+            }
+        }
+        for (int i = 0; i < ncrit; ++i) {
+            const float* net = c.net(nets[i]);
+            const float* w3 = net + L.critic.L[2].off_w;
+            const float* h2 = S + L.s.hc2[i] + (size_t)r * kHidden;
+            float* dz2 = S + L.s.dz2[i] + (size_t)r * kHidden;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int n = lane + 32 * k;
+                const float h = h2[n];
+                const float dz = (h > 0.f) ? __fmul_rn(dq[i], w3[n]) : 0.f;
+                dz2[n] = dz;
+                if (MODE == 0) { acc_w3[i][k] = fmaf(dq[i], h, acc_w3[i][k]); acc_b2[i][k] += dz; }
+            }
+            if (MODE == 0) acc_b3[i] += dq[i];
+        }
+    }
+    // losses
+    for (int i = 0; i < (MODE == 0 ? ncrit : 1); ++i) {
+        const float t = block_sum(lsum[i], c.sm.small);
+        if (threadIdx.x == 0 && loss_out) loss_out[i] = t * invB;
+        __syncthreads();
+    }
+    if (MODE == 0) {
+        // cross-warp reduction of the column partials, then Adam on fc3.weight, fc3.bias, fc2.bias
+        for (int i = 0; i < ncrit; ++i) {
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                c.sm.red[warp * 512 + lane + 32 * k] = acc_w3[i][k];
+                c.sm.red[warp * 512 + 256 + lane + 32 * k] = acc_b2[i][k];
+            }
+            if (lane == 0) c.sm.small[32 + warp] = acc_b3[i];
+            __syncthreads();
+            for (int n = threadIdx.x; n < 512; n += kThreads) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) s += c.sm.red[w * 512 + n];
+                c.sm.vecs[n] = s;
+            }
+            if (threadIdx.x == 0) {
+                float s = 0.f;
+                for (int w = 0; w < kWarps; ++w) s += c.sm.small[32 + w];
+                c.sm.vecs[512] = s;
+            }
+            __syncthreads();
+            const int id = nets[i];
+            float* net = c.net(id); float* nm = c.net_m(id); float* nv = c.net_v(id); float* tn = c.net(tnets[i]);
+            const AdamScalars& as = c.sm.adam[1 + i];
+            const LayerDesc& l3 = L.critic.L[2]; const LayerDesc& l2 = L.critic.L[1];
+            adam_vector(net + l3.off_w, nm + l3.off_w, nv + l3.off_w, tn + l3.off_w, c.sm.vecs, kHidden, as, c.a.h.tau, c.a.h.one_minus_tau, false);
+            adam_vector(net + l3.off_b, nm + l3.off_b, nv + l3.off_b, tn + l3.off_b, c.sm.vecs + 512, 1, as, c.a.h.tau, c.a.h.one_minus_tau, false);
+            adam_vector(net + l2.off_b, nm + l2.off_b, nv + l2.off_b, tn + l2.off_b, c.sm.vecs + 256, kHidden, as, c.a.h.tau, c.a.h.one_minus_tau, false);
+        }
+    }
+}
+
+}  // namespace spp

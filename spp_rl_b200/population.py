@@ -1,0 +1,229 @@
+"""Host-side handle on a device-resident population of SPP agents (thin wrapper over the C ABI).
+
+One `Population` = P independent agents with identical shapes and hyper-parameters -- what the
+reference runs as P OS processes (train/spp_sac_hopper.py:115, rltoolkit/evals.py:86-103).
+All arithmetic happens in libspp_rl_b200.so; this file only marshals numpy / torch buffers.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, SppError, check
+
+
+def _ptr(arr, ctype):
+    """ctypes pointer to a numpy array or torch CPU tensor (must be C-contiguous), or None."""
+    if arr is None:
+        return None
+    if hasattr(arr, "data_ptr"):            # torch tensor (possibly pinned)
+        if not arr.is_contiguous():
+            raise SppError("tensor must be contiguous")
+        return C.cast(arr.data_ptr(), C.POINTER(ctype))
+    if not arr.flags["C_CONTIGUOUS"]:
+        raise SppError("array must be C-contiguous")
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+NET_NAMES = {
+    "actor": _lib.NET_ACTOR, "critic_1": _lib.NET_CRITIC_1, "critic_2": _lib.NET_CRITIC_2, "critic": _lib.NET_CRITIC_1,
+    "acm": _lib.NET_ACM, "critic_1_targ": _lib.NET_CRITIC_1_TARG, "critic_2_targ": _lib.NET_CRITIC_2_TARG,
+    "critic_targ": _lib.NET_CRITIC_1_TARG, "actor_targ": _lib.NET_ACTOR_TARG,
+}
+LOSS_KEYS = ("critic_1", "critic_2", "actor", "pi", "dist", "alpha_loss", "alpha")
+
+
+class Population:
+    def __init__(self, algo="sac", ob_dim=11, ac_dim=3, population=1, device=0, acm_kind="acm", acm_critic=True,
+                 norm_closs=False, min_max_denormalize=True, update_batch_size=256, acm_batch_size=128,
+                 buffer_size=0, store_actions=True, gamma=0.99, tau=0.005, actor_lr=1e-3, critic_lr=1e-3,
+                 alpha_lr=1e-3, acm_lr=3e-3, custom_loss=0.0, alpha=0.2, target_entropy=None):
+        self.lib = _lib.load_library()
+        self.algo = algo
+        self.ob_dim, self.ac_dim, self.P = int(ob_dim), int(ac_dim), int(population)
+        self.B = int(update_batch_size)
+        self.acm_critic = bool(acm_critic)
+        cfg = Config()
+        cfg.algo = _lib.ALGO_SAC if algo == "sac" else _lib.ALGO_DDPG
+        cfg.ob_dim, cfg.ac_dim = self.ob_dim, self.ac_dim
+        cfg.acm_kind = _lib.ACM_MLP if acm_kind in ("acm", "mlp") else _lib.ACM_BASIC
+        cfg.acm_critic, cfg.norm_closs, cfg.min_max_denormalize = int(acm_critic), int(norm_closs), int(min_max_denormalize)
+        cfg.update_batch_size, cfg.acm_batch_size = self.B, int(acm_batch_size)
+        cfg.store_actions, cfg.buffer_size = int(store_actions), int(buffer_size)
+        cfg.gamma, cfg.tau, cfg.actor_lr, cfg.critic_lr = gamma, tau, actor_lr, critic_lr
+        cfg.alpha_lr, cfg.acm_lr, cfg.custom_loss, cfg.alpha = alpha_lr, acm_lr, float(custom_loss), alpha
+        cfg.target_entropy = float(-ac_dim if target_entropy is None else target_entropy)
+        self.cfg = cfg
+        h = C.c_void_p()
+        check(self.lib.spp_population_create(C.byref(cfg), self.P, int(device), C.byref(h)))
+        self.h = h
+        self._tensors = {}
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.spp_population_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.spp_sync(self.h))
+
+    # ------------------------------------------------------------------ limits / stats
+    def set_limits(self, actor_lim, acm_lim):
+        a = _f32(np.broadcast_to(np.asarray(actor_lim, dtype=np.float32), (self.ob_dim,)))
+        m = _f32(np.broadcast_to(np.asarray(acm_lim, dtype=np.float32), (self.ac_dim,)))
+        check(self.lib.spp_set_limits(self.h, _ptr(a, C.c_float), _ptr(m, C.c_float)))
+
+    def set_norm_stats(self, min_obs=None, max_obs=None, obs_mean=None, obs_std=None, agent=-1):
+        arrs = [None if v is None else _f32(v) for v in (min_obs, max_obs, obs_mean, obs_std)]
+        check(self.lib.spp_set_norm_stats(self.h, agent, *[_ptr(v, C.c_float) for v in arrs]))
+
+    # ------------------------------------------------------------------ parameters
+    def tensor_list(self, net):
+        nid = NET_NAMES[net] if isinstance(net, str) else net
+        if nid not in self._tensors:
+            out = []
+            for t in range(self.lib.spp_net_tensor_count(self.h, nid)):
+                name = C.create_string_buffer(64)
+                r, c = C.c_int(), C.c_int()
+                check(self.lib.spp_net_tensor_info(self.h, nid, t, name, 64, C.byref(r), C.byref(c)))
+                out.append((name.value.decode(), r.value, c.value))
+            self._tensors[nid] = out
+        return nid, self._tensors[nid]
+
+    @staticmethod
+    def _ref_shape(name, rows, cols):
+        """Shape of the reference's tensor: biases [rows], gains t [1] / t1 [ac], weights [rows, cols]."""
+        return (rows,) if (name.endswith(".bias") or name in ("t", "t1")) else (rows, cols)
+
+    def load_state_dict(self, net, sd, agent=-1):
+        """`sd`: mapping name -> array in the reference's state_dict layout (rltoolkit nn.Module keys)."""
+        nid, tl = self.tensor_list(net)
+        for t, (name, rows, cols) in enumerate(tl):
+            v = sd[name]
+            v = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            v = _f32(v).reshape(-1)
+            if v.size != int(np.prod(self._ref_shape(name, rows, cols))):
+                raise SppError("tensor %s: expected %s elements" % (name, self._ref_shape(name, rows, cols)))
+            check(self.lib.spp_params_upload(self.h, agent, nid, t, _ptr(v, C.c_float)))
+
+    def state_dict(self, net, agent=0):
+        nid, tl = self.tensor_list(net)
+        out = OrderedDict()
+        for t, (name, rows, cols) in enumerate(tl):
+            shape = self._ref_shape(name, rows, cols)
+            v = np.empty(shape, np.float32)
+            check(self.lib.spp_params_download(self.h, agent, nid, t, _ptr(v, C.c_float)))
+            out[name] = v
+        return out
+
+    def adam_state(self, net, agent=0):
+        """-> (OrderedDict name -> (exp_avg, exp_avg_sq), step)"""
+        nid, tl = self.tensor_list(net)
+        out = OrderedDict()
+        step = C.c_int(0)
+        for t, (name, rows, cols) in enumerate(tl):
+            shape = self._ref_shape(name, rows, cols)
+            m, v = np.empty(shape, np.float32), np.empty(shape, np.float32)
+            check(self.lib.spp_adam_download(self.h, agent, nid, t, _ptr(m, C.c_float), _ptr(v, C.c_float), C.byref(step)))
+            out[name] = (m, v)
+        return out, step.value
+
+    def sync_targets(self, agent=-1):
+        check(self.lib.spp_sync_targets(self.h, agent))
+
+    def alpha(self, agent=0):
+        la, al = C.c_double(), C.c_double()
+        check(self.lib.spp_alpha_get(self.h, agent, C.byref(la), C.byref(al)))
+        return la.value, al.value
+
+    def set_log_alpha(self, log_alpha, agent=-1):
+        check(self.lib.spp_alpha_set(self.h, agent, float(log_alpha)))
+
+    # ------------------------------------------------------------------ replay ring
+    def ring_add_obs(self, agent, obs):
+        o = _f32(obs).reshape(-1)
+        idx = C.c_int64()
+        check(self.lib.spp_ring_add_obs(self.h, agent, _ptr(o, C.c_float), C.byref(idx)))
+        return idx.value
+
+    def ring_add_acm_action(self, agent, acm_action):
+        a = _f32(acm_action).reshape(-1)
+        check(self.lib.spp_ring_add_acm_action(self.h, agent, _ptr(a, C.c_float)))
+
+    def ring_add_timestep(self, agent, obs_idx, next_obs_idx, action, rew, done, end):
+        a = None if action is None else _f32(action).reshape(-1)
+        check(self.lib.spp_ring_add_timestep(self.h, agent, int(obs_idx), int(next_obs_idx), _ptr(a, C.c_float),
+                                             float(rew), int(bool(done)), int(bool(end))))
+
+    def ring_reset(self, agent=-1):
+        check(self.lib.spp_ring_reset(self.h, agent))
+
+    def ring_state(self, agent=0):
+        out = (C.c_int64 * 3)()
+        check(self.lib.spp_ring_state(self.h, agent, out))
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def ring_sample_batch(self, agent, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        n = idx.size
+        obs, nobs = np.empty((n, self.ob_dim), np.float32), np.empty((n, self.ob_dim), np.float32)
+        act = np.empty((n, self.ob_dim), np.float32)
+        rew, done = np.empty(n, np.float32), np.empty(n, np.int8)
+        aacm = np.empty((n, self.ac_dim), np.float32)
+        check(self.lib.spp_ring_sample_batch(self.h, agent, _ptr(idx, C.c_int64), n, _ptr(obs, C.c_float), _ptr(nobs, C.c_float),
+                                             _ptr(act, C.c_float), _ptr(rew, C.c_float), _ptr(done, C.c_int8), _ptr(aacm, C.c_float)))
+        return obs, nobs, act, rew, done, aacm
+
+    def ring_fill_synthetic(self, seed, n, episode_len=1000):
+        check(self.lib.spp_ring_fill_synthetic(self.h, int(seed), int(n), int(episode_len)))
+
+    def ring_gather_bench(self, n_batches, seed=0, stream=None):
+        b = C.c_double()
+        check(self.lib.spp_ring_gather_bench_device(self.h, int(n_batches), int(seed), C.byref(b), stream))
+        return b.value
+
+    # ------------------------------------------------------------------ updates
+    def update_host(self, grad_steps, obs, next_obs, action, reward, done, acm_action, eps=None, seed=0, losses=None):
+        """The reference's update(obs, next_obs, action, reward, done, acm_action), G steps for P agents.
+        Arrays are [P, G, B, ...] host buffers (numpy or pinned torch).  Returns losses [P, G, 8]."""
+        if losses is None:
+            losses = np.empty((self.P, grad_steps, _lib.LOSS_COUNT), np.float32)
+        check(self.lib.spp_update_host(self.h, int(grad_steps), _ptr(obs, C.c_float), _ptr(next_obs, C.c_float),
+                                       _ptr(action, C.c_float), _ptr(reward, C.c_float), _ptr(done, C.c_int8),
+                                       _ptr(acm_action, C.c_float), _ptr(eps, C.c_float), int(seed), _ptr(losses, C.c_float)))
+        return losses
+
+    def update_ring(self, grad_steps, idx=None, eps=None, seed=0, losses=None):
+        """sample_batch + update from the device ring; idx int64 [P, G, B] host indices or None."""
+        if losses is None:
+            losses = np.empty((self.P, grad_steps, _lib.LOSS_COUNT), np.float32)
+        check(self.lib.spp_update_ring(self.h, int(grad_steps), _ptr(idx, C.c_int64), _ptr(eps, C.c_float), int(seed),
+                                       _ptr(losses, C.c_float)))
+        return losses
+
+    def update_ring_device(self, grad_steps, seed=0, losses_dev_ptr=None, stream=None):
+        check(self.lib.spp_update_ring_device(self.h, int(grad_steps), int(seed), losses_dev_ptr, stream))
+
+    # ------------------------------------------------------------------ introspection
+    def debug_scratch(self, agent, name):
+        cap = 4096 * 512
+        buf = np.empty(cap, np.float32)
+        r, ld = C.c_int(), C.c_int()
+        check(self.lib.spp_debug_scratch(self.h, agent, name.encode(), _ptr(buf, C.c_float), cap, C.byref(r), C.byref(ld)))
+        return buf[: r.value * ld.value].reshape(r.value, ld.value).copy()
+
+
+def kernel_launches() -> int:
+    return int(_lib.load_library().spp_kernel_launches())

@@ -1,0 +1,45 @@
+"""-m gpu: the fused CUDA update kernels (through the C ABI) against the CPU oracle on identical
+weights, minibatches and noise.  Tolerance: north_star's 1e-5 relative in fp32, measured as the
+norm-relative error per tensor (post-step weights, Adam moments, targets) and relative error of
+losses; log_alpha (fp64) to 1e-5 relative as well."""
+import pytest
+
+from tests.parity_util import run_offpolicy_parity_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+SAC_CASES = [
+    dict(ob=11, ac=3, batch=256, population=2, steps=3),                                   # Hopper, published flags
+    dict(ob=11, ac=3, batch=100, population=3, steps=2),                                   # script batch size (ragged tile)
+    dict(ob=11, ac=3, batch=64, population=2, steps=2, small_std=True),                    # near-cancelling log-prob terms
+    dict(ob=11, ac=3, batch=64, population=1, steps=2, norm_closs=True),
+    dict(ob=11, ac=3, batch=64, population=1, steps=2, norm_closs=True, min_max=False),
+    dict(ob=11, ac=3, batch=64, population=1, steps=2, custom_loss=0.0),
+    dict(ob=11, ac=3, batch=64, population=1, steps=2, acm_critic=False),
+    dict(ob=3, ac=1, batch=100, population=2, steps=2, min_max=False, actor_lim=[1.0, 1.0, 8.0], acm_lim=[2.0]),   # Pendulum
+    dict(ob=17, ac=6, batch=128, population=2, steps=2),                                   # HalfCheetah
+    dict(ob=111, ac=8, batch=256, population=1, steps=2),                                  # Ant
+    dict(ob=11, ac=3, batch=1, population=1, steps=2),                                     # degenerate batch
+]
+
+
+@pytest.mark.parametrize("case", SAC_CASES, ids=lambda c: "-".join("%s%s" % (k, v) for k, v in c.items() if k not in ("actor_lim", "acm_lim")))
+def test_sac_acm_update_matches_oracle(case):
+    worst = run_offpolicy_parity_case(algo="sac", verbose=True, **case)
+    assert worst < TOL, worst
+
+
+DDPG_CASES = [
+    dict(ob=17, ac=6, batch=256, population=2, steps=3, custom_loss=1.0, acm_kind="basic", gamma=0.95, lr=5e-4),   # config 3
+    dict(ob=17, ac=6, batch=100, population=2, steps=2, custom_loss=1.0, acm_kind="basic", gamma=0.95, lr=5e-4),
+    dict(ob=11, ac=3, batch=64, population=1, steps=2, custom_loss=1.0, acm_kind="acm", norm_closs=True),
+    dict(ob=11, ac=3, batch=64, population=1, steps=2, custom_loss=0.0, acm_critic=False, min_max=False),
+    dict(ob=111, ac=8, batch=128, population=1, steps=2, custom_loss=1.0, acm_kind="basic"),
+]
+
+
+@pytest.mark.parametrize("case", DDPG_CASES, ids=lambda c: "-".join("%s%s" % (k, v) for k, v in c.items()))
+def test_ddpg_acm_update_matches_oracle(case):
+    worst = run_offpolicy_parity_case(algo="ddpg", verbose=True, **case)
+    assert worst < TOL, worst
