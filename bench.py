@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- SPP-SAC grad updates/sec (Hopper shape) on B200, per the driver contract.
+
+A "step" is one burst of the hot path: every agent of the population performs G = 50 consecutive
+SAC_AcM updates (the reference's grad_steps, train/spp_sac_hopper.py:22), each on a B = 256
+minibatch gathered from that agent's device-resident replay ring (capacity 1 M transitions).
+  value  updates/s with everything resident in HBM (device sampler + device noise), CUDA-event timed.
+  e2e    the same metric through the C-ABI host call spp_update_host() -- the reference's
+         update(obs, next_obs, action, reward, done, acm_action) signature -- with pinned HOST
+         minibatches copied H2D and the loss table copied D2H inside the timed region.
+  roofline      algorithmic FLOPs of the update (SURVEY 8d formula) / kernel time vs the measured peak.
+  cpu_baseline  the CPU oracle port (plain-tensor restatement of rltoolkit's update) on the host cores.
+`--impl reference` times that CPU port alone (the reference is Python; /root/reference does not
+exist on the GPU box, so the oracle port is the travelling stand-in).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SPP-SAC grad updates/sec (Hopper shape) + acm rollout transitions/sec"
+OB, AC, B, G = 11, 3, 256, 50
+RING = 1_000_000
+RING_FILL = 999_000            # 999 episodes x 1000 steps (+ 999 terminal observations) fit the 1 M ring
+# Hopper-scale observation statistics (synthetic; same order of magnitude as a trained SPP-SAC Hopper run)
+MIN_OBS = [0.73, -0.20, -1.34, -1.43, -0.89, -1.26, -2.92, -4.62, -5.10, -8.25, -10.0]
+MAX_OBS = [1.68, 0.18, 0.02, 0.04, 0.90, 4.59, 2.83, 2.58, 3.96, 7.69, 10.0]
+
+
+def flops_per_update(ob=OB, ac=AC, b=B, hidden=256, hm1=64, hm2=32):
+    """B*(2Fa + 6Fc + 2Fm + 2(2Fc - Fc1) + 2Fc + Fm + (2Fa - Fa1)), F = 2*MACs of one forward."""
+    fa1 = 2 * ob * hidden
+    fa = fa1 + 2 * hidden * hidden + 2 * hidden * 2 * ob
+    fc1 = 2 * (ob + ac) * hidden
+    fc = fc1 + 2 * hidden * hidden + 2 * hidden
+    fm = 2 * (2 * ob * hm1 + hm1 * hm2 + hm2 * ac)
+    return b * (2 * fa + 6 * fc + 2 * fm + 2 * (2 * fc - fc1) + 2 * fc + fm + (2 * fa - fa1))
+
+
+# ------------------------------------------------------------------------------------------- CPU side
+def _cpu_worker(args):
+    n_updates, seed = args
+    import numpy as np
+    import torch
+
+    torch.set_num_threads(1)          # rltoolkit/evals.py:22-26: one intra-op thread per run
+    from oracle import offpolicy as op
+    from oracle.norm import NormStats
+    from spp_rl_b200.init import init_state
+
+    s = {k: torch.from_numpy(v) for k, v in init_state("sac", OB, AC, seed).items()}
+    s["log_alpha"] = torch.tensor(np.log(0.2), dtype=torch.float64)
+    st = NormStats(True, torch.tensor(MIN_OBS), torch.tensor(MAX_OBS))
+    hp = op.OffPolicyHP(gamma=0.99, custom_loss=0.2, norm_closs=False, acm_critic=True, target_entropy=-float(AC),
+                        actor_lim=torch.ones(OB), acm_lim=torch.ones(AC))
+    g = torch.Generator().manual_seed(seed)
+    mn, mx = torch.tensor(MIN_OBS), torch.tensor(MAX_OBS)
+    obs = torch.rand(B, OB, generator=g) * (mx - mn) + mn
+    nobs = obs + 0.02 * torch.randn(B, OB, generator=g)
+    rew = torch.randn(B, generator=g)
+    done = (torch.rand(B, generator=g) < 1e-3).to(torch.int8)
+    aacm = torch.tanh(torch.randn(B, AC, generator=g))
+    alpha = None
+    for _ in range(3):
+        _, alpha = op.sac_acm_update(s, hp, st, obs, nobs, None, rew, done, aacm, torch.randn(B, OB, generator=g),
+                                     torch.randn(B, OB, generator=g), alpha)
+    t0 = time.perf_counter()
+    for _ in range(n_updates):
+        _, alpha = op.sac_acm_update(s, hp, st, obs, nobs, None, rew, done, aacm, torch.randn(B, OB, generator=g),
+                                     torch.randn(B, OB, generator=g), alpha)
+    return time.perf_counter() - t0
+
+
+def cpu_updates_per_sec(n_updates_per_core, cores):
+    """Mirror of the reference's parallel model: `cores` independent single-thread runs (mp.Pool)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        spans = pool.map(_cpu_worker, [(n_updates_per_core, 50 + i) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    # throughput over the slowest worker's timed span (start-up and warm-up updates excluded)
+    return cores * n_updates_per_core / max(spans), wall
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------- GPU side
+def build_population(device, P, ring=RING):
+    import numpy as np
+    from spp_rl_b200 import Population, init_state
+
+    pop = Population(algo="sac", ob_dim=OB, ac_dim=AC, population=P, device=device, acm_kind="acm", acm_critic=True,
+                     norm_closs=False, min_max_denormalize=True, update_batch_size=B, buffer_size=ring,
+                     store_actions=False, gamma=0.99, tau=0.005, actor_lr=1e-3, critic_lr=1e-3, alpha_lr=1e-3,
+                     custom_loss=0.2, alpha=0.2, target_entropy=-float(AC))
+    pop.set_limits(np.ones(OB, np.float32), np.ones(AC, np.float32))
+    pop.set_norm_stats(np.array(MIN_OBS, np.float32), np.array(MAX_OBS, np.float32))
+    nets = ["actor", "critic_1", "critic_2", "critic_1_targ", "critic_2_targ", "acm"]
+    for a in range(P):
+        s0 = init_state("sac", OB, AC, 1000 + a)
+        for net in nets:
+            pop.load_state_dict(net, {k[len(net) + 1:]: v for k, v in s0.items() if k.startswith(net + ".")}, agent=a)
+    pop.ring_fill_synthetic(seed=7, n=ring * 999 // 1000, episode_len=1000)
+    return pop
+
+
+def main():
+    global G
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--agents-per-gpu", type=int, default=0, help="population per GPU (default: one agent per SM)")
+    ap.add_argument("--ring-capacity", type=int, default=RING, help="replay ring capacity per agent (profiling runs shrink it)")
+    ap.add_argument("--grad-steps", type=int, default=G)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N = args.gpus
+    K, W = args.steps, max(args.warmup, 0)
+    G = args.grad_steps
+    RINGC = args.ring_capacity
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle port)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = host_cores()
+        n = 40
+        ups, wall = 0.0, 0.0
+        vals = []
+        for _ in range(max(1, min(K, 3))):
+            v, wall = cpu_updates_per_sec(n, cores)
+            vals.append(v)
+        ups = statistics.median(vals)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": ups, "unit": "updates/s", "n_gpus": N, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * (148 * G) / ups, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SPP-SAC Hopper shapes (ob 11, ac 3, hidden 256, B 256), CPU oracle port of "
+                                   "rltoolkit SAC_AcM.update, one single-thread run per host core (mp.Pool model)"},
+            "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
+                             "sample": "%d procs x %d updates (+3 warm-up), torch threads=1 each" % (cores, n)},
+            "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ CPU baseline first (fork before CUDA init)
+    cpu_base = None
+    if rank == 0 and N == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        n = 40
+        v, _ = cpu_updates_per_sec(n, cores)
+        cpu_base = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",
+                    "sample": "%d procs x %d updates of the same SAC Hopper B=256 update (+3 warm-up), torch threads=1 each" % (cores, n)}
+
+    import numpy as np
+    import torch
+
+    import __graft_entry__
+    if not os.path.exists(__graft_entry__.LIB):
+        __graft_entry__.build()
+    from spp_rl_b200 import kernel_launches, load_library
+
+    lib = load_library()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    P = args.agents_per_gpu or sm_count
+    pop = build_population(local_rank, P, args.ring_capacity)
+    stream = torch.cuda.Stream(device=local_rank)
+    sptr = stream.cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident value
+    for w in range(W):
+        pop.update_ring_device(G, seed=100 + w, stream=sptr)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = kernel_launches()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        t_all0.record(stream)
+        for k in range(K):
+            evs[k][0].record(stream)
+            pop.update_ring_device(G, seed=1000 + k, stream=sptr)
+            evs[k][1].record(stream)
+        t_all1.record(stream)
+    barrier()
+    launches = kernel_launches() - l0
+    clocks = sampler.stop() if sampler else None
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    updates_per_step = P * G * world
+    value = updates_per_step * K / (total_ms_max * 1e-3)
+
+    # ---- e2e through the host-buffer C-ABI call
+    e2e = None
+    if not args.no_e2e:
+        rng = np.random.RandomState(5 + rank)
+        mn, mx = np.array(MIN_OBS, np.float32), np.array(MAX_OBS, np.float32)
+
+        def pinned(a):
+            return torch.from_numpy(a).pin_memory()
+        h_obs = pinned((rng.rand(P, G, B, OB) * (mx - mn) + mn).astype(np.float32))
+        h_nobs = pinned((h_obs.numpy() + 0.02 * rng.randn(P, G, B, OB)).astype(np.float32))
+        h_rew = pinned(rng.randn(P, G, B).astype(np.float32))
+        h_done = pinned((rng.rand(P, G, B) < 1e-3).astype(np.int8))
+        h_aacm = pinned(np.tanh(rng.randn(P, G, B, AC)).astype(np.float32))
+        h_loss = torch.empty((P, G, 8), dtype=torch.float32).pin_memory()
+        h2d = sum(x.numel() * x.element_size() for x in (h_obs, h_nobs, h_rew, h_done, h_aacm))
+        d2h = h_loss.numel() * 4
+        for w in range(max(W, 1)):
+            pop.update_host(G, h_obs, h_nobs, None, h_rew, h_done, h_aacm, eps=None, seed=w, losses=h_loss)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            pop.update_host(G, h_obs, h_nobs, None, h_rew, h_done, h_aacm, eps=None, seed=50 + k, losses=h_loss)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": updates_per_step * K / float(t.item()), "unit": "updates/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "loss_check": float(h_loss[0, -1, 2])}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured (MEASURED_PEAKS.json bf16 sustained)" if peaks else "fallback (B200_PROFILING.md sustained)"
+        f_upd = flops_per_update()
+        kt = statistics.mean(kern_ms) * 1e-3
+        achieved = f_upd * P * G / kt / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("update_burst_kernel_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world if world > 1 else N, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SPP-SAC Hopper shapes (ob 11, ac 3, hidden 256, B 256) fused update bursts, population of "
+                                   "%d independent agents per GPU (one per SM), each with its own 1M-transition device replay "
+                                   "ring; one step = %d updates per agent" % (P, G),
+                       "agents_per_gpu": P, "grad_steps": G, "batch": B, "ring_capacity": RINGC, "ring_fill": RINGC * 999 // 1000,
+                       "updates_per_step": updates_per_step, "l2": "working set (rings %.1f GB + agent state) >> 126 MB L2, no flush needed"
+                       % (P * RINGC * 114 / 1e9), "parallelism": "independent agents sharded over GPUs, no collective"},
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "flops_per_update": f_upd,
+                         "kernel": "update_burst_kernel<SAC>", "kernel_ms": statistics.mean(kern_ms),
+                         "note": "fp32-exact FFMA path (1e-5 parity); CUDA-core fp32 peak is ~74 TFLOP/s nominal"},
+            "cpu_baseline": cpu_base, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    pop.close()
+
+
+if __name__ == "__main__":
+    main()

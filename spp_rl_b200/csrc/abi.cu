@@ -304,6 +304,9 @@ int spp_net_tensor_info(spp_population* p, int net, int t, char* name, int name_
 }
 
 // direction: 0 upload params, 1 download params, 2 download m, 3 download v
+// Weights exist twice on the device (natural W [rows x ld] and W^T [ld x ld_t], see layout.h).  Uploads write both;
+// downloads read W^T where it exists (target nets are only maintained in that copy).  Adam moments follow the
+// natural layout except for the actor heads, whose dW tile is computed transposed (update_kernel.cu).
 static int tensor_io(spp_population* p, int a, int net, int t, float* host, int dir) {
     if (!p || !host) return fail(SPP_ERR_ARG, "null argument");
     if (net < 0 || net >= NET_COUNT || t < 0 || t >= (int)p->tensors[net].size()) return fail(SPP_ERR_ARG, "bad net/tensor id");
@@ -315,28 +318,54 @@ static int tensor_io(spp_population* p, int a, int net, int t, float* host, int 
     const LayerDesc& l = net_desc(p, net).L[m.layer];
     const size_t stride = (dir >= 2) ? L.train_size : L.params_size;
     float* arena = dir == 2 ? p->mom_m : dir == 3 ? p->mom_v : p->params;
-    size_t off; int n_dev;            // contiguous device span [off, off + n_dev)
-    if (m.is_bias == 0) { off = l.off_w + (size_t)m.row0 * l.ld; n_dev = m.rows * l.ld; }
-    else if (m.is_bias == 1) { off = l.off_b + m.row0; n_dev = m.rows; }
-    else { off = l.off_w + m.col0; n_dev = m.rows; }
-    std::vector<float> stage(n_dev, 0.f);
+    const bool is_w = (m.is_bias == 0);
+    const bool has_t = is_w && l.off_wt >= 0;
+    const bool heads = (net == NET_ACTOR || net == NET_ACTOR_TARG) && m.layer == 2;
+    // which copy a download reads: parameters from W^T when present; moments from the layout the optimiser uses
+    const bool read_t = has_t && (dir == 1 || heads);
+    std::vector<float> nat, tr;
+    if (is_w) {
+        nat.assign((size_t)m.rows * l.ld, 0.f);
+        if (has_t) tr.assign((size_t)l.ld * l.ld_t, 0.f);   // whole W^T block of the layer (heads: both halves)
+    } else {
+        nat.assign(m.rows, 0.f);
+    }
     for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i) {
-        float* dev = arena + (size_t)i * stride + L.net_off[net] + off;
+        float* base = arena + (size_t)i * stride + L.net_off[net];
+        float* dev_nat = is_w ? base + l.off_w + (size_t)m.row0 * l.ld
+                              : base + (m.is_bias == 1 ? l.off_b + m.row0 : l.off_w + m.col0);
+        float* dev_t = has_t ? base + l.off_wt : nullptr;
         if (dir == 0) {
-            if (m.is_bias == 0)
+            if (is_w) {
                 for (int r = 0; r < m.rows; ++r)
-                    for (int c = 0; c < m.cols; ++c) stage[(size_t)r * l.ld + map_col(l, c)] = host[(size_t)r * m.cols + c];
-            else
-                for (int r = 0; r < m.rows; ++r) stage[r] = host[r];
-            CK(cudaMemcpy(dev, stage.data(), n_dev * sizeof(float), cudaMemcpyHostToDevice));
+                    for (int c = 0; c < m.cols; ++c) nat[(size_t)r * l.ld + map_col(l, c)] = host[(size_t)r * m.cols + c];
+                CK(cudaMemcpy(dev_nat, nat.data(), nat.size() * sizeof(float), cudaMemcpyHostToDevice));
+                if (has_t) {   // read-modify-write of the W^T block: only columns [row0, row0 + rows) belong to this tensor
+                    CK(cudaMemcpy(tr.data(), dev_t, tr.size() * sizeof(float), cudaMemcpyDeviceToHost));
+                    for (int r = 0; r < m.rows; ++r)
+                        for (int c = 0; c < m.cols; ++c)
+                            tr[(size_t)map_col(l, c) * l.ld_t + m.row0 + r] = host[(size_t)r * m.cols + c];
+                    CK(cudaMemcpy(dev_t, tr.data(), tr.size() * sizeof(float), cudaMemcpyHostToDevice));
+                }
+            } else {
+                for (int r = 0; r < m.rows; ++r) nat[r] = host[r];
+                CK(cudaMemcpy(dev_nat, nat.data(), nat.size() * sizeof(float), cudaMemcpyHostToDevice));
+            }
         } else {
             CK(cudaStreamSynchronize(p->stream));
-            CK(cudaMemcpy(stage.data(), dev, n_dev * sizeof(float), cudaMemcpyDeviceToHost));
-            if (m.is_bias == 0)
+            if (is_w && read_t) {
+                CK(cudaMemcpy(tr.data(), dev_t, tr.size() * sizeof(float), cudaMemcpyDeviceToHost));
                 for (int r = 0; r < m.rows; ++r)
-                    for (int c = 0; c < m.cols; ++c) host[(size_t)r * m.cols + c] = stage[(size_t)r * l.ld + map_col(l, c)];
-            else
-                for (int r = 0; r < m.rows; ++r) host[r] = stage[r];
+                    for (int c = 0; c < m.cols; ++c)
+                        host[(size_t)r * m.cols + c] = tr[(size_t)map_col(l, c) * l.ld_t + m.row0 + r];
+            } else {
+                CK(cudaMemcpy(nat.data(), dev_nat, nat.size() * sizeof(float), cudaMemcpyDeviceToHost));
+                if (is_w)
+                    for (int r = 0; r < m.rows; ++r)
+                        for (int c = 0; c < m.cols; ++c) host[(size_t)r * m.cols + c] = nat[(size_t)r * l.ld + map_col(l, c)];
+                else
+                    for (int r = 0; r < m.rows; ++r) host[r] = nat[r];
+            }
         }
     }
     return SPP_OK;

@@ -1,4 +1,4 @@
-// FP32 tile GEMM for the fused update kernels: C[m,n] = sum_k A(m,k) * B(n,k), CUDA-core FFMA path.
+// FP32 tile GEMM for the fused update kernels: C[m,n] = sum_k A(m,k) * B(k,n), CUDA-core FFMA path.
 //
 // Operands live in global memory (L2-resident agent state / activation scratch) and are streamed
 // through a 4-stage cp.async (LDGSTS, L2-only) shared-memory pipeline; accumulators stay in
@@ -8,8 +8,13 @@
 // Operand layouts (row-major, leading dimension a multiple of 4 floats, pad columns zero):
 //   A_KC = true : A is [M x K], contraction contiguous   (forward x, backward dY for dX)
 //   A_KC = false: A is [K x M], contraction strided      (dY for dW: K = batch)
-//   B_KC = true : B is [N x K]                            (torch Linear weight in forward)
-//   B_KC = false: B is [K x N]                            (weight in dX; activations in dW)
+//   B is always [K x N] (contraction strided): the forward reads the TRANSPOSED weight copy W^T
+//   [in x out], dX reads the natural weight W [out x in], dW reads activations [batch x in].
+// Keeping B in outer-product form matters on this register file: with both operands fetched as
+// float4-along-k the two multiplicands of every FFMA sit in registers of equal parity (same bank),
+// which the first version of this kernel paid for with dispatch stalls on ~40% of its FFMAs
+// (profiles/r01_update_v1_summary.md).  With B[k][n..n+3] fragments the b operand's parity follows
+// n, the accumulator's parity is free, and the a operand is held in the operand-reuse cache.
 // The exactness target (1e-5 relative vs the fp32 reference) is why this path is FFMA and not
 // single-pass bf16/tf32 tensor cores; k is accumulated in ascending order.
 #pragma once
@@ -33,6 +38,14 @@ struct TileCfg {
 };
 using BigTile = TileCfg<16, 16, 8, 8>;     // 128 x 128, 8x8 per thread
 using NarrowTile = TileCfg<32, 8, 4, 4>;   // 128 x 32,  4x4 per thread (heads, ACM, first layers)
+
+// thread -> element mapping.  Columns are always float4 groups: n = 4*tx + j%4 + 4*TX*(j/4).
+template <class Cfg, bool A_KC>
+__device__ __forceinline__ int row_of(int i, int ty) {
+    return A_KC ? ty + Cfg::TY * i : (i / 4) * (4 * Cfg::TY) + 4 * ty + (i % 4);
+}
+template <class Cfg>
+__device__ __forceinline__ int col_of(int j, int tx) { return (j / 4) * (4 * Cfg::TX) + 4 * tx + (j % 4); }
 
 template <int ROWS, bool KC>
 __device__ __forceinline__ void load_operand(const float* __restrict__ G, int ld, int R, int K, int r0,
@@ -62,13 +75,11 @@ __device__ __forceinline__ void load_operand(const float* __restrict__ G, int ld
 }
 
 // One output tile.  Epi interface:
-//   static constexpr bool kColSum;            // reduce the returned values over m, atomicAdd into colsum_dst()
-//   float* colsum_dst();
-//   template<int NJ> void row(int m, const int (&n)[NJ], float (&v)[NJ], int N);  // v in: acc, out: value for colsum
-template <class Cfg, bool A_KC, bool B_KC, class Epi>
+//   template <class Cfg, bool A_KC> void apply(float (&acc)[MI][NJ], int m0, int n0, int M, int N, float* smem);
+template <class Cfg, bool A_KC, class Epi>
 __device__ __noinline__ void gemm_tile(const float* __restrict__ A, int lda, const float* __restrict__ B,
-                                          int ldb, int M, int N, int K, int m0, int n0,
-                                          float* __restrict__ smem, Epi& epi) {
+                                       int ldb, int M, int N, int K, int m0, int n0,
+                                       float* __restrict__ smem, Epi& epi) {
     constexpr int TY = Cfg::TY, TX = Cfg::TX, MI = Cfg::MI, NJ = Cfg::NJ, TM = Cfg::TM, TN = Cfg::TN;
     const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
     const int nk = (K + TK - 1) / TK;
@@ -85,7 +96,7 @@ __device__ __noinline__ void gemm_tile(const float* __restrict__ A, int lda, con
         if (s < nk) {
             float* sA = smem + s * kStageFloats;
             load_operand<TM, A_KC>(A, lda, M, K, m0, s * TK, sA);
-            load_operand<TN, B_KC>(B, ldb, N, K, n0, s * TK, sA + kOperandFloats);
+            load_operand<TN, false>(B, ldb, N, K, n0, s * TK, sA + kOperandFloats);
         }
         cp_async_commit();
     }
@@ -98,7 +109,7 @@ __device__ __noinline__ void gemm_tile(const float* __restrict__ A, int lda, con
             if (pf < nk) {
                 float* sA = smem + (pf % kStages) * kStageFloats;
                 load_operand<TM, A_KC>(A, lda, M, K, m0, pf * TK, sA);
-                load_operand<TN, B_KC>(B, ldb, N, K, n0, pf * TK, sA + kOperandFloats);
+                load_operand<TN, false>(B, ldb, N, K, n0, pf * TK, sA + kOperandFloats);
             }
             cp_async_commit();
         }
@@ -123,22 +134,14 @@ __device__ __noinline__ void gemm_tile(const float* __restrict__ A, int lda, con
                         af[kk][4 * i4 + 2] = v.z; af[kk][4 * i4 + 3] = v.w;
                     }
             }
-            if constexpr (B_KC) {
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const float4 v = *reinterpret_cast<const float4*>(sB + (tx + TX * j) * kPitchKC + 4 * k4);
-                    bf[0][j] = v.x; bf[1][j] = v.y; bf[2][j] = v.z; bf[3][j] = v.w;
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int j4 = 0; j4 < NJ / 4; ++j4) {
+                    const float4 v = *reinterpret_cast<const float4*>(sB + (4 * k4 + kk) * TN + j4 * (4 * TX) + 4 * tx);
+                    bf[kk][4 * j4 + 0] = v.x; bf[kk][4 * j4 + 1] = v.y;
+                    bf[kk][4 * j4 + 2] = v.z; bf[kk][4 * j4 + 3] = v.w;
                 }
-            } else {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                    for (int j4 = 0; j4 < NJ / 4; ++j4) {
-                        const float4 v = *reinterpret_cast<const float4*>(sB + (4 * k4 + kk) * TN + j4 * (4 * TX) + 4 * tx);
-                        bf[kk][4 * j4 + 0] = v.x; bf[kk][4 * j4 + 1] = v.y;
-                        bf[kk][4 * j4 + 2] = v.z; bf[kk][4 * j4 + 3] = v.w;
-                    }
-            }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
@@ -149,118 +152,140 @@ __device__ __noinline__ void gemm_tile(const float* __restrict__ A, int lda, con
     }
     cp_async_wait<0>();
     __syncthreads();   // every warp is done reading the pipeline; smem is reusable below and by the next tile
-
-    int ncol[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j)
-        ncol[j] = n0 + (B_KC ? tx + TX * j : (j / 4) * (4 * TX) + 4 * tx + (j % 4));
-    float cs[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) cs[j] = 0.f;
-#pragma unroll
-    for (int i = 0; i < MI; ++i) {
-        const int m = m0 + (A_KC ? ty + TY * i : (i / 4) * (4 * TY) + 4 * ty + (i % 4));
-        if (m < M) {
-            epi.template row<NJ>(m, ncol, acc[i], N);
-            if constexpr (Epi::kColSum) {
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) cs[j] += acc[i][j];
-            }
-        }
-    }
-    if constexpr (Epi::kColSum) {
-        float* red = smem;   // [TY][TN]
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) red[ty * TN + (ncol[j] - n0)] = cs[j];
-        __syncthreads();
-        for (int c = tid; c < TN; c += kThreads) {
-            float s = 0.f;
-#pragma unroll 4
-            for (int t = 0; t < TY; ++t) s += red[t * TN + c];
-            if (n0 + c < N) atomicAdd(epi.colsum_dst() + n0 + c, s);
-        }
-        __syncthreads();
-    }
+    epi.template apply<Cfg, A_KC>(acc, m0, n0, M, N, smem);
 }
 
 // All tiles of one GEMM, distributed round-robin over the CTAs that share an agent.
-template <class Cfg, bool A_KC, bool B_KC, class Epi>
+template <class Cfg, bool A_KC, class Epi>
 __device__ __forceinline__ void gemm(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                      int M, int N, int K, float* __restrict__ smem, Epi epi, int cta_rank = 0,
                                      int cta_count = 1) {
     const int mt = (M + Cfg::TM - 1) / Cfg::TM, nt = (N + Cfg::TN - 1) / Cfg::TN;
     for (int t = cta_rank; t < mt * nt; t += cta_count)
-        gemm_tile<Cfg, A_KC, B_KC, Epi>(A, lda, B, ldb, M, N, K, (t / nt) * Cfg::TM, (t % nt) * Cfg::TN, smem, epi);
+        gemm_tile<Cfg, A_KC, Epi>(A, lda, B, ldb, M, N, K, (t / nt) * Cfg::TM, (t % nt) * Cfg::TN, smem, epi);
 }
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ---------------------------------------------------------------------------------- epilogues
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+    if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == ACT_TANH) return tanhf(x);
+    return x;
+}
 
-// C[m, n] = act(acc + bias[n]) (* scale[n]); optional second copy (pre-scale) for backward.
-template <int ACT, bool SCALE>
+// C[m, n] = act(acc + bias[n] (+ t * Sk[m, n])) (* scale[n]); optional pre-scale copy C2 for the backward.
+// Pad columns of every row get act(0) * scale = 0 because weight and bias pads are zero.
+template <int ACT, bool SCALE, bool ADD>
 struct EpiBiasAct {
-    static constexpr bool kColSum = false;
-    float* C; int ldc; const float* bias; const float* scale; float* C2; int ldc2;
-    __device__ float* colsum_dst() { return nullptr; }
-    template <int NJ>
-    __device__ __forceinline__ void row(int m, const int (&n)[NJ], float (&v)[NJ], int N) {
+    float* C; int ldc; const float* bias; const float* scale; float* C2; int ldc2; const float* Sk; int lds; float t;
+    template <class Cfg, bool A_KC>
+    __device__ __forceinline__ void apply(float (&acc)[Cfg::MI][Cfg::NJ], int m0, int n0, int M, int N, float*) {
+        const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
+        constexpr int G4 = Cfg::NJ / 4;
+        float4 b[G4], sc[G4];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            if (n[j] < N) {
-                float x = v[j] + bias[n[j]];
-                if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
-                if (ACT == ACT_TANH) x = tanhf(x);
-                if (SCALE) {
-                    if (C2) C2[(size_t)m * ldc2 + n[j]] = x;
-                    x = x * scale[n[j]];
+        for (int g = 0; g < G4; ++g) {
+            const int n = n0 + col_of<Cfg>(4 * g, tx);
+            b[g] = (n < N) ? ld4(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (SCALE) sc[g] = (n < N) ? ld4(scale + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < Cfg::MI; ++i) {
+            const int m = m0 + row_of<Cfg, A_KC>(i, ty);
+            if (m >= M) continue;
+            float4 ad[G4];
+            if (ADD) {
+#pragma unroll
+                for (int g = 0; g < G4; ++g) {
+                    const int n = n0 + col_of<Cfg>(4 * g, tx);
+                    ad[g] = (n < N) ? ld4(Sk + (size_t)m * lds + n) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                C[(size_t)m * ldc + n[j]] = x;
+            }
+#pragma unroll
+            for (int g = 0; g < G4; ++g) {
+                const int n = n0 + col_of<Cfg>(4 * g, tx);
+                if (n >= N) continue;
+                float4 x = make_float4(acc[i][4 * g] + b[g].x, acc[i][4 * g + 1] + b[g].y, acc[i][4 * g + 2] + b[g].z,
+                                       acc[i][4 * g + 3] + b[g].w);
+                if (ADD) {
+                    x.x = __fadd_rn(x.x, __fmul_rn(t, ad[g].x)); x.y = __fadd_rn(x.y, __fmul_rn(t, ad[g].y));
+                    x.z = __fadd_rn(x.z, __fmul_rn(t, ad[g].z)); x.w = __fadd_rn(x.w, __fmul_rn(t, ad[g].w));
+                }
+                x.x = act_fn<ACT>(x.x); x.y = act_fn<ACT>(x.y); x.z = act_fn<ACT>(x.z); x.w = act_fn<ACT>(x.w);
+                if (SCALE) {
+                    if (C2) st4(C2 + (size_t)m * ldc2 + n, x);
+                    x.x *= sc[g].x; x.y *= sc[g].y; x.z *= sc[g].z; x.w *= sc[g].w;
+                }
+                st4(C + (size_t)m * ldc + n, x);
             }
         }
     }
 };
 
-// C[m, n] = tanh(acc + bias[n] + t * S[m, n])   (BasicAcM hidden layer with its skip connection)
-struct EpiBiasAddAct {
-    static constexpr bool kColSum = false;
-    float* C; int ldc; const float* bias; const float* Sk; int lds; float t;
-    __device__ float* colsum_dst() { return nullptr; }
-    template <int NJ>
-    __device__ __forceinline__ void row(int m, const int (&n)[NJ], float (&v)[NJ], int N) {
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-            if (n[j] < N)
-                C[(size_t)m * ldc + n[j]] = tanhf(__fadd_rn(v[j] + bias[n[j]], __fmul_rn(t, Sk[(size_t)m * lds + n[j]])));
-    }
-};
-
-// Backward through an activation: C[m,n] = acc * act'(H[m,n]); column sums -> bias gradient.
+// Backward through an activation: C[m,n] = acc * act'(H[m,n]); column sums -> bias gradient (atomicAdd).
 //   MASK_RELU: act' = (H > 0);  MASK_TANH: act' = 1 - H^2;  MASK_NONE: 1.  ACCUM: C += ...
 enum Mask { MASK_NONE = 0, MASK_RELU = 1, MASK_TANH = 2 };
 template <int MASK, bool COLSUM, bool ACCUM>
 struct EpiMaskStore {
-    static constexpr bool kColSum = COLSUM;
-    float* C; int ldc; const float* H; int ldh; float* colsum; float mul;
-    __device__ float* colsum_dst() { return colsum; }
-    template <int NJ>
-    __device__ __forceinline__ void row(int m, const int (&n)[NJ], float (&v)[NJ], int N) {
+    float* C; int ldc; const float* H; int ldh; float* colsum;
+    template <class Cfg, bool A_KC>
+    __device__ __forceinline__ void apply(float (&acc)[Cfg::MI][Cfg::NJ], int m0, int n0, int M, int N, float* smem) {
+        const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
+        constexpr int G4 = Cfg::NJ / 4;
+        float cs[Cfg::NJ];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            if (n[j] < N) {
-                float x = v[j];
-                if (MASK == MASK_RELU) x = (H[(size_t)m * ldh + n[j]] > 0.f) ? x : 0.f;
-                if (MASK == MASK_TANH) { const float h = H[(size_t)m * ldh + n[j]]; x = x * (1.f - h * h); }
-                if (ACCUM) x += C[(size_t)m * ldc + n[j]];
-                C[(size_t)m * ldc + n[j]] = x;
-                v[j] = x;
-            } else {
-                v[j] = 0.f;
+        for (int j = 0; j < Cfg::NJ; ++j) cs[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < Cfg::MI; ++i) {
+            const int m = m0 + row_of<Cfg, A_KC>(i, ty);
+            if (m >= M) continue;
+            float4 h[G4], old[G4];
+#pragma unroll
+            for (int g = 0; g < G4; ++g) {
+                const int n = n0 + col_of<Cfg>(4 * g, tx);
+                h[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                old[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MASK != MASK_NONE && n < N) h[g] = ld4(H + (size_t)m * ldh + n);
+                if (ACCUM && n < N) old[g] = ld4(C + (size_t)m * ldc + n);
             }
+#pragma unroll
+            for (int g = 0; g < G4; ++g) {
+                const int n = n0 + col_of<Cfg>(4 * g, tx);
+                if (n >= N) continue;
+                float x[4] = {acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]};
+                const float hh[4] = {h[g].x, h[g].y, h[g].z, h[g].w};
+                const float oo[4] = {old[g].x, old[g].y, old[g].z, old[g].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (MASK == MASK_RELU) x[e] = (hh[e] > 0.f) ? x[e] : 0.f;
+                    if (MASK == MASK_TANH) x[e] = x[e] * (1.f - hh[e] * hh[e]);
+                    if (ACCUM) x[e] += oo[e];
+                    if (COLSUM) cs[4 * g + e] += x[e];
+                }
+                st4(C + (size_t)m * ldc + n, make_float4(x[0], x[1], x[2], x[3]));
+            }
+        }
+        if constexpr (COLSUM) {
+            float* red = smem;   // [TY][TN], pipeline is drained
+#pragma unroll
+            for (int j = 0; j < Cfg::NJ; ++j) red[ty * Cfg::TN + col_of<Cfg>(j, tx)] = cs[j];
+            __syncthreads();
+            for (int c = threadIdx.x; c < Cfg::TN; c += kThreads) {
+                float s = 0.f;
+#pragma unroll 4
+                for (int t = 0; t < Cfg::TY; ++t) s += red[t * Cfg::TN + c];
+                if (n0 + c < N) atomicAdd(colsum + n0 + c, s);
+            }
+            __syncthreads();
         }
     }
 };
 
-// torch.optim.Adam (single-tensor CPU form) on one element, optional Polyak blend into a target.
+// torch.optim.Adam (single-tensor CPU form) on one element.
 struct AdamScalars {
     float lr_over_bc1;     // step_size = lr / (1 - beta1^t)
     float bc2_sqrt;        // sqrt(1 - beta2^t)
@@ -272,31 +297,77 @@ __device__ __forceinline__ float adam_element(float w, float g, float& m, float&
     return __fadd_rn(w, __fdiv_rn(__fmul_rn(-s.lr_over_bc1, m), denom));        // addcdiv_: w + (value * m) / denom
 }
 
-// dW tile -> Adam on W (row-major [rows x ld], element (m,n) or transposed (n,m)), moments alongside,
-// optional target blend t = t*(1-tau) + tau*w (SAC.update_target_q / DDPG.update_target_nets).
-template <bool TRANSPOSED, bool POLYAK>
+// dW tile (TN form, thread owns 4x4 blocks) -> Adam.  Element (m, n) of the tile lives at
+//   R[m * ldr + n]  in the "row" copy (moments Mo/Vo use this layout) and at
+//   Cc[n * ldcc + m] in the "column" copy (may be null), with optional Polyak target in column layout:
+//   Tc[n * ldcc + m] = Tc * (1 - tau) + tau * w_new   (SAC.update_target_q / DDPG.update_target_nets);
+//   Tr is the same blend for a target kept in the row layout.
+// For ordinary layers R = natural W [out x in] and Cc = W^T [in x out] (what the forward reads);
+// for the actor heads the tile is computed transposed, so R = W^T and Cc = W.
 struct EpiAdam {
-    static constexpr bool kColSum = false;
-    float* W; float* Mo; float* Vo; float* T; int ld; AdamScalars s; float tau, one_minus_tau;
-    __device__ float* colsum_dst() { return nullptr; }
-    template <int NJ>
-    __device__ __forceinline__ void row(int m, const int (&n)[NJ], float (&g)[NJ], int N) {
-        float w[NJ], mo[NJ], vo[NJ], t[NJ];
-        size_t idx[NJ];
+    float* R; float* Mo; float* Vo; int ldr; float* Cc; float* Tc; float* Tr; int ldcc; AdamScalars s; float tau, one_minus_tau;
+    template <class Cfg, bool A_KC>
+    __device__ __forceinline__ void apply(float (&acc)[Cfg::MI][Cfg::NJ], int m0, int n0, int M, int N, float*) {
+        static_assert(!A_KC, "Adam epilogue expects the dW (TN) mapping");
+        const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            idx[j] = TRANSPOSED ? (size_t)n[j] * ld + m : (size_t)m * ld + n[j];
-            if (n[j] < N) {
-                w[j] = W[idx[j]]; mo[j] = Mo[idx[j]]; vo[j] = Vo[idx[j]];
-                if (POLYAK) t[j] = T[idx[j]];
-            }
-        }
+        for (int i4 = 0; i4 < Cfg::MI / 4; ++i4) {
+            const int mb = m0 + row_of<Cfg, false>(4 * i4, ty);
+            if (mb >= M) continue;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            if (n[j] < N) {
-                const float wn = adam_element(w[j], g[j], mo[j], vo[j], s);
-                W[idx[j]] = wn; Mo[idx[j]] = mo[j]; Vo[idx[j]] = vo[j];
-                if (POLYAK) T[idx[j]] = __fadd_rn(__fmul_rn(t[j], one_minus_tau), __fmul_rn(tau, wn));
+            for (int j4 = 0; j4 < Cfg::NJ / 4; ++j4) {
+                const int nb = n0 + col_of<Cfg>(4 * j4, tx);
+                if (nb >= N) continue;
+                float4 w[4], mo[4], vo[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {   // rows mb..mb+3
+                    const size_t o = (size_t)(mb + r) * ldr + nb;
+                    const bool ok = (mb + r) < M;
+                    w[r] = ok ? ld4(R + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    mo[r] = ok ? ld4(Mo + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vo[r] = ok ? ld4(Vo + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float wn[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float* wm = reinterpret_cast<float*>(&mo[r]);
+                    float* wv = reinterpret_cast<float*>(&vo[r]);
+                    const float* ww = reinterpret_cast<const float*>(&w[r]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) wn[r][e] = adam_element(ww[e], acc[4 * i4 + r][4 * j4 + e], wm[e], wv[e], s);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if ((mb + r) >= M) continue;
+                    const size_t o = (size_t)(mb + r) * ldr + nb;
+                    const float4 nv = make_float4(wn[r][0], wn[r][1], wn[r][2], wn[r][3]);
+                    st4(R + o, nv);
+                    st4(Mo + o, mo[r]);
+                    st4(Vo + o, vo[r]);
+                    if (Tr) {   // Polyak target kept in the row layout (actor heads of DDPG)
+                        const float4 t = ld4(Tr + o);
+                        st4(Tr + o, make_float4(__fadd_rn(__fmul_rn(t.x, one_minus_tau), __fmul_rn(tau, nv.x)),
+                                                __fadd_rn(__fmul_rn(t.y, one_minus_tau), __fmul_rn(tau, nv.y)),
+                                                __fadd_rn(__fmul_rn(t.z, one_minus_tau), __fmul_rn(tau, nv.z)),
+                                                __fadd_rn(__fmul_rn(t.w, one_minus_tau), __fmul_rn(tau, nv.w))));
+                    }
+                }
+                if (Cc) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {   // column copy: 4 consecutive m for column nb + e
+                        if (nb + e >= N) continue;
+                        const size_t o = (size_t)(nb + e) * ldcc + mb;
+                        const float4 nv = make_float4(wn[0][e], wn[1][e], wn[2][e], wn[3][e]);
+                        st4(Cc + o, nv);
+                        if (Tc) {
+                            const float4 t = ld4(Tc + o);
+                            st4(Tc + o, make_float4(__fadd_rn(__fmul_rn(t.x, one_minus_tau), __fmul_rn(tau, nv.x)),
+                                                    __fadd_rn(__fmul_rn(t.y, one_minus_tau), __fmul_rn(tau, nv.y)),
+                                                    __fadd_rn(__fmul_rn(t.z, one_minus_tau), __fmul_rn(tau, nv.z)),
+                                                    __fadd_rn(__fmul_rn(t.w, one_minus_tau), __fmul_rn(tau, nv.w))));
+                        }
+                    }
+                }
             }
         }
     }

@@ -7,7 +7,9 @@
 //
 //   params arena (per agent):  [actor | critic_1 | critic_2 | acm | critic_1_targ | critic_2_targ | actor_targ]
 //   moment arenas m, v       : same offsets, trainable prefix only (actor, critic_1, critic_2, acm)
-// A net is a list of layers; a layer is W [rows x ld] followed by b [rows padded to 4].
+// A net is a list of layers; a layer is W [rows x ld] (natural), W^T [ld x pad4(rows)] (the copy the forward
+// GEMM reads, see gemm_tile.cuh) and b [rows padded to 4].  The fused Adam epilogue keeps both copies in step;
+// target nets are only ever read through W^T (and their fc3 / bias vectors), so Polyak maintains just those.
 #pragma once
 #include <stdint.h>
 
@@ -19,7 +21,9 @@ constexpr int kMaxLayers = 5;
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 
 struct LayerDesc {
-    int off_w;      // float offset of W inside the net
+    int off_w;      // float offset of W [rows x ld] inside the net (natural torch layout; read by dX)
+    int off_wt;     // float offset of W^T [ld x ld_t] (read by the forward); -1 for vector layers (critic fc3, BasicAcM gains)
+    int ld_t;       // pad4(rows)
     int off_b;      // float offset of b inside the net
     int rows;       // out features
     int cols;       // logical in features (of the padded layout: see split)
@@ -84,7 +88,7 @@ struct Layout {
 enum Algo { ALGO_SAC = 0, ALGO_DDPG = 1 };
 enum AcmKind { ACM_MLP = 0, ACM_BASIC = 1 };
 
-inline int add_layer(NetDesc& n, int& off, int rows, int cols, int split) {
+inline int add_layer(NetDesc& n, int& off, int rows, int cols, int split, bool with_transpose = true) {
     LayerDesc& l = n.L[n.n_layers];
     l.rows = rows;
     l.split = split;
@@ -93,6 +97,15 @@ inline int add_layer(NetDesc& n, int& off, int rows, int cols, int split) {
     l.off_w = off;
     off += rows * l.ld;
     off = (off + 31) & ~31;
+    if (with_transpose) {
+        l.ld_t = pad4(rows);
+        l.off_wt = off;
+        off += l.ld * l.ld_t;
+        off = (off + 31) & ~31;
+    } else {
+        l.ld_t = 0;
+        l.off_wt = -1;
+    }
     l.off_b = off;
     off += pad4(rows);
     off = (off + 31) & ~31;
@@ -123,7 +136,7 @@ inline Layout make_layout(int algo, int ob, int ac, int acm_kind, int acm_critic
     off = 0;
     add_layer(L.critic, off, kHidden, ob + L.act_dim, ob);
     add_layer(L.critic, off, kHidden, kHidden, 0);
-    add_layer(L.critic, off, 1, kHidden, 0);
+    add_layer(L.critic, off, 1, kHidden, 0, false);      // fc3 is used as a vector (row-wise head stages)
     L.critic.size = off;
     off = 0;
     // acm: fc1 [hm1 x (ob|ob)], fc2 [hm2 x hm1], fc3 [ac x hm2]; BasicAcM adds fc21 [hm2 x (ob|ob)] and
@@ -133,7 +146,7 @@ inline Layout make_layout(int algo, int ob, int ac, int acm_kind, int acm_critic
     add_layer(L.acm, off, ac, L.hm2, 0);
     if (acm_kind == ACM_BASIC) {
         add_layer(L.acm, off, L.hm2, 2 * ob, ob);
-        add_layer(L.acm, off, 1, 4 + ac, 0);
+        add_layer(L.acm, off, 1, 4 + ac, 0, false);
     }
     L.acm.size = off;
 

@@ -190,8 +190,8 @@ __device__ void update_step(const Ctx& c, int g) {
     __syncthreads();
     for (int i = 0; i < ncrit; ++i) {   // dz1 = (dz2 W2) * relu'(hc1); column sums -> d b1
         const LayerDesc& l = L.critic.L[1];
-        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, c.gvec(GV_CB1_0 + i), 1.f};
-        gemm<BigTile, true, false>(S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, c.gvec(GV_CB1_0 + i)};
+        gemm<BigTile, true>(S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
     }
     __syncthreads();
     for (int i = 0; i < ncrit; ++i) {
@@ -199,13 +199,13 @@ __device__ void update_step(const Ctx& c, int g) {
         const AdamScalars as = c.sm.adam[1 + i];
         {   // fc2.weight: dW2[m,n] = sum_b dz2[b,m] hc1[b,n]
             const LayerDesc& l = L.critic.L[1];
-            EpiAdam<false, true> epi{net + l.off_w, nm + l.off_w, nv + l.off_w, tn + l.off_w, l.ld, as, h.tau, h.one_minus_tau};
-            gemm<BigTile, false, false>(S + L.s.dz2[i], kHidden, S + L.s.hc1[i], kHidden, kHidden, kHidden, B, c.sm.gemm, epi);
+            EpiAdam epi{net + l.off_w, nm + l.off_w, nv + l.off_w, l.ld, net + l.off_wt, tn + l.off_wt, nullptr, l.ld_t, as, h.tau, h.one_minus_tau};
+            gemm<BigTile, false>(S + L.s.dz2[i], kHidden, S + L.s.hc1[i], kHidden, kHidden, kHidden, B, c.sm.gemm, epi);
         }
         {   // fc1.weight: dW1[m,n] = sum_b dz1[b,m] xc[b,n]
             const LayerDesc& l = L.critic.L[0];
-            EpiAdam<false, true> epi{net + l.off_w, nm + l.off_w, nv + l.off_w, tn + l.off_w, l.ld, as, h.tau, h.one_minus_tau};
-            gemm<NarrowTile, false, false>(S + L.s.dz1[i], kHidden, S + L.s.xc, L.ldc, kHidden, L.ldc, B, c.sm.gemm, epi);
+            EpiAdam epi{net + l.off_w, nm + l.off_w, nv + l.off_w, l.ld, net + l.off_wt, tn + l.off_wt, nullptr, l.ld_t, as, h.tau, h.one_minus_tau};
+            gemm<NarrowTile, false>(S + L.s.dz1[i], kHidden, S + L.s.xc, L.ldc, kHidden, L.ldc, B, c.sm.gemm, epi);
             adam_vector(net + l.off_b, nm + l.off_b, nv + l.off_b, tn + l.off_b, c.gvec(GV_CB1_0 + i), kHidden, as, h.tau,
                         h.one_minus_tau, true);
         }
@@ -222,17 +222,17 @@ __device__ void update_step(const Ctx& c, int g) {
     __syncthreads();
     for (int i = 0; i < ncrit; ++i) {
         const LayerDesc& l = L.critic.L[1];
-        EpiMaskStore<MASK_RELU, false, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, nullptr, 1.f};
-        gemm<BigTile, true, false>(S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+        EpiMaskStore<MASK_RELU, false, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, nullptr};
+        gemm<BigTile, true>(S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
     }
     __syncthreads();
     {   // dxc = sum_i dz1[i] W1_i     [B x ldc]
         const LayerDesc& l = L.critic.L[0];
-        EpiMaskStore<MASK_NONE, false, false> e0{S + L.s.dxc, L.ldc, nullptr, 0, nullptr, 1.f};
-        gemm<NarrowTile, true, false>(S + L.s.dz1[0], kHidden, c.net(crit[0]) + l.off_w, l.ld, B, L.ldc, kHidden, c.sm.gemm, e0);
+        EpiMaskStore<MASK_NONE, false, false> e0{S + L.s.dxc, L.ldc, nullptr, 0, nullptr};
+        gemm<NarrowTile, true>(S + L.s.dz1[0], kHidden, c.net(crit[0]) + l.off_w, l.ld, B, L.ldc, kHidden, c.sm.gemm, e0);
         if (ncrit == 2) {
-            EpiMaskStore<MASK_NONE, false, true> e1{S + L.s.dxc, L.ldc, nullptr, 0, nullptr, 1.f};
-            gemm<NarrowTile, true, false>(S + L.s.dz1[1], kHidden, c.net(crit[1]) + l.off_w, l.ld, B, L.ldc, kHidden, c.sm.gemm, e1);
+            EpiMaskStore<MASK_NONE, false, true> e1{S + L.s.dxc, L.ldc, nullptr, 0, nullptr};
+            gemm<NarrowTile, true>(S + L.s.dz1[1], kHidden, c.net(crit[1]) + l.off_w, l.ld, B, L.ldc, kHidden, c.sm.gemm, e1);
         }
     }
     __syncthreads();
@@ -240,14 +240,14 @@ __device__ void update_step(const Ctx& c, int g) {
     stage_actor_head_bwd<ALGO>(c);
     {   // dza2 = (dml Wheads) * relu'(ha2); column sums -> d b2
         const LayerDesc& l = L.actor.L[2];
-        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza2, kHidden, S + L.s.ha2, kHidden, c.gvec(GV_AB2), 1.f};
-        gemm<BigTile, true, false>(S + L.s.dml, L.ldh, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, L.heads, c.sm.gemm, epi);
+        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza2, kHidden, S + L.s.ha2, kHidden, c.gvec(GV_AB2)};
+        gemm<BigTile, true>(S + L.s.dml, L.ldh, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, L.heads, c.sm.gemm, epi);
     }
     __syncthreads();
     {   // dza1 = (dza2 W2) * relu'(ha1); column sums -> d b1
         const LayerDesc& l = L.actor.L[1];
-        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza1, kHidden, S + L.s.ha1, kHidden, c.gvec(GV_AB1), 1.f};
-        gemm<BigTile, true, false>(S + L.s.dza2, kHidden, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza1, kHidden, S + L.s.ha1, kHidden, c.gvec(GV_AB1)};
+        gemm<BigTile, true>(S + L.s.dza2, kHidden, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
     }
     __syncthreads();
     {
@@ -256,17 +256,21 @@ __device__ void update_step(const Ctx& c, int g) {
         const AdamScalars as = c.sm.adam[0];
         constexpr bool PK = (ALGO == ALGO_DDPG);     // DDPG.update_target_nets blends the actor too (ddpg.py:273-284)
         const LayerDesc& l2 = L.actor.L[2]; const LayerDesc& l1 = L.actor.L[1]; const LayerDesc& l0 = L.actor.L[0];
-        {   // heads (transposed tile): dWh[n, m] = sum_b ha2[b, m] dml[b, n]
-            EpiAdam<true, PK> epi{net + l2.off_w, nm + l2.off_w, nv + l2.off_w, PK ? tn + l2.off_w : nullptr, l2.ld, as, h.tau, h.one_minus_tau};
-            gemm<NarrowTile, false, false>(S + L.s.ha2, kHidden, S + L.s.dml, L.ldh, kHidden, L.heads, B, c.sm.gemm, epi);
+        {   // heads, computed transposed: tile[m = hidden unit, n = head row] = sum_b ha2[b, m] dml[b, n];
+            // row copy = W^T (moments live in that layout), column copy = natural W
+            EpiAdam epi{net + l2.off_wt, nm + l2.off_wt, nv + l2.off_wt, l2.ld_t, net + l2.off_w, nullptr,
+                        PK ? tn + l2.off_wt : nullptr, l2.ld, as, h.tau, h.one_minus_tau};
+            gemm<NarrowTile, false>(S + L.s.ha2, kHidden, S + L.s.dml, L.ldh, kHidden, L.heads, B, c.sm.gemm, epi);
         }
         {
-            EpiAdam<false, PK> epi{net + l1.off_w, nm + l1.off_w, nv + l1.off_w, PK ? tn + l1.off_w : nullptr, l1.ld, as, h.tau, h.one_minus_tau};
-            gemm<BigTile, false, false>(S + L.s.dza2, kHidden, S + L.s.ha1, kHidden, kHidden, kHidden, B, c.sm.gemm, epi);
+            EpiAdam epi{net + l1.off_w, nm + l1.off_w, nv + l1.off_w, l1.ld, net + l1.off_wt, PK ? tn + l1.off_wt : nullptr,
+                        nullptr, l1.ld_t, as, h.tau, h.one_minus_tau};
+            gemm<BigTile, false>(S + L.s.dza2, kHidden, S + L.s.ha1, kHidden, kHidden, kHidden, B, c.sm.gemm, epi);
         }
         {
-            EpiAdam<false, PK> epi{net + l0.off_w, nm + l0.off_w, nv + l0.off_w, PK ? tn + l0.off_w : nullptr, l0.ld, as, h.tau, h.one_minus_tau};
-            gemm<NarrowTile, false, false>(S + L.s.dza1, kHidden, S + L.s.xo, L.ldo, kHidden, L.ldo, B, c.sm.gemm, epi);
+            EpiAdam epi{net + l0.off_w, nm + l0.off_w, nv + l0.off_w, l0.ld, net + l0.off_wt, PK ? tn + l0.off_wt : nullptr,
+                        nullptr, l0.ld_t, as, h.tau, h.one_minus_tau};
+            gemm<NarrowTile, false>(S + L.s.dza1, kHidden, S + L.s.xo, L.ldo, kHidden, L.ldo, B, c.sm.gemm, epi);
         }
         adam_vector(net + l2.off_b, nm + l2.off_b, nv + l2.off_b, PK ? tn + l2.off_b : nullptr, c.gvec(GV_MISC), L.heads, as, h.tau, h.one_minus_tau, true);
         adam_vector(net + l1.off_b, nm + l1.off_b, nv + l1.off_b, PK ? tn + l1.off_b : nullptr, c.gvec(GV_AB2), kHidden, as, h.tau, h.one_minus_tau, true);

@@ -124,13 +124,13 @@ __device__ inline void adam_vector(float* W, float* Mo, float* Vo, float* T, con
     }
 }
 
-// ---- forward of one Linear through the tile GEMM
+// ---- forward of one Linear through the tile GEMM: C = act(X W^T + b), reading the transposed weight copy
 template <class Cfg, int ACT, bool SCALE>
 __device__ inline void linear_fwd(const Ctx& c, const float* X, int ldx, int K, const float* net, const LayerDesc& l,
                                   float* C, int ldc, int B, const float* scale = nullptr, float* C2 = nullptr,
                                   int ldc2 = 0) {
-    EpiBiasAct<ACT, SCALE> epi{C, ldc, net + l.off_b, scale, C2, ldc2};
-    gemm<Cfg, true, true>(X, ldx, net + l.off_w, l.ld, B, l.rows, K, c.sm.gemm, epi);
+    EpiBiasAct<ACT, SCALE, false> epi{C, ldc, net + l.off_b, scale, C2, ldc2, nullptr, 0, 0.f};
+    gemm<Cfg, true>(X, ldx, net + l.off_wt, l.ld_t, B, l.rows, K, c.sm.gemm, epi);
 }
 
 // ---- replay gather (warp per row): fills xo, xn, xc=[obs|action], r, notdone*gamma
@@ -253,9 +253,9 @@ __device__ inline void acm_forward(const Ctx& c) {
     if (L.acm_kind == ACM_MLP) {
         linear_fwd<NarrowTile, ACT_TANH, false>(c, S + L.s.xm, L.ldm, L.ldm, acm, L.acm.L[0], S + L.s.hm1, L.ldm1, B);
         __syncthreads();
-        linear_fwd<NarrowTile, ACT_TANH, false>(c, S + L.s.hm1, L.ldm1, L.hm1, acm, L.acm.L[1], S + L.s.hm2, L.ldm2, B);
+        linear_fwd<NarrowTile, ACT_TANH, false>(c, S + L.s.hm1, L.ldm1, L.ldm1, acm, L.acm.L[1], S + L.s.hm2, L.ldm2, B);
         __syncthreads();
-        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.hm2, acm, L.acm.L[2], S + L.s.xcp + L.ldo, L.ldc, B,
+        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.ldm2, acm, L.acm.L[2], S + L.s.xcp + L.ldo, L.ldc, B,
                                                c.a.acm_lim, S + L.s.tm3, L.lda);
         __syncthreads();
     } else {
@@ -266,11 +266,12 @@ __device__ inline void acm_forward(const Ctx& c) {
         // h1 = tanh(fc2 h + t * s)
         {
             const LayerDesc& l = L.acm.L[1];
-            EpiBiasAddAct epi{S + L.s.hm2, L.ldm2, acm + l.off_b, S + L.s.hms, L.ldm2, acm[L.acm.L[4].off_w]};
-            gemm<NarrowTile, true, true>(S + L.s.hm1, L.ldm1, acm + l.off_w, l.ld, B, l.rows, L.hm1, c.sm.gemm, epi);
+            EpiBiasAct<ACT_TANH, false, true> epi{S + L.s.hm2, L.ldm2, acm + l.off_b, nullptr, nullptr, 0,
+                                                  S + L.s.hms, L.ldm2, acm[L.acm.L[4].off_w]};
+            gemm<NarrowTile, true>(S + L.s.hm1, L.ldm1, acm + l.off_wt, l.ld_t, B, l.rows, L.ldm1, c.sm.gemm, epi);
         }
         __syncthreads();
-        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.hm2, acm, L.acm.L[2], S + L.s.xcp + L.ldo, L.ldc, B,
+        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.ldm2, acm, L.acm.L[2], S + L.s.xcp + L.ldo, L.ldc, B,
                                                acm + L.acm.L[4].off_w + 4, S + L.s.tm3, L.lda);
         __syncthreads();
     }
@@ -293,8 +294,8 @@ __device__ inline void acm_backward_dx(const Ctx& c) {
     __syncthreads();
     {   // d2 = (d3 W3) * (1 - h2^2)      [B x hm2], K = ac
         const LayerDesc& l = L.acm.L[2];
-        EpiMaskStore<MASK_TANH, false, false> epi{S + L.s.dm2, L.ldm2, S + L.s.hm2, L.ldm2, nullptr, 1.f};
-        gemm<NarrowTile, true, false>(S + L.s.dm3, L.lda, acm + l.off_w, l.ld, B, L.hm2, ac, c.sm.gemm, epi);
+        EpiMaskStore<MASK_TANH, false, false> epi{S + L.s.dm2, L.ldm2, S + L.s.hm2, L.ldm2, nullptr};
+        gemm<NarrowTile, true>(S + L.s.dm3, L.lda, acm + l.off_w, l.ld, B, L.hm2, ac, c.sm.gemm, epi);
     }
     __syncthreads();
     if (L.acm_kind == ACM_BASIC) {   // ds = d2 * t
@@ -306,18 +307,18 @@ __device__ inline void acm_backward_dx(const Ctx& c) {
     }
     {   // d1 = (d2 W2) * (1 - h1^2)      [B x hm1], K = hm2
         const LayerDesc& l = L.acm.L[1];
-        EpiMaskStore<MASK_TANH, false, false> epi{S + L.s.dm1, L.ldm1, S + L.s.hm1, L.ldm1, nullptr, 1.f};
-        gemm<NarrowTile, true, false>(S + L.s.dm2, L.ldm2, acm + l.off_w, l.ld, B, L.hm1, L.hm2, c.sm.gemm, epi);
+        EpiMaskStore<MASK_TANH, false, false> epi{S + L.s.dm1, L.ldm1, S + L.s.hm1, L.ldm1, nullptr};
+        gemm<NarrowTile, true>(S + L.s.dm2, L.ldm2, acm + l.off_w, l.ld, B, L.hm1, L.hm2, c.sm.gemm, epi);
     }
     __syncthreads();
     {   // dx = d1 W1 (+ ds W21)          [B x ldm], K = hm1
         const LayerDesc& l = L.acm.L[0];
-        EpiMaskStore<MASK_NONE, false, false> epi{S + L.s.dxm, L.ldm, nullptr, 0, nullptr, 1.f};
-        gemm<NarrowTile, true, false>(S + L.s.dm1, L.ldm1, acm + l.off_w, l.ld, B, L.ldm, L.hm1, c.sm.gemm, epi);
+        EpiMaskStore<MASK_NONE, false, false> epi{S + L.s.dxm, L.ldm, nullptr, 0, nullptr};
+        gemm<NarrowTile, true>(S + L.s.dm1, L.ldm1, acm + l.off_w, l.ld, B, L.ldm, L.hm1, c.sm.gemm, epi);
         if (L.acm_kind == ACM_BASIC) {
             const LayerDesc& l2 = L.acm.L[3];
-            EpiMaskStore<MASK_NONE, false, true> epi2{S + L.s.dxm, L.ldm, nullptr, 0, nullptr, 1.f};
-            gemm<NarrowTile, true, false>(S + L.s.dms, L.ldm2, acm + l2.off_w, l2.ld, B, L.ldm, L.hm2, c.sm.gemm, epi2);
+            EpiMaskStore<MASK_NONE, false, true> epi2{S + L.s.dxm, L.ldm, nullptr, 0, nullptr};
+            gemm<NarrowTile, true>(S + L.s.dms, L.ldm2, acm + l2.off_w, l2.ld, B, L.ldm, L.hm2, c.sm.gemm, epi2);
         }
     }
     __syncthreads();
