@@ -22,12 +22,12 @@
 
 namespace spp {
 
-constexpr int TK = 16;                        // contraction chunk per pipeline stage
-constexpr int kStages = 4;
+constexpr int TK = 32;                        // contraction chunk per pipeline stage
+constexpr int kStages = 3;
 constexpr int kPitchKC = TK + 4;              // k-contiguous smem row pitch (conflict-free float4 reads)
 constexpr int kOperandFloats = 128 * kPitchKC;          // largest operand tile (128 rows, k-contig)
-constexpr int kStageFloats = 2 * kOperandFloats;        // A region + B region
-constexpr int kGemmSmemFloats = kStages * kStageFloats; // 20480 floats = 80 KB
+constexpr int kStageFloats = kOperandFloats + TK * 128; // A region + B region (B is always [TK x TN])
+constexpr int kGemmSmemFloats = kStages * kStageFloats; // 26112 floats = 102 KB
 
 template <int TY_, int TX_, int MI_, int NJ_>
 struct TileCfg {
@@ -47,32 +47,46 @@ __device__ __forceinline__ int row_of(int i, int ty) {
 template <class Cfg>
 __device__ __forceinline__ int col_of(int j, int tx) { return (j / 4) * (4 * Cfg::TX) + 4 * tx + (j % 4); }
 
+// Per-thread state of one operand's global->shared copies, computed once per tile: source pointer of chunk 0,
+// destination offset inside a stage, row validity.  issue() only bumps the pointer and tests the k tail.
 template <int ROWS, bool KC>
-__device__ __forceinline__ void load_operand(const float* __restrict__ G, int ld, int R, int K, int r0,
-                                             int k0, float* __restrict__ S) {
-    const int tid = threadIdx.x;
-    if constexpr (KC) {
-        constexpr int NV = ROWS * (TK / 4);
+struct OperandLoader {
+    static constexpr int NV = KC ? ROWS * (TK / 4) : TK * (ROWS / 4);
+    static constexpr int PER = (NV + kThreads - 1) / kThreads;
+    const float* src[PER];
+    const float* base;
+    int dst[PER], kofs[PER], kstride;
+    bool ok[PER];
+    __device__ __forceinline__ void init(const float* __restrict__ G, int ld, int R, int r0) {
+        base = G;
+        kstride = KC ? 1 : ld;
 #pragma unroll
-        for (int c = tid; c < NV; c += kThreads) {
-            const int row = c / (TK / 4), k4 = c % (TK / 4);
-            const int gr = r0 + row, gk = k0 + 4 * k4;
-            const bool ok = (gr < R) && (gk < K);
-            const float* src = ok ? G + (size_t)gr * ld + gk : G;
-            cp_async16(S + row * kPitchKC + 4 * k4, src, ok ? 16 : 0);
-        }
-    } else {
-        constexpr int NV = TK * (ROWS / 4);
-#pragma unroll
-        for (int c = tid; c < NV; c += kThreads) {
-            const int kr = c / (ROWS / 4), r4 = c % (ROWS / 4);
-            const int gk = k0 + kr, gr = r0 + 4 * r4;
-            const bool ok = (gk < K) && (gr < R);
-            const float* src = ok ? G + (size_t)gk * ld + gr : G;
-            cp_async16(S + kr * ROWS + 4 * r4, src, ok ? 16 : 0);
+        for (int p = 0; p < PER; ++p) {
+            const int c = threadIdx.x + p * kThreads;
+            if constexpr (KC) {
+                const int row = c / (TK / 4), k4 = c % (TK / 4);
+                ok[p] = (c < NV) && (r0 + row < R);
+                src[p] = G + (size_t)(r0 + row) * ld + 4 * k4;
+                dst[p] = row * kPitchKC + 4 * k4;
+                kofs[p] = 4 * k4;
+            } else {
+                const int kr = c / (ROWS / 4), r4 = c % (ROWS / 4);
+                ok[p] = (c < NV) && (r0 + 4 * r4 < R);
+                src[p] = G + (size_t)kr * ld + r0 + 4 * r4;
+                dst[p] = kr * ROWS + 4 * r4;
+                kofs[p] = kr;
+            }
         }
     }
-}
+    __device__ __forceinline__ void issue(int k0, int K, float* __restrict__ S) const {
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            if (NV % kThreads != 0 && threadIdx.x + p * kThreads >= NV) continue;
+            const bool v = ok[p] && (k0 + kofs[p] < K);
+            cp_async16(S + dst[p], v ? src[p] + (size_t)k0 * kstride : base, v ? 16 : 0);
+        }
+    }
+};
 
 // One output tile.  Epi interface:
 //   template <class Cfg, bool A_KC> void apply(float (&acc)[MI][NJ], int m0, int n0, int M, int N, float* smem);
@@ -90,31 +104,38 @@ __device__ __noinline__ void gemm_tile(const float* __restrict__ A, int lda, con
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
 
+    OperandLoader<TM, A_KC> la;
+    OperandLoader<TN, false> lb;
+    la.init(A, lda, M, m0);
+    lb.init(B, ldb, N, n0);
     // prologue
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) {
         if (s < nk) {
             float* sA = smem + s * kStageFloats;
-            load_operand<TM, A_KC>(A, lda, M, K, m0, s * TK, sA);
-            load_operand<TN, false>(B, ldb, N, K, n0, s * TK, sA + kOperandFloats);
+            la.issue(s * TK, K, sA);
+            lb.issue(s * TK, K, sA + kOperandFloats);
         }
         cp_async_commit();
     }
 
+    int slot = 0, pslot = kStages - 1;
     for (int kc = 0; kc < nk; ++kc) {
         cp_async_wait<kStages - 2>();
         __syncthreads();
         {   // prefetch chunk kc + kStages - 1 into the slot freed by iteration kc - 1
             const int pf = kc + kStages - 1;
             if (pf < nk) {
-                float* sA = smem + (pf % kStages) * kStageFloats;
-                load_operand<TM, A_KC>(A, lda, M, K, m0, pf * TK, sA);
-                load_operand<TN, false>(B, ldb, N, K, n0, pf * TK, sA + kOperandFloats);
+                float* sP = smem + pslot * kStageFloats;
+                la.issue(pf * TK, K, sP);
+                lb.issue(pf * TK, K, sP + kOperandFloats);
             }
             cp_async_commit();
+            pslot = (pslot + 1 == kStages) ? 0 : pslot + 1;
         }
-        const float* sA = smem + (kc % kStages) * kStageFloats;
+        const float* sA = smem + slot * kStageFloats;
         const float* sB = sA + kOperandFloats;
+        slot = (slot + 1 == kStages) ? 0 : slot + 1;
 #pragma unroll
         for (int k4 = 0; k4 < TK / 4; ++k4) {
             float af[4][MI], bf[4][NJ];
@@ -239,26 +260,31 @@ struct EpiMaskStore {
         float cs[Cfg::NJ];
 #pragma unroll
         for (int j = 0; j < Cfg::NJ; ++j) cs[j] = 0.f;
+        // issue every global load of the tile first (one latency instead of one per row)
+        float4 h[Cfg::MI][G4], old[Cfg::MI][G4];
+#pragma unroll
+        for (int i = 0; i < Cfg::MI; ++i) {
+            const int m = m0 + row_of<Cfg, A_KC>(i, ty);
+#pragma unroll
+            for (int g = 0; g < G4; ++g) {
+                const int n = n0 + col_of<Cfg>(4 * g, tx);
+                h[i][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                old[i][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MASK != MASK_NONE && m < M && n < N) h[i][g] = ld4(H + (size_t)m * ldh + n);
+                if (ACCUM && m < M && n < N) old[i][g] = ld4(C + (size_t)m * ldc + n);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < Cfg::MI; ++i) {
             const int m = m0 + row_of<Cfg, A_KC>(i, ty);
             if (m >= M) continue;
-            float4 h[G4], old[G4];
-#pragma unroll
-            for (int g = 0; g < G4; ++g) {
-                const int n = n0 + col_of<Cfg>(4 * g, tx);
-                h[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                old[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (MASK != MASK_NONE && n < N) h[g] = ld4(H + (size_t)m * ldh + n);
-                if (ACCUM && n < N) old[g] = ld4(C + (size_t)m * ldc + n);
-            }
 #pragma unroll
             for (int g = 0; g < G4; ++g) {
                 const int n = n0 + col_of<Cfg>(4 * g, tx);
                 if (n >= N) continue;
                 float x[4] = {acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]};
-                const float hh[4] = {h[g].x, h[g].y, h[g].z, h[g].w};
-                const float oo[4] = {old[g].x, old[g].y, old[g].z, old[g].w};
+                const float hh[4] = {h[i][g].x, h[i][g].y, h[i][g].z, h[i][g].w};
+                const float oo[4] = {old[i][g].x, old[i][g].y, old[i][g].z, old[i][g].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     if (MASK == MASK_RELU) x[e] = (hh[e] > 0.f) ? x[e] : 0.f;
@@ -290,11 +316,15 @@ struct AdamScalars {
     float lr_over_bc1;     // step_size = lr / (1 - beta1^t)
     float bc2_sqrt;        // sqrt(1 - beta2^t)
 };
+// sqrt and the two divisions use the MUFU approximations (<= 2 ulp): the update term lr*m/(sqrt(v)+eps) then carries
+// ~2e-7 relative error, far inside the 1e-5 parity budget, at a sixth of the instruction count of IEEE div/sqrt.
 __device__ __forceinline__ float adam_element(float w, float g, float& m, float& v, const AdamScalars& s) {
     m = fmaf(0.1f, __fsub_rn(g, m), m);                                   // lerp_(g, 1 - beta1): ATen's vector path is an fma
     v = __fadd_rn(__fmul_rn(v, 0.999f), __fmul_rn(__fmul_rn(0.001f, g), g));   // mul_(beta2).addcmul_(g, g, 1 - beta2)
-    const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), s.bc2_sqrt), 1e-8f);     // (sqrt(v) / sqrt(bc2)).add_(eps)
-    return __fadd_rn(w, __fdiv_rn(__fmul_rn(-s.lr_over_bc1, m), denom));        // addcdiv_: w + (value * m) / denom
+    float sq;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    const float denom = __fadd_rn(__fdividef(sq, s.bc2_sqrt), 1e-8f);          // (sqrt(v) / sqrt(bc2)).add_(eps)
+    return __fadd_rn(w, __fdividef(__fmul_rn(-s.lr_over_bc1, m), denom));       // addcdiv_: w + (value * m) / denom
 }
 
 // dW tile (TN form, thread owns 4x4 blocks) -> Adam.  Element (m, n) of the tile lives at
@@ -318,14 +348,16 @@ struct EpiAdam {
             for (int j4 = 0; j4 < Cfg::NJ / 4; ++j4) {
                 const int nb = n0 + col_of<Cfg>(4 * j4, tx);
                 if (nb >= N) continue;
-                float4 w[4], mo[4], vo[4];
+                float4 w[4], mo[4], vo[4], tc[4], tr[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {   // rows mb..mb+3
+                for (int r = 0; r < 4; ++r) {   // rows mb..mb+3; every global load of the block is issued up front
                     const size_t o = (size_t)(mb + r) * ldr + nb;
                     const bool ok = (mb + r) < M;
                     w[r] = ok ? ld4(R + o) : make_float4(0.f, 0.f, 0.f, 0.f);
                     mo[r] = ok ? ld4(Mo + o) : make_float4(0.f, 0.f, 0.f, 0.f);
                     vo[r] = ok ? ld4(Vo + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    tr[r] = (Tr && ok) ? ld4(Tr + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    tc[r] = (Tc && nb + r < N) ? ld4(Tc + (size_t)(nb + r) * ldcc + mb) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 float wn[4][4];
 #pragma unroll
@@ -345,7 +377,7 @@ struct EpiAdam {
                     st4(Mo + o, mo[r]);
                     st4(Vo + o, vo[r]);
                     if (Tr) {   // Polyak target kept in the row layout (actor heads of DDPG)
-                        const float4 t = ld4(Tr + o);
+                        const float4 t = tr[r];
                         st4(Tr + o, make_float4(__fadd_rn(__fmul_rn(t.x, one_minus_tau), __fmul_rn(tau, nv.x)),
                                                 __fadd_rn(__fmul_rn(t.y, one_minus_tau), __fmul_rn(tau, nv.y)),
                                                 __fadd_rn(__fmul_rn(t.z, one_minus_tau), __fmul_rn(tau, nv.z)),
@@ -360,7 +392,7 @@ struct EpiAdam {
                         const float4 nv = make_float4(wn[0][e], wn[1][e], wn[2][e], wn[3][e]);
                         st4(Cc + o, nv);
                         if (Tc) {
-                            const float4 t = ld4(Tc + o);
+                            const float4 t = tc[e];
                             st4(Tc + o, make_float4(__fadd_rn(__fmul_rn(t.x, one_minus_tau), __fmul_rn(tau, nv.x)),
                                                     __fadd_rn(__fmul_rn(t.y, one_minus_tau), __fmul_rn(tau, nv.y)),
                                                     __fadd_rn(__fmul_rn(t.z, one_minus_tau), __fmul_rn(tau, nv.z)),

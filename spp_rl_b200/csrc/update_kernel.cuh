@@ -337,32 +337,74 @@ __device__ inline void critics_hidden(const Ctx& c, const float* X, const int* n
     __syncthreads();
 }
 
-// q[r] = hc2[i][r,:] . w3 + b3 for one row (whole warp)
-__device__ inline float critic_head_row(const float* h2row, const float* w3, float b3) {
-    float s = 0.f;
+// ---- critic heads.  fc3 is a 256-vector, so q = hc2 . w3 + b3 is done row-wise: each warp takes kRB rows at a
+//      time, issues all of their loads first (kRB x 8 coalesced 128-byte reads per critic), then reduces.
+constexpr int kRB = 4;
+
+struct HeadRows {
+    float h[2][kRB][8];     // hc2 values of this lane: critic i, row rr, column lane + 32 k
+    float q[2][kRB];
+};
+
+__device__ __forceinline__ void head_rows_load(const Ctx& c, int r0, int ncrit, const float (&w3)[2][8], const float (&b3)[2],
+                                               HeadRows& hr) {
+    const Layout& L = c.a.L;
+    const int lane = lane_id();
 #pragma unroll
-    for (int cidx = 0; cidx < kHidden / 32; ++cidx) {
-        const int n = lane_id() + 32 * cidx;
-        s = fmaf(h2row[n], w3[n], s);
+    for (int i = 0; i < 2; ++i) {
+        if (i >= ncrit) break;
+        const float* h2 = c.S + L.s.hc2[i];
+#pragma unroll
+        for (int rr = 0; rr < kRB; ++rr) {
+            const int r = r0 + rr;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hr.h[i][rr][k] = (r < L.B) ? h2[(size_t)r * kHidden + lane + 32 * k] : 0.f;
+        }
     }
-    return warp_sum(s) + b3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (i >= ncrit) break;
+#pragma unroll
+        for (int rr = 0; rr < kRB; ++rr) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = fmaf(hr.h[i][rr][k], w3[i][k], s);
+            hr.q[i][rr] = warp_sum(s) + b3[i];
+        }
+    }
+}
+
+__device__ __forceinline__ void head_weights_load(const Ctx& c, const int* nets, int ncrit, float (&w3)[2][8], float (&b3)[2]) {
+    const Layout& L = c.a.L;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        b3[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w3[i][k] = 0.f;
+        if (i >= ncrit) continue;
+        const float* net = c.net(nets[i]);
+        b3[i] = net[L.critic.L[2].off_b];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w3[i][k] = net[L.critic.L[2].off_w + lane_id() + 32 * k];
+    }
 }
 
 // ---- Q target: y = r + gamma*(1-done) * (min_i q_i^targ - alpha*logp')      (SAC) / (q^targ) (DDPG)
 __device__ inline void stage_qtarget(const Ctx& c, const int* tnets, int ncrit) {
     const Layout& L = c.a.L;
-    const float* S = c.S;
     float* y = c.vec(VEC_Y);
     const float* vr = c.vec(VEC_R); const float* vnd = c.vec(VEC_ND); const float* lpn = c.vec(VEC_LOGPN);
-    for (int r = warp_id(); r < L.B; r += kWarps) {
-        float q = 0.f;
-        for (int i = 0; i < ncrit; ++i) {
-            const float* net = c.net(tnets[i]);
-            const float qi = critic_head_row(S + L.s.hc2[i] + (size_t)r * kHidden, net + L.critic.L[2].off_w,
-                                             net[L.critic.L[2].off_b]);
-            q = (i == 0) ? qi : fminf(q, qi);
-        }
-        if (lane_id() == 0) {
+    float w3[2][8], b3[2];
+    head_weights_load(c, tnets, ncrit, w3, b3);
+    HeadRows hr;
+    for (int r0 = warp_id() * kRB; r0 < L.B; r0 += kWarps * kRB) {
+        head_rows_load(c, r0, ncrit, w3, b3, hr);
+        if (lane_id() < kRB && r0 + lane_id() < L.B) {
+            const int r = r0 + lane_id();
+            float q = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < kRB; ++rr)
+                if (rr == lane_id()) q = (ncrit == 2) ? fminf(hr.q[0][rr], hr.q[1][rr]) : hr.q[0][rr];
             float inner = q;
             if (L.algo == ALGO_SAC) inner = __fsub_rn(q, __fmul_rn(c.sm.alpha, lpn[r]));
             y[r] = __fadd_rn(vr[r], __fmul_rn(vnd[r], inner));
@@ -385,46 +427,52 @@ __device__ inline void stage_critic_head_bwd(const Ctx& c, const int* nets, cons
     for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int k = 0; k < 8; ++k) { acc_w3[i][k] = 0.f; acc_b2[i][k] = 0.f; }
-    for (int r = warp; r < B; r += kWarps) {
-        float q[2] = {0.f, 0.f};
-        for (int i = 0; i < ncrit; ++i) {
-            const float* net = c.net(nets[i]);
-            q[i] = critic_head_row(S + L.s.hc2[i] + (size_t)r * kHidden, net + L.critic.L[2].off_w, net[L.critic.L[2].off_b]);
-        }
-        float dq[2];
-        if (MODE == 0) {
-            for (int i = 0; i < ncrit; ++i) {
-                const float diff = __fsub_rn(q[i], y[r]);
-                dq[i] = __fmul_rn(norm2, diff);
-                lsum[i] += (lane == 0) ? diff * diff : 0.f;
-            }
-        } else {
-            const float gq = -invB;
-            if (ncrit == 2) {
-                const float tie = (q[0] == q[1]) ? 0.5f * gq : 0.f;
-                dq[0] = (q[0] < q[1] ? gq : 0.f) + tie;
-                dq[1] = (q[1] < q[0] ? gq : 0.f) + tie;
-                const float qm = fminf(q[0], q[1]);
-                lsum[0] += (lane == 0) ? (L.algo == ALGO_SAC ? __fsub_rn(__fmul_rn(c.sm.alpha, lp[r]), qm) : -qm) : 0.f;
-            } else {
-                dq[0] = gq;
-                lsum[0] += (lane == 0) ? -q[0] : 0.f;
-            }
-        }
-        for (int i = 0; i < ncrit; ++i) {
-            const float* net = c.net(nets[i]);
-            const float* w3 = net + L.critic.L[2].off_w;
-            const float* h2 = S + L.s.hc2[i] + (size_t)r * kHidden;
-            float* dz2 = S + L.s.dz2[i] + (size_t)r * kHidden;
+    float w3[2][8], b3[2];
+    head_weights_load(c, nets, ncrit, w3, b3);
+    HeadRows hr;
+    for (int r0 = warp * kRB; r0 < B; r0 += kWarps * kRB) {
+        head_rows_load(c, r0, ncrit, w3, b3, hr);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int n = lane + 32 * k;
-                const float h = h2[n];
-                const float dz = (h > 0.f) ? __fmul_rn(dq[i], w3[n]) : 0.f;
-                dz2[n] = dz;
-                if (MODE == 0) { acc_w3[i][k] = fmaf(dq[i], h, acc_w3[i][k]); acc_b2[i][k] += dz; }
+        for (int rr = 0; rr < kRB; ++rr) {
+            const int r = r0 + rr;
+            if (r >= B) break;
+            float dq[2] = {0.f, 0.f};
+            if (MODE == 0) {
+                const float yr = y[r];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i >= ncrit) break;
+                    const float diff = __fsub_rn(hr.q[i][rr], yr);
+                    dq[i] = __fmul_rn(norm2, diff);
+                    lsum[i] += (lane == 0) ? diff * diff : 0.f;
+                }
+            } else {
+                const float gq = -invB;
+                if (ncrit == 2) {
+                    const float q0 = hr.q[0][rr], q1 = hr.q[1][rr];
+                    const float tie = (q0 == q1) ? 0.5f * gq : 0.f;
+                    dq[0] = (q0 < q1 ? gq : 0.f) + tie;
+                    dq[1] = (q1 < q0 ? gq : 0.f) + tie;
+                    const float qm = fminf(q0, q1);
+                    lsum[0] += (lane == 0) ? (L.algo == ALGO_SAC ? __fsub_rn(__fmul_rn(c.sm.alpha, lp[r]), qm) : -qm) : 0.f;
+                } else {
+                    dq[0] = gq;
+                    lsum[0] += (lane == 0) ? -hr.q[0][rr] : 0.f;
+                }
             }
-            if (MODE == 0) acc_b3[i] += dq[i];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i >= ncrit) break;
+                float* dz2 = S + L.s.dz2[i] + (size_t)r * kHidden;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float h = hr.h[i][rr][k];
+                    const float dz = (h > 0.f) ? __fmul_rn(dq[i], w3[i][k]) : 0.f;
+                    dz2[lane + 32 * k] = dz;
+                    if (MODE == 0) { acc_w3[i][k] = fmaf(dq[i], h, acc_w3[i][k]); acc_b2[i][k] += dz; }
+                }
+                if (MODE == 0) acc_b3[i] += dq[i];
+            }
         }
     }
     // losses
