@@ -82,7 +82,7 @@ def load_library(path: str = None):
     global _lib
     if _lib is not None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("SPP_RL_B200_LIB") or LIB_PATH      # env override: A/B-testing kernel builds
     if not os.path.exists(path):
         raise SppError("%s not found: build it with `python __graft_entry__.py` (there is no CPU fallback)" % path)
     lib = C.CDLL(path)

@@ -20,8 +20,13 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef SPP_K4_UNROLL
+#define SPP_K4_UNROLL 4      // k-steps of 4 unrolled per loop body (1/2/4/8 measured within 3% of each other; 4 was best)
+#endif
+
 namespace spp {
 
+constexpr int kK4Unroll = SPP_K4_UNROLL;
 constexpr int TK = 32;                        // contraction chunk per pipeline stage
 constexpr int kStages = 3;
 constexpr int kPitchKC = TK + 4;              // k-contiguous smem row pitch (conflict-free float4 reads)
@@ -136,7 +141,7 @@ __device__ __noinline__ void gemm_tile(const float* __restrict__ A, int lda, con
         const float* sA = smem + slot * kStageFloats;
         const float* sB = sA + kOperandFloats;
         slot = (slot + 1 == kStages) ? 0 : slot + 1;
-#pragma unroll
+#pragma unroll kK4Unroll
         for (int k4 = 0; k4 < TK / 4; ++k4) {
             float af[4][MI], bf[4][NJ];
             if constexpr (A_KC) {
