@@ -130,6 +130,15 @@ int spp_update_ring(spp_population* p, int grad_steps, const int64_t* idx, const
 /* Fully device-resident form (no host traffic): device sampler + device noise; losses_dev may be NULL. */
 int spp_update_ring_device(spp_population* p, int grad_steps, uint64_t seed, float* losses_dev, void* stream);
 
+/* ---- ACM regression: AcMTrainer.update_acm_batches (rltoolkit/acm/acm.py:356-372), n_batches x
+ *      [rbuffer_sample_acm (rltoolkit/buffer/replay_buffer.py:404-430) -> acm_cat (acm.py:260-264) ->
+ *      batch_update (acm.py:246-258)] in one launch; Adam(acm_lr) on the ACM (AcM or BasicAcM incl. t, t1).
+ * Host form = batch_update(x, y): x [P][n][acm_batch_size][2 ob] = cat[obs, next_obs], y [P][n][acm_batch_size][ac].
+ * Ring form: idx int64 [P][n][acm_batch_size] host indices (np.random.randint stays with the caller), NULL ->
+ * device sampler.  losses [P][n] = the MSE of each step (may be NULL).  Only acm_ob_idx = all observations. */
+int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, float* losses);
+int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, uint64_t seed, float* losses);
+
 /* ---- introspection for tests ------------------------------------------------------------------ */
 /* copy a named scratch buffer of agent a to host ("xo","xn","xc","xcp","xm","ha1","ha2","ml","hc1_0",...);
  * rows/ld describe the returned dense [rows x ld] block. */

@@ -14,6 +14,7 @@
 
 namespace spp {
 cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream);
+cudaError_t launch_acm_train(const UpdateArgs& a, int grid, cudaStream_t stream);
 }
 
 using namespace spp;
@@ -55,7 +56,9 @@ struct spp_population {
     spp_config cfg;
     int P = 0, device = 0, sm_count = 0;
     Layout L;
+    Layout L_acm;               // same nets, scratch sized for acm_batch_size (ACM regression bursts)
     Hyper h;
+    float* scratch_acm = nullptr;
     float *params = nullptr, *mom_m = nullptr, *mom_v = nullptr, *scratch = nullptr, *norm = nullptr, *acm_lim = nullptr;
     int* steps = nullptr;
     double* alpha_state = nullptr;
@@ -147,7 +150,7 @@ int spp_population_destroy(spp_population* p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (void* q : {(void*)p->params, (void*)p->mom_m, (void*)p->mom_v, (void*)p->scratch, (void*)p->norm, (void*)p->acm_lim,
                     (void*)p->steps, (void*)p->alpha_state, (void*)p->r_obs, (void*)p->r_act, (void*)p->r_rew, (void*)p->r_aacm,
-                    (void*)p->r_oidx, (void*)p->r_nidx, (void*)p->r_done, (void*)p->r_end, (void*)p->r_len})
+                    (void*)p->r_oidx, (void*)p->r_nidx, (void*)p->r_done, (void*)p->r_end, (void*)p->r_len, (void*)p->scratch_acm})
         if (q) cudaFree(q);
     for (DevBuf* b : {&p->d_obs, &p->d_nobs, &p->d_act, &p->d_rew, &p->d_done, &p->d_aacm, &p->d_eps, &p->d_idx, &p->d_losses, &p->d_tmp})
         b->release();
@@ -161,6 +164,7 @@ int spp_population_create(const spp_config* cfg, int population, int device, spp
     if (cfg->ob_dim < 1 || cfg->ob_dim > 128 || cfg->ac_dim < 1 || cfg->ac_dim > 32)
         return fail(SPP_ERR_ARG, "spp_population_create: ob_dim must be in [1,128], ac_dim in [1,32]");
     if (cfg->update_batch_size < 1 || cfg->update_batch_size > 4096) return fail(SPP_ERR_ARG, "update_batch_size must be in [1,4096]");
+    if (cfg->acm_batch_size < 0 || cfg->acm_batch_size > 4096) return fail(SPP_ERR_ARG, "acm_batch_size must be in [0,4096]");
     if (cfg->algo != SPP_ALGO_SAC && cfg->algo != SPP_ALGO_DDPG) return fail(SPP_ERR_ARG, "unknown algo");
     if (cfg->acm_kind != SPP_ACM_MLP && cfg->acm_kind != SPP_ACM_BASIC) return fail(SPP_ERR_ARG, "unknown acm_kind");
     if (!cfg->acm_critic && !cfg->store_actions && cfg->buffer_size > 0)
@@ -179,7 +183,9 @@ int spp_population_create(const spp_config* cfg, int population, int device, spp
     Hyper& h = p->h;
     h.gamma = (float)cfg->gamma; h.tau = (float)cfg->tau; h.one_minus_tau = (float)(1.0 - cfg->tau);
     h.custom_loss = (float)cfg->custom_loss; h.target_entropy = (float)cfg->target_entropy;
-    h.actor_lr = cfg->actor_lr; h.critic_lr = cfg->critic_lr; h.alpha_lr = cfg->alpha_lr;
+    h.actor_lr = cfg->actor_lr; h.critic_lr = cfg->critic_lr; h.alpha_lr = cfg->alpha_lr; h.acm_lr = cfg->acm_lr;
+    p->L_acm = make_layout(cfg->algo, cfg->ob_dim, cfg->ac_dim, cfg->acm_kind, cfg->acm_critic ? 1 : 0,
+                           cfg->acm_batch_size > 0 ? cfg->acm_batch_size : 128);
     h.norm_closs = cfg->norm_closs ? 1 : 0; h.norm_clamp = cfg->min_max_denormalize ? 0 : 1;
     build_tensor_maps(p);
     const Layout& L = p->L;
@@ -202,6 +208,7 @@ int spp_population_create(const spp_config* cfg, int population, int device, spp
     ALLOC(p->mom_m, P * L.train_size * sizeof(float));
     ALLOC(p->mom_v, P * L.train_size * sizeof(float));
     ALLOC(p->scratch, P * L.s.size * sizeof(float));
+    ALLOC(p->scratch_acm, P * p->L_acm.s.size * sizeof(float));
     ALLOC(p->norm, P * NORM_COUNT * L.ldo * sizeof(float));
     ALLOC(p->acm_lim, 32 * sizeof(float));
     ALLOC(p->steps, P * 4 * sizeof(int));
@@ -688,6 +695,68 @@ int spp_update_ring_device(spp_population* p, int G, uint64_t seed, float* losse
     a.losses = losses_dev;
     CK(launch_update_burst(a, grid_for(p), stream ? (cudaStream_t)stream : p->stream));
     g_launches++;
+    return SPP_OK;
+}
+
+// ---- ACM regression bursts --------------------------------------------------------------------------
+static void fill_acm_args(spp_population* p, UpdateArgs& a, int n) {
+    fill_args(p, a, n);
+    a.L = p->L_acm;
+    a.scratch = p->scratch_acm;
+}
+
+int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, float* losses) {
+    if (!p || !x || !y) return fail(SPP_ERR_ARG, "spp_acm_update_host: null argument");
+    if (n_batches < 1) return fail(SPP_ERR_ARG, "n_batches must be positive");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L_acm;
+    const size_t rows = (size_t)p->P * n_batches * L.B;
+    cudaStream_t s = p->stream;
+    CK(p->d_obs.ensure(rows * 2 * L.ob * 4)); CK(p->d_aacm.ensure(rows * L.ac * 4));
+    CK(cudaMemcpyAsync(p->d_obs.p, x, rows * 2 * L.ob * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->d_aacm.p, y, rows * L.ac * 4, cudaMemcpyHostToDevice, s));
+    CK(p->d_losses.ensure((size_t)p->P * n_batches * 4));
+    UpdateArgs a;
+    fill_acm_args(p, a, n_batches);
+    a.batch.acm_x = (const float*)p->d_obs.p;
+    a.batch.acm_y = (const float*)p->d_aacm.p;
+    a.losses = (float*)p->d_losses.p;
+    CK(launch_acm_train(a, grid_for(p), s));
+    g_launches++;
+    if (losses) CK(cudaMemcpyAsync(losses, p->d_losses.p, (size_t)p->P * n_batches * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SPP_OK;
+}
+
+int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, uint64_t seed, float* losses) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    if (p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
+    if (n_batches < 1) return fail(SPP_ERR_ARG, "n_batches must be positive");
+    CK(cudaSetDevice(p->device));
+    const Layout& L = p->L_acm;
+    const size_t per = (size_t)n_batches * L.B, rows = (size_t)p->P * per;
+    for (int a = 0; a < p->P; ++a)
+        if (p->cur_len[a] < 1) return fail(SPP_ERR_STATE, "replay ring is empty");
+    cudaStream_t s = p->stream;
+    if (idx) {
+        for (int a = 0; a < p->P; ++a)
+            for (size_t k = 0; k < per; ++k)
+                if (idx[(size_t)a * per + k] < 0 || idx[(size_t)a * per + k] >= p->cur_len[a])
+                    return fail(SPP_ERR_ARG, "sample index outside [0, len(buffer))");
+        CK(p->d_idx.ensure(rows * sizeof(int64_t)));
+        CK(cudaMemcpyAsync(p->d_idx.p, idx, rows * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    }
+    int rc = push_ring_len(p); if (rc) return rc;
+    CK(p->d_losses.ensure((size_t)p->P * n_batches * 4));
+    UpdateArgs a;
+    fill_acm_args(p, a, n_batches);
+    a.idx = idx ? (const int64_t*)p->d_idx.p : nullptr;
+    a.seed = seed;
+    a.losses = (float*)p->d_losses.p;
+    CK(launch_acm_train(a, grid_for(p), s));
+    g_launches++;
+    if (losses) CK(cudaMemcpyAsync(losses, p->d_losses.p, (size_t)p->P * n_batches * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return SPP_OK;
 }
 

@@ -57,6 +57,7 @@ struct ScratchDesc {
     int dz2[2], dz1[2];     // [B x 256]   critic backward
     int hm1, hm2, hms;      // ACM hidden 1 / hidden 2 / BasicAcM skip pre-activation (fc21 x)
     int tm3;                // [B x lda]   ACM tanh(fc3) before the limit scale
+    int ya, pa;             // [B x lda]   ACM training: regression target (actions_acm), prediction / d t1 terms
     int dm3, dm2, dm1, dms; // ACM backward
     int dxc;                // [B x ldc]   d loss / d critic input (policy pass)
     int dxm;                // [B x ldm]   d loss / d ACM input
@@ -174,6 +175,8 @@ inline Layout make_layout(int algo, int ob, int ac, int acm_kind, int acm_critic
     for (int i = 0; i < 2; ++i) { s.dz2[i] = take(Bp * kHidden); s.dz1[i] = take(Bp * kHidden); }
     s.hm1 = take(Bp * L.ldm1); s.hm2 = take(Bp * L.ldm2); s.hms = take(Bp * L.ldm2);
     s.tm3 = take(Bp * L.lda);
+    s.ya = take(Bp * L.lda);
+    s.pa = take(Bp * L.lda);
     s.dm3 = take(Bp * L.lda); s.dm2 = take(Bp * L.ldm2); s.dm1 = take(Bp * L.ldm1); s.dms = take(Bp * L.ldm2);
     s.dxc = take(Bp * L.ldc); s.dxm = take(Bp * L.ldm); s.dml = take(Bp * L.ldh);
     s.dza2 = take(Bp * kHidden); s.dza1 = take(Bp * kHidden);

@@ -179,7 +179,7 @@ __device__ void update_step(const Ctx& c, int g) {
     actor_forward<ALGO>(c, S + L.s.xn, ALGO == ALGO_SAC ? NET_ACTOR : NET_ACTOR_TARG);
     if (ALGO == ALGO_SAC) stage_sample(c, g, 0); else stage_ddpg_post(c, 0);
     __syncthreads();
-    if (L.acm_critic) acm_forward(c);
+    if (L.acm_critic) acm_forward(c, S + L.s.xcp + L.ldo, L.ldc);
     critics_hidden(c, S + L.s.xcp, tcrit, ncrit);
     stage_qtarget(c, tcrit, ncrit);
     __syncthreads();
@@ -216,7 +216,7 @@ __device__ void update_step(const Ctx& c, int g) {
     actor_forward<ALGO>(c, S + L.s.xo, NET_ACTOR);
     if (ALGO == ALGO_SAC) stage_sample(c, g, 1); else stage_ddpg_post(c, 1);
     __syncthreads();
-    if (L.acm_critic) acm_forward(c);
+    if (L.acm_critic) acm_forward(c, S + L.s.xcp + L.ldo, L.ldc);
     critics_hidden(c, S + L.s.xcp, crit, ncrit);
     stage_critic_head_bwd<1>(c, crit, tcrit, ncrit, ls + LOSS_PI);
     __syncthreads();

@@ -30,11 +30,13 @@ struct BatchPtrs {
     const float* rew;        // [P][G][B]
     const int8_t* done;      // [P][G][B]
     const float* aacm;       // [P][G][B][ac]
+    const float* acm_x;      // [P][G][Bacm][2 ob]  ACM regression inputs cat[obs, next_obs]   (acm training only)
+    const float* acm_y;      // [P][G][Bacm][ac]    ACM regression targets
 };
 
 struct Hyper {
     float gamma, tau, one_minus_tau, custom_loss, target_entropy;
-    double actor_lr, critic_lr, alpha_lr;
+    double actor_lr, critic_lr, alpha_lr, acm_lr;
     int norm_closs;          // custom loss in normalised space (MSE(z, normalize(next_obs)))
     int norm_clamp;          // mean-std normalize clamps to +-10 (utils.standardize_and_clip)
 };
@@ -244,8 +246,8 @@ __device__ inline void stage_ddpg_post(const Ctx& c, int pass) {
 }
 
 // ---- ACM forward (AcM: tanh-tanh-tanh*lim; BasicAcM: skip connection and learnable gains).  Writes the action
-//      into the action block of xcp and keeps tanh(fc3) in tm3 for the backward.
-__device__ inline void acm_forward(const Ctx& c) {
+//      to `out` (the action block of xcp in the update step) and keeps tanh(fc3) in tm3 for the backward.
+__device__ inline void acm_forward(const Ctx& c, float* out, int ldout) {
     const Layout& L = c.a.L;
     const float* acm = c.net(NET_ACM);
     float* S = c.S;
@@ -255,7 +257,7 @@ __device__ inline void acm_forward(const Ctx& c) {
         __syncthreads();
         linear_fwd<NarrowTile, ACT_TANH, false>(c, S + L.s.hm1, L.ldm1, L.ldm1, acm, L.acm.L[1], S + L.s.hm2, L.ldm2, B);
         __syncthreads();
-        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.ldm2, acm, L.acm.L[2], S + L.s.xcp + L.ldo, L.ldc, B,
+        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.ldm2, acm, L.acm.L[2], out, ldout, B,
                                                c.a.acm_lim, S + L.s.tm3, L.lda);
         __syncthreads();
     } else {
@@ -271,7 +273,7 @@ __device__ inline void acm_forward(const Ctx& c) {
             gemm<NarrowTile, true>(S + L.s.hm1, L.ldm1, acm + l.off_wt, l.ld_t, B, l.rows, L.ldm1, c.sm.gemm, epi);
         }
         __syncthreads();
-        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.ldm2, acm, L.acm.L[2], S + L.s.xcp + L.ldo, L.ldc, B,
+        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.hm2, L.ldm2, L.ldm2, acm, L.acm.L[2], out, ldout, B,
                                                acm + L.acm.L[4].off_w + 4, S + L.s.tm3, L.lda);
         __syncthreads();
     }

@@ -216,6 +216,21 @@ class Population:
     def update_ring_device(self, grad_steps, seed=0, losses_dev_ptr=None, stream=None):
         check(self.lib.spp_update_ring_device(self.h, int(grad_steps), int(seed), losses_dev_ptr, stream))
 
+    # ------------------------------------------------------------------ ACM regression
+    def acm_update_host(self, n_batches, x, y, losses=None):
+        """n x AcMTrainer.batch_update(x, y): x [P, n, acm_batch_size, 2*ob], y [P, n, acm_batch_size, ac] -> losses [P, n]"""
+        if losses is None:
+            losses = np.empty((self.P, n_batches), np.float32)
+        check(self.lib.spp_acm_update_host(self.h, int(n_batches), _ptr(x, C.c_float), _ptr(y, C.c_float), _ptr(losses, C.c_float)))
+        return losses
+
+    def acm_update_ring(self, n_batches, idx=None, seed=0, losses=None):
+        """AcMTrainer.update_acm_batches(n) from the device ring; idx int64 [P, n, acm_batch_size] or None."""
+        if losses is None:
+            losses = np.empty((self.P, n_batches), np.float32)
+        check(self.lib.spp_acm_update_ring(self.h, int(n_batches), _ptr(idx, C.c_int64), int(seed), _ptr(losses, C.c_float)))
+        return losses
+
     # ------------------------------------------------------------------ introspection
     def debug_scratch(self, agent, name):
         cap = 4096 * 512

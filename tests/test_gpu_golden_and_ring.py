@@ -167,3 +167,70 @@ def test_full_size_properties():
     for k, v in ref_acm.items():
         assert np.array_equal(sd4["acm"][k], v)                               # the ACM is frozen during update()
     assert l4[0, -1, 0] != l4[0, 0, 0]                                        # and the critics did move
+
+
+@pytest.mark.parametrize("kind", ["acm", "basic"])
+def test_acm_regression_matches_reference_fixture(kind):
+    """AcMTrainer.batch_update x3 (rltoolkit/acm/acm.py:246-258) incl. BasicAcM's learnable gains t, t1."""
+    g = np.load(os.path.join(G, "acm_regress.npz"))
+    ob, ac, P, n, Bm = 17, 6, 2, 3, 100
+    pop = Population(algo="ddpg", ob_dim=ob, ac_dim=ac, population=P, acm_kind=kind, acm_batch_size=Bm, acm_lr=1e-3,
+                     update_batch_size=64)
+    s0 = init_state("ddpg", ob, ac, 7, kind, True)
+    if kind == "basic":
+        s0["acm.t"][:] = 0.7
+        s0["acm.t1"][:] = np.linspace(0.5, 1.5, ac)
+    pop.load_state_dict("acm", {k[4:]: v for k, v in s0.items() if k.startswith("acm.")}, agent=-1)
+    rng = np.random.RandomState(11)
+    xs, ys = [], []
+    for _ in range(n):
+        xs.append(rng.randn(Bm, 2 * ob).astype(np.float32)); ys.append(np.tanh(rng.randn(Bm, ac)).astype(np.float32))
+    x = np.ascontiguousarray(np.broadcast_to(np.stack(xs), (P, n, Bm, 2 * ob)))
+    y = np.ascontiguousarray(np.broadcast_to(np.stack(ys), (P, n, Bm, ac)))
+    losses = pop.acm_update_host(n, x, y)
+    for a in range(P):
+        for i in range(n):
+            assert losses[a, i] == pytest.approx(float(g[kind + ":losses"][i]), rel=1e-5)
+        sd = pop.state_dict("acm", agent=a)
+        ad, step = pop.adam_state("acm", agent=a)
+        assert step == n
+        for k, v in sd.items():
+            lim = 1e-4 if v.size <= 16 else 1e-5
+            assert relnorm(v, g[kind + ":acm." + k]) < lim, (k, relnorm(v, g[kind + ":acm." + k]))
+            assert relnorm(ad[k][0], g[kind + ":acm." + k + "#m"]) < lim, k
+            assert relnorm(ad[k][1], g[kind + ":acm." + k + "#v"]) < lim, k
+    pop.close()
+
+
+def test_acm_ring_regression_equals_host_form():
+    """update_acm_batches from the device ring (rbuffer_sample_acm + acm_cat) == batch_update on the gathered rows."""
+    ob, ac, P, n, Bm = 11, 3, 2, 2, 64
+    rng = np.random.RandomState(21)
+
+    def fresh():
+        pop = Population(algo="sac", ob_dim=ob, ac_dim=ac, population=P, acm_batch_size=Bm, acm_lr=3e-3, buffer_size=300,
+                         update_batch_size=64)
+        for a in range(P):
+            s0 = init_state("sac", ob, ac, 60 + a)
+            pop.load_state_dict("acm", {k[4:]: v for k, v in s0.items() if k.startswith("acm.")}, agent=a)
+        return pop
+    pa, pb = fresh(), fresh()
+    for a in range(P):
+        prev = pa.ring_add_obs(a, rng.randn(ob).astype(np.float32))
+        for t in range(200):
+            pa.ring_add_acm_action(a, np.tanh(rng.randn(ac)).astype(np.float32))
+            nxt = pa.ring_add_obs(a, rng.randn(ob).astype(np.float32))
+            pa.ring_add_timestep(a, prev, nxt, rng.randn(ob).astype(np.float32), 0.0, False, False)
+            prev = nxt
+    idx = rng.randint(0, 200, size=(P, n, Bm)).astype(np.int64)
+    l_ring = pa.acm_update_ring(n, idx=idx)
+    rows = [pa.ring_sample_batch(a, idx[a].reshape(-1)) for a in range(P)]
+    x = np.stack([np.concatenate([r[0], r[1]], axis=1).reshape(n, Bm, 2 * ob) for r in rows])
+    y = np.stack([r[5].reshape(n, Bm, ac) for r in rows])
+    l_host = pb.acm_update_host(n, np.ascontiguousarray(x), np.ascontiguousarray(y))
+    assert np.array_equal(l_ring, l_host)
+    for a in range(P):
+        sa, sb = pa.state_dict("acm", a), pb.state_dict("acm", a)
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), (a, k)
+    pa.close(); pb.close()
