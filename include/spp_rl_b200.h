@@ -139,6 +139,20 @@ int spp_update_ring_device(spp_population* p, int grad_steps, uint64_t seed, flo
 int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, float* losses);
 int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, uint64_t seed, float* losses);
 
+/* ---- rollout step: body of DDPG.collect_batch_and_train (rltoolkit/algorithms/ddpg/ddpg.py:202-207) =
+ *      replay_buffer.normalize (obs_norm gate) -> AcMOffPolicy.initial_act (random phase,
+ *      rltoolkit/acm/off_policy/off_policy.py:50-54) | DDPG_AcM.noise_action (rltoolkit/acm/off_policy/ddpg_acm.py:40-50)
+ *      -> AcMOffPolicy.process_action (off_policy.py:89-106), for E observations per agent at once.
+ * obs, noise (torch.randn of the reference), eps (the SAC actor's rsample draw; NULL = deterministic mean, as test()
+ * uses it) are [P][E][ob]; out_target [P][E][ob] is the state target stored in the ring, out_action [P][E][ac] the
+ * ACM action for the environment. */
+int spp_rollout_step_host(spp_population* p, int E, const float* obs, const float* noise, const float* eps, int random_phase,
+                          double act_noise, int obs_norm, int denormalize_actor_out, float* out_target, float* out_action);
+/* Device-resident rollout of a synthetic environment (MuJoCo is unavailable offline): `steps` consecutive vectorised
+ * steps of E environments per agent, everything of the frame loop except the simulator -- actor, noise, clip,
+ * denormalise, ACM, and the ring writes (obs row, timestep row, acm action, reward, done) -- in one launch. */
+int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t seed, double act_noise, void* stream);
+
 /* ---- introspection for tests ------------------------------------------------------------------ */
 /* copy a named scratch buffer of agent a to host ("xo","xn","xc","xcp","xm","ha1","ha2","ml","hc1_0",...);
  * rows/ld describe the returned dense [rows x ld] block. */

@@ -71,6 +71,8 @@ SIGNATURES = {
     "spp_update_ring_device": (C.c_int, [_vp, C.c_int, C.c_uint64, _vp, _vp]),
     "spp_acm_update_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p]),
     "spp_acm_update_ring": (C.c_int, [_vp, C.c_int, _i64p, C.c_uint64, _f32p]),
+    "spp_rollout_step_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_double, C.c_int, C.c_int, _f32p, _f32p]),
+    "spp_rollout_synthetic_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_double, _vp]),
     "spp_debug_scratch": (C.c_int, [_vp, C.c_int, C.c_char_p, _f32p, C.c_int, _i32p, _i32p]),
     "spp_device_info": (C.c_int, [C.c_int, _i32p, _i32p, _i32p, C.c_char_p, C.c_int]),
     "spp_kernel_launches": (C.c_int64, []),

@@ -15,6 +15,7 @@
 namespace spp {
 cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream);
 cudaError_t launch_acm_train(const UpdateArgs& a, int grid, cudaStream_t stream);
+cudaError_t launch_rollout(const RolloutArgs& r, int grid, cudaStream_t stream);
 }
 
 using namespace spp;
@@ -72,6 +73,9 @@ struct spp_population {
     bool len_dirty = true;
     // staging
     DevBuf d_obs, d_nobs, d_act, d_rew, d_done, d_aacm, d_eps, d_idx, d_losses, d_tmp;
+    DevBuf d_roll_scratch, d_env, d_cur;     // rollout: scratch for E rows per agent, synthetic env state, cursors
+    int roll_E = 0;
+    Layout L_roll;
     cudaStream_t stream = nullptr;
     uint64_t seq = 0;
     std::vector<TensorMap> tensors[NET_COUNT];
@@ -152,7 +156,7 @@ int spp_population_destroy(spp_population* p) {
                     (void*)p->steps, (void*)p->alpha_state, (void*)p->r_obs, (void*)p->r_act, (void*)p->r_rew, (void*)p->r_aacm,
                     (void*)p->r_oidx, (void*)p->r_nidx, (void*)p->r_done, (void*)p->r_end, (void*)p->r_len, (void*)p->scratch_acm})
         if (q) cudaFree(q);
-    for (DevBuf* b : {&p->d_obs, &p->d_nobs, &p->d_act, &p->d_rew, &p->d_done, &p->d_aacm, &p->d_eps, &p->d_idx, &p->d_losses, &p->d_tmp})
+    for (DevBuf* b : {&p->d_obs, &p->d_nobs, &p->d_act, &p->d_rew, &p->d_done, &p->d_aacm, &p->d_eps, &p->d_idx, &p->d_losses, &p->d_tmp, &p->d_roll_scratch, &p->d_env, &p->d_cur})
         b->release();
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -757,6 +761,83 @@ int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, ui
     g_launches++;
     if (losses) CK(cudaMemcpyAsync(losses, p->d_losses.p, (size_t)p->P * n_batches * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return SPP_OK;
+}
+
+// ---- rollout -----------------------------------------------------------------------------------------
+static int prepare_rollout(spp_population* p, int E, RolloutArgs& r) {
+    if (E < 1 || E > 4096) return fail(SPP_ERR_ARG, "environments per agent must be in [1,4096]");
+    if (p->roll_E != E) {
+        p->L_roll = make_layout(p->cfg.algo, p->cfg.ob_dim, p->cfg.ac_dim, p->cfg.acm_kind, p->cfg.acm_critic ? 1 : 0, E);
+        const size_t bytes = (size_t)p->P * p->L_roll.s.size * sizeof(float);
+        CK(p->d_roll_scratch.ensure(bytes));
+        CK(cudaMemsetAsync(p->d_roll_scratch.p, 0, bytes, p->stream));
+        CK(p->d_env.ensure((size_t)p->P * E * p->L_roll.ldo * sizeof(float)));
+        CK(cudaMemsetAsync(p->d_env.p, 0, (size_t)p->P * E * p->L_roll.ldo * sizeof(float), p->stream));
+        p->roll_E = E;
+    }
+    memset(&r, 0, sizeof(r));
+    fill_args(p, r.u, 1);
+    r.u.L = p->L_roll;
+    r.u.scratch = (float*)p->d_roll_scratch.p;
+    r.steps = 1;
+    return SPP_OK;
+}
+
+int spp_rollout_step_host(spp_population* p, int E, const float* obs, const float* noise, const float* eps, int random_phase,
+                          double act_noise, int obs_norm, int denormalize_actor_out, float* out_target, float* out_action) {
+    if (!p || !obs || !noise || !out_target || !out_action) return fail(SPP_ERR_ARG, "spp_rollout_step_host: null argument");
+    CK(cudaSetDevice(p->device));
+    RolloutArgs r;
+    int rc = prepare_rollout(p, E, r); if (rc) return rc;
+    const Layout& L = p->L_roll;
+    const size_t n_ob = (size_t)p->P * E * L.ob, n_ac = (size_t)p->P * E * L.ac;
+    cudaStream_t s = p->stream;
+    CK(p->d_obs.ensure(n_ob * 4)); CK(p->d_nobs.ensure(n_ob * 4)); CK(p->d_act.ensure(n_ob * 4)); CK(p->d_aacm.ensure(n_ac * 4));
+    CK(cudaMemcpyAsync(p->d_obs.p, obs, n_ob * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(p->d_nobs.p, noise, n_ob * 4, cudaMemcpyHostToDevice, s));
+    if (eps) { CK(p->d_eps.ensure(n_ob * 4)); CK(cudaMemcpyAsync(p->d_eps.p, eps, n_ob * 4, cudaMemcpyHostToDevice, s)); }
+    r.in_obs = (const float*)p->d_obs.p; r.in_noise = (const float*)p->d_nobs.p; r.in_eps = eps ? (const float*)p->d_eps.p : nullptr;
+    r.out_target = (float*)p->d_act.p; r.out_action = (float*)p->d_aacm.p;
+    r.random_phase = random_phase ? 1 : 0; r.obs_norm = obs_norm ? 1 : 0; r.denormalize_out = denormalize_actor_out ? 1 : 0;
+    r.act_noise = (float)act_noise;
+    CK(launch_rollout(r, grid_for(p), s));
+    g_launches++;
+    CK(cudaMemcpyAsync(out_target, r.out_target, n_ob * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out_action, r.out_action, n_ac * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return SPP_OK;
+}
+
+int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t seed, double act_noise, void* stream) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    if (p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
+    if (steps < 1) return fail(SPP_ERR_ARG, "steps must be positive");
+    if ((int64_t)(steps + 1) * E > p->S) return fail(SPP_ERR_ARG, "steps * E must fit the ring");
+    CK(cudaSetDevice(p->device));
+    RolloutArgs r;
+    int rc = prepare_rollout(p, E, r); if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
+    CK(p->d_cur.ensure((size_t)p->P * 2 * sizeof(int64_t)));
+    std::vector<int64_t> cur(2 * (size_t)p->P);
+    for (int a = 0; a < p->P; ++a) { cur[a] = p->obs_cur[a]; cur[p->P + a] = p->ts_cur[a]; }
+    CK(cudaMemcpyAsync(p->d_cur.p, cur.data(), cur.size() * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    r.env_state = (float*)p->d_env.p;
+    r.w_obs = p->r_obs; r.w_oidx = p->r_oidx; r.w_nidx = p->r_nidx; r.w_act = p->r_act; r.w_rew = p->r_rew;
+    r.w_done = p->r_done; r.w_end = p->r_end; r.w_aacm = p->r_aacm;
+    r.obs_cur = (const int64_t*)p->d_cur.p; r.ts_cur = r.obs_cur + p->P;
+    r.steps = steps; r.denormalize_out = 1; r.act_noise = (float)act_noise; r.u.seed = seed;
+    CK(launch_rollout(r, grid_for(p), s));
+    g_launches++;
+    for (int a = 0; a < p->P; ++a) {   // host mirror of the cursors (no episode resets in the synthetic environment)
+        const int64_t n = (int64_t)steps * E;
+        p->obs_cur[a] = (p->obs_cur[a] + n) % p->S;
+        const int64_t ts = p->ts_cur[a] + n;
+        p->cur_len[a] = ts >= p->S ? p->S : (ts > p->cur_len[a] ? ts : p->cur_len[a]);
+        p->ts_cur[a] = ts % p->S;
+    }
+    p->len_dirty = true;
     return SPP_OK;
 }
 

@@ -6,24 +6,6 @@ namespace spp {
 // loss slots in Smem::small
 constexpr int kLossBase = 8;
 
-// ---- actor hidden layers + heads.  X: [B x ldo]
-template <int ALGO>
-__device__ inline void actor_forward(const Ctx& c, const float* X, int actor_net) {
-    const Layout& L = c.a.L;
-    float* S = c.S;
-    const float* net = c.net(actor_net);
-    linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldo, L.ldo, net, L.actor.L[0], S + L.s.ha1, kHidden, L.B);
-    __syncthreads();
-    linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.ha1, kHidden, kHidden, net, L.actor.L[1], S + L.s.ha2, kHidden, L.B);
-    __syncthreads();
-    if (ALGO == ALGO_SAC)
-        linear_fwd<NarrowTile, ACT_NONE, false>(c, S + L.s.ha2, kHidden, kHidden, net, L.actor.L[2], S + L.s.ml, L.ldh, L.B);
-    else   // tanh(fc3) * lim ; tanh kept in zt
-        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.ha2, kHidden, kHidden, net, L.actor.L[2], S + L.s.ml, L.ldh, L.B,
-                                               c.normv(NORM_LIM), S + L.s.zt, L.ldo);
-    __syncthreads();
-}
-
 // ---- backward through the actor heads (warp per row); also custom (distance) loss and the SAC temperature step.
 template <int ALGO>
 __device__ inline void stage_actor_head_bwd(const Ctx& c) {

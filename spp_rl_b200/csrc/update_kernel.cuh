@@ -517,4 +517,42 @@ __device__ inline void stage_critic_head_bwd(const Ctx& c, const int* nets, cons
     }
 }
 
+// ---- actor hidden layers + heads.  X: [B x ldo]
+template <int ALGO>
+__device__ inline void actor_forward(const Ctx& c, const float* X, int actor_net) {
+    const Layout& L = c.a.L;
+    float* S = c.S;
+    const float* net = c.net(actor_net);
+    linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldo, L.ldo, net, L.actor.L[0], S + L.s.ha1, kHidden, L.B);
+    __syncthreads();
+    linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.ha1, kHidden, kHidden, net, L.actor.L[1], S + L.s.ha2, kHidden, L.B);
+    __syncthreads();
+    if (ALGO == ALGO_SAC)
+        linear_fwd<NarrowTile, ACT_NONE, false>(c, S + L.s.ha2, kHidden, kHidden, net, L.actor.L[2], S + L.s.ml, L.ldh, L.B);
+    else   // tanh(fc3) * lim ; tanh kept in zt
+        linear_fwd<NarrowTile, ACT_TANH, true>(c, S + L.s.ha2, kHidden, kHidden, net, L.actor.L[2], S + L.s.ml, L.ldh, L.B,
+                                               c.normv(NORM_LIM), S + L.s.zt, L.ldo);
+    __syncthreads();
+}
+
+struct RolloutArgs {
+    UpdateArgs u;              // L.B = E (environments per agent); scratch sized for E rows
+    // explicit form (host-facing noise_action + process_action):
+    const float* in_obs;       // [P][E][ob]   raw observations
+    const float* in_noise;     // [P][E][ob]   N(0,1) exploration noise (torch.randn in the reference), or null -> Philox
+    const float* in_eps;       // [P][E][ob]   N(0,1) of the SAC actor's rsample, or null -> Philox
+    float* out_target;         // [P][E][ob]   state target handed to the ACM (what the ring stores as "action")
+    float* out_action;         // [P][E][ac]   ACM action handed to the environment
+    // device-resident synthetic form:
+    float* env_state;          // [P][E][ldo]  current observation of every environment, or null (explicit form)
+    float* w_obs; int32_t* w_oidx; int32_t* w_nidx; float* w_act; float* w_rew; uint8_t* w_done; uint8_t* w_end; float* w_aacm;
+    const int64_t* obs_cur;    // [P] obs-row cursor at launch (row of env 0's CURRENT observation)
+    const int64_t* ts_cur;     // [P] timestep cursor at launch
+    int steps;                 // consecutive environment steps per launch (device form)
+    int random_phase;          // frames < random_frames: target = lim * N(0,1) (initial_act)
+    int obs_norm;              // normalise the actor / ACM input (replay_buffer.normalize gate)
+    int denormalize_out;       // denormalize_actor_out
+    float act_noise;
+};
+
 }  // namespace spp

@@ -231,6 +231,23 @@ class Population:
         check(self.lib.spp_acm_update_ring(self.h, int(n_batches), _ptr(idx, C.c_int64), int(seed), _ptr(losses, C.c_float)))
         return losses
 
+    # ------------------------------------------------------------------ rollout
+    def rollout_step(self, obs, noise, eps=None, random_phase=False, act_noise=0.1, obs_norm=False, denormalize_actor_out=True):
+        """noise_action / initial_act + process_action for E observations per agent: obs, noise, eps [P, E, ob]
+        -> (state_target [P, E, ob], acm_action [P, E, ac])."""
+        obs = _f32(obs); noise = _f32(noise)
+        E = obs.shape[1]
+        eps = None if eps is None else _f32(eps)
+        tgt = np.empty((self.P, E, self.ob_dim), np.float32)
+        act = np.empty((self.P, E, self.ac_dim), np.float32)
+        check(self.lib.spp_rollout_step_host(self.h, int(E), _ptr(obs, C.c_float), _ptr(noise, C.c_float), _ptr(eps, C.c_float),
+                                             int(bool(random_phase)), float(act_noise), int(bool(obs_norm)),
+                                             int(bool(denormalize_actor_out)), _ptr(tgt, C.c_float), _ptr(act, C.c_float)))
+        return tgt, act
+
+    def rollout_synthetic(self, envs_per_agent, steps, seed=0, act_noise=0.1, stream=None):
+        check(self.lib.spp_rollout_synthetic_device(self.h, int(envs_per_agent), int(steps), int(seed), float(act_noise), stream))
+
     # ------------------------------------------------------------------ introspection
     def debug_scratch(self, agent, name):
         cap = 4096 * 512
