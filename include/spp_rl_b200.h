@@ -153,6 +153,64 @@ int spp_rollout_step_host(spp_population* p, int E, const float* obs, const floa
  * denormalise, ACM, and the ring writes (obs row, timestep row, acm action, reward, done) -- in one launch. */
 int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t seed, double act_noise, void* stream);
 
+/* ---- SPP-PPO (PPO_AcM): one policy, 64-wide tanh nets (rltoolkit/basic_model.py:7-77), data-parallel over rows.
+ * A `spp_ppo` holds the actor (+ log_scale) and critic, one on-policy batch of up to max_rows transitions and the
+ * minibatch staging.  Net ids: 0 = actor, 1 = critic; tensors in the reference's state_dict order. */
+typedef struct spp_ppo spp_ppo;
+typedef struct spp_ppo_config {
+    int32_t ob_dim, ac_dim;
+    int32_t min_max_denormalize, norm_closs;
+    int64_t max_rows;               /* capacity of the on-policy batch held by this rank */
+    int64_t max_batch_rows;         /* largest minibatch (ppo_batch_size) */
+    double gamma, gae_lambda, ppo_epsilon, entropy_coef, custom_loss, actor_lr, critic_lr;
+} spp_ppo_config;
+int spp_ppo_create(const spp_ppo_config* cfg, int device, spp_ppo** out);
+int spp_ppo_destroy(spp_ppo* p);
+int spp_ppo_sync(spp_ppo* p);
+int spp_ppo_stream(spp_ppo* p, void** stream);
+int spp_ppo_set_limits(spp_ppo* p, const float* actor_lim);
+int spp_ppo_set_norm_stats(spp_ppo* p, const float* min_obs, const float* max_obs, const float* obs_mean, const float* obs_std);
+int spp_ppo_tensor_count(spp_ppo* p, int net);
+int spp_ppo_tensor_info(spp_ppo* p, int net, int t, char* name, int name_cap, int* rows, int* cols);
+int spp_ppo_params_upload(spp_ppo* p, int net, int t, const float* host);
+int spp_ppo_params_download(spp_ppo* p, int net, int t, float* host);
+int spp_ppo_adam_download(spp_ppo* p, int net, int t, float* exp_avg, float* exp_avg_sq, int* step);
+/* The collected batch = the contents of rltoolkit's Memory after A2C.collect_batch (rltoolkit/algorithms/a2c/a2c.py:144-184):
+ * raw obs / next_obs [N][ob] (Memory.obs / Memory.next_obs, rltoolkit/buffer/memory.py:146-168; normalised on the device
+ * like Memory.norm_obs), sampled state targets [N][ob], their log-probs, rewards, done, end [N] (float 0/1).
+ * Trajectories: traj_start[k], traj_len[k] rows apart by traj_stride (1 for the reference's rollout-major order, E for a
+ * step-major [T][E] layout); every trajectory must end with end = 1 exactly as collect_batch guarantees.
+ * global_rows = rows over all ranks (0 = N). */
+int spp_ppo_load_rollout(spp_ppo* p, int64_t N, const float* obs, const float* next_obs, const float* actions, const float* logp,
+                         const float* rew, const float* done, const float* end, const int64_t* traj_start, const int64_t* traj_len,
+                         int n_traj, int64_t traj_stride, int64_t global_rows);
+int spp_ppo_set_global_rows(spp_ppo* p, int64_t global_rows);
+/* A2C.update_critic (a2c.py:186-225): n_target_updates x [q = r + gamma (1-done) V(s') ; n_updates_per_target x full-batch
+ * Adam on 0.5 mean((q - V(s))^2)].  Step-wise forms for data-parallel runs: targets, grad (-> reduced gradient buffer and
+ * scalar slot 0 = sum of squared errors), [all-reduce spp_ppo_grad_buffer over NCCL], apply. */
+int spp_ppo_update_critic(spp_ppo* p, int n_target_updates, int n_updates_per_target, float* mean_loss);
+int spp_ppo_critic_targets(spp_ppo* p);
+int spp_ppo_critic_grad(spp_ppo* p);
+int spp_ppo_critic_apply(spp_ppo* p);
+/* PPO.calculate_advantage = calculate_q_val + calculate_gae (rltoolkit/algorithms/ppo/ppo.py:101-150) incl. the bootstrap
+ * at non-terminal ends; adv_host [N] may be NULL.  AdvantageDataset normalisation (advantage_dataset.py:9-12): unbiased std,
+ * eps 1.2e-7; global_stats = (n, sum, sum of squares) over all ranks or NULL for local. */
+int spp_ppo_advantages(spp_ppo* p, float* adv_host);
+int spp_ppo_adv_stats(spp_ppo* p, double out[3]);
+int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats);
+/* PPO_AcM.update_actor_acm (rltoolkit/acm/on_policy.py:164-216): perms [max_epochs][N] replace DataLoader(shuffle=True);
+ * keeps the partial last minibatch, takes KL on the last minibatch only, stops when KL >= kl_threshold, and divides the
+ * summed losses (actor, entropy, policy, dist) by (i + 1) exactly like the reference.  Step-wise forms as for the critic;
+ * scalar slots after a grad call: 0 = sum of clipped-loss terms, 2 = sum of squared custom-loss distances, 3 = sum of
+ * (old - new) log-probs. */
+int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int batch_size, double kl_threshold, float losses[4],
+                         int* epochs_run, float* last_kl);
+int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int64_t n_global);
+int spp_ppo_actor_apply(spp_ppo* p);
+int spp_ppo_scalars(spp_ppo* p, float out[8]);
+/* device pointers of the reduced gradient vector (n_floats) and the 8 scalar slots, for torch.distributed all_reduce */
+int spp_ppo_grad_buffer(spp_ppo* p, void** dev_ptr, int* n_floats, void** scal_ptr);
+
 /* ---- introspection for tests ------------------------------------------------------------------ */
 /* copy a named scratch buffer of agent a to host ("xo","xn","xc","xcp","xm","ha1","ha2","ml","hc1_0",...);
  * rows/ld describe the returned dense [rows x ld] block. */

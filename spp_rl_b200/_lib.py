@@ -17,6 +17,15 @@ LOSS_CRITIC_1, LOSS_CRITIC_2, LOSS_ACTOR, LOSS_PI, LOSS_DIST, LOSS_ALPHA, LOSS_A
 LOSS_COUNT = 8
 
 
+class PpoConfig(C.Structure):
+    _fields_ = [
+        ("ob_dim", C.c_int32), ("ac_dim", C.c_int32), ("min_max_denormalize", C.c_int32), ("norm_closs", C.c_int32),
+        ("max_rows", C.c_int64), ("max_batch_rows", C.c_int64),
+        ("gamma", C.c_double), ("gae_lambda", C.c_double), ("ppo_epsilon", C.c_double), ("entropy_coef", C.c_double),
+        ("custom_loss", C.c_double), ("actor_lr", C.c_double), ("critic_lr", C.c_double),
+    ]
+
+
 class SppError(RuntimeError):
     pass
 
@@ -73,6 +82,31 @@ SIGNATURES = {
     "spp_acm_update_ring": (C.c_int, [_vp, C.c_int, _i64p, C.c_uint64, _f32p]),
     "spp_rollout_step_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_double, C.c_int, C.c_int, _f32p, _f32p]),
     "spp_rollout_synthetic_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_double, _vp]),
+    "spp_ppo_create": (C.c_int, [C.POINTER(PpoConfig), C.c_int, C.POINTER(_vp)]),
+    "spp_ppo_destroy": (C.c_int, [_vp]),
+    "spp_ppo_sync": (C.c_int, [_vp]),
+    "spp_ppo_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "spp_ppo_set_limits": (C.c_int, [_vp, _f32p]),
+    "spp_ppo_set_norm_stats": (C.c_int, [_vp, _f32p, _f32p, _f32p, _f32p]),
+    "spp_ppo_tensor_count": (C.c_int, [_vp, C.c_int]),
+    "spp_ppo_tensor_info": (C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.c_int, _i32p, _i32p]),
+    "spp_ppo_params_upload": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
+    "spp_ppo_params_download": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
+    "spp_ppo_adam_download": (C.c_int, [_vp, C.c_int, C.c_int, _f32p, _f32p, _i32p]),
+    "spp_ppo_load_rollout": (C.c_int, [_vp, C.c_int64, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _i64p, _i64p, C.c_int, C.c_int64, C.c_int64]),
+    "spp_ppo_set_global_rows": (C.c_int, [_vp, C.c_int64]),
+    "spp_ppo_update_critic": (C.c_int, [_vp, C.c_int, C.c_int, _f32p]),
+    "spp_ppo_critic_targets": (C.c_int, [_vp]),
+    "spp_ppo_critic_grad": (C.c_int, [_vp]),
+    "spp_ppo_critic_apply": (C.c_int, [_vp]),
+    "spp_ppo_advantages": (C.c_int, [_vp, _f32p]),
+    "spp_ppo_adv_stats": (C.c_int, [_vp, _f64p]),
+    "spp_ppo_normalize_adv": (C.c_int, [_vp, _f64p]),
+    "spp_ppo_update_actor": (C.c_int, [_vp, _i64p, C.c_int, C.c_int, C.c_double, _f32p, _i32p, _f32p]),
+    "spp_ppo_actor_minibatch_grad": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64]),
+    "spp_ppo_actor_apply": (C.c_int, [_vp]),
+    "spp_ppo_scalars": (C.c_int, [_vp, _f32p]),
+    "spp_ppo_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), _i32p, C.POINTER(_vp)]),
     "spp_debug_scratch": (C.c_int, [_vp, C.c_int, C.c_char_p, _f32p, C.c_int, _i32p, _i32p]),
     "spp_device_info": (C.c_int, [C.c_int, _i32p, _i32p, _i32p, C.c_char_p, C.c_int]),
     "spp_kernel_launches": (C.c_int64, []),

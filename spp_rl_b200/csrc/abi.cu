@@ -24,6 +24,8 @@ static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int spp_set_error_(int code, const std::string& msg) { return fail(code, msg); }     // shared with ppo_abi.cu
+void spp_count_launch_() { g_launches++; }
 #define CK(expr)                                                                                      \
     do {                                                                                              \
         cudaError_t e_ = (expr);                                                                      \

@@ -1,0 +1,435 @@
+// C ABI of the SPP-PPO path (include/spp_rl_b200.h, "spp_ppo_*"): one policy, data-parallel over rows.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/spp_rl_b200.h"
+#include "ppo_kernels.cuh"
+#include "update_kernel.cuh"
+
+using namespace spp;
+
+extern "C" const char* spp_last_error(void);
+int spp_set_error_(int code, const std::string& msg);     // defined in abi.cu
+void spp_count_launch_();
+
+#define PCK(expr)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return spp_set_error_(SPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct PTensor { std::string name; int layer; int is_bias; int rows, cols; };
+
+struct spp_ppo {
+    spp_ppo_config cfg;
+    int device = 0, sm_count = 0, grid = 0;
+    PpoLayout L;
+    PpoHyper h;
+    int64_t cap_rows = 0, cap_batch = 0;
+    float *actor = nullptr, *actor_m = nullptr, *actor_v = nullptr, *critic = nullptr, *critic_m = nullptr, *critic_v = nullptr;
+    float* norm = nullptr;
+    PpoData d{};
+    PpoBatch b{};
+    PpoScratch s{};
+    float *part = nullptr, *gbuf = nullptr, *scal = nullptr, *gscal = nullptr, *raw = nullptr;
+    double* dstats = nullptr;
+    int64_t* dperm = nullptr;
+    int part_stride = 0;
+    int step_actor = 0, step_critic = 0;
+    int64_t scratch_rows = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<PTensor> tensors[2];
+    std::vector<void*> allocs;
+};
+
+static const NetDesc& pnet(const spp_ppo* p, int net) { return net == 0 ? p->L.actor : p->L.critic; }
+
+static int rows_per_cta(int64_t n, int grid) {
+    int64_t r = (n + grid - 1) / grid;
+    r = ((r + 127) / 128) * 128;
+    return (int)(r < 128 ? 128 : r);
+}
+
+static void fill(const spp_ppo* p, PpoArgs& a, int64_t rows_for_chunks) {
+    memset(&a, 0, sizeof(a));
+    a.L = p->L; a.h = p->h; a.d = p->d; a.b = p->b; a.s = p->s;
+    a.actor = p->actor; a.actor_m = p->actor_m; a.actor_v = p->actor_v;
+    a.critic = p->critic; a.critic_m = p->critic_m; a.critic_v = p->critic_v;
+    a.norm = p->norm; a.part = p->part; a.part_stride = p->part_stride; a.gbuf = p->gbuf; a.scal = p->scal; a.gscal = p->gscal;
+    a.rows_per_cta = rows_per_cta(rows_for_chunks, p->grid);
+}
+
+extern "C" {
+
+int spp_ppo_destroy(spp_ppo* p) {
+    if (!p) return SPP_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (void* q : p->allocs) cudaFree(q);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return SPP_OK;
+}
+
+int spp_ppo_create(const spp_ppo_config* cfg, int device, spp_ppo** out) {
+    if (!cfg || !out) return spp_set_error_(SPP_ERR_ARG, "spp_ppo_create: null argument");
+    if (cfg->ob_dim < 1 || cfg->ob_dim > 128 || cfg->ac_dim < 1 || cfg->ac_dim > 32) return spp_set_error_(SPP_ERR_ARG, "bad dims");
+    if (cfg->max_rows < 1 || cfg->max_batch_rows < 1) return spp_set_error_(SPP_ERR_ARG, "max_rows and max_batch_rows must be positive");
+    int ndev = 0;
+    PCK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return spp_set_error_(SPP_ERR_ARG, "no such CUDA device");
+    PCK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PCK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return spp_set_error_(SPP_ERR_UNSUPPORTED, "spp_rl_b200 is built for sm_100a (B200) only");
+    spp_ppo* p = new spp_ppo();
+    p->cfg = *cfg; p->device = device; p->sm_count = prop.multiProcessorCount; p->grid = prop.multiProcessorCount;
+    p->L = make_ppo_layout(cfg->ob_dim, cfg->ac_dim);
+    p->h.gamma = (float)cfg->gamma; p->h.discount = (float)(cfg->gae_lambda * cfg->gamma); p->h.discount_d = cfg->gae_lambda * cfg->gamma;
+    p->h.epsilon = (float)cfg->ppo_epsilon; p->h.entropy_coef = (float)cfg->entropy_coef; p->h.custom_loss = (float)cfg->custom_loss;
+    p->cap_rows = cfg->max_rows; p->cap_batch = cfg->max_batch_rows;
+    const int ldo = p->L.ldo;
+    auto alloc = [&](void** q, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(q, bytes ? bytes : 16);
+        if (e == cudaSuccess) { e = cudaMemset(*q, 0, bytes ? bytes : 16); p->allocs.push_back(*q); }
+        return e;
+    };
+#define PALLOC(ptr, bytes)                                                                           \
+    do {                                                                                             \
+        cudaError_t e_ = alloc((void**)&(ptr), (bytes));                                             \
+        if (e_ != cudaSuccess) {                                                                     \
+            std::string m = std::string("cudaMalloc(" #ptr "): ") + cudaGetErrorString(e_);          \
+            spp_ppo_destroy(p);                                                                      \
+            return spp_set_error_(SPP_ERR_CUDA, m);                                                  \
+        }                                                                                            \
+    } while (0)
+    const size_t N = (size_t)p->cap_rows, NB = (size_t)p->cap_batch;
+    PALLOC(p->actor, p->L.actor.size * 4); PALLOC(p->actor_m, p->L.actor.size * 4); PALLOC(p->actor_v, p->L.actor.size * 4);
+    PALLOC(p->critic, p->L.critic.size * 4); PALLOC(p->critic_m, p->L.critic.size * 4); PALLOC(p->critic_v, p->L.critic.size * 4);
+    PALLOC(p->norm, NORM_COUNT * ldo * 4);
+    PALLOC(p->d.x, N * ldo * 4); PALLOC(p->d.xn, N * ldo * 4); PALLOC(p->d.act, N * ldo * 4); PALLOC(p->raw, N * ldo * 4);
+    PALLOC(p->d.logp, N * 4); PALLOC(p->d.rew, N * 4); PALLOC(p->d.done, N * 4); PALLOC(p->d.end, N * 4);
+    PALLOC(p->d.v, N * 4); PALLOC(p->d.nv, N * 4); PALLOC(p->d.q, N * 4); PALLOC(p->d.adv, N * 4);
+    PALLOC(p->d.traj_start, N * 8); PALLOC(p->d.traj_len, N * 8);
+    PALLOC(p->b.x, NB * ldo * 4); PALLOC(p->b.act, NB * ldo * 4); PALLOC(p->b.xn, NB * ldo * 4); PALLOC(p->b.logp, NB * 4); PALLOC(p->b.adv, NB * 4);
+    p->scratch_rows = (int64_t)p->grid * rows_per_cta((int64_t)(N > NB ? N : NB), p->grid);
+    const size_t SR = (size_t)p->scratch_rows;
+    PALLOC(p->s.h1, SR * kPpoHidden * 4); PALLOC(p->s.h2, NB * kPpoHidden * 4 + 4096); PALLOC(p->s.dz2, SR * kPpoHidden * 4); PALLOC(p->s.dz1, SR * kPpoHidden * 4);
+    PALLOC(p->s.mean, (NB + 128) * ldo * 4); PALLOC(p->s.t3, (NB + 128) * ldo * 4); PALLOC(p->s.d3, (NB + 128) * ldo * 4); PALLOC(p->s.newlogp, (NB + 128) * 4);
+    p->part_stride = p->L.actor.size > p->L.critic.size ? p->L.actor.size : p->L.critic.size;
+    PALLOC(p->part, (size_t)p->grid * p->part_stride * 4); PALLOC(p->gbuf, (size_t)p->part_stride * 4);
+    PALLOC(p->scal, (size_t)p->grid * PS_COUNT * 4); PALLOC(p->gscal, PS_COUNT * 4);
+    PALLOC(p->dstats, (size_t)p->grid * 2 * 8);
+    PALLOC(p->dperm, NB * 8);
+#undef PALLOC
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { spp_ppo_destroy(p); return spp_set_error_(SPP_ERR_CUDA, "stream"); }
+    auto lin = [](std::vector<PTensor>& v, const char* nm, int layer, int rows, int cols) {
+        v.push_back({std::string(nm) + ".weight", layer, 0, rows, cols});
+        v.push_back({std::string(nm) + ".bias", layer, 1, rows, 1});
+    };
+    p->tensors[0].push_back({"log_scale", 3, 2, cfg->ob_dim, 1});       // state_dict order of basic_model.Actor
+    lin(p->tensors[0], "fc1", 0, kPpoHidden, cfg->ob_dim); lin(p->tensors[0], "fc2", 1, kPpoHidden, kPpoHidden); lin(p->tensors[0], "fc3", 2, cfg->ob_dim, kPpoHidden);
+    lin(p->tensors[1], "fc1", 0, kPpoHidden, cfg->ob_dim); lin(p->tensors[1], "fc2", 1, kPpoHidden, kPpoHidden); lin(p->tensors[1], "fc3", 2, 1, kPpoHidden);
+    *out = p;
+    std::vector<float> ones(128, 1.f);
+    int rc = spp_ppo_set_limits(p, ones.data());
+    if (rc == SPP_OK) rc = spp_ppo_set_norm_stats(p, nullptr, nullptr, nullptr, nullptr);
+    if (rc != SPP_OK) { spp_ppo_destroy(p); *out = nullptr; }
+    return rc;
+}
+
+int spp_ppo_set_limits(spp_ppo* p, const float* actor_lim) {
+    if (!p || !actor_lim) return spp_set_error_(SPP_ERR_ARG, "null argument");
+    PCK(cudaSetDevice(p->device));
+    std::vector<float> v(p->L.ldo, 0.f);
+    for (int j = 0; j < p->L.ob; ++j) v[j] = actor_lim[j];
+    PCK(cudaMemcpy(p->norm + NORM_LIM * p->L.ldo, v.data(), p->L.ldo * 4, cudaMemcpyHostToDevice));
+    return SPP_OK;
+}
+
+int spp_ppo_set_norm_stats(spp_ppo* p, const float* min_obs, const float* max_obs, const float* obs_mean, const float* obs_std) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null argument");
+    PCK(cudaSetDevice(p->device));
+    const int ldo = p->L.ldo, ob = p->L.ob;
+    std::vector<float> v(4 * (size_t)ldo, 0.f);
+    float* doff = v.data(); float* dsc = doff + ldo; float* nsub = dsc + ldo; float* ndiv = nsub + ldo;
+    for (int j = 0; j < ldo; ++j) { dsc[j] = (j < ob) ? 1.f : 0.f; ndiv[j] = 1.f; }
+    if (p->cfg.min_max_denormalize) {
+        if (min_obs && max_obs)
+            for (int j = 0; j < ob; ++j) {
+                const float mean = (max_obs[j] + min_obs[j]) / 2.f;
+                doff[j] = mean; dsc[j] = (max_obs[j] - min_obs[j]) / 2.f; nsub[j] = mean; ndiv[j] = (max_obs[j] - mean) + 1e-8f;
+            }
+    } else if (obs_mean && obs_std) {
+        for (int j = 0; j < ob; ++j) { doff[j] = obs_mean[j]; dsc[j] = obs_std[j] + 1e-8f; nsub[j] = obs_mean[j]; ndiv[j] = obs_std[j] + 1e-8f; }
+    }
+    PCK(cudaMemcpy(p->norm, v.data(), 4 * (size_t)ldo * 4, cudaMemcpyHostToDevice));
+    return SPP_OK;
+}
+
+int spp_ppo_tensor_count(spp_ppo* p, int net) { return (p && (net == 0 || net == 1)) ? (int)p->tensors[net].size() : -1; }
+
+int spp_ppo_tensor_info(spp_ppo* p, int net, int t, char* name, int name_cap, int* rows, int* cols) {
+    if (!p || net < 0 || net > 1 || t < 0 || t >= (int)p->tensors[net].size()) return spp_set_error_(SPP_ERR_ARG, "bad net/tensor id");
+    const PTensor& m = p->tensors[net][t];
+    if (name && name_cap > 0) { strncpy(name, m.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (rows) *rows = m.rows;
+    if (cols) *cols = m.cols;
+    return SPP_OK;
+}
+
+// dir 0 upload, 1 download params, 2 download exp_avg, 3 download exp_avg_sq
+static int ppo_tensor_io(spp_ppo* p, int net, int t, float* host, int dir) {
+    if (!p || !host || net < 0 || net > 1 || t < 0 || t >= (int)p->tensors[net].size()) return spp_set_error_(SPP_ERR_ARG, "bad argument");
+    PCK(cudaSetDevice(p->device));
+    PCK(cudaStreamSynchronize(p->stream));
+    const PTensor& m = p->tensors[net][t];
+    const LayerDesc& l = pnet(p, net).L[m.layer];
+    float* arena = net == 0 ? (dir == 2 ? p->actor_m : dir == 3 ? p->actor_v : p->actor) : (dir == 2 ? p->critic_m : dir == 3 ? p->critic_v : p->critic);
+    if (m.is_bias == 0) {
+        std::vector<float> nat((size_t)m.rows * l.ld, 0.f), tr;
+        if (dir == 0) {
+            for (int r = 0; r < m.rows; ++r) for (int c = 0; c < m.cols; ++c) nat[(size_t)r * l.ld + c] = host[(size_t)r * m.cols + c];
+            PCK(cudaMemcpy(arena + l.off_w, nat.data(), nat.size() * 4, cudaMemcpyHostToDevice));
+            if (l.off_wt >= 0) {
+                tr.assign((size_t)l.ld * l.ld_t, 0.f);
+                for (int r = 0; r < m.rows; ++r) for (int c = 0; c < m.cols; ++c) tr[(size_t)c * l.ld_t + r] = host[(size_t)r * m.cols + c];
+                PCK(cudaMemcpy(arena + l.off_wt, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+            }
+        } else {
+            PCK(cudaMemcpy(nat.data(), arena + l.off_w, nat.size() * 4, cudaMemcpyDeviceToHost));
+            for (int r = 0; r < m.rows; ++r) for (int c = 0; c < m.cols; ++c) host[(size_t)r * m.cols + c] = nat[(size_t)r * l.ld + c];
+        }
+    } else {
+        float* dev = arena + (m.is_bias == 1 ? l.off_b : l.off_w);
+        if (dir == 0) PCK(cudaMemcpy(dev, host, m.rows * 4, cudaMemcpyHostToDevice));
+        else PCK(cudaMemcpy(host, dev, m.rows * 4, cudaMemcpyDeviceToHost));
+    }
+    return SPP_OK;
+}
+int spp_ppo_params_upload(spp_ppo* p, int net, int t, const float* host) { return ppo_tensor_io(p, net, t, const_cast<float*>(host), 0); }
+int spp_ppo_params_download(spp_ppo* p, int net, int t, float* host) { return ppo_tensor_io(p, net, t, host, 1); }
+int spp_ppo_adam_download(spp_ppo* p, int net, int t, float* exp_avg, float* exp_avg_sq, int* step) {
+    int rc = SPP_OK;
+    if (exp_avg) rc = ppo_tensor_io(p, net, t, exp_avg, 2);
+    if (rc == SPP_OK && exp_avg_sq) rc = ppo_tensor_io(p, net, t, exp_avg_sq, 3);
+    if (rc == SPP_OK && step) *step = net == 0 ? p->step_actor : p->step_critic;
+    return rc;
+}
+
+int spp_ppo_load_rollout(spp_ppo* p, int64_t N, const float* obs, const float* next_obs, const float* actions, const float* logp,
+                         const float* rew, const float* done, const float* end, const int64_t* traj_start, const int64_t* traj_len,
+                         int n_traj, int64_t traj_stride, int64_t global_rows) {
+    if (!p || !obs || !next_obs || !actions || !logp || !rew || !done || !end || !traj_start || !traj_len)
+        return spp_set_error_(SPP_ERR_ARG, "spp_ppo_load_rollout: null argument");
+    if (N < 1 || N > p->cap_rows) return spp_set_error_(SPP_ERR_ARG, "N outside [1, max_rows]");
+    if (n_traj < 1 || n_traj > N) return spp_set_error_(SPP_ERR_ARG, "bad trajectory count");
+    PCK(cudaSetDevice(p->device));
+    cudaStream_t s = p->stream;
+    const int ob = p->L.ob, ldo = p->L.ldo;
+    const int clamp = p->cfg.min_max_denormalize ? 0 : 1;
+    p->d.N = N; p->d.Ntot = global_rows > 0 ? global_rows : N; p->d.n_traj = n_traj; p->d.traj_stride = traj_stride;
+    // Memory.norm_obs / norm_next_obs (rltoolkit/buffer/memory.py:170-176): normalise once on the device
+    PCK(cudaMemcpyAsync(p->raw, obs, (size_t)N * ob * 4, cudaMemcpyHostToDevice, s));
+    PCK(launch_ppo_normalize_rows(p->raw, p->d.x, N, ob, ldo, p->norm, clamp, p->grid * 4, s));
+    PCK(cudaStreamSynchronize(s));
+    PCK(cudaMemcpyAsync(p->raw, next_obs, (size_t)N * ob * 4, cudaMemcpyHostToDevice, s));
+    PCK(launch_ppo_normalize_rows(p->raw, p->d.xn, N, ob, ldo, p->norm, clamp, p->grid * 4, s));
+    PCK(cudaMemcpy2DAsync(p->d.act, ldo * 4, actions, ob * 4, ob * 4, N, cudaMemcpyHostToDevice, s));
+    PCK(cudaMemcpyAsync(p->d.logp, logp, N * 4, cudaMemcpyHostToDevice, s));
+    PCK(cudaMemcpyAsync(p->d.rew, rew, N * 4, cudaMemcpyHostToDevice, s));
+    PCK(cudaMemcpyAsync(p->d.done, done, N * 4, cudaMemcpyHostToDevice, s));
+    PCK(cudaMemcpyAsync(p->d.end, end, N * 4, cudaMemcpyHostToDevice, s));
+    PCK(cudaMemcpyAsync(p->d.traj_start, traj_start, (size_t)n_traj * 8, cudaMemcpyHostToDevice, s));
+    PCK(cudaMemcpyAsync(p->d.traj_len, traj_len, (size_t)n_traj * 8, cudaMemcpyHostToDevice, s));
+    PCK(cudaStreamSynchronize(s));
+    spp_count_launch_(); spp_count_launch_();
+    return SPP_OK;
+}
+
+// ---- critic ------------------------------------------------------------------------------------------
+int spp_ppo_critic_targets(spp_ppo* p) {      // q = r + gamma (1 - done) V(next_obs), detached (a2c.py:203-206)
+    if (!p || p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
+    PCK(cudaSetDevice(p->device));
+    PpoArgs a; fill(p, a, p->d.N); a.mode = 1;
+    PCK(launch_ppo_critic_values(a, p->grid, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
+int spp_ppo_critic_grad(spp_ppo* p) {         // local gradient of 0.5 mean((q - V)^2) -> reduced buffer; loss sum in gscal
+    if (!p || p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
+    PCK(cudaSetDevice(p->device));
+    PpoArgs a; fill(p, a, p->d.N);
+    PCK(launch_ppo_critic_grad(a, p->grid, p->stream)); spp_count_launch_();
+    PCK(launch_ppo_reduce(a, p->grid, p->L.critic.size, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
+int spp_ppo_critic_apply(spp_ppo* p) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    PCK(cudaSetDevice(p->device));
+    PpoArgs a; fill(p, a, p->d.N);
+    PCK(launch_ppo_adam(a, 1, ++p->step_critic, p->cfg.critic_lr, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
+int spp_ppo_scalars(spp_ppo* p, float out[8]) {
+    if (!p || !out) return spp_set_error_(SPP_ERR_ARG, "null");
+    PCK(cudaSetDevice(p->device));
+    PCK(cudaMemcpyAsync(out, p->gscal, PS_COUNT * 4, cudaMemcpyDeviceToHost, p->stream));
+    PCK(cudaStreamSynchronize(p->stream));
+    return SPP_OK;
+}
+
+int spp_ppo_update_critic(spp_ppo* p, int n_target_updates, int n_updates_per_target, float* mean_loss) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    double tot = 0.0;
+    for (int t = 0; t < n_target_updates; ++t) {
+        int rc = spp_ppo_critic_targets(p); if (rc) return rc;
+        for (int u = 0; u < n_updates_per_target; ++u) {
+            rc = spp_ppo_critic_grad(p); if (rc) return rc;
+            float sc[8];
+            rc = spp_ppo_scalars(p, sc); if (rc) return rc;
+            tot += 0.5 * (double)sc[PS_LOSS] / (double)p->d.Ntot;
+            rc = spp_ppo_critic_apply(p); if (rc) return rc;
+        }
+    }
+    if (mean_loss) *mean_loss = (float)(tot / ((double)n_target_updates * n_updates_per_target));
+    return SPP_OK;
+}
+
+// ---- advantages ------------------------------------------------------------------------------------------
+int spp_ppo_advantages(spp_ppo* p, float* adv_host) {
+    if (!p || p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
+    PCK(cudaSetDevice(p->device));
+    PpoArgs a; fill(p, a, p->d.N); a.mode = 0;
+    PCK(launch_ppo_critic_values(a, p->grid, p->stream)); spp_count_launch_();
+    PCK(launch_ppo_gae(a, p->stream)); spp_count_launch_();
+    if (adv_host) PCK(cudaMemcpyAsync(adv_host, p->d.adv, p->d.N * 4, cudaMemcpyDeviceToHost, p->stream));
+    PCK(cudaStreamSynchronize(p->stream));
+    return SPP_OK;
+}
+
+int spp_ppo_adv_stats(spp_ppo* p, double out[3]) {       // local (n, sum, sum of squares) in fp64
+    if (!p || !out) return spp_set_error_(SPP_ERR_ARG, "null");
+    PCK(cudaSetDevice(p->device));
+    PpoArgs a; fill(p, a, p->d.N);
+    PCK(launch_ppo_adv_stats(a, p->dstats, p->grid, p->stream)); spp_count_launch_();
+    std::vector<double> h(2 * (size_t)p->grid);
+    PCK(cudaMemcpyAsync(h.data(), p->dstats, h.size() * 8, cudaMemcpyDeviceToHost, p->stream));
+    PCK(cudaStreamSynchronize(p->stream));
+    double s = 0, s2 = 0;
+    for (int i = 0; i < p->grid; ++i) { s += h[2 * i]; s2 += h[2 * i + 1]; }
+    out[0] = (double)p->d.N; out[1] = s; out[2] = s2;
+    return SPP_OK;
+}
+
+int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats) {   // (A - mean) / (std_unbiased + 1.2e-7)
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    double st[3];
+    if (global_stats) { st[0] = global_stats[0]; st[1] = global_stats[1]; st[2] = global_stats[2]; }
+    else { int rc = spp_ppo_adv_stats(p, st); if (rc) return rc; }
+    const double n = st[0], mean = st[1] / n;
+    const double var = n > 1 ? (st[2] - n * mean * mean) / (n - 1) : 0.0;
+    const float denom = (float)std::sqrt(var > 0 ? var : 0.0) + 1.2e-7f;
+    PpoArgs a; fill(p, a, p->d.N);
+    PCK(launch_ppo_adv_apply(a, (float)mean, denom, p->grid * 4, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
+// ---- actor -----------------------------------------------------------------------------------------------
+int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int64_t n_global) {
+    if (!p || !perm) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (n < 1 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [1, max_batch_rows]");
+    PCK(cudaSetDevice(p->device));
+    for (int64_t i = 0; i < n; ++i) if (perm[i] < 0 || perm[i] >= p->d.N) return spp_set_error_(SPP_ERR_ARG, "permutation index out of range");
+    PCK(cudaMemcpyAsync(p->dperm, perm, (size_t)n * 8, cudaMemcpyHostToDevice, p->stream));
+    p->b.n = n;
+    p->b.n_mean = n_global > 0 ? n_global : n;      // the clipped loss is a mean over the GLOBAL minibatch in data-parallel runs
+    PpoArgs a; fill(p, a, n);
+    PCK(launch_ppo_gather(a, p->dperm, p->cfg.norm_closs ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
+    PCK(launch_ppo_reduce(a, p->grid, p->L.actor.size, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
+int spp_ppo_actor_apply(spp_ppo* p) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    PCK(cudaSetDevice(p->device));
+    PpoArgs a; fill(p, a, p->b.n);
+    PCK(launch_ppo_adam(a, 0, ++p->step_actor, p->cfg.actor_lr, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
+int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int batch_size, double kl_threshold, float losses[4],
+                         int* epochs_run, float* last_kl) {
+    if (!p || !perms) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
+    const int64_t N = p->d.N;
+    const int ob = p->L.ob;
+    double tot[4] = {0, 0, 0, 0};
+    double kl = 0.0;
+    int i = 0, ran = 0;
+    // state-independent entropy: sum_j 0.5 + 0.5 log(2 pi) + log_scale_j  (re-read per minibatch: log_scale moves)
+    for (i = 0; i < max_epochs; ++i) {
+        if (kl >= kl_threshold) break;
+        int64_t last_n = 0;
+        for (int64_t s0 = 0; s0 < N; s0 += batch_size) {
+            const int64_t n = (N - s0 < batch_size) ? N - s0 : batch_size;
+            std::vector<float> ls(ob);
+            PCK(cudaMemcpyAsync(ls.data(), p->actor + p->L.actor.L[3].off_w, ob * 4, cudaMemcpyDeviceToHost, p->stream));
+            int rc = spp_ppo_actor_minibatch_grad(p, perms + (size_t)i * N + s0, n, 0); if (rc) return rc;
+            float sc[8];
+            rc = spp_ppo_scalars(p, sc); if (rc) return rc;
+            float ent = 0.f;
+            for (int j = 0; j < ob; ++j) ent += 0.5f + 0.918938533204672741780329736406f + ls[j];
+            const double actor_loss = (double)sc[PS_LOSS] / (double)n;
+            const double dist = p->h.custom_loss != 0.f ? (double)sc[PS_DIST] / ((double)n * ob) : 0.0;
+            tot[0] += actor_loss; tot[1] += ent; tot[3] += dist;
+            tot[2] += actor_loss - (double)p->h.entropy_coef * ent + (double)p->h.custom_loss * dist;
+            kl = (double)sc[PS_KL] / (double)n;
+            last_n = n;
+            rc = spp_ppo_actor_apply(p); if (rc) return rc;
+        }
+        (void)last_n;
+        ++ran;
+    }
+    // the reference divides by (i + 1) with i the loop variable at exit (one more than the epochs run after an early stop)
+    const double div = (double)((i < max_epochs ? i : max_epochs - 1) + 1);
+    if (losses) for (int k = 0; k < 4; ++k) losses[k] = (float)(tot[k] / div);
+    if (epochs_run) *epochs_run = ran;
+    if (last_kl) *last_kl = (float)kl;
+    return SPP_OK;
+}
+
+int spp_ppo_grad_buffer(spp_ppo* p, void** dev_ptr, int* n_floats, void** scal_ptr) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (dev_ptr) *dev_ptr = p->gbuf;
+    if (n_floats) *n_floats = p->part_stride;
+    if (scal_ptr) *scal_ptr = p->gscal;
+    return SPP_OK;
+}
+
+int spp_ppo_set_global_rows(spp_ppo* p, int64_t global_rows) {
+    if (!p || global_rows < 1) return spp_set_error_(SPP_ERR_ARG, "bad argument");
+    p->d.Ntot = global_rows;
+    return SPP_OK;
+}
+
+int spp_ppo_sync(spp_ppo* p) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    PCK(cudaSetDevice(p->device));
+    PCK(cudaStreamSynchronize(p->stream));
+    return SPP_OK;
+}
+
+int spp_ppo_stream(spp_ppo* p, void** stream) {
+    if (!p || !stream) return spp_set_error_(SPP_ERR_ARG, "null");
+    *stream = (void*)p->stream;
+    return SPP_OK;
+}
+
+}  // extern "C"

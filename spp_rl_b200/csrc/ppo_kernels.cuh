@@ -1,0 +1,109 @@
+// SPP-PPO device code: 64-wide tanh nets over very large on-policy batches.
+// One policy, data-parallel over rows: every CTA owns a contiguous chunk of rows, runs the MLP chain on it with the
+// same FFMA tile GEMMs as the off-policy kernels, and leaves its partial gradient in a private slot; a second
+// kernel sums the slots in a fixed order (deterministic), after which the host may all-reduce the vector over
+// NCCL (data-parallel SPP-PPO) before the Adam kernel applies it.
+#pragma once
+#include "gemm_tile.cuh"
+#include "layout.h"
+
+namespace spp {
+
+constexpr int kPpoHidden = 64;                  // rltoolkit/basic_model.py:15-17,69-71
+using MidTile = TileCfg<32, 8, 4, 8>;           // 128 x 64: one tile spans every hidden unit
+using SmallTile = TileCfg<16, 16, 4, 4>;        // 64 x 64: a whole dW of the 64-wide layers
+
+struct PpoLayout {
+    int ob, ac, ldo, lda;
+    NetDesc actor;      // fc1 [64 x ob], fc2 [64 x 64], fc3 [ob x 64], pseudo layer 3: log_scale [1 x ob] (vector)
+    NetDesc critic;     // fc1 [64 x ob], fc2 [64 x 64], fc3 [1 x 64] (vector)
+};
+
+inline PpoLayout make_ppo_layout(int ob, int ac) {
+    PpoLayout L{};
+    L.ob = ob; L.ac = ac; L.ldo = pad4(ob); L.lda = pad4(ac);
+    int off = 0;
+    add_layer(L.actor, off, kPpoHidden, ob, 0);
+    add_layer(L.actor, off, kPpoHidden, kPpoHidden, 0);
+    add_layer(L.actor, off, ob, kPpoHidden, 0);
+    add_layer(L.actor, off, 1, ob, 0, false);
+    L.actor.size = off;
+    off = 0;
+    add_layer(L.critic, off, kPpoHidden, ob, 0);
+    add_layer(L.critic, off, kPpoHidden, kPpoHidden, 0);
+    add_layer(L.critic, off, 1, kPpoHidden, 0, false);
+    L.critic.size = off;
+    return L;
+}
+
+struct PpoHyper {
+    float gamma, discount /* gamma * lambda */, epsilon, entropy_coef, custom_loss;
+    double discount_d;
+};
+
+// rows of the current on-policy batch (any order in which each trajectory is contiguous and time-ascending)
+struct PpoData {
+    int64_t N;              // rows held by this rank
+    int64_t Ntot;           // rows over all ranks (means are over the global batch)
+    float* x;               // [N][ldo]  normalised obs          (Memory.norm_obs)
+    float* xn;              // [N][ldo]  normalised next obs     (Memory.norm_next_obs)
+    float* act;             // [N][ldo]  sampled state targets (normalised space, as stored by the rollout)
+    float* logp;            // [N]       log-prob of the sampled target under the rollout policy
+    float* rew; float* done; float* end;    // [N]
+    float* v; float* nv;    // [N]       V(obs), V(next_obs)
+    float* q;               // [N]       r + gamma (1 - done) V(next_obs)
+    float* adv;             // [N]       GAE advantages (normalised in place by ppo_adv_normalize)
+    int64_t* traj_start;    // [n_traj]  first row of every trajectory scanned by one thread (E entries for [E][T] data)
+    int64_t* traj_len;      // [n_traj]
+    int64_t traj_stride;    // row stride between consecutive time steps of one trajectory (1: rollout-major, E: step-major)
+    int n_traj;
+};
+
+// minibatch staging (rows gathered by the shuffled permutation)
+struct PpoBatch {
+    int64_t n;              // rows in this minibatch (on this rank)
+    int64_t n_mean;         // rows the loss mean is taken over (the global minibatch in data-parallel runs)
+    float* x; float* act; float* xn;    // [n][ldo]
+    float* logp; float* adv;            // [n]
+};
+
+struct PpoScratch {
+    float* h1; float* h2; float* dz2; float* dz1;   // [rows][64]
+    float* mean; float* t3; float* d3;              // [rows][ldo]  actor head: tanh*lim, tanh, grad of pre-activation
+    float* newlogp;                                 // [rows]
+};
+
+struct PpoArgs {
+    PpoLayout L;
+    PpoHyper h;
+    PpoData d;
+    PpoBatch b;
+    PpoScratch s;
+    float* actor; float* actor_m; float* actor_v;       // parameter / moment arenas (NetDesc offsets)
+    float* critic; float* critic_m; float* critic_v;
+    const float* norm;          // [NORM_COUNT][ldo] as in the off-policy kernels (denormalise offsets / scales, limits)
+    float* part;                // [grid][part_stride] per-CTA partial gradients
+    int part_stride;
+    float* gbuf;                // [part_stride] reduced gradient (what NCCL all-reduces in data-parallel runs)
+    float* scal;                // [grid][8] per-CTA scalar partials; reduced into gscal[8]
+    float* gscal;
+    int rows_per_cta;           // multiple of 128
+    int mode;                   // kernel specific
+};
+
+// scalar slots
+enum { PS_LOSS = 0, PS_ENTROPY = 1, PS_DIST = 2, PS_KL = 3, PS_COUNT = 8 };
+
+cudaError_t launch_ppo_critic_values(const PpoArgs& a, int grid, cudaStream_t s);      // v, nv, q
+cudaError_t launch_ppo_critic_grad(const PpoArgs& a, int grid, cudaStream_t s);        // partial grads of 0.5 mean((q - V)^2)
+cudaError_t launch_ppo_actor_grad(const PpoArgs& a, int grid, cudaStream_t s);         // partial grads of the clipped loss
+cudaError_t launch_ppo_reduce(const PpoArgs& a, int n_part, int n_elems, cudaStream_t s);
+cudaError_t launch_ppo_adam(const PpoArgs& a, int which_net, int step, double lr, cudaStream_t s);
+cudaError_t launch_ppo_gae(const PpoArgs& a, cudaStream_t s);
+cudaError_t launch_ppo_adv_stats(const PpoArgs& a, double* d_stats, int grid, cudaStream_t s);     // n, sum, sum of squares (fp64)
+cudaError_t launch_ppo_adv_apply(const PpoArgs& a, float mean, float inv_std, int grid, cudaStream_t s);
+cudaError_t launch_ppo_gather(const PpoArgs& a, const int64_t* d_perm, int denorm, int grid, cudaStream_t s);
+cudaError_t launch_ppo_normalize_rows(const float* raw, float* out, int64_t n, int ob, int ldo, const float* norm, int clamp,
+                                      int grid, cudaStream_t s);
+
+}  // namespace spp

@@ -1,0 +1,175 @@
+"""Host handle on the device-resident SPP-PPO policy (thin wrapper over the spp_ppo_* C ABI).
+
+Mirrors the update part of rltoolkit's PPO_AcM.perform_iteration (rltoolkit/acm/on_policy.py:55-86):
+update_critic -> calculate_advantage (q-values + GAE) -> advantage normalisation -> clipped-ratio actor epochs
+with KL early stop.  In data-parallel runs (one process per GPU) the per-step gradient vector is all-reduced with
+torch.distributed (NCCL) between the device-side grad and apply kernels.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib
+from ._lib import PpoConfig, SppError, check
+from .population import _f32, _ptr
+
+NETS = {"actor": 0, "critic": 1}
+
+
+class PpoPolicy:
+    def __init__(self, ob_dim, ac_dim, max_rows, max_batch_rows, device=0, min_max_denormalize=True, norm_closs=False,
+                 gamma=0.99, gae_lambda=0.95, ppo_epsilon=0.2, entropy_coef=0.0, custom_loss=0.0, actor_lr=3e-4, critic_lr=3e-4):
+        self.lib = _lib.load_library()
+        cfg = PpoConfig()
+        cfg.ob_dim, cfg.ac_dim = int(ob_dim), int(ac_dim)
+        cfg.min_max_denormalize, cfg.norm_closs = int(min_max_denormalize), int(norm_closs)
+        cfg.max_rows, cfg.max_batch_rows = int(max_rows), int(max_batch_rows)
+        cfg.gamma, cfg.gae_lambda, cfg.ppo_epsilon, cfg.entropy_coef = gamma, gae_lambda, ppo_epsilon, entropy_coef
+        cfg.custom_loss, cfg.actor_lr, cfg.critic_lr = float(custom_loss), actor_lr, critic_lr
+        self.cfg = cfg
+        self.ob_dim, self.ac_dim = int(ob_dim), int(ac_dim)
+        h = C.c_void_p()
+        check(self.lib.spp_ppo_create(C.byref(cfg), int(device), C.byref(h)))
+        self.h = h
+        self.N = 0
+        self._tensors = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.spp_ppo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.spp_ppo_sync(self.h))
+
+    # ------------------------------------------------------------------ parameters
+    def set_limits(self, actor_lim):
+        a = _f32(np.broadcast_to(np.asarray(actor_lim, np.float32), (self.ob_dim,)))
+        check(self.lib.spp_ppo_set_limits(self.h, _ptr(a, C.c_float)))
+
+    def set_norm_stats(self, min_obs=None, max_obs=None, obs_mean=None, obs_std=None):
+        arrs = [None if v is None else _f32(v) for v in (min_obs, max_obs, obs_mean, obs_std)]
+        check(self.lib.spp_ppo_set_norm_stats(self.h, *[_ptr(v, C.c_float) for v in arrs]))
+
+    def tensor_list(self, net):
+        nid = NETS[net]
+        if nid not in self._tensors:
+            out = []
+            for t in range(self.lib.spp_ppo_tensor_count(self.h, nid)):
+                name = C.create_string_buffer(64)
+                r, c = C.c_int(), C.c_int()
+                check(self.lib.spp_ppo_tensor_info(self.h, nid, t, name, 64, C.byref(r), C.byref(c)))
+                out.append((name.value.decode(), r.value, c.value))
+            self._tensors[nid] = out
+        return nid, self._tensors[nid]
+
+    @staticmethod
+    def _shape(name, rows, cols):
+        return (rows,) if (name.endswith(".bias") or name == "log_scale") else (rows, cols)
+
+    def load_state_dict(self, net, sd):
+        nid, tl = self.tensor_list(net)
+        for t, (name, rows, cols) in enumerate(tl):
+            v = sd[name]
+            v = _f32(v.detach().cpu().numpy() if hasattr(v, "detach") else v).reshape(-1)
+            if v.size != int(np.prod(self._shape(name, rows, cols))):
+                raise SppError("tensor %s has the wrong size" % name)
+            check(self.lib.spp_ppo_params_upload(self.h, nid, t, _ptr(v, C.c_float)))
+
+    def state_dict(self, net):
+        nid, tl = self.tensor_list(net)
+        out = OrderedDict()
+        for t, (name, rows, cols) in enumerate(tl):
+            v = np.empty(self._shape(name, rows, cols), np.float32)
+            check(self.lib.spp_ppo_params_download(self.h, nid, t, _ptr(v, C.c_float)))
+            out[name] = v
+        return out
+
+    # ------------------------------------------------------------------ data
+    def load_rollout(self, obs, next_obs, actions, logp, rew, done, end, traj_start, traj_len, traj_stride=1, global_rows=0):
+        obs, next_obs, actions = _f32(obs), _f32(next_obs), _f32(actions)
+        logp, rew, done, end = _f32(logp), _f32(rew), _f32(done), _f32(end)
+        ts = np.ascontiguousarray(traj_start, np.int64); tl = np.ascontiguousarray(traj_len, np.int64)
+        self.N = obs.shape[0]
+        check(self.lib.spp_ppo_load_rollout(self.h, self.N, _ptr(obs, C.c_float), _ptr(next_obs, C.c_float), _ptr(actions, C.c_float),
+                                            _ptr(logp, C.c_float), _ptr(rew, C.c_float), _ptr(done, C.c_float), _ptr(end, C.c_float),
+                                            _ptr(ts, C.c_int64), _ptr(tl, C.c_int64), int(ts.size), int(traj_stride), int(global_rows)))
+
+    # ------------------------------------------------------------------ single-GPU forms
+    def update_critic(self, n_target_updates=10, n_updates_per_target=10):
+        loss = C.c_float()
+        check(self.lib.spp_ppo_update_critic(self.h, int(n_target_updates), int(n_updates_per_target), C.byref(loss)))
+        return loss.value
+
+    def advantages(self, want_host=True):
+        adv = np.empty(self.N, np.float32) if want_host else None
+        check(self.lib.spp_ppo_advantages(self.h, _ptr(adv, C.c_float)))
+        return adv
+
+    def normalize_adv(self, global_stats=None):
+        g = None if global_stats is None else np.ascontiguousarray(global_stats, np.float64)
+        check(self.lib.spp_ppo_normalize_adv(self.h, _ptr(g, C.c_double)))
+
+    def adv_stats(self):
+        out = (C.c_double * 3)()
+        check(self.lib.spp_ppo_adv_stats(self.h, out))
+        return np.array([out[0], out[1], out[2]])
+
+    def update_actor(self, perms, batch_size, kl_threshold, max_epochs=None):
+        perms = np.ascontiguousarray(perms, np.int64)
+        max_epochs = perms.shape[0] if max_epochs is None else int(max_epochs)
+        losses = (C.c_float * 4)()
+        epochs, kl = C.c_int(), C.c_float()
+        check(self.lib.spp_ppo_update_actor(self.h, _ptr(perms, C.c_int64), max_epochs, int(batch_size), float(kl_threshold), losses,
+                                            C.byref(epochs), C.byref(kl)))
+        return {"actor": losses[0], "entropy": losses[1], "policy": losses[2], "dist": losses[3]}, epochs.value, kl.value
+
+    # ------------------------------------------------------------------ data-parallel forms (torch.distributed)
+    def grad_tensor(self):
+        """torch views (no copy) of the reduced gradient vector and the 8 scalar slots, for dist.all_reduce."""
+        import torch
+
+        ptr, sptr, n = C.c_void_p(), C.c_void_p(), C.c_int()
+        check(self.lib.spp_ppo_grad_buffer(self.h, C.byref(ptr), C.byref(n), C.byref(sptr)))
+
+        class _Arr:
+            def __init__(self, p, k):
+                self.__cuda_array_interface__ = {"shape": (k,), "typestr": "<f4", "data": (p, False), "version": 2}
+        return torch.as_tensor(_Arr(ptr.value, n.value), device="cuda"), torch.as_tensor(_Arr(sptr.value, 8), device="cuda")
+
+    def scalars(self):
+        out = (C.c_float * 8)()
+        check(self.lib.spp_ppo_scalars(self.h, out))
+        return np.array(list(out), np.float32)
+
+    def update_critic_dp(self, dist, n_target_updates=10, n_updates_per_target=10):
+        """update_critic with one NCCL all-reduce of the gradient vector per optimiser step."""
+        g, sc = self.grad_tensor()
+        tot, ntot = 0.0, None
+        for _ in range(n_target_updates):
+            check(self.lib.spp_ppo_critic_targets(self.h))
+            for _ in range(n_updates_per_target):
+                check(self.lib.spp_ppo_critic_grad(self.h))
+                self.sync()
+                dist.all_reduce(g)
+                dist.all_reduce(sc)
+                tot += float(sc[0].item())
+                check(self.lib.spp_ppo_critic_apply(self.h))
+        return tot
+
+    def actor_minibatch_dp(self, dist, perm_local, n_global):
+        g, sc = self.grad_tensor()
+        p = np.ascontiguousarray(perm_local, np.int64)
+        check(self.lib.spp_ppo_actor_minibatch_grad(self.h, _ptr(p, C.c_int64), int(p.size), int(n_global)))
+        self.sync()
+        dist.all_reduce(g)
+        dist.all_reduce(sc)
+        check(self.lib.spp_ppo_actor_apply(self.h))
+        return sc.cpu().numpy()

@@ -1,0 +1,121 @@
+"""-m gpu: the SPP-PPO kernels against the golden fixture produced by the unmodified reference (PPO_AcM on Walker2d
+shapes: critic fit, q-values + GAE incl. truncation bootstrap, advantage normalisation, clipped-ratio actor epochs with
+KL early stop) and against the oracle on a larger synthetic batch laid out step-major ([T][E], stride E)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo as P
+from oracle.norm import NormStats, denormalize, normalize
+from spp_rl_b200.ppo import PpoPolicy
+from tests.parity_util import relnorm
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _trajectories(end):
+    starts, lens, s = [], [], 0
+    for i, e in enumerate(end):
+        if e:
+            starts.append(s); lens.append(i + 1 - s); s = i + 1
+    assert s == len(end), "every trajectory must finish with end = 1"
+    return np.array(starts, np.int64), np.array(lens, np.int64)
+
+
+def test_ppo_update_matches_reference_fixture():
+    g = np.load(os.path.join(G, "ppo_walker.npz"))
+    gamma, lam, eps_clip, kl_thr, max_ep, bs, a_lr, c_lr, ent, closs, ntu, nupt = [float(x) for x in g["hp"]]
+    ob, ac = g["chain"].shape[1], g["actions_acm"].shape[1]
+    oi, ni = P.chain_views(len(g["chain"]), list(g["joints"]))
+    obs, nobs = g["chain"][oi], g["chain"][ni]
+    N = obs.shape[0]
+    pol = PpoPolicy(ob, ac, max_rows=N, max_batch_rows=int(bs), min_max_denormalize=True, norm_closs=False, gamma=gamma, gae_lambda=lam,
+                    ppo_epsilon=eps_clip, entropy_coef=ent, custom_loss=closs, actor_lr=a_lr, critic_lr=c_lr)
+    pol.set_limits(float(g["actor_lim"]))
+    pol.set_norm_stats(g["min_obs"], g["max_obs"], g["obs_mean"], g["obs_std"])
+    for net in ("actor", "critic"):
+        pol.load_state_dict(net, {k[len("pre:" + net) + 1:]: g[k] for k in g.files if k.startswith("pre:" + net + ".")})
+    ts, tl = _trajectories(g["end"])
+    pol.load_rollout(obs, nobs, g["actions"], g["logp"], g["rewards"], g["done"], g["end"], ts, tl)
+    loss = pol.update_critic(int(ntu), int(nupt))
+    assert loss == pytest.approx(float(g["critic_loss"]), rel=1e-4)
+    sd = pol.state_dict("critic")
+    for k, v in sd.items():
+        assert relnorm(v, g["fit:critic." + k]) < (1e-4 if v.size <= 16 else 1e-5), (k, relnorm(v, g["fit:critic." + k]))
+    adv = pol.advantages()
+    assert np.abs(adv - g["adv"]).max() < 2e-5 * max(1.0, np.abs(g["adv"]).max())
+    pol.normalize_adv()
+    losses, epochs, kl = pol.update_actor(g["perms"], int(bs), kl_thr, int(max_ep))
+    assert epochs + 1 == int(g["epochs_run"])          # the reference counts i + 1 after its early-stop break
+    ref = g["actor_losses"]
+    for key, r in zip(("actor", "entropy", "policy", "dist"), ref):
+        assert losses[key] == pytest.approx(float(r), rel=2e-4), key
+    sd = pol.state_dict("actor")
+    for k, v in sd.items():
+        assert relnorm(v, g["post:actor." + k]) < 2e-5, (k, relnorm(v, g["post:actor." + k]))
+    pol.close()
+
+
+def test_ppo_step_major_large_batch_matches_oracle():
+    """E environments x T steps in step-major order (row = t * E + e): GAE strides by E; several CTAs per phase."""
+    ob, ac, E, T = 17, 6, 96, 40
+    N = E * T
+    rng = np.random.RandomState(3)
+    mn, mx = (-rng.rand(ob) * 2 - 0.5).astype(np.float32), (rng.rand(ob) * 2 + 0.5).astype(np.float32)
+    obs = (rng.rand(N, ob) * (mx - mn) + mn).astype(np.float32)
+    nobs = (obs + 0.05 * rng.randn(N, ob)).astype(np.float32)
+    act = (0.5 * rng.randn(N, ob)).astype(np.float32)
+    logp = (-10 + rng.randn(N)).astype(np.float32)
+    rew = rng.randn(N).astype(np.float32)
+    done = (rng.rand(N) < 0.02).astype(np.float32)
+    end = done.copy()
+    end[rng.rand(N) < 0.02] = 1
+    end[(T - 1) * E:] = 1                                   # every environment's trajectory ends at the last step
+    s = {}
+    def lin(net, name, o, i):
+        b = 1 / np.sqrt(i)
+        s[net + "." + name + ".weight"] = torch.from_numpy(rng.uniform(-b, b, (o, i)).astype(np.float32))
+        s[net + "." + name + ".bias"] = torch.from_numpy(rng.uniform(-b, b, (o,)).astype(np.float32))
+    for net, out in (("actor", ob), ("critic", 1)):
+        lin(net, "fc1", 64, ob); lin(net, "fc2", 64, 64); lin(net, "fc3", out, 64)
+    s["actor.log_scale"] = torch.full((ob,), -1.34)
+    pol = PpoPolicy(ob, ac, max_rows=N, max_batch_rows=1024, min_max_denormalize=True, gamma=0.99, gae_lambda=0.95, custom_loss=0.1,
+                    entropy_coef=0.01)
+    pol.set_norm_stats(mn, mx)
+    for net in ("actor", "critic"):
+        pol.load_state_dict(net, {k[len(net) + 1:]: v for k, v in s.items() if k.startswith(net + ".")})
+    pol.load_rollout(obs, nobs, act, logp, rew, done, end, np.arange(E), np.full(E, T), traj_stride=E)
+    st = NormStats(True, torch.from_numpy(mn), torch.from_numpy(mx))
+    x, xn = normalize(st, torch.from_numpy(obs), True), normalize(st, torch.from_numpy(nobs), True)
+    tr, td, te = torch.from_numpy(rew), torch.from_numpy(done), torch.from_numpy(end)
+    ref_loss = P.update_critic(s, x, xn, tr, td, 0.99, 3e-4, 2, 3)
+    assert pol.update_critic(2, 3) == pytest.approx(ref_loss, rel=1e-4)
+    # oracle GAE per environment (time-major view of the step-major rows)
+    v = torch.zeros(N); nv = torch.zeros(N)
+    from oracle import nets
+    from oracle.offpolicy import sub
+    v = nets.ppo_critic_fwd(sub(s, "critic"), x)[0].squeeze(-1); nv = nets.ppo_critic_fwd(sub(s, "critic"), xn)[0].squeeze(-1)
+    q = P.q_values(tr, td, nv, 0.99)
+    adv_ref = torch.empty(N)
+    for e in range(E):
+        rows = torch.arange(e, N, E)
+        adv_ref[rows] = P.gae(q[rows], v[rows], nv[rows], td[rows], te[rows], 0.99, 0.95)
+    adv = pol.advantages()
+    assert np.abs(adv - adv_ref.numpy()).max() < 2e-5 * max(1.0, float(adv_ref.abs().max()))
+    pol.normalize_adv()
+    advn = P.normalize_adv(adv_ref)
+    perms = np.stack([rng.permutation(N) for _ in range(3)]).astype(np.int64)
+    tot, epochs, kl = P.update_actor_acm(s, x, denormalize(st, torch.from_numpy(act)), denormalize(st, xn), torch.from_numpy(logp), advn,
+                                         [torch.from_numpy(p) for p in perms], 1.0, 3e-4, 0.2, 1e9, 3, 1000, 0.01, 0.1)
+    losses, epochs_c, kl_c = pol.update_actor(perms, 1000, 1e9, 3)
+    assert epochs_c == epochs
+    assert kl_c == pytest.approx(kl, rel=1e-3, abs=1e-5)
+    for key in ("actor", "entropy", "policy", "dist"):
+        assert losses[key] == pytest.approx(tot[key], rel=2e-4, abs=1e-5), key
+    sd = pol.state_dict("actor")
+    for k, val in sd.items():
+        assert relnorm(val, s["actor." + k].numpy()) < 2e-5, (k, relnorm(val, s["actor." + k].numpy()))
+    pol.close()
