@@ -135,9 +135,13 @@ int spp_update_ring_device(spp_population* p, int grad_steps, uint64_t seed, flo
  *      batch_update (acm.py:246-258)] in one launch; Adam(acm_lr) on the ACM (AcM or BasicAcM incl. t, t1).
  * Host form = batch_update(x, y): x [P][n][acm_batch_size][2 ob] = cat[obs, next_obs], y [P][n][acm_batch_size][ac].
  * Ring form: idx int64 [P][n][acm_batch_size] host indices (np.random.randint stays with the caller), NULL ->
- * device sampler.  losses [P][n] = the MSE of each step (may be NULL).  Only acm_ob_idx = all observations. */
-int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, float* losses);
-int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, uint64_t seed, float* losses);
+ * device sampler.  losses [P][n] = the MSE of each step (may be NULL).  Only acm_ob_idx = all observations.
+ * last_rows: rows of the FINAL step when it is a partial minibatch (DataLoader's drop_last = False in
+ * AcMTrainer.update_acm, rltoolkit/acm/acm.py:285-293); 0 = every step is a full acm_batch_size batch. */
+int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses);
+int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, int last_rows, uint64_t seed, float* losses);
+/* learning rates may change between calls (StepLR on the ACM optimiser, rltoolkit/acm/acm.py:181-183,299); negative = keep */
+int spp_set_learning_rates(spp_population* p, double actor_lr, double critic_lr, double alpha_lr, double acm_lr);
 
 /* ---- rollout step: body of DDPG.collect_batch_and_train (rltoolkit/algorithms/ddpg/ddpg.py:202-207) =
  *      replay_buffer.normalize (obs_norm gate) -> AcMOffPolicy.initial_act (random phase,
@@ -208,6 +212,13 @@ int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int b
 int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int64_t n_global);
 int spp_ppo_actor_apply(spp_ppo* p);
 int spp_ppo_scalars(spp_ppo* p, float out[8]);
+/* Rollout step of A2C.collect_batch (rltoolkit/algorithms/a2c/a2c.py:165-167) for E observations at once:
+ * Memory.normalize -> Actor.act (rltoolkit/basic_model.py:32-51; noise [E][ob] = the N(0,1) of Normal.sample) -> the
+ * denormalisation half of AcMOnPolicyTrainer.process_action (rltoolkit/acm/on_policy.py:46-47).  action [E][ob] is the
+ * sampled target the Memory stores, logp [E] its log-prob, target [E][ob] what is concatenated with the normalised obs
+ * for the ACM (spp_rollout_step_host with random_phase = 1, obs_norm = 1 and noise = action evaluates that ACM call). */
+int spp_ppo_act(spp_ppo* p, int64_t E, const float* obs, const float* noise, int denormalize_actor_out, float* action, float* logp,
+                float* target);
 /* device pointers of the reduced gradient vector (n_floats) and the 8 scalar slots, for torch.distributed all_reduce */
 int spp_ppo_grad_buffer(spp_ppo* p, void** dev_ptr, int* n_floats, void** scal_ptr);
 

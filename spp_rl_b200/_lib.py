@@ -78,8 +78,9 @@ SIGNATURES = {
     "spp_update_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p, _f32p, _i8p, _f32p, _f32p, C.c_uint64, _f32p]),
     "spp_update_ring": (C.c_int, [_vp, C.c_int, _i64p, _f32p, C.c_uint64, _f32p]),
     "spp_update_ring_device": (C.c_int, [_vp, C.c_int, C.c_uint64, _vp, _vp]),
-    "spp_acm_update_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p]),
-    "spp_acm_update_ring": (C.c_int, [_vp, C.c_int, _i64p, C.c_uint64, _f32p]),
+    "spp_acm_update_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, C.c_int, _f32p]),
+    "spp_acm_update_ring": (C.c_int, [_vp, C.c_int, _i64p, C.c_int, C.c_uint64, _f32p]),
+    "spp_set_learning_rates": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "spp_rollout_step_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_double, C.c_int, C.c_int, _f32p, _f32p]),
     "spp_rollout_synthetic_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_double, _vp]),
     "spp_ppo_create": (C.c_int, [C.POINTER(PpoConfig), C.c_int, C.POINTER(_vp)]),
@@ -106,6 +107,7 @@ SIGNATURES = {
     "spp_ppo_actor_minibatch_grad": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64]),
     "spp_ppo_actor_apply": (C.c_int, [_vp]),
     "spp_ppo_scalars": (C.c_int, [_vp, _f32p]),
+    "spp_ppo_act": (C.c_int, [_vp, C.c_int64, _f32p, _f32p, C.c_int, _f32p, _f32p, _f32p]),
     "spp_ppo_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), _i32p, C.POINTER(_vp)]),
     "spp_debug_scratch": (C.c_int, [_vp, C.c_int, C.c_char_p, _f32p, C.c_int, _i32p, _i32p]),
     "spp_device_info": (C.c_int, [C.c_int, _i32p, _i32p, _i32p, C.c_char_p, C.c_int]),

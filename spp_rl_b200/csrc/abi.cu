@@ -447,6 +447,15 @@ int spp_alpha_set(spp_population* p, int a, double log_alpha) {
     return SPP_OK;
 }
 
+int spp_set_learning_rates(spp_population* p, double actor_lr, double critic_lr, double alpha_lr, double acm_lr) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    if (actor_lr >= 0) p->h.actor_lr = actor_lr;
+    if (critic_lr >= 0) p->h.critic_lr = critic_lr;
+    if (alpha_lr >= 0) p->h.alpha_lr = alpha_lr;
+    if (acm_lr >= 0) p->h.acm_lr = acm_lr;
+    return SPP_OK;
+}
+
 // ---- replay ring -----------------------------------------------------------------------------------
 static int ring_check(spp_population* p, int a) {
     if (!p) return fail(SPP_ERR_ARG, "null population");
@@ -711,7 +720,7 @@ static void fill_acm_args(spp_population* p, UpdateArgs& a, int n) {
     a.scratch = p->scratch_acm;
 }
 
-int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, float* losses) {
+int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses) {
     if (!p || !x || !y) return fail(SPP_ERR_ARG, "spp_acm_update_host: null argument");
     if (n_batches < 1) return fail(SPP_ERR_ARG, "n_batches must be positive");
     CK(cudaSetDevice(p->device));
@@ -724,6 +733,8 @@ int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const 
     CK(p->d_losses.ensure((size_t)p->P * n_batches * 4));
     UpdateArgs a;
     fill_acm_args(p, a, n_batches);
+    if (last_rows < 0 || last_rows > L.B) return fail(SPP_ERR_ARG, "last_rows outside [0, acm_batch_size]");
+    a.acm_last_rows = (last_rows == L.B) ? 0 : last_rows;
     a.batch.acm_x = (const float*)p->d_obs.p;
     a.batch.acm_y = (const float*)p->d_aacm.p;
     a.losses = (float*)p->d_losses.p;
@@ -734,7 +745,7 @@ int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const 
     return SPP_OK;
 }
 
-int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, uint64_t seed, float* losses) {
+int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, int last_rows, uint64_t seed, float* losses) {
     if (!p) return fail(SPP_ERR_ARG, "null population");
     if (p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
     if (n_batches < 1) return fail(SPP_ERR_ARG, "n_batches must be positive");
@@ -746,9 +757,11 @@ int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, ui
     cudaStream_t s = p->stream;
     if (idx) {
         for (int a = 0; a < p->P; ++a)
-            for (size_t k = 0; k < per; ++k)
+            for (size_t k = 0; k < per; ++k) {
+                if (last_rows > 0 && k >= per - L.B + (size_t)last_rows) break;      // unused tail of a partial last batch
                 if (idx[(size_t)a * per + k] < 0 || idx[(size_t)a * per + k] >= p->cur_len[a])
                     return fail(SPP_ERR_ARG, "sample index outside [0, len(buffer))");
+            }
         CK(p->d_idx.ensure(rows * sizeof(int64_t)));
         CK(cudaMemcpyAsync(p->d_idx.p, idx, rows * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     }
@@ -756,6 +769,8 @@ int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, ui
     CK(p->d_losses.ensure((size_t)p->P * n_batches * 4));
     UpdateArgs a;
     fill_acm_args(p, a, n_batches);
+    if (last_rows < 0 || last_rows > L.B) return fail(SPP_ERR_ARG, "last_rows outside [0, acm_batch_size]");
+    a.acm_last_rows = (last_rows == L.B) ? 0 : last_rows;
     a.idx = idx ? (const int64_t*)p->d_idx.p : nullptr;
     a.seed = seed;
     a.losses = (float*)p->d_losses.p;

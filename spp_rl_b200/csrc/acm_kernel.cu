@@ -16,7 +16,7 @@ __device__ inline void acm_gather(const Ctx& c, int g) {
             const RingPtrs& R = c.a.ring;
             int64_t i;
             if (c.a.idx) {
-                i = c.a.idx[((size_t)c.agent * c.a.G + g) * B + r];
+                i = c.a.idx[((size_t)c.agent * c.a.G + g) * (c.a.batch_row_stride > 0 ? c.a.batch_row_stride : B) + r];
             } else {
                 const uint4 x = Philox::gen(c.a.seed ^ 0x51ED270B0B5ull, ((uint64_t)c.agent << 32) | (uint32_t)g,
                                             (c.a.seq << 20) | (uint32_t)r);
@@ -28,7 +28,8 @@ __device__ inline void acm_gather(const Ctx& c, int g) {
             for (int j = lane; j < ob; j += 32) { xm[r * L.ldm + j] = po[j]; xm[r * L.ldm + ldo + j] = pn[j]; }
             for (int j = lane; j < L.ac; j += 32) ya[r * L.lda + j] = R.aacm[(base + i) * L.lda + j];
         } else {
-            const size_t row = ((size_t)c.agent * c.a.G + g) * B + r;
+            const int stride = c.a.batch_row_stride > 0 ? c.a.batch_row_stride : B;
+            const size_t row = ((size_t)c.agent * c.a.G + g) * stride + r;
             const float* px = c.a.batch.acm_x + row * 2 * ob;
             for (int j = lane; j < ob; j += 32) { xm[r * L.ldm + j] = px[j]; xm[r * L.ldm + ldo + j] = px[ob + j]; }
             for (int j = lane; j < L.ac; j += 32) ya[r * L.lda + j] = c.a.batch.acm_y[row * L.ac + j];
@@ -138,7 +139,15 @@ __global__ void __launch_bounds__(kThreads, 1) acm_train_kernel(const __grid_con
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
         Ctx c(a, agent, sm);
-        for (int g = 0; g < a.G; ++g) acm_train_step(c, g);
+        const int full = (a.acm_last_rows > 0) ? a.G - 1 : a.G;
+        for (int g = 0; g < full; ++g) acm_train_step(c, g);
+        if (a.acm_last_rows > 0) {       // DataLoader keeps the partial last minibatch (drop_last = False)
+            UpdateArgs tail = a;
+            tail.L.B = a.acm_last_rows;
+            tail.batch_row_stride = a.L.B;
+            Ctx ct(tail, agent, sm);
+            acm_train_step(ct, a.G - 1);
+        }
     }
 }
 

@@ -405,6 +405,26 @@ int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int b
     return SPP_OK;
 }
 
+int spp_ppo_act(spp_ppo* p, int64_t E, const float* obs, const float* noise, int denormalize_actor_out, float* action, float* logp,
+                float* target) {
+    if (!p || !obs || !noise || !action || !logp || !target) return spp_set_error_(SPP_ERR_ARG, "spp_ppo_act: null argument");
+    if (E < 1 || E > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "E outside [1, max_batch_rows]");
+    PCK(cudaSetDevice(p->device));
+    cudaStream_t s = p->stream;
+    const int ob = p->L.ob, ldo = p->L.ldo;
+    PCK(cudaMemcpyAsync(p->raw, obs, (size_t)E * ob * 4, cudaMemcpyHostToDevice, s));
+    PCK(launch_ppo_normalize_rows(p->raw, p->b.x, E, ob, ldo, p->norm, p->cfg.min_max_denormalize ? 0 : 1, p->grid * 4, s)); spp_count_launch_();
+    PCK(cudaMemcpy2DAsync(p->s.d3, ldo * 4, noise, ob * 4, ob * 4, E, cudaMemcpyHostToDevice, s));
+    p->b.n = E; p->b.n_mean = E;
+    PpoArgs a; fill(p, a, E); a.mode = denormalize_actor_out ? 1 : 0;
+    PCK(launch_ppo_act(a, p->grid, s)); spp_count_launch_();
+    PCK(cudaMemcpy2DAsync(action, ob * 4, p->b.act, ldo * 4, ob * 4, E, cudaMemcpyDeviceToHost, s));
+    PCK(cudaMemcpy2DAsync(target, ob * 4, p->b.xn, ldo * 4, ob * 4, E, cudaMemcpyDeviceToHost, s));
+    PCK(cudaMemcpyAsync(logp, p->b.logp, (size_t)E * 4, cudaMemcpyDeviceToHost, s));
+    PCK(cudaStreamSynchronize(s));
+    return SPP_OK;
+}
+
 int spp_ppo_grad_buffer(spp_ppo* p, void** dev_ptr, int* n_floats, void** scal_ptr) {
     if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
     if (dev_ptr) *dev_ptr = p->gbuf;

@@ -273,6 +273,49 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_actor_grad_kernel(const __gri
     gemm<SmallTile, false>(dz1, kPpoHidden, X, ldo, kPpoHidden, ldo, ck.rows, smem, g1);
 }
 
+// ------------------------------------------------------------------------------------------------ on-policy act
+// Rollout step of A2C.collect_batch (rltoolkit/algorithms/a2c/a2c.py:165-166): x = Memory.normalize(obs) (already in
+// a.b.x), mean = tanh(fc3(tanh(fc2(tanh(fc1 x))))) * lim, action = mean + noise * exp(log_scale) (Normal.sample),
+// logp = Independent(Normal).log_prob(action) (rltoolkit/basic_model.py:32-51).  Outputs: a.b.act (sampled target,
+// normalised space), a.b.logp, a.b.xn (denormalised target handed to the ACM, rltoolkit/acm/on_policy.py:46-47).
+// `a.b.adv` holds nothing here; the noise comes in through a.s.d3.
+__global__ void __launch_bounds__(kThreads, 1) ppo_act_kernel(const __grid_constant__ PpoArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const Chunk ck = my_chunk(a.b.n, a.rows_per_cta);
+    if (ck.rows == 0) return;
+    const int ob = a.L.ob, ldo = a.L.ldo;
+    const LayerDesc& l0 = a.L.actor.L[0]; const LayerDesc& l1 = a.L.actor.L[1]; const LayerDesc& l2 = a.L.actor.L[2]; const LayerDesc& l3 = a.L.actor.L[3];
+    const float* X = a.b.x + ck.r0 * ldo;
+    float* h1 = a.s.h1 + ck.r0 * kPpoHidden; float* h2 = a.s.h2 + ck.r0 * kPpoHidden;
+    float* mean = a.s.mean + ck.r0 * ldo;
+    const float* lim = a.norm + NORM_LIM * ldo; const float* doff = a.norm + NORM_DOFF * ldo; const float* dsc = a.norm + NORM_DSCALE * ldo;
+    EpiBiasAct<ACT_TANH, false, false> e1{h1, kPpoHidden, a.actor + l0.off_b, nullptr, nullptr, 0, nullptr, 0, 0.f};
+    gemm<MidTile, true>(X, ldo, a.actor + l0.off_wt, l0.ld_t, ck.rows, kPpoHidden, ldo, smem, e1);
+    __syncthreads();
+    EpiBiasAct<ACT_TANH, false, false> e2{h2, kPpoHidden, a.actor + l1.off_b, nullptr, nullptr, 0, nullptr, 0, 0.f};
+    gemm<MidTile, true>(h1, kPpoHidden, a.actor + l1.off_wt, l1.ld_t, ck.rows, kPpoHidden, kPpoHidden, smem, e2);
+    __syncthreads();
+    EpiBiasAct<ACT_TANH, true, false> e3{mean, ldo, a.actor + l2.off_b, lim, nullptr, 0, nullptr, 0, 0.f};
+    gemm<NarrowTile, true>(h2, kPpoHidden, a.actor + l2.off_wt, l2.ld_t, ck.rows, ob, kPpoHidden, smem, e3);
+    __syncthreads();
+    const float* ls = a.actor + l3.off_w;
+    const float kLogSqrt2Pi = 0.918938533204672741780329736406f;
+    for (int i = threadIdx.x; i < ck.rows; i += kThreads) {
+        const int64_t r = ck.r0 + i;
+        float lp = 0.f;
+        for (int j = 0; j < ob; ++j) {
+            const float sd = expf(ls[j]);
+            const float mu = mean[(size_t)i * ldo + j];
+            const float act = __fadd_rn(mu, __fmul_rn(a.s.d3[r * ldo + j], sd));
+            const float d = __fsub_rn(act, mu);
+            lp += __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, __fmul_rn(sd, sd))), logf(sd)), kLogSqrt2Pi);
+            a.b.act[r * ldo + j] = act;
+            a.b.xn[r * ldo + j] = (a.mode == 1) ? __fadd_rn(doff[j], __fmul_rn(act, dsc[j])) : act;
+        }
+        a.b.logp[r] = lp;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ reduce / Adam
 __global__ void ppo_reduce_kernel(const float* __restrict__ part, int stride, int n_part, int n, float* __restrict__ out,
                                   const float* __restrict__ scal, float* __restrict__ gscal) {
@@ -397,6 +440,12 @@ cudaError_t launch_ppo_actor_grad(const PpoArgs& a, int grid, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(ppo_actor_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPpoSmem);
     if (e != cudaSuccess) return e;
     ppo_actor_grad_kernel<<<grid, kThreads, kPpoSmem, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_ppo_act(const PpoArgs& a, int grid, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(ppo_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPpoSmem);
+    if (e != cudaSuccess) return e;
+    ppo_act_kernel<<<grid, kThreads, kPpoSmem, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_ppo_reduce(const PpoArgs& a, int n_part, int n_elems, cudaStream_t s) {

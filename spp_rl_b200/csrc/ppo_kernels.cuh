@@ -97,6 +97,7 @@ enum { PS_LOSS = 0, PS_ENTROPY = 1, PS_DIST = 2, PS_KL = 3, PS_COUNT = 8 };
 cudaError_t launch_ppo_critic_values(const PpoArgs& a, int grid, cudaStream_t s);      // v, nv, q
 cudaError_t launch_ppo_critic_grad(const PpoArgs& a, int grid, cudaStream_t s);        // partial grads of 0.5 mean((q - V)^2)
 cudaError_t launch_ppo_actor_grad(const PpoArgs& a, int grid, cudaStream_t s);         // partial grads of the clipped loss
+cudaError_t launch_ppo_act(const PpoArgs& a, int grid, cudaStream_t s);                // on-policy rollout step
 cudaError_t launch_ppo_reduce(const PpoArgs& a, int n_part, int n_elems, cudaStream_t s);
 cudaError_t launch_ppo_adam(const PpoArgs& a, int which_net, int step, double lr, cudaStream_t s);
 cudaError_t launch_ppo_gae(const PpoArgs& a, cudaStream_t s);

@@ -45,7 +45,9 @@ __device__ inline void rollout_post(const Ctx& c, const RolloutArgs& r, int step
             ez = normal_from_bits(w.z, w.w);
         }
         float z;
-        if (r.random_phase) {
+        if (r.random_phase == 2) {
+            z = nz;                                                      // caller supplies the state target (process_action only)
+        } else if (r.random_phase) {
             z = __fmul_rn(lim[j], nz);                                   // actor_ac_lim * randn (off_policy.py:51)
         } else {
             if (ALGO == ALGO_SAC) {

@@ -65,6 +65,8 @@ struct UpdateArgs {
     float* losses;           // [P][G][8] or null
     int G;
     int population;
+    int batch_row_stride;    // rows between consecutive steps in the staged batch / index arrays (0 = L.B)
+    int acm_last_rows;       // ACM regression: rows of the final step when it is a partial batch (0 = full)
 };
 
 enum { LOSS_CRITIC_1 = 0, LOSS_CRITIC_2 = 1, LOSS_ACTOR = 2, LOSS_PI = 3, LOSS_DIST = 4, LOSS_ALPHA = 5, LOSS_ALPHA_VALUE = 6, LOSS_COUNT = 8 };

@@ -140,6 +140,9 @@ class Population:
             out[name] = (m, v)
         return out, step.value
 
+    def set_learning_rates(self, actor_lr=-1.0, critic_lr=-1.0, alpha_lr=-1.0, acm_lr=-1.0):
+        check(self.lib.spp_set_learning_rates(self.h, float(actor_lr), float(critic_lr), float(alpha_lr), float(acm_lr)))
+
     def sync_targets(self, agent=-1):
         check(self.lib.spp_sync_targets(self.h, agent))
 
@@ -217,18 +220,18 @@ class Population:
         check(self.lib.spp_update_ring_device(self.h, int(grad_steps), int(seed), losses_dev_ptr, stream))
 
     # ------------------------------------------------------------------ ACM regression
-    def acm_update_host(self, n_batches, x, y, losses=None):
+    def acm_update_host(self, n_batches, x, y, losses=None, last_rows=0):
         """n x AcMTrainer.batch_update(x, y): x [P, n, acm_batch_size, 2*ob], y [P, n, acm_batch_size, ac] -> losses [P, n]"""
         if losses is None:
             losses = np.empty((self.P, n_batches), np.float32)
-        check(self.lib.spp_acm_update_host(self.h, int(n_batches), _ptr(x, C.c_float), _ptr(y, C.c_float), _ptr(losses, C.c_float)))
+        check(self.lib.spp_acm_update_host(self.h, int(n_batches), _ptr(x, C.c_float), _ptr(y, C.c_float), int(last_rows), _ptr(losses, C.c_float)))
         return losses
 
-    def acm_update_ring(self, n_batches, idx=None, seed=0, losses=None):
+    def acm_update_ring(self, n_batches, idx=None, seed=0, losses=None, last_rows=0):
         """AcMTrainer.update_acm_batches(n) from the device ring; idx int64 [P, n, acm_batch_size] or None."""
         if losses is None:
             losses = np.empty((self.P, n_batches), np.float32)
-        check(self.lib.spp_acm_update_ring(self.h, int(n_batches), _ptr(idx, C.c_int64), int(seed), _ptr(losses, C.c_float)))
+        check(self.lib.spp_acm_update_ring(self.h, int(n_batches), _ptr(idx, C.c_int64), int(last_rows), int(seed), _ptr(losses, C.c_float)))
         return losses
 
     # ------------------------------------------------------------------ rollout
@@ -241,7 +244,7 @@ class Population:
         tgt = np.empty((self.P, E, self.ob_dim), np.float32)
         act = np.empty((self.P, E, self.ac_dim), np.float32)
         check(self.lib.spp_rollout_step_host(self.h, int(E), _ptr(obs, C.c_float), _ptr(noise, C.c_float), _ptr(eps, C.c_float),
-                                             int(bool(random_phase)), float(act_noise), int(bool(obs_norm)),
+                                             int(random_phase), float(act_noise), int(bool(obs_norm)),
                                              int(bool(denormalize_actor_out)), _ptr(tgt, C.c_float), _ptr(act, C.c_float)))
         return tgt, act
 

@@ -102,6 +102,16 @@ class PpoPolicy:
                                             _ptr(logp, C.c_float), _ptr(rew, C.c_float), _ptr(done, C.c_float), _ptr(end, C.c_float),
                                             _ptr(ts, C.c_int64), _ptr(tl, C.c_int64), int(ts.size), int(traj_stride), int(global_rows)))
 
+    def act(self, obs, noise, denormalize_actor_out=True):
+        """Actor.act + denormalise for E observations: -> (action [E, ob], logp [E], acm_target [E, ob])."""
+        obs, noise = _f32(obs), _f32(noise)
+        E = obs.shape[0]
+        action = np.empty((E, self.ob_dim), np.float32); target = np.empty((E, self.ob_dim), np.float32)
+        logp = np.empty(E, np.float32)
+        check(self.lib.spp_ppo_act(self.h, E, _ptr(obs, C.c_float), _ptr(noise, C.c_float), int(bool(denormalize_actor_out)),
+                                   _ptr(action, C.c_float), _ptr(logp, C.c_float), _ptr(target, C.c_float)))
+        return action, logp, target
+
     # ------------------------------------------------------------------ single-GPU forms
     def update_critic(self, n_target_updates=10, n_updates_per_target=10):
         loss = C.c_float()

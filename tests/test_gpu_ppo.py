@@ -119,3 +119,52 @@ def test_ppo_step_major_large_batch_matches_oracle():
     for k, val in sd.items():
         assert relnorm(val, s["actor." + k].numpy()) < 2e-5, (k, relnorm(val, s["actor." + k].numpy()))
     pol.close()
+
+
+def test_on_policy_rollout_step_matches_oracle():
+    """P1: Memory.normalize -> Actor.act -> process_action, incl. quirk 18 (normalised obs next to a denormalised target)."""
+    from oracle import rollout as R
+    from spp_rl_b200 import Population, init_state
+    ob, ac, E = 17, 6, 300
+    rng = np.random.RandomState(5)
+    mn, mx = (-rng.rand(ob) * 2 - 0.5).astype(np.float32), (rng.rand(ob) * 2 + 0.5).astype(np.float32)
+    obs = (rng.rand(E, ob) * (mx - mn) + mn).astype(np.float32)
+    noise = rng.randn(E, ob).astype(np.float32)
+    s = {}
+    for name, o, i in (("fc1", 64, ob), ("fc2", 64, 64), ("fc3", ob, 64)):
+        b = 1 / np.sqrt(i)
+        s["actor." + name + ".weight"] = torch.from_numpy(rng.uniform(-b, b, (o, i)).astype(np.float32))
+        s["actor." + name + ".bias"] = torch.from_numpy(rng.uniform(-b, b, (o,)).astype(np.float32))
+    s["actor.log_scale"] = torch.full((ob,), -1.34)
+    acm0 = {k: v for k, v in init_state("sac", ob, ac, 77).items() if k.startswith("acm.")}
+    s.update({k: torch.from_numpy(v) for k, v in acm0.items()})
+    st = NormStats(True, torch.from_numpy(mn), torch.from_numpy(mx))
+    a_ref, lp_ref, acm_ref = R.on_policy_step(s, st, torch.from_numpy(obs), torch.from_numpy(noise), 1.0, torch.ones(ac))
+    pol = PpoPolicy(ob, ac, max_rows=1024, max_batch_rows=1024, min_max_denormalize=True)
+    pol.set_norm_stats(mn, mx)
+    pol.load_state_dict("actor", {k[6:]: v for k, v in s.items() if k.startswith("actor.")})
+    action, logp, target = pol.act(obs, noise)
+    np.testing.assert_allclose(action, a_ref.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(logp, lp_ref.numpy(), rtol=1e-5, atol=1e-5)
+    pop = Population(algo="sac", ob_dim=ob, ac_dim=ac, population=1, min_max_denormalize=True, update_batch_size=64)
+    pop.set_norm_stats(mn, mx)
+    pop.load_state_dict("acm", {k[4:]: v for k, v in acm0.items()})
+    tgt2, acm_action = pop.rollout_step(obs[None], action[None], None, random_phase=True, obs_norm=True, denormalize_actor_out=True)
+    np.testing.assert_allclose(tgt2[0], target, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(acm_action[0], acm_ref.numpy(), rtol=1e-5, atol=2e-6)
+    pol.close(); pop.close()
+
+
+def test_acm_ring_add_buffer_joint_quirk():
+    """P7: ReplayBufferAcM.add_buffer (rltoolkit/buffer/replay_buffer.py:284-297) through the ring ABI, joint quirk included."""
+    from spp_rl_b200 import Population
+    from spp_rl_b200.rltoolkit_api import add_rollouts_to_acm_ring
+    g = np.load(os.path.join(G, "acm_add_buffer.npz"))
+    ob, ac = g["chain"].shape[1], g["acts"].shape[1]
+    pop = Population(algo="sac", ob_dim=ob, ac_dim=ac, population=1, buffer_size=40, update_batch_size=8, acm_batch_size=8)
+    add_rollouts_to_acm_ring(pop, 0, g["chain"], g["acts"], list(g["joints"]))
+    L = int(g["length"])
+    assert pop.ring_state(0)[2] == L
+    obs, nobs, _, _, _, aacm = pop.ring_sample_batch(0, np.arange(L, dtype=np.int64))
+    assert np.array_equal(obs, g["obs"]) and np.array_equal(nobs, g["next_obs"]) and np.array_equal(aacm, g["actions_acm"])
+    pop.close()
