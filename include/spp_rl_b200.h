@@ -226,6 +226,10 @@ int spp_ppo_grad_buffer(spp_ppo* p, void** dev_ptr, int* n_floats, void** scal_p
 /* copy a named scratch buffer of agent a to host ("xo","xn","xc","xcp","xm","ha1","ha2","ml","hc1_0",...);
  * rows/ld describe the returned dense [rows x ld] block. */
 int spp_debug_scratch(spp_population* p, int a, const char* name, float* host, int cap, int* rows, int* ld);
+/* tcgen05 building-block self-test: C[128x128] = A * B on one CTA through kind::tf32 tensor-core MMAs.
+ * a_mn / b_mn: 0 = operand stored [128][K] (contraction contiguous), 1 = stored [K][128]; split: 0 = one tf32 pass,
+ * 1 = three-pass hi/lo split (fp32-accurate).  K a multiple of 4.  Host arrays. */
+int spp_umma_selftest(int a_mn, int b_mn, int K, int split, const float* A, const float* B, float* C);
 int spp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_cap);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t spp_kernel_launches(void);
