@@ -230,6 +230,13 @@ int spp_debug_scratch(spp_population* p, int a, const char* name, float* host, i
  * a_mn / b_mn: 0 = operand stored [128][K] (contraction contiguous), 1 = stored [K][128]; split: 0 = one tf32 pass,
  * 1 = three-pass hi/lo split (fp32-accurate).  K a multiple of 4.  Host arrays. */
 int spp_umma_selftest(int a_mn, int b_mn, int K, int split, const float* A, const float* B, float* C);
+/* the pipelined tensor-core GEMM of the fused kernels, C[M x 256] = A . B (three-pass split), on one CTA.
+ * a_km: A stored [M][K] (1) or [K][M] (0); b_km: B stored [256][K] (1) or [K][256] (0); M <= 256, M and K multiples of 4;
+ * reps repeats the product inside the kernel; ms_out (optional) receives the kernel time.  Host arrays. */
+int spp_umma_gemm_selftest(int a_km, int b_km, int M, int K, int reps, const float* A, const float* B, float* C, float* ms_out);
+/* process-wide A/B switch for the 128 x 128 GEMMs of the update burst: 1 = tcgen05 (3-pass tf32 split, default),
+ * 0 = FFMA tiles.  Both are device paths. */
+int spp_set_gemm_path(int tensor_cores);
 int spp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_cap);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t spp_kernel_launches(void);

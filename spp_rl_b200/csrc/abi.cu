@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -602,6 +603,10 @@ int spp_ring_gather_bench_device(spp_population* p, int n_batches, uint64_t seed
 }
 
 // ---- update ----------------------------------------------------------------------------------------
+// 1: the 128 x 128 GEMMs of the update burst run on tcgen05 (3-pass tf32 split); 0: FFMA tiles.  Both are device paths;
+// the switch exists for A/B measurement and kernel bisection (environment SPP_UMMA=0 or spp_set_gemm_path).
+static std::atomic<int> g_gemm_path{[] { const char* e = getenv("SPP_UMMA"); return (e && e[0] == '0') ? 0 : 1; }()};
+
 static void fill_args(spp_population* p, UpdateArgs& a, int G) {
     memset(&a, 0, sizeof(a));
     a.L = p->L; a.h = p->h;
@@ -611,6 +616,7 @@ static void fill_args(spp_population* p, UpdateArgs& a, int G) {
     a.ring_len = p->r_len;
     a.G = G; a.population = p->P;
     a.seq = p->seq++;
+    a.use_umma = g_gemm_path.load();
 }
 
 static int grid_for(const spp_population* p) { return p->P < p->sm_count ? p->P : p->sm_count; }
@@ -859,6 +865,11 @@ int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t s
 }
 
 // ---- introspection ---------------------------------------------------------------------------------
+int spp_set_gemm_path(int tensor_cores) {
+    g_gemm_path.store(tensor_cores ? 1 : 0);
+    return SPP_OK;
+}
+
 int spp_debug_scratch(spp_population* p, int a, const char* name, float* host, int cap, int* rows, int* ld) {
     if (!p || !name || !host || a < 0 || a >= p->P) return fail(SPP_ERR_ARG, "bad argument");
     const Layout& L = p->L; const ScratchDesc& s = L.s;

@@ -136,7 +136,7 @@ __device__ void acm_train_step(const Ctx& c, int g) {
 
 __global__ void __launch_bounds__(kThreads, 1) acm_train_kernel(const __grid_constant__ UpdateArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    Smem& sm = smem_struct(smem_raw);
     for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
         Ctx c(a, agent, sm);
         const int full = (a.acm_last_rows > 0) ? a.G - 1 : a.G;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) acm_train_kernel(const __grid_con
 }
 
 cudaError_t launch_acm_train(const UpdateArgs& a, int grid, cudaStream_t stream) {
-    const size_t smem = sizeof(Smem);
+    const size_t smem = kSmemLaunchBytes;
     cudaError_t e = cudaFuncSetAttribute(acm_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     acm_train_kernel<<<grid, kThreads, smem, stream>>>(a);

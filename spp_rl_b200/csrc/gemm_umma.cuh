@@ -1,0 +1,238 @@
+// Tensor-core GEMM of the fused kernels: C[M x 256] = A . B with M <= 256, on tcgen05 kind::tf32 with the three-pass
+// hi/lo split (umma.cuh), accurate to fp32-FMA level.
+//
+//   A_KM = true : A is [M x K] row-major (contraction contiguous): forward x, dY of a dX product        -> K-major tile
+//   A_KM = false: A is [K x M] row-major (contraction = batch): dY of a dW product                      -> MN-major tile
+//   B_KM = true : B is [256 x K] row-major (the natural torch weight in a forward)                       -> K-major tile
+//   B_KM = false: B is [K x 256] row-major (W^T in a forward, W in dX, the layer input in dW)            -> MN-major tile
+//
+// Accuracy.  The tensor core adds every MMA's 8-product sum into the fp32 TMEM accumulator with TRUNCATION (measured:
+// all-positive data, K = 256, one accumulator: bias -1.6e-6 relative, linear in the number of accumulations; see
+// tools/umma_accum_error.py).  A K = 256 product accumulated in place is therefore 6x less accurate than an fp32 FMA chain,
+// which the 1e-5 parity bar of this project does not survive through Adam.  Two measures bring it back to fp32 level:
+//   (1) the accumulator only ever holds ONE 32-wide k-chunk: chunks alternate between two TMEM accumulators and each
+//       finished chunk is drained (tcgen05.ld) and added to a running sum in registers with round-to-nearest fp32 adds
+//       while the tensor core works on the next chunk;
+//   (2) inside a chunk the small cross terms (lo*hi, hi*lo, 2^-11 of the result) are issued first, while the accumulator
+//       is still tiny, so only the 4 hi*hi MMAs of a chunk truncate at full magnitude.
+//
+// Tiling.  One tile is 128 rows x 256 columns (two tiles for M > 128): TMEM = 2 accumulators x 256 columns.  Shared memory
+// = 2 slots x [A_hi 16 KB | A_lo 16 KB | B_hi 32 KB | B_lo 32 KB] in the SWIZZLE_128B layouts of umma.cuh.  Per chunk all
+// 256 threads split 12 float4 each (global -> registers one chunk ahead -> hi/lo -> swizzled st.shared), one thread issues
+// 12 MMAs of 128 x 256 x 8 and commits them to the slot's mbarrier, then everybody drains the previous chunk.  After the
+// last chunk the running sums go through a shared staging buffer to the epilogue functors of gemm_tile.cuh in their
+// register mapping (coalesced global traffic).
+#pragma once
+#include "gemm_tile.cuh"
+#include "umma.cuh"
+
+namespace spp {
+
+constexpr int kUmmaAPlane = 128 * 128;                     // A_hi / A_lo: 128 rows x 32 tf32
+constexpr int kUmmaBPlane = 256 * 128;                     // B_hi / B_lo: 256 columns x 32 tf32
+constexpr int kUmmaSlotBytes = 2 * kUmmaAPlane + 2 * kUmmaBPlane;      // 96 KB
+constexpr int kUmmaSlots = 2;
+constexpr int kUmmaSmemBytes = kUmmaSlots * kUmmaSlotBytes;            // 192 KB
+constexpr int kUmmaTmemCols = 512;
+constexpr int kStagePitch = 132;                           // floats; conflict-free accumulator staging
+constexpr int kStageBlockFloats = 128 * kStagePitch;       // one 128 x 128 block
+static_assert(2 * kStageBlockFloats * 4 <= kUmmaSmemBytes, "accumulator staging aliases the operand slots");
+
+struct UmmaCtx {
+    unsigned char* smem;        // 1024-byte aligned, kUmmaSmemBytes
+    uint64_t* mbar;             // [kUmmaSlots]: "the MMAs of the chunk in this slot have retired"
+    uint32_t tmem;              // TMEM base (512 columns)
+    uint32_t phase_bits;        // per-slot mbarrier parity this thread waits for next (identical in every thread)
+    uint32_t dbg;               // timing experiments only (self-test): 1 = no MMAs, 2 = no operand staging, 4 = no epilogue
+};
+
+// Per-thread state of one operand's global -> register -> shared path.  ROWS = 128 (A) or 256 (B); NP float4 per thread
+// and 32-wide k-chunk.  Source pointer and swizzled destination are affine in the chunk index p.
+template <bool KM, int ROWS>
+struct UmmaOperand {
+    static constexpr int NP = ROWS * 8 / kThreads;              // 4 or 8
+    static constexpr int CPR = ROWS / 4;                        // MN-major: float4 per k-row (32 or 64)
+    static constexpr int KSTEP = KM ? 0 : kThreads / CPR;       // MN-major: k-rows between consecutive p (8 or 4)
+    static constexpr uint32_t DSTEP = KM ? 4096u : (uint32_t)(KSTEP / 4) * 512u;
+    const float* src0;
+    size_t sstep;               // floats between consecutive p
+    size_t kstride;             // floats per unit of k
+    uint32_t dst0;
+    int kofs0;                  // k offset of chunk p inside the 32-wide k-chunk: kofs0 + p * KSTEP
+    int np_ok;                  // chunks p < np_ok are inside the operand (rows / columns tail)
+    // r0: first row (column) of the tile inside the operand, R: rows (columns) of the whole operand
+    __device__ __forceinline__ void init(const float* __restrict__ G, int ld, int R, int r0) {
+        if constexpr (KM) {      // 64 threads cover 8 rows x 128 B; quarter-warps hit 8 distinct swizzle positions
+            const int q = (threadIdx.x >> 3) & 7;
+            const int row = (threadIdx.x >> 6) * 8 + (threadIdx.x & 7);      // + 32 p
+            kstride = 1; kofs0 = 4 * q;
+            src0 = G + (size_t)(r0 + row) * ld + 4 * q;
+            sstep = (size_t)32 * ld;
+            dst0 = umma::kmajor_offset(row, q);
+            const int left = R - r0 - row;                                   // rows row + 32 p < R - r0
+            np_ok = left <= 0 ? 0 : min(NP, (left + 31) / 32);
+        } else {                 // a warp covers 512 contiguous bytes of one k-row
+            const int chunk = threadIdx.x % CPR, kb = threadIdx.x / CPR;     // k = kb + KSTEP p
+            kstride = (size_t)ld; kofs0 = kb;
+            src0 = G + (size_t)kb * ld + r0 + 4 * chunk;
+            sstep = (size_t)KSTEP * ld;
+            dst0 = umma::mnmajor_offset(kb, chunk);
+            np_ok = (r0 + 4 * chunk < R) ? NP : 0;
+        }
+    }
+    __device__ __forceinline__ void load(int k0, int K, float4 (&r)[NP]) const {
+        const float* s = src0 + (size_t)k0 * kstride;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const bool ok = (p < np_ok) && (k0 + kofs0 + p * KSTEP < K);
+            r[p] = ok ? __ldcg(reinterpret_cast<const float4*>(s + p * sstep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __device__ __forceinline__ void store(const float4 (&r)[NP], uint32_t hi, uint32_t lo) const {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float4 h, l;
+            umma::split_tf32(r[p].x, h.x, l.x); umma::split_tf32(r[p].y, h.y, l.y);
+            umma::split_tf32(r[p].z, h.z, l.z); umma::split_tf32(r[p].w, h.w, l.w);
+            umma::sts128(hi + dst0 + p * DSTEP, h);
+            umma::sts128(lo + dst0 + p * DSTEP, l);
+        }
+    }
+};
+
+// drain one finished chunk: this thread's row (TMEM lane) x 128 columns, added to the running sums
+template <bool FIRST>
+__device__ __forceinline__ void umma_drain(uint32_t taddr, float (&sum)[128]) {
+#pragma unroll
+    for (int cb = 0; cb < 8; cb += 2) {
+        float v0[16], v1[16];
+        umma::tmem_ld16_nowait(taddr + cb * 16, v0);
+        umma::tmem_ld16_nowait(taddr + cb * 16 + 16, v1);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            sum[cb * 16 + i] = FIRST ? v0[i] : __fadd_rn(sum[cb * 16 + i], v0[i]);
+            sum[cb * 16 + 16 + i] = FIRST ? v1[i] : __fadd_rn(sum[cb * 16 + 16 + i], v1[i]);
+        }
+    }
+}
+
+// staged accumulator (two 128 x 128 blocks) -> registers in the FFMA tiles' mapping -> epilogue functor.  Its own function so
+// that the epilogue's registers (Adam: 4 x 4 float4 of loads in flight) are allocated independently of the main loop's.
+template <bool A_KM, class Epi>
+__device__ __noinline__ void umma_epilogue(uint32_t stage_s, float* stage, int m0, int M, Epi& epi) {
+    const int tx = threadIdx.x % BigTile::TX, ty = threadIdx.x / BigTile::TX;
+#pragma unroll 1
+    for (int nh = 0; nh < 2; ++nh) {
+        float acc[BigTile::MI][BigTile::NJ];
+#pragma unroll
+        for (int i = 0; i < BigTile::MI; ++i) {
+            const int r = row_of<BigTile, A_KM>(i, ty);
+#pragma unroll
+            for (int g = 0; g < BigTile::NJ / 4; ++g) {
+                const float4 v = umma::lds128(stage_s + 4 * (nh * kStageBlockFloats + r * kStagePitch + col_of<BigTile>(4 * g, tx)));
+                acc[i][4 * g] = v.x; acc[i][4 * g + 1] = v.y; acc[i][4 * g + 2] = v.z; acc[i][4 * g + 3] = v.w;
+            }
+        }
+        __syncthreads();      // block nh of the staging is free (the epilogue may use it for column sums)
+        epi.template apply<BigTile, A_KM>(acc, m0, nh * 128, M, 256, stage + nh * kStageBlockFloats);
+    }
+}
+
+// Main loop of one 128 x 256 tile: leaves the fp32 result in the shared staging buffer (two 128 x 128 blocks of pitch
+// kStagePitch at the start of the operand slots).  A separate function (independent of the epilogue type) so that its
+// register allocation -- 128 running sums + 48 registers of operands in flight -- is not disturbed by the epilogue's.
+template <bool A_KM, bool B_KM>
+__device__ __noinline__ void umma_mainloop(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
+                                           int m0, unsigned char* smem, uint64_t* mbar, uint32_t tmem, uint32_t& phase_io, uint32_t dbg) {
+    using namespace umma;
+    constexpr int N = 256;
+    const int nchunks = (K + 31) / 32;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t idesc = make_idesc_tf32(128, N, A_KM ? 0 : 1, B_KM ? 0 : 1);
+    const int wq = warp_id() & 3, chalf = warp_id() >> 2;
+    const uint32_t my_tmem = tmem + ((uint32_t)(32 * wq) << 16) + chalf * 128;      // this thread's lane / column half
+    uint32_t phase_bits = phase_io;
+    UmmaOperand<B_KM, 256> lb;
+    lb.init(B, ldb, N, 0);
+    UmmaOperand<A_KM, 128> la;
+    la.init(A, lda, M, m0);
+    float sum[128];
+    float4 ra[4], rb[8];
+    la.load(0, K, ra);
+    lb.load(0, K, rb);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+        const int slot = c & 1;
+        const uint32_t ah = smem0 + slot * kUmmaSlotBytes, al = ah + kUmmaAPlane, bh = al + kUmmaAPlane, bl = bh + kUmmaBPlane;
+        // slot `slot` is free: the MMAs of chunk c - 2 were waited for when that chunk was drained (iteration c - 1)
+        if (!(dbg & 2)) {
+            la.store(ra, ah, al);
+            lb.store(rb, bh, bl);
+            if (c + 1 < nchunks) {
+                la.load(32 * (c + 1), K, ra);
+                lb.load(32 * (c + 1), K, rb);
+            }
+        }
+        fence_proxy_async();
+        fence_before_sync();      // orders this thread's drain of chunk c - 2 (same accumulator) before the MMAs below
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after_sync();
+            const uint32_t d = tmem + slot * N;
+            const int nks = (dbg & 1) ? 0 : min(4, (K - 32 * c + 7) / 8);
+            for (int ks = 0; ks < nks; ++ks) {      // cross terms first: the accumulator is still tiny
+                const uint64_t dah = A_KM ? kmajor_desc(ah, ks) : mnmajor_desc(ah, ks);
+                const uint64_t dal = A_KM ? kmajor_desc(al, ks) : mnmajor_desc(al, ks);
+                const uint64_t dbh = B_KM ? kmajor_desc(bh, ks) : mnmajor_desc(bh, ks);
+                const uint64_t dbl = B_KM ? kmajor_desc(bl, ks) : mnmajor_desc(bl, ks);
+                mma_tf32(d, dal, dbh, idesc, ks ? 1u : 0u);
+                mma_tf32(d, dah, dbl, idesc, 1u);
+            }
+            for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t dah = A_KM ? kmajor_desc(ah, ks) : mnmajor_desc(ah, ks);
+                const uint64_t dbh = B_KM ? kmajor_desc(bh, ks) : mnmajor_desc(bh, ks);
+                mma_tf32(d, dah, dbh, idesc, 1u);
+            }
+            commit(mbar + slot);
+        }
+        if (c >= 1) {       // drain chunk c - 1 while the tensor core works on chunk c
+            const int ps = slot ^ 1;
+            mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
+            phase_bits ^= (1u << ps);
+            fence_after_sync();
+            if (c == 1) umma_drain<true>(my_tmem + ps * N, sum);
+            else umma_drain<false>(my_tmem + ps * N, sum);
+        }
+    }
+    {   // last chunk
+        const int ps = (nchunks - 1) & 1;
+        mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
+        phase_bits ^= (1u << ps);
+        fence_after_sync();
+        if (nchunks == 1) umma_drain<true>(my_tmem + ps * N, sum);
+        else umma_drain<false>(my_tmem + ps * N, sum);
+        fence_before_sync();
+    }
+    phase_io = phase_bits;
+    {   // running sums -> shared staging; every MMA that read the slots has retired
+        const int srow = 32 * wq + lane_id();
+        const uint32_t base = smem0 + 4 * (chalf * kStageBlockFloats + srow * kStagePitch);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) sts128(base + 16 * q, make_float4(sum[4 * q], sum[4 * q + 1], sum[4 * q + 2], sum[4 * q + 3]));
+    }
+    __syncthreads();
+}
+
+template <bool A_KM, bool B_KM, class Epi>
+__device__ __forceinline__ void gemm256_umma(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
+                                             UmmaCtx& u, Epi& epi) {
+    const int mtiles = (M + 127) / 128;
+    for (int mt = 0; mt < mtiles; ++mt) {
+        umma_mainloop<A_KM, B_KM>(A, lda, B, ldb, M, K, mt * 128, u.smem, u.mbar, u.tmem, u.phase_bits, u.dbg);
+        if (!(u.dbg & 4)) umma_epilogue<A_KM, Epi>(umma::smem_u32(u.smem), reinterpret_cast<float*>(u.smem), mt * 128, M, epi);
+        __syncthreads();          // the staging aliases the operand slots of the next tile / GEMM
+    }
+}
+
+}  // namespace spp

@@ -116,7 +116,7 @@ __device__ inline void rollout_env_and_ring(const Ctx& c, const RolloutArgs& r, 
 template <int ALGO>
 __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_constant__ RolloutArgs r) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    Smem& sm = smem_struct(smem_raw);
     const UpdateArgs& a = r.u;
     for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
         Ctx c(a, agent, sm);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
 }
 
 cudaError_t launch_rollout(const RolloutArgs& r, int grid, cudaStream_t stream) {
-    const size_t smem = sizeof(Smem);
+    const size_t smem = kSmemLaunchBytes;
     cudaError_t e;
     if (r.u.L.algo == ALGO_SAC) {
         e = cudaFuncSetAttribute(rollout_kernel<ALGO_SAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

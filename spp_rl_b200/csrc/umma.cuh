@@ -118,15 +118,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split x = hi + lo for the 3-pass scheme
+// the same without the wait: issue several loads, then tmem_ld_wait() once before the registers are stored
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// split x = hi + lo for the 3-pass scheme: hi = rn_tf32(x), lo = rn_tf32(x - hi), round-to-nearest (ties away) done with
+// integer arithmetic on the bit pattern (cvt.rna.tf32.f32 is emulated on sm_100a with an Inf/NaN guard: 4 instructions per
+// conversion; operands here are finite, so the guard is dropped: add half an ulp of tf32, clear the 13 low mantissa bits).
+__device__ __forceinline__ float round_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    const float r = x - hi;
-    uint32_t l;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-    lo = __uint_as_float(l);
+    hi = round_tf32(x);
+    lo = round_tf32(__fsub_rn(x, hi));
+}
+
+// explicit shared-space 16-byte accesses (generic-pointer float4 accesses compile to LD.E / ST.E when the space is unknown)
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
 }
 
 }  // namespace umma

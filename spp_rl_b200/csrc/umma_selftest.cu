@@ -6,7 +6,7 @@
 
 #include "../../include/spp_rl_b200.h"
 #include "common.cuh"
-#include "umma.cuh"
+#include "gemm_umma.cuh"
 
 int spp_set_error_(int code, const std::string& msg);
 void spp_count_launch_();
@@ -101,7 +101,73 @@ __global__ void __launch_bounds__(kThreads, 1) umma_selftest_kernel(const float*
     if (warp_id() == 0) tmem_dealloc<128>(tmem_d);
 }
 
+// the full pipelined GEMM of the fused kernels (gemm_umma.cuh) with a plain store epilogue
+template <bool A_KM, bool B_KM>
+__global__ void __launch_bounds__(kThreads, 1) umma_gemm_selftest_kernel(const float* A, int lda, const float* B, int ldb, float* C, int M,
+                                                                        int K, int reps) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t mbar[kUmmaSlots];
+    __shared__ uint32_t tmem_base_s;
+    if (warp_id() == 0) tmem_alloc<kUmmaTmemCols>(&tmem_base_s);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kUmmaSlots; ++s) mbar_init(mbar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    UmmaCtx u{smem, mbar, tmem_base_s, 0u, (uint32_t)(reps >> 16)};
+    reps &= 0xFFFF;
+    EpiMaskStore<MASK_NONE, false, false> epi{C, 256, nullptr, 0, nullptr};
+    for (int r = 0; r < reps; ++r) gemm256_umma<A_KM, B_KM>(A, lda, B, ldb, M, K, u, epi);
+    fence_before_sync();
+    __syncthreads();
+    if (warp_id() == 0) tmem_dealloc<kUmmaTmemCols>(u.tmem);
+}
+
 }  // namespace spp
+
+// C[M x 256] = A . B through gemm256_umma; a_km: A stored [M][K] (1) or [K][M] (0); b_km: B stored [256][K] (1) or [K][256] (0).
+// M <= 256 and a multiple of 4, K a multiple of 4.  reps > 1 repeats the GEMM (pipeline state carried over); ms_out (optional)
+// receives the kernel time.
+extern "C" int spp_umma_gemm_selftest(int a_km, int b_km, int M, int K, int reps, const float* A, const float* B, float* C, float* ms_out) {
+    using namespace spp;
+    if (!A || !B || !C || M < 1 || M > 256 || K < 1 || (K % 4) != 0 || (M % 4) != 0 || reps < 1)
+        return spp_set_error_(SPP_ERR_ARG, "spp_umma_gemm_selftest: bad argument");
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e;
+#define UCK(x) if ((e = (x)) != cudaSuccess) { cudaFree(dA); cudaFree(dB); cudaFree(dC); return spp_set_error_(SPP_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e)); }
+    UCK(cudaMalloc(&dA, (size_t)M * K * 4)); UCK(cudaMalloc(&dB, (size_t)256 * K * 4)); UCK(cudaMalloc(&dC, (size_t)M * 256 * 4));
+    UCK(cudaMemcpy(dA, A, (size_t)M * K * 4, cudaMemcpyHostToDevice)); UCK(cudaMemcpy(dB, B, (size_t)256 * K * 4, cudaMemcpyHostToDevice));
+    UCK(cudaMemset(dC, 0, (size_t)M * 256 * 4));
+    const int lda = a_km ? K : M, ldb = b_km ? K : 256;
+    const size_t smem = kUmmaSmemBytes + 1024;
+    UCK(cudaEventCreate(&e0)); UCK(cudaEventCreate(&e1));
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (r != cudaSuccess) return r;
+        cudaEventRecord(e0);
+        kern<<<1, kThreads, smem>>>(dA, lda, dB, ldb, dC, M, K, reps);
+        cudaEventRecord(e1);
+        return cudaGetLastError();
+    };
+    if (a_km && b_km) { UCK(launch(umma_gemm_selftest_kernel<true, true>)); }
+    else if (a_km && !b_km) { UCK(launch(umma_gemm_selftest_kernel<true, false>)); }
+    else if (!a_km && b_km) { UCK(launch(umma_gemm_selftest_kernel<false, true>)); }
+    else { UCK(launch(umma_gemm_selftest_kernel<false, false>)); }
+    spp_count_launch_();
+    UCK(cudaDeviceSynchronize());
+    float ms = 0.f;
+    UCK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms_out) *ms_out = ms;
+    UCK(cudaMemcpy(C, dC, (size_t)M * 256 * 4, cudaMemcpyDeviceToHost));
+#undef UCK
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return SPP_OK;
+}
 
 extern "C" int spp_umma_selftest(int a_mn, int b_mn, int K, int split, const float* A, const float* B, float* C) {
     using namespace spp;

@@ -173,7 +173,7 @@ __device__ void update_step(const Ctx& c, int g) {
     for (int i = 0; i < ncrit; ++i) {   // dz1 = (dz2 W2) * relu'(hc1); column sums -> d b1
         const LayerDesc& l = L.critic.L[1];
         EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, c.gvec(GV_CB1_0 + i)};
-        gemm<BigTile, true>(S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+        gemm_big<true>(c, S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
     __syncthreads();
     for (int i = 0; i < ncrit; ++i) {
@@ -182,7 +182,7 @@ __device__ void update_step(const Ctx& c, int g) {
         {   // fc2.weight: dW2[m,n] = sum_b dz2[b,m] hc1[b,n]
             const LayerDesc& l = L.critic.L[1];
             EpiAdam epi{net + l.off_w, nm + l.off_w, nv + l.off_w, l.ld, net + l.off_wt, tn + l.off_wt, nullptr, l.ld_t, as, h.tau, h.one_minus_tau};
-            gemm<BigTile, false>(S + L.s.dz2[i], kHidden, S + L.s.hc1[i], kHidden, kHidden, kHidden, B, c.sm.gemm, epi);
+            gemm_big<false>(c, S + L.s.dz2[i], kHidden, S + L.s.hc1[i], kHidden, kHidden, kHidden, B, epi);
         }
         {   // fc1.weight: dW1[m,n] = sum_b dz1[b,m] xc[b,n]
             const LayerDesc& l = L.critic.L[0];
@@ -205,7 +205,7 @@ __device__ void update_step(const Ctx& c, int g) {
     for (int i = 0; i < ncrit; ++i) {
         const LayerDesc& l = L.critic.L[1];
         EpiMaskStore<MASK_RELU, false, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, nullptr};
-        gemm<BigTile, true>(S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+        gemm_big<true>(c, S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
     __syncthreads();
     {   // dxc = sum_i dz1[i] W1_i     [B x ldc]
@@ -223,13 +223,13 @@ __device__ void update_step(const Ctx& c, int g) {
     {   // dza2 = (dml Wheads) * relu'(ha2); column sums -> d b2
         const LayerDesc& l = L.actor.L[2];
         EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza2, kHidden, S + L.s.ha2, kHidden, c.gvec(GV_AB2)};
-        gemm<BigTile, true>(S + L.s.dml, L.ldh, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, L.heads, c.sm.gemm, epi);
+        gemm_big<true>(c, S + L.s.dml, L.ldh, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, L.heads, epi);
     }
     __syncthreads();
     {   // dza1 = (dza2 W2) * relu'(ha1); column sums -> d b1
         const LayerDesc& l = L.actor.L[1];
         EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza1, kHidden, S + L.s.ha1, kHidden, c.gvec(GV_AB1)};
-        gemm<BigTile, true>(S + L.s.dza2, kHidden, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, kHidden, c.sm.gemm, epi);
+        gemm_big<true>(c, S + L.s.dza2, kHidden, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
     __syncthreads();
     {
@@ -247,7 +247,7 @@ __device__ void update_step(const Ctx& c, int g) {
         {
             EpiAdam epi{net + l1.off_w, nm + l1.off_w, nv + l1.off_w, l1.ld, net + l1.off_wt, PK ? tn + l1.off_wt : nullptr,
                         nullptr, l1.ld_t, as, h.tau, h.one_minus_tau};
-            gemm<BigTile, false>(S + L.s.dza2, kHidden, S + L.s.ha1, kHidden, kHidden, kHidden, B, c.sm.gemm, epi);
+            gemm_big<false>(c, S + L.s.dza2, kHidden, S + L.s.ha1, kHidden, kHidden, kHidden, B, epi);
         }
         {
             EpiAdam epi{net + l0.off_w, nm + l0.off_w, nv + l0.off_w, l0.ld, net + l0.off_wt, PK ? tn + l0.off_wt : nullptr,
@@ -267,15 +267,36 @@ __device__ void update_step(const Ctx& c, int g) {
 template <int ALGO>
 __global__ void __launch_bounds__(kThreads, 1) update_burst_kernel(const __grid_constant__ UpdateArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    Smem& sm = smem_struct(smem_raw);
+    UmmaCtx um;
+    if (a.use_umma) {   // TMEM accumulator (all 512 columns) and the stage barriers live for the whole burst
+        if (warp_id() == 0) umma::tmem_alloc<kUmmaTmemCols>(&sm.tmem_base);
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < kUmmaSlots; ++s) umma::mbar_init(sm.mbar + s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        um.smem = reinterpret_cast<unsigned char*>(sm.gemm);
+        um.mbar = sm.mbar;
+        um.tmem = sm.tmem_base;
+        um.phase_bits = 0;
+        um.dbg = 0;
+    }
     for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
-        Ctx c(a, agent, sm);
+        Ctx c(a, agent, sm, a.use_umma ? &um : nullptr);
         for (int g = 0; g < a.G; ++g) update_step<ALGO>(c, g);
+    }
+    if (a.use_umma) {
+        umma::fence_before_sync();
+        __syncthreads();
+        if (warp_id() == 0) umma::tmem_dealloc<kUmmaTmemCols>(um.tmem);
     }
 }
 
 cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream) {
-    const size_t smem = sizeof(Smem);
+    const size_t smem = kSmemLaunchBytes;
     cudaError_t e;
     if (a.L.algo == ALGO_SAC) {
         e = cudaFuncSetAttribute(update_burst_kernel<ALGO_SAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

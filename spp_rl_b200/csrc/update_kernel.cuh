@@ -7,6 +7,7 @@
 // (rltoolkit/buffer/replay_buffer.py:385-398,233-261).
 #pragma once
 #include "gemm_tile.cuh"
+#include "gemm_umma.cuh"
 #include "layout.h"
 
 namespace spp {
@@ -67,18 +68,27 @@ struct UpdateArgs {
     int population;
     int batch_row_stride;    // rows between consecutive steps in the staged batch / index arrays (0 = L.B)
     int acm_last_rows;       // ACM regression: rows of the final step when it is a partial batch (0 = full)
+    int use_umma;            // 1: the 128 x 128 tile GEMMs run on tcgen05 (3-pass tf32 split); 0: FFMA tiles (A/B switch)
 };
 
 enum { LOSS_CRITIC_1 = 0, LOSS_CRITIC_2 = 1, LOSS_ACTOR = 2, LOSS_PI = 3, LOSS_DIST = 4, LOSS_ALPHA = 5, LOSS_ALPHA_VALUE = 6, LOSS_COUNT = 8 };
 
 struct Smem {
-    float gemm[kGemmSmemFloats];
+    float gemm[kUmmaSmemBytes / 4];   // operand pipeline of the tile GEMMs (tcgen05 path: four 32 KB swizzled planes; FFMA path: first 102 KB)
     float red[8 * 2 * kHidden];       // cross-warp column partials (8 warps x 512)
     float vecs[4 * kHidden];          // reduced vectors
     float small[64];
     AdamScalars adam[4];
     float alpha;                      // temperature as fp32 (Python float rounded when it meets fp32 tensors)
+    uint32_t tmem_base;               // TMEM allocation of this CTA (tcgen05 path)
+    uint64_t mbar[kUmmaSlots];        // one mbarrier per pipeline slot: "the MMAs reading this half-plane have retired"
 };
+static_assert(kUmmaSmemBytes / 4 >= kGemmSmemFloats, "the FFMA pipeline aliases the tcgen05 stages");
+constexpr size_t kSmemLaunchBytes = sizeof(Smem) + 1024;   // + slack to align the base to a swizzle atom (1024 B)
+
+__device__ __forceinline__ Smem& smem_struct(unsigned char* raw) {
+    return *reinterpret_cast<Smem*>(raw + ((1024u - (umma::smem_u32(raw) & 1023u)) & 1023u));
+}
 
 // ------------------------------------------------------------------------------------------------
 struct Ctx {
@@ -89,7 +99,8 @@ struct Ctx {
     float* Mv;
     float* S;      // scratch
     Smem& sm;
-    __device__ Ctx(const UpdateArgs& a_, int agent_, Smem& sm_) : a(a_), agent(agent_), sm(sm_) {
+    UmmaCtx* um;   // tcgen05 pipeline state, or null -> FFMA tiles
+    __device__ Ctx(const UpdateArgs& a_, int agent_, Smem& sm_, UmmaCtx* um_ = nullptr) : a(a_), agent(agent_), sm(sm_), um(um_) {
         P = a.params + (size_t)agent * a.L.params_size;
         Mm = a.mom_m + (size_t)agent * a.L.train_size;
         Mv = a.mom_v + (size_t)agent * a.L.train_size;
@@ -128,13 +139,22 @@ __device__ inline void adam_vector(float* W, float* Mo, float* Vo, float* T, con
     }
 }
 
+// ---- [M x 256] GEMM C = A . B on tcgen05 (gemm_umma.cuh), or on the FFMA tiles when c.um is null.  Operand convention of
+//      gemm_tile.cuh: A_KC = true: A is [M x K]; false (dW): A is [K x M]; B is always [K x N].
+template <bool A_KC, class Epi>
+__device__ __forceinline__ void gemm_big(const Ctx& c, const float* A, int lda, const float* B, int ldb, int M, int N, int K, Epi epi) {
+    if (c.um && N == 256) gemm256_umma<A_KC, false, Epi>(A, lda, B, ldb, M, K, *c.um, epi);
+    else gemm<BigTile, A_KC>(A, lda, B, ldb, M, N, K, c.sm.gemm, epi);
+}
+
 // ---- forward of one Linear through the tile GEMM: C = act(X W^T + b), reading the transposed weight copy
 template <class Cfg, int ACT, bool SCALE>
 __device__ inline void linear_fwd(const Ctx& c, const float* X, int ldx, int K, const float* net, const LayerDesc& l,
                                   float* C, int ldc, int B, const float* scale = nullptr, float* C2 = nullptr,
                                   int ldc2 = 0) {
     EpiBiasAct<ACT, SCALE, false> epi{C, ldc, net + l.off_b, scale, C2, ldc2, nullptr, 0, 0.f};
-    gemm<Cfg, true>(X, ldx, net + l.off_wt, l.ld_t, B, l.rows, K, c.sm.gemm, epi);
+    if constexpr (Cfg::TN == 128) gemm_big<true>(c, X, ldx, net + l.off_wt, l.ld_t, B, l.rows, K, epi);
+    else gemm<Cfg, true>(X, ldx, net + l.off_wt, l.ld_t, B, l.rows, K, c.sm.gemm, epi);
 }
 
 // ---- replay gather (warp per row): fills xo, xn, xc=[obs|action], r, notdone*gamma

@@ -11,7 +11,10 @@ TOL = 1e-5
 
 SAC_CASES = [
     dict(ob=11, ac=3, batch=256, population=2, steps=3),                                   # Hopper, published flags
-    dict(ob=11, ac=3, batch=100, population=3, steps=2),                                   # script batch size (ragged tile)
+    # script batch size (ragged tile).  seed 2: with seed 0, agent 1 / step 1 has an actor fc1 pre-activation of 5.8e-8 (typical
+    # |z| 0.7), i.e. a ReLU exactly at a tie whose mask is decided by the last bit of the dot product's summation order -- a
+    # single flipped mask is a 3e-4 change of the fc1 gradient and says nothing about either implementation.
+    dict(ob=11, ac=3, batch=100, population=3, steps=2, seed=2),
     dict(ob=11, ac=3, batch=64, population=2, steps=2, small_std=True),                    # near-cancelling log-prob terms
     dict(ob=11, ac=3, batch=64, population=1, steps=2, norm_closs=True),
     dict(ob=11, ac=3, batch=64, population=1, steps=2, norm_closs=True, min_max=False),
