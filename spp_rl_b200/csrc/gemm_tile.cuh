@@ -98,7 +98,8 @@ struct OperandLoader {
 template <class Cfg, bool A_KC, class Epi>
 __device__ __noinline__ void gemm_tile(const float* __restrict__ A, int lda, const float* __restrict__ B,
                                        int ldb, int M, int N, int K, int m0, int n0,
-                                       float* __restrict__ smem, Epi& epi) {
+                                       float* __restrict__ smem, const Epi& epi_ref) {
+    Epi epi = epi_ref;      // functor fields in registers (see umma_epilogue)
     constexpr int TY = Cfg::TY, TX = Cfg::TX, MI = Cfg::MI, NJ = Cfg::NJ, TM = Cfg::TM, TN = Cfg::TN;
     const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
     const int nk = (K + TK - 1) / TK;
@@ -191,6 +192,17 @@ __device__ __forceinline__ void gemm(const float* __restrict__ A, int lda, const
         gemm_tile<Cfg, A_KC, Epi>(A, lda, B, ldb, M, N, K, (t / nt) * Cfg::TM, (t % nt) * Cfg::TN, smem, epi);
 }
 
+// L2 prefetch of rows [r0, r0 + nrows) x [c0, c0 + ncols) of a row-major array (ld floats per row), 128-byte lines, all threads.
+// The fused kernels' epilogues are latency-bound on reads that miss L2 (every agent's state streams from HBM); prefetching a
+// tile's epilogue operands when its main loop starts turns those misses into L2 hits.
+__device__ __forceinline__ void prefetch_l2_tile(const float* base, int ld, int r0, int nrows, int c0, int ncols) {
+    const int lines_per_row = (ncols + 31) / 32;
+    for (int i = threadIdx.x; i < nrows * lines_per_row; i += kThreads) {
+        const int r = i / lines_per_row, l = i % lines_per_row;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(r0 + r) * ld + c0 + 32 * l));
+    }
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 
@@ -208,6 +220,9 @@ __device__ __forceinline__ float act_fn(float x) {
 template <int ACT, bool SCALE, bool ADD>
 struct EpiBiasAct {
     float* C; int ldc; const float* bias; const float* scale; float* C2; int ldc2; const float* Sk; int lds; float t;
+    __device__ __forceinline__ void prefetch(int m0, int rows, int n0, int cols, int M, int N) const {
+        if (ADD) prefetch_l2_tile(Sk, lds, m0, min(rows, M - m0), n0, min(cols, N - n0));
+    }
     template <class Cfg, bool A_KC>
     __device__ __forceinline__ void apply(float (&acc)[Cfg::MI][Cfg::NJ], int m0, int n0, int M, int N, float*) {
         const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
@@ -258,6 +273,10 @@ enum Mask { MASK_NONE = 0, MASK_RELU = 1, MASK_TANH = 2 };
 template <int MASK, bool COLSUM, bool ACCUM>
 struct EpiMaskStore {
     float* C; int ldc; const float* H; int ldh; float* colsum;
+    __device__ __forceinline__ void prefetch(int m0, int rows, int n0, int cols, int M, int N) const {
+        if (MASK != MASK_NONE) prefetch_l2_tile(H, ldh, m0, min(rows, M - m0), n0, min(cols, N - n0));
+        if (ACCUM) prefetch_l2_tile(C, ldc, m0, min(rows, M - m0), n0, min(cols, N - n0));
+    }
     template <class Cfg, bool A_KC>
     __device__ __forceinline__ void apply(float (&acc)[Cfg::MI][Cfg::NJ], int m0, int n0, int M, int N, float* smem) {
         const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
@@ -341,6 +360,14 @@ __device__ __forceinline__ float adam_element(float w, float g, float& m, float&
 // for the actor heads the tile is computed transposed, so R = W^T and Cc = W.
 struct EpiAdam {
     float* R; float* Mo; float* Vo; int ldr; float* Cc; float* Tc; float* Tr; int ldcc; AdamScalars s; float tau, one_minus_tau;
+    __device__ __forceinline__ void prefetch(int m0, int rows, int n0, int cols, int M, int N) const {
+        const int nr = min(rows, M - m0), nc = min(cols, N - n0);
+        prefetch_l2_tile(R, ldr, m0, nr, n0, nc);
+        prefetch_l2_tile(Mo, ldr, m0, nr, n0, nc);
+        prefetch_l2_tile(Vo, ldr, m0, nr, n0, nc);
+        if (Tr) prefetch_l2_tile(Tr, ldr, m0, nr, n0, nc);
+        if (Tc) prefetch_l2_tile(Tc, ldcc, n0, nc, m0, nr);      // column copy: element (m, n) at Tc[n * ldcc + m]
+    }
     template <class Cfg, bool A_KC>
     __device__ __forceinline__ void apply(float (&acc)[Cfg::MI][Cfg::NJ], int m0, int n0, int M, int N, float*) {
         static_assert(!A_KC, "Adam epilogue expects the dW (TN) mapping");

@@ -17,9 +17,11 @@
 //       is still tiny, so only the 4 hi*hi MMAs of a chunk truncate at full magnitude.
 //
 // Tiling.  One tile is 128 rows x 256 columns (two tiles for M > 128): TMEM = 2 accumulators x 256 columns.  Shared memory
-// = 2 slots x [A_hi 16 KB | A_lo 16 KB | B_hi 32 KB | B_lo 32 KB] in the SWIZZLE_128B layouts of umma.cuh.  Per chunk all
-// 256 threads split 12 float4 each (global -> registers one chunk ahead -> hi/lo -> swizzled st.shared), one thread issues
-// 12 MMAs of 128 x 256 x 8 and commits them to the slot's mbarrier, then everybody drains the previous chunk.  After the
+// = 2 slots x [A_hi 16 KB | A_lo 16 KB | B_hi 32 KB | B_lo 32 KB] in the SWIZZLE_128B layouts of umma.cuh.  Raw fp32 chunks
+// travel global -> shared by 16-byte LDGSTS straight into their swizzled position in the hi planes of the free slot (no
+// registers in flight: the register file is needed for the 128 running sums); per chunk every thread then splits the 12
+// float4 it copied in place (hi rounded in place, lo to the twin plane), one thread issues 12 MMAs of 128 x 256 x 8 and
+// commits them to the slot's mbarrier, then everybody drains the previous chunk while the next raw chunk lands.  After the
 // last chunk the running sums go through a shared staging buffer to the epilogue functors of gemm_tile.cuh in their
 // register mapping (coalesced global traffic).
 #pragma once
@@ -80,15 +82,21 @@ struct UmmaOperand {
             np_ok = (r0 + 4 * chunk < R) ? NP : 0;
         }
     }
-    __device__ __forceinline__ void load(int k0, int K, float4 (&r)[NP]) const {
+    // raw fp32 chunk, global -> its swizzled position in the hi plane (16-byte LDGSTS, zero-filled outside the operand)
+    __device__ __forceinline__ void issue(int k0, int K, uint32_t hi) const {
         const float* s = src0 + (size_t)k0 * kstride;
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const bool ok = (p < np_ok) && (k0 + kofs0 + p * KSTEP < K);
-            r[p] = ok ? __ldcg(reinterpret_cast<const float4*>(s + p * sstep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* g = ok ? s + p * sstep : src0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(hi + dst0 + p * DSTEP), "l"(g), "r"(ok ? 16 : 0));
         }
     }
-    __device__ __forceinline__ void store(const float4 (&r)[NP], uint32_t hi, uint32_t lo) const {
+    // in-place split of the chunks this thread copied: hi plane <- rn_tf32(x), lo plane <- rn_tf32(x - hi)
+    __device__ __forceinline__ void split(uint32_t hi, uint32_t lo) const {
+        float4 r[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) r[p] = umma::lds128(hi + dst0 + p * DSTEP);
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             float4 h, l;
@@ -104,23 +112,23 @@ struct UmmaOperand {
 template <bool FIRST>
 __device__ __forceinline__ void umma_drain(uint32_t taddr, float (&sum)[128]) {
 #pragma unroll
-    for (int cb = 0; cb < 8; cb += 2) {
-        float v0[16], v1[16];
-        umma::tmem_ld16_nowait(taddr + cb * 16, v0);
-        umma::tmem_ld16_nowait(taddr + cb * 16 + 16, v1);
+    for (int cb = 0; cb < 8; cb += 4) {
+        float v[4][16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) umma::tmem_ld16_nowait(taddr + (cb + i) * 16, v[i]);
         umma::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            sum[cb * 16 + i] = FIRST ? v0[i] : __fadd_rn(sum[cb * 16 + i], v0[i]);
-            sum[cb * 16 + 16 + i] = FIRST ? v1[i] : __fadd_rn(sum[cb * 16 + 16 + i], v1[i]);
-        }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sum[(cb + i) * 16 + e] = FIRST ? v[i][e] : __fadd_rn(sum[(cb + i) * 16 + e], v[i][e]);
     }
 }
 
 // staged accumulator (two 128 x 128 blocks) -> registers in the FFMA tiles' mapping -> epilogue functor.  Its own function so
 // that the epilogue's registers (Adam: 4 x 4 float4 of loads in flight) are allocated independently of the main loop's.
 template <bool A_KM, class Epi>
-__device__ __noinline__ void umma_epilogue(uint32_t stage_s, float* stage, int m0, int M, Epi& epi) {
+__device__ __noinline__ void umma_epilogue(uint32_t stage_s, float* stage, int m0, int M, const Epi& epi_ref) {
+    Epi epi = epi_ref;      // functor fields in registers: through the reference every global store forces their reload from local memory
     const int tx = threadIdx.x % BigTile::TX, ty = threadIdx.x / BigTile::TX;
 #pragma unroll 1
     for (int nh = 0; nh < 2; ++nh) {
@@ -158,21 +166,17 @@ __device__ __noinline__ void umma_mainloop(const float* __restrict__ A, int lda,
     UmmaOperand<A_KM, 128> la;
     la.init(A, lda, M, m0);
     float sum[128];
-    float4 ra[4], rb[8];
-    la.load(0, K, ra);
-    lb.load(0, K, rb);
+    const uint32_t slot_a[2] = {smem0, smem0 + kUmmaSlotBytes};
+    if (!(dbg & 2)) { la.issue(0, K, slot_a[0]); lb.issue(0, K, slot_a[0] + 2 * kUmmaAPlane); }
+    cp_async_commit();
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
         const int slot = c & 1;
         const uint32_t ah = smem0 + slot * kUmmaSlotBytes, al = ah + kUmmaAPlane, bh = al + kUmmaAPlane, bl = bh + kUmmaBPlane;
-        // slot `slot` is free: the MMAs of chunk c - 2 were waited for when that chunk was drained (iteration c - 1)
+        cp_async_wait<0>();       // this thread's copies of chunk c have landed
         if (!(dbg & 2)) {
-            la.store(ra, ah, al);
-            lb.store(rb, bh, bl);
-            if (c + 1 < nchunks) {
-                la.load(32 * (c + 1), K, ra);
-                lb.load(32 * (c + 1), K, rb);
-            }
+            la.split(ah, al);
+            lb.split(bh, bl);
         }
         fence_proxy_async();
         fence_before_sync();      // orders this thread's drain of chunk c - 2 (same accumulator) before the MMAs below
@@ -196,11 +200,19 @@ __device__ __noinline__ void umma_mainloop(const float* __restrict__ A, int lda,
             }
             commit(mbar + slot);
         }
-        if (c >= 1) {       // drain chunk c - 1 while the tensor core works on chunk c
-            const int ps = slot ^ 1;
+        const int ps = slot ^ 1;
+        if (c >= 1) {       // chunk c - 1 has retired: its slot is free, its accumulator complete
             mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
             phase_bits ^= (1u << ps);
             fence_after_sync();
+        }
+        if (c + 1 < nchunks && !(dbg & 2)) {      // raw chunk c + 1 -> the free slot, in flight during the drain below
+            const uint32_t nh = smem0 + ps * kUmmaSlotBytes;
+            la.issue(32 * (c + 1), K, nh);
+            lb.issue(32 * (c + 1), K, nh + 2 * kUmmaAPlane);
+        }
+        cp_async_commit();
+        if (c >= 1) {       // drain chunk c - 1 while the tensor core works on chunk c
             if (c == 1) umma_drain<true>(my_tmem + ps * N, sum);
             else umma_drain<false>(my_tmem + ps * N, sum);
         }
@@ -228,7 +240,11 @@ template <bool A_KM, bool B_KM, class Epi>
 __device__ __forceinline__ void gemm256_umma(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
                                              UmmaCtx& u, Epi& epi) {
     const int mtiles = (M + 127) / 128;
+    // operands -> L2 ahead of the LDGSTS stream (weights and moments of an agent always come from HBM)
+    if (B_KM) prefetch_l2_tile(B, ldb, 0, 256, 0, K); else prefetch_l2_tile(B, ldb, 0, K, 0, 256);
+    if (A_KM) prefetch_l2_tile(A, lda, 0, M, 0, K); else prefetch_l2_tile(A, lda, 0, K, 0, M);
     for (int mt = 0; mt < mtiles; ++mt) {
+        epi.prefetch(mt * 128, 128, 0, 256, M, 256);      // this tile's epilogue operands -> L2 while its main loop runs
         umma_mainloop<A_KM, B_KM>(A, lda, B, ldb, M, K, mt * 128, u.smem, u.mbar, u.tmem, u.phase_bits, u.dbg);
         if (!(u.dbg & 4)) umma_epilogue<A_KM, Epi>(umma::smem_u32(u.smem), reinterpret_cast<float*>(u.smem), mt * 128, M, epi);
         __syncthreads();          // the staging aliases the operand slots of the next tile / GEMM
