@@ -269,30 +269,12 @@ __global__ void __launch_bounds__(kThreads, 1) update_burst_kernel(const __grid_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = smem_struct(smem_raw);
     UmmaCtx um;
-    if (a.use_umma) {   // TMEM accumulator (all 512 columns) and the stage barriers live for the whole burst
-        if (warp_id() == 0) umma::tmem_alloc<kUmmaTmemCols>(&sm.tmem_base);
-        if (threadIdx.x == 0) {
-            for (int s = 0; s < kUmmaSlots; ++s) umma::mbar_init(sm.mbar + s, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        umma::fence_before_sync();
-        __syncthreads();
-        umma::fence_after_sync();
-        um.smem = reinterpret_cast<unsigned char*>(sm.gemm);
-        um.mbar = sm.mbar;
-        um.tmem = sm.tmem_base;
-        um.phase_bits = 0;
-        um.dbg = 0;
-    }
+    if (a.use_umma) umma_setup(sm, um);
     for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
         Ctx c(a, agent, sm, a.use_umma ? &um : nullptr);
         for (int g = 0; g < a.G; ++g) update_step<ALGO>(c, g);
     }
-    if (a.use_umma) {
-        umma::fence_before_sync();
-        __syncthreads();
-        if (warp_id() == 0) umma::tmem_dealloc<kUmmaTmemCols>(um.tmem);
-    }
+    if (a.use_umma) umma_teardown(um);
 }
 
 cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream) {

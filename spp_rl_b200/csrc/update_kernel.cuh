@@ -116,6 +116,28 @@ struct Ctx {
     __device__ float* gvec(int which) const { return S + a.L.s.gvec + which * 512; }
 };
 
+// ---- tcgen05 state of a persistent CTA: TMEM accumulators (all 512 columns) and the slot barriers live for the whole launch
+__device__ __forceinline__ void umma_setup(Smem& sm, UmmaCtx& um) {
+    if (warp_id() == 0) umma::tmem_alloc<kUmmaTmemCols>(&sm.tmem_base);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kUmmaSlots; ++s) umma::mbar_init(sm.mbar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    um.smem = reinterpret_cast<unsigned char*>(sm.gemm);
+    um.mbar = sm.mbar;
+    um.tmem = sm.tmem_base;
+    um.phase_bits = 0;
+    um.dbg = 0;
+}
+__device__ __forceinline__ void umma_teardown(UmmaCtx& um) {
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp_id() == 0) umma::tmem_dealloc<kUmmaTmemCols>(um.tmem);
+}
+
 // ---- Adam bookkeeping: bump the step of optimiser `opt` and publish its scalars (thread 0 only)
 __device__ inline void adam_begin(const Ctx& c, int opt, double lr) {
     int* st = c.a.steps + (size_t)c.agent * 4 + opt;
