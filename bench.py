@@ -237,6 +237,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its version banner to stdout at any debug level; rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     P = args.agents_per_gpu or sm_count

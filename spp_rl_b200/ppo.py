@@ -181,5 +181,6 @@ class PpoPolicy:
         self.sync()
         dist.all_reduce(g)
         dist.all_reduce(sc)
+        out = sc.cpu().numpy()          # also orders the all-reduces (torch's stream) before the apply (the library's stream)
         check(self.lib.spp_ppo_actor_apply(self.h))
-        return sc.cpu().numpy()
+        return out

@@ -37,3 +37,35 @@ def gather_tables(local: torch.Tensor, total_agents: int, dist=None) -> torch.Te
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return torch.cat([o[:n] for o, n in zip(out, sizes)], dim=0)
+
+
+# ---- SPP-PPO data parallelism: environments shard over ranks, trajectories never cross GPUs.
+# Global rollout rows are step-major, row g = t * E + e; rank r owns environments [r * E/W, (r + 1) * E/W) and keeps them
+# step-major with stride E/W, so GAE is local and a global minibatch is the union of the ranks' slices of one permutation.
+def env_shard_rows(E: int, T: int, rank: int, world: int):
+    """Global row ids of the rows `rank` owns, in its local (step-major, stride E/W) order."""
+    import numpy as np
+
+    if E % world:
+        raise ValueError("environments (%d) must divide evenly over %d ranks" % (E, world))
+    El = E // world
+    return (np.arange(T)[:, None] * E + rank * El + np.arange(El)[None, :]).reshape(-1)
+
+
+def local_minibatch(global_idx, E: int, rank: int, world: int):
+    """The part of a global minibatch (global row ids) that `rank` owns, as LOCAL row ids, in minibatch order."""
+    import numpy as np
+
+    idx = np.asarray(global_idx, np.int64)
+    El = E // world
+    e = idx % E
+    mine = (e // El) == rank
+    return ((idx[mine] // E) * El + e[mine] % El).astype(np.int64)
+
+
+def allreduce_adv_stats(local_stats, dist=None, device="cpu"):
+    """(n, sum, sum of squares) of the local advantages -> the global triple, in fp64 (torch.std parity needs it)."""
+    t = torch.as_tensor(local_stats, dtype=torch.float64, device=device).clone()
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t.cpu().numpy()

@@ -6,7 +6,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from spp_rl_b200.sharding import agent_shard, gather_tables, max_over_ranks
+import numpy as np
+
+from spp_rl_b200.sharding import agent_shard, allreduce_adv_stats, env_shard_rows, gather_tables, local_minibatch, max_over_ranks
 
 
 def _free_port():
@@ -52,3 +54,52 @@ def test_two_rank_gloo_gather_and_timing():
         assert table == expect            # every rank sees the whole population's table in agent order
         assert slow == 2.0                # max over ranks, not the local time
     assert res[0][1] + res[1][1] == list(range(total))
+
+
+def test_env_sharding_covers_rows_and_minibatches():
+    """SPP-PPO data parallelism: every global row has exactly one owner, local order is step-major with stride E/W, and the
+    ranks' slices of a global minibatch partition it."""
+    E, T = 12, 5
+    for world in (1, 2, 3, 4):
+        owned = [env_shard_rows(E, T, r, world) for r in range(world)]
+        assert sorted(np.concatenate(owned).tolist()) == list(range(E * T))
+        El = E // world
+        for r, rows in enumerate(owned):
+            assert rows.reshape(T, El)[:, 0].tolist() == [t * E + r * El for t in range(T)]       # env r*El at every step
+            # local row ids of a permutation slice point back at the same global rows
+            perm = np.random.RandomState(world + r).permutation(E * T)[:23]
+            loc = local_minibatch(perm, E, r, world)
+            mine = [g for g in perm.tolist() if (g % E) // El == r]
+            assert rows[loc].tolist() == mine
+        sizes = [len(local_minibatch(np.arange(E * T), E, r, world)) for r in range(world)]
+        assert sum(sizes) == E * T
+
+
+def _adv_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a = np.random.RandomState(0).randn(1000)[rank::world]            # this rank's advantages
+    g = allreduce_adv_stats([a.size, a.sum(), (a * a).sum()], dist)
+    q.put((rank, g.tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_advantage_statistics():
+    """the fp64 (n, sum, sum of squares) all-reduce reproduces torch.std (unbiased) of the undivided advantage vector"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_adv_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a = np.random.RandomState(0).randn(1000)
+    for _, (n, s1, s2) in res:
+        mean = s1 / n
+        std = np.sqrt((s2 - n * mean * mean) / (n - 1))
+        assert n == 1000 and abs(mean - a.mean()) < 1e-12
+        assert abs(std - float(torch.from_numpy(a).std())) < 1e-12
