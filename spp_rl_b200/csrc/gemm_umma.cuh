@@ -151,8 +151,8 @@ __device__ __noinline__ void umma_epilogue(uint32_t stage_s, float* stage, int m
 // kStagePitch at the start of the operand slots).  A separate function (independent of the epilogue type) so that its
 // register allocation -- 128 running sums + 48 registers of operands in flight -- is not disturbed by the epilogue's.
 template <bool A_KM, bool B_KM>
-__device__ __noinline__ void umma_mainloop(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
-                                           int m0, unsigned char* smem, uint64_t* mbar, uint32_t tmem, uint32_t& phase_io, uint32_t dbg) {
+__device__ __noinline__ uint32_t umma_mainloop(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
+                                               int m0, unsigned char* smem, uint64_t* mbar, uint32_t tmem, uint32_t phase_in, uint32_t dbg) {
     using namespace umma;
     constexpr int N = 256;
     const int nchunks = (K + 31) / 32;
@@ -160,7 +160,7 @@ __device__ __noinline__ void umma_mainloop(const float* __restrict__ A, int lda,
     const uint32_t idesc = make_idesc_tf32(128, N, A_KM ? 0 : 1, B_KM ? 0 : 1);
     const int wq = warp_id() & 3, chalf = warp_id() >> 2;
     const uint32_t my_tmem = tmem + ((uint32_t)(32 * wq) << 16) + chalf * 128;      // this thread's lane / column half
-    uint32_t phase_bits = phase_io;
+    uint32_t phase_bits = phase_in;      // everything by value: a by-reference argument would pin the caller's state in local memory
     UmmaOperand<B_KM, 256> lb;
     lb.init(B, ldb, N, 0);
     UmmaOperand<A_KM, 128> la;
@@ -226,7 +226,6 @@ __device__ __noinline__ void umma_mainloop(const float* __restrict__ A, int lda,
         else umma_drain<false>(my_tmem + ps * N, sum);
         fence_before_sync();
     }
-    phase_io = phase_bits;
     {   // running sums -> shared staging; every MMA that read the slots has retired
         const int srow = 32 * wq + lane_id();
         const uint32_t base = smem0 + 4 * (chalf * kStageBlockFloats + srow * kStagePitch);
@@ -234,18 +233,15 @@ __device__ __noinline__ void umma_mainloop(const float* __restrict__ A, int lda,
         for (int q = 0; q < 32; ++q) sts128(base + 16 * q, make_float4(sum[4 * q], sum[4 * q + 1], sum[4 * q + 2], sum[4 * q + 3]));
     }
     __syncthreads();
+    return phase_bits;
 }
 
 template <bool A_KM, bool B_KM, class Epi>
 __device__ __forceinline__ void gemm256_umma(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
                                              UmmaCtx& u, Epi& epi) {
     const int mtiles = (M + 127) / 128;
-    // operands -> L2 ahead of the LDGSTS stream (weights and moments of an agent always come from HBM)
-    if (B_KM) prefetch_l2_tile(B, ldb, 0, 256, 0, K); else prefetch_l2_tile(B, ldb, 0, K, 0, 256);
-    if (A_KM) prefetch_l2_tile(A, lda, 0, M, 0, K); else prefetch_l2_tile(A, lda, 0, K, 0, M);
     for (int mt = 0; mt < mtiles; ++mt) {
-        epi.prefetch(mt * 128, 128, 0, 256, M, 256);      // this tile's epilogue operands -> L2 while its main loop runs
-        umma_mainloop<A_KM, B_KM>(A, lda, B, ldb, M, K, mt * 128, u.smem, u.mbar, u.tmem, u.phase_bits, u.dbg);
+        u.phase_bits = umma_mainloop<A_KM, B_KM>(A, lda, B, ldb, M, K, mt * 128, u.smem, u.mbar, u.tmem, u.phase_bits, u.dbg);
         if (!(u.dbg & 4)) umma_epilogue<A_KM, Epi>(umma::smem_u32(u.smem), reinterpret_cast<float*>(u.smem), mt * 128, M, epi);
         __syncthreads();          // the staging aliases the operand slots of the next tile / GEMM
     }
