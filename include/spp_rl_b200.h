@@ -107,6 +107,11 @@ int spp_ring_sample_batch(spp_population* p, int a, const int64_t* idx, int n, f
                           float* action, float* reward, int8_t* done, float* acm_action);
 /* Synthetic prefill for benchmarks: n transitions per agent in episodes of
  * `episode_len`, obs ~ U(min_obs,max_obs), next = obs + 0.02 N(0,1), reward ~ N(0,1), done ~ Bern(1e-3). */
+/* MetaReplayBuffer.update_obs_mean_std (rltoolkit/buffer/replay_buffer.py:83-96) on the device for every agent of the population:
+ * out [P][6][ob] (host, fp64) = mean, population std (numpy ddof 0), and the four order statistics of self.obs per column that
+ * np.percentile(obs, 1) and np.percentile(obs, 99) interpolate between (ranks floor / ceil of q (n - 1)); exact elements of the
+ * buffer, so the caller finishes the percentile with numpy's own lerp.  bytes_out (optional): ring bytes streamed. */
+int spp_ring_obs_stats(spp_population* p, double* out, double* bytes_out);
 int spp_ring_fill_synthetic(spp_population* p, uint64_t seed, int64_t n, int episode_len);
 /* Device-resident gather of n_batches minibatches per agent (indices drawn on device): measures the
  * HBM path of sample_batch in isolation.  bytes_out = algorithmic bytes moved per call. */

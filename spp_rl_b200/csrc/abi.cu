@@ -72,6 +72,7 @@ struct spp_population {
     int32_t *r_oidx = nullptr, *r_nidx = nullptr;
     uint8_t *r_done = nullptr, *r_end = nullptr;
     int64_t* r_len = nullptr;    // device copy of current_len per agent
+    DevBuf d_stat_partial, d_stat_moments, d_stat_state, d_stat_hist;      // spp_ring_obs_stats scratch
     std::vector<int64_t> obs_cur, ts_cur, cur_len;
     bool len_dirty = true;
     // staging
@@ -159,7 +160,8 @@ int spp_population_destroy(spp_population* p) {
                     (void*)p->steps, (void*)p->alpha_state, (void*)p->r_obs, (void*)p->r_act, (void*)p->r_rew, (void*)p->r_aacm,
                     (void*)p->r_oidx, (void*)p->r_nidx, (void*)p->r_done, (void*)p->r_end, (void*)p->r_len, (void*)p->scratch_acm})
         if (q) cudaFree(q);
-    for (DevBuf* b : {&p->d_obs, &p->d_nobs, &p->d_act, &p->d_rew, &p->d_done, &p->d_aacm, &p->d_eps, &p->d_idx, &p->d_losses, &p->d_tmp, &p->d_roll_scratch, &p->d_env, &p->d_cur})
+    for (DevBuf* b : {&p->d_obs, &p->d_nobs, &p->d_act, &p->d_rew, &p->d_done, &p->d_aacm, &p->d_eps, &p->d_idx, &p->d_losses, &p->d_tmp, &p->d_roll_scratch, &p->d_env, &p->d_cur,
+                      &p->d_stat_partial, &p->d_stat_moments, &p->d_stat_state, &p->d_stat_hist})
         b->release();
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -579,6 +581,44 @@ int spp_ring_fill_synthetic(spp_population* p, uint64_t seed, int64_t n, int epi
     CK(cudaStreamSynchronize(p->stream));
     for (int a = 0; a < p->P; ++a) { p->obs_cur[a] = (n + n_eps) % p->S; p->ts_cur[a] = n % p->S; p->cur_len[a] = n; }
     p->len_dirty = true;
+    return SPP_OK;
+}
+
+// MetaReplayBuffer.update_obs_mean_std (rltoolkit/buffer/replay_buffer.py:83-96) for every agent: out [P][6][ob] =
+// mean, population std, and the order statistics x[floor(v1)], x[ceil(v1)], x[floor(v99)], x[ceil(v99)] with v_q = q (n - 1)
+int spp_ring_obs_stats(spp_population* p, double* out, double* bytes_out) {
+    if (!p || !out) return fail(SPP_ERR_ARG, "spp_ring_obs_stats: null argument");
+    if (p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
+    for (int a = 0; a < p->P; ++a) if (p->cur_len[a] < 1) return fail(SPP_ERR_STATE, "replay ring is empty");
+    CK(cudaSetDevice(p->device));
+    int rc = push_ring_len(p); if (rc) return rc;
+    const int ob = p->L.ob, P = p->P;
+    int nb = (8 * p->sm_count) / P; if (nb < 8) nb = 8; if (nb > 1024) nb = 1024;
+    const size_t n_state = (size_t)P * ob * 4 * 2;
+    CK(p->d_stat_partial.ensure((size_t)P * nb * ob * sizeof(double)));
+    CK(p->d_stat_moments.ensure((size_t)2 * P * ob * sizeof(double)));
+    CK(p->d_stat_state.ensure(n_state * sizeof(unsigned long long)));
+    CK(p->d_stat_hist.ensure((size_t)P * ob * 4 * 256 * sizeof(unsigned int)));
+    std::vector<unsigned long long> h_state(n_state);
+    CK(launch_ring_obs_stats(ring_view(p), P, p->r_len, p->cur_len.data(), nb, (double*)p->d_stat_partial.p, (double*)p->d_stat_moments.p,
+                             (unsigned long long*)p->d_stat_state.p, (unsigned int*)p->d_stat_hist.p, h_state.data(), p->stream));
+    g_launches += 12;
+    std::vector<double> mom((size_t)2 * P * ob);
+    CK(cudaMemcpyAsync(mom.data(), p->d_stat_moments.p, mom.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(h_state.data(), p->d_stat_state.p, n_state * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    double bytes = 0;
+    for (int a = 0; a < P; ++a) {
+        bytes += 6.0 * (double)p->cur_len[a] * (ob * 4.0 + 4.0);      // 6 passes over len rows: ob floats + the obs index
+        for (int j = 0; j < ob; ++j) {
+            double* o = out + (size_t)a * 6 * ob;
+            o[0 * ob + j] = mom[(size_t)a * ob + j];
+            o[1 * ob + j] = mom[(size_t)(P + a) * ob + j];
+            for (int T = 0; T < 4; ++T)
+                o[(2 + T) * ob + j] = (double)ring_stats_key_to_float((uint32_t)h_state[(((size_t)a * ob + j) * 4 + T) * 2]);
+        }
+    }
+    if (bytes_out) *bytes_out = bytes;
     return SPP_OK;
 }
 

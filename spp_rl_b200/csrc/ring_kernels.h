@@ -20,4 +20,11 @@ cudaError_t launch_ring_fill(const RingView& R, float* obs, int32_t* oidx, int32
                              uint8_t* done, uint8_t* end, float* aacm, int P, int64_t n, int T, uint64_t seed,
                              const float* norm, int norm_stride, int grid, cudaStream_t s);
 
+// MetaReplayBuffer.update_obs_mean_std on the device (stats_kernels.cu): moments in d_moments [2][P][ob] (mean, std) and the four
+// order statistics per column as sortable keys in d_state [P][ob][4][2] (key, 0) after the last pass
+cudaError_t launch_ring_obs_stats(const RingView& R, int P, const int64_t* d_len, const int64_t* h_len, int nb, double* d_partial,
+                                  double* d_moments, unsigned long long* d_state, unsigned int* d_hist, unsigned long long* h_state,
+                                  cudaStream_t s);
+float ring_stats_key_to_float(uint32_t key);
+
 }  // namespace spp

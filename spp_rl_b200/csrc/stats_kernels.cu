@@ -1,0 +1,211 @@
+// Replay-ring observation statistics on the device: MetaReplayBuffer.update_obs_mean_std
+// (rltoolkit/buffer/replay_buffer.py:83-96) = whole-buffer mean, population std (numpy, ddof 0) and the 1st / 99th percentiles
+// (numpy "linear" interpolation between two order statistics) of `self.obs = _obs[_obs_idx[:current_len]]`, for every agent of a
+// population at once.  The reference does this on the host with numpy every iteration (O(S log S) per agent and column).
+//
+// All passes are HBM-bound streams over the ring:  2 for the moments (sum, then sum of squared deviations from the mean, fp64,
+// fixed summation order) and 4 for an exact 8-bit-per-pass radix select of four order statistics per column (the floor / ceil
+// ranks of both percentiles), so every result is exactly an element of the buffer and the percentile interpolation is done
+// in fp64 on the host with numpy's own formula -> bit-exact against np.percentile.
+//
+// Thread mapping: a block owns a contiguous range of rows; thread t < (256 / ob) * ob has a FIXED column j = t % ob and walks
+// rows t / ob, t / ob + 256 / ob, ... of the range, so consecutive threads read consecutive floats of (mostly consecutive)
+// ring rows and every thread keeps its accumulator / histogram column in registers / a private shared-memory slice.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+#include "ring_kernels.h"
+
+namespace spp {
+
+constexpr int kStatTargets = 4;      // order statistics per column: lo/hi rank of the 1st and of the 99th percentile
+constexpr int kStatColsPerBlock = 12;
+
+__device__ __forceinline__ uint32_t sortable_key(float x) {      // monotone map float -> uint32
+    const uint32_t b = __float_as_uint(x);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__host__ __device__ inline float key_to_float(uint32_t k) {
+    const uint32_t b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
+
+// pass 0: partial[a][blk][j] = sum of column j over the block's rows;  pass 1: sum of (x - mean[a][j])^2
+__global__ void __launch_bounds__(256) stats_moment_kernel(RingView R, const int64_t* __restrict__ len, int pass,
+                                                           const double* __restrict__ mean, double* __restrict__ partial) {
+    const int a = blockIdx.y, nb = gridDim.x, ob = R.ob;
+    const int64_t n = len[a];
+    const int rows_per_iter = 256 / ob, active = rows_per_iter * ob;
+    const int64_t per = (n + nb - 1) / nb, r0 = (int64_t)blockIdx.x * per, r1 = min(n, r0 + per);
+    const size_t base = (size_t)a * R.S;
+    __shared__ double red[256];
+    double acc = 0.0;
+    const int j = threadIdx.x % ob;
+    if (threadIdx.x < active) {
+        const double mu = pass ? mean[(size_t)a * ob + j] : 0.0;
+        // 4 rows in flight per thread: the index load and the value load of a row are dependent, so without this every element
+        // costs two exposed HBM latencies
+        for (int64_t i = r0 + threadIdx.x / ob; i < r1; i += 4 * rows_per_iter) {
+            int32_t oi[4]; float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int64_t ii = i + (int64_t)u * rows_per_iter; oi[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = oi[u] >= 0 ? R.obs[(base + oi[u]) * R.ldo + j] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (oi[u] < 0) continue;
+                const double x = (double)v[u];
+                if (pass) { const double d = fabs(x - mu); acc += d * d; } else acc += x;
+            }
+        }
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < ob) {      // fixed order: deterministic
+        double s = 0.0;
+        for (int t = threadIdx.x; t < active; t += ob) s += red[t];
+        partial[((size_t)a * nb + blockIdx.x) * ob + threadIdx.x] = s;
+    }
+}
+
+// out[a][j] = sum over blocks (fixed order) / n;  pass 1 additionally takes the square root
+__global__ void stats_moment_finish_kernel(const double* __restrict__ partial, const int64_t* __restrict__ len, int P, int nb, int ob,
+                                           int pass, double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P * ob) return;
+    const int a = t / ob, j = t % ob;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += partial[((size_t)a * nb + b) * ob + j];
+    const double m = s / (double)len[a];
+    out[t] = pass ? sqrt(m) : m;
+}
+
+// One radix pass (byte `pass` from the top): for every column and target, histogram the current byte of the keys whose higher
+// bytes equal the target's prefix.  state[a][j][T] = {prefix (key bits found so far), remaining rank}; hist[a][j][T][256].
+__global__ void __launch_bounds__(256) stats_select_hist_kernel(RingView R, const int64_t* __restrict__ len, int pass,
+                                                                const unsigned long long* __restrict__ state, unsigned int* __restrict__ hist) {
+    const int a = blockIdx.y, nb = gridDim.x, ob = R.ob;
+    const int j0 = blockIdx.z * kStatColsPerBlock, cols = min(kStatColsPerBlock, ob - j0);
+    const int64_t n = len[a];
+    const int rows_per_iter = 256 / cols, active = rows_per_iter * cols;
+    const int64_t per = (n + nb - 1) / nb, r0 = (int64_t)blockIdx.x * per, r1 = min(n, r0 + per);
+    const size_t base = (size_t)a * R.S;
+    extern __shared__ unsigned int sh[];      // [cols][kStatTargets][256]
+    for (int i = threadIdx.x; i < cols * kStatTargets * 256; i += 256) sh[i] = 0;
+    __syncthreads();
+    if (threadIdx.x < active) {
+        const int jj = threadIdx.x % cols, j = j0 + jj;
+        const int shift = 24 - 8 * pass;
+        uint32_t prefix[kStatTargets];
+#pragma unroll
+        for (int T = 0; T < kStatTargets; ++T) prefix[T] = (uint32_t)(state[(((size_t)a * ob + j) * kStatTargets + T) * 2]);
+        unsigned int* h = sh + (size_t)jj * kStatTargets * 256;
+        // targets that still share a prefix share a histogram (they differ only in the rank they look for)
+        bool own[kStatTargets];
+#pragma unroll
+        for (int T = 0; T < kStatTargets; ++T) {
+            own[T] = true;
+#pragma unroll
+            for (int U = 0; U < T; ++U) own[T] = own[T] && (prefix[U] != prefix[T]);
+        }
+        for (int64_t i = r0 + threadIdx.x / cols; i < r1; i += 4 * rows_per_iter) {      // 4 rows in flight per thread
+            int32_t oi[4]; float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int64_t ii = i + (int64_t)u * rows_per_iter; oi[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = oi[u] >= 0 ? R.obs[(base + oi[u]) * R.ldo + j] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (oi[u] < 0) continue;
+                const uint32_t k = sortable_key(v[u]);
+                const uint32_t byte = (k >> shift) & 255u;
+                const uint32_t hi = pass ? (k >> (shift + 8)) : 0u;
+#pragma unroll
+                for (int T = 0; T < kStatTargets; ++T)
+                    if (own[T] && (pass == 0 || hi == prefix[T])) atomicAdd(h + T * 256 + byte, 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cols * kStatTargets * 256; i += 256) {
+        const unsigned int v = sh[i];
+        if (v) atomicAdd(hist + ((size_t)a * ob + j0) * kStatTargets * 256 + i, v);
+    }
+}
+
+// one warp per (agent, column): walk the 256 bins of every target, append the byte that contains its rank, clear the histogram
+__global__ void stats_select_step_kernel(int P, int ob, int pass, unsigned long long* __restrict__ state, unsigned int* __restrict__ hist) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= P * ob) return;
+    unsigned long long* st = state + (size_t)w * kStatTargets * 2;
+    unsigned int* h = hist + (size_t)w * kStatTargets * 256;
+    uint32_t prefix[kStatTargets];
+    for (int T = 0; T < kStatTargets; ++T) prefix[T] = (uint32_t)st[2 * T];
+    __syncwarp();
+    for (int T = 0; T < kStatTargets; ++T) {
+        int src = T;      // a target that shared its prefix with an earlier one reads that one's histogram
+        for (int U = T - 1; U >= 0; --U) if (prefix[U] == prefix[T]) src = U;
+        if (lane == 0) {
+            unsigned long long rank = st[2 * T + 1], cum = 0;
+            int b = 0;
+            for (; b < 255; ++b) {
+                const unsigned int c = h[src * 256 + b];
+                if (cum + c > rank) break;
+                cum += c;
+            }
+            st[2 * T] = ((unsigned long long)prefix[T] << 8) | (unsigned long long)b;
+            st[2 * T + 1] = rank - cum;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < kStatTargets * 256; i += 32) h[i] = 0;
+}
+
+float ring_stats_key_to_float(uint32_t key) { return key_to_float(key); }
+
+cudaError_t launch_ring_obs_stats(const RingView& R, int P, const int64_t* d_len, const int64_t* h_len, int nb, double* d_partial,
+                                  double* d_moments /*[2][P][ob]*/, unsigned long long* d_state, unsigned int* d_hist,
+                                  unsigned long long* h_state /*pinned or pageable staging*/, cudaStream_t s) {
+    const int ob = R.ob;
+    double* d_mean = d_moments; double* d_std = d_moments + (size_t)P * ob;
+    if (ob > 256) return cudaErrorInvalidValue;
+    dim3 grid(nb, P);
+    stats_moment_kernel<<<grid, 256, 0, s>>>(R, d_len, 0, nullptr, d_partial);
+    stats_moment_finish_kernel<<<(P * ob + 255) / 256, 256, 0, s>>>(d_partial, d_len, P, nb, ob, 0, d_mean);
+    stats_moment_kernel<<<grid, 256, 0, s>>>(R, d_len, 1, d_mean, d_partial);
+    stats_moment_finish_kernel<<<(P * ob + 255) / 256, 256, 0, s>>>(d_partial, d_len, P, nb, ob, 1, d_std);
+    // ranks as numpy computes them for method "linear": virtual index (n - 1) * q in fp64, lo = floor, hi = min(lo + 1, n - 1)
+    for (int a = 0; a < P; ++a) {
+        const int64_t n = h_len[a];
+        const double q[2] = {0.01, 0.99};      // np.true_divide(1, 100), np.true_divide(99, 100)
+        for (int j = 0; j < ob; ++j)
+            for (int T = 0; T < kStatTargets; ++T) {
+                const double v = (double)(n - 1) * q[T / 2];
+                int64_t lo = (int64_t)floor(v);
+                int64_t r = (T & 1) ? (lo + 1 < n ? lo + 1 : n - 1) : lo;
+                if (r < 0) r = 0;
+                h_state[(((size_t)a * ob + j) * kStatTargets + T) * 2] = 0ull;
+                h_state[(((size_t)a * ob + j) * kStatTargets + T) * 2 + 1] = (unsigned long long)r;
+            }
+    }
+    cudaError_t e = cudaMemcpyAsync(d_state, h_state, (size_t)P * ob * kStatTargets * 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(d_hist, 0, (size_t)P * ob * kStatTargets * 256 * sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    const int groups = (ob + kStatColsPerBlock - 1) / kStatColsPerBlock;
+    const size_t sh = (size_t)kStatColsPerBlock * kStatTargets * 256 * sizeof(unsigned int);      // 48 KB
+    e = cudaFuncSetAttribute(stats_select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return e;
+    for (int pass = 0; pass < 4; ++pass) {
+        stats_select_hist_kernel<<<dim3(nb, P, groups), 256, sh, s>>>(R, d_len, pass, d_state, d_hist);
+        stats_select_step_kernel<<<(P * ob * 32 + 255) / 256, 256, 0, s>>>(P, ob, pass, d_state, d_hist);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace spp

@@ -248,6 +248,26 @@ class Population:
                                              int(bool(denormalize_actor_out)), _ptr(tgt, C.c_float), _ptr(act, C.c_float)))
         return tgt, act
 
+    def ring_obs_stats(self, return_bytes=False):
+        """MetaReplayBuffer.update_obs_mean_std (rltoolkit/buffer/replay_buffer.py:83-96) for every agent, on the device:
+        -> dict of [P, ob] float64 arrays: mean, std (numpy ddof 0), p1, p99 (np.percentile 'linear').  The kernels return the
+        exact order statistics; the interpolation below is numpy's own `_lerp` in fp64, so p1 / p99 are bit-exact."""
+        out = np.empty((self.P, 6, self.ob_dim), np.float64)
+        nbytes = C.c_double()
+        check(self.lib.spp_ring_obs_stats(self.h, _ptr(out, C.c_double), C.byref(nbytes)))
+        res = {"mean": out[:, 0].copy(), "std": out[:, 1].copy()}
+        n = np.array([self.ring_state(a)[2] for a in range(self.P)], np.float64)
+        for name, q, lo, hi in (("p1", 1, 2, 3), ("p99", 99, 4, 5)):
+            qq = np.true_divide(q, 100)
+            v = (n - 1) * qq                                           # numpy's 'linear' method: get_virtual_index
+            t = (v - np.floor(v))[:, None]
+            a, b = out[:, lo], out[:, hi]
+            d = b - a
+            lerp = a + d * t
+            lerp = np.where(t >= 0.5, b - d * (1 - t), lerp)           # numpy.lib._function_base_impl._lerp
+            res[name] = lerp
+        return (res, nbytes.value) if return_bytes else res
+
     def rollout_synthetic(self, envs_per_agent, steps, seed=0, act_noise=0.1, stream=None):
         check(self.lib.spp_rollout_synthetic_device(self.h, int(envs_per_agent), int(steps), int(seed), float(act_noise), stream))
 

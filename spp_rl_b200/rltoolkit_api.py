@@ -145,13 +145,15 @@ class ReplayRing:
 
     def update_obs_mean_std(self):
         """MetaReplayBuffer.update_obs_mean_std (replay_buffer.py:83-96): whole-buffer mean / population std and the
-        1st / 99th percentiles with running widening.  Host numpy for now."""
+        1st / 99th percentiles with running widening.  The statistics come from the device (spp_ring_obs_stats: fp64 moments and an
+        exact radix select of the order statistics np.percentile interpolates between); only [ob]-sized vectors cross the ABI."""
         if len(self) > 10:
-            obs = self.all_obs()
-            self.obs_mean = torch.tensor(obs.mean(axis=0), dtype=self.dtype)
-            self.obs_std = torch.tensor(obs.std(axis=0), dtype=self.dtype)
-            cur_max = torch.from_numpy(np.percentile(obs, 99, axis=0)).float()
-            cur_min = torch.from_numpy(np.percentile(obs, 1, axis=0)).float()
+            st = self.pop.ring_obs_stats()
+            a = self.agent
+            self.obs_mean = torch.tensor(st["mean"][a], dtype=self.dtype)
+            self.obs_std = torch.tensor(st["std"][a], dtype=self.dtype)
+            cur_max = torch.from_numpy(st["p99"][a]).float()
+            cur_min = torch.from_numpy(st["p1"][a]).float()
             if self.max_obs is None or self.min_obs is None:
                 self.max_obs, self.min_obs = cur_max, cur_min
             else:
