@@ -185,45 +185,57 @@ __device__ inline void stage_gather(const Ctx& c, int g) {
     const int B = L.B, ob = L.ob, ldo = L.ldo;
     float* xo = c.S + L.s.xo; float* xn = c.S + L.s.xn; float* xc = c.S + L.s.xc;
     float* vr = c.vec(VEC_R); float* vnd = c.vec(VEC_ND);
-    const int lane = lane_id();
     const bool from_ring = (c.a.batch.obs == nullptr);
-    for (int r = warp_id(); r < B; r += kWarps) {
-        const float *po, *pn, *pa; float rew; int done;
-        if (from_ring) {
-            const RingPtrs& R = c.a.ring;
-            int64_t i;
-            if (c.a.idx) {
-                i = c.a.idx[((size_t)c.agent * c.a.G + g) * B + r];
-            } else {   // device sampler: uniform over [0, current_len)
-                const uint4 x = Philox::gen(c.a.seed ^ 0x9E3779B97F4A7C15ull, ((uint64_t)c.agent << 32) | (uint32_t)g,
-                                            (c.a.seq << 20) | (uint32_t)r);
-                i = (int64_t)__umul64hi(((uint64_t)x.x << 32) | x.y, (uint64_t)c.a.ring_len[c.agent]);
+    // Two phases per block of 256 rows, so that the dependent loads (index -> obs_idx / next_obs_idx -> rows) of ALL rows are in
+    // flight together instead of one row per warp at a time: (1) one thread per row resolves the three row pointers into shared
+    // memory and writes reward / gamma (1 - done); (2) the rows are copied with the (row, column) pairs flattened over the CTA.
+    const float** rp = reinterpret_cast<const float**>(c.sm.red);      // [3][kThreads] row pointers: obs, next_obs, action
+    for (int r0 = 0; r0 < B; r0 += kThreads) {
+        const int nr = min(kThreads, B - r0);
+        const int r = r0 + threadIdx.x;
+        if (threadIdx.x < nr) {
+            const float *po, *pn, *pa; float rew; int done;
+            if (from_ring) {
+                const RingPtrs& R = c.a.ring;
+                int64_t i;
+                if (c.a.idx) {
+                    i = c.a.idx[((size_t)c.agent * c.a.G + g) * B + r];
+                } else {   // device sampler: uniform over [0, current_len)
+                    const uint4 x = Philox::gen(c.a.seed ^ 0x9E3779B97F4A7C15ull, ((uint64_t)c.agent << 32) | (uint32_t)g,
+                                                (c.a.seq << 20) | (uint32_t)r);
+                    i = (int64_t)__umul64hi(((uint64_t)x.x << 32) | x.y, (uint64_t)c.a.ring_len[c.agent]);
+                }
+                const size_t base = (size_t)c.agent * R.S;
+                po = R.obs + (base + R.oidx[base + i]) * ldo;
+                pn = R.obs + (base + R.nidx[base + i]) * ldo;
+                pa = L.acm_critic ? R.aacm + (base + i) * L.lda : R.act + (base + i) * ldo;
+                rew = R.rew[base + i];
+                done = R.done[base + i];
+            } else {
+                const BatchPtrs& Bt = c.a.batch;
+                const size_t row = ((size_t)c.agent * c.a.G + g) * B + r;
+                po = Bt.obs + row * ob; pn = Bt.nobs + row * ob;
+                pa = L.acm_critic ? Bt.aacm + row * L.ac : Bt.act + row * ob;
+                rew = Bt.rew[row];
+                done = Bt.done[row];
             }
-            const size_t base = (size_t)c.agent * R.S;
-            po = R.obs + (base + R.oidx[base + i]) * ldo;
-            pn = R.obs + (base + R.nidx[base + i]) * ldo;
-            pa = L.acm_critic ? R.aacm + (base + i) * L.lda : R.act + (base + i) * ldo;
-            rew = R.rew[base + i];
-            done = R.done[base + i];
-        } else {
-            const BatchPtrs& Bt = c.a.batch;
-            const size_t row = ((size_t)c.agent * c.a.G + g) * B + r;
-            po = Bt.obs + row * ob; pn = Bt.nobs + row * ob;
-            pa = L.acm_critic ? Bt.aacm + row * L.ac : Bt.act + row * ob;
-            rew = Bt.rew[row];
-            done = Bt.done[row];
-        }
-        for (int j = lane; j < ob; j += 32) {
-            const float o = po[j];
-            xo[r * ldo + j] = o;
-            xn[r * ldo + j] = pn[j];
-            xc[r * L.ldc + j] = o;
-        }
-        for (int j = lane; j < L.act_dim; j += 32) xc[r * L.ldc + ldo + j] = pa[j];
-        if (lane == 0) {
+            rp[threadIdx.x] = po; rp[kThreads + threadIdx.x] = pn; rp[2 * kThreads + threadIdx.x] = pa;
             vr[r] = rew;
             vnd[r] = __fmul_rn(c.a.h.gamma, (float)(1 - done));   // gamma * (1 - done)
         }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nr * ob; e += kThreads) {
+            const int rr = e / ob, j = e - rr * ob, row = r0 + rr;
+            const float o = rp[rr][j];
+            xo[row * ldo + j] = o;
+            xn[row * ldo + j] = rp[kThreads + rr][j];
+            xc[row * L.ldc + j] = o;
+        }
+        for (int e = threadIdx.x; e < nr * L.act_dim; e += kThreads) {
+            const int rr = e / L.act_dim, j = e - rr * L.act_dim;
+            xc[(r0 + rr) * L.ldc + ldo + j] = rp[2 * kThreads + rr][j];
+        }
+        __syncthreads();
     }
 }
 
