@@ -26,9 +26,15 @@ __device__ inline void stage_actor_head_bwd(const Ctx& c) {
     const float norm_d = (float)(2.0 / ((double)B * (double)ob));
     float cb[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     float dist_sum = 0.f, term_sum = 0.f, aterm_sum = 0.f;
-    for (int r = warp; r < B; r += kWarps) {
+    // lane groups as in stage_sample: a warp works on 32 / gs rows at a time
+    int gs = 32;
+    while (gs > 4 && (gs >> 1) >= ob) gs >>= 1;
+    const int rpw = 32 / gs, grp = lane / gs, gl = lane % gs;
+    for (int rb = warp * rpw; rb < B; rb += kWarps * rpw) {
+        const int r = rb + grp;
+        if (r >= B) continue;
         int k = 0;
-        for (int j = lane; j < ob; j += 32, ++k) {
+        for (int j = gl; j < ob; j += gs, ++k) {
             const float th = zt[r * ldo + j];
             const float zd = xm[r * L.ldm + ldo + j];
             float dz = 0.f, dzd = 0.f;
@@ -81,7 +87,7 @@ __device__ inline void stage_actor_head_bwd(const Ctx& c) {
                 if (k < 4) cb[0][k] += d3;
             }
         }
-        if (ALGO == ALGO_SAC && lane == 0) {
+        if (ALGO == ALGO_SAC && gl == 0) {
             const float term = __fsub_rn(-lp[r], h.target_entropy);
             term_sum += __fmul_rn(invB, term);
             aterm_sum += term;
@@ -89,18 +95,18 @@ __device__ inline void stage_actor_head_bwd(const Ctx& c) {
     }
     // head-bias gradients: cross-warp reduce -> gvec(GV_MISC)[0..heads)
     __syncthreads();
-    {
+    {   // one slot of `heads` floats per lane group: (8 warps x rpw groups) x heads <= 1776 floats
+        const int slot = warp * rpw + grp;
         int k = 0;
-        for (int j = lane; j < ob; j += 32, ++k) {
-            c.sm.red[warp * 512 + j] = cb[0][k];
-            if (ALGO == ALGO_SAC) c.sm.red[warp * 512 + ob + j] = cb[1][k];
+        for (int j = gl; j < ob; j += gs, ++k) {
+            c.sm.red[slot * L.heads + j] = cb[0][k];
+            if (ALGO == ALGO_SAC) c.sm.red[slot * L.heads + ob + j] = cb[1][k];
         }
     }
     __syncthreads();
     for (int n = threadIdx.x; n < L.heads; n += kThreads) {
         float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += c.sm.red[w * 512 + n];
+        for (int w = 0; w < kWarps * rpw; ++w) s += c.sm.red[w * L.heads + n];      // fixed order: deterministic
         c.gvec(GV_MISC)[n] = s;
     }
     const float dist_tot = block_sum(dist_sum, c.sm.small);

@@ -250,9 +250,18 @@ __device__ inline void stage_sample(const Ctx& c, int g, int pass) {
     float* logp_out = c.vec(pass == 0 ? VEC_LOGPN : VEC_LOGP);
     const float* lim = c.normv(NORM_LIM); const float* doff = c.normv(NORM_DOFF); const float* dsc = c.normv(NORM_DSCALE);
     const float kLogSqrt2Pi = 0.918938533204672741780329736406f, kLog2 = 0.693147180559945309417232121458f;
-    for (int r = warp_id(); r < B; r += kWarps) {
+    // A row is handled by a group of gs lanes (the smallest power of two >= ob, at least 4), so a warp works on 32 / gs rows at a
+    // time (Hopper: 2, Pendulum: 8) instead of leaving the lanes >= ob idle.  The group-wide xor tree gives bit-identical sums to
+    // a 32-lane tree over zero-padded lanes.
+    int gs = 32;
+    while (gs > 4 && (gs >> 1) >= ob) gs >>= 1;
+    const int rpw = 32 / gs, grp = lane / gs, gl = lane % gs;
+    for (int rb = warp_id() * rpw; rb < B; rb += kWarps * rpw) {
+        const int r = rb + grp;
+        const bool valid = r < B;
         float lp = 0.f, corr = 0.f;
-        for (int j = lane; j < ob; j += 32) {
+        if (valid)
+        for (int j = gl; j < ob; j += gs) {
             const float mu = ml[r * L.ldh + j];
             const float ls = fminf(fmaxf(ml[r * L.ldh + ob + j], -20.f), 2.f);
             const float sd = expf(ls);
@@ -278,8 +287,11 @@ __device__ inline void stage_sample(const Ctx& c, int g, int pass) {
             else xcp[r * L.ldc + ldo + j] = zd;
             if (pass == 1) { zt[r * ldo + j] = th; epsb[r * ldo + j] = e; if (!L.acm_critic) xm[r * L.ldm + ldo + j] = zd; }
         }
-        lp = warp_sum(lp); corr = warp_sum(corr);
-        if (lane == 0) logp_out[r] = __fsub_rn(lp, __fmul_rn(2.f, corr));
+        for (int o = gs >> 1; o > 0; o >>= 1) {
+            lp += __shfl_xor_sync(0xffffffffu, lp, o);
+            corr += __shfl_xor_sync(0xffffffffu, corr, o);
+        }
+        if (valid && gl == 0) logp_out[r] = __fsub_rn(lp, __fmul_rn(2.f, corr));
     }
 }
 
@@ -291,14 +303,14 @@ __device__ inline void stage_ddpg_post(const Ctx& c, int pass) {
     const float* ml = c.S + L.s.ml;
     float* xm = c.S + L.s.xm; float* xcp = c.S + L.s.xcp;
     const float* doff = c.normv(NORM_DOFF); const float* dsc = c.normv(NORM_DSCALE);
-    for (int r = warp_id(); r < B; r += kWarps)
-        for (int j = lane; j < ob; j += 32) {
-            const float zd = __fadd_rn(doff[j], __fmul_rn(ml[r * L.ldh + j], dsc[j]));
-            const float xv = x[r * ldo + j];
-            xcp[r * L.ldc + j] = xv;
-            if (L.acm_critic) { xm[r * L.ldm + j] = xv; xm[r * L.ldm + ldo + j] = zd; }
-            else { xcp[r * L.ldc + ldo + j] = zd; if (pass == 1) xm[r * L.ldm + ldo + j] = zd; }
-        }
+    for (int e = threadIdx.x; e < B * ob; e += kThreads) {      // (row, column) pairs flattened over the CTA
+        const int r = e / ob, j = e - r * ob;
+        const float zd = __fadd_rn(doff[j], __fmul_rn(ml[r * L.ldh + j], dsc[j]));
+        const float xv = x[r * ldo + j];
+        xcp[r * L.ldc + j] = xv;
+        if (L.acm_critic) { xm[r * L.ldm + j] = xv; xm[r * L.ldm + ldo + j] = zd; }
+        else { xcp[r * L.ldc + ldo + j] = zd; if (pass == 1) xm[r * L.ldm + ldo + j] = zd; }
+    }
 }
 
 // ---- ACM forward (AcM: tanh-tanh-tanh*lim; BasicAcM: skip connection and learnable gains).  Writes the action
