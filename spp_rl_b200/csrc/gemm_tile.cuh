@@ -236,6 +236,9 @@ __device__ __forceinline__ float act_fn(float x) {
 template <int ACT, bool SCALE, bool ADD>
 struct EpiBiasAct {
     float* C; int ldc; const float* bias; const float* scale; float* C2; int ldc2; const float* Sk; int lds; float t;
+    // optional (128 x 128 tiles only): the sign pattern of the stored tile, bit i * NJ + j of word [(m0 / 128) * 2 + n0 / 128][thread]
+    // = (C[row_of(i), col_of(j)] > 0).  The backward's EpiMaskStore<MASK_RELU> reads these 8 bytes per thread instead of the tile.
+    unsigned long long* mask_out = nullptr;
     __device__ __forceinline__ void prefetch(int m0, int rows, int n0, int cols, int M, int N) const {
         if (ADD) prefetch_l2_tile(Sk, lds, m0, min(rows, M - m0), n0, min(cols, N - n0));
     }
@@ -244,6 +247,7 @@ struct EpiBiasAct {
         const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
         constexpr int G4 = Cfg::NJ / 4;
         float4 b[G4], sc[G4];
+        unsigned long long bits = 0ull;
 #pragma unroll
         for (int g = 0; g < G4; ++g) {
             const int n = n0 + col_of<Cfg>(4 * g, tx);
@@ -278,8 +282,12 @@ struct EpiBiasAct {
                     x.x *= sc[g].x; x.y *= sc[g].y; x.z *= sc[g].z; x.w *= sc[g].w;
                 }
                 st4(C + (size_t)m * ldc + n, x);
+                if constexpr (Cfg::MI * Cfg::NJ == 64)
+                    bits |= (unsigned long long)((x.x > 0.f) | ((x.y > 0.f) << 1) | ((x.z > 0.f) << 2) | ((x.w > 0.f) << 3)) << (i * Cfg::NJ + 4 * g);
             }
         }
+        if constexpr (Cfg::MI * Cfg::NJ == 64)
+            if (mask_out) mask_out[(size_t)((m0 / 128) * 2 + n0 / 128) * kThreads + threadIdx.x] = bits;
     }
 };
 
@@ -289,6 +297,7 @@ enum Mask { MASK_NONE = 0, MASK_RELU = 1, MASK_TANH = 2 };
 template <int MASK, bool COLSUM, bool ACCUM>
 struct EpiMaskStore {
     float* C; int ldc; const float* H; int ldh; float* colsum;
+    const unsigned long long* mask_in = nullptr;      // MASK_RELU, 128 x 128 tiles: the bits EpiBiasAct::mask_out left, instead of H
     __device__ __forceinline__ void prefetch(int m0, int rows, int n0, int cols, int M, int N) const {
         if (MASK != MASK_NONE) prefetch_l2_tile(H, ldh, m0, min(rows, M - m0), n0, min(cols, N - n0));
         if (ACCUM) prefetch_l2_tile(C, ldc, m0, min(rows, M - m0), n0, min(cols, N - n0));
@@ -302,6 +311,9 @@ struct EpiMaskStore {
         for (int j = 0; j < Cfg::NJ; ++j) cs[j] = 0.f;
         // issue every global load of the tile first (one latency instead of one per row)
         float4 h[Cfg::MI][G4], old[Cfg::MI][G4];
+        const bool use_bits = (MASK == MASK_RELU) && (Cfg::MI * Cfg::NJ == 64) && mask_in != nullptr;
+        unsigned long long bits = 0ull;
+        if (use_bits) bits = mask_in[(size_t)((m0 / 128) * 2 + n0 / 128) * kThreads + threadIdx.x];
 #pragma unroll
         for (int i = 0; i < Cfg::MI; ++i) {
             const int m = m0 + row_of<Cfg, A_KC>(i, ty);
@@ -310,7 +322,10 @@ struct EpiMaskStore {
                 const int n = n0 + col_of<Cfg>(4 * g, tx);
                 h[i][g] = make_float4(0.f, 0.f, 0.f, 0.f);
                 old[i][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (MASK != MASK_NONE && m < M && n < N) h[i][g] = ld4(H + (size_t)m * ldh + n);
+                if (use_bits) {
+                    const unsigned int q = (unsigned int)(bits >> (i * Cfg::NJ + 4 * g)) & 15u;
+                    h[i][g] = make_float4((float)(q & 1u), (float)((q >> 1) & 1u), (float)((q >> 2) & 1u), (float)((q >> 3) & 1u));
+                } else if (MASK != MASK_NONE && m < M && n < N) h[i][g] = ld4(H + (size_t)m * ldh + n);
                 if (ACCUM && m < M && n < N) old[i][g] = ld4(C + (size_t)m * ldc + n);
             }
         }

@@ -173,8 +173,8 @@ __device__ __forceinline__ void gemm_big(const Ctx& c, const float* A, int lda, 
 template <class Cfg, int ACT, bool SCALE>
 __device__ inline void linear_fwd(const Ctx& c, const float* X, int ldx, int K, const float* net, const LayerDesc& l,
                                   float* C, int ldc, int B, const float* scale = nullptr, float* C2 = nullptr,
-                                  int ldc2 = 0) {
-    EpiBiasAct<ACT, SCALE, false> epi{C, ldc, net + l.off_b, scale, C2, ldc2, nullptr, 0, 0.f};
+                                  int ldc2 = 0, float* relu_bits = nullptr) {
+    EpiBiasAct<ACT, SCALE, false> epi{C, ldc, net + l.off_b, scale, C2, ldc2, nullptr, 0, 0.f, reinterpret_cast<unsigned long long*>(relu_bits)};
     if constexpr (Cfg::TN == 128) gemm_big<true>(c, X, ldx, net + l.off_wt, l.ld_t, B, l.rows, K, epi);
     else gemm<Cfg, true>(X, ldx, net + l.off_wt, l.ld_t, B, l.rows, K, c.sm.gemm, epi);
 }
@@ -399,7 +399,8 @@ __device__ inline void critics_hidden(const Ctx& c, const float* X, const int* n
     const Layout& L = c.a.L;
     float* S = c.S;
     for (int i = 0; i < ncrit; ++i)
-        linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldc, L.ldc, c.net(nets[i]), L.critic.L[0], S + L.s.hc1[i], kHidden, L.B);
+        linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldc, L.ldc, c.net(nets[i]), L.critic.L[0], S + L.s.hc1[i], kHidden, L.B, nullptr,
+                                             nullptr, 0, S + L.s.mk_hc1[i]);
     __syncthreads();
     for (int i = 0; i < ncrit; ++i)
         linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.hc1[i], kHidden, kHidden, c.net(nets[i]), L.critic.L[1],
@@ -591,9 +592,10 @@ __device__ inline void actor_forward(const Ctx& c, const float* X, int actor_net
     const Layout& L = c.a.L;
     float* S = c.S;
     const float* net = c.net(actor_net);
-    linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldo, L.ldo, net, L.actor.L[0], S + L.s.ha1, kHidden, L.B);
+    linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldo, L.ldo, net, L.actor.L[0], S + L.s.ha1, kHidden, L.B, nullptr, nullptr, 0, S + L.s.mk_ha1);
     __syncthreads();
-    linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.ha1, kHidden, kHidden, net, L.actor.L[1], S + L.s.ha2, kHidden, L.B);
+    linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.ha1, kHidden, kHidden, net, L.actor.L[1], S + L.s.ha2, kHidden, L.B, nullptr, nullptr, 0,
+                                         S + L.s.mk_ha2);
     __syncthreads();
     if (ALGO == ALGO_SAC)
         linear_fwd<NarrowTile, ACT_NONE, false>(c, S + L.s.ha2, kHidden, kHidden, net, L.actor.L[2], S + L.s.ml, L.ldh, L.B);
