@@ -293,11 +293,11 @@ struct EpiBiasAct {
 
 // Backward through an activation: C[m,n] = acc * act'(H[m,n]); column sums -> bias gradient (atomicAdd).
 //   MASK_RELU: act' = (H > 0);  MASK_TANH: act' = 1 - H^2;  MASK_NONE: 1.  ACCUM: C += ...
-enum Mask { MASK_NONE = 0, MASK_RELU = 1, MASK_TANH = 2 };
+enum Mask { MASK_NONE = 0, MASK_RELU = 1, MASK_TANH = 2, MASK_RELU_BITS = 3 };      // _BITS: mask_in instead of H (128 x 128 tiles)
 template <int MASK, bool COLSUM, bool ACCUM>
 struct EpiMaskStore {
     float* C; int ldc; const float* H; int ldh; float* colsum;
-    const unsigned long long* mask_in = nullptr;      // MASK_RELU, 128 x 128 tiles: the bits EpiBiasAct::mask_out left, instead of H
+    const unsigned long long* mask_in = nullptr;      // MASK_RELU_BITS: the bits EpiBiasAct::mask_out left
     __device__ __forceinline__ void prefetch(int m0, int rows, int n0, int cols, int M, int N) const {
         if (MASK != MASK_NONE) prefetch_l2_tile(H, ldh, m0, min(rows, M - m0), n0, min(cols, N - n0));
         if (ACCUM) prefetch_l2_tile(C, ldc, m0, min(rows, M - m0), n0, min(cols, N - n0));
@@ -311,9 +311,9 @@ struct EpiMaskStore {
         for (int j = 0; j < Cfg::NJ; ++j) cs[j] = 0.f;
         // issue every global load of the tile first (one latency instead of one per row)
         float4 h[Cfg::MI][G4], old[Cfg::MI][G4];
-        const bool use_bits = (MASK == MASK_RELU) && (Cfg::MI * Cfg::NJ == 64) && mask_in != nullptr;
+        static_assert(MASK != MASK_RELU_BITS || Cfg::MI * Cfg::NJ == 64, "bit masks are defined for the 8 x 8 per-thread mapping");
         unsigned long long bits = 0ull;
-        if (use_bits) bits = mask_in[(size_t)((m0 / 128) * 2 + n0 / 128) * kThreads + threadIdx.x];
+        if (MASK == MASK_RELU_BITS) bits = mask_in[(size_t)((m0 / 128) * 2 + n0 / 128) * kThreads + threadIdx.x];
 #pragma unroll
         for (int i = 0; i < Cfg::MI; ++i) {
             const int m = m0 + row_of<Cfg, A_KC>(i, ty);
@@ -322,10 +322,7 @@ struct EpiMaskStore {
                 const int n = n0 + col_of<Cfg>(4 * g, tx);
                 h[i][g] = make_float4(0.f, 0.f, 0.f, 0.f);
                 old[i][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (use_bits) {
-                    const unsigned int q = (unsigned int)(bits >> (i * Cfg::NJ + 4 * g)) & 15u;
-                    h[i][g] = make_float4((float)(q & 1u), (float)((q >> 1) & 1u), (float)((q >> 2) & 1u), (float)((q >> 3) & 1u));
-                } else if (MASK != MASK_NONE && m < M && n < N) h[i][g] = ld4(H + (size_t)m * ldh + n);
+                if (MASK != MASK_NONE && MASK != MASK_RELU_BITS && m < M && n < N) h[i][g] = ld4(H + (size_t)m * ldh + n);
                 if (ACCUM && m < M && n < N) old[i][g] = ld4(C + (size_t)m * ldc + n);
             }
         }
@@ -343,6 +340,7 @@ struct EpiMaskStore {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     if (MASK == MASK_RELU) x[e] = (hh[e] > 0.f) ? x[e] : 0.f;
+                    if (MASK == MASK_RELU_BITS) x[e] = ((bits >> (i * Cfg::NJ + 4 * g + e)) & 1ull) ? x[e] : 0.f;
                     if (MASK == MASK_TANH) x[e] = x[e] * (1.f - hh[e] * hh[e]);
                     if (ACCUM) x[e] += oo[e];
                     if (COLSUM) cs[4 * g + e] += x[e];

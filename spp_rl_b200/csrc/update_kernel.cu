@@ -178,7 +178,7 @@ __device__ void update_step(const Ctx& c, int g) {
     __syncthreads();
     for (int i = 0; i < ncrit; ++i) {   // dz1 = (dz2 W2) * relu'(hc1); column sums -> d b1
         const LayerDesc& l = L.critic.L[1];
-        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, c.gvec(GV_CB1_0 + i),
+        EpiMaskStore<MASK_RELU_BITS, true, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, c.gvec(GV_CB1_0 + i),
                                                  reinterpret_cast<const unsigned long long*>(S + L.s.mk_hc1[i])};
         gemm_big<true>(c, S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
@@ -211,7 +211,7 @@ __device__ void update_step(const Ctx& c, int g) {
     __syncthreads();
     for (int i = 0; i < ncrit; ++i) {
         const LayerDesc& l = L.critic.L[1];
-        EpiMaskStore<MASK_RELU, false, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, nullptr,
+        EpiMaskStore<MASK_RELU_BITS, false, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, nullptr,
                                                   reinterpret_cast<const unsigned long long*>(S + L.s.mk_hc1[i])};
         gemm_big<true>(c, S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
@@ -230,14 +230,14 @@ __device__ void update_step(const Ctx& c, int g) {
     stage_actor_head_bwd<ALGO>(c);
     {   // dza2 = (dml Wheads) * relu'(ha2); column sums -> d b2
         const LayerDesc& l = L.actor.L[2];
-        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza2, kHidden, S + L.s.ha2, kHidden, c.gvec(GV_AB2),
+        EpiMaskStore<MASK_RELU_BITS, true, false> epi{S + L.s.dza2, kHidden, S + L.s.ha2, kHidden, c.gvec(GV_AB2),
                                                  reinterpret_cast<const unsigned long long*>(S + L.s.mk_ha2)};
         gemm_big<true>(c, S + L.s.dml, L.ldh, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, L.heads, epi);
     }
     __syncthreads();
     {   // dza1 = (dza2 W2) * relu'(ha1); column sums -> d b1
         const LayerDesc& l = L.actor.L[1];
-        EpiMaskStore<MASK_RELU, true, false> epi{S + L.s.dza1, kHidden, S + L.s.ha1, kHidden, c.gvec(GV_AB1),
+        EpiMaskStore<MASK_RELU_BITS, true, false> epi{S + L.s.dza1, kHidden, S + L.s.ha1, kHidden, c.gvec(GV_AB1),
                                                  reinterpret_cast<const unsigned long long*>(S + L.s.mk_ha1)};
         gemm_big<true>(c, S + L.s.dza2, kHidden, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
