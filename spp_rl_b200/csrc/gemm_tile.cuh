@@ -239,6 +239,10 @@ struct EpiBiasAct {
     // optional (128 x 128 tiles only): the sign pattern of the stored tile, bit i * NJ + j of word [(m0 / 128) * 2 + n0 / 128][thread]
     // = (C[row_of(i), col_of(j)] > 0).  The backward's EpiMaskStore<MASK_RELU> reads these 8 bytes per thread instead of the tile.
     unsigned long long* mask_out = nullptr;
+    // optional (128 x 128 tiles of a 256-wide layer, TX = 16): fold a following 256 -> 1 linear head into this epilogue.
+    // dot_out[m * 32 + (n0 / 128) * 16 + tx] = sum over the thread's 8 columns of C[m, n] * dot_w[n]; the consumer adds the 32
+    // partials of a row in a fixed order.  C may then be null (the activation itself is never stored).
+    const float* dot_w = nullptr; float* dot_out = nullptr;
     __device__ __forceinline__ void prefetch(int m0, int rows, int n0, int cols, int M, int N) const {
         if (ADD) prefetch_l2_tile(Sk, lds, m0, min(rows, M - m0), n0, min(cols, N - n0));
     }
@@ -246,12 +250,13 @@ struct EpiBiasAct {
     __device__ __forceinline__ void apply(float (&acc)[Cfg::MI][Cfg::NJ], int m0, int n0, int M, int N, float*) {
         const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
         constexpr int G4 = Cfg::NJ / 4;
-        float4 b[G4], sc[G4];
+        float4 b[G4], sc[G4], dw[G4];
         unsigned long long bits = 0ull;
 #pragma unroll
         for (int g = 0; g < G4; ++g) {
             const int n = n0 + col_of<Cfg>(4 * g, tx);
             b[g] = (n < N) ? ld4(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dw[g] = (dot_out && n < N) ? ld4(dot_w + n) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (SCALE) sc[g] = (n < N) ? ld4(scale + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
@@ -259,6 +264,7 @@ struct EpiBiasAct {
             const int m = m0 + row_of<Cfg, A_KC>(i, ty);
             if (m >= M) continue;
             float4 ad[G4];
+            float dot = 0.f;
             if (ADD) {
 #pragma unroll
                 for (int g = 0; g < G4; ++g) {
@@ -281,10 +287,12 @@ struct EpiBiasAct {
                     if (C2) st4(C2 + (size_t)m * ldc2 + n, x);
                     x.x *= sc[g].x; x.y *= sc[g].y; x.z *= sc[g].z; x.w *= sc[g].w;
                 }
-                st4(C + (size_t)m * ldc + n, x);
+                if (C) st4(C + (size_t)m * ldc + n, x);
+                dot = fmaf(x.x, dw[g].x, dot); dot = fmaf(x.y, dw[g].y, dot); dot = fmaf(x.z, dw[g].z, dot); dot = fmaf(x.w, dw[g].w, dot);
                 if constexpr (Cfg::MI * Cfg::NJ == 64)
                     bits |= (unsigned long long)((x.x > 0.f) | ((x.y > 0.f) << 1) | ((x.z > 0.f) << 2) | ((x.w > 0.f) << 3)) << (i * Cfg::NJ + 4 * g);
             }
+            if (Cfg::TX == 16 && dot_out) dot_out[(size_t)m * 32 + (n0 / 128) * 16 + tx] = dot;
         }
         if constexpr (Cfg::MI * Cfg::NJ == 64)
             if (mask_out) mask_out[(size_t)((m0 / 128) * 2 + n0 / 128) * kThreads + threadIdx.x] = bits;

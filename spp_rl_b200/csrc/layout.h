@@ -63,6 +63,8 @@ struct ScratchDesc {
     int dxm;                // [B x ldm]   d loss / d ACM input
     int dml;                // [B x ldh]   d loss / d actor head outputs
     int dza2, dza1;         // [B x 256]   actor backward
+    int mk_hc2[2];          // relu mask of hc2 for the passes that never store hc2 (target and policy pass)
+    int qpart[2];           // [B x 32] partial critic-head dot products, see EpiBiasAct::dot_out
     int mk_hc1[2], mk_ha1, mk_ha2;   // relu masks of hc1 / ha1 / ha2 as bits (64 per thread and 128 x 128 block), see EpiBiasAct::mask_out
     int vec;                // per-row vectors: r, notdone, y, logp_n, logp, q[2], dq[2]  (9 x Bp)
     int gvec;               // small gradient vectors (bias grads, fc3 grads): see kGvec*
@@ -184,6 +186,8 @@ inline Layout make_layout(int algo, int ob, int ac, int acm_kind, int acm_critic
     {   // one uint64 per thread and 128 x 128 output block: ceil(B / 128) row tiles x 2 column halves x 256 threads x 2 floats
         const int mk = ((Bp + 127) / 128) * 2 * 256 * 2;
         s.mk_hc1[0] = take(mk); s.mk_hc1[1] = take(mk); s.mk_ha1 = take(mk); s.mk_ha2 = take(mk);
+        s.mk_hc2[0] = take(mk); s.mk_hc2[1] = take(mk);
+        s.qpart[0] = take(Bp * 32); s.qpart[1] = take(Bp * 32);
     }
     s.vec = take(9 * Bp);
     s.gvec = take(8 * 512);

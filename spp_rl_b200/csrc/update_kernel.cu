@@ -168,12 +168,12 @@ __device__ void update_step(const Ctx& c, int g) {
     if (ALGO == ALGO_SAC) stage_sample(c, g, 0); else stage_ddpg_post(c, 0);
     __syncthreads();
     if (L.acm_critic) acm_forward(c, S + L.s.xcp + L.ldo, L.ldc);
-    critics_hidden(c, S + L.s.xcp, tcrit, ncrit);
+    critics_hidden(c, S + L.s.xcp, tcrit, ncrit, true);
     stage_qtarget(c, tcrit, ncrit);
     __syncthreads();
 
     // ---- Phase B: critic step(s) (sac_acm.py:117-131 / ddpg_acm.py:175-182), Polyak fused (sac.py:186-199)
-    critics_hidden(c, S + L.s.xc, crit, ncrit);
+    critics_hidden(c, S + L.s.xc, crit, ncrit, false);
     stage_critic_head_bwd<0>(c, crit, tcrit, ncrit, ls + LOSS_CRITIC_1);
     __syncthreads();
     for (int i = 0; i < ncrit; ++i) {   // dz1 = (dz2 W2) * relu'(hc1); column sums -> d b1
@@ -206,8 +206,8 @@ __device__ void update_step(const Ctx& c, int g) {
     if (ALGO == ALGO_SAC) stage_sample(c, g, 1); else stage_ddpg_post(c, 1);
     __syncthreads();
     if (L.acm_critic) acm_forward(c, S + L.s.xcp + L.ldo, L.ldc);
-    critics_hidden(c, S + L.s.xcp, crit, ncrit);
-    stage_critic_head_bwd<1>(c, crit, tcrit, ncrit, ls + LOSS_PI);
+    critics_hidden(c, S + L.s.xcp, crit, ncrit, true);
+    stage_policy_head_bwd(c, crit, ncrit, ls + LOSS_PI);
     __syncthreads();
     for (int i = 0; i < ncrit; ++i) {
         const LayerDesc& l = L.critic.L[1];

@@ -173,8 +173,9 @@ __device__ __forceinline__ void gemm_big(const Ctx& c, const float* A, int lda, 
 template <class Cfg, int ACT, bool SCALE>
 __device__ inline void linear_fwd(const Ctx& c, const float* X, int ldx, int K, const float* net, const LayerDesc& l,
                                   float* C, int ldc, int B, const float* scale = nullptr, float* C2 = nullptr,
-                                  int ldc2 = 0, float* relu_bits = nullptr) {
-    EpiBiasAct<ACT, SCALE, false> epi{C, ldc, net + l.off_b, scale, C2, ldc2, nullptr, 0, 0.f, reinterpret_cast<unsigned long long*>(relu_bits)};
+                                  int ldc2 = 0, float* relu_bits = nullptr, const float* dot_w = nullptr, float* dot_out = nullptr) {
+    EpiBiasAct<ACT, SCALE, false> epi{C, ldc, net + l.off_b, scale, C2, ldc2, nullptr, 0, 0.f, reinterpret_cast<unsigned long long*>(relu_bits),
+                                      dot_w, dot_out};
     if constexpr (Cfg::TN == 128) gemm_big<true>(c, X, ldx, net + l.off_wt, l.ld_t, B, l.rows, K, epi);
     else gemm<Cfg, true>(X, ldx, net + l.off_wt, l.ld_t, B, l.rows, K, c.sm.gemm, epi);
 }
@@ -394,23 +395,47 @@ __device__ inline void acm_backward_dx(const Ctx& c) {
     __syncthreads();
 }
 
-// ---- critic hidden layers for `ncrit` critics: hc1 = relu(fc1 x), hc2 = relu(fc2 hc1)
-__device__ inline void critics_hidden(const Ctx& c, const float* X, const int* nets, int ncrit) {
+constexpr int kRB = 4;      // rows a warp handles at a time in the critic-head stages
+
+// ---- critic hidden layers for `ncrit` critics: hc1 = relu(fc1 x), hc2 = relu(fc2 hc1).
+//      fused_head: hc2 is never stored; the fc2 epilogue leaves its relu mask as bits (mk_hc2) and the 32 partial dot products
+//      per row of q = hc2 . w3 (qpart) -- all the target pass and the policy pass need (stage_qtarget, stage_policy_head_bwd).
+__device__ inline void critics_hidden(const Ctx& c, const float* X, const int* nets, int ncrit, bool fused_head) {
     const Layout& L = c.a.L;
     float* S = c.S;
     for (int i = 0; i < ncrit; ++i)
         linear_fwd<BigTile, ACT_RELU, false>(c, X, L.ldc, L.ldc, c.net(nets[i]), L.critic.L[0], S + L.s.hc1[i], kHidden, L.B, nullptr,
                                              nullptr, 0, S + L.s.mk_hc1[i]);
     __syncthreads();
-    for (int i = 0; i < ncrit; ++i)
-        linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.hc1[i], kHidden, kHidden, c.net(nets[i]), L.critic.L[1],
-                                             S + L.s.hc2[i], kHidden, L.B);
+    for (int i = 0; i < ncrit; ++i) {
+        const float* net = c.net(nets[i]);
+        if (fused_head)
+            linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.hc1[i], kHidden, kHidden, net, L.critic.L[1], nullptr, kHidden, L.B, nullptr, nullptr, 0,
+                                                 S + L.s.mk_hc2[i], net + L.critic.L[2].off_w, S + L.s.qpart[i]);
+        else
+            linear_fwd<BigTile, ACT_RELU, false>(c, S + L.s.hc1[i], kHidden, kHidden, net, L.critic.L[1], S + L.s.hc2[i], kHidden, L.B);
+    }
     __syncthreads();
+}
+
+// q of `ncrit` critics for 4 rows r0..r0+3 from the partials the fc2 epilogue left: lane s holds partial s of a row, the warp tree adds
+// them in a fixed order.  Result valid in every lane.
+__device__ __forceinline__ void q_from_partials(const Ctx& c, int r0, int ncrit, const float (&b3)[2], float (&q)[2][kRB]) {
+    const Layout& L = c.a.L;
+    float p[2][kRB];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int rr = 0; rr < kRB; ++rr)
+            p[i][rr] = (i < ncrit && r0 + rr < L.B) ? c.S[L.s.qpart[i] + (size_t)(r0 + rr) * 32 + lane_id()] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int rr = 0; rr < kRB; ++rr) q[i][rr] = warp_sum(p[i][rr]) + b3[i];
 }
 
 // ---- critic heads.  fc3 is a 256-vector, so q = hc2 . w3 + b3 is done row-wise: each warp takes kRB rows at a
 //      time, issues all of their loads first (kRB x 8 coalesced 128-byte reads per critic), then reduces.
-constexpr int kRB = 4;
 
 struct HeadRows {
     float h[2][kRB][8];     // hc2 values of this lane: critic i, row rr, column lane + 32 k
@@ -465,22 +490,91 @@ __device__ inline void stage_qtarget(const Ctx& c, const int* tnets, int ncrit) 
     const Layout& L = c.a.L;
     float* y = c.vec(VEC_Y);
     const float* vr = c.vec(VEC_R); const float* vnd = c.vec(VEC_ND); const float* lpn = c.vec(VEC_LOGPN);
-    float w3[2][8], b3[2];
-    head_weights_load(c, tnets, ncrit, w3, b3);
-    HeadRows hr;
+    float b3[2] = {0.f, 0.f};
+    for (int i = 0; i < ncrit; ++i) b3[i] = c.net(tnets[i])[L.critic.L[2].off_b];
     for (int r0 = warp_id() * kRB; r0 < L.B; r0 += kWarps * kRB) {
-        head_rows_load(c, r0, ncrit, w3, b3, hr);
+        float qq[2][kRB];
+        q_from_partials(c, r0, ncrit, b3, qq);
         if (lane_id() < kRB && r0 + lane_id() < L.B) {
             const int r = r0 + lane_id();
             float q = 0.f;
 #pragma unroll
             for (int rr = 0; rr < kRB; ++rr)
-                if (rr == lane_id()) q = (ncrit == 2) ? fminf(hr.q[0][rr], hr.q[1][rr]) : hr.q[0][rr];
+                if (rr == lane_id()) q = (ncrit == 2) ? fminf(qq[0][rr], qq[1][rr]) : qq[0][rr];
             float inner = q;
             if (L.algo == ALGO_SAC) inner = __fsub_rn(q, __fmul_rn(c.sm.alpha, lpn[r]));
             y[r] = __fadd_rn(vr[r], __fmul_rn(vnd[r], inner));
         }
     }
+}
+
+// ---- policy pass through the critic heads (fused form): loss = mean(alpha logp - min_i q_i) (SAC) / mean(-q) (DDPG), dq = -1/B routed
+//      to argmin_i q_i, and dz2_i[r, k] = (hc2_i[r, k] > 0) dq_i w3_i[k] rebuilt from the relu bits -- hc2 itself was never stored.
+//      Lane l owns the 8 columns of thread tx = l % 16 of column half nh = l / 16 in the epilogue's mapping.
+__device__ inline void stage_policy_head_bwd(const Ctx& c, const int* nets, int ncrit, float* loss_out) {
+    const Layout& L = c.a.L;
+    float* S = c.S;
+    const int B = L.B, lane = lane_id(), warp = warp_id();
+    const float* lp = c.vec(VEC_LOGP);
+    const float gq = -1.0f / (float)B, invB = 1.0f / (float)B;
+    const int nh = lane >> 4, tx = lane & 15, c0 = nh * 128 + 4 * tx;
+    float4 w3a[2], w3b[2]; float b3[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        w3a[i] = w3b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i >= ncrit) continue;
+        const float* net = c.net(nets[i]);
+        b3[i] = net[L.critic.L[2].off_b];
+        w3a[i] = ld4(net + L.critic.L[2].off_w + c0);
+        w3b[i] = ld4(net + L.critic.L[2].off_w + c0 + 64);
+    }
+    float lsum = 0.f;
+    for (int r0 = warp * kRB; r0 < B; r0 += kWarps * kRB) {
+        float qq[2][kRB];
+        q_from_partials(c, r0, ncrit, b3, qq);
+        unsigned long long wd[2][kRB];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int rr = 0; rr < kRB; ++rr) {
+                const int r = r0 + rr;
+                wd[i][rr] = 0ull;
+                if (i < ncrit && r < B)
+                    wd[i][rr] = reinterpret_cast<const unsigned long long*>(S + L.s.mk_hc2[i])[(size_t)((r >> 7) * 2 + nh) * kThreads + (r & 15) * 16 + tx];
+            }
+#pragma unroll
+        for (int rr = 0; rr < kRB; ++rr) {
+            const int r = r0 + rr;
+            if (r >= B) break;
+            float dq[2] = {0.f, 0.f};
+            if (ncrit == 2) {
+                const float q0 = qq[0][rr], q1 = qq[1][rr];
+                const float tie = (q0 == q1) ? 0.5f * gq : 0.f;
+                dq[0] = (q0 < q1 ? gq : 0.f) + tie;
+                dq[1] = (q1 < q0 ? gq : 0.f) + tie;
+                const float qm = fminf(q0, q1);
+                lsum += (lane == 0) ? (L.algo == ALGO_SAC ? __fsub_rn(__fmul_rn(c.sm.alpha, lp[r]), qm) : -qm) : 0.f;
+            } else {
+                dq[0] = gq;
+                lsum += (lane == 0) ? -qq[0][rr] : 0.f;
+            }
+            const int sh = 8 * ((r & 127) >> 4);      // byte i = (r % 128) / 16 of the thread's word
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i >= ncrit) break;
+                const unsigned int m8 = (unsigned int)(wd[i][rr] >> sh) & 255u;
+                float* dz2 = S + L.s.dz2[i] + (size_t)r * kHidden;
+                const float d = dq[i];
+                st4(dz2 + c0, make_float4((m8 & 1u) ? __fmul_rn(d, w3a[i].x) : 0.f, (m8 & 2u) ? __fmul_rn(d, w3a[i].y) : 0.f,
+                                          (m8 & 4u) ? __fmul_rn(d, w3a[i].z) : 0.f, (m8 & 8u) ? __fmul_rn(d, w3a[i].w) : 0.f));
+                st4(dz2 + c0 + 64, make_float4((m8 & 16u) ? __fmul_rn(d, w3b[i].x) : 0.f, (m8 & 32u) ? __fmul_rn(d, w3b[i].y) : 0.f,
+                                               (m8 & 64u) ? __fmul_rn(d, w3b[i].z) : 0.f, (m8 & 128u) ? __fmul_rn(d, w3b[i].w) : 0.f));
+            }
+        }
+    }
+    const float t = block_sum(lsum, c.sm.small);
+    if (threadIdx.x == 0 && loss_out) loss_out[0] = t * invB;
+    __syncthreads();
 }
 
 // ---- critic loss + backward through fc3 (+ Adam on fc3 / b3 / b2 of each critic).
