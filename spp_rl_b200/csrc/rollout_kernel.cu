@@ -80,19 +80,28 @@ __device__ inline void rollout_env_and_ring(const Ctx& c, const RolloutArgs& r, 
     const int64_t S = c.a.ring.S;
     const size_t base = (size_t)c.agent * S;
     const int64_t o0 = r.obs_cur[c.agent] + (int64_t)step * E, t0 = r.ts_cur[c.agent] + (int64_t)step * E;
-    for (int row = warp_id(); row < E; row += kWarps) {
-        const int lane = lane_id();
+    // a lane group of gs lanes (smallest power of two >= ob, at least 4) per environment: 32 / gs environments per warp at a time;
+    // the group-wide xor tree gives the same sum as a 32-lane tree over zero-padded lanes
+    int gs = 32;
+    while (gs > 4 && (gs >> 1) >= ob) gs >>= 1;
+    const int rpw = 32 / gs, grp = lane_id() / gs, lane = lane_id() % gs;
+    for (int rb = warp_id() * rpw; rb < E; rb += kWarps * rpw) {
+        const int row = rb + grp;
+        const bool valid = row < E;
         const int64_t orow = (o0 + row) % S, nrow = (o0 + E + row) % S, trow = (t0 + row) % S;
-        float* st = r.env_state + ((size_t)c.agent * E + row) * ldo;
+        float* st = r.env_state + ((size_t)c.agent * E + (valid ? row : 0)) * ldo;
         float mix = 0.f;
-        for (int j = lane; j < ac; j += 32) {
-            const float a = pa[row * L.lda + j];
-            r.w_aacm[(base + trow) * L.lda + j] = a;
-            mix += a * (0.3f + 0.1f * (float)j);
-        }
-        mix = tanhf(warp_sum(mix));
+        if (valid)
+            for (int j = lane; j < ac; j += gs) {
+                const float a = pa[row * L.lda + j];
+                r.w_aacm[(base + trow) * L.lda + j] = a;
+                mix += a * (0.3f + 0.1f * (float)j);
+            }
+        for (int o = gs >> 1; o > 0; o >>= 1) mix += __shfl_xor_sync(0xffffffffu, mix, o);
+        mix = tanhf(mix);
+        if (!valid) continue;
         float rew = 0.f;
-        for (int j = lane; j < ob; j += 32) {
+        for (int j = lane; j < ob; j += gs) {
             const uint4 w = Philox::gen(c.a.seed ^ 0xE9Full, ((uint64_t)c.agent << 32) | (uint32_t)step, (c.a.seq << 24) | (uint32_t)(row * ob + j));
             const float o = st[j];
             const float nx = 0.98f * o + 0.1f * mix * (1.f - 0.01f * (float)j) + 0.02f * normal_from_bits(w.x, w.y);
