@@ -88,7 +88,11 @@ __device__ inline void rollout_env_and_ring(const Ctx& c, const RolloutArgs& r, 
     for (int rb = warp_id() * rpw; rb < E; rb += kWarps * rpw) {
         const int row = rb + grp;
         const bool valid = row < E;
-        const int64_t orow = (o0 + row) % S, nrow = (o0 + E + row) % S, trow = (t0 + row) % S;
+        // cursors < S, row < E and (steps + 1) E <= S: at most two wraps -- conditional subtraction instead of a 64-bit modulo
+        int64_t orow = o0 + row, nrow = o0 + E + row, trow = t0 + row;
+        orow -= orow >= S ? S : 0; orow -= orow >= S ? S : 0;
+        nrow -= nrow >= S ? S : 0; nrow -= nrow >= S ? S : 0;
+        trow -= trow >= S ? S : 0; trow -= trow >= S ? S : 0;
         float* st = r.env_state + ((size_t)c.agent * E + (valid ? row : 0)) * ldo;
         float mix = 0.f;
         if (valid)
