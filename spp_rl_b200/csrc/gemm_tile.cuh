@@ -1,7 +1,9 @@
-// FP32 tile GEMM for the fused update kernels: C[m,n] = sum_k A(m,k) * B(k,n), CUDA-core FFMA path.
+// FP32 tile GEMM for the fused kernels: C[m,n] = sum_k A(m,k) * B(k,n), CUDA-core FFMA path.  It carries the narrow products
+// (heads, ACM, first-layer dW, dX to the inputs), the 64-wide SPP-PPO nets, and -- as the A/B fallback of gemm_umma.cuh -- the
+// 256-wide products.  The epilogue functors defined here are shared with the tensor-core path.
 //
 // Operands live in global memory (L2-resident agent state / activation scratch) and are streamed
-// through a 4-stage cp.async (LDGSTS, L2-only) shared-memory pipeline; accumulators stay in
+// through a 3-stage cp.async (LDGSTS, L2-only) shared-memory pipeline; accumulators stay in
 // registers and leave through an epilogue functor (bias+activation store, masked store with column
 // sums, Adam+Polyak read-modify-write), so no gradient or pre-activation is ever materialised twice.
 //
@@ -15,8 +17,8 @@
 // which the first version of this kernel paid for with dispatch stalls on ~40% of its FFMAs
 // (profiles/r01_update_v1_summary.md).  With B[k][n..n+3] fragments the b operand's parity follows
 // n, the accumulator's parity is free, and the a operand is held in the operand-reuse cache.
-// The exactness target (1e-5 relative vs the fp32 reference) is why this path is FFMA and not
-// single-pass bf16/tf32 tensor cores; k is accumulated in ascending order.
+// k is accumulated in ascending order with one fmaf per product (the exactness target is 1e-5 relative vs the fp32 reference;
+// the tensor-core path needs a three-pass operand split and a per-chunk accumulator drain to meet it, gemm_umma.cuh).
 #pragma once
 #include "common.cuh"
 
