@@ -40,11 +40,13 @@ constexpr int kStagePitch = 132;                           // floats; conflict-f
 constexpr int kStageBlockFloats = 128 * kStagePitch;       // one 128 x 128 block
 static_assert(2 * kStageBlockFloats * 4 <= kUmmaSmemBytes, "accumulator staging aliases the operand slots");
 
+// Pipeline state of a CTA, all of it in SHARED memory (a struct in the kernel's frame would sit in local memory, which the 213 KB
+// shared-memory carve-out leaves almost no L1 for): the GEMM entry reads it once, thread 0 writes the parities back.
 struct UmmaCtx {
     unsigned char* smem;        // 1024-byte aligned, kUmmaSmemBytes
     uint64_t* mbar;             // [kUmmaSlots]: "the MMAs of the chunk in this slot have retired"
     uint32_t tmem;              // TMEM base (512 columns)
-    uint32_t phase_bits;        // per-slot mbarrier parity this thread waits for next (identical in every thread)
+    uint32_t phase_bits;        // per-slot mbarrier parity the threads wait for next (identical in every thread)
     uint32_t dbg;               // timing experiments only (self-test): 1 = no MMAs, 2 = no operand staging, 4 = no epilogue
 };
 
@@ -240,10 +242,14 @@ template <bool A_KM, bool B_KM, class Epi>
 __device__ __forceinline__ void gemm256_umma(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
                                              UmmaCtx& u, Epi& epi) {
     const int mtiles = (M + 127) / 128;
+    unsigned char* smem = u.smem; uint64_t* mbar = u.mbar;
+    const uint32_t tmem = u.tmem, dbg = u.dbg;
+    uint32_t phase = u.phase_bits;
     for (int mt = 0; mt < mtiles; ++mt) {
-        u.phase_bits = umma_mainloop<A_KM, B_KM>(A, lda, B, ldb, M, K, mt * 128, u.smem, u.mbar, u.tmem, u.phase_bits, u.dbg);
-        if (!(u.dbg & 4)) umma_epilogue<A_KM, Epi>(umma::smem_u32(u.smem), reinterpret_cast<float*>(u.smem), mt * 128, M, epi);
-        __syncthreads();          // the staging aliases the operand slots of the next tile / GEMM
+        phase = umma_mainloop<A_KM, B_KM>(A, lda, B, ldb, M, K, mt * 128, smem, mbar, tmem, phase, dbg);
+        if (!(dbg & 4)) umma_epilogue<A_KM, Epi>(umma::smem_u32(smem), reinterpret_cast<float*>(smem), mt * 128, M, epi);
+        if (threadIdx.x == 0) u.phase_bits = phase;
+        __syncthreads();          // the staging aliases the operand slots of the next tile / GEMM; publishes the parities
     }
 }
 

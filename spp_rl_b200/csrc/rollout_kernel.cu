@@ -131,10 +131,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = smem_struct(smem_raw);
     const UpdateArgs& a = r.u;
-    UmmaCtx um;
-    if (a.use_umma) umma_setup(sm, um);
+    UmmaCtx* um = a.use_umma ? umma_setup(sm) : nullptr;
     for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
-        Ctx c(a, agent, sm, a.use_umma ? &um : nullptr);
+        Ctx c(a, agent, sm, um);
         const Layout& L = a.L;
         for (int step = 0; step < r.steps; ++step) {
             rollout_load(c, r, step);
@@ -151,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
             __syncthreads();
         }
     }
-    if (a.use_umma) umma_teardown(um);
+    if (um) umma_teardown(um);
 }
 
 cudaError_t launch_rollout(const RolloutArgs& r, int grid, cudaStream_t stream) {

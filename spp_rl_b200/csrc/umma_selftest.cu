@@ -117,8 +117,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_selftest_kernel(const f
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    UmmaCtx u{smem, mbar, tmem_base_s, 0u, (uint32_t)(reps >> 16)};
+    __shared__ UmmaCtx u;      // pipeline state is shared: thread 0 publishes the barrier parities after every tile
+    if (threadIdx.x == 0) u = UmmaCtx{smem, mbar, tmem_base_s, 0u, (uint32_t)(reps >> 16)};
     reps &= 0xFFFF;
+    __syncthreads();
     EpiMaskStore<MASK_NONE, false, false> epi{C, 256, nullptr, 0, nullptr};
     for (int r = 0; r < reps; ++r) gemm256_umma<A_KM, B_KM>(A, lda, B, ldb, M, K, u, epi);
     fence_before_sync();

@@ -81,6 +81,7 @@ struct Smem {
     AdamScalars adam[4];
     float alpha;                      // temperature as fp32 (Python float rounded when it meets fp32 tensors)
     uint32_t tmem_base;               // TMEM allocation of this CTA (tcgen05 path)
+    UmmaCtx um;                       // tcgen05 pipeline state (shared, see gemm_umma.cuh)
     uint64_t mbar[kUmmaSlots];        // one mbarrier per pipeline slot: "the MMAs reading this half-plane have retired"
 };
 static_assert(kUmmaSmemBytes / 4 >= kGemmSmemFloats, "the FFMA pipeline aliases the tcgen05 stages");
@@ -117,7 +118,7 @@ struct Ctx {
 };
 
 // ---- tcgen05 state of a persistent CTA: TMEM accumulators (all 512 columns) and the slot barriers live for the whole launch
-__device__ __forceinline__ void umma_setup(Smem& sm, UmmaCtx& um) {
+__device__ __forceinline__ UmmaCtx* umma_setup(Smem& sm) {
     if (warp_id() == 0) umma::tmem_alloc<kUmmaTmemCols>(&sm.tmem_base);
     if (threadIdx.x == 0) {
         for (int s = 0; s < kUmmaSlots; ++s) umma::mbar_init(sm.mbar + s, 1);
@@ -126,16 +127,20 @@ __device__ __forceinline__ void umma_setup(Smem& sm, UmmaCtx& um) {
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    um.smem = reinterpret_cast<unsigned char*>(sm.gemm);
-    um.mbar = sm.mbar;
-    um.tmem = sm.tmem_base;
-    um.phase_bits = 0;
-    um.dbg = 0;
+    if (threadIdx.x == 0) {
+        sm.um.smem = reinterpret_cast<unsigned char*>(sm.gemm);
+        sm.um.mbar = sm.mbar;
+        sm.um.tmem = sm.tmem_base;
+        sm.um.phase_bits = 0;
+        sm.um.dbg = 0;
+    }
+    __syncthreads();
+    return &sm.um;
 }
-__device__ __forceinline__ void umma_teardown(UmmaCtx& um) {
+__device__ __forceinline__ void umma_teardown(UmmaCtx* um) {
     umma::fence_before_sync();
     __syncthreads();
-    if (warp_id() == 0) umma::tmem_dealloc<kUmmaTmemCols>(um.tmem);
+    if (warp_id() == 0) umma::tmem_dealloc<kUmmaTmemCols>(um->tmem);
 }
 
 // ---- Adam bookkeeping: bump the step of optimiser `opt` and publish its scalars (thread 0 only)
