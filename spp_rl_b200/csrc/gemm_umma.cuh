@@ -59,8 +59,8 @@ struct UmmaOperand {
     static constexpr int KSTEP = KM ? 0 : kThreads / CPR;       // MN-major: k-rows between consecutive p (8 or 4)
     static constexpr uint32_t DSTEP = KM ? 4096u : (uint32_t)(KSTEP / 4) * 512u;
     const float* src0;
-    size_t sstep;               // floats between consecutive p
-    size_t kstride;             // floats per unit of k
+    uint32_t sstep;             // floats between consecutive p   (32-bit: an operand is far smaller than 2^32 floats, and every
+    uint32_t kstride;           // floats per unit of k            register counts next to the 128 running sums of the main loop)
     uint32_t dst0;
     int kofs0;                  // k offset of chunk p inside the 32-wide k-chunk: kofs0 + p * KSTEP
     int np_ok;                  // chunks p < np_ok are inside the operand (rows / columns tail)
@@ -71,41 +71,96 @@ struct UmmaOperand {
             const int row = (threadIdx.x >> 6) * 8 + (threadIdx.x & 7);      // + 32 p
             kstride = 1; kofs0 = 4 * q;
             src0 = G + (size_t)(r0 + row) * ld + 4 * q;
-            sstep = (size_t)32 * ld;
+            sstep = 32u * (uint32_t)ld;
             dst0 = umma::kmajor_offset(row, q);
             const int left = R - r0 - row;                                   // rows row + 32 p < R - r0
             np_ok = left <= 0 ? 0 : min(NP, (left + 31) / 32);
         } else {                 // a warp covers 512 contiguous bytes of one k-row
             const int chunk = threadIdx.x % CPR, kb = threadIdx.x / CPR;     // k = kb + KSTEP p
-            kstride = (size_t)ld; kofs0 = kb;
+            kstride = (uint32_t)ld; kofs0 = kb;
             src0 = G + (size_t)kb * ld + r0 + 4 * chunk;
-            sstep = (size_t)KSTEP * ld;
+            sstep = (uint32_t)KSTEP * (uint32_t)ld;
             dst0 = umma::mnmajor_offset(kb, chunk);
             np_ok = (r0 + 4 * chunk < R) ? NP : 0;
         }
     }
     // raw fp32 chunk, global -> its swizzled position in the hi plane (16-byte LDGSTS, zero-filled outside the operand)
     __device__ __forceinline__ void issue(int k0, int K, uint32_t hi) const {
-        const float* s = src0 + (size_t)k0 * kstride;
+        const float* s = src0 + (uint32_t)k0 * kstride;
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const bool ok = (p < np_ok) && (k0 + kofs0 + p * KSTEP < K);
-            const float* g = ok ? s + p * sstep : src0;
+            const float* g = ok ? s + (uint32_t)p * sstep : src0;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(hi + dst0 + p * DSTEP), "l"(g), "r"(ok ? 16 : 0));
         }
     }
     // in-place split of the chunks this thread copied: hi plane <- rn_tf32(x), lo plane <- rn_tf32(x - hi)
     __device__ __forceinline__ void split(uint32_t hi, uint32_t lo) const {
+        // four chunks at a time: the 128 running sums of the main loop leave ~100 registers for everything else
+#pragma unroll
+        for (int p0 = 0; p0 < NP; p0 += 4) {
+            float4 r[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) r[p] = umma::lds128(hi + dst0 + (p0 + p) * DSTEP);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float4 h, l;
+                umma::split_tf32(r[p].x, h.x, l.x); umma::split_tf32(r[p].y, h.y, l.y);
+                umma::split_tf32(r[p].z, h.z, l.z); umma::split_tf32(r[p].w, h.w, l.w);
+                umma::sts128(hi + dst0 + (p0 + p) * DSTEP, h);
+                umma::sts128(lo + dst0 + (p0 + p) * DSTEP, l);
+            }
+        }
+    }
+};
+
+// The A operand with its storage order as a RUNTIME flag (same affine scheme): the main loop is then ONE function for forward / dX
+// (K-major A) and dW (MN-major A) products.  With two template instances ptxas gave only one of them a full register budget and
+// kept the other's 128 running sums in local memory (~1.1 KB of spills, LDL / STL in every drain).
+struct UmmaOperandA {
+    static constexpr int NP = 4;
+    const float* src0;
+    uint32_t sstep, kstride, dst0, dstep;
+    int kofs0, kstep, np_ok;
+    __device__ __forceinline__ void init(bool km, const float* __restrict__ G, int ld, int R, int r0) {
+        if (km) {
+            const int q = (threadIdx.x >> 3) & 7;
+            const int row = (threadIdx.x >> 6) * 8 + (threadIdx.x & 7);      // + 32 p
+            kstride = 1; kofs0 = 4 * q; kstep = 0; dstep = 4096u;
+            src0 = G + (size_t)(r0 + row) * ld + 4 * q;
+            sstep = 32u * (uint32_t)ld;
+            dst0 = umma::kmajor_offset(row, q);
+            const int left = R - r0 - row;
+            np_ok = left <= 0 ? 0 : min(NP, (left + 31) / 32);
+        } else {
+            const int chunk = threadIdx.x % 32, kb = threadIdx.x / 32;       // k = kb + 8 p
+            kstride = (uint32_t)ld; kofs0 = kb; kstep = 8; dstep = 1024u;
+            src0 = G + (size_t)kb * ld + r0 + 4 * chunk;
+            sstep = 8u * (uint32_t)ld;
+            dst0 = umma::mnmajor_offset(kb, chunk);
+            np_ok = (r0 + 4 * chunk < R) ? NP : 0;
+        }
+    }
+    __device__ __forceinline__ void issue(int k0, int K, uint32_t hi) const {
+        const float* s = src0 + (uint32_t)k0 * kstride;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const bool ok = (p < np_ok) && (k0 + kofs0 + p * kstep < K);
+            const float* g = ok ? s + (uint32_t)p * sstep : src0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(hi + dst0 + p * dstep), "l"(g), "r"(ok ? 16 : 0));
+        }
+    }
+    __device__ __forceinline__ void split(uint32_t hi, uint32_t lo) const {
         float4 r[NP];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) r[p] = umma::lds128(hi + dst0 + p * DSTEP);
+        for (int p = 0; p < NP; ++p) r[p] = umma::lds128(hi + dst0 + p * dstep);
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             float4 h, l;
             umma::split_tf32(r[p].x, h.x, l.x); umma::split_tf32(r[p].y, h.y, l.y);
             umma::split_tf32(r[p].z, h.z, l.z); umma::split_tf32(r[p].w, h.w, l.w);
-            umma::sts128(hi + dst0 + p * DSTEP, h);
-            umma::sts128(lo + dst0 + p * DSTEP, l);
+            umma::sts128(hi + dst0 + p * dstep, h);
+            umma::sts128(lo + dst0 + p * dstep, l);
         }
     }
 };
@@ -114,13 +169,16 @@ struct UmmaOperand {
 template <bool FIRST>
 __device__ __forceinline__ void umma_drain(uint32_t taddr, float (&sum)[128]) {
 #pragma unroll
-    for (int cb = 0; cb < 8; cb += 4) {
-        float v[4][16];
+#ifndef SPP_DRAIN_STEP
+#define SPP_DRAIN_STEP 2      // TMEM loads in flight per wait: 4 costs 16 of the 128 running sums their registers (local-memory spills)
+#endif
+    for (int cb = 0; cb < 8; cb += SPP_DRAIN_STEP) {
+        float v[SPP_DRAIN_STEP][16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) umma::tmem_ld16_nowait(taddr + (cb + i) * 16, v[i]);
+        for (int i = 0; i < SPP_DRAIN_STEP; ++i) umma::tmem_ld16_nowait(taddr + (cb + i) * 16, v[i]);
         umma::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < SPP_DRAIN_STEP; ++i)
 #pragma unroll
             for (int e = 0; e < 16; ++e) sum[(cb + i) * 16 + e] = FIRST ? v[i][e] : __fadd_rn(sum[(cb + i) * 16 + e], v[i][e]);
     }
@@ -152,9 +210,9 @@ __device__ __noinline__ void umma_epilogue(uint32_t stage_s, float* stage, int m
 // Main loop of one 128 x 256 tile: leaves the fp32 result in the shared staging buffer (two 128 x 128 blocks of pitch
 // kStagePitch at the start of the operand slots).  A separate function (independent of the epilogue type) so that its
 // register allocation -- 128 running sums + 48 registers of operands in flight -- is not disturbed by the epilogue's.
-template <bool A_KM, bool B_KM>
-__device__ __noinline__ uint32_t umma_mainloop(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
-                                               int m0, unsigned char* smem, uint64_t* mbar, uint32_t tmem, uint32_t phase_in, uint32_t dbg) {
+template <bool B_KM>
+__device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M,
+                                               int K, int m0, unsigned char* smem, uint64_t* mbar, uint32_t tmem, uint32_t phase_in, uint32_t dbg) {
     using namespace umma;
     constexpr int N = 256;
     const int nchunks = (K + 31) / 32;
@@ -165,8 +223,8 @@ __device__ __noinline__ uint32_t umma_mainloop(const float* __restrict__ A, int 
     uint32_t phase_bits = phase_in;      // everything by value: a by-reference argument would pin the caller's state in local memory
     UmmaOperand<B_KM, 256> lb;
     lb.init(B, ldb, N, 0);
-    UmmaOperand<A_KM, 128> la;
-    la.init(A, lda, M, m0);
+    UmmaOperandA la;
+    la.init(A_KM, A, lda, M, m0);
     float sum[128];
     const uint32_t slot_a[2] = {smem0, smem0 + kUmmaSlotBytes};
     if (!(dbg & 2)) { la.issue(0, K, slot_a[0]); lb.issue(0, K, slot_a[0] + 2 * kUmmaAPlane); }
@@ -246,7 +304,7 @@ __device__ __forceinline__ void gemm256_umma(const float* __restrict__ A, int ld
     const uint32_t tmem = u.tmem, dbg = u.dbg;
     uint32_t phase = u.phase_bits;
     for (int mt = 0; mt < mtiles; ++mt) {
-        phase = umma_mainloop<A_KM, B_KM>(A, lda, B, ldb, M, K, mt * 128, smem, mbar, tmem, phase, dbg);
+        phase = umma_mainloop<B_KM>(A_KM, A, lda, B, ldb, M, K, mt * 128, smem, mbar, tmem, phase, dbg);
         if (!(dbg & 4)) umma_epilogue<A_KM, Epi>(umma::smem_u32(smem), reinterpret_cast<float*>(smem), mt * 128, M, epi);
         if (threadIdx.x == 0) u.phase_bits = phase;
         __syncthreads();          // the staging aliases the operand slots of the next tile / GEMM; publishes the parities
