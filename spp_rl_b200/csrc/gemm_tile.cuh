@@ -420,7 +420,7 @@ struct EpiAdam {
             for (int j4 = 0; j4 < Cfg::NJ / 4; ++j4) {
                 const int nb = n0 + col_of<Cfg>(4 * j4, tx);
                 if (nb >= N) continue;
-                float4 w[4], mo[4], vo[4], tc[4], tr[4];
+                float4 w[4], mo[4], vo[4], tg[4];      // tg: the Polyak target block, row layout (Tr) or column layout (Tc) -- never both
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {   // rows mb..mb+3; every global load of the block is issued up front
                     const size_t o = (size_t)(mb + r) * ldr + nb;
@@ -428,8 +428,8 @@ struct EpiAdam {
                     w[r] = ok ? ld4(R + o) : make_float4(0.f, 0.f, 0.f, 0.f);
                     mo[r] = ok ? ld4_stream(Mo + o, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
                     vo[r] = ok ? ld4_stream(Vo + o, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    tr[r] = (Tr && ok) ? ld4(Tr + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    tc[r] = (Tc && nb + r < N) ? ld4(Tc + (size_t)(nb + r) * ldcc + mb) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    tg[r] = Tr ? (ok ? ld4(Tr + o) : make_float4(0.f, 0.f, 0.f, 0.f))
+                               : ((Tc && nb + r < N) ? ld4(Tc + (size_t)(nb + r) * ldcc + mb) : make_float4(0.f, 0.f, 0.f, 0.f));
                 }
                 float wn[4][4];
 #pragma unroll
@@ -449,7 +449,7 @@ struct EpiAdam {
                     st4_stream(Mo + o, mo[r], pol);
                     st4_stream(Vo + o, vo[r], pol);
                     if (Tr) {   // Polyak target kept in the row layout (actor heads of DDPG)
-                        const float4 t = tr[r];
+                        const float4 t = tg[r];
                         st4(Tr + o, make_float4(__fadd_rn(__fmul_rn(t.x, one_minus_tau), __fmul_rn(tau, nv.x)),
                                                 __fadd_rn(__fmul_rn(t.y, one_minus_tau), __fmul_rn(tau, nv.y)),
                                                 __fadd_rn(__fmul_rn(t.z, one_minus_tau), __fmul_rn(tau, nv.z)),
@@ -463,8 +463,8 @@ struct EpiAdam {
                         const size_t o = (size_t)(nb + e) * ldcc + mb;
                         const float4 nv = make_float4(wn[0][e], wn[1][e], wn[2][e], wn[3][e]);
                         st4(Cc + o, nv);
-                        if (Tc) {
-                            const float4 t = tc[e];
+                        if (Tc && !Tr) {
+                            const float4 t = tg[e];
                             st4(Tc + o, make_float4(__fadd_rn(__fmul_rn(t.x, one_minus_tau), __fmul_rn(tau, nv.x)),
                                                     __fadd_rn(__fmul_rn(t.y, one_minus_tau), __fmul_rn(tau, nv.y)),
                                                     __fadd_rn(__fmul_rn(t.z, one_minus_tau), __fmul_rn(tau, nv.z)),
