@@ -296,8 +296,17 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
     return phase_bits;
 }
 
+// The wrapper is a real call in the update kernel: the main loop and the epilogues get their register budget from the live set
+// of their caller (ptxas allocates across the call graph), and inlined into the 35 k-instruction kernel body that live set cost the
+// epilogues ~0.5 KB and the body 2.5 KB of spills through a ~15 KB L1 (+7.7 % updates/s as a call).  The rollout kernel has
+// two wide products per step and a small body: there the call itself costs more (-5 %), so it keeps the wrapper inline.
+#ifdef SPP_UMMA_WRAPPER_INLINE
+#define SPP_UMMA_WRAPPER_ATTR __forceinline__
+#else
+#define SPP_UMMA_WRAPPER_ATTR __noinline__
+#endif
 template <bool A_KM, bool B_KM, class Epi>
-__device__ __forceinline__ void gemm256_umma(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
+__device__ SPP_UMMA_WRAPPER_ATTR void gemm256_umma(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int K,
                                              UmmaCtx& u, Epi& epi) {
     const int mtiles = (M + 127) / 128;
     unsigned char* smem = u.smem; uint64_t* mbar = u.mbar;

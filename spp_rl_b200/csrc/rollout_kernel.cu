@@ -6,6 +6,7 @@
 // writes of rltoolkit/buffer/replay_buffer.py:56-75,133-137,332-333.  MuJoCo is not available: the device-resident
 // form advances a synthetic environment (obs' = 0.98 obs + 0.1 tanh(a-mix) + 0.02 N(0,1)) so that everything the
 // reference does per frame except the simulator itself is on the device.
+#define SPP_UMMA_WRAPPER_INLINE 1      // see gemm_umma.cuh
 #include "update_kernel.cuh"
 
 namespace spp {
