@@ -145,6 +145,10 @@ int spp_update_ring_device(spp_population* p, int grad_steps, uint64_t seed, flo
  * AcMTrainer.update_acm, rltoolkit/acm/acm.py:285-293); 0 = every step is a full acm_batch_size batch. */
 int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses);
 int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, int last_rows, uint64_t seed, float* losses);
+/* AcMTrainer.calculate_validation_loss (rltoolkit/acm/acm.py:329-343): forward + MSE only, no optimiser step, on the same
+ * host layout as spp_acm_update_host (the validation set cut into acm_batch_size chunks, last_rows in the final one);
+ * losses [P][n_batches] = the MSE of each chunk -- the caller weights them by their row counts. */
+int spp_acm_eval_host(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses);
 /* learning rates may change between calls (StepLR on the ACM optimiser, rltoolkit/acm/acm.py:181-183,299); negative = keep */
 int spp_set_learning_rates(spp_population* p, double actor_lr, double critic_lr, double alpha_lr, double acm_lr);
 

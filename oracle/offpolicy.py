@@ -281,3 +281,27 @@ def acm_batch_update(state, x, y, acm_lim, lr):
     grads, _ = nets.acm_bwd(acm, cache, 2.0 * diff / diff.numel(), acm_lim, need_w=True, need_x=False)
     adam_step_net(state, "acm", grads, lr)
     return loss
+
+
+def acm_update_epochs(state, obs, next_obs, actions_acm, perms, batch_size, acm_lim, lr0, sched_step, sched_gamma, epoch0=0):
+    """AcMTrainer.update_acm, rltoolkit/acm/acm.py:266-303: per epoch one shuffled pass (DataLoader(shuffle=True), the partial
+    last minibatch kept), then acm_scheduler.step() (StepLR, acm.py:181-183).  perms[e] stands for the sampler's permutation.
+    Returns the per-epoch mean minibatch losses (self.loss["acm"] after each epoch)."""
+    x = torch.cat([obs, next_obs], dim=1)
+    out = []
+    for e, perm in enumerate(perms):
+        lr = lr0 * sched_gamma ** ((epoch0 + e) // sched_step)
+        tot, nb = 0.0, 0
+        for b0 in range(0, len(perm), batch_size):
+            sel = torch.as_tensor(perm[b0:b0 + batch_size], dtype=torch.long)
+            tot += acm_batch_update(state, x[sel], actions_acm[sel], acm_lim, lr)
+            nb += 1
+        out.append(tot / nb)
+    return out
+
+
+def acm_validation_loss(state, obs, next_obs, actions_acm, acm_lim):
+    """AcMTrainer.calculate_validation_loss, rltoolkit/acm/acm.py:329-343: one no-grad MSE over the whole validation buffer."""
+    pred, _ = nets.acm_fwd(sub(state, "acm"), torch.cat([obs, next_obs], dim=1), acm_lim)
+    diff = pred - actions_acm
+    return float((diff * diff).mean().item())

@@ -766,8 +766,18 @@ static void fill_acm_args(spp_population* p, UpdateArgs& a, int n) {
     a.scratch = p->scratch_acm;
 }
 
+static int acm_host_pass(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses, int eval);
+
 int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses) {
-    if (!p || !x || !y) return fail(SPP_ERR_ARG, "spp_acm_update_host: null argument");
+    return acm_host_pass(p, n_batches, x, y, last_rows, losses, 0);
+}
+
+int spp_acm_eval_host(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses) {
+    return acm_host_pass(p, n_batches, x, y, last_rows, losses, 1);
+}
+
+static int acm_host_pass(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses, int eval) {
+    if (!p || !x || !y) return fail(SPP_ERR_ARG, "spp_acm_update_host / spp_acm_eval_host: null argument");
     if (n_batches < 1) return fail(SPP_ERR_ARG, "n_batches must be positive");
     CK(cudaSetDevice(p->device));
     const Layout& L = p->L_acm;
@@ -781,6 +791,7 @@ int spp_acm_update_host(spp_population* p, int n_batches, const float* x, const 
     fill_acm_args(p, a, n_batches);
     if (last_rows < 0 || last_rows > L.B) return fail(SPP_ERR_ARG, "last_rows outside [0, acm_batch_size]");
     a.acm_last_rows = (last_rows == L.B) ? 0 : last_rows;
+    a.acm_eval = eval;
     a.batch.acm_x = (const float*)p->d_obs.p;
     a.batch.acm_y = (const float*)p->d_aacm.p;
     a.losses = (float*)p->d_losses.p;

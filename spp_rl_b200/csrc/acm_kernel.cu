@@ -45,7 +45,8 @@ __device__ void acm_train_step(const Ctx& c, int g) {
     const int B = L.B, ac = L.ac;
     const bool basic = (L.acm_kind == ACM_BASIC);
     float* acm = c.net(NET_ACM); float* nm = c.net_m(NET_ACM); float* nv = c.net_v(NET_ACM);
-    if (threadIdx.x == 0) adam_begin(c, 3, h.acm_lr);
+    const bool eval = c.a.acm_eval != 0;
+    if (threadIdx.x == 0 && !eval) adam_begin(c, 3, h.acm_lr);
     for (int i = threadIdx.x; i < 4 * 512; i += kThreads) __stcg(c.gvec(0) + i, 0.f);
     acm_gather(c, g);
     __syncthreads();
@@ -68,6 +69,7 @@ __device__ void acm_train_step(const Ctx& c, int g) {
     const float ltot = block_sum(lsum, c.sm.small);
     __syncthreads();
     if (threadIdx.x == 0 && c.a.losses) c.a.losses[(size_t)c.agent * c.a.G + g] = ltot / ((float)B * (float)ac);
+    if (eval) return;      // AcMTrainer.calculate_validation_loss (rltoolkit/acm/acm.py:329-343): no_grad forward + loss
     if (threadIdx.x < ac) {      // deterministic column sums over the batch
         float s3 = 0.f, st1 = 0.f;
         for (int r = 0; r < B; ++r) {

@@ -68,6 +68,7 @@ struct UpdateArgs {
     int population;
     int batch_row_stride;    // rows between consecutive steps in the staged batch / index arrays (0 = L.B)
     int acm_last_rows;       // ACM regression: rows of the final step when it is a partial batch (0 = full)
+    int acm_eval;            // ACM regression: forward + loss only (calculate_validation_loss), no optimiser step
     int use_umma;            // 1: the 128 x 128 tile GEMMs run on tcgen05 (3-pass tf32 split); 0: FFMA tiles (A/B switch)
 };
 

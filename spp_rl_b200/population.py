@@ -227,6 +227,23 @@ class Population:
         check(self.lib.spp_acm_update_host(self.h, int(n_batches), _ptr(x, C.c_float), _ptr(y, C.c_float), int(last_rows), _ptr(losses, C.c_float)))
         return losses
 
+    def acm_validation_loss(self, x, y):
+        """AcMTrainer.calculate_validation_loss (acm.py:329-343) for one validation set per agent: x [P, N, 2*ob],
+        y [P, N, ac] -> MSE [P].  The set is cut into acm_batch_size chunks on the device; chunk means are combined in fp64."""
+        x = _f32(x); y = _f32(y)
+        N, B = x.shape[1], int(self.cfg.acm_batch_size)
+        if N < 1:
+            raise ValueError("No validation data. Were the pretrain ran?")
+        nb = (N + B - 1) // B
+        xp = np.zeros((self.P, nb * B, x.shape[2]), np.float32); xp[:, :N] = x
+        yp = np.zeros((self.P, nb * B, y.shape[2]), np.float32); yp[:, :N] = y
+        last = N - (nb - 1) * B
+        losses = np.empty((self.P, nb), np.float32)
+        check(self.lib.spp_acm_eval_host(self.h, nb, _ptr(xp, C.c_float), _ptr(yp, C.c_float), 0 if last == B else last,
+                                         _ptr(losses, C.c_float)))
+        w = np.full(nb, B, np.float64); w[-1] = last
+        return (losses.astype(np.float64) * w).sum(axis=1) / N
+
     def acm_update_ring(self, n_batches, idx=None, seed=0, losses=None, last_rows=0):
         """AcMTrainer.update_acm_batches(n) from the device ring; idx int64 [P, n, acm_batch_size] or None."""
         if losses is None:

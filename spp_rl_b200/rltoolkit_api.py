@@ -160,6 +160,54 @@ class ReplayRing:
                 self.max_obs, self.min_obs = torch.max(cur_max, self.max_obs), torch.min(cur_min, self.min_obs)
 
 
+class ValidationRing:
+    """The ACM validation buffer (ReplayBufferAcM, rltoolkit/buffer/replay_buffer.py:264-300 over MetaReplayBuffer :8-81):
+    host memory in the reference as well -- it is filled once in pre_train and only read by calculate_validation_loss,
+    whose arithmetic runs on the device (spp_acm_eval_host).  Same cursor state machine as the device ring (A10)."""
+
+    def __init__(self, size, ob_dim, ac_dim):
+        self.size = int(size)
+        self._obs = np.zeros((self.size, ob_dim), np.float32)
+        self._obs_idx = np.zeros(self.size, np.int64)
+        self._next_obs_idx = np.zeros(self.size, np.int64)
+        self._actions_acm = np.zeros((self.size, ac_dim), np.float32)
+        self.reset_idx()
+
+    def reset_idx(self):
+        self.obs_idx = self.ts_idx = self.current_len = 0
+
+    def __len__(self):
+        return self.current_len
+
+    def add_obs(self, obs):
+        self._obs[self.obs_idx] = np.asarray(obs, np.float32).reshape(-1)
+        i = self.obs_idx
+        self.obs_idx = (self.obs_idx + 1) % self.size
+        return i
+
+    def add_timestep(self, obs_idx, next_obs_idx, acm_action):
+        self._obs_idx[self.ts_idx], self._next_obs_idx[self.ts_idx] = obs_idx, next_obs_idx
+        self._actions_acm[self.ts_idx] = np.asarray(acm_action, np.float32).reshape(-1)
+        if next_obs_idx < self.ts_idx:
+            self.current_len = self.ts_idx + 1
+            self.ts_idx = 0
+        else:
+            self.ts_idx += 1
+        self.current_len = max(self.ts_idx, self.current_len)
+
+    @property
+    def obs(self):
+        return self._obs[self._obs_idx[: self.current_len]]
+
+    @property
+    def next_obs(self):
+        return self._obs[self._next_obs_idx[: self.current_len]]
+
+    @property
+    def actions_acm(self):
+        return self._actions_acm[: self.current_len]
+
+
 class _Frames:
     def __init__(self):
         self.frames = 0
@@ -215,6 +263,10 @@ class _OffPolicyAcM:
         self.acm_scheduler_epoch = 0
         self._init_weights()
         self.loss = {"actor": 0.0, "acm": 0.0}
+        if self.acm_val_buffer_size:                                  # acm.py:140-146 (10 % head room for terminal observations)
+            self.acm_val_buffer_size = int(self.acm_val_buffer_size * 1.1)
+            self.acm_val_buffer = ValidationRing(self.acm_val_buffer_size, self.ob_dim, self.ac_dim)
+            self.loss["acm_val"] = 0.0
         self._cached_acm_action = None
 
     # ------------------------------------------------------------------ nets
@@ -300,6 +352,8 @@ class _OffPolicyAcM:
         idx = np.stack([np.random.randint(0, n, self.acm_batch_size) for _ in range(n_batches)]).astype(np.int64)[None]
         losses = self._pop.acm_update_ring(n_batches, idx=np.ascontiguousarray(idx))
         self.loss["acm"] = float(losses[0].sum() / n_batches)
+        if self.acm_val_buffer_size:
+            self.loss["acm_val"] = self.calculate_validation_loss()
 
     def update_acm(self, epochs, pretrain=False):
         """AcMTrainer.update_acm (acm.py:266-303): shuffled epochs over the whole ring, StepLR stepped once per epoch."""
@@ -315,6 +369,32 @@ class _OffPolicyAcM:
             losses = self._pop.acm_update_ring(nb, idx=idx, last_rows=0 if last == B else last)
             self.loss["acm"] = float(losses[0].sum() / nb)
             self.acm_scheduler_epoch += 1
+        if self.acm_val_buffer_size:
+            self.loss["acm_val"] = self.calculate_validation_loss()
+
+    def get_val_x_y(self):
+        b = self.acm_val_buffer                                       # acm.py:313-327
+        return np.concatenate([b.obs, b.next_obs], axis=1), b.actions_acm
+
+    def calculate_validation_loss(self):
+        """AcMTrainer.calculate_validation_loss (acm.py:329-343): MSE of the ACM over the whole validation buffer."""
+        x, y = self.get_val_x_y()
+        assert len(x) > 0, "No validation data. Were the pretrain ran?"
+        return float(self._pop.acm_validation_loss(x[None], y[None])[0])
+
+    def collect_initial_batch(self, buffer, samples_no):
+        collected = 0
+        while collected < samples_no:                                 # acm.py:204-232
+            prev_idx = buffer.add_obs(self.env.reset())
+            end = False
+            while not end:
+                action = self.env.action_space.sample()
+                obs, _, end, _ = self.env.step(action)
+                next_idx = buffer.add_obs(obs)
+                buffer.add_timestep(prev_idx, next_idx, action)
+                prev_idx = next_idx
+                collected += 1
+        return buffer
 
     # ------------------------------------------------------------------ acting
     def initial_act(self, obs):
@@ -408,7 +488,9 @@ class _OffPolicyAcM:
                 collected += 1
 
     def pre_train(self):
-        self.collect_samples()                                        # acm.py:234-244 (no validation buffer on this path)
+        if self.acm_val_buffer_size:                                  # acm.py:234-244
+            self.acm_val_buffer = self.collect_initial_batch(self.acm_val_buffer, self.acm_val_buffer_size)
+        self.collect_samples()
         self.update_acm(epochs=self.acm_pre_train_epochs, pretrain=True)
         self.update_obs_mean_std(self.replay_buffer)
         if not self.acm_keep_pretrain:

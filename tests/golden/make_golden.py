@@ -15,6 +15,7 @@ Fixtures written next to this file:
   acm_add_buffer.npz     ReplayBufferAcM.add_buffer joint behaviour
   ppo_walker.npz         PPO_AcM pieces on Walker2d shapes: critic fit, GAE, advantage normalisation, actor epochs
   acm_regress.npz        AcMTrainer.batch_update x3 (AcM and BasicAcM)
+  acm_epochs.npz         AcMTrainer.update_acm x3 epochs (shuffle, partial last minibatch, StepLR) + validation loss
 """
 import os
 import sys
@@ -207,6 +208,56 @@ def acm_regress_fixture():
     print("acm_regress: done")
 
 
+def acm_epochs_fixture():
+    """AcMTrainer.update_acm (acm.py:266-303) x3 epochs over a 250-row buffer, batch 64 (partial last minibatch of 58),
+    StepLR(step 1, gamma 0.5) stepped once per epoch, and calculate_validation_loss (acm.py:329-343) on a 90-row set."""
+    ob, ac, n, nval, B = 17, 6, 250, 90, 64
+    torch.manual_seed(0)
+    m = rl.DDPG_AcM(env_name="HalfCheetah-v2", acm_pre_train_samples=n, acm_val_buffer_size=nval, buffer_size=1000,
+                    tensorboard_dir=None, log_dir=None, acm_lr=2e-3, acm_batch_size=B, acm_scheduler_step=1,
+                    acm_scheduler_gamma=0.5, debug_mode=False)
+    s0 = init_state("ddpg", ob, ac, 9, "acm", True)
+    load_nets(m, s0, ["acm"])
+    m.acm = m.acm
+    rng = np.random.RandomState(23)
+
+    def fill(buf, rows, off_policy):
+        chain = rng.randn(rows + 1, ob).astype(np.float32)
+        acts = np.tanh(rng.randn(rows, ac)).astype(np.float32)
+        prev = buf.add_obs(torch.from_numpy(chain[0:1]))
+        for t in range(rows):
+            if off_policy:
+                buf.add_acm_action(acts[t])
+            nxt = buf.add_obs(torch.from_numpy(chain[t + 1:t + 2]))
+            if off_policy:
+                buf.add_timestep(prev, nxt, torch.from_numpy(chain[t + 1:t + 2]), 0.0, False, False)
+            else:
+                buf.add_timestep(prev, nxt, torch.from_numpy(acts[t:t + 1]))
+            prev = nxt
+        return chain, acts
+
+    chain, acts = fill(m.replay_buffer, n, True)
+    vchain, vacts = fill(m.acm_val_buffer, nval, False)
+    perms = [torch.randperm(n, generator=torch.Generator().manual_seed(31 + e)) for e in range(3)]
+    calls = [0]
+    orig = torch.randperm
+
+    def fake(k, *a, **kw):     # RandomSampler calls randperm twice per epoch (the second for an empty remainder)
+        calls[0] += 1
+        return perms[(calls[0] - 1) // 2]
+    torch.randperm = fake
+    losses, vals, lrs = [], [], []
+    for e in range(3):
+        m.update_acm(epochs=1)
+        losses.append(m.loss["acm"]); vals.append(m.loss["acm_val"]); lrs.append(m.acm_optimizer.param_groups[0]["lr"])
+    torch.randperm = orig
+    out = dump_state(m, ["acm"], {"acm": m.acm_optimizer})
+    out.update(chain=chain, acts=acts, vchain=vchain, vacts=vacts, perms=torch.stack(perms).numpy(), losses=np.array(losses),
+               val_losses=np.array(vals), lrs_after=np.array(lrs))
+    np.savez_compressed(os.path.join(HERE, "acm_epochs.npz"), **out)
+    print("acm_epochs: losses", losses, "val", vals, "lr after each epoch", lrs)
+
+
 def ppo_fixture():
     from oracle import ppo as P
     from oracle.norm import NormStats, normalize
@@ -263,4 +314,5 @@ if __name__ == "__main__":
     ddpg_fixture()
     ring_fixture()
     acm_regress_fixture()
+    acm_epochs_fixture()
     ppo_fixture()

@@ -87,3 +87,55 @@ def test_ddpg_acm_with_basic_acm_runs():
     assert set(m.acm.state_dict()) == {"t", "t1", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc21.weight", "fc21.bias", "fc3.weight", "fc3.bias"}
     assert all(np.isfinite(v) for v in m.loss.values())
     m.close()
+
+
+def test_update_acm_epochs_steplr_and_validation_loss_match_reference_fixture():
+    """AcMTrainer.update_acm (acm.py:266-303) x3 epochs -- shuffled pass with the partial last minibatch, StepLR(1, 0.5) stepped per
+    epoch -- and calculate_validation_loss (acm.py:329-343), against the unmodified reference (tests/golden/acm_epochs.npz)."""
+    from spp_rl_b200.init import init_state
+    from tests.parity_util import relnorm
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "acm_epochs.npz"))
+    ob, ac = 17, 6
+    m = DDPG_AcM(env_name="HalfCheetah-v2", acm_pre_train_samples=250, acm_val_buffer_size=90, buffer_size=1000, acm_lr=2e-3,
+                 acm_batch_size=64, acm_scheduler_step=1, acm_scheduler_gamma=0.5, update_batch_size=64)
+    assert m.acm_val_buffer.size == 99 and m.loss["acm_val"] == 0.0
+    s0 = init_state("ddpg", ob, ac, 9, "acm", True)
+    m.acm.load_state_dict({k[4:]: torch.from_numpy(v.copy()) for k, v in s0.items() if k.startswith("acm.")})
+    chain, acts = g["chain"], g["acts"]
+    prev = m.replay_buffer.add_obs(chain[0:1])
+    for t in range(len(acts)):
+        m.replay_buffer.add_acm_action(acts[t])
+        nxt = m.replay_buffer.add_obs(chain[t + 1:t + 2])
+        m.replay_buffer.add_timestep(prev, nxt, torch.from_numpy(chain[t + 1:t + 2]), 0.0, False, False)
+        prev = nxt
+    vchain, vacts = g["vchain"], g["vacts"]
+    prev = m.acm_val_buffer.add_obs(vchain[0])
+    for t in range(len(vacts)):
+        nxt = m.acm_val_buffer.add_obs(vchain[t + 1])
+        m.acm_val_buffer.add_timestep(prev, nxt, vacts[t])
+        prev = nxt
+    assert len(m.acm_val_buffer) == 90 and len(m.replay_buffer) == 250
+    perms = [torch.from_numpy(p) for p in g["perms"]]
+    orig, calls = torch.randperm, [0]
+
+    def fake(n, *a, **k):
+        calls[0] += 1
+        return perms[calls[0] - 1]
+    torch.randperm = fake
+    try:
+        for e in range(3):
+            m.update_acm(epochs=1)
+            assert m.loss["acm"] == pytest.approx(float(g["losses"][e]), rel=1e-5)
+            assert m.loss["acm_val"] == pytest.approx(float(g["val_losses"][e]), rel=1e-5)
+    finally:
+        torch.randperm = orig
+    sd = m._pop.state_dict("acm")
+    ad, step = m._pop.adam_state("acm")
+    assert step == 12                                   # 3 epochs x ceil(250 / 64) minibatches
+    for k, v in sd.items():
+        lim = 1e-4 if v.size <= 16 else 1e-5
+        assert relnorm(v, g["acm." + k]) < lim, (k, relnorm(v, g["acm." + k]))
+        assert relnorm(ad[k][0], g["acm." + k + "#m"]) < lim, k
+        assert relnorm(ad[k][1], g["acm." + k + "#v"]) < lim, k
+    m.close()

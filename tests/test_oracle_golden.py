@@ -132,6 +132,24 @@ def test_acm_regression_matches_reference(kind):
             assert relnorm(s[k[len(kind) + 1:]].numpy(), g[k]) < 5e-6, k
 
 
+def test_acm_epochs_and_validation_loss_match_reference():
+    """update_acm x3 (shuffle, partial last minibatch, StepLR per epoch) + calculate_validation_loss, reference fixture."""
+    g = _load("acm_epochs.npz")
+    ob, ac = 17, 6
+    s = oracle_state(init_state("ddpg", ob, ac, 9, "acm", True), "ddpg")
+    chain, acts = torch.from_numpy(g["chain"]), torch.from_numpy(g["acts"])
+    vchain, vacts = torch.from_numpy(g["vchain"]), torch.from_numpy(g["vacts"])
+    for e in range(3):
+        l = op.acm_update_epochs(s, chain[:-1], chain[1:], acts, [g["perms"][e]], 64, torch.ones(ac), 2e-3, 1, 0.5, epoch0=e)
+        assert l[0] == pytest.approx(float(g["losses"][e]), rel=5e-6)
+        v = op.acm_validation_loss(s, vchain[:-1], vchain[1:], vacts, torch.ones(ac))
+        assert v == pytest.approx(float(g["val_losses"][e]), rel=5e-6)
+    assert list(g["lrs_after"]) == [1e-3, 5e-4, 2.5e-4]
+    for k in g.files:
+        if k.startswith("acm.") and "#" not in k:
+            assert relnorm(s[k].numpy(), g[k]) < 5e-6, k
+
+
 def test_ppo_pieces_match_reference():
     g = _load("ppo_walker.npz")
     hp = g["hp"]
