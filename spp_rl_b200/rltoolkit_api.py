@@ -72,6 +72,15 @@ class NetView:
         return self
 
 
+def sampler_permutation(n):
+    """One epoch of DataLoader(shuffle=True): RandomSampler.__iter__ draws a seed from torch's global generator and
+    permutes with a private generator seeded by it."""
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return torch.randperm(n, generator=g)
+
+
 class ReplayRing:
     """BufferAcMOffPolicy surface (rltoolkit/buffer/replay_buffer.py:303-401) over one agent's device ring."""
 
@@ -361,7 +370,7 @@ class _OffPolicyAcM:
         nb = (n + B - 1) // B
         last = n - (nb - 1) * B
         for _ in range(epochs):
-            perm = torch.randperm(n).numpy().astype(np.int64)        # DataLoader(shuffle=True)
+            perm = sampler_permutation(n).numpy().astype(np.int64)      # DataLoader(shuffle=True)
             idx = np.zeros((1, nb, B), np.int64)
             idx.reshape(-1)[:n] = perm
             lr = self.acm_lr * self.acm_scheduler_gamma ** (self.acm_scheduler_epoch // self.acm_scheduler_step)
@@ -556,3 +565,10 @@ class SAC_AcM(_OffPolicyAcM):
 
 class DDPG_AcM(_OffPolicyAcM):
     ALGO = "ddpg"
+
+
+def __getattr__(name):      # `from spp_rl_b200.rltoolkit_api import PPO_AcM` (the on-policy class lives in rltoolkit_ppo.py)
+    if name == "PPO_AcM":
+        from .rltoolkit_ppo import PPO_AcM
+        return PPO_AcM
+    raise AttributeError(name)

@@ -139,3 +139,110 @@ def test_update_acm_epochs_steplr_and_validation_loss_match_reference_fixture():
         assert relnorm(ad[k][0], g["acm." + k + "#m"]) < lim, k
         assert relnorm(ad[k][1], g["acm." + k + "#v"]) < lim, k
     m.close()
+
+
+PPO_KW = dict(      # rltoolkit/acm/on_policy.py:221-244 (sizes shrunk)
+    env_name="HalfCheetah-v2", gamma=0.99, acm_pre_train_samples=400, acm_pre_train_epochs=2, iterations=2, batch_size=300, stats_freq=5,
+    acm_update_freq=1, acm_epochs=1, acm_lr=1e-4, actor_lr=3e-4, critic_lr=3e-4, kl_div_threshold=0.1, max_ppo_epochs=4,
+    ppo_batch_size=128, acm_batch_size=64, denormalize_actor_out=True, min_max_denormalize=True, custom_loss=0.5, tensorboard_dir=None,
+    obs_norm=True, test_episodes=1, acm_val_buffer_size=200)
+
+
+class _ShortEpisodes:
+    """The synthetic stand-in with 60-step episodes, so that a 300-row batch holds several rollouts (joints, truncations)."""
+
+    def __init__(self):
+        from spp_rl_b200 import envs
+        self.e = envs.make("HalfCheetah-v2", seed=3)
+        self._max_episode_steps = 60
+        self.observation_space, self.action_space = self.e.observation_space, self.e.action_space
+        self.t = 0
+
+    def reset(self):
+        self.t = 0
+        return self.e.reset()
+
+    def step(self, a):
+        o, r, d, i = self.e.step(a)
+        self.t += 1
+        return o, r, bool(d or self.t >= 60), i
+
+    def close(self):
+        pass
+
+
+def test_ppo_acm_script_kwargs_pretrain_train_test_save_load(tmp_path):
+    from spp_rl_b200.rltoolkit_ppo import PPO_AcM
+
+    torch.manual_seed(0); np.random.seed(0)
+    m = PPO_AcM(env=_ShortEpisodes(), **PPO_KW)
+    assert float(m.actor_ac_lim) == 1.0 and m.max_ep_len == 60 and m.buffer_size == 440
+    m.pre_train()
+    assert len(m.replay_buffer) >= 400 and m.min_obs is not None and np.isfinite(m.loss["acm"]) and m.loss["acm_val"] > 0
+    w0 = m.actor.state_dict()["fc1.weight"].clone()
+    c0 = m.critic.state_dict()["fc3.weight"].clone()
+    a0 = m.acm.state_dict()["fc1.weight"].clone()
+    m.train()
+    assert m.iteration == 2 and m.stats_logger.frames >= 600 and len(m.buffer) >= 300
+    assert set(m.loss) >= {"actor", "critic", "acm", "acm_val", "policy", "dist", "entropy"}
+    assert all(np.isfinite(v) for v in m.loss.values()), m.loss
+    assert 2 <= m.kl_div_updates_counter <= 2 * 5
+    assert not torch.equal(w0, m.actor.state_dict()["fc1.weight"]) and not torch.equal(c0, m.critic.state_dict()["fc3.weight"])
+    assert not torch.equal(a0, m.acm.state_dict()["fc1.weight"])
+    # memory views (memory.py:146-170): obs / next_obs skip the joints, one action per row
+    b = m.buffer
+    assert b.obs.shape == b.next_obs.shape == (len(b), 17) and len(b.actions_acm) == len(b)
+    assert torch.equal(b.obs[1], b.next_obs[0]) and b.end[-1]
+    assert np.isfinite(m.test(1))
+    path = os.path.join(tmp_path, "ppo.pkl")
+    m.save(path)
+    d = pickle.load(open(path, "rb"))
+    assert list(d) == ["actor", "critic", "obs_mean", "obs_std", "min_obs", "max_obs", "acm"]
+    assert tuple(d["actor"]["fc3.weight"].shape) == (17, 64) and tuple(d["actor"]["log_scale"].shape) == (17,)
+    m2 = PPO_AcM(env=_ShortEpisodes(), **PPO_KW)
+    m2.load(path)
+    for net in ("actor", "critic", "acm"):
+        a, b2 = getattr(m, net).state_dict(), getattr(m2, net).state_dict()
+        assert list(a) == list(b2) and all(torch.equal(a[k], b2[k]) for k in a)
+    with pytest.raises(NotImplementedError):
+        PPO_AcM(env=_ShortEpisodes(), **dict(PPO_KW, custom_loss=0.0))
+    m.close(); m2.close()
+
+
+def test_ppo_acm_iteration_equals_the_kernel_level_calls():
+    """perform_iteration's update half == PpoPolicy calls on the same rollout (the fixture-pinned path of test_gpu_ppo.py)."""
+    from spp_rl_b200.ppo import PpoPolicy
+    from spp_rl_b200.rltoolkit_ppo import PPO_AcM, RolloutMemory
+
+    torch.manual_seed(4); np.random.seed(4)
+    m = PPO_AcM(env=_ShortEpisodes(), **PPO_KW)
+    m.pre_train()
+    m.buffer = RolloutMemory(m.min_obs, m.max_obs, m.obs_mean, m.obs_std, True)
+    m.collect_batch(m.buffer)
+    b = m.buffer
+    N = len(b)
+    pol = PpoPolicy(17, 6, max_rows=N, max_batch_rows=128, min_max_denormalize=True, norm_closs=True, gamma=0.99, gae_lambda=0.95,
+                    ppo_epsilon=0.2, entropy_coef=0.0, custom_loss=0.5, actor_lr=3e-4, critic_lr=3e-4)
+    pol.set_limits(1.0)
+    pol.set_norm_stats(m.min_obs.numpy(), m.max_obs.numpy(), m.obs_mean.numpy(), m.obs_std.numpy())
+    for net in ("actor", "critic"):
+        pol.load_state_dict(net, getattr(m, net).state_dict())
+    end = np.asarray(b.end, np.float32)
+    stops = np.nonzero(end)[0]; starts = np.concatenate([[0], stops[:-1] + 1])
+    pol.load_rollout(b.obs.numpy(), b.next_obs.numpy(), torch.cat(b.actions).numpy(), torch.cat(b.action_logprobs).numpy(),
+                     np.asarray(b.rewards, np.float32), np.asarray(b.done, np.float32), end, starts, stops + 1 - starts)
+    closs = pol.update_critic(10, 10)
+    pol.advantages(); pol.normalize_adv()
+    state = torch.get_rng_state()
+    from spp_rl_b200.rltoolkit_api import sampler_permutation
+    perms = torch.stack([sampler_permutation(N) for _ in range(4)]).numpy()
+    torch.set_rng_state(state)
+    losses, epochs, _ = pol.update_actor(perms, 128, 0.1, 4)
+    adv = m.update_critic(b)
+    m.update_actor(adv, b)
+    assert m.loss["critic"] == closs and m.loss["policy"] == losses["policy"] and m.kl_div_updates_counter == epochs + 1
+    for net in ("actor", "critic"):
+        sa, sb = getattr(m, net).state_dict(), pol.state_dict(net)
+        assert all(np.array_equal(sa[k].numpy(), sb[k]) for k in sb), net
+    assert sum(e for e in b.end) >= 5 and any(e and not d for e, d in zip(b.end, b.done))      # truncated rollouts bootstrap
+    pol.close(); m.close()
