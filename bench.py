@@ -341,14 +341,16 @@ def main():
         if not args.no_e2e:
             rng = np.random.RandomState(9 + rank)
             mn, mx = np.array(MIN_OBS, np.float32), np.array(MAX_OBS, np.float32)
-            h_o = (rng.rand(P, E, OB) * (mx - mn) + mn).astype(np.float32)
-            h_n = rng.randn(P, E, OB).astype(np.float32)
-            h_e = rng.randn(P, E, OB).astype(np.float32)
-            pop.rollout_step(h_o, h_n, h_e)
+            pin = lambda a: torch.from_numpy(a).pin_memory().numpy()      # noqa: E731  (views of pinned host buffers)
+            h_o = pin((rng.rand(P, E, OB) * (mx - mn) + mn).astype(np.float32))
+            h_n = pin(rng.randn(P, E, OB).astype(np.float32))
+            h_e = pin(rng.randn(P, E, OB).astype(np.float32))
+            h_out = (pin(np.zeros((P, E, OB), np.float32)), pin(np.zeros((P, E, AC), np.float32)))
+            pop.rollout_step(h_o, h_n, h_e, out=h_out)
             barrier()
             t0 = time.perf_counter()
             for k in range(K * 4):
-                tgt, act = pop.rollout_step(h_o, h_n, h_e)
+                tgt, act = pop.rollout_step(h_o, h_n, h_e, out=h_out)
             dt = time.perf_counter() - t0
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             if dist is not None:

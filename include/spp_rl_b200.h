@@ -243,8 +243,11 @@ int spp_umma_selftest(int a_mn, int b_mn, int K, int split, const float* A, cons
  * a_km: A stored [M][K] (1) or [K][M] (0); b_km: B stored [256][K] (1) or [K][256] (0); M <= 256, M and K multiples of 4;
  * reps repeats the product inside the kernel; ms_out (optional) receives the kernel time.  Host arrays. */
 int spp_umma_gemm_selftest(int a_km, int b_km, int M, int K, int reps, const float* A, const float* B, float* C, float* ms_out);
-/* process-wide A/B switch for the 128 x 128 GEMMs of the update burst: 1 = tcgen05 (3-pass tf32 split, default),
- * 0 = FFMA tiles.  Both are device paths. */
+/* process-wide switch for the 256-wide GEMMs of the fused kernels; all three are device paths:
+ *   1 = tcgen05, 3-pass tf32 hi/lo split with per-chunk fp32 drain -- fp32-accurate, the default and the one every parity claim is made on;
+ *   0 = FFMA tiles (A/B reference for the tensor-core path);
+ *   2 = tcgen05, ONE tf32 pass, the whole K accumulated in TMEM -- the reduced-precision variant (stated tolerance 1e-2 relative on
+ *       losses and post-step weights, tests/test_gpu_update_parity.py); never used unless selected here or by SPP_UMMA=2. */
 int spp_set_gemm_path(int tensor_cores);
 int spp_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, char* name, int name_cap);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */

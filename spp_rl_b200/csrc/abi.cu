@@ -645,7 +645,7 @@ int spp_ring_gather_bench_device(spp_population* p, int n_batches, uint64_t seed
 // ---- update ----------------------------------------------------------------------------------------
 // 1: the 128 x 128 GEMMs of the update burst run on tcgen05 (3-pass tf32 split); 0: FFMA tiles.  Both are device paths;
 // the switch exists for A/B measurement and kernel bisection (environment SPP_UMMA=0 or spp_set_gemm_path).
-static std::atomic<int> g_gemm_path{[] { const char* e = getenv("SPP_UMMA"); return (e && e[0] == '0') ? 0 : 1; }()};
+static std::atomic<int> g_gemm_path{[] { const char* e = getenv("SPP_UMMA"); return (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1); }()};
 
 static void fill_args(spp_population* p, UpdateArgs& a, int G) {
     memset(&a, 0, sizeof(a));
@@ -917,7 +917,8 @@ int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t s
 
 // ---- introspection ---------------------------------------------------------------------------------
 int spp_set_gemm_path(int tensor_cores) {
-    g_gemm_path.store(tensor_cores ? 1 : 0);
+    if (tensor_cores < 0 || tensor_cores > 2) return fail(SPP_ERR_ARG, "gemm path must be 0 (FFMA), 1 (tcgen05, 3-pass tf32) or 2 (tcgen05, single tf32 pass)");
+    g_gemm_path.store(tensor_cores);
     return SPP_OK;
 }
 

@@ -31,6 +31,7 @@
 namespace spp {
 
 constexpr int kUmmaAPlane = 128 * 128;                     // A_hi / A_lo: 128 rows x 32 tf32
+constexpr uint32_t kUmmaSinglePass = 8;   // UmmaCtx::dbg bit: reduced-precision variant (one tf32 pass, whole K in one TMEM accumulator)
 constexpr int kUmmaBPlane = 256 * 128;                     // B_hi / B_lo: 256 columns x 32 tf32
 constexpr int kUmmaSlotBytes = 2 * kUmmaAPlane + 2 * kUmmaBPlane;      // 96 KB
 constexpr int kUmmaSlots = 2;
@@ -220,6 +221,7 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
     const uint32_t idesc = make_idesc_tf32(128, N, A_KM ? 0 : 1, B_KM ? 0 : 1);
     const int wq = warp_id() & 3, chalf = warp_id() >> 2;
     const uint32_t my_tmem = tmem + ((uint32_t)(32 * wq) << 16) + chalf * 128;      // this thread's lane / column half
+    const bool fast = (dbg & kUmmaSinglePass) != 0;
     uint32_t phase_bits = phase_in;      // everything by value: a by-reference argument would pin the caller's state in local memory
     UmmaOperand<B_KM, 256> lb;
     lb.init(B, ldb, N, 0);
@@ -234,7 +236,7 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
         const int slot = c & 1;
         const uint32_t ah = smem0 + slot * kUmmaSlotBytes, al = ah + kUmmaAPlane, bh = al + kUmmaAPlane, bl = bh + kUmmaBPlane;
         cp_async_wait<0>();       // this thread's copies of chunk c have landed
-        if (!(dbg & 2)) {
+        if (!(dbg & (2 | kUmmaSinglePass))) {
             la.split(ah, al);
             lb.split(bh, bl);
         }
@@ -243,8 +245,15 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
         __syncthreads();
         if (threadIdx.x == 0) {
             fence_after_sync();
-            const uint32_t d = tmem + slot * N;
+            const uint32_t d = tmem + (fast ? 0 : slot * N);
             const int nks = (dbg & 1) ? 0 : min(4, (K - 32 * c + 7) / 8);
+            if (fast) {     // reduced-precision variant: the raw fp32 words are the tf32 operands, the whole K accumulates in TMEM
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t dah = A_KM ? kmajor_desc(ah, ks) : mnmajor_desc(ah, ks);
+                    const uint64_t dbh = B_KM ? kmajor_desc(bh, ks) : mnmajor_desc(bh, ks);
+                    mma_tf32(d, dah, dbh, idesc, (c | ks) ? 1u : 0u);
+                }
+            } else {
             for (int ks = 0; ks < nks; ++ks) {      // cross terms first: the accumulator is still tiny
                 const uint64_t dah = A_KM ? kmajor_desc(ah, ks) : mnmajor_desc(ah, ks);
                 const uint64_t dal = A_KM ? kmajor_desc(al, ks) : mnmajor_desc(al, ks);
@@ -257,6 +266,7 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
                 const uint64_t dah = A_KM ? kmajor_desc(ah, ks) : mnmajor_desc(ah, ks);
                 const uint64_t dbh = B_KM ? kmajor_desc(bh, ks) : mnmajor_desc(bh, ks);
                 mma_tf32(d, dah, dbh, idesc, 1u);
+            }
             }
             commit(mbar + slot);
         }
@@ -272,7 +282,7 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
             lb.issue(32 * (c + 1), K, nh + 2 * kUmmaAPlane);
         }
         cp_async_commit();
-        if (c >= 1) {       // drain chunk c - 1 while the tensor core works on chunk c
+        if (c >= 1 && !fast) {       // drain chunk c - 1 while the tensor core works on chunk c
             if (c == 1) umma_drain<true>(my_tmem + ps * N, sum);
             else umma_drain<false>(my_tmem + ps * N, sum);
         }
@@ -282,7 +292,7 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
         mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
         phase_bits ^= (1u << ps);
         fence_after_sync();
-        if (nchunks == 1) umma_drain<true>(my_tmem + ps * N, sum);
+        if (nchunks == 1 || fast) umma_drain<true>(my_tmem + (fast ? 0 : ps * N), sum);
         else umma_drain<false>(my_tmem + ps * N, sum);
         fence_before_sync();
     }
@@ -295,6 +305,7 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
     __syncthreads();
     return phase_bits;
 }
+
 
 // The wrapper is a real call in the update kernel: the main loop and the epilogues get their register budget from the live set
 // of their caller (ptxas allocates across the call graph), and inlined into the 35 k-instruction kernel body that live set cost the

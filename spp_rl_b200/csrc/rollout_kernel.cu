@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = smem_struct(smem_raw);
     const UpdateArgs& a = r.u;
-    UmmaCtx* um = a.use_umma ? umma_setup(sm) : nullptr;
+    UmmaCtx* um = a.use_umma ? umma_setup(sm, a.use_umma) : nullptr;
     for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
         Ctx c(a, agent, sm, um);
         const Layout& L = a.L;

@@ -278,7 +278,7 @@ template <int ALGO>
 __global__ void __launch_bounds__(kThreads, 1) update_burst_kernel(const __grid_constant__ UpdateArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = smem_struct(smem_raw);
-    UmmaCtx* um = a.use_umma ? umma_setup(sm) : nullptr;
+    UmmaCtx* um = a.use_umma ? umma_setup(sm, a.use_umma) : nullptr;
     for (int agent = blockIdx.x; agent < a.population; agent += gridDim.x) {
         Ctx c(a, agent, sm, um);
         for (int g = 0; g < a.G; ++g) update_step<ALGO>(c, g);

@@ -69,7 +69,8 @@ struct UpdateArgs {
     int batch_row_stride;    // rows between consecutive steps in the staged batch / index arrays (0 = L.B)
     int acm_last_rows;       // ACM regression: rows of the final step when it is a partial batch (0 = full)
     int acm_eval;            // ACM regression: forward + loss only (calculate_validation_loss), no optimiser step
-    int use_umma;            // 1: the 128 x 128 tile GEMMs run on tcgen05 (3-pass tf32 split); 0: FFMA tiles (A/B switch)
+    int use_umma;            // GEMM path of the 256-wide products: 1 tcgen05 3-pass tf32 split (fp32-accurate, default), 0 FFMA tiles,
+                             // 2 tcgen05 single tf32 pass (reduced-precision variant, stated tolerance 1e-2)
 };
 
 enum { LOSS_CRITIC_1 = 0, LOSS_CRITIC_2 = 1, LOSS_ACTOR = 2, LOSS_PI = 3, LOSS_DIST = 4, LOSS_ALPHA = 5, LOSS_ALPHA_VALUE = 6, LOSS_COUNT = 8 };
@@ -119,7 +120,7 @@ struct Ctx {
 };
 
 // ---- tcgen05 state of a persistent CTA: TMEM accumulators (all 512 columns) and the slot barriers live for the whole launch
-__device__ __forceinline__ UmmaCtx* umma_setup(Smem& sm) {
+__device__ __forceinline__ UmmaCtx* umma_setup(Smem& sm, int path) {
     if (warp_id() == 0) umma::tmem_alloc<kUmmaTmemCols>(&sm.tmem_base);
     if (threadIdx.x == 0) {
         for (int s = 0; s < kUmmaSlots; ++s) umma::mbar_init(sm.mbar + s, 1);
@@ -133,7 +134,7 @@ __device__ __forceinline__ UmmaCtx* umma_setup(Smem& sm) {
         sm.um.mbar = sm.mbar;
         sm.um.tmem = sm.tmem_base;
         sm.um.phase_bits = 0;
-        sm.um.dbg = 0;
+        sm.um.dbg = (path == 2) ? kUmmaSinglePass : 0u;
     }
     __syncthreads();
     return &sm.um;

@@ -252,14 +252,22 @@ class Population:
         return losses
 
     # ------------------------------------------------------------------ rollout
-    def rollout_step(self, obs, noise, eps=None, random_phase=False, act_noise=0.1, obs_norm=False, denormalize_actor_out=True):
+    def rollout_step(self, obs, noise, eps=None, random_phase=False, act_noise=0.1, obs_norm=False, denormalize_actor_out=True,
+                     out=None):
         """noise_action / initial_act + process_action for E observations per agent: obs, noise, eps [P, E, ob]
-        -> (state_target [P, E, ob], acm_action [P, E, ac])."""
+        -> (state_target [P, E, ob], acm_action [P, E, ac]).  `out` = (target, action) float32 arrays to fill (e.g. views of
+        pinned buffers, so that the device-to-host copies are true asynchronous DMA)."""
         obs = _f32(obs); noise = _f32(noise)
         E = obs.shape[1]
         eps = None if eps is None else _f32(eps)
-        tgt = np.empty((self.P, E, self.ob_dim), np.float32)
-        act = np.empty((self.P, E, self.ac_dim), np.float32)
+        if out is None:
+            tgt = np.empty((self.P, E, self.ob_dim), np.float32)
+            act = np.empty((self.P, E, self.ac_dim), np.float32)
+        else:
+            tgt, act = out
+            if tgt.shape != (self.P, E, self.ob_dim) or act.shape != (self.P, E, self.ac_dim) or tgt.dtype != np.float32 \
+                    or act.dtype != np.float32 or not (tgt.flags.c_contiguous and act.flags.c_contiguous):
+                raise ValueError("out = (target [P, E, ob], action [P, E, ac]) contiguous float32 arrays")
         check(self.lib.spp_rollout_step_host(self.h, int(E), _ptr(obs, C.c_float), _ptr(noise, C.c_float), _ptr(eps, C.c_float),
                                              int(random_phase), float(act_noise), int(bool(obs_norm)),
                                              int(bool(denormalize_actor_out)), _ptr(tgt, C.c_float), _ptr(act, C.c_float)))

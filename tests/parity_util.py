@@ -51,7 +51,7 @@ def upload_state(pop, np_state, agent, algo):
         pop.load_state_dict(net, sd, agent=agent)
 
 
-def compare_states(pop, ostate, agent, algo, verbose=False, tag=""):
+def compare_states(pop, ostate, agent, algo, verbose=False, tag="", moment_weight=1.0):
     """worst norm-relative error over all tensors and Adam moments of one agent"""
     nets = ["actor", "critic_1", "critic_2", "critic_1_targ", "critic_2_targ", "acm"] if algo == "sac" else \
         ["actor", "actor_targ", "critic", "critic_targ", "acm"]
@@ -73,7 +73,7 @@ def compare_states(pop, ostate, agent, algo, verbose=False, tag=""):
                     em, ev = relnorm(m, ostate[key + "#m"].numpy()), relnorm(v, ostate[key + "#v"].numpy())
                     if m.size <= 16:
                         em, ev = em * 0.1, ev * 0.1
-                    worst = max(worst, em, ev)
+                    worst = max(worst, em * moment_weight, ev * moment_weight)
                     if verbose and max(em, ev) > 1e-6:
                         print("  %s agent %d %s moments relnorm m %.3e v %.3e" % (tag, agent, key, em, ev))
             assert step == ostate[net + "#step"], (net, step, ostate[net + "#step"])
@@ -82,7 +82,7 @@ def compare_states(pop, ostate, agent, algo, verbose=False, tag=""):
 
 def run_offpolicy_parity_case(algo="sac", ob=11, ac=3, batch=64, population=2, steps=2, seed=0, custom_loss=0.2,
                               norm_closs=False, acm_critic=True, min_max=True, acm_kind="acm", verbose=False,
-                              gamma=0.99, lr=1e-3, small_std=False, actor_lim=1.0, acm_lim=1.0):
+                              gamma=0.99, lr=1e-3, small_std=False, actor_lim=1.0, acm_lim=1.0, alpha_tol=1e-6, moment_weight=1.0):
     P, G, B = population, steps, batch
     mn, mx, mean, std = make_stats(ob, seed, min_max)
     obs, nobs, act, rew, done, aacm, eps = make_batches(ob, ac, P, G, B, seed, mn, mx)
@@ -121,7 +121,7 @@ def run_offpolicy_parity_case(algo="sac", ob=11, ac=3, batch=64, population=2, s
                 if custom_loss:
                     pairs += [("sac", 3), ("dist", 4)]
                 pairs += [("alpha", 5)]
-                if abs(losses[a, g, 6] - alpha) > 1e-6 * abs(alpha):
+                if abs(losses[a, g, 6] - alpha) > alpha_tol * abs(alpha):
                     raise AssertionError("alpha mismatch %r vs %r" % (losses[a, g, 6], alpha))
             else:
                 ol = op.ddpg_acm_update(s, hp, st, t(obs), t(nobs), t(act), t(rew), t(done), t(aacm))
@@ -133,7 +133,7 @@ def run_offpolicy_parity_case(algo="sac", ob=11, ac=3, batch=64, population=2, s
                 if verbose and e > 1e-5:
                     print("  loss %s agent %d step %d: cuda %.8g oracle %.8g" % (name, a, g, losses[a, g, slot], ol[name]))
                 worst = max(worst, min(e, 1.0) if e > 1e-5 else 0.0)
-        worst = max(worst, compare_states(pop, s, a, algo, verbose=verbose, tag=algo))
+        worst = max(worst, compare_states(pop, s, a, algo, verbose=verbose, tag=algo, moment_weight=moment_weight))
         if algo == "sac":
             la, _ = pop.alpha(a)
             e = abs(la - float(s["log_alpha"])) / abs(float(s["log_alpha"]))
