@@ -219,6 +219,9 @@ int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats);
 int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int batch_size, double kl_threshold, float losses[4],
                          int* epochs_run, float* last_kl);
 int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int64_t n_global);
+/* the same with the local row ids already on the DEVICE (produced on spp_ppo_stream()'s stream, e.g. by filtering the global
+ * minibatch there): no host copy, no host-side range check -- the ids must lie in [0, local rows). */
+int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int64_t n, int64_t n_global);
 int spp_ppo_actor_apply(spp_ppo* p);
 int spp_ppo_scalars(spp_ppo* p, float out[8]);
 /* Rollout step of A2C.collect_batch (rltoolkit/algorithms/a2c/a2c.py:165-167) for E observations at once:

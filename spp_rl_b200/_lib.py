@@ -107,6 +107,7 @@ SIGNATURES = {
     "spp_ppo_normalize_adv": (C.c_int, [_vp, _f64p]),
     "spp_ppo_update_actor": (C.c_int, [_vp, _i64p, C.c_int, C.c_int, C.c_double, _f32p, _i32p, _f32p]),
     "spp_ppo_actor_minibatch_grad": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64]),
+    "spp_ppo_actor_minibatch_grad_device": (C.c_int, [_vp, C.c_void_p, C.c_int64, C.c_int64]),
     "spp_ppo_actor_apply": (C.c_int, [_vp]),
     "spp_ppo_scalars": (C.c_int, [_vp, _f32p]),
     "spp_ppo_act": (C.c_int, [_vp, C.c_int64, _f32p, _f32p, C.c_int, _f32p, _f32p, _f32p]),

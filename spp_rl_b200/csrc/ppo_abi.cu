@@ -86,7 +86,7 @@ int spp_ppo_create(const spp_ppo_config* cfg, int device, spp_ppo** out) {
     PCK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return spp_set_error_(SPP_ERR_UNSUPPORTED, "spp_rl_b200 is built for sm_100a (B200) only");
     spp_ppo* p = new spp_ppo();
-    p->cfg = *cfg; p->device = device; p->sm_count = prop.multiProcessorCount; p->grid = prop.multiProcessorCount;
+    p->cfg = *cfg; p->device = device; p->sm_count = prop.multiProcessorCount; p->grid = 2 * prop.multiProcessorCount;      // two resident CTAs per SM (kPpoCtasPerSm)
     p->L = make_ppo_layout(cfg->ob_dim, cfg->ac_dim);
     p->h.gamma = (float)cfg->gamma; p->h.discount = (float)(cfg->gae_lambda * cfg->gamma); p->h.discount_d = cfg->gae_lambda * cfg->gamma;
     p->h.epsilon = (float)cfg->ppo_epsilon; p->h.entropy_coef = (float)cfg->entropy_coef; p->h.custom_loss = (float)cfg->custom_loss;
@@ -349,6 +349,20 @@ int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int
     PCK(cudaMemcpyAsync(p->dperm, perm, (size_t)n * 8, cudaMemcpyHostToDevice, p->stream));
     p->b.n = n;
     p->b.n_mean = n_global > 0 ? n_global : n;      // the clipped loss is a mean over the GLOBAL minibatch in data-parallel runs
+    PpoArgs a; fill(p, a, n);
+    PCK(launch_ppo_gather(a, p->dperm, p->cfg.norm_closs ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
+    PCK(launch_ppo_reduce(a, p->grid, p->L.actor.size, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
+int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int64_t n, int64_t n_global) {
+    if (!p || !perm_dev) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (n < 1 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [1, max_batch_rows]");
+    PCK(cudaSetDevice(p->device));
+    PCK(cudaMemcpyAsync(p->dperm, perm_dev, (size_t)n * 8, cudaMemcpyDeviceToDevice, p->stream));
+    p->b.n = n;
+    p->b.n_mean = n_global > 0 ? n_global : n;
     PpoArgs a; fill(p, a, n);
     PCK(launch_ppo_gather(a, p->dperm, p->cfg.norm_closs ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();

@@ -88,7 +88,7 @@ struct EpiCriticHead {
 
 // plain store of a dW tile into the CTA's partial-gradient arena (natural [rows x ld] layout)
 struct EpiStorePartial {
-    float* G; int ld;
+    float* G; int ld; bool accumulate;      // accumulate: add to what an earlier row block of this CTA left there (fixed order)
     template <class Cfg, bool A_KC>
     __device__ __forceinline__ void apply(float (&acc)[Cfg::MI][Cfg::NJ], int m0, int n0, int M, int N, float*) {
         const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
@@ -99,12 +99,24 @@ struct EpiStorePartial {
 #pragma unroll
             for (int g = 0; g < Cfg::NJ / 4; ++g) {
                 const int n = n0 + col_of<Cfg>(4 * g, tx);
-                if (n < N) st4(G + (size_t)m * ld + n, make_float4(acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]));
+                if (n >= N) continue;
+                float4 v = make_float4(acc[i][4 * g], acc[i][4 * g + 1], acc[i][4 * g + 2], acc[i][4 * g + 3]);
+                if (accumulate) {
+                    const float4 o = ld4(G + (size_t)m * ld + n);
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                st4(G + (size_t)m * ld + n, v);
             }
         }
     }
 };
 
+// Rows a CTA pushes through the whole layer chain before it moves on: the [rows x 64] intermediates (h1, dz2, dz1) of one block
+// are 128 KB each and are re-used block after block, so they live in L2 (148 CTAs x 384 KB) instead of streaming through HBM --
+// at config-4 sizes (56 k rows per CTA) the chain used to write and re-read ~10 GB per optimiser step.
+constexpr int kPpoRowBlock = 512;
+
+constexpr int kPpoCtasPerSm = 2;      // 8 warps per SM leave the FMA pipe 42 % busy (ncu): two CTAs (2 x 102 KB, <= 128 registers) share an SM
 struct Chunk { int64_t r0; int rows; };
 __device__ __forceinline__ Chunk my_chunk(int64_t n, int rows_per_cta) {
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -117,21 +129,24 @@ __device__ __forceinline__ Chunk my_chunk(int64_t n, int rows_per_cta) {
 // ------------------------------------------------------------------------------------------------ critic
 // mode 0: V(x) -> v, V(xn) -> nv, q = r + gamma (1 - done) nv        (calculate_q_val + the state values GAE needs)
 // mode 1: q only (the target pass at the top of each of A2C.update_critic's outer iterations)
-__global__ void __launch_bounds__(kThreads, 1) ppo_critic_values_kernel(const __grid_constant__ PpoArgs a) {
+__global__ void __launch_bounds__(kThreads, kPpoCtasPerSm) ppo_critic_values_kernel(const __grid_constant__ PpoArgs a) {
     extern __shared__ __align__(16) float smem[];
     const Chunk ck = my_chunk(a.d.N, a.rows_per_cta);
     if (ck.rows == 0) return;
     const LayerDesc& l0 = a.L.critic.L[0]; const LayerDesc& l1 = a.L.critic.L[1]; const LayerDesc& l2 = a.L.critic.L[2];
-    float* h1 = a.s.h1 + ck.r0 * kPpoHidden;
+    float* h1 = a.s.h1 + ck.r0 * kPpoHidden;      // the first kPpoRowBlock rows of the CTA's own region, re-used by every block
     for (int pass = (a.mode == 1 ? 1 : 0); pass < 2; ++pass) {
-        const float* X = (pass == 0 ? a.d.x : a.d.xn) + ck.r0 * a.L.ldo;
-        EpiBiasAct<ACT_TANH, false, false> e1{h1, kPpoHidden, a.critic + l0.off_b, nullptr, nullptr, 0, nullptr, 0, 0.f};
-        gemm<MidTile, true>(X, a.L.ldo, a.critic + l0.off_wt, l0.ld_t, ck.rows, kPpoHidden, a.L.ldo, smem, e1);
-        __syncthreads();
-        EpiCriticHead e2{a.critic + l1.off_b, a.critic + l2.off_w, a.critic[l2.off_b], nullptr, (pass == 0 ? a.d.v : a.d.nv) + ck.r0,
-                         nullptr, 0.f, nullptr, nullptr, nullptr, nullptr};
-        gemm<MidTile, true>(h1, kPpoHidden, a.critic + l1.off_wt, l1.ld_t, ck.rows, kPpoHidden, kPpoHidden, smem, e2);
-        __syncthreads();
+        for (int b0 = 0; b0 < ck.rows; b0 += kPpoRowBlock) {
+            const int rows = min(kPpoRowBlock, ck.rows - b0);
+            const float* X = (pass == 0 ? a.d.x : a.d.xn) + (ck.r0 + b0) * a.L.ldo;
+            EpiBiasAct<ACT_TANH, false, false> e1{h1, kPpoHidden, a.critic + l0.off_b, nullptr, nullptr, 0, nullptr, 0, 0.f};
+            gemm<MidTile, true>(X, a.L.ldo, a.critic + l0.off_wt, l0.ld_t, rows, kPpoHidden, a.L.ldo, smem, e1);
+            __syncthreads();
+            EpiCriticHead e2{a.critic + l1.off_b, a.critic + l2.off_w, a.critic[l2.off_b], nullptr, (pass == 0 ? a.d.v : a.d.nv) + ck.r0 + b0,
+                             nullptr, 0.f, nullptr, nullptr, nullptr, nullptr};
+            gemm<MidTile, true>(h1, kPpoHidden, a.critic + l1.off_wt, l1.ld_t, rows, kPpoHidden, kPpoHidden, smem, e2);
+            __syncthreads();
+        }
     }
     for (int i = threadIdx.x; i < ck.rows; i += kThreads) {
         const int64_t r = ck.r0 + i;
@@ -139,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_values_kernel(const __
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_kernel(const __grid_constant__ PpoArgs a) {
+__global__ void __launch_bounds__(kThreads, kPpoCtasPerSm) ppo_critic_grad_kernel(const __grid_constant__ PpoArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* part = a.part + (size_t)blockIdx.x * a.part_stride;
     float* scal = a.scal + (size_t)blockIdx.x * PS_COUNT;
@@ -149,27 +164,31 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_kernel(const __gr
     const Chunk ck = my_chunk(a.d.N, a.rows_per_cta);
     if (ck.rows == 0) return;
     const LayerDesc& l0 = a.L.critic.L[0]; const LayerDesc& l1 = a.L.critic.L[1]; const LayerDesc& l2 = a.L.critic.L[2];
-    const float* X = a.d.x + ck.r0 * a.L.ldo;
     float* h1 = a.s.h1 + ck.r0 * kPpoHidden; float* dz2 = a.s.dz2 + ck.r0 * kPpoHidden; float* dz1 = a.s.dz1 + ck.r0 * kPpoHidden;
-    EpiBiasAct<ACT_TANH, false, false> e1{h1, kPpoHidden, a.critic + l0.off_b, nullptr, nullptr, 0, nullptr, 0, 0.f};
-    gemm<MidTile, true>(X, a.L.ldo, a.critic + l0.off_wt, l0.ld_t, ck.rows, kPpoHidden, a.L.ldo, smem, e1);
-    __syncthreads();
-    EpiCriticHead e2{a.critic + l1.off_b, a.critic + l2.off_w, a.critic[l2.off_b], a.d.q + ck.r0, nullptr, dz2, 1.0f / (float)a.d.Ntot,
-                     part + l2.off_w, part + l2.off_b, part + l1.off_b, scal + PS_LOSS};
-    gemm<MidTile, true>(h1, kPpoHidden, a.critic + l1.off_wt, l1.ld_t, ck.rows, kPpoHidden, kPpoHidden, smem, e2);
-    __syncthreads();
-    EpiMaskStore<MASK_TANH, true, false> e3{dz1, kPpoHidden, h1, kPpoHidden, part + l0.off_b};
-    gemm<MidTile, true>(dz2, kPpoHidden, a.critic + l1.off_w, l1.ld, ck.rows, kPpoHidden, kPpoHidden, smem, e3);
-    __syncthreads();
-    EpiStorePartial g2{part + l1.off_w, l1.ld};
-    gemm<SmallTile, false>(dz2, kPpoHidden, h1, kPpoHidden, kPpoHidden, kPpoHidden, ck.rows, smem, g2);
-    EpiStorePartial g1{part + l0.off_w, l0.ld};
-    gemm<SmallTile, false>(dz1, kPpoHidden, X, a.L.ldo, kPpoHidden, a.L.ldo, ck.rows, smem, g1);
+    for (int b0 = 0; b0 < ck.rows; b0 += kPpoRowBlock) {      // the scratch of the CTA's first block is re-used by every block
+        const int rows = min(kPpoRowBlock, ck.rows - b0);
+        const float* X = a.d.x + (ck.r0 + b0) * a.L.ldo;
+        EpiBiasAct<ACT_TANH, false, false> e1{h1, kPpoHidden, a.critic + l0.off_b, nullptr, nullptr, 0, nullptr, 0, 0.f};
+        gemm<MidTile, true>(X, a.L.ldo, a.critic + l0.off_wt, l0.ld_t, rows, kPpoHidden, a.L.ldo, smem, e1);
+        __syncthreads();
+        EpiCriticHead e2{a.critic + l1.off_b, a.critic + l2.off_w, a.critic[l2.off_b], a.d.q + ck.r0 + b0, nullptr, dz2, 1.0f / (float)a.d.Ntot,
+                         part + l2.off_w, part + l2.off_b, part + l1.off_b, scal + PS_LOSS};
+        gemm<MidTile, true>(h1, kPpoHidden, a.critic + l1.off_wt, l1.ld_t, rows, kPpoHidden, kPpoHidden, smem, e2);
+        __syncthreads();
+        EpiMaskStore<MASK_TANH, true, false> e3{dz1, kPpoHidden, h1, kPpoHidden, part + l0.off_b};
+        gemm<MidTile, true>(dz2, kPpoHidden, a.critic + l1.off_w, l1.ld, rows, kPpoHidden, kPpoHidden, smem, e3);
+        __syncthreads();
+        EpiStorePartial g2{part + l1.off_w, l1.ld, b0 > 0};
+        gemm<SmallTile, false>(dz2, kPpoHidden, h1, kPpoHidden, kPpoHidden, kPpoHidden, rows, smem, g2);
+        EpiStorePartial g1{part + l0.off_w, l0.ld, b0 > 0};
+        gemm<SmallTile, false>(dz1, kPpoHidden, X, a.L.ldo, kPpoHidden, a.L.ldo, rows, smem, g1);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ actor
 // One minibatch (rows already gathered into a.b): clipped-ratio loss, entropy bonus, partial gradients, KL sum.
-__global__ void __launch_bounds__(kThreads, 1) ppo_actor_grad_kernel(const __grid_constant__ PpoArgs a) {
+__global__ void __launch_bounds__(kThreads, kPpoCtasPerSm) ppo_actor_grad_kernel(const __grid_constant__ PpoArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* part = a.part + (size_t)blockIdx.x * a.part_stride;
     float* scal = a.scal + (size_t)blockIdx.x * PS_COUNT;

@@ -159,28 +159,56 @@ class PpoPolicy:
         check(self.lib.spp_ppo_scalars(self.h, out))
         return np.array(list(out), np.float32)
 
-    def update_critic_dp(self, dist, n_target_updates=10, n_updates_per_target=10):
-        """update_critic with one NCCL all-reduce of the gradient vector per optimiser step."""
-        g, sc = self.grad_tensor()
-        tot, ntot = 0.0, None
-        for _ in range(n_target_updates):
-            check(self.lib.spp_ppo_critic_targets(self.h))
-            for _ in range(n_updates_per_target):
-                check(self.lib.spp_ppo_critic_grad(self.h))
-                self.sync()
-                dist.all_reduce(g)
-                dist.all_reduce(sc)
-                tot += float(sc[0].item())
-                check(self.lib.spp_ppo_critic_apply(self.h))
-        return tot
+    def _ext_stream(self):
+        """The library's stream as a torch stream: collectives issued under it are ordered between the kernels by the stream
+        itself, so the data-parallel loops need no host synchronisation per optimiser step."""
+        if getattr(self, "_torch_stream", None) is None:
+            import torch
 
-    def actor_minibatch_dp(self, dist, perm_local, n_global):
+            ptr = C.c_void_p()
+            check(self.lib.spp_ppo_stream(self.h, C.byref(ptr)))
+            self._torch_stream = torch.cuda.ExternalStream(ptr.value) if ptr.value else torch.cuda.default_stream()
+        return self._torch_stream
+
+    def update_critic_dp(self, dist, n_target_updates=10, n_updates_per_target=10):
+        """update_critic with one NCCL all-reduce of the gradient vector per optimiser step; everything is
+        enqueued on the library's stream (grad kernel -> all-reduce -> Adam kernel), the loss sum is read once at the end."""
+        import torch
+
         g, sc = self.grad_tensor()
-        p = np.ascontiguousarray(perm_local, np.int64)
-        check(self.lib.spp_ppo_actor_minibatch_grad(self.h, _ptr(p, C.c_int64), int(p.size), int(n_global)))
-        self.sync()
-        dist.all_reduce(g)
-        dist.all_reduce(sc)
-        out = sc.cpu().numpy()          # also orders the all-reduces (torch's stream) before the apply (the library's stream)
-        check(self.lib.spp_ppo_actor_apply(self.h))
+        st = self._ext_stream()
+        with torch.cuda.stream(st):
+            tot = torch.zeros((), dtype=torch.float64, device=g.device)
+            for _ in range(n_target_updates):
+                check(self.lib.spp_ppo_critic_targets(self.h))
+                for _ in range(n_updates_per_target):
+                    check(self.lib.spp_ppo_critic_grad(self.h))
+                    dist.all_reduce(g)
+                    dist.all_reduce(sc)
+                    tot += sc[0].double()
+                    check(self.lib.spp_ppo_critic_apply(self.h))
+        st.synchronize()
+        return float(tot.item())
+
+    def actor_minibatch_dp(self, dist, perm_local, n_global, want_host=True):
+        """One data-parallel actor minibatch; returns the 8 reduced scalars (host array, or a device tensor without any host
+        synchronisation when want_host is False -- the caller then reads them once per epoch for the KL test)."""
+        import torch
+
+        g, sc = self.grad_tensor()
+        st = self._ext_stream()
+        with torch.cuda.stream(st):
+            if torch.is_tensor(perm_local):      # local row ids already on the device (filtered there, under this stream)
+                p = perm_local.contiguous()
+                check(self.lib.spp_ppo_actor_minibatch_grad_device(self.h, C.c_void_p(p.data_ptr()), int(p.numel()), int(n_global)))
+            else:
+                p = np.ascontiguousarray(perm_local, np.int64)
+                check(self.lib.spp_ppo_actor_minibatch_grad(self.h, _ptr(p, C.c_int64), int(p.size), int(n_global)))
+            dist.all_reduce(g)
+            dist.all_reduce(sc)
+            out = sc.clone()
+            check(self.lib.spp_ppo_actor_apply(self.h))
+        if want_host:
+            st.synchronize()
+            return out.cpu().numpy()
         return out

@@ -63,6 +63,30 @@ def local_minibatch(global_idx, E: int, rank: int, world: int):
     return ((idx[mine] // E) * El + e[mine] % El).astype(np.int64)
 
 
+def local_minibatch_device(global_idx, E: int, rank: int, world: int):
+    """local_minibatch for a torch int64 tensor on the device (same result, same order); the boolean selection synchronises
+    once to learn the count, which the caller needs on the host anyway."""
+    El = E // world
+    e = global_idx % E
+    mine = torch.div(e, El, rounding_mode="floor") == rank
+    return (torch.div(global_idx, E, rounding_mode="floor") * El + e % El)[mine]
+
+
+def epoch_local_minibatches_device(perm, batch: int, E: int, rank: int, world: int):
+    """One epoch at once: `perm` (torch int64, the epoch's global permutation) -> (local row ids of every row this rank owns, in
+    permutation order, and the host list of offsets such that minibatch k is ids[off[k]:off[k + 1]]).  A handful of device ops
+    and ONE host read per epoch instead of a filter + synchronisation per minibatch."""
+    El = E // world
+    e = perm % E
+    mine = torch.div(e, El, rounding_mode="floor") == rank
+    ids = (torch.div(perm, E, rounding_mode="floor") * El + e % El)[mine]
+    csum = torch.cumsum(mine.to(torch.int64), 0)
+    n = perm.numel()
+    ends = torch.arange(batch, n + batch, batch, device=perm.device).clamp_(max=n) - 1
+    off = [0] + csum[ends].tolist()
+    return ids, off
+
+
 def allreduce_adv_stats(local_stats, dist=None, device="cpu"):
     """(n, sum, sum of squares) of the local advantages -> the global triple, in fp64 (torch.std parity needs it)."""
     t = torch.as_tensor(local_stats, dtype=torch.float64, device=device).clone()

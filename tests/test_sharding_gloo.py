@@ -8,7 +8,8 @@ import torch.multiprocessing as mp
 
 import numpy as np
 
-from spp_rl_b200.sharding import agent_shard, allreduce_adv_stats, env_shard_rows, gather_tables, local_minibatch, max_over_ranks
+from spp_rl_b200.sharding import (agent_shard, allreduce_adv_stats, env_shard_rows, epoch_local_minibatches_device, gather_tables, local_minibatch,
+                                  local_minibatch_device, max_over_ranks)
 
 
 def _free_port():
@@ -71,6 +72,12 @@ def test_env_sharding_covers_rows_and_minibatches():
             loc = local_minibatch(perm, E, r, world)
             mine = [g for g in perm.tolist() if (g % E) // El == r]
             assert rows[loc].tolist() == mine
+            assert local_minibatch_device(torch.from_numpy(perm), E, r, world).tolist() == loc.tolist()      # the torch form (device path)
+        full = np.random.RandomState(9).permutation(E * T)
+        for r in range(world):      # a whole epoch filtered at once == the minibatches filtered one by one (ragged last minibatch)
+            ids, off = epoch_local_minibatches_device(torch.from_numpy(full), 23, E, r, world)
+            for k, b0 in enumerate(range(0, E * T, 23)):
+                assert ids[off[k]:off[k + 1]].tolist() == local_minibatch(full[b0:b0 + 23], E, r, world).tolist()
         sizes = [len(local_minibatch(np.arange(E * T), E, r, world)) for r in range(world)]
         assert sum(sizes) == E * T
 
