@@ -72,9 +72,12 @@ class NetView:
         return self
 
 
-def sampler_permutation(n):
-    """One epoch of DataLoader(shuffle=True): RandomSampler.__iter__ draws a seed from torch's global generator and
-    permutes with a private generator seeded by it."""
+def sampler_permutation(n, dataloader=True):
+    """The row order of one pass over DataLoader(dataset, shuffle=True) (acm.py:285, on_policy.py:166) under torch's global
+    generator: every new iterator of a DataLoader first draws its base seed from the global generator (_BaseDataLoaderIter), then
+    RandomSampler.__iter__ draws the seed of a private generator and permutes with it.  dataloader=False: a bare RandomSampler."""
+    if dataloader:
+        torch.empty((), dtype=torch.int64).random_()
     seed = int(torch.empty((), dtype=torch.int64).random_().item())
     g = torch.Generator()
     g.manual_seed(seed)

@@ -308,11 +308,11 @@ class PPO_AcM:
         perms = torch.stack([sampler_permutation(n) for _ in range(self.max_ppo_epochs)]).numpy()
         losses, epochs, kl = self._pol.update_actor(perms, self.ppo_batch_size, self.kl_div_threshold, self.max_ppo_epochs)
         torch.set_rng_state(state)                                    # the reference draws one sampler seed per epoch it actually runs
-        for _ in range(epochs):
+        for _ in range(2 * epochs):                                   # (DataLoader base seed + sampler seed) per epoch
             torch.empty((), dtype=torch.int64).random_()
         self.loss.update({k: float(v) for k, v in losses.items()})
         self.loss["entropy"] = float(losses["entropy"])
-        self.kl_div_updates_counter += epochs + 1
+        self.kl_div_updates_counter += min(epochs + 1, self.max_ppo_epochs)      # the reference adds i + 1, i = loop index at exit
         self.last_kl = kl
 
     def perform_iteration(self):

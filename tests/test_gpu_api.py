@@ -240,7 +240,7 @@ def test_ppo_acm_iteration_equals_the_kernel_level_calls():
     losses, epochs, _ = pol.update_actor(perms, 128, 0.1, 4)
     adv = m.update_critic(b)
     m.update_actor(adv, b)
-    assert m.loss["critic"] == closs and m.loss["policy"] == losses["policy"] and m.kl_div_updates_counter == epochs + 1
+    assert m.loss["critic"] == closs and m.loss["policy"] == losses["policy"] and m.kl_div_updates_counter == min(epochs + 1, 4)
     for net in ("actor", "critic"):
         sa, sb = getattr(m, net).state_dict(), pol.state_dict(net)
         assert all(np.array_equal(sa[k].numpy(), sb[k]) for k in sb), net

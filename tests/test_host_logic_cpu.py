@@ -1,0 +1,78 @@
+"""CPU: host-side mirrors that carry no arithmetic but decide WHICH rows and WHICH random numbers the device path sees --
+checked against torch's own DataLoader sampler and against the oracle's restatement of the reference's memory views."""
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, RandomSampler, TensorDataset
+
+from oracle import ppo as P
+from spp_rl_b200.rltoolkit_api import ValidationRing, sampler_permutation
+from spp_rl_b200.rltoolkit_ppo import PPO_DEFAULTS, RolloutMemory
+
+
+def test_sampler_permutation_is_the_dataloaders_shuffle():
+    """update_acm / update_actor_acm iterate DataLoader(shuffle=True) (acm.py:285, on_policy.py:166): same seed -> same order and
+    the same state of torch's global generator afterwards (so later draws stay aligned with the reference as well)."""
+    n = 257
+    for seed in (0, 7):
+        torch.manual_seed(seed)
+        ref = [list(RandomSampler(range(n))) for _ in range(3)]
+        after_ref = torch.rand(1).item()
+        torch.manual_seed(seed)
+        got = [sampler_permutation(n, dataloader=False).tolist() for _ in range(3)]
+        after = torch.rand(1).item()
+        assert got == ref and after == after_ref
+    torch.manual_seed(3)
+    x = torch.arange(n, dtype=torch.float32)[:, None]
+    batches = [b[0][:, 0].long().tolist() for b in DataLoader(TensorDataset(x), batch_size=64, shuffle=True)]
+    torch.manual_seed(3)
+    perm = sampler_permutation(n).tolist()
+    assert [perm[i:i + 64] for i in range(0, n, 64)] == batches and len(batches[-1]) == n - 4 * 64      # partial last minibatch kept
+
+
+def test_rollout_memory_views_skip_the_joints_like_the_reference():
+    """Memory.obs / next_obs (rltoolkit/buffer/memory.py:146-170) over a chain with three rollouts == the oracle's chain_views."""
+    rng = np.random.RandomState(0)
+    m = RolloutMemory()
+    lens = [4, 1, 6]
+    for L in lens:
+        prev = m.add_obs(torch.from_numpy(rng.randn(1, 5).astype(np.float32)))
+        for t in range(L):
+            nxt = m.add_obs(torch.from_numpy(rng.randn(1, 5).astype(np.float32)))
+            m.add_timestep(prev, nxt, torch.zeros(1, 5), torch.zeros(1), 0.0, False, t == L - 1)
+            m.add_acm_action(np.zeros(2, np.float32))
+            prev = nxt
+        m.end_rollout()
+    chain = torch.cat(m._obs)
+    oi, ni = P.chain_views(len(chain), list(m._new_rollout_idx))
+    assert len(m) == sum(lens) == len(oi) and m._new_rollout_idx == [5, 7, 14]
+    assert torch.equal(m.obs, chain[oi]) and torch.equal(m.next_obs, chain[ni])
+    assert [i for i, e in enumerate(m.end) if e] == [3, 4, 10]
+
+
+def test_validation_ring_follows_the_replay_state_machine():
+    """ValidationRing == MetaReplayBuffer's cursor rules (replay_buffer.py:56-75): wrap of the observation cursor shrinks current_len."""
+    r = ValidationRing(6, 2, 1)
+    prev = r.add_obs(np.zeros(2))
+    for t in range(9):
+        nxt = r.add_obs(np.full(2, t + 1.0))
+        r.add_timestep(prev, nxt, np.array([float(t)]))
+        prev = nxt
+    # oracle: the same sequence through the reference-pinned ring restatement
+    from oracle.ring import Ring
+    o = Ring(6, 2, 2, 1)
+    prev = o.add_obs(np.zeros(2))
+    for t in range(9):
+        nxt = o.add_obs(np.full(2, t + 1.0))
+        o.add_acm_action(np.array([float(t)]))
+        o.add_timestep(prev, nxt)
+        prev = nxt
+    assert (r.obs_idx, r.ts_idx, r.current_len) == (o.obs_cur, o.ts_cur, o.current_len)
+    n = r.current_len
+    assert np.array_equal(r._obs_idx[:n], o.obs_idx[:n]) and np.array_equal(r._next_obs_idx[:n], o.next_obs_idx[:n])
+    assert np.array_equal(r.actions_acm, o.actions_acm[:n]) and np.array_equal(r.obs, o.obs[o.obs_idx[:n]])
+
+
+def test_ppo_defaults_are_the_reference_config():
+    assert PPO_DEFAULTS["actor_lr"] == 3e-3 and PPO_DEFAULTS["critic_lr"] == 3e-4 and PPO_DEFAULTS["ppo_batch_size"] == 1000
+    assert PPO_DEFAULTS["kl_div_threshold"] == 0.15 and PPO_DEFAULTS["max_ppo_epochs"] == 50 and PPO_DEFAULTS["gae_lambda"] == 0.95
+    assert "tau" not in PPO_DEFAULTS and "buffer_size" not in PPO_DEFAULTS
