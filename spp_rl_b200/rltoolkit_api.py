@@ -347,8 +347,8 @@ class _OffPolicyAcM:
         """DDPG_AcM.make_update (ddpg_acm.py:75-85): grad_steps x (sample_batch + update) in ONE fused launch, then the
         ACM regression when its condition holds."""
         if self.unbiased_update:
-            raise NotImplementedError("unbiased_update is outside the fused path")
-        if self.update_condition():
+            self.make_unbiased_update()
+        elif self.update_condition():
             G, B, n = self.grad_steps, self.update_batch_size, len(self.replay_buffer)
             idx = np.stack([np.random.randint(0, n, B) for _ in range(G)]).astype(np.int64)[None]
             losses = self._pop.update_ring(G, idx=np.ascontiguousarray(idx), eps=self._draw_eps(G))
@@ -358,6 +358,17 @@ class _OffPolicyAcM:
                 self.update_acm_batches(self.acm_update_batches)
             else:
                 self.update_acm(self.acm_epochs)
+
+    def make_unbiased_update(self):
+        """DDPG_AcM.make_unbiased_update (ddpg_acm.py:59-73): the stored next observation stands in for the state-target action.
+        The grad_steps minibatches are gathered from the device ring and go through the explicit-batch form in ONE fused launch."""
+        if self.update_condition():
+            G, B, n = self.grad_steps, self.update_batch_size, len(self.replay_buffer)
+            idx = np.concatenate([np.random.randint(0, n, B) for _ in range(G)]).astype(np.int64)
+            obs, nobs, _, rew, done, aacm = self._pop.ring_sample_batch(0, idx)
+            shp = lambda a: np.ascontiguousarray(a.reshape((1, G, B) + a.shape[1:]))
+            losses = self._pop.update_host(G, shp(obs), shp(nobs), shp(nobs), shp(rew), shp(done), shp(aacm), eps=self._draw_eps(G))
+            self._store_losses(losses[0, -1])
 
     def update_acm_batches(self, n_batches):
         n = len(self.replay_buffer)

@@ -246,3 +246,33 @@ def test_ppo_acm_iteration_equals_the_kernel_level_calls():
         assert all(np.array_equal(sa[k].numpy(), sb[k]) for k in sb), net
     assert sum(e for e in b.end) >= 5 and any(e and not d for e, d in zip(b.end, b.done))      # truncated rollouts bootstrap
     pol.close(); m.close()
+
+
+def test_unbiased_update_equals_the_reference_loop_of_single_steps():
+    """DDPG_AcM.make_unbiased_update (ddpg_acm.py:59-73): action := next_obs; fused launch == loop of update() calls.  acm_critic=False
+    makes the critic actually consume that action."""
+    kw = dict(SCRIPT_KW, env_name="HalfCheetah-v2", grad_steps=3, update_freq=1, random_frames=0, acm_update_freq=10 ** 9, acm_critic=False,
+              unbiased_update=True, custom_loss=1.0)
+    models = []
+    for _ in range(2):
+        torch.manual_seed(6); np.random.seed(6)
+        m = DDPG_AcM(**kw)
+        m.pre_train()
+        models.append(m)
+    a, b = models
+    for net in ("actor", "critic", "acm"):
+        b._pop.load_state_dict(net, a._pop.state_dict(net))
+    a._pop.sync_targets(); b._pop.sync_targets()
+    a.stats_logger.frames = b.stats_logger.frames = 7
+    torch.manual_seed(12); np.random.seed(12)
+    a.make_update()
+    torch.manual_seed(12); np.random.seed(12)
+    for g in range(3):
+        obs, next_obs, _, reward, done, acm_action = b.replay_buffer.sample_batch(b.update_batch_size)
+        b.update(obs=obs, next_obs=next_obs, action=next_obs, reward=reward, done=done, acm_action=acm_action)
+    for net in ("actor", "critic"):
+        sa, sb = a._pop.state_dict(net), b._pop.state_dict(net)
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), (net, k)
+    assert a.loss["critic"] == b.loss["critic"]
+    a.close(); b.close()
