@@ -254,7 +254,7 @@ class PPO_AcM:
             noise = torch.empty(1, self.ob_dim).normal_().numpy()     # Normal.sample(): one standard-normal tensor per step
         o = np.asarray(obs, np.float32).reshape(1, self.ob_dim)
         action, logp, target = self._pol.act(o, noise, self.denormalize_actor_out)
-        _, acm_action = self._pop.rollout_step(o[None], action[None], None, random_phase=True, obs_norm=True,
+        _, acm_action = self._pop.rollout_step(o[None], action[None], None, random_phase=2, obs_norm=True,      # 2: the target is given
                                                denormalize_actor_out=self.denormalize_actor_out)
         return torch.from_numpy(action), torch.from_numpy(logp), acm_action[0, 0]
 
