@@ -21,6 +21,10 @@ namespace spp {
 
 constexpr int kStatTargets = 4;      // order statistics per column: lo/hi rank of the 1st and of the 99th percentile
 constexpr int kStatColsPerBlock = 12;
+#ifndef SPP_STAT_ROWS
+#define SPP_STAT_ROWS 8
+#endif
+constexpr int kStatRowsInFlight = SPP_STAT_ROWS;      // rows per thread and batch
 
 __device__ __forceinline__ uint32_t sortable_key(float x) {      // monotone map float -> uint32
     const uint32_t b = __float_as_uint(x);
@@ -50,14 +54,21 @@ __global__ void __launch_bounds__(256) stats_moment_kernel(RingView R, const int
         const double mu = pass ? mean[(size_t)a * ob + j] : 0.0;
         // 4 rows in flight per thread: the index load and the value load of a row are dependent, so without this every element
         // costs two exposed HBM latencies
-        for (int64_t i = r0 + threadIdx.x / ob; i < r1; i += 4 * rows_per_iter) {
-            int32_t oi[4]; float v[4];
+        // software-pipelined: the indices of batch k + 1 are loaded while the values of batch k are in flight, so only ONE HBM
+        // latency per batch is exposed (with the index load in front of its own value load the passes ran at 2.3 TB/s)
+        constexpr int U = kStatRowsInFlight;
+        int32_t on[U];
+        int64_t i = r0 + threadIdx.x / ob;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int64_t ii = i + (int64_t)u * rows_per_iter; oi[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+        for (int u = 0; u < U; ++u) { const int64_t ii = i + (int64_t)u * rows_per_iter; on[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+        for (; i < r1; i += U * rows_per_iter) {
+            int32_t oi[U]; float v[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = oi[u] >= 0 ? R.obs[(base + oi[u]) * R.ldo + j] : 0.f;
+            for (int u = 0; u < U; ++u) { oi[u] = on[u]; v[u] = oi[u] >= 0 ? R.obs[(base + oi[u]) * R.ldo + j] : 0.f; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) { const int64_t ii = i + (int64_t)(U + u) * rows_per_iter; on[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
                 if (oi[u] < 0) continue;
                 const double x = (double)v[u];
                 if (pass) { const double d = fabs(x - mu); acc += d * d; } else acc += x;
@@ -113,14 +124,19 @@ __global__ void __launch_bounds__(256) stats_select_hist_kernel(RingView R, cons
 #pragma unroll
             for (int U = 0; U < T; ++U) own[T] = own[T] && (prefix[U] != prefix[T]);
         }
-        for (int64_t i = r0 + threadIdx.x / cols; i < r1; i += 4 * rows_per_iter) {      // 4 rows in flight per thread
-            int32_t oi[4]; float v[4];
+        constexpr int U = kStatRowsInFlight;      // same software pipeline as the moment passes
+        int32_t on[U];
+        int64_t i = r0 + threadIdx.x / cols;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int64_t ii = i + (int64_t)u * rows_per_iter; oi[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+        for (int u = 0; u < U; ++u) { const int64_t ii = i + (int64_t)u * rows_per_iter; on[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+        for (; i < r1; i += U * rows_per_iter) {
+            int32_t oi[U]; float v[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = oi[u] >= 0 ? R.obs[(base + oi[u]) * R.ldo + j] : 0.f;
+            for (int u = 0; u < U; ++u) { oi[u] = on[u]; v[u] = oi[u] >= 0 ? R.obs[(base + oi[u]) * R.ldo + j] : 0.f; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) { const int64_t ii = i + (int64_t)(U + u) * rows_per_iter; on[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
                 if (oi[u] < 0) continue;
                 const uint32_t k = sortable_key(v[u]);
                 const uint32_t byte = (k >> shift) & 255u;
