@@ -8,7 +8,7 @@
 // ranks of both percentiles), so every result is exactly an element of the buffer and the percentile interpolation is done
 // in fp64 on the host with numpy's own formula -> bit-exact against np.percentile.
 //
-// Thread mapping: a block owns a contiguous range of rows; thread t < (256 / ob) * ob has a FIXED column j = t % ob and walks
+// Thread mapping (rows wider than 16 floats; narrower rows use the *_rows_kernel variants below): a block owns a contiguous range of rows; thread t < (256 / ob) * ob has a FIXED column j = t % ob and walks
 // rows t / ob, t / ob + 256 / ob, ... of the range, so consecutive threads read consecutive floats of (mostly consecutive)
 // ring rows and every thread keeps its accumulator / histogram column in registers / a private shared-memory slice.
 #include <cmath>
@@ -84,6 +84,74 @@ __global__ void __launch_bounds__(256) stats_moment_kernel(RingView R, const int
     }
 }
 
+// Moment pass with a ROW per thread (observation rows of up to 16 floats: Pendulum, Hopper): float4 loads of the whole row, 4 rows in
+// flight per thread (192 B instead of 16 B of loads outstanding per thread), one fp64 accumulator per column; the 256 per-thread
+// sums of a column are combined by a fixed shuffle tree and the 8 warp partials in warp order (deterministic).
+template <int NV>
+__global__ void __launch_bounds__(256, 2) stats_moment_rows_kernel(RingView R, const int64_t* __restrict__ len, int pass,
+                                                                const double* __restrict__ mean, double* __restrict__ partial) {
+    const int a = blockIdx.y, nb = gridDim.x, ob = R.ob;
+    const int64_t n = len[a];
+    const int64_t per = (n + nb - 1) / nb, r0 = (int64_t)blockIdx.x * per, r1 = min(n, r0 + per);
+    const size_t base = (size_t)a * R.S;
+    constexpr int C = 4 * NV, U = 4;
+    double acc[C], mu[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { acc[c] = 0.0; mu[c] = (pass && c < ob) ? mean[(size_t)a * ob + c] : 0.0; }
+    int32_t on[U];
+    int64_t i = r0 + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int64_t ii = i + (int64_t)u * 256; on[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+    for (; i < r1; i += U * 256) {
+        int32_t oi[U]; float4 v[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            oi[u] = on[u];
+            const float4* row = reinterpret_cast<const float4*>(R.obs + (base + (oi[u] >= 0 ? oi[u] : 0)) * R.ldo);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) v[u][q] = oi[u] >= 0 ? row[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int64_t ii = i + (int64_t)(U + u) * 256; on[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (oi[u] < 0) continue;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const float x4[4] = {v[u][q].x, v[u][q].y, v[u][q].z, v[u][q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double x = (double)x4[e];
+                    if (pass) { const double d = fabs(x - mu[4 * q + e]); acc[4 * q + e] += d * d; } else acc[4 * q + e] += x;
+                }
+            }
+        }
+    }
+    __shared__ double red[C][kWarps];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        double t = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane_id() == 0) red[c][warp_id()] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < ob) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) t += red[threadIdx.x][w];
+        partial[((size_t)a * nb + blockIdx.x) * ob + threadIdx.x] = t;
+    }
+}
+
+static void launch_moment(const RingView& R, dim3 grid, const int64_t* d_len, int pass, const double* d_mean, double* d_partial, cudaStream_t s) {
+    if (R.ldo == 4 && R.ob <= 4) stats_moment_rows_kernel<1><<<grid, 256, 0, s>>>(R, d_len, pass, d_mean, d_partial);
+    else if (R.ldo == 8) stats_moment_rows_kernel<2><<<grid, 256, 0, s>>>(R, d_len, pass, d_mean, d_partial);
+    else if (R.ldo == 12) stats_moment_rows_kernel<3><<<grid, 256, 0, s>>>(R, d_len, pass, d_mean, d_partial);
+    else if (R.ldo == 16) stats_moment_rows_kernel<4><<<grid, 256, 0, s>>>(R, d_len, pass, d_mean, d_partial);
+    else stats_moment_kernel<<<grid, 256, 0, s>>>(R, d_len, pass, d_mean, d_partial);      // wider rows: one column per thread
+}
+
 // out[a][j] = sum over blocks (fixed order) / n;  pass 1 additionally takes the square root
 __global__ void stats_moment_finish_kernel(const double* __restrict__ partial, const int64_t* __restrict__ len, int P, int nb, int ob,
                                            int pass, double* __restrict__ out) {
@@ -154,6 +222,88 @@ __global__ void __launch_bounds__(256) stats_select_hist_kernel(RingView R, cons
     }
 }
 
+// Radix pass with a ROW per thread (rows of up to 16 floats), same loads as stats_moment_rows_kernel.  All 32 lanes of a warp are in
+// the same column at the same time, so hot bins serialise in the shared-memory atomic unit (pass 0: a handful of exponent bins);
+// that costs less than the one-float-per-thread loads did (1.5-1.7 TB/s).  Later passes filter on the prefix first: few atomics.
+template <int NV>
+__global__ void __launch_bounds__(256, 2) stats_select_hist_rows_kernel(RingView R, const int64_t* __restrict__ len, int pass,
+                                                                        const unsigned long long* __restrict__ state,
+                                                                        unsigned int* __restrict__ hist) {
+    const int a = blockIdx.y, nb = gridDim.x, ob = R.ob;
+    const int64_t n = len[a];
+    const int64_t per = (n + nb - 1) / nb, r0 = (int64_t)blockIdx.x * per, r1 = min(n, r0 + per);
+    const size_t base = (size_t)a * R.S;
+    constexpr int C = 4 * NV, U = 4;
+    extern __shared__ unsigned int sh[];      // [ob][kStatTargets][256]
+    for (int i = threadIdx.x; i < ob * kStatTargets * 256; i += 256) sh[i] = 0;
+    const int shift = 24 - 8 * pass;
+    uint32_t prefix[C][kStatTargets];         // registers: every thread sees every column
+    unsigned long long ownbits = 0;           // bit 4 c + T: target T of column c owns a histogram (no earlier target shares its prefix)
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int T = 0; T < kStatTargets; ++T) prefix[c][T] = c < ob ? (uint32_t)(state[(((size_t)a * ob + c) * kStatTargets + T) * 2]) : 0u;
+#pragma unroll
+        for (int T = 0; T < kStatTargets; ++T) {
+            bool own = c < ob;
+#pragma unroll
+            for (int V = 0; V < T; ++V) own = own && (prefix[c][V] != prefix[c][T]);
+            if (own) ownbits |= 1ull << (4 * c + T);
+        }
+    }
+    __syncthreads();
+    int32_t on[U];
+    int64_t i = r0 + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; ++u) { const int64_t ii = i + (int64_t)u * 256; on[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+    for (; i < r1; i += U * 256) {
+        int32_t oi[U]; float4 v[U][NV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            oi[u] = on[u];
+            const float4* row = reinterpret_cast<const float4*>(R.obs + (base + (oi[u] >= 0 ? oi[u] : 0)) * R.ldo);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) v[u][q] = oi[u] >= 0 ? row[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int64_t ii = i + (int64_t)(U + u) * 256; on[u] = ii < r1 ? R.oidx[base + ii] : -1; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (oi[u] < 0) continue;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const float x4[4] = {v[u][q].x, v[u][q].y, v[u][q].z, v[u][q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * q + e;
+                    if (c >= ob) continue;
+                    const uint32_t k = sortable_key(x4[e]);
+                    const uint32_t byte = (k >> shift) & 255u;
+                    const uint32_t hi = pass ? (k >> (shift + 8)) : 0u;
+#pragma unroll
+                    for (int T = 0; T < kStatTargets; ++T)
+                        if (((ownbits >> (4 * c + T)) & 1ull) && (pass == 0 || hi == prefix[c][T])) atomicAdd(sh + (c * kStatTargets + T) * 256 + byte, 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < ob * kStatTargets * 256; k += 256) {
+        const unsigned int v = sh[k];
+        if (v) atomicAdd(hist + (size_t)a * ob * kStatTargets * 256 + k, v);
+    }
+}
+
+template <int NV>
+static cudaError_t launch_hist_rows(const RingView& R, dim3 grid, const int64_t* d_len, int pass, const unsigned long long* d_state,
+                                    unsigned int* d_hist, cudaStream_t s) {
+    const size_t sh = (size_t)R.ob * kStatTargets * 256 * sizeof(unsigned int);
+    cudaError_t e = cudaFuncSetAttribute(stats_select_hist_rows_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return e;
+    stats_select_hist_rows_kernel<NV><<<grid, 256, sh, s>>>(R, d_len, pass, d_state, d_hist);
+    return cudaGetLastError();
+}
+
 // one warp per (agent, column): walk the 256 bins of every target, append the byte that contains its rank, clear the histogram
 __global__ void stats_select_step_kernel(int P, int ob, int pass, unsigned long long* __restrict__ state, unsigned int* __restrict__ hist) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -191,9 +341,9 @@ cudaError_t launch_ring_obs_stats(const RingView& R, int P, const int64_t* d_len
     double* d_mean = d_moments; double* d_std = d_moments + (size_t)P * ob;
     if (ob > 256) return cudaErrorInvalidValue;
     dim3 grid(nb, P);
-    stats_moment_kernel<<<grid, 256, 0, s>>>(R, d_len, 0, nullptr, d_partial);
+    launch_moment(R, grid, d_len, 0, nullptr, d_partial, s);
     stats_moment_finish_kernel<<<(P * ob + 255) / 256, 256, 0, s>>>(d_partial, d_len, P, nb, ob, 0, d_mean);
-    stats_moment_kernel<<<grid, 256, 0, s>>>(R, d_len, 1, d_mean, d_partial);
+    launch_moment(R, grid, d_len, 1, d_mean, d_partial, s);
     stats_moment_finish_kernel<<<(P * ob + 255) / 256, 256, 0, s>>>(d_partial, d_len, P, nb, ob, 1, d_std);
     // ranks as numpy computes them for method "linear": virtual index (n - 1) * q in fp64, lo = floor, hi = min(lo + 1, n - 1)
     for (int a = 0; a < P; ++a) {
@@ -218,7 +368,12 @@ cudaError_t launch_ring_obs_stats(const RingView& R, int P, const int64_t* d_len
     e = cudaFuncSetAttribute(stats_select_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
     if (e != cudaSuccess) return e;
     for (int pass = 0; pass < 4; ++pass) {
-        stats_select_hist_kernel<<<dim3(nb, P, groups), 256, sh, s>>>(R, d_len, pass, d_state, d_hist);
+        if (R.ldo == 4 && ob <= 4) e = launch_hist_rows<1>(R, grid, d_len, pass, d_state, d_hist, s);
+        else if (R.ldo == 8) e = launch_hist_rows<2>(R, grid, d_len, pass, d_state, d_hist, s);
+        else if (R.ldo == 12) e = launch_hist_rows<3>(R, grid, d_len, pass, d_state, d_hist, s);
+        else if (R.ldo == 16) e = launch_hist_rows<4>(R, grid, d_len, pass, d_state, d_hist, s);
+        else stats_select_hist_kernel<<<dim3(nb, P, groups), 256, sh, s>>>(R, d_len, pass, d_state, d_hist);      // wider rows: one column per thread
+        if (e != cudaSuccess) return e;
         stats_select_step_kernel<<<(P * ob * 32 + 255) / 256, 256, 0, s>>>(P, ob, pass, d_state, d_hist);
     }
     return cudaGetLastError();
