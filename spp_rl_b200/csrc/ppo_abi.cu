@@ -120,8 +120,10 @@ int spp_ppo_create(const spp_ppo_config* cfg, int device, spp_ppo** out) {
     PALLOC(p->s.h1, SR * kPpoHidden * 4); PALLOC(p->s.h2, NB * kPpoHidden * 4 + 4096); PALLOC(p->s.dz2, SR * kPpoHidden * 4); PALLOC(p->s.dz1, SR * kPpoHidden * 4);
     PALLOC(p->s.mean, (NB + 128) * ldo * 4); PALLOC(p->s.t3, (NB + 128) * ldo * 4); PALLOC(p->s.d3, (NB + 128) * ldo * 4); PALLOC(p->s.newlogp, (NB + 128) * 4);
     p->part_stride = p->L.actor.size > p->L.critic.size ? p->L.actor.size : p->L.critic.size;
-    PALLOC(p->part, (size_t)p->grid * p->part_stride * 4); PALLOC(p->gbuf, (size_t)p->part_stride * 4);
-    PALLOC(p->scal, (size_t)p->grid * PS_COUNT * 4); PALLOC(p->gscal, PS_COUNT * 4);
+    PALLOC(p->part, (size_t)p->grid * p->part_stride * 4);
+    // reduced gradient vector and the reduced scalars in ONE buffer: a data-parallel step all-reduces them with one collective
+    PALLOC(p->gbuf, (size_t)(p->part_stride + PS_COUNT) * 4); p->gscal = p->gbuf + p->part_stride;
+    PALLOC(p->scal, (size_t)p->grid * PS_COUNT * 4);
     PALLOC(p->dstats, (size_t)p->grid * 2 * 8);
     PALLOC(p->dperm, NB * 8);
 #undef PALLOC

@@ -144,15 +144,33 @@ class PpoPolicy:
     # ------------------------------------------------------------------ data-parallel forms (torch.distributed)
     def grad_tensor(self):
         """torch views (no copy) of the reduced gradient vector and the 8 scalar slots, for dist.all_reduce."""
+        g, sc, _ = self._grad_views()
+        return g, sc
+
+    def _grad_views(self):
         import torch
 
-        ptr, sptr, n = C.c_void_p(), C.c_void_p(), C.c_int()
-        check(self.lib.spp_ppo_grad_buffer(self.h, C.byref(ptr), C.byref(n), C.byref(sptr)))
+        if getattr(self, "_views", None) is None:
+            ptr, sptr, n = C.c_void_p(), C.c_void_p(), C.c_int()
+            check(self.lib.spp_ppo_grad_buffer(self.h, C.byref(ptr), C.byref(n), C.byref(sptr)))
 
-        class _Arr:
-            def __init__(self, p, k):
-                self.__cuda_array_interface__ = {"shape": (k,), "typestr": "<f4", "data": (p, False), "version": 2}
-        return torch.as_tensor(_Arr(ptr.value, n.value), device="cuda"), torch.as_tensor(_Arr(sptr.value, 8), device="cuda")
+            class _Arr:
+                def __init__(self, p, k):
+                    self.__cuda_array_interface__ = {"shape": (k,), "typestr": "<f4", "data": (p, False), "version": 2}
+            g = torch.as_tensor(_Arr(ptr.value, n.value), device="cuda")
+            sc = torch.as_tensor(_Arr(sptr.value, 8), device="cuda")
+            # the library keeps the scalars right behind the gradient vector: one collective per optimiser step covers both
+            both = torch.as_tensor(_Arr(ptr.value, n.value + 8), device="cuda") if sptr.value == ptr.value + 4 * n.value else None
+            self._views = (g, sc, both)
+        return self._views
+
+    def _allreduce_grads(self, dist):
+        g, sc, both = self._grad_views()
+        if both is not None:
+            dist.all_reduce(both)
+        else:
+            dist.all_reduce(g)
+            dist.all_reduce(sc)
 
     def scalars(self):
         out = (C.c_float * 8)()
@@ -183,8 +201,7 @@ class PpoPolicy:
                 check(self.lib.spp_ppo_critic_targets(self.h))
                 for _ in range(n_updates_per_target):
                     check(self.lib.spp_ppo_critic_grad(self.h))
-                    dist.all_reduce(g)
-                    dist.all_reduce(sc)
+                    self._allreduce_grads(dist)
                     tot += sc[0].double()
                     check(self.lib.spp_ppo_critic_apply(self.h))
         st.synchronize()
@@ -204,8 +221,7 @@ class PpoPolicy:
             else:
                 p = np.ascontiguousarray(perm_local, np.int64)
                 check(self.lib.spp_ppo_actor_minibatch_grad(self.h, _ptr(p, C.c_int64), int(p.size), int(n_global)))
-            dist.all_reduce(g)
-            dist.all_reduce(sc)
+            self._allreduce_grads(dist)
             out = sc.clone()
             check(self.lib.spp_ppo_actor_apply(self.h))
         if want_host:

@@ -91,7 +91,7 @@ def main():
     pol.advantages(want_host=False)
     pol.normalize_adv(allreduce_adv_stats(pol.adv_stats(), dist, "cuda"))
     pol.sync(); w2 = time.perf_counter()
-    n_allreduce = args.critic_targets * args.critic_steps * 2 + 1
+    n_allreduce = args.critic_targets * args.critic_steps + 1      # gradient vector and scalars travel in one buffer
     for ep in range(args.epochs):
         with torch.cuda.stream(pol._ext_stream()):      # the epoch's permutation goes to the device once; ranks filter their rows there
             perm_dev = torch.from_numpy(perms[ep]).cuda()
@@ -99,7 +99,7 @@ def main():
             for k, b0 in enumerate(range(0, N, args.batch)):
                 pol.actor_minibatch_dp(dist, ids[off[k]:off[k + 1]], min(args.batch, N - b0),
                                        want_host=(b0 + args.batch >= N))      # one host read per epoch (KL test)
-                n_allreduce += 2
+                n_allreduce += 1
     pol.sync()
     w3 = time.perf_counter()
     phases = {"critic_fit": (w1 - w0) * 1e3, "advantages_and_normalisation": (w2 - w1) * 1e3, "actor_epochs": (w3 - w2) * 1e3}
