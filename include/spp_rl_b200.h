@@ -134,6 +134,9 @@ int spp_update_ring(spp_population* p, int grad_steps, const int64_t* idx, const
                     float* losses);
 /* Fully device-resident form (no host traffic): device sampler + device noise; losses_dev may be NULL. */
 int spp_update_ring_device(spp_population* p, int grad_steps, uint64_t seed, float* losses_dev, void* stream);
+/* profiling: the same burst with %globaltimer stamps at agent 0's 24 stage boundaries; out_us[0..23) = mean microseconds per
+ * stage over the grad_steps updates (stage names: tools/stage_profile.py) */
+int spp_update_stage_profile(spp_population* p, int grad_steps, uint64_t seed, double* out_us, int cap, int* n_out);
 
 /* ---- ACM regression: AcMTrainer.update_acm_batches (rltoolkit/acm/acm.py:356-372), n_batches x
  *      [rbuffer_sample_acm (rltoolkit/buffer/replay_buffer.py:404-430) -> acm_cat (acm.py:260-264) ->
@@ -158,7 +161,9 @@ int spp_set_learning_rates(spp_population* p, double actor_lr, double critic_lr,
  *      -> AcMOffPolicy.process_action (off_policy.py:89-106), for E observations per agent at once.
  * obs, noise (torch.randn of the reference), eps (the SAC actor's rsample draw; NULL = deterministic mean, as test()
  * uses it) are [P][E][ob]; out_target [P][E][ob] is the state target stored in the ring, out_action [P][E][ac] the
- * ACM action for the environment. */
+ * ACM action for the environment.
+ * random_phase: 0 = the actor acts (noise_action); 1 = frames < random_frames, target = actor_ac_lim * noise (initial_act);
+ * 2 = `noise` IS the state target already (a bare process_action call: no actor, no limit scale, no clip). */
 int spp_rollout_step_host(spp_population* p, int E, const float* obs, const float* noise, const float* eps, int random_phase,
                           double act_noise, int obs_norm, int denormalize_actor_out, float* out_target, float* out_action);
 /* Device-resident rollout of a synthetic environment (MuJoCo is unavailable offline): `steps` consecutive vectorised
@@ -228,7 +233,7 @@ int spp_ppo_scalars(spp_ppo* p, float out[8]);
  * Memory.normalize -> Actor.act (rltoolkit/basic_model.py:32-51; noise [E][ob] = the N(0,1) of Normal.sample) -> the
  * denormalisation half of AcMOnPolicyTrainer.process_action (rltoolkit/acm/on_policy.py:46-47).  action [E][ob] is the
  * sampled target the Memory stores, logp [E] its log-prob, target [E][ob] what is concatenated with the normalised obs
- * for the ACM (spp_rollout_step_host with random_phase = 1, obs_norm = 1 and noise = action evaluates that ACM call). */
+ * for the ACM (spp_rollout_step_host with random_phase = 2, obs_norm = 1 and noise = action evaluates that ACM call). */
 int spp_ppo_act(spp_ppo* p, int64_t E, const float* obs, const float* noise, int denormalize_actor_out, float* action, float* logp,
                 float* target);
 /* device pointers of the reduced gradient vector (n_floats) and the 8 scalar slots, for torch.distributed all_reduce */

@@ -79,6 +79,7 @@ SIGNATURES = {
     "spp_update_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p, _f32p, _i8p, _f32p, _f32p, C.c_uint64, _f32p]),
     "spp_update_ring": (C.c_int, [_vp, C.c_int, _i64p, _f32p, C.c_uint64, _f32p]),
     "spp_update_ring_device": (C.c_int, [_vp, C.c_int, C.c_uint64, _vp, _vp]),
+    "spp_update_stage_profile": (C.c_int, [_vp, C.c_int, C.c_uint64, _f64p, C.c_int, _i32p]),
     "spp_acm_update_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, C.c_int, _f32p]),
     "spp_acm_eval_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, C.c_int, _f32p]),
     "spp_acm_update_ring": (C.c_int, [_vp, C.c_int, _i64p, C.c_int, C.c_uint64, _f32p]),

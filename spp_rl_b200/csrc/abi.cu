@@ -34,6 +34,11 @@ void spp_count_launch_() { g_launches++; }
             return fail(SPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
     } while (0)
 
+// Host -> device writes of ring rows, statistics and parameters go through the population's own (non-blocking) stream, so they
+// are ordered against in-flight work of the asynchronous entry points; pageable sources are staged before the call returns.
+#define H2D(dst, src, bytes) CK(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, p->stream))
+#define H2D_DONE() CK(cudaStreamSynchronize(p->stream))
+
 struct TensorMap {
     std::string name;
     int layer;      // index into NetDesc::L
@@ -266,10 +271,11 @@ int spp_set_limits(spp_population* p, const float* actor_lim, const float* acm_l
     std::vector<float> v(L.ldo, 0.f);
     for (int j = 0; j < L.ob; ++j) v[j] = actor_lim[j];
     for (int a = 0; a < p->P; ++a)
-        CK(cudaMemcpy(p->norm + ((size_t)a * NORM_COUNT + NORM_LIM) * L.ldo, v.data(), L.ldo * sizeof(float), cudaMemcpyHostToDevice));
+        H2D(p->norm + ((size_t)a * NORM_COUNT + NORM_LIM) * L.ldo, v.data(), L.ldo * sizeof(float));
     std::vector<float> m(32, 0.f);
     for (int j = 0; j < L.ac; ++j) m[j] = acm_lim[j];
-    CK(cudaMemcpy(p->acm_lim, m.data(), 32 * sizeof(float), cudaMemcpyHostToDevice));
+    H2D(p->acm_lim, m.data(), 32 * sizeof(float));
+    H2D_DONE();
     return SPP_OK;
 }
 
@@ -300,7 +306,8 @@ int spp_set_norm_stats(spp_population* p, int a, const float* min_obs, const flo
         }
     }
     for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i)
-        CK(cudaMemcpy(p->norm + (size_t)i * NORM_COUNT * L.ldo, v.data(), 4 * (size_t)L.ldo * sizeof(float), cudaMemcpyHostToDevice));
+        H2D(p->norm + (size_t)i * NORM_COUNT * L.ldo, v.data(), 4 * (size_t)L.ldo * sizeof(float));
+    H2D_DONE();
     return SPP_OK;
 }
 
@@ -355,17 +362,20 @@ static int tensor_io(spp_population* p, int a, int net, int t, float* host, int 
             if (is_w) {
                 for (int r = 0; r < m.rows; ++r)
                     for (int c = 0; c < m.cols; ++c) nat[(size_t)r * l.ld + map_col(l, c)] = host[(size_t)r * m.cols + c];
-                CK(cudaMemcpy(dev_nat, nat.data(), nat.size() * sizeof(float), cudaMemcpyHostToDevice));
+                H2D(dev_nat, nat.data(), nat.size() * sizeof(float));
+                H2D_DONE();
                 if (has_t) {   // read-modify-write of the W^T block: only columns [row0, row0 + rows) belong to this tensor
                     CK(cudaMemcpy(tr.data(), dev_t, tr.size() * sizeof(float), cudaMemcpyDeviceToHost));
                     for (int r = 0; r < m.rows; ++r)
                         for (int c = 0; c < m.cols; ++c)
                             tr[(size_t)map_col(l, c) * l.ld_t + m.row0 + r] = host[(size_t)r * m.cols + c];
-                    CK(cudaMemcpy(dev_t, tr.data(), tr.size() * sizeof(float), cudaMemcpyHostToDevice));
+                    H2D(dev_t, tr.data(), tr.size() * sizeof(float));
+                    H2D_DONE();
                 }
             } else {
                 for (int r = 0; r < m.rows; ++r) nat[r] = host[r];
-                CK(cudaMemcpy(dev_nat, nat.data(), nat.size() * sizeof(float), cudaMemcpyHostToDevice));
+                H2D(dev_nat, nat.data(), nat.size() * sizeof(float));
+                H2D_DONE();
             }
         } else {
             CK(cudaStreamSynchronize(p->stream));
@@ -446,7 +456,8 @@ int spp_alpha_set(spp_population* p, int a, double log_alpha) {
     CK(cudaSetDevice(p->device));
     const double st[4] = {log_alpha, 0.0, 0.0, 0.0};
     for (int i = (a < 0 ? 0 : a); i < (a < 0 ? p->P : a + 1); ++i)
-        CK(cudaMemcpy(p->alpha_state + (size_t)i * 4, st, sizeof(st), cudaMemcpyHostToDevice));
+        H2D(p->alpha_state + (size_t)i * 4, st, sizeof(st));
+    H2D_DONE();
     return SPP_OK;
 }
 
@@ -473,7 +484,8 @@ int spp_ring_add_obs(spp_population* p, int a, const float* obs, int64_t* out_id
     CK(cudaSetDevice(p->device));
     const Layout& L = p->L;
     const int64_t i = p->obs_cur[a];
-    CK(cudaMemcpy(p->r_obs + ((size_t)a * p->S + i) * L.ldo, obs, L.ob * sizeof(float), cudaMemcpyHostToDevice));
+    H2D(p->r_obs + ((size_t)a * p->S + i) * L.ldo, obs, L.ob * sizeof(float));
+    H2D_DONE();
     p->obs_cur[a] = (i + 1) % p->S;                        // replay_buffer.py:56-60
     if (out_idx) *out_idx = i;
     return SPP_OK;
@@ -483,7 +495,8 @@ int spp_ring_add_acm_action(spp_population* p, int a, const float* acm_action) {
     int rc = ring_check(p, a); if (rc) return rc;
     if (!acm_action) return fail(SPP_ERR_ARG, "null acm_action");
     CK(cudaSetDevice(p->device));
-    CK(cudaMemcpy(p->r_aacm + ((size_t)a * p->S + p->ts_cur[a]) * p->L.lda, acm_action, p->L.ac * sizeof(float), cudaMemcpyHostToDevice));
+    H2D(p->r_aacm + ((size_t)a * p->S + p->ts_cur[a]) * p->L.lda, acm_action, p->L.ac * sizeof(float));
+    H2D_DONE();
     return SPP_OK;                                         // replay_buffer.py:332-333
 }
 
@@ -497,12 +510,13 @@ int spp_ring_add_timestep(spp_population* p, int a, int64_t obs_idx, int64_t nex
     const size_t row = (size_t)a * p->S + ts;
     const int32_t oi = (int32_t)obs_idx, ni = (int32_t)next_obs_idx;
     const uint8_t d = done ? 1 : 0, e = end ? 1 : 0;
-    CK(cudaMemcpy(p->r_oidx + row, &oi, 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->r_nidx + row, &ni, 4, cudaMemcpyHostToDevice));
-    if (action && p->r_act) CK(cudaMemcpy(p->r_act + row * L.ldo, action, L.ob * sizeof(float), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->r_rew + row, &reward, 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->r_done + row, &d, 1, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->r_end + row, &e, 1, cudaMemcpyHostToDevice));
+    H2D(p->r_oidx + row, &oi, 4);
+    H2D(p->r_nidx + row, &ni, 4);
+    if (action && p->r_act) H2D(p->r_act + row * L.ldo, action, L.ob * sizeof(float));
+    H2D(p->r_rew + row, &reward, 4);
+    H2D(p->r_done + row, &d, 1);
+    H2D(p->r_end + row, &e, 1);
+    H2D_DONE();      // one synchronisation for the six row writes
     // replay_buffer.py:70-75
     if (next_obs_idx < ts) { p->cur_len[a] = ts + 1; p->ts_cur[a] = 0; }
     else p->ts_cur[a] = ts + 1;
@@ -759,6 +773,36 @@ int spp_update_ring_device(spp_population* p, int G, uint64_t seed, float* losse
     return SPP_OK;
 }
 
+// Stage timeline of one update burst (agent 0): the kernel stamps %globaltimer at its kStageMarks stage boundaries; out_us
+// receives the mean duration of each of the kStageMarks - 1 intervals over the G steps, in microseconds.
+int spp_update_stage_profile(spp_population* p, int G, uint64_t seed, double* out_us, int cap, int* n_out) {
+    if (!p || !out_us) return fail(SPP_ERR_ARG, "null argument");
+    if (p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
+    if (G < 1 || cap < kStageMarks - 1) return fail(SPP_ERR_ARG, "G must be positive and cap >= 23");
+    for (int a = 0; a < p->P; ++a)
+        if (p->cur_len[a] < 1) return fail(SPP_ERR_STATE, "replay ring is empty");
+    CK(cudaSetDevice(p->device));
+    int rc = push_ring_len(p); if (rc) return rc;
+    const size_t n = (size_t)G * kStageMarks;
+    CK(p->d_tmp.ensure(n * sizeof(unsigned long long)));
+    UpdateArgs a;
+    fill_args(p, a, G);
+    a.seed = seed;
+    a.timing = (unsigned long long*)p->d_tmp.p;
+    CK(launch_update_burst(a, grid_for(p), p->stream));
+    g_launches++;
+    std::vector<unsigned long long> t(n);
+    CK(cudaMemcpyAsync(t.data(), p->d_tmp.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int i = 0; i + 1 < kStageMarks; ++i) {
+        double s = 0;
+        for (int g = 0; g < G; ++g) s += (double)(t[(size_t)g * kStageMarks + i + 1] - t[(size_t)g * kStageMarks + i]);
+        out_us[i] = s / G * 1e-3;
+    }
+    if (n_out) *n_out = kStageMarks - 1;
+    return SPP_OK;
+}
+
 // ---- ACM regression bursts --------------------------------------------------------------------------
 static void fill_acm_args(spp_population* p, UpdateArgs& a, int n) {
     fill_args(p, a, n);
@@ -861,6 +905,7 @@ static int prepare_rollout(spp_population* p, int E, RolloutArgs& r) {
 int spp_rollout_step_host(spp_population* p, int E, const float* obs, const float* noise, const float* eps, int random_phase,
                           double act_noise, int obs_norm, int denormalize_actor_out, float* out_target, float* out_action) {
     if (!p || !obs || !noise || !out_target || !out_action) return fail(SPP_ERR_ARG, "spp_rollout_step_host: null argument");
+    if (random_phase < 0 || random_phase > 2) return fail(SPP_ERR_ARG, "random_phase must be 0 (actor), 1 (lim * noise) or 2 (noise IS the state target)");
     CK(cudaSetDevice(p->device));
     RolloutArgs r;
     int rc = prepare_rollout(p, E, r); if (rc) return rc;
@@ -873,7 +918,7 @@ int spp_rollout_step_host(spp_population* p, int E, const float* obs, const floa
     if (eps) { CK(p->d_eps.ensure(n_ob * 4)); CK(cudaMemcpyAsync(p->d_eps.p, eps, n_ob * 4, cudaMemcpyHostToDevice, s)); }
     r.in_obs = (const float*)p->d_obs.p; r.in_noise = (const float*)p->d_nobs.p; r.in_eps = eps ? (const float*)p->d_eps.p : nullptr;
     r.out_target = (float*)p->d_act.p; r.out_action = (float*)p->d_aacm.p;
-    r.random_phase = random_phase ? 1 : 0; r.obs_norm = obs_norm ? 1 : 0; r.denormalize_out = denormalize_actor_out ? 1 : 0;
+    r.random_phase = random_phase; r.obs_norm = obs_norm ? 1 : 0; r.denormalize_out = denormalize_actor_out ? 1 : 0;
     r.act_noise = (float)act_noise;
     CK(launch_rollout(r, grid_for(p), s));
     g_launches++;

@@ -343,10 +343,20 @@ int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats) {   // (A - me
 }
 
 // ---- actor -----------------------------------------------------------------------------------------------
+// A rank of a data-parallel run may own NO row of a global minibatch (a short final minibatch, a small ppo_batch_size): its
+// contribution is a zero gradient vector and zero scalars -- it must still join the all-reduce and the Adam step.
+static int empty_minibatch(spp_ppo* p, int64_t n_global) {
+    PCK(cudaMemsetAsync(p->gbuf, 0, (size_t)(p->part_stride + PS_COUNT) * 4, p->stream));
+    p->b.n = 0;
+    p->b.n_mean = n_global > 0 ? n_global : 1;
+    return SPP_OK;
+}
+
 int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int64_t n_global) {
-    if (!p || !perm) return spp_set_error_(SPP_ERR_ARG, "null");
-    if (n < 1 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [1, max_batch_rows]");
+    if (!p || (!perm && n > 0)) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (n < 0 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [0, max_batch_rows]");
     PCK(cudaSetDevice(p->device));
+    if (n == 0) return empty_minibatch(p, n_global);
     for (int64_t i = 0; i < n; ++i) if (perm[i] < 0 || perm[i] >= p->d.N) return spp_set_error_(SPP_ERR_ARG, "permutation index out of range");
     PCK(cudaMemcpyAsync(p->dperm, perm, (size_t)n * 8, cudaMemcpyHostToDevice, p->stream));
     p->b.n = n;
@@ -359,9 +369,10 @@ int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int
 }
 
 int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int64_t n, int64_t n_global) {
-    if (!p || !perm_dev) return spp_set_error_(SPP_ERR_ARG, "null");
-    if (n < 1 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [1, max_batch_rows]");
+    if (!p || (!perm_dev && n > 0)) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (n < 0 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [0, max_batch_rows]");
     PCK(cudaSetDevice(p->device));
+    if (n == 0) return empty_minibatch(p, n_global);
     PCK(cudaMemcpyAsync(p->dperm, perm_dev, (size_t)n * 8, cudaMemcpyDeviceToDevice, p->stream));
     p->b.n = n;
     p->b.n_mean = n_global > 0 ? n_global : n;

@@ -141,6 +141,15 @@ __device__ inline void stage_actor_head_bwd(const Ctx& c) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// stage-boundary time stamp of agent 0 (profiling entry point spp_update_stage_profile; a null pointer in every other launch)
+__device__ __forceinline__ void stage_mark(const Ctx& c, int g, int i) {
+    if (c.a.timing && c.agent == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        c.a.timing[(size_t)g * kStageMarks + i] = t;
+    }
+}
+
 template <int ALGO>
 __device__ void update_step(const Ctx& c, int g) {
     const Layout& L = c.a.L;
@@ -152,6 +161,7 @@ __device__ void update_step(const Ctx& c, int g) {
     const int tcrit[2] = {NET_CRITIC_1_TARG, NET_CRITIC_2_TARG};
     float* ls = c.sm.small + kLossBase;
 
+    stage_mark(c, g, 0);
     // ---- bookkeeping
     if (threadIdx.x == 0) {
         if (ALGO == ALGO_SAC) c.sm.alpha = (float)exp(c.a.alpha_state[(size_t)c.agent * 4]);
@@ -162,20 +172,28 @@ __device__ void update_step(const Ctx& c, int g) {
     for (int i = threadIdx.x; i < 4 * 512; i += kThreads) __stcg(c.gvec(0) + i, 0.f);
     stage_gather(c, g);
     __syncthreads();
+    stage_mark(c, g, 1);
 
     // ---- Phase A: Q target (sac_acm.py:43-56 / ddpg_acm.py:113-121)
     actor_forward<ALGO>(c, S + L.s.xn, ALGO == ALGO_SAC ? NET_ACTOR : NET_ACTOR_TARG);
+    stage_mark(c, g, 2);
     if (ALGO == ALGO_SAC) stage_sample(c, g, 0); else stage_ddpg_post(c, 0);
     __syncthreads();
+    stage_mark(c, g, 3);
     if (L.acm_critic) acm_forward(c, S + L.s.xcp + L.ldo, L.ldc);
+    stage_mark(c, g, 4);
     critics_hidden(c, S + L.s.xcp, tcrit, ncrit, true);
+    stage_mark(c, g, 5);
     stage_qtarget(c, tcrit, ncrit);
     __syncthreads();
+    stage_mark(c, g, 6);
 
     // ---- Phase B: critic step(s) (sac_acm.py:117-131 / ddpg_acm.py:175-182), Polyak fused (sac.py:186-199)
     critics_hidden(c, S + L.s.xc, crit, ncrit, false);
+    stage_mark(c, g, 7);
     stage_critic_head_bwd<0>(c, crit, tcrit, ncrit, ls + LOSS_CRITIC_1);
     __syncthreads();
+    stage_mark(c, g, 8);
     for (int i = 0; i < ncrit; ++i) {   // dz1 = (dz2 W2) * relu'(hc1); column sums -> d b1
         const LayerDesc& l = L.critic.L[1];
         EpiMaskStore<MASK_RELU_BITS, true, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, c.gvec(GV_CB1_0 + i),
@@ -183,6 +201,7 @@ __device__ void update_step(const Ctx& c, int g) {
         gemm_big<true>(c, S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
     __syncthreads();
+    stage_mark(c, g, 9);
     for (int i = 0; i < ncrit; ++i) {
         float* net = c.net(crit[i]); float* nm = c.net_m(crit[i]); float* nv = c.net_v(crit[i]); float* tn = c.net(tcrit[i]);
         const AdamScalars as = c.sm.adam[1 + i];
@@ -200,15 +219,21 @@ __device__ void update_step(const Ctx& c, int g) {
         }
     }
     __syncthreads();
+    stage_mark(c, g, 10);
 
     // ---- Phase C: policy step against the updated critic(s) (sac_acm.py:133-145,60-87 / ddpg_acm.py:125-145,187-192)
     actor_forward<ALGO>(c, S + L.s.xo, NET_ACTOR);
+    stage_mark(c, g, 11);
     if (ALGO == ALGO_SAC) stage_sample(c, g, 1); else stage_ddpg_post(c, 1);
     __syncthreads();
+    stage_mark(c, g, 12);
     if (L.acm_critic) acm_forward(c, S + L.s.xcp + L.ldo, L.ldc);
+    stage_mark(c, g, 13);
     critics_hidden(c, S + L.s.xcp, crit, ncrit, true);
+    stage_mark(c, g, 14);
     stage_policy_head_bwd(c, crit, ncrit, ls + LOSS_PI);
     __syncthreads();
+    stage_mark(c, g, 15);
     for (int i = 0; i < ncrit; ++i) {
         const LayerDesc& l = L.critic.L[1];
         EpiMaskStore<MASK_RELU_BITS, false, false> epi{S + L.s.dz1[i], kHidden, S + L.s.hc1[i], kHidden, nullptr,
@@ -216,6 +241,7 @@ __device__ void update_step(const Ctx& c, int g) {
         gemm_big<true>(c, S + L.s.dz2[i], kHidden, c.net(crit[i]) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
     __syncthreads();
+    stage_mark(c, g, 16);
     {   // dxc = sum_i dz1[i] W1_i     [B x ldc]
         const LayerDesc& l = L.critic.L[0];
         EpiMaskStore<MASK_NONE, false, false> e0{S + L.s.dxc, L.ldc, nullptr, 0, nullptr};
@@ -226,8 +252,11 @@ __device__ void update_step(const Ctx& c, int g) {
         }
     }
     __syncthreads();
+    stage_mark(c, g, 17);
     if (L.acm_critic) acm_backward_dx(c);
+    stage_mark(c, g, 18);
     stage_actor_head_bwd<ALGO>(c);
+    stage_mark(c, g, 19);
     {   // dza2 = (dml Wheads) * relu'(ha2); column sums -> d b2
         const LayerDesc& l = L.actor.L[2];
         EpiMaskStore<MASK_RELU_BITS, true, false> epi{S + L.s.dza2, kHidden, S + L.s.ha2, kHidden, c.gvec(GV_AB2),
@@ -235,6 +264,7 @@ __device__ void update_step(const Ctx& c, int g) {
         gemm_big<true>(c, S + L.s.dml, L.ldh, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, L.heads, epi);
     }
     __syncthreads();
+    stage_mark(c, g, 20);
     {   // dza1 = (dza2 W2) * relu'(ha1); column sums -> d b1
         const LayerDesc& l = L.actor.L[1];
         EpiMaskStore<MASK_RELU_BITS, true, false> epi{S + L.s.dza1, kHidden, S + L.s.ha1, kHidden, c.gvec(GV_AB1),
@@ -242,6 +272,7 @@ __device__ void update_step(const Ctx& c, int g) {
         gemm_big<true>(c, S + L.s.dza2, kHidden, c.net(NET_ACTOR) + l.off_w, l.ld, B, kHidden, kHidden, epi);
     }
     __syncthreads();
+    stage_mark(c, g, 21);
     {
         float* net = c.net(NET_ACTOR); float* nm = c.net_m(NET_ACTOR); float* nv = c.net_v(NET_ACTOR);
         float* tn = (ALGO == ALGO_DDPG) ? c.net(NET_ACTOR_TARG) : nullptr;
@@ -269,9 +300,11 @@ __device__ void update_step(const Ctx& c, int g) {
         adam_vector(net + l0.off_b, nm + l0.off_b, nv + l0.off_b, PK ? tn + l0.off_b : nullptr, c.gvec(GV_AB1), kHidden, as, h.tau, h.one_minus_tau, true);
     }
     __syncthreads();
+    stage_mark(c, g, 22);
     if (threadIdx.x < LOSS_COUNT && c.a.losses)
         c.a.losses[((size_t)c.agent * c.a.G + g) * LOSS_COUNT + threadIdx.x] = ls[threadIdx.x];
     __syncthreads();
+    stage_mark(c, g, 23);
 }
 
 template <int ALGO>

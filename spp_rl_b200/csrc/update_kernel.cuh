@@ -69,10 +69,12 @@ struct UpdateArgs {
     int batch_row_stride;    // rows between consecutive steps in the staged batch / index arrays (0 = L.B)
     int acm_last_rows;       // ACM regression: rows of the final step when it is a partial batch (0 = full)
     int acm_eval;            // ACM regression: forward + loss only (calculate_validation_loss), no optimiser step
+    unsigned long long* timing;   // [G][kStageMarks] %globaltimer stamps of agent 0's stage boundaries (spp_update_stage_profile), or null
     int use_umma;            // GEMM path of the 256-wide products: 1 tcgen05 3-pass tf32 split (fp32-accurate, default), 0 FFMA tiles,
                              // 2 tcgen05 single tf32 pass (reduced-precision variant, stated tolerance 1e-2)
 };
 
+constexpr int kStageMarks = 24;
 enum { LOSS_CRITIC_1 = 0, LOSS_CRITIC_2 = 1, LOSS_ACTOR = 2, LOSS_PI = 3, LOSS_DIST = 4, LOSS_ALPHA = 5, LOSS_ALPHA_VALUE = 6, LOSS_COUNT = 8 };
 
 struct Smem {

@@ -7,6 +7,8 @@ dynamics; the MuJoCo names are SHAPE-ONLY synthetic stand-ins (unbounded observa
 Pass a real gym environment through the `env=` constructor argument of the algorithm classes to use one.
 """
 import math
+import os
+import warnings
 
 import numpy as np
 
@@ -88,9 +90,37 @@ class SyntheticControl:
 _SHAPES = {"Hopper-v2": (11, 3), "HalfCheetah-v2": (17, 6), "Walker2d-v2": (17, 6), "Ant-v2": (111, 8)}
 
 
-def make(name, seed=0):
+def _real_gym():
+    """The installed gym / gymnasium package, or None (the oracle's import shim under oracle/shims is not a simulator)."""
+    for mod in ("gym", "gymnasium"):
+        try:
+            g = __import__(mod)
+        except Exception:
+            continue
+        if getattr(g, "__spp_shim__", False) or "oracle/shims" in (getattr(g, "__file__", "") or "").replace(os.sep, "/"):
+            continue
+        return g
+    return None
+
+
+def make(name, seed=0, synthetic=None):
+    """gym.make(name) when a real gym is installed (rltoolkit/rl.py:45).  Without one: Pendulum-v0 is the classic-control dynamics
+    restated above; the MuJoCo names fall back to the SHAPE-ONLY SyntheticControl stand-in -- silently only on explicit opt-in
+    (synthetic=True or SPP_RL_SYNTHETIC_ENVS=1), otherwise with a RuntimeWarning, because returns measured on it mean nothing."""
+    if synthetic is None:
+        synthetic = os.environ.get("SPP_RL_SYNTHETIC_ENVS", "") == "1"
+    g = None if synthetic else _real_gym()
+    if g is not None:
+        try:
+            return g.make(name)
+        except Exception as e:      # e.g. mujoco-py missing: say so instead of silently training on fake dynamics
+            warnings.warn("gym.make(%r) failed (%s); falling back to the offline stand-in" % (name, e), RuntimeWarning, stacklevel=2)
     if name == "Pendulum-v0":
         return Pendulum(seed)
     if name in _SHAPES:
+        if not synthetic:
+            warnings.warn("no gym/MuJoCo in this environment: %r is a SHAPE-ONLY synthetic stand-in (SyntheticControl); returns are "
+                          "not comparable with the reference's.  Pass env=<gym env>, or opt in with synthetic=True / "
+                          "SPP_RL_SYNTHETIC_ENVS=1 to silence this warning." % (name,), RuntimeWarning, stacklevel=2)
         return SyntheticControl(*_SHAPES[name], seed=seed)
     raise KeyError("unknown environment %r (pass env=<gym env> to use a real one)" % (name,))

@@ -98,6 +98,7 @@ class PpoPolicy:
         logp, rew, done, end = _f32(logp), _f32(rew), _f32(done), _f32(end)
         ts = np.ascontiguousarray(traj_start, np.int64); tl = np.ascontiguousarray(traj_len, np.int64)
         self.N = obs.shape[0]
+        self.Ntot = int(global_rows) if global_rows else self.N
         check(self.lib.spp_ppo_load_rollout(self.h, self.N, _ptr(obs, C.c_float), _ptr(next_obs, C.c_float), _ptr(actions, C.c_float),
                                             _ptr(logp, C.c_float), _ptr(rew, C.c_float), _ptr(done, C.c_float), _ptr(end, C.c_float),
                                             _ptr(ts, C.c_int64), _ptr(tl, C.c_int64), int(ts.size), int(traj_stride), int(global_rows)))
@@ -205,7 +206,8 @@ class PpoPolicy:
                     tot += sc[0].double()
                     check(self.lib.spp_ppo_critic_apply(self.h))
         st.synchronize()
-        return float(tot.item())
+        # the reference's loss["critic"]: mean over the optimiser steps of 0.5 * SSE / N (a2c.py:208-216), N = the GLOBAL row count
+        return 0.5 * float(tot.item()) / (float(self.Ntot) * n_target_updates * n_updates_per_target)
 
     def actor_minibatch_dp(self, dist, perm_local, n_global, want_host=True):
         """One data-parallel actor minibatch; returns the 8 reduced scalars (host array, or a device tensor without any host
@@ -217,7 +219,8 @@ class PpoPolicy:
         with torch.cuda.stream(st):
             if torch.is_tensor(perm_local):      # local row ids already on the device (filtered there, under this stream)
                 p = perm_local.contiguous()
-                check(self.lib.spp_ppo_actor_minibatch_grad_device(self.h, C.c_void_p(p.data_ptr()), int(p.numel()), int(n_global)))
+                ptr = C.c_void_p(p.data_ptr()) if p.numel() else None      # a rank may own no row of this minibatch
+                check(self.lib.spp_ppo_actor_minibatch_grad_device(self.h, ptr, int(p.numel()), int(n_global)))
             else:
                 p = np.ascontiguousarray(perm_local, np.int64)
                 check(self.lib.spp_ppo_actor_minibatch_grad(self.h, _ptr(p, C.c_int64), int(p.size), int(n_global)))

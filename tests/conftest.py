@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("SPP_RL_SYNTHETIC_ENVS", "1")      # the suite opts in to the shape-only MuJoCo stand-ins (spp_rl_b200/envs.py)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

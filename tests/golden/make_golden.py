@@ -16,6 +16,9 @@ Fixtures written next to this file:
   ppo_walker.npz         PPO_AcM pieces on Walker2d shapes: critic fit, GAE, advantage normalisation, actor epochs
   acm_regress.npz        AcMTrainer.batch_update x3 (AcM and BasicAcM)
   acm_epochs.npz         AcMTrainer.update_acm x3 epochs (shuffle, partial last minibatch, StepLR) + validation loss
+  rollout_steps.npz      the frame-loop body under recorded noise: DDPG_AcM.noise_action / AcMOffPolicy.initial_act /
+                         process_action for SAC_AcM and DDPG_AcM (three limit / normalisation settings), deterministic test()
+                         actions, and Actor.act + AcMOnPolicyTrainer.process_action for PPO_AcM
 """
 import os
 import sys
@@ -309,10 +312,148 @@ def ppo_fixture():
     print("ppo_walker: N", N, "epochs", m.kl_div_updates_counter, "losses", out["actor_losses"])
 
 
+class _Recorder:
+    """Records the reference's random draws without changing them: rsample's _standard_normal, torch.randn and torch.normal
+    (Normal.sample) are wrapped; the torch.normal wrapper draws z itself and returns z * scale + loc, which is what ATen's
+    normal(Tensor, Tensor) computes (checked against the original under the same seed in rollout_fixture)."""
+
+    def __init__(self):
+        import torch.distributions.normal as dn
+        self.dn, self.log = dn, []
+        self.o_sn, self.o_randn, self.o_normal = dn._standard_normal, torch.randn, torch.normal
+
+    def __enter__(self):
+        def sn(shape, dtype, device):
+            z = self.o_sn(shape, dtype, device); self.log.append(("eps", z.clone())); return z
+
+        def randn(*a, **k):
+            z = self.o_randn(*a, **k); self.log.append(("randn", z.clone())); return z
+
+        def normal(loc, scale, *a, **k):
+            z = torch.empty(loc.shape).normal_(); self.log.append(("normal", z.clone())); return z * scale + loc
+        self.dn._standard_normal, torch.randn, torch.normal = sn, randn, normal
+        return self
+
+    def __exit__(self, *a):
+        self.dn._standard_normal, torch.randn, torch.normal = self.o_sn, self.o_randn, self.o_normal
+
+    def take(self, kind):
+        for i, (k, z) in enumerate(self.log):
+            if k == kind:
+                return self.log.pop(i)[1]
+        return None
+
+
+def rollout_fixture():
+    """Frame-loop body of the reference under recorded noise:
+    off-policy: replay_buffer.normalize -> initial_act | noise_action -> process_action (ddpg.py:202-207, off_policy.py:50-54,
+    89-106, ddpg_acm.py:40-50), one observation at a time as the reference does; on-policy: buffer.normalize -> Actor.act ->
+    process_action (a2c.py:165-167, basic_model.py:32-51, on_policy.py:34-53)."""
+    out = {}
+    E = 12
+    cases = [
+        # published SPP-SAC flags: min-max denormalisation, lim = 1
+        ("sac_hopper", rl.SAC_AcM, "Hopper-v2", dict(min_max_denormalize=True, denormalize_actor_out=True), "acm"),
+        # bounded observation space, no denormalisation: lim = obs.high = [1, 1, 8] (acm.py:102-108)
+        ("sac_pendulum", rl.SAC_AcM, "Pendulum-v0", dict(min_max_denormalize=False, denormalize_actor_out=False), "acm"),
+        # mean-std denormalisation: lim = 10; BasicAcM as in train/spp_ddpg_hcheetah.py
+        ("ddpg_hcheetah", rl.DDPG_AcM, "HalfCheetah-v2", dict(min_max_denormalize=False, denormalize_actor_out=True), "basic"),
+    ]
+    for ci, (name, cls, env, flags, kind) in enumerate(cases):
+        torch.manual_seed(100 + ci); np.random.seed(100 + ci)
+        m = cls(env_name=env, acm_pre_train_samples=100, acm_val_buffer_size=None, buffer_size=1000, tensorboard_dir=None,
+                log_dir=None, **flags)
+        ob, ac = m.ob_dim, m.ac_dim
+        algo = "sac" if cls is rl.SAC_AcM else "ddpg"
+        if kind == "basic":
+            m.acm = BasicAcM(2 * ob, ac, False)
+        s0 = init_state(algo, ob, ac, 40 + ci, kind, False)
+        if kind == "basic":
+            s0["acm.t"][:] = 0.7; s0["acm.t1"][:] = np.linspace(0.5, 1.5, ac)
+        nets = ["actor", "acm"]
+        load_nets(m, s0, nets)
+        mn, mx, mean, std = make_stats(ob, 3 + ci, flags["min_max_denormalize"])
+        for k, v in (("min_obs", mn), ("max_obs", mx), ("obs_mean", mean), ("obs_std", std)):
+            setattr(m.replay_buffer, k, torch.from_numpy(v))
+        rng = np.random.RandomState(5 + ci)
+        obs = (rng.rand(E, ob) * (mx - mn) + mn).astype(np.float32)
+        rec = {k: [] for k in ("eps", "noise", "target", "acm", "init_noise", "init_target", "init_acm", "det_target", "det_acm")}
+        for e in range(E):
+            o = m.replay_buffer.normalize(torch.from_numpy(obs[e:e + 1]))
+            with _Recorder() as r:
+                a = m.noise_action(o, m.act_noise)
+                rec["noise"].append(r.take("randn").numpy().reshape(-1))
+                z = r.take("eps")
+                if z is not None:
+                    rec["eps"].append(z.numpy().reshape(-1))
+            rec["target"].append(a.numpy().reshape(-1).copy())
+            rec["acm"].append(np.asarray(m.process_action(a, o)).reshape(-1).copy())
+            with _Recorder() as r:
+                a = m.initial_act(o)
+                rec["init_noise"].append(r.take("randn").numpy().reshape(-1))
+            rec["init_target"].append(a.numpy().reshape(-1).copy())
+            rec["init_acm"].append(np.asarray(m.process_action(a, o)).reshape(-1).copy())
+            a = m.noise_action(o, act_noise=0, deterministic=True)      # what test() does (ddpg.py:385-410)
+            rec["det_target"].append(a.numpy().reshape(-1).copy())
+            rec["det_acm"].append(np.asarray(m.process_action(a, o)).reshape(-1).copy())
+        out[name + ":obs"] = obs
+        for k, v in rec.items():
+            if v:
+                out[name + ":" + k] = np.array(v, np.float32)
+        out[name + ":actor_lim"] = np.broadcast_to(np.asarray(m.actor_ac_lim, np.float32), (ob,)).copy()
+        out[name + ":acm_lim"] = np.asarray(m.ac_lim, np.float32).reshape(-1)
+        out[name + ":act_noise"] = np.array(m.act_noise)
+        out[name + ":meta"] = np.array([ob, ac, 40 + ci, 3 + ci, int(flags["min_max_denormalize"]), int(flags["denormalize_actor_out"])])
+        print("rollout", name, "lim", out[name + ":actor_lim"][:3], "act_noise", m.act_noise, "target[0]", rec["target"][0][:3])
+
+    # torch.normal(loc, scale) == z * scale + loc with z = empty.normal_() under the same generator state (the recorder's claim)
+    loc, sc = torch.randn(1, 17), torch.rand(1, 17) + 0.1
+    torch.manual_seed(5); a = torch.normal(loc, sc)
+    torch.manual_seed(5); b = torch.empty(1, 17).normal_() * sc + loc
+    assert torch.equal(a, b)
+
+    # on-policy
+    torch.manual_seed(7); np.random.seed(7)
+    m = rl.PPO_AcM(env_name="Walker2d-v2", acm_pre_train_samples=100, acm_pre_train_epochs=1, iterations=1, batch_size=100,
+                   denormalize_actor_out=True, min_max_denormalize=True, custom_loss=0.1, obs_norm=True, tensorboard_dir=None,
+                   log_dir=None, acm_val_buffer_size=None)
+    ob, ac = m.ob_dim, m.ac_dim
+    mn, mx, mean, std = make_stats(ob, 9, True)
+    m.min_obs, m.max_obs = torch.from_numpy(mn), torch.from_numpy(mx)
+    m.replay_buffer.min_obs, m.replay_buffer.max_obs = m.min_obs, m.max_obs
+    buf = MemoryAcM(obs_mean=m.obs_mean, obs_std=m.obs_std, device=m.device, alpha=m.obs_norm_alpha, max_obs=m.max_obs,
+                    min_obs=m.min_obs, min_max_denormalize=m.min_max_denormalize)
+    m.buffer = buf
+    rng = np.random.RandomState(19)
+    obs = (rng.rand(E, ob) * (mx - mn) + mn).astype(np.float32)
+    rec = {k: [] for k in ("noise", "action", "logp", "acm")}
+    for e in range(E):
+        o = buf.normalize(torch.from_numpy(obs[e:e + 1]))
+        with _Recorder() as r:
+            a, lp = m.actor.act(o)
+            rec["noise"].append(r.take("normal").numpy().reshape(-1))
+        rec["action"].append(a.numpy().reshape(-1).copy()); rec["logp"].append(float(lp))
+        rec["acm"].append(np.asarray(m.process_action(a, o)).reshape(-1).copy())
+    out["ppo_walker:obs"] = obs
+    for k, v in rec.items():
+        out["ppo_walker:" + k] = np.array(v, np.float32)
+    for net in ("actor", "acm"):
+        for k, v in getattr(m, net).state_dict().items():
+            out["ppo_walker:" + net + "." + k] = v.detach().numpy().copy()
+    out["ppo_walker:min_obs"], out["ppo_walker:max_obs"] = mn, mx
+    out["ppo_walker:actor_lim"] = np.array(float(m.actor_ac_lim)); out["ppo_walker:acm_lim"] = m.ac_lim.numpy()
+    out["torch_version"] = np.array(torch.__version__)
+    np.savez_compressed(os.path.join(HERE, "rollout_steps.npz"), **out)
+    print("rollout_steps: ppo logp[0]", rec["logp"][0])
+
+
 if __name__ == "__main__":
+    if "--only-rollout" in sys.argv:
+        rollout_fixture(); sys.exit(0)
     sac_fixture()
     ddpg_fixture()
     ring_fixture()
     acm_regress_fixture()
     acm_epochs_fixture()
     ppo_fixture()
+    rollout_fixture()

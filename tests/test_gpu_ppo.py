@@ -149,7 +149,7 @@ def test_on_policy_rollout_step_matches_oracle():
     pop = Population(algo="sac", ob_dim=ob, ac_dim=ac, population=1, min_max_denormalize=True, update_batch_size=64)
     pop.set_norm_stats(mn, mx)
     pop.load_state_dict("acm", {k[4:]: v for k, v in acm0.items()})
-    tgt2, acm_action = pop.rollout_step(obs[None], action[None], None, random_phase=True, obs_norm=True, denormalize_actor_out=True)
+    tgt2, acm_action = pop.rollout_step(obs[None], action[None], None, random_phase=2, obs_norm=True, denormalize_actor_out=True)
     np.testing.assert_allclose(tgt2[0], target, rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(acm_action[0], acm_ref.numpy(), rtol=1e-5, atol=2e-6)
     pol.close(); pop.close()

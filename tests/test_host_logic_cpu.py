@@ -1,6 +1,7 @@
 """CPU: host-side mirrors that carry no arithmetic but decide WHICH rows and WHICH random numbers the device path sees --
 checked against torch's own DataLoader sampler and against the oracle's restatement of the reference's memory views."""
 import numpy as np
+import pytest
 import torch
 from torch.utils.data import DataLoader, RandomSampler, TensorDataset
 
@@ -76,3 +77,28 @@ def test_ppo_defaults_are_the_reference_config():
     assert PPO_DEFAULTS["actor_lr"] == 3e-3 and PPO_DEFAULTS["critic_lr"] == 3e-4 and PPO_DEFAULTS["ppo_batch_size"] == 1000
     assert PPO_DEFAULTS["kl_div_threshold"] == 0.15 and PPO_DEFAULTS["max_ppo_epochs"] == 50 and PPO_DEFAULTS["gae_lambda"] == 0.95
     assert "tau" not in PPO_DEFAULTS and "buffer_size" not in PPO_DEFAULTS
+
+
+def test_synthetic_environment_fallback_is_loud(monkeypatch):
+    """envs.make: without gym the MuJoCo names are shape-only stand-ins -- a RuntimeWarning unless the caller opted in."""
+    import warnings
+
+    from spp_rl_b200 import envs
+    monkeypatch.setattr(envs, "_real_gym", lambda: None)
+    monkeypatch.delenv("SPP_RL_SYNTHETIC_ENVS", raising=False)
+    with pytest.warns(RuntimeWarning, match="SHAPE-ONLY"):
+        e = envs.make("Hopper-v2")
+    assert e.observation_space.shape == (11,)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        envs.make("Hopper-v2", synthetic=True)
+        envs.make("Pendulum-v0")                      # faithful classic-control dynamics: no warning
+    with pytest.raises(KeyError):
+        envs.make("NoSuchEnv-v0")
+
+    class FakeGym:
+        @staticmethod
+        def make(name):
+            return ("real", name)
+    monkeypatch.setattr(envs, "_real_gym", lambda: FakeGym)
+    assert envs.make("Hopper-v2") == ("real", "Hopper-v2")      # a real gym wins over the stand-in

@@ -179,3 +179,57 @@ def test_ppo_pieces_match_reference():
     for k in g.files:
         if k.startswith("post:"):
             assert relnorm(s[k[5:]].numpy(), g[k]) < 2e-6, k
+
+
+# ---- frame-loop body (A11 / P1): the oracle against the reference's noise_action / initial_act / process_action / Actor.act
+ROLLOUT_CASES = [("sac_hopper", "sac", "acm"), ("sac_pendulum", "sac", "acm"), ("ddpg_hcheetah", "ddpg", "basic")]
+
+
+def rollout_case_inputs(g, name, algo, kind):
+    """state, NormStats, limits and flags of one case of tests/golden/rollout_steps.npz (shared with the -m gpu tests)."""
+    ob, ac, wseed, sseed, min_max, denorm = [int(x) for x in g[name + ":meta"]]
+    s0 = init_state(algo, ob, ac, wseed, kind, False)
+    if kind == "basic":
+        s0["acm.t"][:] = 0.7
+        s0["acm.t1"][:] = np.linspace(0.5, 1.5, ac)
+    mn, mx, mean, std = make_stats(ob, sseed, bool(min_max))
+    st = NormStats(bool(min_max), torch.from_numpy(mn), torch.from_numpy(mx), torch.from_numpy(mean), torch.from_numpy(std), obs_norm=False)
+    return s0, st, (mn, mx, mean, std), g[name + ":actor_lim"], g[name + ":acm_lim"], float(g[name + ":act_noise"]), bool(denorm)
+
+
+@pytest.mark.parametrize("name,algo,kind", ROLLOUT_CASES)
+def test_rollout_step_oracle_matches_reference(name, algo, kind):
+    from oracle import rollout as R
+    g = _load("rollout_steps.npz")
+    s0, st, _, lim, alim, act_noise, denorm = rollout_case_inputs(g, name, algo, kind)
+    s = oracle_state(s0, algo)
+    t = torch.from_numpy
+    obs = t(g[name + ":obs"])
+    eps = t(g[name + ":eps"]) if algo == "sac" else None
+    tgt, acm = R.off_policy_step(s, st, obs, t(g[name + ":noise"]), t(lim), t(alim), act_noise, algo=algo, eps=eps,
+                                 random_phase=False, denormalize_actor_out=denorm)
+    np.testing.assert_allclose(tgt.numpy(), g[name + ":target"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(acm.numpy(), g[name + ":acm"], rtol=1e-5, atol=1e-6)
+    tgt, acm = R.off_policy_step(s, st, obs, t(g[name + ":init_noise"]), t(lim), t(alim), act_noise, algo=algo, eps=eps,
+                                 random_phase=True, denormalize_actor_out=denorm)
+    np.testing.assert_allclose(tgt.numpy(), g[name + ":init_target"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(acm.numpy(), g[name + ":init_acm"], rtol=1e-5, atol=1e-6)
+    # test(): deterministic actor, no exploration noise (ddpg.py:385-410)
+    zero = torch.zeros_like(obs)
+    tgt, acm = R.off_policy_step(s, st, obs, zero, t(lim), t(alim), 0.0, algo=algo, eps=zero if algo == "sac" else None,
+                                 random_phase=False, denormalize_actor_out=denorm)
+    np.testing.assert_allclose(tgt.numpy(), g[name + ":det_target"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(acm.numpy(), g[name + ":det_acm"], rtol=1e-5, atol=1e-6)
+
+
+def test_on_policy_step_oracle_matches_reference():
+    from oracle import rollout as R
+    g = _load("rollout_steps.npz")
+    t = torch.from_numpy
+    s = {k[len("ppo_walker:"):]: t(g[k]) for k in g.files if k.startswith("ppo_walker:actor.") or k.startswith("ppo_walker:acm.")}
+    st = NormStats(True, t(g["ppo_walker:min_obs"]), t(g["ppo_walker:max_obs"]))
+    a, lp, acm = R.on_policy_step(s, st, t(g["ppo_walker:obs"]), t(g["ppo_walker:noise"]), float(g["ppo_walker:actor_lim"]),
+                                  t(g["ppo_walker:acm_lim"]))
+    np.testing.assert_allclose(a.numpy(), g["ppo_walker:action"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(lp.numpy(), g["ppo_walker:logp"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(acm.numpy(), g["ppo_walker:acm"], rtol=1e-5, atol=1e-6)
