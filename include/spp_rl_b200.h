@@ -227,6 +227,14 @@ int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int
 /* the same with the local row ids already on the DEVICE (produced on spp_ppo_stream()'s stream, e.g. by filtering the global
  * minibatch there): no host copy, no host-side range check -- the ids must lie in [0, local rows). */
 int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int64_t n, int64_t n_global);
+/* 1: the actor epochs are plain PPO.update_actor (rltoolkit/algorithms/ppo/ppo.py:152-192), what PPO_AcM falls back to when
+ * custom_loss == 0 (rltoolkit/acm/on_policy.py:88-98): no distance term, the log-prob is taken of the stored actions as they are,
+ * and losses[] = {actor, entropy, sum, 0} are the raw sums over minibatches (no division by the epoch count).  0 (default):
+ * PPO_AcM.update_actor_acm (on_policy.py:164-216). */
+/* advantages [N] handed in by the caller instead of spp_ppo_advantages (PPO.update_actor(advantages, buffer), ppo.py:152) */
+int spp_ppo_load_advantages(spp_ppo* p, const float* adv_host);
+int spp_ppo_adam_reset(spp_ppo* p, int net);      /* fresh Adam state of one net (a module assigned to model.actor / model.critic) */
+int spp_ppo_set_actor_mode(spp_ppo* p, int plain_ppo);
 int spp_ppo_actor_apply(spp_ppo* p);
 int spp_ppo_scalars(spp_ppo* p, float out[8]);
 /* Rollout step of A2C.collect_batch (rltoolkit/algorithms/a2c/a2c.py:165-167) for E observations at once:

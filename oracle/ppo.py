@@ -166,13 +166,16 @@ def advantages(state, norm_obs, norm_next_obs, reward, done, end, gamma, lam):
 
 def update_actor_acm(state, norm_obs, actions, next_obs, old_logp, adv_norm, perms, lim, lr,
                      epsilon, kl_threshold, max_epochs, batch_size, entropy_coef=0.0,
-                     custom_loss=0.0):
+                     custom_loss=0.0, plain=False):
     """PPO_AcM.update_actor_acm epoch loop, rltoolkit/acm/on_policy.py:164-216, with the shuffles
     injected (`perms[e]` replaces DataLoader(shuffle=True)'s torch.randperm of epoch e).
 
     Reproduces: the partial last minibatch is kept; KL is taken on the LAST minibatch only
     (quirk 16); the summed losses are divided by (i + 1) where i is the loop variable at exit --
     when the KL test breaks at the top of iteration i, that is one more than the epochs run.
+    plain=True: PPO.update_actor (rltoolkit/algorithms/ppo/ppo.py:152-192), what PPO_AcM.update_actor runs when custom_loss == 0
+    (on_policy.py:88-98): `actions` are the stored (normalised-space) actions, there is no distance term, and the loss sums
+    `actor`, `entropy`, `sum` (returned under "policy") are NOT divided by the epoch count.
     -> (losses, epochs_run, kl)"""
     N = norm_obs.shape[0]
     tot = {"actor": 0.0, "entropy": 0.0, "policy": 0.0, "dist": 0.0}
@@ -190,6 +193,7 @@ def update_actor_acm(state, norm_obs, actions, next_obs, old_logp, adv_norm, per
                 tot[k] += losses.get(k, 0.0)
         kl = kl_divergence(old_logp[idx], new_logp)
         epochs_run += 1
-    for k in tot:
-        tot[k] /= i + 1
+    if not plain:
+        for k in tot:
+            tot[k] /= i + 1
     return tot, epochs_run, kl

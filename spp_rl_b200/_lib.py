@@ -110,6 +110,9 @@ SIGNATURES = {
     "spp_ppo_actor_minibatch_grad": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64]),
     "spp_ppo_actor_minibatch_grad_device": (C.c_int, [_vp, C.c_void_p, C.c_int64, C.c_int64]),
     "spp_ppo_actor_apply": (C.c_int, [_vp]),
+    "spp_ppo_set_actor_mode": (C.c_int, [_vp, C.c_int]),
+    "spp_ppo_adam_reset": (C.c_int, [_vp, C.c_int]),
+    "spp_ppo_load_advantages": (C.c_int, [_vp, _f32p]),
     "spp_ppo_scalars": (C.c_int, [_vp, _f32p]),
     "spp_ppo_act": (C.c_int, [_vp, C.c_int64, _f32p, _f32p, C.c_int, _f32p, _f32p, _f32p]),
     "spp_ppo_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), _i32p, C.POINTER(_vp)]),

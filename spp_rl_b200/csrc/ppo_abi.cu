@@ -39,6 +39,7 @@ struct spp_ppo {
     int64_t* dperm = nullptr;
     int part_stride = 0;
     int step_actor = 0, step_critic = 0;
+    int plain_ppo = 0;          // 1: PPO.update_actor (custom_loss == 0): no distance term, log-prob of the stored actions as they are
     int64_t scratch_rows = 0;
     cudaStream_t stream = nullptr;
     std::vector<PTensor> tensors[2];
@@ -60,6 +61,7 @@ static void fill(const spp_ppo* p, PpoArgs& a, int64_t rows_for_chunks) {
     a.critic = p->critic; a.critic_m = p->critic_m; a.critic_v = p->critic_v;
     a.norm = p->norm; a.part = p->part; a.part_stride = p->part_stride; a.gbuf = p->gbuf; a.scal = p->scal; a.gscal = p->gscal;
     a.rows_per_cta = rows_per_cta(rows_for_chunks, p->grid);
+    if (p->plain_ppo) a.h.custom_loss = 0.f;
 }
 
 extern "C" {
@@ -222,6 +224,17 @@ int spp_ppo_adam_download(spp_ppo* p, int net, int t, float* exp_avg, float* exp
     return rc;
 }
 
+int spp_ppo_adam_reset(spp_ppo* p, int net) {      // fresh optimiser state (a new module assigned to model.actor / model.critic)
+    if (!p || net < 0 || net > 1) return spp_set_error_(SPP_ERR_ARG, "bad argument");
+    PCK(cudaSetDevice(p->device));
+    PCK(cudaStreamSynchronize(p->stream));
+    const size_t n = (size_t)pnet(p, net).size * 4;
+    PCK(cudaMemset(net == 0 ? p->actor_m : p->critic_m, 0, n));
+    PCK(cudaMemset(net == 0 ? p->actor_v : p->critic_v, 0, n));
+    if (net == 0) p->step_actor = 0; else p->step_critic = 0;
+    return SPP_OK;
+}
+
 int spp_ppo_load_rollout(spp_ppo* p, int64_t N, const float* obs, const float* next_obs, const float* actions, const float* logp,
                          const float* rew, const float* done, const float* end, const int64_t* traj_start, const int64_t* traj_len,
                          int n_traj, int64_t traj_stride, int64_t global_rows) {
@@ -315,6 +328,14 @@ int spp_ppo_advantages(spp_ppo* p, float* adv_host) {
     return SPP_OK;
 }
 
+int spp_ppo_load_advantages(spp_ppo* p, const float* adv_host) {      // advantages computed elsewhere (update_actor(advantages, buffer))
+    if (!p || !adv_host || p->d.N < 1) return spp_set_error_(SPP_ERR_ARG, "null argument or no rollout loaded");
+    PCK(cudaSetDevice(p->device));
+    PCK(cudaMemcpyAsync(p->d.adv, adv_host, (size_t)p->d.N * 4, cudaMemcpyHostToDevice, p->stream));
+    PCK(cudaStreamSynchronize(p->stream));
+    return SPP_OK;
+}
+
 int spp_ppo_adv_stats(spp_ppo* p, double out[3]) {       // local (n, sum, sum of squares) in fp64
     if (!p || !out) return spp_set_error_(SPP_ERR_ARG, "null");
     PCK(cudaSetDevice(p->device));
@@ -362,7 +383,7 @@ int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int
     p->b.n = n;
     p->b.n_mean = n_global > 0 ? n_global : n;      // the clipped loss is a mean over the GLOBAL minibatch in data-parallel runs
     PpoArgs a; fill(p, a, n);
-    PCK(launch_ppo_gather(a, p->dperm, p->cfg.norm_closs ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
     PCK(launch_ppo_reduce(a, p->grid, p->L.actor.size, p->stream)); spp_count_launch_();
     return SPP_OK;
@@ -377,7 +398,7 @@ int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int
     p->b.n = n;
     p->b.n_mean = n_global > 0 ? n_global : n;
     PpoArgs a; fill(p, a, n);
-    PCK(launch_ppo_gather(a, p->dperm, p->cfg.norm_closs ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
     PCK(launch_ppo_reduce(a, p->grid, p->L.actor.size, p->stream)); spp_count_launch_();
     return SPP_OK;
@@ -414,9 +435,9 @@ int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int b
             float ent = 0.f;
             for (int j = 0; j < ob; ++j) ent += 0.5f + 0.918938533204672741780329736406f + ls[j];
             const double actor_loss = (double)sc[PS_LOSS] / (double)n;
-            const double dist = p->h.custom_loss != 0.f ? (double)sc[PS_DIST] / ((double)n * ob) : 0.0;
+            const double dist = (p->h.custom_loss != 0.f && !p->plain_ppo) ? (double)sc[PS_DIST] / ((double)n * ob) : 0.0;
             tot[0] += actor_loss; tot[1] += ent; tot[3] += dist;
-            tot[2] += actor_loss - (double)p->h.entropy_coef * ent + (double)p->h.custom_loss * dist;
+            tot[2] += actor_loss - (double)p->h.entropy_coef * ent + (p->plain_ppo ? 0.0 : (double)p->h.custom_loss * dist);
             kl = (double)sc[PS_KL] / (double)n;
             last_n = n;
             rc = spp_ppo_actor_apply(p); if (rc) return rc;
@@ -425,7 +446,8 @@ int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int b
         ++ran;
     }
     // the reference divides by (i + 1) with i the loop variable at exit (one more than the epochs run after an early stop)
-    const double div = (double)((i < max_epochs ? i : max_epochs - 1) + 1);
+    // (PPO_AcM.update_actor_acm, on_policy.py:211-214); plain PPO.update_actor reports the raw sums (ppo.py:186-188)
+    const double div = p->plain_ppo ? 1.0 : (double)((i < max_epochs ? i : max_epochs - 1) + 1);
     if (losses) for (int k = 0; k < 4; ++k) losses[k] = (float)(tot[k] / div);
     if (epochs_run) *epochs_run = ran;
     if (last_kl) *last_kl = (float)kl;
@@ -457,6 +479,12 @@ int spp_ppo_grad_buffer(spp_ppo* p, void** dev_ptr, int* n_floats, void** scal_p
     if (dev_ptr) *dev_ptr = p->gbuf;
     if (n_floats) *n_floats = p->part_stride;
     if (scal_ptr) *scal_ptr = p->gscal;
+    return SPP_OK;
+}
+
+int spp_ppo_set_actor_mode(spp_ppo* p, int plain_ppo) {
+    if (!p || plain_ppo < 0 || plain_ppo > 1) return spp_set_error_(SPP_ERR_ARG, "bad argument");
+    p->plain_ppo = plain_ppo;
     return SPP_OK;
 }
 

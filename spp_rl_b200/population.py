@@ -140,6 +140,11 @@ class Population:
             out[name] = (m, v)
         return out, step.value
 
+    def adam_reset(self, net, agent=-1):
+        """fresh optimiser state for one net (what assigning a new module to model.<net> does in the reference)"""
+        nid = NET_NAMES[net] if isinstance(net, str) else net
+        check(self.lib.spp_adam_reset(self.h, int(agent), nid))
+
     def set_learning_rates(self, actor_lr=-1.0, critic_lr=-1.0, alpha_lr=-1.0, acm_lr=-1.0):
         check(self.lib.spp_set_learning_rates(self.h, float(actor_lr), float(critic_lr), float(alpha_lr), float(acm_lr)))
 

@@ -56,6 +56,7 @@ class PpoPolicy:
 
     def set_norm_stats(self, min_obs=None, max_obs=None, obs_mean=None, obs_std=None):
         arrs = [None if v is None else _f32(v) for v in (min_obs, max_obs, obs_mean, obs_std)]
+        self._stats = arrs
         check(self.lib.spp_ppo_set_norm_stats(self.h, *[_ptr(v, C.c_float) for v in arrs]))
 
     def tensor_list(self, net):
@@ -113,6 +114,19 @@ class PpoPolicy:
                                    _ptr(action, C.c_float), _ptr(logp, C.c_float), _ptr(target, C.c_float)))
         return action, logp, target
 
+    def act_normalized(self, norm_obs, noise, denormalize_actor_out=True):
+        """act() for observations that are normalised already (model.actor.act(buffer.normalize(obs)) in the notebook)."""
+        saved = getattr(self, "_stats", None)
+        try:
+            check(self.lib.spp_ppo_set_norm_stats(self.h, None, None, None, None))      # identity normalisation for this call
+            return self.act(norm_obs, noise, denormalize_actor_out)
+        finally:
+            if saved is not None:
+                self.set_norm_stats(*saved)
+
+    def adam_reset(self, net):
+        check(self.lib.spp_ppo_adam_reset(self.h, NETS[net]))
+
     # ------------------------------------------------------------------ single-GPU forms
     def update_critic(self, n_target_updates=10, n_updates_per_target=10):
         loss = C.c_float()
@@ -124,6 +138,12 @@ class PpoPolicy:
         check(self.lib.spp_ppo_advantages(self.h, _ptr(adv, C.c_float)))
         return adv
 
+    def load_advantages(self, adv):
+        a = _f32(adv).reshape(-1)
+        if a.size != self.N:
+            raise SppError("advantages must have one entry per loaded row")
+        check(self.lib.spp_ppo_load_advantages(self.h, _ptr(a, C.c_float)))
+
     def normalize_adv(self, global_stats=None):
         g = None if global_stats is None else np.ascontiguousarray(global_stats, np.float64)
         check(self.lib.spp_ppo_normalize_adv(self.h, _ptr(g, C.c_double)))
@@ -132,6 +152,10 @@ class PpoPolicy:
         out = (C.c_double * 3)()
         check(self.lib.spp_ppo_adv_stats(self.h, out))
         return np.array([out[0], out[1], out[2]])
+
+    def set_actor_mode(self, plain_ppo):
+        """plain_ppo=True: PPO.update_actor (custom_loss == 0, ppo.py:152-192) instead of PPO_AcM.update_actor_acm."""
+        check(self.lib.spp_ppo_set_actor_mode(self.h, int(bool(plain_ppo))))
 
     def update_actor(self, perms, batch_size, kl_threshold, max_epochs=None):
         perms = np.ascontiguousarray(perms, np.int64)

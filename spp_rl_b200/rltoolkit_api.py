@@ -266,14 +266,8 @@ class _OffPolicyAcM:
         self.stats_logger = _Frames()
         self.obs_mean, self.obs_std = torch.zeros(self.ob_dim), torch.ones(self.ob_dim)
         self.min_obs = self.max_obs = None
-        self._pop = Population(
-            algo=self.ALGO, ob_dim=self.ob_dim, ac_dim=self.ac_dim, population=1, device=device, acm_kind=acm_model,
-            acm_critic=self.acm_critic, norm_closs=self.norm_closs, min_max_denormalize=self.min_max_denormalize,
-            update_batch_size=self.update_batch_size, acm_batch_size=self.acm_batch_size, buffer_size=self.buffer_size,
-            store_actions=True, gamma=self.gamma, tau=self.tau, actor_lr=self.actor_lr, critic_lr=self.critic_lr,
-            alpha_lr=self.alpha_lr, acm_lr=self.acm_lr, custom_loss=float(self.custom_loss), alpha=self.alpha,
-            target_entropy=self.target_entropy)
-        self._pop.set_limits(np.broadcast_to(self.actor_ac_lim.numpy(), (self.ob_dim,)), self.ac_lim.numpy())
+        self._device_index = device
+        self._pop = self._make_population(acm_model)
         self.replay_buffer = ReplayRing(self._pop, 0, self.buffer_size, self.ob_dim, self.min_max_denormalize, self.obs_norm)
         self.acm_scheduler_epoch = 0
         self._init_weights()
@@ -284,7 +278,71 @@ class _OffPolicyAcM:
             self.loss["acm_val"] = 0.0
         self._cached_acm_action = None
 
+    def _make_population(self, acm_kind):
+        pop = Population(
+            algo=self.ALGO, ob_dim=self.ob_dim, ac_dim=self.ac_dim, population=1, device=self._device_index, acm_kind=acm_kind,
+            acm_critic=self.acm_critic, norm_closs=self.norm_closs, min_max_denormalize=self.min_max_denormalize,
+            update_batch_size=self.update_batch_size, acm_batch_size=self.acm_batch_size, buffer_size=self.buffer_size,
+            store_actions=True, gamma=self.gamma, tau=self.tau, actor_lr=self.actor_lr, critic_lr=self.critic_lr,
+            alpha_lr=self.alpha_lr, acm_lr=self.acm_lr, custom_loss=float(self.custom_loss), alpha=self.alpha,
+            target_entropy=self.target_entropy)
+        pop.set_limits(np.broadcast_to(self.actor_ac_lim.numpy(), (self.ob_dim,)), self.ac_lim.numpy())
+        return pop
+
     # ------------------------------------------------------------------ nets
+    NET_ATTRS = ("actor", "critic", "critic_1", "critic_2", "acm", "actor_targ", "critic_targ", "critic_1_targ", "critic_2_targ")
+
+    def __setattr__(self, name, value):
+        """`model.acm = BasicAcM(...)` (notebook cell 24), `model.actor = ...`: the reference's property setters take an nn.Module,
+        move it to the device and build a fresh optimiser (acm.py:176-183, ddpg.py:141-157, sac.py:116-136).  Here the module's
+        parameters are uploaded to the device path and the optimiser state of that net is reset; an ACM of the other kind
+        re-creates the device population.  Anything without a state_dict() is refused -- never silently detached."""
+        if name in self.NET_ATTRS and "_pop" in self.__dict__:
+            self._assign_net(name, value)
+        else:
+            object.__setattr__(self, name, value)
+
+    def _assign_net(self, name, module):
+        from .modules import acm_kind_of
+        if not hasattr(module, "state_dict"):
+            raise TypeError("model.%s needs a module with state_dict() (got %s); its parameters move to the device path" % (name, type(module).__name__))
+        sd = module.state_dict()
+        if name == "acm":
+            kind = acm_kind_of(sd, self.ob_dim, self.ac_dim)
+            if (kind == "basic") != (self._pop.cfg.acm_kind == 1):
+                self._rebuild_population(kind)
+            self._pop.load_state_dict("acm", sd)
+            self._pop.adam_reset("acm")
+            self.acm_scheduler_epoch = 0
+            self._pop.set_learning_rates(acm_lr=self.acm_lr)
+            return
+        if name not in self._net_names() and not name.endswith("_targ"):
+            raise AttributeError("%s has no net %r" % (type(self).__name__, name))
+        self._pop.load_state_dict(name, sd)
+        if not name.endswith("_targ"):
+            self._pop.adam_reset(name)
+            targ = name + "_targ"
+            if name.startswith("critic") or self.ALGO == "ddpg":      # the setters deep-copy the target (SAC has no actor target)
+                self._pop.load_state_dict(targ, sd)
+
+    def _rebuild_population(self, acm_kind):
+        """Same agent with the other kind of ACM: device memory is laid out per kind, so the population is created anew and every
+        other net, the temperature and the statistics are carried over.  Only before any transition is stored."""
+        if len(self.replay_buffer) > 0:
+            raise RuntimeError("assign model.acm before collecting data: the replay ring lives with the device population")
+        old = self._pop
+        nets = self._net_names()[:-1] + (["critic_1_targ", "critic_2_targ"] if self.ALGO == "sac" else ["actor_targ", "critic_targ"])
+        saved = {net: old.state_dict(net) for net in nets}
+        log_alpha = old.alpha(0)[0] if self.ALGO == "sac" else None
+        old.close()
+        object.__setattr__(self, "_pop", self._make_population(acm_kind))
+        for net, sd in saved.items():
+            self._pop.load_state_dict(net, sd)
+        if log_alpha is not None:
+            self._pop.set_log_alpha(log_alpha)
+        self.replay_buffer.pop = self._pop
+        self._push_stats()
+
     def _net_names(self):
         return ["actor", "critic_1", "critic_2", "acm"] if self.ALGO == "sac" else ["actor", "critic", "acm"]
 
@@ -298,7 +356,7 @@ class _OffPolicyAcM:
         self._pop.sync_targets()
 
     def __getattr__(self, name):
-        if name in ("actor", "critic", "critic_1", "critic_2", "acm", "actor_targ", "critic_targ", "critic_1_targ", "critic_2_targ"):
+        if name in self.NET_ATTRS and "_pop" in self.__dict__:
             return NetView(self.__dict__["_pop"], name)
         raise AttributeError(name)
 

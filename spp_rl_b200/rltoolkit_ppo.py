@@ -51,6 +51,16 @@ class _PolicyNetView:
     def train(self, mode=True):
         return self
 
+    def act(self, obs, deterministic=False):
+        """Actor.act (rltoolkit/basic_model.py:32-51) on already-normalised observations [E, ob] -> (action, log-prob); the noise is
+        the one standard-normal tensor Normal.sample draws from torch's global generator."""
+        if self._net != "actor":
+            raise AttributeError("critic has no act()")
+        o = torch.as_tensor(obs, dtype=torch.float32).reshape(-1, self._pol.ob_dim)
+        noise = torch.zeros_like(o) if deterministic else torch.empty_like(o).normal_()
+        action, logp, _ = self._pol.act_normalized(o.numpy(), noise.numpy())
+        return torch.from_numpy(action), torch.from_numpy(logp)
+
 
 class AcmReplayRing(ReplayRing):
     """ReplayBufferAcM surface (rltoolkit/buffer/replay_buffer.py:264-300) over the agent's device ring."""
@@ -68,7 +78,9 @@ class RolloutMemory:
     """MemoryAcM (rltoolkit/buffer/memory.py:130-315): one batch of full rollouts as a chain of observations (terminal
     observations included) plus per-timestep lists.  `_new_rollout_idx` holds the chain positions where a new rollout starts."""
 
-    def __init__(self, min_obs=None, max_obs=None, obs_mean=None, obs_std=None, min_max_denormalize=False):
+    def __init__(self, min_obs=None, max_obs=None, obs_mean=None, obs_std=None, min_max_denormalize=False, device=None, alpha=None):
+        # device / alpha: accepted for the notebook's MemoryAcM(obs_mean=..., device=..., alpha=..., ...) call (cell 44); the EMA
+        # statistics update they belong to (memory.py:283-302) is not on the SPP path (the replay ring's statistics are used)
         self._obs, self._actions, self._action_logprobs, self._rewards, self._done, self._end = [], [], [], [], [], []
         self._new_rollout_idx, self.actions_acm = [], []
         self.current_len = 0
@@ -124,7 +136,12 @@ class RolloutMemory:
         return torch.clamp((obs - self.obs_mean) / (self.obs_std + 1e-8), -MAX_ABS_OBS_VALUE, MAX_ABS_OBS_VALUE)
 
 
+MemoryAcM = RolloutMemory      # the reference's name (rltoolkit.buffer.MemoryAcM), as the notebook imports it
+
+
 class PPO_AcM:
+    NET_ATTRS = ("actor", "critic", "acm")
+
     def __init__(self, env=None, acm_model="acm", device=0, **kw):
         unknown = set(kw) - set(PPO_DEFAULTS) - {"log_all", "evals", "max_frames"}
         if unknown:
@@ -133,8 +150,6 @@ class PPO_AcM:
         c.update(kw)
         self.__dict__.update({k: c[k] for k in PPO_DEFAULTS})
         assert self.iterations > 0, "Iteration has to be positive not %r" % (self.iterations,)
-        if not self.custom_loss:
-            raise NotImplementedError("PPO_AcM with custom_loss = 0 falls back to plain PPO.update_actor, which is outside the SPP path")
         if not (self.min_max_denormalize and self.denormalize_actor_out):
             raise NotImplementedError("the device path covers the published SPP-PPO setting: min_max_denormalize=True, denormalize_actor_out=True")
         if self.acm_ob_idx is not None:
@@ -162,16 +177,14 @@ class PPO_AcM:
         self.min_obs = self.max_obs = None
         self.buffer = None
         self.buffer_size = int(self.acm_pre_train_samples * 1.1)      # acm.py:125-126
-        self._pop = Population(algo="ddpg", ob_dim=self.ob_dim, ac_dim=self.ac_dim, population=1, device=device, acm_kind=acm_model,
-                               acm_critic=True, norm_closs=self.norm_closs, min_max_denormalize=self.min_max_denormalize,
-                               update_batch_size=64, acm_batch_size=self.acm_batch_size, buffer_size=self.buffer_size,
-                               store_actions=False, acm_lr=self.acm_lr)
-        self._pop.set_limits(np.broadcast_to(self.actor_ac_lim.numpy(), (self.ob_dim,)), self.ac_lim.numpy())
+        self._device_index = device
+        self._pop = self._make_population(acm_model)
         self._pol = PpoPolicy(self.ob_dim, self.ac_dim, max_rows=self.batch_size + self.max_ep_len, max_batch_rows=self.ppo_batch_size,
                               device=device, min_max_denormalize=self.min_max_denormalize, norm_closs=self.norm_closs, gamma=self.gamma,
                               gae_lambda=self.gae_lambda, ppo_epsilon=self.ppo_epsilon, entropy_coef=self.entropy_coef,
                               custom_loss=float(self.custom_loss), actor_lr=self.actor_lr, critic_lr=self.critic_lr)
         self._pol.set_limits(self.actor_ac_lim.numpy())
+        self._pol.set_actor_mode(plain_ppo=not self.custom_loss)      # custom_loss == 0: PPO.update_actor (on_policy.py:88-98)
         self.replay_buffer = AcmReplayRing(self._pop, 0, self.buffer_size, self.ob_dim, self.min_max_denormalize, self.obs_norm)
         self.acm_scheduler_epoch = 0
         self._init_weights()
@@ -203,12 +216,47 @@ class PPO_AcM:
         s0 = init_state("ddpg", self.ob_dim, self.ac_dim, seed, kind, True)
         self._pop.load_state_dict("acm", {k[4:]: v for k, v in s0.items() if k.startswith("acm.")})
 
+    def _make_population(self, acm_kind):
+        pop = Population(algo="ddpg", ob_dim=self.ob_dim, ac_dim=self.ac_dim, population=1, device=self._device_index, acm_kind=acm_kind,
+                         acm_critic=True, norm_closs=self.norm_closs, min_max_denormalize=self.min_max_denormalize,
+                         update_batch_size=64, acm_batch_size=self.acm_batch_size, buffer_size=self.buffer_size,
+                         store_actions=False, acm_lr=self.acm_lr)
+        pop.set_limits(np.broadcast_to(self.actor_ac_lim.numpy(), (self.ob_dim,)), self.ac_lim.numpy())
+        return pop
+
     def __getattr__(self, name):
-        if name in ("actor", "critic"):
+        if name in ("actor", "critic") and "_pol" in self.__dict__:
             return _PolicyNetView(self.__dict__["_pol"], name)
-        if name == "acm":
+        if name == "acm" and "_pop" in self.__dict__:
             return NetView(self.__dict__["_pop"], "acm")
         raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        """`model.acm = BasicAcM(...)`, `model.actor = ...` as in the reference's property setters (acm.py:176-183, a2c.py): the module's
+        parameters move to the device path with a fresh optimiser state; objects without state_dict() are refused."""
+        if name in self.NET_ATTRS and "_pop" in self.__dict__ and "_pol" in self.__dict__:
+            if not hasattr(value, "state_dict"):
+                raise TypeError("model.%s needs a module with state_dict() (got %s)" % (name, type(value).__name__))
+            sd = value.state_dict()
+            if name == "acm":
+                from .modules import acm_kind_of
+                kind = acm_kind_of(sd, self.ob_dim, self.ac_dim)
+                if (kind == "basic") != (self._pop.cfg.acm_kind == 1):
+                    if len(self.replay_buffer) > 0:
+                        raise RuntimeError("assign model.acm before collecting data: the ACM replay ring lives with the device population")
+                    self._pop.close()
+                    object.__setattr__(self, "_pop", self._make_population(kind))
+                    self.replay_buffer.pop = self._pop
+                    self._push_stats()
+                self._pop.load_state_dict("acm", sd)
+                self._pop.adam_reset("acm")
+                self.acm_scheduler_epoch = 0
+                self._pop.set_learning_rates(acm_lr=self.acm_lr)
+            else:
+                self._pol.load_state_dict(name, sd)
+                self._pol.adam_reset(name)
+        else:
+            object.__setattr__(self, name, value)
 
     def _push_stats(self):
         mn = None if self.min_obs is None else self.min_obs.numpy()
@@ -258,6 +306,17 @@ class PPO_AcM:
                                                denormalize_actor_out=self.denormalize_actor_out)
         return torch.from_numpy(action), torch.from_numpy(logp), acm_action[0, 0]
 
+    def process_action(self, action, obs, *args, **kwargs):
+        """AcMOnPolicyTrainer.process_action (on_policy.py:34-53) as the notebook calls it: `obs` is ALREADY normalised by the caller
+        (buffer.normalize), `action` is the actor's output; the ACM sees cat[obs, denormalised action] (quirk 18)."""
+        a = torch.as_tensor(action, dtype=torch.float32).reshape(1, -1, self.ob_dim).numpy()
+        o = torch.as_tensor(obs, dtype=torch.float32).reshape(1, -1, self.ob_dim).numpy()
+        _, acm_action = self._pop.rollout_step(o, a, None, random_phase=2, obs_norm=False, denormalize_actor_out=self.denormalize_actor_out)
+        acm_action = acm_action[0, 0]
+        if self.buffer is not None:
+            self.buffer.add_acm_action(acm_action)
+        return acm_action
+
     def collect_batch(self, buffer):
         start = len(buffer)
         while len(buffer) < self.batch_size:                          # a2c.py:141-180
@@ -297,7 +356,10 @@ class PPO_AcM:
         return torch.from_numpy(self._pol.advantages())
 
     def update_actor(self, advantages, buffer):
-        self.update_actor_acm(advantages, buffer)                     # on_policy.py:88-98 (custom_loss != 0)
+        """on_policy.py:88-98: PPO_AcM.update_actor_acm when custom_loss != 0, otherwise plain PPO.update_actor (ppo.py:152-192) --
+        the same device epochs in the mode set at construction (spp_ppo_set_actor_mode); the plain form reports the loss sums
+        `actor`, `entropy`, `sum` without the division by the epoch count."""
+        self.update_actor_acm(advantages, buffer)
 
     def update_actor_acm(self, advantages, buffer):
         """PPO_AcM.update_actor_acm (on_policy.py:164-216); `advantages` are the ones update_critic left on the device."""
@@ -310,8 +372,10 @@ class PPO_AcM:
         torch.set_rng_state(state)                                    # the reference draws one sampler seed per epoch it actually runs
         for _ in range(2 * epochs):                                   # (DataLoader base seed + sampler seed) per epoch
             torch.empty((), dtype=torch.int64).random_()
-        self.loss.update({k: float(v) for k, v in losses.items()})
-        self.loss["entropy"] = float(losses["entropy"])
+        if self.custom_loss:
+            self.loss.update({k: float(v) for k, v in losses.items()})
+        else:
+            self.loss.update({"actor": float(losses["actor"]), "entropy": float(losses["entropy"]), "sum": float(losses["policy"])})
         self.kl_div_updates_counter += min(epochs + 1, self.max_ppo_epochs)      # the reference adds i + 1, i = loop index at exit
         self.last_kl = kl
 

@@ -19,6 +19,9 @@ Fixtures written next to this file:
   rollout_steps.npz      the frame-loop body under recorded noise: DDPG_AcM.noise_action / AcMOffPolicy.initial_act /
                          process_action for SAC_AcM and DDPG_AcM (three limit / normalisation settings), deterministic test()
                          actions, and Actor.act + AcMOnPolicyTrainer.process_action for PPO_AcM
+  ppo_plain.npz          plain PPO.update_actor (what PPO_AcM runs when custom_loss == 0, on_policy.py:88-98) on ppo_walker's rollout
+  pkl_actions.npz        notebooks/load_and_test.ipynb flow on each of the 9 trained models/*.pkl (copied to tests/golden/models/):
+                         construct with the notebook's flags, load(), deterministic action + ACM action on fixed observations
 """
 import os
 import sys
@@ -447,7 +450,110 @@ def rollout_fixture():
     print("rollout_steps: ppo logp[0]", rec["logp"][0])
 
 
+def ppo_plain_fixture():
+    """PPO_AcM(custom_loss=0).update_actor -> PPO.update_actor (ppo.py:152-192) on the rollout, advantages and pre-update actor of
+    ppo_walker.npz, with the same injected shuffles: post-update actor, the raw loss sums and the epoch counter."""
+    g = np.load(os.path.join(HERE, "ppo_walker.npz"))
+    hp = g["hp"]
+    torch.manual_seed(0); np.random.seed(0)
+    m = rl.PPO_AcM(env_name="Walker2d-v2", gamma=float(hp[0]), acm_pre_train_samples=100, acm_pre_train_epochs=1, iterations=1, batch_size=700,
+                   actor_lr=float(hp[6]), critic_lr=float(hp[7]), kl_div_threshold=float(hp[3]), max_ppo_epochs=int(hp[4]),
+                   ppo_batch_size=int(hp[5]), denormalize_actor_out=True, min_max_denormalize=True, custom_loss=0.0, obs_norm=True,
+                   tensorboard_dir=None, log_dir=None, acm_val_buffer_size=None, norm_closs=False)
+    m.actor.load_state_dict({k[len("pre:actor."):]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("pre:actor.")})
+    m.actor = m.actor      # optimiser on the loaded parameters
+    t = torch.from_numpy
+    buf = MemoryAcM(obs_mean=t(g["obs_mean"]), obs_std=t(g["obs_std"]), device=m.device, alpha=m.obs_norm_alpha, max_obs=t(g["max_obs"]),
+                    min_obs=t(g["min_obs"]), min_max_denormalize=True)
+    chain, joints = g["chain"], set(int(j) for j in g["joints"])
+    ts = 0
+    prev = buf.add_obs(t(chain[0:1]))
+    for i in range(1, len(chain)):
+        if i in joints:
+            buf.end_rollout()
+            prev = buf.add_obs(t(chain[i:i + 1]))
+            continue
+        nxt = buf.add_obs(t(chain[i:i + 1]))
+        buf.add_timestep(prev, nxt, t(g["actions"][ts:ts + 1]), t(g["logp"][ts:ts + 1]), float(g["rewards"][ts]), bool(g["done"][ts]), bool(g["end"][ts]))
+        prev = nxt; ts += 1
+    buf.end_rollout()
+    assert ts == len(g["actions"]) == len(buf)
+    perms = [t(p_) for p_ in g["perms"]]
+    calls = [0]
+    orig = torch.randperm
+
+    def fake(n, *a, **k):
+        calls[0] += 1
+        return perms[(calls[0] - 1) // 2]
+    torch.randperm = fake
+    c0 = m.kl_div_updates_counter
+    m.update_actor(t(g["adv"].copy()), buf)
+    torch.randperm = orig
+    out = {"epochs_counter": np.array(m.kl_div_updates_counter - c0),
+           "losses": np.array([m.loss["actor"], m.loss["entropy"], m.loss["sum"]], np.float64)}
+    for k, v in m.actor.state_dict().items():
+        out["post:actor." + k] = v.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "ppo_plain.npz"), **out)
+    print("ppo_plain: epochs counter", out["epochs_counter"], "losses", out["losses"])
+
+
+PKL_MODELS = [      # (file, class, env, BasicAcM?, norm_closs) -- the cells of notebooks/load_and_test.ipynb
+    ("hopper_sac_acm_model.pkl", "SAC_AcM", "Hopper-v2", False, False),
+    ("hcheetah_sac_acm_model.pkl", "SAC_AcM", "HalfCheetah-v2", False, False),
+    ("ant3m_sac_acm_model.pkl", "SAC_AcM", "Ant-v2", False, False),
+    ("hcheetah_ddpg_acm_model.pkl", "DDPG_AcM", "HalfCheetah-v2", True, False),
+    ("hopper_ddpg_acm_model.pkl", "DDPG_AcM", "Hopper-v2", True, False),
+    ("ant3m_ddpg_acm_model.pkl", "DDPG_AcM", "Ant-v2", True, False),
+    ("hcheetah_ppo_acm.pkl", "PPO_AcM", "HalfCheetah-v2", False, True),
+    ("hopper_ppo_acm.pkl", "PPO_AcM", "Hopper-v2", False, True),
+    ("walker_ppo_acm.pkl", "PPO_AcM", "Walker2d-v2", False, True),
+]
+
+
+def pkl_fixture():
+    """The notebook's load-and-act flow (notebooks/load_and_test.ipynb cells 2-8, 23-27, 42-46) on every shipped model, with
+    fixed observations instead of a MuJoCo episode: deterministic actor output and the ACM action that would go to the env."""
+    out = {}
+    E = 6
+    mdir = os.path.join(HERE, "models")
+    for fi, (fname, cls, env, basic, norm_closs) in enumerate(PKL_MODELS):
+        torch.manual_seed(0)
+        kw = dict(env_name=env, custom_loss=1, denormalize_actor_out=True, min_max_denormalize=True, norm_closs=norm_closs,
+                  tensorboard_dir=None, log_dir=None)
+        if cls != "PPO_AcM":
+            kw.update(acm_critic=True, buffer_size=1000)
+        m = getattr(rl, cls)(**kw)
+        if basic:
+            m.acm = BasicAcM(m.ob_dim * 2, m.ac_dim, False)
+        m.load(os.path.join(mdir, fname))
+        rng = np.random.RandomState(77 + fi)
+        mn, mx = m.min_obs.numpy(), m.max_obs.numpy()
+        obs = (rng.rand(E, m.ob_dim) * (mx - mn) + mn).astype(np.float32)
+        tg, aa = [], []
+        if cls == "PPO_AcM":
+            m.replay_buffer.min_obs, m.replay_buffer.max_obs = m.min_obs, m.max_obs
+            m.buffer = MemoryAcM(obs_mean=m.obs_mean, obs_std=m.obs_std, device=m.device, alpha=m.obs_norm_alpha, max_obs=m.max_obs,
+                                 min_obs=m.min_obs, min_max_denormalize=m.min_max_denormalize)
+            for e in range(E):
+                o = m.buffer.normalize(m.process_obs(obs[e]))
+                a, _ = m.actor.act(o, deterministic=True)
+                tg.append(a.numpy().reshape(-1).copy()); aa.append(np.asarray(m.process_action(a, o)).reshape(-1).copy())
+        else:
+            for e in range(E):
+                o = m.replay_buffer.normalize(m.process_obs(obs[e]))
+                a = m.noise_action(o, act_noise=0, deterministic=True)
+                tg.append(a.numpy().reshape(-1).copy()); aa.append(np.asarray(m.process_action(a, o)).reshape(-1).copy())
+        out[fname + ":obs"] = obs; out[fname + ":target"] = np.array(tg, np.float32); out[fname + ":acm"] = np.array(aa, np.float32)
+        print("pkl", fname, "ob", m.ob_dim, "ac", m.ac_dim, "target[0][:3]", tg[0][:3], "acm[0]", aa[0][:3])
+    out["torch_version"] = np.array(torch.__version__)
+    np.savez_compressed(os.path.join(HERE, "pkl_actions.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--only-ppo-plain" in sys.argv:
+        ppo_plain_fixture(); sys.exit(0)
+    if "--only-pkl" in sys.argv:
+        pkl_fixture(); sys.exit(0)
     if "--only-rollout" in sys.argv:
         rollout_fixture(); sys.exit(0)
     sac_fixture()
@@ -457,3 +563,5 @@ if __name__ == "__main__":
     acm_epochs_fixture()
     ppo_fixture()
     rollout_fixture()
+    ppo_plain_fixture()
+    pkl_fixture()

@@ -204,9 +204,11 @@ def test_ppo_acm_script_kwargs_pretrain_train_test_save_load(tmp_path):
     for net in ("actor", "critic", "acm"):
         a, b2 = getattr(m, net).state_dict(), getattr(m2, net).state_dict()
         assert list(a) == list(b2) and all(torch.equal(a[k], b2[k]) for k in a)
-    with pytest.raises(NotImplementedError):
-        PPO_AcM(env=_ShortEpisodes(), **dict(PPO_KW, custom_loss=0.0))
-    m.close(); m2.close()
+    m3 = PPO_AcM(env=_ShortEpisodes(), **dict(PPO_KW, custom_loss=0.0))      # P6: falls back to plain PPO.update_actor (on_policy.py:88-98)
+    m3.pre_train()
+    m3.train()
+    assert set(m3.loss) >= {"actor", "entropy", "sum", "critic"} and all(np.isfinite(v) for v in m3.loss.values())
+    m.close(); m2.close(); m3.close()
 
 
 def test_ppo_acm_iteration_equals_the_kernel_level_calls():

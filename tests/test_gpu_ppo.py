@@ -59,6 +59,35 @@ def test_ppo_update_matches_reference_fixture():
     pol.close()
 
 
+def test_plain_ppo_actor_epochs_match_reference_fixture():
+    """P6: custom_loss == 0 -> PPO.update_actor (ppo.py:152-192): no distance term, log-prob of the stored actions, raw loss sums."""
+    g, gp = np.load(os.path.join(G, "ppo_walker.npz")), np.load(os.path.join(G, "ppo_plain.npz"))
+    gamma, lam, eps_clip, kl_thr, max_ep, bs, a_lr, c_lr, ent, closs, ntu, nupt = [float(x) for x in g["hp"]]
+    ob, ac = g["chain"].shape[1], g["actions_acm"].shape[1]
+    oi, ni = P.chain_views(len(g["chain"]), list(g["joints"]))
+    obs, nobs = g["chain"][oi], g["chain"][ni]
+    N = obs.shape[0]
+    pol = PpoPolicy(ob, ac, max_rows=N, max_batch_rows=int(bs), min_max_denormalize=True, norm_closs=False, gamma=gamma, gae_lambda=lam,
+                    ppo_epsilon=eps_clip, entropy_coef=ent, custom_loss=0.0, actor_lr=a_lr, critic_lr=c_lr)
+    pol.set_actor_mode(plain_ppo=True)
+    pol.set_limits(float(g["actor_lim"]))
+    pol.set_norm_stats(g["min_obs"], g["max_obs"], g["obs_mean"], g["obs_std"])
+    for net in ("actor", "critic"):
+        pol.load_state_dict(net, {k[len("pre:" + net) + 1:]: g[k] for k in g.files if k.startswith("pre:" + net + ".")})
+    ts, tl = _trajectories(g["end"])
+    pol.load_rollout(obs, nobs, g["actions"], g["logp"], g["rewards"], g["done"], g["end"], ts, tl)
+    pol.load_advantages(g["adv"])
+    pol.normalize_adv()
+    losses, epochs, kl = pol.update_actor(g["perms"], int(bs), kl_thr, int(max_ep))
+    assert min(epochs + 1, int(max_ep)) == int(gp["epochs_counter"])
+    for key, r in zip(("actor", "entropy", "policy"), gp["losses"]):
+        assert losses[key] == pytest.approx(float(r), rel=2e-4), key
+    sd = pol.state_dict("actor")
+    for k, v in sd.items():
+        assert relnorm(v, gp["post:actor." + k]) < 2e-5, (k, relnorm(v, gp["post:actor." + k]))
+    pol.close()
+
+
 def test_ppo_step_major_large_batch_matches_oracle():
     """E environments x T steps in step-major order (row = t * E + e): GAE strides by E; several CTAs per phase."""
     ob, ac, E, T = 17, 6, 96, 40

@@ -233,3 +233,23 @@ def test_on_policy_step_oracle_matches_reference():
     np.testing.assert_allclose(a.numpy(), g["ppo_walker:action"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(lp.numpy(), g["ppo_walker:logp"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(acm.numpy(), g["ppo_walker:acm"], rtol=1e-5, atol=1e-6)
+
+
+def test_plain_ppo_actor_epochs_match_reference():
+    """P6: PPO_AcM(custom_loss=0).update_actor -> PPO.update_actor (ppo.py:152-192) on ppo_walker's rollout."""
+    g, gp = _load("ppo_walker.npz"), _load("ppo_plain.npz")
+    gamma, lam, eps_clip, kl_thr, max_ep, bs, a_lr, c_lr, ent, closs, ntu, nupt = [float(x) for x in g["hp"]]
+    st = NormStats(True, torch.from_numpy(g["min_obs"]), torch.from_numpy(g["max_obs"]))
+    chain = torch.from_numpy(g["chain"])
+    oi, _ = P.chain_views(len(chain), list(g["joints"]))
+    s = {k[4:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("pre:actor.")}
+    advn = P.normalize_adv(torch.from_numpy(g["adv"]))
+    tot, epochs, _ = P.update_actor_acm(s, normalize(st, chain[oi], True), torch.from_numpy(g["actions"]), None, torch.from_numpy(g["logp"]),
+                                        advn, [torch.from_numpy(p) for p in g["perms"]], float(g["actor_lim"]), a_lr, eps_clip, kl_thr,
+                                        int(max_ep), int(bs), ent, 0.0, plain=True)
+    assert min(epochs + 1, int(max_ep)) == int(gp["epochs_counter"])
+    for v, r in zip([tot["actor"], tot["entropy"], tot["policy"]], gp["losses"]):
+        assert v == pytest.approx(float(r), rel=1e-5)
+    for k in gp.files:
+        if k.startswith("post:"):
+            assert relnorm(s[k[5:]].numpy(), gp[k]) < 2e-6, k
