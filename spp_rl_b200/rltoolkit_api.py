@@ -93,6 +93,33 @@ class ReplayRing:
         self.obs_mean, self.obs_std = torch.zeros(ob_dim), torch.ones(ob_dim)
         self.min_obs = self.max_obs = None
         self.dtype = torch.float32
+        self._end = np.zeros(self.size, bool)          # host mirror of the end flags: last_rollout() walks them (replay_buffer.py:170-177)
+
+    def last_end(self, idx):
+        end = self._end[idx]
+        while not end:
+            idx -= 1
+            if idx < 0:
+                idx = self.current_len - 1
+            end = self._end[idx]
+        return idx
+
+    def last_rollout(self):
+        """BufferAcMOffPolicy.last_rollout (replay_buffer.py:335-383): walk back from the newest timestep to the last end flag, then
+        to the end flag before it; the rows in between come from the device ring in one gather."""
+        i = self.last_end(self.ts_idx - 1)
+        rows = []
+        next_end = False
+        while not next_end:
+            rows.insert(0, i)
+            i -= 1
+            if i < 0:
+                i = self.current_len - 1
+            next_end = self._end[i]
+        obs, nobs, act, rew, _, aacm = self.pop.ring_sample_batch(self.agent, np.asarray(rows, np.int64))
+        end = [bool(self._end[r]) for r in rows]
+        end[-1] = True                                                  # Memory.add_rollout (memory.py:262-263)
+        return LastRollout(np.concatenate([obs, nobs[-1:]]), act, list(rew), end, aacm)
 
     def __len__(self):
         return self.pop.ring_state(self.agent)[2]
@@ -115,6 +142,7 @@ class ReplayRing:
         self.pop.ring_add_acm_action(self.agent, np.asarray(acm_action, np.float32).reshape(-1))
 
     def add_timestep(self, obs_idx, next_obs_idx, action, rew, done, end):
+        self._end[self.ts_idx] = bool(end)
         self.pop.ring_add_timestep(self.agent, obs_idx, next_obs_idx, torch.as_tensor(action).cpu().numpy().reshape(-1), rew, done, end)
 
     def sample_batch(self, batch_size=64, device=None):
@@ -221,9 +249,55 @@ class ValidationRing:
 
 
 class _Frames:
+    """StatsLogger (rltoolkit/stats_logger.py:10-26): frame / rollout counters and the running return, an exponential moving
+    average (0.9) of the last finished rollout's return."""
+
     def __init__(self):
         self.frames = 0
         self.rollouts = 0
+        self.running_return = None
+        self.test_return = None
+        self.time_list = []
+        self.stats = []
+        self._alpha = 0.9
+
+    def calc_running_return(self, buffer):
+        new_mean_return = buffer.average_returns_per_rollout
+        if self.running_return is None:
+            self.running_return = new_mean_return
+        else:
+            self.running_return *= self._alpha
+            self.running_return += (1 - self._alpha) * new_mean_return
+        return self.running_return
+
+
+class LastRollout:
+    """What BufferAcMOffPolicy.last_rollout() hands to the stats logger (replay_buffer.py:335-383): the last FULL rollout of the
+    ring as a MemoryAcM -- observation chain (T + 1 rows), state-target actions, rewards, end flags, ACM actions."""
+
+    def __init__(self, obs, actions, rewards, end, actions_acm):
+        self.obs_chain, self.actions, self.rewards, self.end, self.actions_acm = obs, actions, rewards, end, actions_acm
+
+    def __len__(self):
+        return len(self.rewards)
+
+    @property
+    def returns_rollouts(self):                  # memory.py:203-212 (float32 accumulation, as numpy does there)
+        returns, ret = [], 0
+        for r, e in zip(self.rewards, self.end):
+            ret += r
+            if e:
+                returns.append(ret)
+                ret = 0
+        return np.array(returns)
+
+    @property
+    def rollouts_no(self):
+        return sum(self.end)
+
+    @property
+    def average_returns_per_rollout(self):
+        return sum(self.returns_rollouts) / self.rollouts_no
 
 
 class _OffPolicyAcM:
@@ -551,8 +625,9 @@ class _OffPolicyAcM:
         return buffer
 
     def perform_iteration(self):
-        self.collect_batch_and_train(self.batch_size)
+        self.collect_batch_and_train(self.batch_size)                 # ddpg.py:159-169
         self.replay_buffer = self.update_obs_mean_std(self.replay_buffer)
+        return self.replay_buffer.last_rollout()
 
     def collect_samples(self):
         collected = 0
@@ -583,11 +658,30 @@ class _OffPolicyAcM:
     def train(self, iterations=None):
         if iterations:
             self.iterations += iterations
+        import time
+        buffer = None
         while self.iteration < self.iterations:                       # rl.py:197-235
-            self.perform_iteration()
+            t0 = time.time()
+            buffer = self.perform_iteration()
+            self.stats_logger.time_list.append(time.time() - t0)
+            running_return = self.stats_logger.calc_running_return(buffer)
+            if self.return_done is not None and running_return >= self.return_done:
+                break
+            if self.iteration % self.stats_freq == 0:
+                self.logs_after_iteration(buffer)
             self.iteration += 1
             if self.max_frames is not None and self.max_frames < self.stats_logger.frames:
                 break
+        if buffer is not None:
+            self.logs_after_iteration(buffer, done=True)
+
+    def logs_after_iteration(self, buffer, done=False):
+        """rl.py:320-341 without the TensorBoard writer (observability is outside the hot path): the periodic test() and the
+        (iteration, running return) history."""
+        if self.test_episodes is not None:
+            self.stats_logger.test_return = self.test()
+        self.stats_logger.stats.append([self.iteration, self.stats_logger.running_return])
+        self.stats_logger.time_list = []
 
     def test(self, episodes=None):
         episodes = self.test_episodes if episodes is None else episodes

@@ -20,6 +20,8 @@ Fixtures written next to this file:
                          process_action for SAC_AcM and DDPG_AcM (three limit / normalisation settings), deterministic test()
                          actions, and Actor.act + AcMOnPolicyTrainer.process_action for PPO_AcM
   ppo_plain.npz          plain PPO.update_actor (what PPO_AcM runs when custom_loss == 0, on_policy.py:88-98) on ppo_walker's rollout
+  config1_pendulum.npz   BASELINE config 1: SAC_AcM on Pendulum-v0, pre_train() + train() for 400 frames from fixed weights and seeds:
+                         replay indices drawn, ring cursors / index arrays, observation chain, final weights, statistics, returns
   pkl_actions.npz        notebooks/load_and_test.ipynb flow on each of the 9 trained models/*.pkl (copied to tests/golden/models/):
                          construct with the notebook's flags, load(), deterministic action + ACM action on fixed observations
 """
@@ -497,6 +499,82 @@ def ppo_plain_fixture():
     print("ppo_plain: epochs counter", out["epochs_counter"], "losses", out["losses"])
 
 
+CONFIG1_KW = dict(env_name="Pendulum-v0", update_batch_size=256, acm_pre_train_samples=400, acm_pre_train_epochs=2, acm_val_buffer_size=None,
+                  buffer_size=5000, iterations=2, batch_size=200, grad_steps=10, update_freq=50, random_frames=100, acm_update_freq=100,
+                  acm_epochs=1, acm_batch_size=128, custom_loss=0.2, acm_critic=True, norm_closs=False, denormalize_actor_out=True,
+                  min_max_denormalize=True, gamma=0.99, stats_freq=1, verbose=0)
+
+
+def config1_fixture():
+    """SURVEY 8d config 1 (reference plumbing on CPU, checks the boundary end to end): the reference's own SAC_AcM(...).pre_train();
+    .train() on the Pendulum stub.  The mirror, started from the same weights under the same numpy / torch seeds, must draw the same
+    replay indices, leave the same ring cursors and index arrays, and end with the same weights to 1e-5."""
+    import time
+    torch.manual_seed(11); np.random.seed(11)
+    m = rl.SAC_AcM(tensorboard_dir=None, log_dir=None, **CONFIG1_KW)
+    out = {}
+    nets = ["actor", "critic_1", "critic_2", "acm"]
+    for net in nets:
+        for k, v in getattr(m, net).state_dict().items():
+            out["init:" + net + "." + k] = v.detach().numpy().copy()
+    # The reference's OWN sensitivity: the same run with ONE initial weight moved by one unit in the last place.  400 frames of closed
+    # loop (the actions drive the pendulum that produces the next observations) and 80 Adam steps amplify that; the mirror cannot be
+    # expected to track the reference more closely than the reference tracks itself, so the test bounds each tensor by
+    # max(1e-5, 4 x this).
+    torch.manual_seed(11); np.random.seed(11)
+    m2 = rl.SAC_AcM(tensorboard_dir=None, log_dir=None, **CONFIG1_KW)
+    for net in nets:
+        getattr(m2, net).load_state_dict(getattr(m, net).state_dict())
+    m2.critic_1_targ.load_state_dict(m.critic_1_targ.state_dict()); m2.critic_2_targ.load_state_dict(m.critic_2_targ.state_dict())
+    with torch.no_grad():
+        w = m2.actor.fc1.weight
+        w[0, 0] = torch.nextafter(w[0, 0], torch.tensor(float("inf")))
+    torch.manual_seed(12); np.random.seed(12)
+    m2.pre_train(); m2.train()
+    drawn = []
+    orig = np.random.randint
+
+    def rec(lo, hi=None, size=None, *a, **k):
+        r = orig(lo, hi, size, *a, **k)
+        drawn.append(np.concatenate([[hi, np.size(r)], np.ravel(r)]).astype(np.int64))
+        return r
+    torch.manual_seed(12); np.random.seed(12)
+    np.random.randint = rec
+    t0 = time.perf_counter()
+    m.pre_train()
+    t1 = time.perf_counter()
+    m.train()
+    t2 = time.perf_counter()
+    np.random.randint = orig
+    rb = m.replay_buffer
+    L = rb.current_len
+    out.update(obs_idx=np.array(rb.obs_idx), ts_idx=np.array(rb.ts_idx), current_len=np.array(L), ring_obs_idx=rb._obs_idx[:L].copy(),
+               ring_next_obs_idx=rb._next_obs_idx[:L].copy(), ring_obs=rb._obs[: rb.obs_idx].astype(np.float32), ring_rew=rb._rewards[:L].copy(),
+               ring_done=rb._done[:L].copy(), ring_aacm=rb._actions_acm[:L].astype(np.float32), ring_act=rb._actions[:L].astype(np.float32),
+               drawn=np.concatenate(drawn), n_draws=np.array(len(drawn)), frames=np.array(m.stats_logger.frames),
+               rollouts=np.array(m.stats_logger.rollouts), running_return=np.array(m.stats_logger.running_return),
+               alpha=np.array(m.alpha), min_obs=m.min_obs.numpy(), max_obs=m.max_obs.numpy(), obs_mean=m.obs_mean.numpy(), obs_std=m.obs_std.numpy(),
+               loss_keys=np.array(sorted(m.loss.keys())), loss_vals=np.array([m.loss[k] for k in sorted(m.loss.keys())], np.float64),
+               ref_seconds=np.array([t1 - t0, t2 - t1]))
+    from tests.parity_util import relnorm
+    worst = 0.0
+    for net in nets + ["critic_1_targ", "critic_2_targ"]:
+        for k, v in getattr(m, net).state_dict().items():
+            out["final:" + net + "." + k] = v.detach().numpy().copy()
+            e = relnorm(getattr(m2, net).state_dict()[k].numpy(), v.detach().numpy())
+            out["sens:" + net + "." + k] = np.array(e)
+            worst = max(worst, e)
+    rb2 = m2.replay_buffer
+    out["sens_obs"] = np.array(np.abs(rb2._obs[: rb.obs_idx] - rb._obs[: rb.obs_idx]).max())
+    out["sens_aacm"] = np.array(np.abs(rb2._actions_acm[:L] - rb._actions_acm[:L]).max())
+    out["sens_act"] = np.array(np.abs(rb2._actions[:L] - rb._actions[:L]).max())
+    print("config1: reference vs reference with one weight moved by 1 ulp: worst weight relnorm %.2e, obs %.2e, acm action %.2e, target %.2e"
+          % (worst, out["sens_obs"], out["sens_aacm"], out["sens_act"]))
+    np.savez_compressed(os.path.join(HERE, "config1_pendulum.npz"), **out)
+    print("config1: frames", m.stats_logger.frames, "len", L, "draws", len(drawn), "running_return", m.stats_logger.running_return,
+          "reference: pre_train %.2f s, train %.2f s = %.1f frames/s" % (t1 - t0, t2 - t1, m.stats_logger.frames / (t2 - t1)))
+
+
 PKL_MODELS = [      # (file, class, env, BasicAcM?, norm_closs) -- the cells of notebooks/load_and_test.ipynb
     ("hopper_sac_acm_model.pkl", "SAC_AcM", "Hopper-v2", False, False),
     ("hcheetah_sac_acm_model.pkl", "SAC_AcM", "HalfCheetah-v2", False, False),
@@ -550,6 +628,8 @@ def pkl_fixture():
 
 
 if __name__ == "__main__":
+    if "--only-config1" in sys.argv:
+        config1_fixture(); sys.exit(0)
     if "--only-ppo-plain" in sys.argv:
         ppo_plain_fixture(); sys.exit(0)
     if "--only-pkl" in sys.argv:
@@ -564,4 +644,5 @@ if __name__ == "__main__":
     ppo_fixture()
     rollout_fixture()
     ppo_plain_fixture()
+    config1_fixture()
     pkl_fixture()
