@@ -46,12 +46,42 @@ def flops_per_update(ob=OB, ac=AC, b=B, hidden=256, hm1=64, hm2=32):
 
 
 # ------------------------------------------------------------------------------------------- CPU side
-def _cpu_worker(args):
-    n_updates, seed = args
+# The CPU arm times the reference's OWN SAC_AcM.update (rltoolkit/acm/off_policy/sac_acm.py:89-162) when the reference package is
+# available -- oracle/_ref (copied byte for byte by oracle/build_ref.py; it travels to the GPU box) or /root/reference -- through
+# the import shims of oracle/ref_import.py; otherwise the oracle's plain-tensor port.  Parallel model = the reference's: one
+# single-thread run per host core (mp.Pool in train/spp_sac_hopper.py:115, torch.set_num_threads(1) in rltoolkit/evals.py:22-26).
+def _cpu_batch(seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    mn, mx = torch.tensor(MIN_OBS), torch.tensor(MAX_OBS)
+    obs = torch.rand(B, OB, generator=g) * (mx - mn) + mn
+    nobs = obs + 0.02 * torch.randn(B, OB, generator=g)
+    act = torch.randn(B, OB, generator=g)
+    rew = torch.randn(B, generator=g)
+    done = (torch.rand(B, generator=g) < 1e-3).to(torch.int8)
+    aacm = torch.tanh(torch.randn(B, AC, generator=g))
+    return obs, nobs, act, rew, done, aacm
+
+
+def _make_cpu_updater(kind, seed, threads):
+    """-> a closure running ONE SAC_AcM.update on a fixed B = 256 Hopper-shaped minibatch (fresh N(0,1) draws inside, as rsample does)."""
     import numpy as np
     import torch
 
-    torch.set_num_threads(1)          # rltoolkit/evals.py:22-26: one intra-op thread per run
+    torch.set_num_threads(threads)
+    obs, nobs, act, rew, done, aacm = _cpu_batch(seed)
+    if kind == "reference":
+        import tempfile
+
+        from oracle.ref_import import import_reference
+        rl = import_reference(scratch_dir=tempfile.mkdtemp(prefix="spp_ref_"))
+        torch.manual_seed(seed)
+        m = rl.SAC_AcM(env_name="Hopper-v2", update_batch_size=B, custom_loss=0.2, acm_critic=True, norm_closs=False,
+                       denormalize_actor_out=True, min_max_denormalize=True, acm_pre_train_samples=100, acm_val_buffer_size=None,
+                       buffer_size=1000, tensorboard_dir=None, log_dir=None, gamma=0.99, actor_lr=1e-3, critic_lr=1e-3, alpha_lr=1e-3,
+                       alpha=0.2, verbose=0)
+        m.replay_buffer.min_obs, m.replay_buffer.max_obs = torch.tensor(MIN_OBS), torch.tensor(MAX_OBS)
+        return lambda: m.update(obs, nobs, act, rew, done, aacm)
     from oracle import offpolicy as op
     from oracle.norm import NormStats
     from spp_rl_b200.init import init_state
@@ -61,35 +91,102 @@ def _cpu_worker(args):
     st = NormStats(True, torch.tensor(MIN_OBS), torch.tensor(MAX_OBS))
     hp = op.OffPolicyHP(gamma=0.99, custom_loss=0.2, norm_closs=False, acm_critic=True, target_entropy=-float(AC),
                         actor_lim=torch.ones(OB), acm_lim=torch.ones(AC))
-    g = torch.Generator().manual_seed(seed)
-    mn, mx = torch.tensor(MIN_OBS), torch.tensor(MAX_OBS)
-    obs = torch.rand(B, OB, generator=g) * (mx - mn) + mn
-    nobs = obs + 0.02 * torch.randn(B, OB, generator=g)
-    rew = torch.randn(B, generator=g)
-    done = (torch.rand(B, generator=g) < 1e-3).to(torch.int8)
-    aacm = torch.tanh(torch.randn(B, AC, generator=g))
-    alpha = None
-    for _ in range(3):
-        _, alpha = op.sac_acm_update(s, hp, st, obs, nobs, None, rew, done, aacm, torch.randn(B, OB, generator=g),
-                                     torch.randn(B, OB, generator=g), alpha)
-    t0 = time.perf_counter()
-    for _ in range(n_updates):
-        _, alpha = op.sac_acm_update(s, hp, st, obs, nobs, None, rew, done, aacm, torch.randn(B, OB, generator=g),
-                                     torch.randn(B, OB, generator=g), alpha)
-    return time.perf_counter() - t0
+    g = torch.Generator().manual_seed(seed + 1)
+    state = {"alpha": None}
+
+    def step():
+        _, state["alpha"] = op.sac_acm_update(s, hp, st, obs, nobs, None, rew, done, aacm, torch.randn(B, OB, generator=g),
+                                              torch.randn(B, OB, generator=g), state["alpha"])
+    return step
 
 
-def cpu_updates_per_sec(n_updates_per_core, cores):
-    """Mirror of the reference's parallel model: `cores` independent single-thread runs (mp.Pool)."""
-    import multiprocessing as mp
+def _cpu_worker_loop(conn, kind, seed, threads):
+    try:
+        step = _make_cpu_updater(kind, seed, threads)
+        for _ in range(3):
+            step()
+        conn.send(("ready", 0.0))
+        while True:
+            n = conn.recv()
+            if n <= 0:
+                break
+            t0 = time.perf_counter()
+            for _ in range(n):
+                step()
+            conn.send(("done", time.perf_counter() - t0))
+    except Exception as e:      # surfaced by CpuArm
+        conn.send(("error", repr(e)))
 
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        spans = pool.map(_cpu_worker, [(n_updates_per_core, 50 + i) for i in range(cores)])
-    wall = time.perf_counter() - t0
-    # throughput over the slowest worker's timed span (start-up and warm-up updates excluded)
-    return cores * n_updates_per_core / max(spans), wall
+
+def cpu_kind():
+    here = os.path.join(ROOT, "oracle", "_ref", "rltoolkit")
+    return "reference" if (os.path.isdir(here) or os.path.isdir("/root/reference/rltoolkit/rltoolkit")) else "port"
+
+
+class CpuArm:
+    """`procs` persistent worker processes (forked before any CUDA initialisation), each holding its own model; step(n) runs n
+    updates in every worker concurrently and returns the wall time of the slowest."""
+
+    def __init__(self, procs, threads=1, kind=None):
+        import multiprocessing as mp
+        self.kind = kind or cpu_kind()
+        ctx = mp.get_context("fork")
+        self.workers = []
+        for i in range(procs):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_worker_loop, args=(b, self.kind, 50 + i, threads), daemon=True)
+            p.start()
+            self.workers.append((p, a))
+        for _, c in self.workers:
+            tag, v = c.recv()
+            if tag != "ready":
+                self.close()
+                raise RuntimeError("CPU worker failed: %s" % (v,))
+
+    def step(self, n):
+        t0 = time.perf_counter()
+        for _, c in self.workers:
+            c.send(n)
+        spans = []
+        for _, c in self.workers:
+            tag, v = c.recv()
+            if tag != "done":
+                raise RuntimeError("CPU worker failed: %s" % (v,))
+            spans.append(v)
+        return time.perf_counter() - t0, max(spans)
+
+    def close(self):
+        for p, c in self.workers:
+            try:
+                c.send(0)
+            except Exception:
+                pass
+        for p, _ in self.workers:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
+
+
+def cpu_baseline_block(cores):
+    """cpu_baseline of the N = 1 line: a bounded sample (about 15-25 s of CPU work) of the same update on the box's host cores."""
+    kind = cpu_kind()
+    n = 60 if kind == "reference" else 40
+    arm = CpuArm(cores, 1, kind)
+    try:
+        wall, span = arm.step(n)
+    finally:
+        arm.close()
+    out = {"value": cores * n / span, "unit": "updates/s", "cores": cores, "kind": kind, "n_cores_host": os.cpu_count(),
+           "per_core": n / span,
+           "sample": "%d single-thread processes x %d updates of the same SAC Hopper B=256 update (+3 warm-up each), %s"
+                     % (cores, n, "the reference's own SAC_AcM.update from oracle/_ref" if kind == "reference" else "oracle port")}
+    one = CpuArm(1, cores, kind)      # SURVEY 8d: plus one run with all intra-op threads
+    try:
+        _, span1 = one.step(30)
+    finally:
+        one.close()
+    out["all_threads_one_process"] = {"value": 30 / span1, "unit": "updates/s", "threads": cores}
+    return out
 
 
 def host_cores():
@@ -146,21 +243,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- GPU side
+HOPPER_PKL = os.path.join(ROOT, "tests", "golden", "models", "hopper_sac_acm_model.pkl")
+
+
 def build_population(device, P, ring=RING):
+    """every agent starts from the reference's trained models/hopper_sac_acm_model.pkl (targets = copies of the
+    critics), observation statistics from the same pickle, custom_loss 0.2, acm_critic, min-max denormalisation, gamma 0.99,
+    lr 1e-3, tau 0.005, alpha 0.2; the rings are prefilled synthetically (obs ~ U(min_obs, max_obs), episodes of 1000)."""
+    import pickle
+
     import numpy as np
-    from spp_rl_b200 import Population, init_state
+    from spp_rl_b200 import Population
 
     pop = Population(algo="sac", ob_dim=OB, ac_dim=AC, population=P, device=device, acm_kind="acm", acm_critic=True,
                      norm_closs=False, min_max_denormalize=True, update_batch_size=B, buffer_size=ring,
                      store_actions=False, gamma=0.99, tau=0.005, actor_lr=1e-3, critic_lr=1e-3, alpha_lr=1e-3,
                      custom_loss=0.2, alpha=0.2, target_entropy=-float(AC))
     pop.set_limits(np.ones(OB, np.float32), np.ones(AC, np.float32))
-    pop.set_norm_stats(np.array(MIN_OBS, np.float32), np.array(MAX_OBS, np.float32))
-    nets = ["actor", "critic_1", "critic_2", "critic_1_targ", "critic_2_targ", "acm"]
-    for a in range(P):
-        s0 = init_state("sac", OB, AC, 1000 + a)
-        for net in nets:
-            pop.load_state_dict(net, {k[len(net) + 1:]: v for k, v in s0.items() if k.startswith(net + ".")}, agent=a)
+    with open(HOPPER_PKL, "rb") as f:
+        d = pickle.load(f)
+    pop.set_norm_stats(d["min_obs"].numpy(), d["max_obs"].numpy())
+    for net, src in (("actor", "actor"), ("critic_1", "critic_1"), ("critic_2", "critic_2"), ("critic_1_targ", "critic_1"),
+                     ("critic_2_targ", "critic_2"), ("acm", "acm")):
+        pop.load_state_dict(net, d[src])      # agent = -1: every agent
     pop.ring_fill_synthetic(seed=7, n=ring * 999 // 1000, episode_len=1000)
     return pop
 
@@ -190,26 +295,34 @@ def main():
     G = args.grad_steps
     RINGC = args.ring_capacity
 
-    # ------------------------------------------------------------------ reference arm (CPU oracle port)
+    # ------------------------------------------------------------------ reference arm: the reference's CPU implementation of the path
     if args.impl == "reference":
         if rank != 0:
             return
         cores = host_cores()
-        n = 40
-        ups, wall = 0.0, 0.0
-        vals = []
-        for _ in range(max(1, min(K, 3))):
-            v, wall = cpu_updates_per_sec(n, cores)
-            vals.append(v)
-        ups = statistics.median(vals)
+        kind = cpu_kind()
+        n = 20                      # updates per core and step: a bounded sample of the 7 400-update step of our arm
+        arm = CpuArm(cores, 1, kind)
+        try:
+            for _ in range(W):
+                arm.step(n)
+            t0 = time.perf_counter()
+            for _ in range(K):
+                arm.step(n)
+            total = time.perf_counter() - t0
+        finally:
+            arm.close()
+        ups = cores * n * K / total
+        sample = "%d single-thread processes x %d updates per step (%s), %d warm-up + %d timed steps" % (
+            cores, n, "rltoolkit SAC_AcM.update from oracle/_ref, unmodified" if kind == "reference" else "oracle port of SAC_AcM.update", W, K)
         line = {
             "impl": "reference", "metric": METRIC, "value": ups, "unit": "updates/s", "n_gpus": N, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * (148 * G) / ups, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "SPP-SAC Hopper shapes (ob 11, ac 3, hidden 256, B 256), CPU oracle port of "
-                                   "rltoolkit SAC_AcM.update, one single-thread run per host core (mp.Pool model)"},
-            "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
-                             "sample": "%d procs x %d updates (+3 warm-up), torch threads=1 each" % (cores, n)},
+            "config": {"workload": "SPP-SAC Hopper shapes (ob 11, ac 3, hidden 256, B 256): SAC_AcM.update on the host cores, one "
+                                   "single-thread run per core (the reference's mp.Pool model); one step = %d updates" % (cores * n),
+                       "updates_per_step": cores * n, "batch": B},
+            "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -219,11 +332,7 @@ def main():
     # ------------------------------------------------------------------ CPU baseline first (fork before CUDA init)
     cpu_base = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
-        cores = host_cores()
-        n = 40
-        v, _ = cpu_updates_per_sec(n, cores)
-        cpu_base = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port",
-                    "sample": "%d procs x %d updates of the same SAC Hopper B=256 update (+3 warm-up), torch threads=1 each" % (cores, n)}
+        cpu_base = cpu_baseline_block(host_cores())
 
     import numpy as np
     import torch
@@ -238,7 +347,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.pop("NCCL_DEBUG", None)      # NCCL prints its version banner to stdout at any debug level; rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     P = args.agents_per_gpu or sm_count
@@ -385,6 +493,26 @@ def main():
                               "h2d_bytes_per_step": int(3 * h_o.nbytes), "d2h_bytes_per_step": int(tgt.nbytes + act.nbytes),
                               "note": "spp_rollout_step_host: one vectorised noise_action + process_action call per step"}
 
+    # ---- the minibatch gather alone (A1), HBM side of sample_batch: population-wide, device-drawn indices, dense output
+    gather = None
+    if not args.no_rollout:
+        NB = 20
+        for _ in range(2):
+            gbytes = pop.ring_gather_bench(NB, seed=1, stream=sptr)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            g0.record(stream)
+            for k in range(K):
+                gbytes = pop.ring_gather_bench(NB, seed=2 + k, stream=sptr)
+            g1.record(stream)
+        barrier()
+        g_ms = g0.elapsed_time(g1) / K
+        gather = {"rows_per_launch": P * NB * B, "ms_per_launch": g_ms, "algorithmic_bytes_per_launch": gbytes,
+                  "algorithmic_gbs": gbytes / (g_ms * 1e-3) / 1e9, "rows_per_s": P * NB * B / (g_ms * 1e-3),
+                  "note": "ring_gather_bench_kernel: B*((2 ob + ac + 1)*4 + 1) bytes read and written per row + two 4-byte index "
+                          "words; random 44-byte rows of a %.1f GB ring, DRAM sectors moved per row are in profiles/" % (P * RINGC * 114 / 1e9)}
+
     if rank == 0:
         peaks = {}
         try:
@@ -404,8 +532,8 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6500.0)
         hbm = None if traffic is None else {"measured_traffic_gbs": traffic / kt / 1e9, "peak_gbs": hbm_peak, "frac": traffic / kt / 1e9 / hbm_peak,
-                                            "note": "ncu DRAM bytes per update x updates per launch / live kernel time: the kernel moves 4.3x its "
-                                                    "algorithmic bytes (DESIGN.md section 6) at a third of the copy bandwidth"}
+                                            "note": "traffic is a PROFILE CONSTANT, not measured in this run: ncu dram__bytes_read + write per update "
+                                                    "(profiles/traffic.json, one --set full capture of this kernel) x the updates of one launch here"}
         line = {
             "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world if world > 1 else N, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -422,7 +550,7 @@ def main():
                          "kernel": "update_burst_kernel<SAC>", "kernel_ms": statistics.mean(kern_ms),
                          "note": "256-wide GEMMs on tcgen05 kind::tf32, 3-pass hi/lo split with per-chunk fp32 drain (1e-5 parity); "
                                  "achieved counts algorithmic fp32 FLOPs (each is 3 tensor-core passes); peak is the dense bf16 figure"},
-            "rollout": rollout, "reduced_precision_variant": variant, "cpu_baseline": cpu_base, "clocks": clocks,
+            "rollout": rollout, "gather": gather, "reduced_precision_variant": variant, "cpu_baseline": cpu_base, "clocks": clocks,
         }
         if rollout is not None:
             rollout["roofline"]["peak"] = peak

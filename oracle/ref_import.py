@@ -1,15 +1,19 @@
-"""Import the UNMODIFIED reference (rltoolkit) in the build container -- ORACLE INFRASTRUCTURE.
+"""Import the UNMODIFIED reference (rltoolkit) -- ORACLE INFRASTRUCTURE.
 
-Only usable where /root/reference exists (this container, never the GPU box).  Used by
-tests/golden/make_golden.py to generate fixtures and by oracle validation scripts.  Installs
+From /root/reference where that exists (the build container: tests/golden/make_golden.py generates the fixtures from it), else
+from oracle/_ref (the byte-for-byte copy made by oracle/build_ref.py, which travels to the GPU box so that bench.py's CPU
+baseline can time the reference's own code there).  Installs
 the three shims SURVEY.md section 8c lists: a gym stub, a pyvirtualdisplay stub, and the removed
 `numpy.int` alias (rltoolkit/buffer/replay_buffer.py:29-30,106).
 """
 import os
 import sys
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference/rltoolkit"
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+if not os.path.isdir(os.path.join(REF_ROOT, "rltoolkit")):
+    REF_ROOT = os.path.join(_HERE, "_ref")
+_SHIMS = os.path.join(_HERE, "shims")
 
 
 def reference_available() -> bool:
