@@ -168,8 +168,9 @@ int spp_rollout_step_host(spp_population* p, int E, const float* obs, const floa
                           double act_noise, int obs_norm, int denormalize_actor_out, float* out_target, float* out_action);
 /* Device-resident rollout of a synthetic environment (MuJoCo is unavailable offline): `steps` consecutive vectorised
  * steps of E environments per agent, everything of the frame loop except the simulator -- actor, noise, clip,
- * denormalise, ACM, and the ring writes (obs row, timestep row, acm action, reward, done) -- in one launch. */
-int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t seed, double act_noise, void* stream);
+ * denormalise, ACM, and the ring writes (obs row, timestep row, acm action, reward, done) -- in one launch.
+ * random_phase 1: the frames before `random_frames` (ddpg.py:205-206): state target = actor_ac_lim * N(0,1), no actor pass. */
+int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t seed, double act_noise, int random_phase, void* stream);
 
 /* ---- SPP-PPO (PPO_AcM): one policy, 64-wide tanh nets (rltoolkit/basic_model.py:7-77), data-parallel over rows.
  * A `spp_ppo` holds the actor (+ log_scale) and critic, one on-policy batch of up to max_rows transitions and the
@@ -227,14 +228,25 @@ int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int
 /* the same with the local row ids already on the DEVICE (produced on spp_ppo_stream()'s stream, e.g. by filtering the global
  * minibatch there): no host copy, no host-side range check -- the ids must lie in [0, local rows). */
 int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int64_t n, int64_t n_global);
+/* advantages [N] handed in by the caller instead of spp_ppo_advantages (PPO.update_actor(advantages, buffer), ppo.py:152) */
+int spp_ppo_load_advantages(spp_ppo* p, const float* adv_host);
+int spp_ppo_adam_reset(spp_ppo* p, int net);      /* fresh Adam state of one net (a module assigned to model.actor / model.critic) */
 /* 1: the actor epochs are plain PPO.update_actor (rltoolkit/algorithms/ppo/ppo.py:152-192), what PPO_AcM falls back to when
  * custom_loss == 0 (rltoolkit/acm/on_policy.py:88-98): no distance term, the log-prob is taken of the stored actions as they are,
  * and losses[] = {actor, entropy, sum, 0} are the raw sums over minibatches (no division by the epoch count).  0 (default):
  * PPO_AcM.update_actor_acm (on_policy.py:164-216). */
-/* advantages [N] handed in by the caller instead of spp_ppo_advantages (PPO.update_actor(advantages, buffer), ppo.py:152) */
-int spp_ppo_load_advantages(spp_ppo* p, const float* adv_host);
-int spp_ppo_adam_reset(spp_ppo* p, int net);      /* fresh Adam state of one net (a module assigned to model.actor / model.critic) */
 int spp_ppo_set_actor_mode(spp_ppo* p, int plain_ppo);
+/* One epoch with the LOCAL row ids on the device: minibatch k = ids_dev[off[k], off[k+1]) (host offsets, nb + 1 of them; a rank may
+ * own none of a minibatch), n_global[k] = rows of minibatch k over all ranks (NULL = local).  No host synchronisation per step;
+ * log_host [nb][8 + pad4(ob)] = reduced scalars of every minibatch followed by log_scale as that minibatch saw it. */
+int spp_ppo_actor_epoch_device(spp_ppo* p, const int64_t* ids_dev, const int64_t* off, const int64_t* n_global, int nb, float* log_host);
+/* ---- data parallelism (config 4, one policy, environments shard over ranks): the reference has no distributed code;
+ *      here every optimiser step of spp_ppo_update_critic / spp_ppo_actor_epoch_device all-reduces the gradient vector together
+ *      with the 8 scalars (one NCCL collective over NVLink on the policy's stream), spp_ppo_normalize_adv all-reduces the fp64
+ *      advantage statistics.  id: 128 bytes from spp_comm_unique_id on rank 0, distributed by the caller (e.g. torch.distributed). */
+int spp_comm_unique_id(char out[128]);
+int spp_ppo_comm_init(spp_ppo* p, const char id[128], int rank, int world);
+int spp_ppo_comm_info(spp_ppo* p, int* world, int64_t* allreduces, int* nccl_version);
 int spp_ppo_actor_apply(spp_ppo* p);
 int spp_ppo_scalars(spp_ppo* p, float out[8]);
 /* Rollout step of A2C.collect_batch (rltoolkit/algorithms/a2c/a2c.py:165-167) for E observations at once:
@@ -244,6 +256,23 @@ int spp_ppo_scalars(spp_ppo* p, float out[8]);
  * for the ACM (spp_rollout_step_host with random_phase = 2, obs_norm = 1 and noise = action evaluates that ACM call). */
 int spp_ppo_act(spp_ppo* p, int64_t E, const float* obs, const float* noise, int denormalize_actor_out, float* action, float* logp,
                 float* target);
+/* The whole collect_batch loop on the device (rltoolkit/algorithms/a2c/a2c.py:144-184 + rltoolkit/acm/on_policy.py:34-53), vectorised
+ * over E synthetic environments (MuJoCo is unavailable offline) for T steps in ONE launch: normalise -> Actor.act -> denormalise ->
+ * ACM of `pop`'s agent (it sees cat[normalised obs, target], quirk 18) -> env.step -> the policy's [T][E] store (step-major rows,
+ * traj_stride = E: what spp_ppo_update_critic / spp_ppo_advantages / the actor epochs read), time-limit truncation at max_ep_len
+ * (a2c.py:168-171), `end` set at episode ends and at the last step of the batch.  The environments persist across calls
+ * (reset_envs = 1 restarts them).  noise_act / noise_env / noise_reset [T][E][ob] and u_done [T][E] are injected host tensors
+ * (parity tests); NULL draws from Philox(seed).  Replaces spp_ppo_load_rollout; asynchronous on the policy's stream. */
+int spp_ppo_rollout_synthetic(spp_ppo* p, spp_population* pop, int agent, int E, int T, int max_ep_len, double done_prob, uint64_t seed,
+                              int denormalize_actor_out, int reset_envs, const float* noise_act, const float* noise_env,
+                              const float* u_done, const float* noise_reset);
+/* one column of the loaded rows as a dense host array: "x", "xn", "act", "raw_obs", "raw_next" [N][ob]; "aacm" [N][ac];
+ * "logp", "rew", "done", "end", "adv", "v" [N] */
+int spp_ppo_store_download(spp_ppo* p, const char* name, float* host);
+/* ReplayBufferAcM.add_buffer (rltoolkit/buffer/replay_buffer.py:284-297) from the store a device rollout left in `store`: environment
+ * by environment, every trajectory cut into rollouts at its `end` flags, with the reference's behaviour at rollout joints (quirk 19)
+ * and the ring cursor state machine of add_obs / add_timestep (:56-75).  The host walks integers only; the rows move on the device. */
+int spp_ring_add_rollout_store(spp_population* p, int agent, spp_ppo* store);
 /* device pointers of the reduced gradient vector (n_floats) and the 8 scalar slots, for torch.distributed all_reduce */
 int spp_ppo_grad_buffer(spp_ppo* p, void** dev_ptr, int* n_floats, void** scal_ptr);
 

@@ -85,7 +85,7 @@ SIGNATURES = {
     "spp_acm_update_ring": (C.c_int, [_vp, C.c_int, _i64p, C.c_int, C.c_uint64, _f32p]),
     "spp_set_learning_rates": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "spp_rollout_step_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_double, C.c_int, C.c_int, _f32p, _f32p]),
-    "spp_rollout_synthetic_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_double, _vp]),
+    "spp_rollout_synthetic_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int, _vp]),
     "spp_ppo_create": (C.c_int, [C.POINTER(PpoConfig), C.c_int, C.POINTER(_vp)]),
     "spp_ppo_destroy": (C.c_int, [_vp]),
     "spp_ppo_sync": (C.c_int, [_vp]),
@@ -113,6 +113,14 @@ SIGNATURES = {
     "spp_ppo_set_actor_mode": (C.c_int, [_vp, C.c_int]),
     "spp_ppo_adam_reset": (C.c_int, [_vp, C.c_int]),
     "spp_ppo_load_advantages": (C.c_int, [_vp, _f32p]),
+    "spp_ppo_actor_epoch_device": (C.c_int, [_vp, C.c_void_p, _i64p, _i64p, C.c_int, _f32p]),
+    "spp_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "spp_ppo_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
+    "spp_ppo_comm_info": (C.c_int, [_vp, _i32p, _i64p, _i32p]),
+    "spp_ppo_rollout_synthetic": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int, C.c_int,
+                                             _f32p, _f32p, _f32p, _f32p]),
+    "spp_ppo_store_download": (C.c_int, [_vp, C.c_char_p, _f32p]),
+    "spp_ring_add_rollout_store": (C.c_int, [_vp, C.c_int, _vp]),
     "spp_ppo_scalars": (C.c_int, [_vp, _f32p]),
     "spp_ppo_act": (C.c_int, [_vp, C.c_int64, _f32p, _f32p, C.c_int, _f32p, _f32p, _f32p]),
     "spp_ppo_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), _i32p, C.POINTER(_vp)]),

@@ -141,6 +141,17 @@ static void build_tensor_maps(spp_population* p) {
 static inline int map_col(const LayerDesc& l, int c) { return (l.split > 0 && c >= l.split) ? pad4(l.split) + (c - l.split) : c; }
 
 // ------------------------------------------------------------------------------------------------
+#include "ppo_rollout.h"
+int spp_population_acm_view_(spp_population* p, int agent, spp::PopulationAcmView* out) {
+    if (!p || !out || agent < 0 || agent >= p->P) return fail(SPP_ERR_ARG, "bad population / agent");
+    const Layout& L = p->L;
+    out->device = p->device; out->ob = L.ob; out->ac = L.ac; out->lda = L.lda; out->ldo = L.ldo; out->acm_kind = L.acm_kind;
+    out->hm1 = L.hm1; out->hm2 = L.hm2; out->ldm1 = L.ldm1; out->ldm2 = L.ldm2; out->acm_desc = L.acm;
+    out->acm = p->params + (size_t)agent * L.params_size + L.net_off[NET_ACM];
+    out->acm_lim = p->acm_lim;
+    return SPP_OK;
+}
+
 extern "C" {
 
 int spp_abi_version(void) { return SPP_ABI_VERSION; }
@@ -521,6 +532,71 @@ int spp_ring_add_timestep(spp_population* p, int a, int64_t obs_idx, int64_t nex
     if (next_obs_idx < ts) { p->cur_len[a] = ts + 1; p->ts_cur[a] = 0; }
     else p->ts_cur[a] = ts + 1;
     p->cur_len[a] = p->ts_cur[a] > p->cur_len[a] ? p->ts_cur[a] : p->cur_len[a];
+    p->len_dirty = true;
+    return SPP_OK;
+}
+
+// ReplayBufferAcM.add_buffer (rltoolkit/buffer/replay_buffer.py:284-297) for the [T][E] store a device rollout left in `store`
+// (spp_ppo_rollout_synthetic): the store's trajectories are taken environment by environment, each cut into rollouts at its `end`
+// flags, as the chain of observations (terminal observations included) + one ACM action per transition that MemoryAcM would hold.
+// The loop below is the reference's, joint behaviour included (the first transition after a joint is skipped and the chain index
+// runs one ahead from there on) -- on integers only: it decides which store row ends up in which ring
+// slot under the cursor state machine of add_obs / add_timestep (:56-75), and one kernel then moves the rows on the device.
+int spp_ring_add_rollout_store(spp_population* p, int a, spp_ppo* store) {
+    int rc = ring_check(p, a); if (rc) return rc;
+    spp::PpoStoreView st;
+    rc = spp_ppo_store_view_(store, &st); if (rc) return rc;
+    const Layout& L = p->L;
+    if (st.device != p->device || st.ob != L.ob || st.lda != L.lda || st.ldo != L.ldo) return fail(SPP_ERR_ARG, "population and rollout store disagree (device / shapes)");
+    CK(cudaSetDevice(p->device));
+    const int E = st.E, T = st.T;
+    const int64_t N = (int64_t)E * T, S = p->S;
+    std::vector<float> end((size_t)N);
+    CK(cudaStreamSynchronize(st.stream));
+    CK(cudaMemcpy(end.data(), st.end, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    constexpr int64_t kNext = 1ll << 62;
+    std::vector<int64_t> chain; chain.reserve((size_t)N + N / 64 + E + 1);
+    std::vector<uint8_t> joint; joint.reserve(chain.capacity() + 1);
+    for (int e = 0; e < E; ++e)
+        for (int t = 0; t < T; ++t) {
+            const int64_t row = (int64_t)t * E + e;
+            chain.push_back(row); joint.push_back(0);
+            if (end[row] != 0.f || t == T - 1) { chain.push_back(row | kNext); joint.push_back(0); if (joint.size() < chain.capacity()) {} }
+        }
+    // joint[i] = 1 where a new rollout starts (position after every terminal observation)
+    joint.push_back(0);
+    for (size_t i = 0; i < chain.size(); ++i) if (chain[i] & kNext) joint[i + 1] = 1;
+    std::vector<int64_t> obs_src((size_t)S, -1), ts_src((size_t)S, -1);
+    std::vector<int32_t> ts_oidx((size_t)S, 0), ts_nidx((size_t)S, 0);
+    int64_t obs_cur = p->obs_cur[a], ts_cur = p->ts_cur[a], cur_len = p->cur_len[a];
+    auto add_obs = [&](int64_t src) { const int64_t i = obs_cur; obs_src[i] = src; obs_cur = (i + 1) % S; return i; };
+    size_t i = 0;
+    int64_t obs_idx = add_obs(chain[0]);
+    for (int64_t k = 0; k < N; ++k) {
+        ++i;
+        const int64_t next_idx = add_obs(chain[i]);
+        if (joint[i]) { ++i; continue; }
+        const int64_t ts = ts_cur;
+        ts_src[ts] = (k % T) * E + k / T;      // the k-th ACM action in environment-major order
+        ts_oidx[ts] = (int32_t)obs_idx; ts_nidx[ts] = (int32_t)next_idx;
+        if (next_idx < ts) { cur_len = ts + 1; ts_cur = 0; } else ts_cur = ts + 1;      // replay_buffer.py:70-75
+        cur_len = ts_cur > cur_len ? ts_cur : cur_len;
+        obs_idx = next_idx;
+    }
+    DevBuf d1, d2, d3, d4;
+    CK(d1.ensure((size_t)S * 8)); CK(d2.ensure((size_t)S * 8)); CK(d3.ensure((size_t)S * 4)); CK(d4.ensure((size_t)S * 4));
+    CK(cudaMemcpyAsync(d1.p, obs_src.data(), (size_t)S * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(d2.p, ts_src.data(), (size_t)S * 8, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(d3.p, ts_oidx.data(), (size_t)S * 4, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(d4.p, ts_nidx.data(), (size_t)S * 4, cudaMemcpyHostToDevice, p->stream));
+    const size_t base = (size_t)a * S;
+    CK(spp::launch_ring_add_store(p->r_obs + base * L.ldo, p->r_oidx + base, p->r_nidx + base, p->r_aacm + base * L.lda, p->r_rew + base,
+                                  p->r_done + base, p->r_end + base, S, L.ob, L.ac, L.ldo, L.lda, (const int64_t*)d1.p, (const int64_t*)d2.p,
+                                  (const int32_t*)d3.p, (const int32_t*)d4.p, st, p->stream));
+    g_launches++;
+    CK(cudaStreamSynchronize(p->stream));
+    d1.release(); d2.release(); d3.release(); d4.release();
+    p->obs_cur[a] = obs_cur; p->ts_cur[a] = ts_cur; p->cur_len[a] = cur_len;
     p->len_dirty = true;
     return SPP_OK;
 }
@@ -928,8 +1004,9 @@ int spp_rollout_step_host(spp_population* p, int E, const float* obs, const floa
     return SPP_OK;
 }
 
-int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t seed, double act_noise, void* stream) {
+int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t seed, double act_noise, int random_phase, void* stream) {
     if (!p) return fail(SPP_ERR_ARG, "null population");
+    if (random_phase < 0 || random_phase > 1) return fail(SPP_ERR_ARG, "random_phase must be 0 (actor + noise) or 1 (lim * N(0,1), frames < random_frames)");
     if (p->S <= 0) return fail(SPP_ERR_STATE, "no replay ring");
     if (steps < 1) return fail(SPP_ERR_ARG, "steps must be positive");
     if ((int64_t)(steps + 1) * E > p->S) return fail(SPP_ERR_ARG, "steps * E must fit the ring");
@@ -946,7 +1023,7 @@ int spp_rollout_synthetic_device(spp_population* p, int E, int steps, uint64_t s
     r.w_obs = p->r_obs; r.w_oidx = p->r_oidx; r.w_nidx = p->r_nidx; r.w_act = p->r_act; r.w_rew = p->r_rew;
     r.w_done = p->r_done; r.w_end = p->r_end; r.w_aacm = p->r_aacm;
     r.obs_cur = (const int64_t*)p->d_cur.p; r.ts_cur = r.obs_cur + p->P;
-    r.steps = steps; r.denormalize_out = 1; r.act_noise = (float)act_noise; r.u.seed = seed;
+    r.steps = steps; r.denormalize_out = 1; r.act_noise = (float)act_noise; r.u.seed = seed; r.random_phase = random_phase;
     CK(launch_rollout(r, grid_for(p), s));
     g_launches++;
     for (int a = 0; a < p->P; ++a) {   // host mirror of the cursors (no episode resets in the synthetic environment)

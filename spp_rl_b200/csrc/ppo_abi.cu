@@ -21,6 +21,51 @@ void spp_count_launch_();
             return spp_set_error_(SPP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+// ---- NCCL, bound at run time (dlopen): the library has no link-time dependency on it, so it loads on boxes without NCCL and
+//      re-uses the copy torch already mapped when it is called from a torch.distributed process.  Only the five entry points the
+//      data-parallel SPP-PPO path needs; enum values as in nccl.h (ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0).
+#include <dlfcn.h>
+namespace {
+struct NcclUniqueId { char internal[128]; };
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+    bool ok = false;
+    std::string err;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy already in the process (torch's), if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return api; }
+    api.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(ncclComm_t*, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    api.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    api.GetVersion = (int (*)(int*))dlsym(h, "ncclGetVersion");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    if (!api.ok) api.err = "libnccl.so.2 lacks an expected symbol";
+    return api;
+}
+}  // namespace
+#define NCK(expr)                                                                                       \
+    do {                                                                                                \
+        int r_ = (expr);                                                                                \
+        if (r_ != 0) return spp_set_error_(SPP_ERR_CUDA, std::string(#expr) + ": " + nccl().GetErrorString(r_)); \
+    } while (0)
+
+#include "ppo_rollout.h"
+
 struct PTensor { std::string name; int layer; int is_bias; int rows, cols; };
 
 struct spp_ppo {
@@ -39,6 +84,14 @@ struct spp_ppo {
     int64_t* dperm = nullptr;
     int part_stride = 0;
     int step_actor = 0, step_critic = 0;
+    ncclComm_t comm = nullptr;  // data-parallel runs (spp_ppo_comm_init): gradients + scalars are all-reduced inside the entry points
+    int rank = 0, world = 1;
+    int64_t n_allreduce = 0;    // collectives issued so far (reported by the benches)
+    float* slog = nullptr;      // [kLogSlots][PS_COUNT + ldo]: per-step scalars (+ log_scale) recorded on the device, read once per loop
+    // device rollout (spp_ppo_rollout_synthetic): persistent environment state and the extra store columns the ACM ring needs
+    float* env_state = nullptr; int* env_len = nullptr; int env_E = 0;
+    float* st_aacm = nullptr; float* st_raw_next = nullptr; int st_lda = 0;
+    int store_E = 0, store_T = 0;      // shape of the [T][E] store the last device rollout left (0: rows came from spp_ppo_load_rollout)
     int plain_ppo = 0;          // 1: PPO.update_actor (custom_loss == 0): no distance term, log-prob of the stored actions as they are
     int64_t scratch_rows = 0;
     cudaStream_t stream = nullptr;
@@ -46,6 +99,7 @@ struct spp_ppo {
     std::vector<void*> allocs;
 };
 
+constexpr int kLogSlots = 4096;
 static const NetDesc& pnet(const spp_ppo* p, int net) { return net == 0 ? p->L.actor : p->L.critic; }
 
 static int rows_per_cta(int64_t n, int grid) {
@@ -64,12 +118,22 @@ static void fill(const spp_ppo* p, PpoArgs& a, int64_t rows_for_chunks) {
     if (p->plain_ppo) a.h.custom_loss = 0.f;
 }
 
+int spp_ppo_store_view_(spp_ppo* p, PpoStoreView* out) {
+    if (!p || !out) return spp_set_error_(SPP_ERR_ARG, "null argument");
+    if (p->store_E < 1 || !p->st_aacm) return spp_set_error_(SPP_ERR_STATE, "the policy holds no device rollout (spp_ppo_rollout_synthetic)");
+    out->device = p->device; out->E = p->store_E; out->T = p->store_T; out->ob = p->L.ob; out->ldo = p->L.ldo; out->lda = p->st_lda;
+    out->raw_obs = p->raw; out->raw_next = p->st_raw_next; out->aacm = p->st_aacm; out->end = p->d.end; out->stream = p->stream;
+    return SPP_OK;
+}
+
 extern "C" {
 
 int spp_ppo_destroy(spp_ppo* p) {
     if (!p) return SPP_OK;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->comm) { nccl().CommDestroy(p->comm); p->comm = nullptr; }
+    for (void* q : {(void*)p->env_state, (void*)p->env_len, (void*)p->st_aacm, (void*)p->st_raw_next}) if (q) cudaFree(q);
     for (void* q : p->allocs) cudaFree(q);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -128,6 +192,7 @@ int spp_ppo_create(const spp_ppo_config* cfg, int device, spp_ppo** out) {
     PALLOC(p->scal, (size_t)p->grid * PS_COUNT * 4);
     PALLOC(p->dstats, (size_t)p->grid * 2 * 8);
     PALLOC(p->dperm, NB * 8);
+    PALLOC(p->slog, (size_t)kLogSlots * (PS_COUNT + ldo) * 4);
 #undef PALLOC
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { spp_ppo_destroy(p); return spp_set_error_(SPP_ERR_CUDA, "stream"); }
     auto lin = [](std::vector<PTensor>& v, const char* nm, int layer, int rows, int cols) {
@@ -247,6 +312,7 @@ int spp_ppo_load_rollout(spp_ppo* p, int64_t N, const float* obs, const float* n
     const int ob = p->L.ob, ldo = p->L.ldo;
     const int clamp = p->cfg.min_max_denormalize ? 0 : 1;
     p->d.N = N; p->d.Ntot = global_rows > 0 ? global_rows : N; p->d.n_traj = n_traj; p->d.traj_stride = traj_stride;
+    p->store_E = p->store_T = 0;
     // Memory.norm_obs / norm_next_obs (rltoolkit/buffer/memory.py:170-176): normalise once on the device
     PCK(cudaMemcpyAsync(p->raw, obs, (size_t)N * ob * 4, cudaMemcpyHostToDevice, s));
     PCK(launch_ppo_normalize_rows(p->raw, p->d.x, N, ob, ldo, p->norm, clamp, p->grid * 4, s));
@@ -262,6 +328,140 @@ int spp_ppo_load_rollout(spp_ppo* p, int64_t N, const float* obs, const float* n
     PCK(cudaMemcpyAsync(p->d.traj_len, traj_len, (size_t)n_traj * 8, cudaMemcpyHostToDevice, s));
     PCK(cudaStreamSynchronize(s));
     spp_count_launch_(); spp_count_launch_();
+    return SPP_OK;
+}
+
+// ---- data parallelism: one NCCL communicator per policy, collectives on the policy's own stream ----------
+int spp_comm_unique_id(char out[128]) {
+    if (!out) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (!nccl().ok) return spp_set_error_(SPP_ERR_UNSUPPORTED, nccl().err);
+    NcclUniqueId id;
+    NCK(nccl().GetUniqueId(&id));
+    memcpy(out, id.internal, 128);
+    return SPP_OK;
+}
+
+int spp_ppo_comm_init(spp_ppo* p, const char id_bytes[128], int rank, int world) {
+    if (!p || !id_bytes || world < 1 || rank < 0 || rank >= world) return spp_set_error_(SPP_ERR_ARG, "spp_ppo_comm_init: bad argument");
+    if (!nccl().ok) return spp_set_error_(SPP_ERR_UNSUPPORTED, nccl().err);
+    PCK(cudaSetDevice(p->device));
+    if (p->comm) { nccl().CommDestroy(p->comm); p->comm = nullptr; }
+    p->rank = rank; p->world = world;
+    if (world == 1) return SPP_OK;
+    NcclUniqueId id;
+    memcpy(id.internal, id_bytes, 128);
+    NCK(nccl().CommInitRank(&p->comm, world, id, rank));
+    // the first collective of a communicator sets up its channels (seconds): pay for it here, not inside the first optimiser step
+    PCK(cudaMemsetAsync(p->dstats, 0, 3 * sizeof(double), p->stream));
+    NCK(nccl().AllReduce(p->dstats, p->dstats, 3, 8 /* ncclFloat64 */, 0, p->comm, p->stream));
+    PCK(cudaStreamSynchronize(p->stream));
+    return SPP_OK;
+}
+
+int spp_ppo_comm_info(spp_ppo* p, int* world, int64_t* allreduces, int* nccl_version) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (world) *world = p->comm ? p->world : 1;
+    if (allreduces) *allreduces = p->n_allreduce;
+    if (nccl_version) { *nccl_version = 0; if (nccl().ok && nccl().GetVersion) nccl().GetVersion(nccl_version); }
+    return SPP_OK;
+}
+
+// gradient vector and the 8 reduced scalars sit in one buffer: ONE collective per optimiser step covers both
+static int allreduce_grads(spp_ppo* p) {
+    if (!p->comm) return SPP_OK;
+    NCK(nccl().AllReduce(p->gbuf, p->gbuf, (size_t)(p->part_stride + PS_COUNT), 7 /* ncclFloat32 */, 0 /* ncclSum */, p->comm, p->stream));
+    p->n_allreduce++;
+    return SPP_OK;
+}
+
+__global__ void ppo_record_kernel(const float* __restrict__ gscal, const float* __restrict__ log_scale, int ldo, float* __restrict__ slot) {
+    const int i = threadIdx.x;
+    if (i < PS_COUNT) slot[i] = gscal[i];
+    else if (i < PS_COUNT + ldo) slot[i] = log_scale ? log_scale[i - PS_COUNT] : 0.f;
+}
+static int record_step(spp_ppo* p, int slot, bool with_log_scale) {
+    ppo_record_kernel<<<1, 256, 0, p->stream>>>(p->gscal, with_log_scale ? p->actor + p->L.actor.L[3].off_w : nullptr, p->L.ldo,
+                                                p->slog + (size_t)slot * (PS_COUNT + p->L.ldo));
+    PCK(cudaGetLastError());
+    return SPP_OK;
+}
+
+// ---- device-resident rollout (P1): E vectorised synthetic environments x T steps into the [T][E] store --------------------------
+int spp_ppo_rollout_synthetic(spp_ppo* p, spp_population* pop, int agent, int E, int T, int max_ep_len, double done_prob, uint64_t seed,
+                              int denormalize_actor_out, int reset_envs, const float* noise_act, const float* noise_env,
+                              const float* u_done, const float* noise_reset) {
+    if (!p || !pop) return spp_set_error_(SPP_ERR_ARG, "spp_ppo_rollout_synthetic: null argument");
+    if (E < 1 || T < 1 || (int64_t)E * T > p->cap_rows) return spp_set_error_(SPP_ERR_ARG, "E * T outside [1, max_rows]");
+    if (max_ep_len < 1 || done_prob < 0.0 || done_prob > 1.0) return spp_set_error_(SPP_ERR_ARG, "bad max_ep_len / done_prob");
+    PopulationAcmView av;
+    int rc = spp_population_acm_view_(pop, agent, &av); if (rc) return rc;
+    if (av.device != p->device || av.ob != p->L.ob || av.ac != p->L.ac) return spp_set_error_(SPP_ERR_ARG, "population and policy disagree (device / shapes)");
+    PCK(cudaSetDevice(p->device));
+    cudaStream_t s = p->stream;
+    const int ldo = p->L.ldo, ob = p->L.ob;
+    const int64_t N = (int64_t)E * T;
+    if (p->env_E != E) {      // (re)create the environments
+        if (p->env_state) { cudaFree(p->env_state); cudaFree(p->env_len); p->env_state = nullptr; p->env_len = nullptr; }
+        PCK(cudaMalloc(&p->env_state, (size_t)E * ldo * 4)); PCK(cudaMalloc(&p->env_len, (size_t)E * 4));
+        p->env_E = E; reset_envs = 1;
+    }
+    if (reset_envs) { PCK(cudaMemsetAsync(p->env_state, 0, (size_t)E * ldo * 4, s)); PCK(cudaMemsetAsync(p->env_len, 0, (size_t)E * 4, s)); }
+    if (!p->st_aacm || p->st_lda != av.lda) {
+        if (p->st_aacm) { cudaFree(p->st_aacm); p->st_aacm = nullptr; }
+        if (!p->st_raw_next) PCK(cudaMalloc(&p->st_raw_next, (size_t)p->cap_rows * ldo * 4));
+        PCK(cudaMalloc(&p->st_aacm, (size_t)p->cap_rows * av.lda * 4));
+        p->st_lda = av.lda;
+    }
+    PpoRolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.L = p->L; a.actor = p->actor; a.norm = p->norm;
+    a.acm = av.acm; a.acm_desc = av.acm_desc; a.acm_kind = av.acm_kind; a.ac = av.ac; a.lda = av.lda; a.hm1 = av.hm1; a.hm2 = av.hm2;
+    a.ldm1 = av.ldm1; a.ldm2 = av.ldm2; a.acm_lim = av.acm_lim;
+    a.E = E; a.T = T; a.max_ep_len = max_ep_len; a.done_prob = (float)done_prob;
+    a.state = p->env_state; a.ep_len = p->env_len;
+    a.x = p->d.x; a.xn = p->d.xn; a.act = p->d.act; a.logp = p->d.logp; a.rew = p->d.rew; a.done = p->d.done; a.end = p->d.end;
+    a.aacm = p->st_aacm; a.raw_obs = p->raw; a.raw_next = p->st_raw_next;
+    a.seed = seed; a.denorm_out = denormalize_actor_out ? 1 : 0; a.clamp = p->cfg.min_max_denormalize ? 0 : 1;
+    float* tmp[4] = {nullptr, nullptr, nullptr, nullptr};
+    const float* src[4] = {noise_act, noise_env, u_done, noise_reset};
+    const size_t bytes[4] = {(size_t)N * ob * 4, (size_t)N * ob * 4, (size_t)N * 4, (size_t)N * ob * 4};
+    for (int i = 0; i < 4; ++i)
+        if (src[i]) { PCK(cudaMalloc(&tmp[i], bytes[i])); PCK(cudaMemcpyAsync(tmp[i], src[i], bytes[i], cudaMemcpyHostToDevice, s)); }
+    a.noise_act = tmp[0]; a.noise_env = tmp[1]; a.u_done = tmp[2]; a.noise_reset = tmp[3];
+    // trajectories of the store: environment e owns rows e, e + E, ... (T of them)
+    std::vector<int64_t> ts(E), tl(E, T);
+    for (int e = 0; e < E; ++e) ts[e] = e;
+    PCK(cudaMemcpyAsync(p->d.traj_start, ts.data(), (size_t)E * 8, cudaMemcpyHostToDevice, s));
+    PCK(cudaMemcpyAsync(p->d.traj_len, tl.data(), (size_t)E * 8, cudaMemcpyHostToDevice, s));
+    PCK(cudaStreamSynchronize(s));      // ts / tl are host temporaries
+    PCK(launch_ppo_rollout(a, s)); spp_count_launch_();
+    p->d.N = N; p->d.Ntot = N; p->d.n_traj = E; p->d.traj_stride = E;
+    p->store_E = E; p->store_T = T;
+    bool any = false;
+    for (int i = 0; i < 4; ++i) any = any || tmp[i];
+    if (any) { PCK(cudaStreamSynchronize(s)); for (int i = 0; i < 4; ++i) if (tmp[i]) cudaFree(tmp[i]); }
+    return SPP_OK;
+}
+
+// one column of the store as the reference's Memory would hold it: [N][ob] ("x", "xn", "act", "raw_obs", "raw_next"), [N][ac] ("aacm"),
+// [N] ("logp", "rew", "done", "end", "adv", "v")
+int spp_ppo_store_download(spp_ppo* p, const char* name, float* host) {
+    if (!p || !name || !host) return spp_set_error_(SPP_ERR_ARG, "null argument");
+    if (p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
+    PCK(cudaSetDevice(p->device));
+    PCK(cudaStreamSynchronize(p->stream));
+    const std::string n(name);
+    const int64_t N = p->d.N;
+    const int ob = p->L.ob, ldo = p->L.ldo;
+    const float* m = nullptr; int w = 0, ld = 0;
+    if (n == "x") { m = p->d.x; w = ob; ld = ldo; } else if (n == "xn") { m = p->d.xn; w = ob; ld = ldo; }
+    else if (n == "act") { m = p->d.act; w = ob; ld = ldo; } else if (n == "raw_obs") { m = p->raw; w = ob; ld = ldo; }
+    else if (n == "raw_next") { m = p->st_raw_next; w = ob; ld = ldo; } else if (n == "aacm") { m = p->st_aacm; w = p->L.ac; ld = p->st_lda; }
+    else if (n == "logp") { m = p->d.logp; w = 1; ld = 1; } else if (n == "rew") { m = p->d.rew; w = 1; ld = 1; }
+    else if (n == "done") { m = p->d.done; w = 1; ld = 1; } else if (n == "end") { m = p->d.end; w = 1; ld = 1; }
+    else if (n == "adv") { m = p->d.adv; w = 1; ld = 1; } else if (n == "v") { m = p->d.v; w = 1; ld = 1; }
+    if (!m) return spp_set_error_(SPP_ERR_ARG, "unknown (or not yet produced) store column: " + n);
+    PCK(cudaMemcpy2D(host, (size_t)w * 4, m, (size_t)ld * 4, (size_t)w * 4, N, cudaMemcpyDeviceToHost));
     return SPP_OK;
 }
 
@@ -301,18 +501,26 @@ int spp_ppo_scalars(spp_ppo* p, float out[8]) {
 
 int spp_ppo_update_critic(spp_ppo* p, int n_target_updates, int n_updates_per_target, float* mean_loss) {
     if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
-    double tot = 0.0;
+    const int steps = n_target_updates * n_updates_per_target;
+    if (steps < 1 || steps > kLogSlots) return spp_set_error_(SPP_ERR_ARG, "critic steps outside [1, 4096]");
+    // grad kernel -> reduce -> [all-reduce] -> record the loss sum -> Adam, all enqueued on the policy's stream; ONE host read at the end
+    int k = 0;
     for (int t = 0; t < n_target_updates; ++t) {
         int rc = spp_ppo_critic_targets(p); if (rc) return rc;
-        for (int u = 0; u < n_updates_per_target; ++u) {
+        for (int u = 0; u < n_updates_per_target; ++u, ++k) {
             rc = spp_ppo_critic_grad(p); if (rc) return rc;
-            float sc[8];
-            rc = spp_ppo_scalars(p, sc); if (rc) return rc;
-            tot += 0.5 * (double)sc[PS_LOSS] / (double)p->d.Ntot;
+            rc = allreduce_grads(p); if (rc) return rc;
+            rc = record_step(p, k, false); if (rc) return rc;
             rc = spp_ppo_critic_apply(p); if (rc) return rc;
         }
     }
-    if (mean_loss) *mean_loss = (float)(tot / ((double)n_target_updates * n_updates_per_target));
+    const int w = PS_COUNT + p->L.ldo;
+    std::vector<float> log((size_t)steps * w);
+    PCK(cudaMemcpyAsync(log.data(), p->slog, log.size() * 4, cudaMemcpyDeviceToHost, p->stream));
+    PCK(cudaStreamSynchronize(p->stream));
+    double tot = 0.0;
+    for (int i = 0; i < steps; ++i) tot += 0.5 * (double)log[(size_t)i * w + PS_LOSS] / (double)p->d.Ntot;      // a2c.py:208-216
+    if (mean_loss) *mean_loss = (float)(tot / (double)steps);
     return SPP_OK;
 }
 
@@ -354,7 +562,16 @@ int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats) {   // (A - me
     if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
     double st[3];
     if (global_stats) { st[0] = global_stats[0]; st[1] = global_stats[1]; st[2] = global_stats[2]; }
-    else { int rc = spp_ppo_adv_stats(p, st); if (rc) return rc; }
+    else {
+        int rc = spp_ppo_adv_stats(p, st); if (rc) return rc;
+        if (p->comm) {      // (n, sum, sum of squares) over all ranks, in fp64 (torch.std parity needs it)
+            PCK(cudaMemcpyAsync(p->dstats, st, 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            NCK(nccl().AllReduce(p->dstats, p->dstats, 3, 8 /* ncclFloat64 */, 0, p->comm, p->stream));
+            p->n_allreduce++;
+            PCK(cudaMemcpyAsync(st, p->dstats, 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            PCK(cudaStreamSynchronize(p->stream));
+        }
+    }
     const double n = st[0], mean = st[1] / n;
     const double var = n > 1 ? (st[2] - n * mean * mean) / (n - 1) : 0.0;
     const float denom = (float)std::sqrt(var > 0 ? var : 0.0) + 1.2e-7f;
@@ -412,39 +629,71 @@ int spp_ppo_actor_apply(spp_ppo* p) {
     return SPP_OK;
 }
 
+// One epoch of minibatch steps with the LOCAL row ids already on the device (ids_dev, a device pointer; minibatch k = ids[off[k], off[k + 1])
+// of this rank, n_global[k] rows over all ranks).  Per step: gather -> grad -> reduce -> [all-reduce] -> record scalars + log_scale ->
+// Adam, all on the policy's stream with no host synchronisation; the log (nb x (8 + ldo) floats) is read once at the end.
+// log_host [nb][8 + ldo]: slots 0..7 = the reduced scalars of minibatch k, then log_scale as it was BEFORE that step.
+int spp_ppo_actor_epoch_device(spp_ppo* p, const int64_t* ids_dev, const int64_t* off, const int64_t* n_global, int nb, float* log_host) {
+    if (!p || !off || !log_host || nb < 1 || nb > kLogSlots) return spp_set_error_(SPP_ERR_ARG, "spp_ppo_actor_epoch_device: bad argument");
+    if (p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
+    PCK(cudaSetDevice(p->device));
+    for (int k = 0; k < nb; ++k) {
+        const int64_t n = off[k + 1] - off[k];
+        if (n < 0 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [0, max_batch_rows]");
+        int rc = spp_ppo_actor_minibatch_grad_device(p, n > 0 ? ids_dev + off[k] : nullptr, n, n_global ? n_global[k] : 0); if (rc) return rc;
+        rc = allreduce_grads(p); if (rc) return rc;
+        rc = record_step(p, k, true); if (rc) return rc;
+        rc = spp_ppo_actor_apply(p); if (rc) return rc;
+    }
+    const int w = PS_COUNT + p->L.ldo;
+    PCK(cudaMemcpyAsync(log_host, p->slog, (size_t)nb * w * 4, cudaMemcpyDeviceToHost, p->stream));
+    PCK(cudaStreamSynchronize(p->stream));
+    return SPP_OK;
+}
+
 int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int batch_size, double kl_threshold, float losses[4],
                          int* epochs_run, float* last_kl) {
     if (!p || !perms) return spp_set_error_(SPP_ERR_ARG, "null");
     if (p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
+    if (p->comm) return spp_set_error_(SPP_ERR_STATE, "data-parallel runs filter the permutation per rank: use spp_ppo_actor_epoch_device");
+    if (batch_size < 1 || batch_size > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "batch_size outside [1, max_batch_rows]");
     const int64_t N = p->d.N;
-    const int ob = p->L.ob;
+    const int ob = p->L.ob, w = PS_COUNT + p->L.ldo;
+    const int nb = (int)((N + batch_size - 1) / batch_size);
+    if (nb > kLogSlots) return spp_set_error_(SPP_ERR_ARG, "more than 4096 minibatches per epoch");
+    PCK(cudaSetDevice(p->device));
+    for (int64_t i = 0; i < (int64_t)max_epochs * N; ++i)
+        if (perms[i] < 0 || perms[i] >= N) return spp_set_error_(SPP_ERR_ARG, "permutation index out of range");
+    int64_t* dperm_epoch = nullptr;
+    PCK(cudaMalloc(&dperm_epoch, (size_t)N * 8));
+    std::vector<int64_t> off(nb + 1), ng(nb);
+    for (int k = 0; k <= nb; ++k) off[k] = (int64_t)k * batch_size < N ? (int64_t)k * batch_size : N;
+    for (int k = 0; k < nb; ++k) ng[k] = off[k + 1] - off[k];
+    std::vector<float> log((size_t)nb * w);
     double tot[4] = {0, 0, 0, 0};
     double kl = 0.0;
-    int i = 0, ran = 0;
-    // state-independent entropy: sum_j 0.5 + 0.5 log(2 pi) + log_scale_j  (re-read per minibatch: log_scale moves)
+    int i = 0, ran = 0, rc = SPP_OK;
     for (i = 0; i < max_epochs; ++i) {
         if (kl >= kl_threshold) break;
-        int64_t last_n = 0;
-        for (int64_t s0 = 0; s0 < N; s0 += batch_size) {
-            const int64_t n = (N - s0 < batch_size) ? N - s0 : batch_size;
-            std::vector<float> ls(ob);
-            PCK(cudaMemcpyAsync(ls.data(), p->actor + p->L.actor.L[3].off_w, ob * 4, cudaMemcpyDeviceToHost, p->stream));
-            int rc = spp_ppo_actor_minibatch_grad(p, perms + (size_t)i * N + s0, n, 0); if (rc) return rc;
-            float sc[8];
-            rc = spp_ppo_scalars(p, sc); if (rc) return rc;
+        cudaError_t e = cudaMemcpyAsync(dperm_epoch, perms + (size_t)i * N, (size_t)N * 8, cudaMemcpyHostToDevice, p->stream);
+        if (e != cudaSuccess) { cudaFree(dperm_epoch); return spp_set_error_(SPP_ERR_CUDA, cudaGetErrorString(e)); }
+        rc = spp_ppo_actor_epoch_device(p, dperm_epoch, off.data(), ng.data(), nb, log.data());
+        if (rc) { cudaFree(dperm_epoch); return rc; }
+        for (int k = 0; k < nb; ++k) {
+            const float* sc = log.data() + (size_t)k * w;
+            const double n = (double)ng[k];
+            // state-independent entropy: sum_j 0.5 + 0.5 log(2 pi) + log_scale_j, with log_scale as it was in that minibatch
             float ent = 0.f;
-            for (int j = 0; j < ob; ++j) ent += 0.5f + 0.918938533204672741780329736406f + ls[j];
-            const double actor_loss = (double)sc[PS_LOSS] / (double)n;
-            const double dist = (p->h.custom_loss != 0.f && !p->plain_ppo) ? (double)sc[PS_DIST] / ((double)n * ob) : 0.0;
+            for (int j = 0; j < ob; ++j) ent += 0.5f + 0.918938533204672741780329736406f + sc[PS_COUNT + j];
+            const double actor_loss = (double)sc[PS_LOSS] / n;
+            const double dist = (p->h.custom_loss != 0.f && !p->plain_ppo) ? (double)sc[PS_DIST] / (n * ob) : 0.0;
             tot[0] += actor_loss; tot[1] += ent; tot[3] += dist;
             tot[2] += actor_loss - (double)p->h.entropy_coef * ent + (p->plain_ppo ? 0.0 : (double)p->h.custom_loss * dist);
-            kl = (double)sc[PS_KL] / (double)n;
-            last_n = n;
-            rc = spp_ppo_actor_apply(p); if (rc) return rc;
+            kl = (double)sc[PS_KL] / n;      // after the loop: the LAST (possibly short) minibatch of the epoch (quirk 16)
         }
-        (void)last_n;
         ++ran;
     }
+    cudaFree(dperm_epoch);
     // the reference divides by (i + 1) with i the loop variable at exit (one more than the epochs run after an early stop)
     // (PPO_AcM.update_actor_acm, on_policy.py:211-214); plain PPO.update_actor reports the raw sums (ppo.py:186-188)
     const double div = p->plain_ppo ? 1.0 : (double)((i < max_epochs ? i : max_epochs - 1) + 1);

@@ -1,0 +1,217 @@
+// SPP-PPO on-policy rollout, device-resident and vectorised over E environments: the body of A2C.collect_batch
+// (rltoolkit/algorithms/a2c/a2c.py:144-184) with AcMOnPolicyTrainer.process_action (rltoolkit/acm/on_policy.py:34-53):
+//   x = Memory.normalize(obs) -> Actor.act (mean = tanh(fc3 tanh(fc2 tanh(fc1 x))) * lim, action = mean + N(0,1) exp(log_scale),
+//   log-prob; rltoolkit/basic_model.py:32-51) -> denormalise -> ACM(cat[x, target]) (quirk 18: the ACM sees the NORMALISED
+//   observation) -> env.step -> store (obs, next_obs, action, logp, reward, done, end) + the ACM action.
+// The reference steps ONE environment per Python iteration; here every CTA owns a slice of <= kRolloutRows environments and walks
+// all T steps of them without leaving the SM: activations live in shared memory, the 64-wide weights (25 KB actor + 18 KB ACM at
+// Walker2d shapes) stay L1-resident (read-only for the whole launch, __ldg), and the [T][E] store is written step-major -- exactly
+// the layout the update kernels read (traj_stride = E).  MuJoCo is unavailable offline: the environment is the synthetic one of the
+// off-policy rollout (obs' = 0.98 obs + 0.1 tanh(a-mix) + 0.02 N(0,1); reward = obs'[0]; done with probability done_prob; time-limit
+// truncation at max_ep_len as in a2c.py:168-171; reset to 0.1 N(0,1)).  Noise comes from Philox, or from injected tensors (tests).
+// Every dot product accumulates k ascending with one fmaf per product, as the FFMA tiles of ppo_act_kernel do.
+#include "ppo_rollout.h"
+
+#include "common.cuh"
+#include "update_kernel.cuh"      // NORM_* indices
+
+namespace spp {
+
+constexpr int kRolloutRows = 32;
+
+// out[r][n] = act(sum_k in[r][k] Wt[k][n] + b[n] (+ t * skip[r][n])) (* scale[n]); thread = (n, row group of 8)
+template <int ACT, bool SCALE, bool SKIP>
+__device__ __forceinline__ void dense_rows(const float* __restrict__ in, int ldin, int K, const float* __restrict__ Wt, int ldt,
+                                           const float* __restrict__ bias, int N, float* __restrict__ out, int ldout, int R,
+                                           const float* __restrict__ scale = nullptr, float* __restrict__ out_pre = nullptr,
+                                           const float* __restrict__ skip = nullptr, int ldskip = 0, float t = 0.f) {
+    const int groups = (R + 7) / 8;
+    for (int idx = threadIdx.x; idx < groups * N; idx += blockDim.x) {
+        const int n = idx % N, r0 = (idx / N) * 8;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int k = 0; k < K; k += 4) {      // K is a multiple of 4 (padded layouts, pad weights are zero)
+            float w[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(Wt + (size_t)(k + kk) * ldt + n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(in + (size_t)(r0 + i) * ldin + k);      // rows >= R hold zeros
+                acc[i] = fmaf(v.x, w[0], acc[i]); acc[i] = fmaf(v.y, w[1], acc[i]);
+                acc[i] = fmaf(v.z, w[2], acc[i]); acc[i] = fmaf(v.w, w[3], acc[i]);
+            }
+        }
+        const float b = __ldg(bias + n);
+        const float sc = SCALE ? __ldg(scale + n) : 1.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (r0 + i >= R) break;
+            float x = acc[i] + b;
+            if (SKIP) x = __fadd_rn(x, __fmul_rn(t, skip[(size_t)(r0 + i) * ldskip + n]));
+            if (ACT == 2) x = tanhf(x);
+            if (out_pre) out_pre[(size_t)(r0 + i) * ldout + n] = x;
+            out[(size_t)(r0 + i) * ldout + n] = SCALE ? x * sc : x;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant__ PpoRolloutArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int ob = a.L.ob, ldo = a.L.ldo, ac = a.ac, lda = a.lda, ldm = 2 * ldo;
+    const int e0 = blockIdx.x * kRolloutRows;
+    const int R = min(kRolloutRows, a.E - e0);
+    if (R <= 0) return;
+    // shared-memory activations, every row buffer padded to 8-row groups (zero rows beyond R)
+    float* xin = sm;                               // [32][ldm]   [x | target]
+    float* h1 = xin + kRolloutRows * ldm;          // [32][64]
+    float* h2 = h1 + kRolloutRows * kPpoHidden;    // [32][64]
+    float* mean = h2 + kRolloutRows * kPpoHidden;  // [32][ldo]
+    float* m1 = mean + kRolloutRows * ldo;         // [32][ldm1]
+    float* m2 = m1 + kRolloutRows * a.ldm1;        // [32][ldm2]
+    float* ms = m2 + kRolloutRows * a.ldm2;        // [32][ldm2]  BasicAcM skip
+    float* pa = ms + kRolloutRows * a.ldm2;        // [32][lda]
+    float* obs = pa + kRolloutRows * lda;          // [32][ldo]   raw observation of every environment
+    int* eplen = reinterpret_cast<int*>(obs + kRolloutRows * ldo);      // [32]
+    const int total = kRolloutRows * (ldm + 2 * kPpoHidden + ldo + a.ldm1 + 2 * a.ldm2 + lda + ldo);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * ob; i += blockDim.x) obs[(i / ob) * ldo + i % ob] = a.state[(size_t)(e0 + i / ob) * ldo + i % ob];
+    for (int i = threadIdx.x; i < R; i += blockDim.x) eplen[i] = a.ep_len[e0 + i];
+    __syncthreads();
+
+    const LayerDesc& l0 = a.L.actor.L[0]; const LayerDesc& l1 = a.L.actor.L[1]; const LayerDesc& l2 = a.L.actor.L[2]; const LayerDesc& l3 = a.L.actor.L[3];
+    const float* nsub = a.norm + NORM_NSUB * ldo; const float* ndiv = a.norm + NORM_NDIV * ldo;
+    const float* doff = a.norm + NORM_DOFF * ldo; const float* dsc = a.norm + NORM_DSCALE * ldo; const float* lim = a.norm + NORM_LIM * ldo;
+    const float* ls = a.actor + l3.off_w;
+    const float kLogSqrt2Pi = 0.918938533204672741780329736406f;
+    const NetDesc& M = a.acm_desc;
+
+    for (int t = 0; t < a.T; ++t) {
+        const size_t row0 = (size_t)t * a.E + e0;
+        // 1. normalise (Memory.normalize, rltoolkit/buffer/memory.py:170-176) and store obs
+        for (int i = threadIdx.x; i < R * ob; i += blockDim.x) {
+            const int r = i / ob, j = i % ob;
+            const float o = obs[r * ldo + j];
+            float v = __fdiv_rn(__fsub_rn(o, nsub[j]), ndiv[j]);
+            if (a.clamp) v = fminf(fmaxf(v, -10.f), 10.f);
+            xin[r * ldm + j] = v;
+            a.x[(row0 + r) * ldo + j] = v;
+            if (a.raw_obs) a.raw_obs[(row0 + r) * ldo + j] = o;
+        }
+        __syncthreads();
+        // 2. actor
+        dense_rows<2, false, false>(xin, ldm, ldo, a.actor + l0.off_wt, l0.ld_t, a.actor + l0.off_b, kPpoHidden, h1, kPpoHidden, R);
+        __syncthreads();
+        dense_rows<2, false, false>(h1, kPpoHidden, kPpoHidden, a.actor + l1.off_wt, l1.ld_t, a.actor + l1.off_b, kPpoHidden, h2, kPpoHidden, R);
+        __syncthreads();
+        dense_rows<2, true, false>(h2, kPpoHidden, kPpoHidden, a.actor + l2.off_wt, l2.ld_t, a.actor + l2.off_b, ob, mean, ldo, R, lim);
+        __syncthreads();
+        // 3. sample, log-prob, denormalised target (one thread per environment: the log-prob sum runs j ascending as torch's sum(-1))
+        for (int r = threadIdx.x; r < R; r += blockDim.x) {
+            float lp = 0.f;
+            for (int j = 0; j < ob; ++j) {
+                float nz;
+                if (a.noise_act) nz = a.noise_act[(row0 + r) * ob + j];
+                else {
+                    const uint4 w = Philox::gen(a.seed, (uint64_t)t, (uint64_t)(e0 + r) * 128 + j);
+                    nz = normal_from_bits(w.x, w.y);
+                }
+                const float sd = expf(ls[j]);
+                const float mu = mean[r * ldo + j];
+                const float act = __fadd_rn(mu, __fmul_rn(nz, sd));
+                const float d = __fsub_rn(act, mu);
+                lp += __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, __fmul_rn(sd, sd))), logf(sd)), kLogSqrt2Pi);
+                a.act[(row0 + r) * ldo + j] = act;
+                xin[r * ldm + ldo + j] = a.denorm_out ? __fadd_rn(doff[j], __fmul_rn(act, dsc[j])) : act;
+            }
+            a.logp[row0 + r] = lp;
+        }
+        __syncthreads();
+        // 4. ACM (AcM: tanh-tanh-tanh * action limit; BasicAcM: skip connection and learnable gains)
+        if (a.acm_kind == ACM_MLP) {
+            dense_rows<2, false, false>(xin, ldm, ldm, a.acm + M.L[0].off_wt, M.L[0].ld_t, a.acm + M.L[0].off_b, a.hm1, m1, a.ldm1, R);
+            __syncthreads();
+            dense_rows<2, false, false>(m1, a.ldm1, a.ldm1, a.acm + M.L[1].off_wt, M.L[1].ld_t, a.acm + M.L[1].off_b, a.hm2, m2, a.ldm2, R);
+            __syncthreads();
+            dense_rows<2, true, false>(m2, a.ldm2, a.ldm2, a.acm + M.L[2].off_wt, M.L[2].ld_t, a.acm + M.L[2].off_b, ac, pa, lda, R, a.acm_lim);
+        } else {
+            dense_rows<2, false, false>(xin, ldm, ldm, a.acm + M.L[0].off_wt, M.L[0].ld_t, a.acm + M.L[0].off_b, a.hm1, m1, a.ldm1, R);
+            dense_rows<0, false, false>(xin, ldm, ldm, a.acm + M.L[3].off_wt, M.L[3].ld_t, a.acm + M.L[3].off_b, a.hm2, ms, a.ldm2, R);
+            __syncthreads();
+            dense_rows<2, false, true>(m1, a.ldm1, a.ldm1, a.acm + M.L[1].off_wt, M.L[1].ld_t, a.acm + M.L[1].off_b, a.hm2, m2, a.ldm2, R, nullptr,
+                                       nullptr, ms, a.ldm2, __ldg(a.acm + M.L[4].off_w));
+            __syncthreads();
+            dense_rows<2, true, false>(m2, a.ldm2, a.ldm2, a.acm + M.L[2].off_wt, M.L[2].ld_t, a.acm + M.L[2].off_b, ac, pa, lda, R,
+                                       a.acm + M.L[4].off_w + 4);
+        }
+        __syncthreads();
+        // 5. environment step + store (one thread per environment)
+        for (int r = threadIdx.x; r < R; r += blockDim.x) {
+            const int e = e0 + r;
+            float mix = 0.f;
+            for (int j = 0; j < ac; ++j) {
+                const float v = pa[r * lda + j];
+                if (a.aacm) a.aacm[(row0 + r) * lda + j] = v;
+                mix += v * (0.3f + 0.1f * (float)j);
+            }
+            mix = tanhf(mix);
+            float u_done, rew = 0.f;
+            uint4 wd = make_uint4(0, 0, 0, 0);
+            if (a.u_done) u_done = a.u_done[row0 + r];
+            else { wd = Philox::gen(a.seed ^ 0xD0Eull, (uint64_t)t, (uint64_t)e); u_done = (float)(wd.x >> 8) * (1.0f / 16777216.0f); }
+            const int len = eplen[r] + 1;
+            const bool done = u_done < a.done_prob;
+            const bool end = done || len == a.max_ep_len;
+            for (int j = 0; j < ob; ++j) {
+                float nz;
+                if (a.noise_env) nz = a.noise_env[(row0 + r) * ob + j];
+                else {
+                    const uint4 w = Philox::gen(a.seed ^ 0xE9Full, (uint64_t)t, (uint64_t)e * 128 + j);
+                    nz = normal_from_bits(w.x, w.y);
+                }
+                const float o = obs[r * ldo + j];
+                const float nx = 0.98f * o + 0.1f * mix * (1.f - 0.01f * (float)j) + 0.02f * nz;
+                if (j == 0) rew = nx;
+                float v = __fdiv_rn(__fsub_rn(nx, nsub[j]), ndiv[j]);
+                if (a.clamp) v = fminf(fmaxf(v, -10.f), 10.f);
+                a.xn[(row0 + r) * ldo + j] = v;
+                if (a.raw_next) a.raw_next[(row0 + r) * ldo + j] = nx;
+                float nxt = nx;
+                if (end) {      // env.reset(): the next rollout of this environment starts here
+                    float rz;
+                    if (a.noise_reset) rz = a.noise_reset[(row0 + r) * ob + j];
+                    else {
+                        const uint4 w = Philox::gen(a.seed ^ 0x5E7ull, (uint64_t)t, (uint64_t)e * 128 + j);
+                        rz = normal_from_bits(w.x, w.y);
+                    }
+                    nxt = 0.1f * rz;
+                }
+                obs[r * ldo + j] = nxt;
+            }
+            a.rew[row0 + r] = rew;
+            a.done[row0 + r] = (done && len != a.max_ep_len) ? 1.f : 0.f;      // a2c.py:170: done = False if ep_len == max_ep_len else done
+            a.end[row0 + r] = (end || t == a.T - 1) ? 1.f : 0.f;               // the batch cuts every trajectory at its last step
+            eplen[r] = end ? 0 : len;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < R * ob; i += blockDim.x) a.state[(size_t)(e0 + i / ob) * ldo + i % ob] = obs[(i / ob) * ldo + i % ob];
+    for (int i = threadIdx.x; i < R; i += blockDim.x) a.ep_len[e0 + i] = eplen[i];
+}
+
+size_t ppo_rollout_smem_bytes(const PpoRolloutArgs& a) {
+    const int ldo = a.L.ldo;
+    return (size_t)kRolloutRows * (2 * ldo + 2 * kPpoHidden + ldo + a.ldm1 + 2 * a.ldm2 + a.lda + ldo) * 4 + kRolloutRows * 4 + 16;
+}
+
+cudaError_t launch_ppo_rollout(const PpoRolloutArgs& a, cudaStream_t s) {
+    const size_t smem = ppo_rollout_smem_bytes(a);
+    cudaError_t e = cudaFuncSetAttribute(ppo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (a.E + kRolloutRows - 1) / kRolloutRows;
+    ppo_rollout_kernel<<<grid, 256, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace spp

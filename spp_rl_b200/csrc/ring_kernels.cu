@@ -2,6 +2,7 @@
 // Reference semantics: rltoolkit/buffer/replay_buffer.py:233-261,385-398 (sample), :56-75,133-137,332-333 (adds).
 #include "common.cuh"
 #include "ring_kernels.h"
+#include "ppo_rollout.h"
 
 namespace spp {
 
@@ -95,9 +96,42 @@ __global__ void ring_fill_kernel(RingView R, float* obs, int32_t* oidx, int32_t*
     }
 }
 
+// ReplayBufferAcM.add_buffer on device data (rltoolkit/buffer/replay_buffer.py:284-297): the host walked the cursor state machine
+// (integers only) and left, per ring slot, where its final content comes from; every slot is written by exactly one thread group.
+__global__ void ring_add_store_kernel(float* r_obs, int32_t* r_oidx, int32_t* r_nidx, float* r_aacm, float* r_rew, uint8_t* r_done,
+                                      uint8_t* r_end, int64_t S, int ob, int ac, int ldo, int lda, const int64_t* __restrict__ obs_src,
+                                      const int64_t* __restrict__ ts_src, const int32_t* __restrict__ ts_oidx,
+                                      const int32_t* __restrict__ ts_nidx, const float* __restrict__ raw_obs,
+                                      const float* __restrict__ raw_next, const float* __restrict__ aacm) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = obs_src[s];
+        if (o >= 0) {
+            const bool nxt = (o >> 62) & 1;
+            const int64_t row = o & ((1ll << 62) - 1);
+            const float* src = (nxt ? raw_next : raw_obs) + row * ldo;
+            for (int j = 0; j < ob; ++j) r_obs[s * ldo + j] = src[j];
+        }
+        const int64_t k = ts_src[s];
+        if (k >= 0) {
+            for (int j = 0; j < ac; ++j) r_aacm[s * lda + j] = aacm[k * lda + j];
+            r_oidx[s] = ts_oidx[s]; r_nidx[s] = ts_nidx[s];
+            r_rew[s] = 0.f; r_done[s] = 0; r_end[s] = 0;      // ReplayBufferAcM.add_timestep stores no reward / done (replay_buffer.py:299-300)
+        }
+    }
+}
+
 }  // namespace spp
 
 namespace spp {
+
+cudaError_t launch_ring_add_store(float* r_obs, int32_t* r_oidx, int32_t* r_nidx, float* r_aacm, float* r_rew, uint8_t* r_done, uint8_t* r_end,
+                                  int64_t S, int ob, int ac, int ldo, int lda, const int64_t* obs_src, const int64_t* ts_src,
+                                  const int32_t* ts_oidx, const int32_t* ts_nidx, const PpoStoreView& st, cudaStream_t s) {
+    const int blocks = (int)((S + 255) / 256);
+    ring_add_store_kernel<<<blocks < 1 ? 1 : (blocks > 1184 ? 1184 : blocks), 256, 0, s>>>(r_obs, r_oidx, r_nidx, r_aacm, r_rew, r_done, r_end, S, ob, ac, ldo,
+                                                                                   lda, obs_src, ts_src, ts_oidx, ts_nidx, st.raw_obs, st.raw_next, st.aacm);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ring_gather(const RingView& R, int agent, const int64_t* d_idx, int n, const GatherOut& o, cudaStream_t s) {
     const int blocks = (n * 32 + 255) / 256;

@@ -175,6 +175,10 @@ class Population:
         check(self.lib.spp_ring_add_timestep(self.h, agent, int(obs_idx), int(next_obs_idx), _ptr(a, C.c_float),
                                              float(rew), int(bool(done)), int(bool(end))))
 
+    def ring_add_rollout_store(self, agent, policy):
+        """ReplayBufferAcM.add_buffer (replay_buffer.py:284-297) from the [T][E] store a device rollout left in `policy` (PpoPolicy)."""
+        check(self.lib.spp_ring_add_rollout_store(self.h, int(agent), policy.h))
+
     def ring_reset(self, agent=-1):
         check(self.lib.spp_ring_reset(self.h, agent))
 
@@ -298,8 +302,58 @@ class Population:
             res[name] = lerp
         return (res, nbytes.value) if return_bytes else res
 
-    def rollout_synthetic(self, envs_per_agent, steps, seed=0, act_noise=0.1, stream=None):
-        check(self.lib.spp_rollout_synthetic_device(self.h, int(envs_per_agent), int(steps), int(seed), float(act_noise), stream))
+    def rollout_synthetic(self, envs_per_agent, steps, seed=0, act_noise=0.1, stream=None, random_phase=False):
+        check(self.lib.spp_rollout_synthetic_device(self.h, int(envs_per_agent), int(steps), int(seed), float(act_noise),
+                                                    int(bool(random_phase)), stream))
+
+    # ------------------------------------------------------------------ the whole train loop, population-batched and device-resident
+    def train_synthetic(self, frames, envs_per_agent=1, update_freq=50, grad_steps=50, random_frames=100, act_noise=0.1,
+                        steps_per_epoch=1000, acm_update_freq=0, acm_update_batches=0, update_stats=True, seed=0, stream=None,
+                        state=None):
+        """P agents' frame loop of DDPG.collect_batch_and_train + DDPG_AcM.make_update (rltoolkit/algorithms/ddpg/ddpg.py:191-237,
+        rltoolkit/acm/off_policy/ddpg_acm.py:52-85) and the per-iteration statistics refresh (ddpg.py:159-169), with every
+        stage on the device: rollout_synthetic (actor -> noise -> ACM -> synthetic env -> ring) -> update bursts -> ACM
+        regression batches -> ring_obs_stats.  The launches are cut exactly where the reference's conditions fire (train_schedule):
+        with envs_per_agent = 1 the frame counter, the update frames and the ACM-update frames are the reference's; with E
+        environments per agent one vector step counts E frames.  `state`: the dict a previous call returned (frames, iteration,
+        stats), to continue a run.  -> state with `launch_log` (the executed schedule)."""
+        st = dict(frames=0, iteration=0, min_obs=None, max_obs=None, updates=0, acm_batches=0, stats_updates=0) if state is None else dict(state)
+        E = int(envs_per_agent)
+        log = []
+        for ev in train_schedule(st["frames"], frames, E, self.B, update_freq, grad_steps, random_frames, steps_per_epoch,
+                                 acm_update_freq, acm_update_batches, st["iteration"], lambda: self.ring_state(0)[2]):
+            kind = ev[0]
+            if kind == "rollout":
+                _, steps, random_phase, f0 = ev
+                self.rollout_synthetic(E, steps, seed=seed * 1000003 + f0, act_noise=act_noise, stream=stream, random_phase=random_phase)
+                st["frames"] = f0 + steps * E
+            elif kind == "update":
+                self.update_ring_device(ev[1], seed=seed * 7919 + st["frames"], stream=stream)
+                st["updates"] += ev[1] * self.P
+            elif kind == "acm":
+                if stream is not None:
+                    self.sync_stream(stream)
+                self.acm_update_ring(ev[1], idx=None, seed=seed * 31 + st["frames"])
+                st["acm_batches"] += ev[1] * self.P
+            elif kind == "stats":
+                st["iteration"] += 1
+                if update_stats:
+                    if stream is not None:
+                        self.sync_stream(stream)
+                    r = self.ring_obs_stats()
+                    mn, mx = r["p1"].astype(np.float32), r["p99"].astype(np.float32)      # MetaReplayBuffer.update_obs_mean_std: running widening
+                    st["min_obs"] = mn if st["min_obs"] is None else np.minimum(mn, st["min_obs"])
+                    st["max_obs"] = mx if st["max_obs"] is None else np.maximum(mx, st["max_obs"])
+                    for a in range(self.P):
+                        self.set_norm_stats(st["min_obs"][a], st["max_obs"][a], r["mean"][a].astype(np.float32), r["std"][a].astype(np.float32), agent=a)
+                    st["stats_updates"] += 1
+            log.append(ev)
+        st["launch_log"] = log
+        return st
+
+    def sync_stream(self, stream):
+        import torch
+        torch.cuda.ExternalStream(stream).synchronize() if isinstance(stream, int) else stream.synchronize()
 
     # ------------------------------------------------------------------ introspection
     def debug_scratch(self, agent, name):
@@ -312,3 +366,41 @@ class Population:
 
 def kernel_launches() -> int:
     return int(_lib.load_library().spp_kernel_launches())
+
+
+def train_schedule(frame0, frames, E, batch, update_freq, grad_steps, random_frames, steps_per_epoch, acm_update_freq, acm_update_batches,
+                   iteration0=0, ring_len=None):
+    """The launches of Population.train_synthetic in order, as tuples: ("rollout", vector_steps, random_phase, first_frame),
+    ("update", grad_steps), ("acm", n_batches), ("stats",).  Pure host logic (CPU-tested against a frame-by-frame restatement of
+    the reference's conditions): after every frame f (frames counted AFTER the increment, ddpg.py:221-223)
+        update      if len(ring) > batch and f % update_freq == 0                      (DDPG.update_condition, ddpg.py:225-229)
+        acm update  if iteration > 0 and acm batches > 0 and f % acm_update_freq == 0  (DDPG_AcM.acm_update_condition, ddpg_acm.py:52-57)
+        stats       when f reaches a multiple of steps_per_epoch                        (perform_iteration, ddpg.py:159-169)
+    and the random phase ends at random_frames (ddpg.py:205-208).  Consecutive frames with no event in between are one rollout
+    launch.  ring_len: callable -> current ring length (None: assume the ring holds every frame since frame 0, uncapped)."""
+    E = int(E)
+    for name, v in (("update_freq", update_freq), ("steps_per_epoch", steps_per_epoch), ("random_frames", random_frames)):
+        if v % E:
+            raise ValueError("%s (%d) must be a multiple of envs_per_agent (%d)" % (name, v, E))
+    if acm_update_batches and acm_update_freq % E:
+        raise ValueError("acm_update_freq must be a multiple of envs_per_agent")
+    f, it = int(frame0), int(iteration0)
+    end = f + int(frames)
+    while f < end:
+        # next frame count at which anything can happen
+        nxt = end
+        for period in (update_freq, steps_per_epoch) + ((acm_update_freq,) if acm_update_batches and acm_update_freq else ()):
+            nxt = min(nxt, (f // period + 1) * period)
+        if f < random_frames:
+            nxt = min(nxt, random_frames)
+        steps = (nxt - f) // E
+        yield ("rollout", steps, f < random_frames, f)
+        f = nxt
+        n = ring_len() if ring_len is not None else f
+        if n > batch and f % update_freq == 0:
+            yield ("update", grad_steps)
+        if it > 0 and acm_update_batches and acm_update_freq and f % acm_update_freq == 0:
+            yield ("acm", acm_update_batches)
+        if f % steps_per_epoch == 0:
+            yield ("stats",)
+            it += 1

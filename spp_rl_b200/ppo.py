@@ -104,6 +104,22 @@ class PpoPolicy:
                                             _ptr(logp, C.c_float), _ptr(rew, C.c_float), _ptr(done, C.c_float), _ptr(end, C.c_float),
                                             _ptr(ts, C.c_int64), _ptr(tl, C.c_int64), int(ts.size), int(traj_stride), int(global_rows)))
 
+    def rollout_synthetic(self, pop, envs, steps, agent=0, max_ep_len=1000, done_prob=0.001, seed=0, denormalize_actor_out=True,
+                          reset_envs=False, noise_act=None, noise_env=None, u_done=None, noise_reset=None):
+        """A2C.collect_batch on the device (spp_ppo_rollout_synthetic): `envs` vectorised synthetic environments x `steps` steps through
+        this policy and the ACM of `pop`'s agent, into the policy's [T][E] store.  Injected noise tensors are for the parity tests."""
+        arrs = [None if v is None else _f32(v) for v in (noise_act, noise_env, u_done, noise_reset)]
+        check(self.lib.spp_ppo_rollout_synthetic(self.h, pop.h, int(agent), int(envs), int(steps), int(max_ep_len), float(done_prob), int(seed),
+                                                 int(bool(denormalize_actor_out)), int(bool(reset_envs)), *[_ptr(v, C.c_float) for v in arrs]))
+        self.N = self.Ntot = int(envs) * int(steps)
+
+    def store(self, name):
+        """One column of the loaded rows ("x", "xn", "act", "raw_obs", "raw_next", "aacm", "logp", "rew", "done", "end", "adv", "v")."""
+        w = {"x": self.ob_dim, "xn": self.ob_dim, "act": self.ob_dim, "raw_obs": self.ob_dim, "raw_next": self.ob_dim, "aacm": self.ac_dim}.get(name, 0)
+        out = np.empty((self.N, w) if w else (self.N,), np.float32)
+        check(self.lib.spp_ppo_store_download(self.h, name.encode(), _ptr(out, C.c_float)))
+        return out
+
     def act(self, obs, noise, denormalize_actor_out=True):
         """Actor.act + denormalise for E observations: -> (action [E, ob], logp [E], acm_target [E, ob])."""
         obs, noise = _f32(obs), _f32(noise)
@@ -166,7 +182,83 @@ class PpoPolicy:
                                             C.byref(epochs), C.byref(kl)))
         return {"actor": losses[0], "entropy": losses[1], "policy": losses[2], "dist": losses[3]}, epochs.value, kl.value
 
-    # ------------------------------------------------------------------ data-parallel forms (torch.distributed)
+    # ------------------------------------------------------------------ data parallelism: NCCL inside the library
+    def comm_init(self, dist):
+        """One NCCL communicator for this policy over the ranks of the (already initialised) torch.distributed process group: rank 0
+        draws the 128-byte id (spp_comm_unique_id), torch.distributed only carries it to the other ranks.  Afterwards update_critic,
+        normalize_adv and actor_epoch_device all-reduce inside the library, on the policy's stream."""
+        import torch
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            check(self.lib.spp_comm_unique_id(buf))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(dev)
+        dist.broadcast(t, 0)
+        check(self.lib.spp_ppo_comm_init(self.h, bytes(t.cpu().numpy().tobytes()), rank, world))
+        self.world, self.rank = world, rank
+
+    def comm_info(self):
+        w, n, v = C.c_int(), C.c_int64(), C.c_int()
+        check(self.lib.spp_ppo_comm_info(self.h, C.byref(w), C.byref(n), C.byref(v)))
+        return {"world": w.value, "allreduces": n.value, "nccl_version": v.value}
+
+    def actor_epoch_device(self, ids_dev, off, n_global=None):
+        """One epoch of minibatch steps (gather -> grad -> [all-reduce] -> Adam) with this rank's LOCAL row ids on the device
+        (torch int64 CUDA tensor produced on the policy's stream); off: host offsets (len nb + 1).  -> log [nb, 8 + pad4(ob)]."""
+        off = np.ascontiguousarray(off, np.int64)
+        nb = off.size - 1
+        ng = None if n_global is None else np.ascontiguousarray(n_global, np.int64)
+        ldo = (self.ob_dim + 3) // 4 * 4
+        log = np.empty((nb, 8 + ldo), np.float32)
+        ptr = C.c_void_p(ids_dev.data_ptr()) if ids_dev is not None and ids_dev.numel() else None
+        check(self.lib.spp_ppo_actor_epoch_device(self.h, ptr, _ptr(off, C.c_int64), _ptr(ng, C.c_int64), int(nb), _ptr(log, C.c_float)))
+        return log
+
+    def iteration_dp(self, perms, batch, E, kl_threshold=1e9, critic_targets=10, critic_steps=10, rank=0, world=1):
+        """The update half of PPO_AcM.perform_iteration (on_policy.py:55-86) on this rank's environment shard: critic fit ->
+        advantages -> advantage normalisation -> actor epochs with the KL early stop.  perms: [epochs, N_global] GLOBAL permutations
+        (every rank holds the same); each rank filters its rows on the device (sharding.epoch_local_minibatches_device) and all
+        collectives run inside the library (comm_init).  world == 1 runs the same code path without a communicator.
+        -> dict(critic_loss, epochs, kl, phases_ms (host clock after a stream sync per phase), allreduces)."""
+        import time
+
+        import torch
+
+        from .sharding import epoch_local_minibatches_device
+
+        n0 = self.comm_info()["allreduces"]
+        t0 = time.perf_counter()
+        closs = self.update_critic(critic_targets, critic_steps)
+        t1 = time.perf_counter()
+        self.advantages(want_host=False)
+        self.normalize_adv()
+        self.sync()
+        t2 = time.perf_counter()
+        perms = np.ascontiguousarray(perms, np.int64)
+        N = perms.shape[1]
+        nb = (N + batch - 1) // batch
+        ng = np.minimum(batch, N - batch * np.arange(nb)).astype(np.int64)
+        kl, ran = 0.0, 0
+        st = self._ext_stream()
+        for ep in range(perms.shape[0]):
+            if kl >= kl_threshold:
+                break
+            with torch.cuda.stream(st):      # the epoch's permutation goes to the device once; the rank filters its rows there
+                perm_dev = torch.from_numpy(perms[ep]).to("cuda", non_blocking=False)
+                if world > 1:
+                    ids, off = epoch_local_minibatches_device(perm_dev, batch, E, rank, world)
+                else:
+                    ids, off = perm_dev, [min(k * batch, N) for k in range(nb + 1)]
+                log = self.actor_epoch_device(ids, off, ng)
+            kl = float(log[-1, 3]) / float(ng[-1])      # PS_KL of the LAST (possibly short) minibatch of the epoch (quirk 16)
+            ran += 1
+        t3 = time.perf_counter()
+        return {"critic_loss": closs, "epochs": ran, "kl": kl, "allreduces": self.comm_info()["allreduces"] - n0,
+                "phases_ms": {"critic_fit": (t1 - t0) * 1e3, "advantages_and_normalisation": (t2 - t1) * 1e3, "actor_epochs": (t3 - t2) * 1e3}}
+
+    # ------------------------------------------------------------------ step-wise data-parallel forms (collective issued by torch.distributed)
     def grad_tensor(self):
         """torch views (no copy) of the reduced gradient vector and the 8 scalar slots, for dist.all_reduce."""
         g, sc, _ = self._grad_views()

@@ -102,3 +102,55 @@ def test_synthetic_environment_fallback_is_loud(monkeypatch):
             return ("real", name)
     monkeypatch.setattr(envs, "_real_gym", lambda: FakeGym)
     assert envs.make("Hopper-v2") == ("real", "Hopper-v2")      # a real gym wins over the stand-in
+
+
+def _frame_by_frame(frames, batch, update_freq, grad_steps, random_frames, steps_per_epoch, acm_freq, acm_batches):
+    """The reference's frame loop, one frame at a time (ddpg.py:191-237, ddpg_acm.py:52-85, ddpg.py:159-169): -> event list with
+    consecutive event-free frames of one phase merged into a single ("rollout", n, random, first_frame)."""
+    ev, run, it, f = [], None, 0, 0
+    while f < frames:
+        random = f < random_frames                      # stats_logger.frames < random_frames, tested BEFORE the increment
+        if run is not None and run[2] == random:
+            run[1] += 1
+        else:
+            if run is not None:
+                ev.append(tuple(run))
+            run = ["rollout", 1, random, f]
+        f += 1
+        fired = []
+        if f > batch and f % update_freq == 0:          # len(replay_buffer) > update_batch_size: one transition per frame
+            fired.append(("update", grad_steps))
+        if it > 0 and acm_batches > 0 and f % acm_freq == 0:
+            fired.append(("acm", acm_batches))
+        if f % steps_per_epoch == 0:
+            fired.append(("stats",))
+            it += 1
+        if fired:
+            ev.append(tuple(run)); run = None
+            ev.extend(fired)
+    if run is not None:
+        ev.append(tuple(run))
+    return ev
+
+
+def test_population_train_schedule_fires_where_the_reference_loop_does():
+    from spp_rl_b200.population import train_schedule
+
+    for cfg in ((3000, 256, 50, 50, 100, 1000, 200, 10), (2500, 64, 7, 3, 21, 350, 35, 2), (1200, 256, 50, 50, 0, 400, 0, 0),
+                (999, 10, 1, 1, 5, 100, 3, 1)):
+        frames, batch, uf, gs, rf, spe, af, ab = cfg
+        want = _frame_by_frame(frames, batch, uf, gs, rf, spe, af, ab)
+        got = list(train_schedule(0, frames, 1, batch, uf, gs, rf, spe, af, ab))
+        # the schedule cuts rollouts at every POSSIBLE event frame (the ring length is only known at run time); merge neighbours
+        merged = []
+        for e in got:
+            if e[0] == "rollout" and merged and merged[-1][0] == "rollout" and merged[-1][2] == e[2]:
+                merged[-1] = ("rollout", merged[-1][1] + e[1], e[2], merged[-1][3])
+            else:
+                merged.append(e)
+        assert merged == want, cfg
+    # E environments per agent: one vector step = E frames; the same frames fire
+    got = [e for e in train_schedule(0, 2000, 10, 256, 50, 50, 100, 1000, 200, 10) if e[0] != "rollout"]
+    want = [e for e in _frame_by_frame(2000, 256, 50, 50, 100, 1000, 200, 10) if e[0] != "rollout"]
+    assert got == want
+    assert sum(e[1] * 10 for e in train_schedule(0, 2000, 10, 256, 50, 50, 100, 1000, 200, 10) if e[0] == "rollout") == 2000

@@ -16,7 +16,7 @@ import torch
 import torch.distributed as dist
 
 from spp_rl_b200.ppo import PpoPolicy
-from spp_rl_b200.sharding import allreduce_adv_stats, env_shard_rows, epoch_local_minibatches_device, local_minibatch
+from spp_rl_b200.sharding import env_shard_rows
 
 OB, AC = 17, 6      # Walker2d shapes
 
@@ -63,8 +63,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--critic-targets", type=int, default=2)
     ap.add_argument("--critic-steps", type=int, default=5)
+    ap.add_argument("--dump", default="", help="npz path: post-iteration weights of the data-parallel and the single-GPU run (rank 0)")
     args = ap.parse_args()
-    os.environ.pop("NCCL_DEBUG", None)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -76,33 +76,24 @@ def main():
     # local rows: environment slice [rank * El, (rank + 1) * El) of every step, step-major with stride El
     rows = env_shard_rows(E, T, rank, world)
     pol = make_policy(local, El * T, args.batch, d, w)
+    pol.comm_init(dist)      # NCCL communicator inside the library: every optimiser step all-reduces on the policy's own stream
     pol.load_rollout(d["obs"][rows], d["nobs"][rows], d["act"][rows], d["logp"][rows], d["rew"][rows], d["done"][rows], d["end"][rows],
                      np.arange(El), np.full(El, T), traj_stride=El, global_rows=N)
     rng = np.random.RandomState(11)
     perms = np.stack([rng.permutation(N) for _ in range(args.epochs)]).astype(np.int64)
 
+    def reset(p):      # the initial weights with a fresh optimiser state
+        for net in ("actor", "critic"):
+            p.load_state_dict(net, {k[len(net) + 1:]: v for k, v in w.items() if k.startswith(net + ".")})
+            p.adam_reset(net)
+    # warm-up: one shortened iteration (first-use costs of the kernels and of torch's device ops), then back to the start state
+    pol.iteration_dp(perms[:1], args.batch, E, 1e9, 1, 1, rank, world)
+    reset(pol)
     torch.cuda.synchronize(); dist.barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    import time
-    w0 = time.perf_counter()
-    closs = pol.update_critic_dp(dist, args.critic_targets, args.critic_steps)
-    w1 = time.perf_counter()
-    pol.advantages(want_host=False)
-    pol.normalize_adv(allreduce_adv_stats(pol.adv_stats(), dist, "cuda"))
-    pol.sync(); w2 = time.perf_counter()
-    n_allreduce = args.critic_targets * args.critic_steps + 1      # gradient vector and scalars travel in one buffer
-    for ep in range(args.epochs):
-        with torch.cuda.stream(pol._ext_stream()):      # the epoch's permutation goes to the device once; ranks filter their rows there
-            perm_dev = torch.from_numpy(perms[ep]).cuda()
-            ids, off = epoch_local_minibatches_device(perm_dev, args.batch, E, rank, world)
-            for k, b0 in enumerate(range(0, N, args.batch)):
-                pol.actor_minibatch_dp(dist, ids[off[k]:off[k + 1]], min(args.batch, N - b0),
-                                       want_host=(b0 + args.batch >= N))      # one host read per epoch (KL test)
-                n_allreduce += 1
+    res = pol.iteration_dp(perms, args.batch, E, 1e9, args.critic_targets, args.critic_steps, rank, world)
     pol.sync()
-    w3 = time.perf_counter()
-    phases = {"critic_fit": (w1 - w0) * 1e3, "advantages_and_normalisation": (w2 - w1) * 1e3, "actor_epochs": (w3 - w2) * 1e3}
     t1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
@@ -118,27 +109,34 @@ def main():
     if rank == 0:
         one = make_policy(local, N, args.batch, d, w)
         one.load_rollout(d["obs"], d["nobs"], d["act"], d["logp"], d["rew"], d["done"], d["end"], np.arange(E), np.full(E, T), traj_stride=E)
+        one.iteration_dp(perms[:1], args.batch, E, 1e9, 1, 1, 0, 1)
+        reset(one)
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        one.update_critic(args.critic_targets, args.critic_steps)
-        one.advantages(want_host=False)
-        one.normalize_adv()
-        one.update_actor(perms, args.batch, 1e9, args.epochs)
+        res1 = one.iteration_dp(perms, args.batch, E, 1e9, args.critic_targets, args.critic_steps, 0, 1)
         one.sync()
         s1.record(); torch.cuda.synchronize()
         worst = 0.0
+        dump = {}
         for net in ("actor", "critic"):
             sd1 = one.state_dict(net)
             for k, v in sd1.items():
                 e = relnorm(sd_dp[net][k], v) * (0.1 if v.size <= 16 else 1.0)
                 worst = max(worst, e)
+                dump["dp:%s.%s" % (net, k)] = sd_dp[net][k]
+                dump["one:%s.%s" % (net, k)] = v
         one.close()
+        if args.dump:
+            np.savez(args.dump, critic_loss_dp=res["critic_loss"], critic_loss_one=res1["critic_loss"], **dump)
+        info = pol.comm_info()
         out = {"metric": "SPP-PPO iteration (critic fit + GAE + advantage normalisation + clipped-ratio actor epochs), data-parallel over environments",
-               "n_gpus": world, "envs": E, "steps": T, "rows": N, "global_minibatch": args.batch, "epochs": args.epochs,
-               "critic_steps": args.critic_targets * args.critic_steps, "allreduces": n_allreduce, "ms_dp": float(ms.item()), "ms_phases_rank0": phases,
-               "transitions_per_s_dp": N / (float(ms.item()) * 1e-3), "ms_single_gpu": s0.elapsed_time(s1),
-               "dp_vs_single_worst_relnorm": worst, "ranks_bit_identical": bool(same.item() == 1.0), "critic_loss_sum": closs}
-        print(json.dumps(out))
+               "n_gpus": world, "envs": E, "steps": T, "rows": N, "global_minibatch": args.batch, "epochs": res["epochs"],
+               "critic_steps": args.critic_targets * args.critic_steps, "allreduces": res["allreduces"], "nccl_version": info["nccl_version"],
+               "ms_dp": float(ms.item()), "ms_phases_rank0": res["phases_ms"],
+               "transitions_per_s_dp": N / (float(ms.item()) * 1e-3), "ms_single_gpu": s0.elapsed_time(s1), "ms_phases_single_gpu": res1["phases_ms"],
+               "dp_vs_single_worst_relnorm": worst, "ranks_bit_identical": bool(same.item() == 1.0),
+               "critic_loss_dp": res["critic_loss"], "critic_loss_single_gpu": res1["critic_loss"]}
+        print(json.dumps(out), flush=True)
     pol.close()
     dist.destroy_process_group()
     if rank == 0 and (out["dp_vs_single_worst_relnorm"] > 2e-5 or not out["ranks_bit_identical"]):
