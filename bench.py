@@ -270,6 +270,140 @@ def build_population(device, P, ring=RING):
     return pop
 
 
+def ppo_cfg4_block(local_rank, rank, world, dist, K, W, E_total=4096, T=2048, batch=65536, epochs=2, critic_targets=10, critic_steps=10,
+                   acm_batches=100, acm_ring=110_000):
+    """BASELINE config 4 -- SPP-PPO Walker2d shapes, 4096 vectorised synthetic envs x 2048-step rollouts -- as WHOLE iterations of
+    PPO_AcM.perform_iteration (on_policy.py:55-86): device rollout -> critic fit (10 x 10 full-batch steps) -> GAE -> advantage
+    normalisation -> clipped-ratio actor epochs (65 536-row global minibatches) -> add_buffer -> ACM update batches.  Environments
+    shard over ranks (strong scaling: the 4096 environments are fixed); every optimiser step all-reduces the gradient vector with
+    NCCL inside the library.  The ACM replicas regress on their own rank's ring (local ACMs, no collective)."""
+    import numpy as np
+    import torch
+
+    from spp_rl_b200 import Population
+    from spp_rl_b200.ppo import PpoPolicy
+
+    ob, ac = 17, 6
+    if E_total % world:
+        return {"skipped": "environments do not divide over %d ranks" % world}
+    El = E_total // world
+    N, Nl = E_total * T, El * T
+    rng = np.random.RandomState(3)
+    mn, mx = (-rng.rand(ob) * 2 - 0.5).astype(np.float32), (rng.rand(ob) * 2 + 0.5).astype(np.float32)
+    pol = PpoPolicy(ob, ac, max_rows=Nl, max_batch_rows=batch, device=local_rank, min_max_denormalize=True, norm_closs=True, gamma=0.99,
+                    gae_lambda=0.95, custom_loss=0.5, entropy_coef=0.0, actor_lr=3e-4, critic_lr=3e-4)
+    pol.set_norm_stats(mn, mx)
+    for net, out in (("actor", ob), ("critic", 1)):
+        sd = {}
+        for name, o, i in (("fc1", 64, ob), ("fc2", 64, 64), ("fc3", out, 64)):
+            b = 1 / np.sqrt(i)
+            sd[name + ".weight"] = rng.uniform(-b, b, (o, i)).astype(np.float32)
+            sd[name + ".bias"] = rng.uniform(-b, b, (o,)).astype(np.float32)
+        if net == "actor":
+            sd["log_scale"] = np.full((ob,), -1.34, np.float32)
+        pol.load_state_dict(net, sd)
+    pop = Population(algo="ddpg", ob_dim=ob, ac_dim=ac, population=1, device=local_rank, acm_kind="acm", acm_critic=True, min_max_denormalize=True,
+                     update_batch_size=64, acm_batch_size=256, buffer_size=acm_ring, store_actions=False, acm_lr=1e-4)
+    pop.set_norm_stats(mn, mx)
+    pop.set_limits(np.ones(ob, np.float32), np.ones(ac, np.float32))
+    if world > 1:
+        pol.comm_init(dist)
+    st = pol._ext_stream()
+    gen = torch.Generator(device="cuda")
+    phases = {}
+
+    def iteration(i, timed):
+        t = [time.perf_counter()]
+        pol.rollout_synthetic(pop, El, T, max_ep_len=1000, done_prob=0.001, seed=1000 * i + rank, reset_envs=(i == 0))
+        pol.set_global_rows(N)
+        pol.sync(); t.append(time.perf_counter())
+        gen.manual_seed(77 + i)      # the same global permutations on every rank
+        with torch.cuda.stream(st):
+            perms = [torch.randperm(N, device="cuda", generator=gen) for _ in range(epochs)]
+        res = pol.iteration_dp(perms, batch, E_total, 1e9, critic_targets, critic_steps, rank, world)
+        t.append(time.perf_counter())
+        pop.ring_add_rollout_store(0, pol)
+        t.append(time.perf_counter())
+        pop.acm_update_ring(acm_batches, idx=None, seed=5 + i)
+        pop.sync(); t.append(time.perf_counter())
+        if timed:
+            for name, dt in (("rollout", t[1] - t[0]), ("add_buffer", t[3] - t[2]), ("acm_update", t[4] - t[3])):
+                phases[name] = phases.get(name, 0.0) + dt * 1e3
+            for name, v in res["phases_ms"].items():
+                phases[name] = phases.get(name, 0.0) + v
+        return res
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for w in range(max(W, 1)):
+        iteration(w, False)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        res = iteration(max(W, 1) + k, True)
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item()) * 1e3 / K
+    info = pol.comm_info()
+    out = {"workload": "SPP-PPO Walker2d shapes (ob 17, ac 6, hidden 64): %d vectorised synthetic envs x %d steps = %d transitions per iteration; "
+                       "whole PPO_AcM.perform_iteration on the device" % (E_total, T, N),
+           "scaling": "strong", "n_gpus": world, "ms_per_iteration": ms, "transitions_per_s": N / (ms * 1e-3),
+           "phases_ms_rank0": {k: v / K for k, v in phases.items()}, "critic_steps": critic_targets * critic_steps, "actor_epochs": res["epochs"],
+           "global_minibatch": batch, "allreduces_per_iteration": res["allreduces"], "nccl_version": info["nccl_version"],
+           "acm_update_batches": acm_batches, "critic_loss": res["critic_loss"], "kl": res["kl"],
+           "timing": "host clock between barriers + device synchronisation on both sides (the iteration spans two streams and host index work), max over ranks"}
+    pol.close(); pop.close()
+    return out
+
+
+def population_train_block(local_rank, rank, world, dist, name, algo, ob, ac, agents_per_gpu, frames, warm_frames, ring=60_000, envs_per_agent=1):
+    """BASELINE configs 3 / 5 through the population-batched train loop (Population.train_synthetic): rollout -> update bursts ->
+    ACM batches -> ring statistics, scheduled as ddpg.py:191-237 / ddpg_acm.py:52-85 (update_freq 50, grad_steps 50, random_frames 100,
+    iterations of 1000 frames); agents shard over ranks with no collective.  frames/s = env frames of all agents / wall time."""
+    import numpy as np
+    import torch
+
+    from spp_rl_b200 import Population, init_state
+
+    pop = Population(algo=algo, ob_dim=ob, ac_dim=ac, population=agents_per_gpu, device=local_rank, acm_kind="acm", acm_critic=True,
+                     min_max_denormalize=True, update_batch_size=B, acm_batch_size=128, buffer_size=ring, store_actions=False,
+                     gamma=0.99, tau=0.005, actor_lr=1e-3, critic_lr=1e-3, custom_loss=0.2)
+    pop.set_limits(np.ones(ob, np.float32), np.ones(ac, np.float32))
+    pop.set_norm_stats(-np.ones(ob, np.float32), np.ones(ob, np.float32))
+    for a in range(agents_per_gpu):
+        s0 = init_state(algo, ob, ac, 1000 + rank * agents_per_gpu + a, "acm", True)
+        for net in (("actor", "critic_1", "critic_2", "acm") if algo == "sac" else ("actor", "critic", "acm")):
+            pop.load_state_dict(net, {k[len(net) + 1:]: v for k, v in s0.items() if k.startswith(net + ".")}, agent=a)
+    pop.sync_targets()
+    kw = dict(envs_per_agent=envs_per_agent, update_freq=50, grad_steps=50, random_frames=100, act_noise=0.1, steps_per_epoch=1000,
+              acm_update_freq=200, acm_update_batches=10, update_stats=True, seed=rank)
+    st = pop.train_synthetic(warm_frames, **kw)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    st = pop.train_synthetic(frames, state=st, **kw)
+    pop.sync(); torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    upd = sum(e[1] for e in st["launch_log"] if e[0] == "update") * agents_per_gpu * world
+    out = {"workload": name, "scaling": "weak", "n_gpus": world, "agents_per_gpu": agents_per_gpu, "frames_per_agent": frames,
+           "frames_per_s": agents_per_gpu * world * frames / dt, "updates_per_s": upd / dt, "seconds": dt,
+           "launches": {k: sum(1 for e in st["launch_log"] if e[0] == k) for k in ("rollout", "update", "acm", "stats")},
+           "ring_capacity": ring, "envs_per_agent": envs_per_agent}
+    pop.close()
+    return out
+
+
 def main():
     global G
     ap = argparse.ArgumentParser()
@@ -284,6 +418,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variant", action="store_true", help="skip the reduced-precision (single tf32 pass) extra measurement")
     ap.add_argument("--no-rollout", action="store_true", help="skip the rollout (transitions/s) half of the metric")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the SPP-PPO config-4 whole-iteration block")
+    ap.add_argument("--no-train-loop", action="store_true", help="skip the population train-loop blocks (configs 3 and 5)")
     ap.add_argument("--rollout-envs", type=int, default=256, help="vectorised synthetic environments per agent")
     ap.add_argument("--rollout-steps", type=int, default=32, help="environment steps per rollout launch")
     args = ap.parse_args()
@@ -513,6 +649,19 @@ def main():
                   "note": "ring_gather_bench_kernel: B*((2 ob + ac + 1)*4 + 1) bytes read and written per row + two 4-byte index "
                           "words; random 44-byte rows of a %.1f GB ring, DRAM sectors moved per row are in profiles/" % (P * RINGC * 114 / 1e9)}
 
+    # ---- BASELINE configs 3 / 5 through the population train loop, config 4 as whole SPP-PPO iterations (all ranks take part)
+    pop.close()
+    pop = None
+    train_loop = None
+    if not args.no_train_loop:
+        train_loop = [population_train_block(local_rank, rank, world, dist, "config 3: SPP-DDPG HalfCheetah shapes (ob 17, ac 6), 256 independent agents per GPU",
+                                             "ddpg", 17, 6, 256, 1000, 500),
+                      population_train_block(local_rank, rank, world, dist, "config 5: SPP-SAC Ant shapes (ob 111, ac 8), 128 agents per GPU (1024 over 8 GPUs)",
+                                             "sac", 111, 8, 128, 500, 500)]
+    ppo_cfg4 = None
+    if not args.no_ppo:
+        ppo_cfg4 = ppo_cfg4_block(local_rank, rank, world, dist, max(1, min(K, 3)), 1)
+
     if rank == 0:
         peaks = {}
         try:
@@ -550,7 +699,7 @@ def main():
                          "kernel": "update_burst_kernel<SAC>", "kernel_ms": statistics.mean(kern_ms),
                          "note": "256-wide GEMMs on tcgen05 kind::tf32, 3-pass hi/lo split with per-chunk fp32 drain (1e-5 parity); "
                                  "achieved counts algorithmic fp32 FLOPs (each is 3 tensor-core passes); peak is the dense bf16 figure"},
-            "rollout": rollout, "gather": gather, "reduced_precision_variant": variant, "cpu_baseline": cpu_base, "clocks": clocks,
+            "rollout": rollout, "gather": gather, "train_loop": train_loop, "ppo_cfg4": ppo_cfg4, "reduced_precision_variant": variant, "cpu_baseline": cpu_base, "clocks": clocks,
         }
         if rollout is not None:
             rollout["roofline"]["peak"] = peak
@@ -558,7 +707,8 @@ def main():
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
-    pop.close()
+    if pop is not None:
+        pop.close()
 
 
 if __name__ == "__main__":

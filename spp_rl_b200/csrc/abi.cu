@@ -551,33 +551,44 @@ int spp_ring_add_rollout_store(spp_population* p, int a, spp_ppo* store) {
     CK(cudaSetDevice(p->device));
     const int E = st.E, T = st.T;
     const int64_t N = (int64_t)E * T, S = p->S;
-    std::vector<float> end((size_t)N);
-    CK(cudaStreamSynchronize(st.stream));
-    CK(cudaMemcpy(end.data(), st.end, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    // `end` flags, environment-major (the order the chain is walked in), one byte each
+    std::vector<uint8_t> endT((size_t)N);
+    {
+        std::vector<float> end((size_t)N);
+        CK(cudaStreamSynchronize(st.stream));
+        CK(cudaMemcpy(end.data(), st.end, (size_t)N * 4, cudaMemcpyDeviceToHost));
+        constexpr int kB = 64;      // blocked transpose [T][E] -> [E][T]
+        for (int t0 = 0; t0 < T; t0 += kB)
+            for (int e0 = 0; e0 < E; e0 += kB)
+                for (int t = t0; t < T && t < t0 + kB; ++t)
+                    for (int e = e0; e < E && e < e0 + kB; ++e)
+                        endT[(size_t)e * T + t] = (end[(size_t)t * E + e] != 0.f || t == T - 1) ? 1 : 0;
+    }
     constexpr int64_t kNext = 1ll << 62;
-    std::vector<int64_t> chain; chain.reserve((size_t)N + N / 64 + E + 1);
-    std::vector<uint8_t> joint; joint.reserve(chain.capacity() + 1);
-    for (int e = 0; e < E; ++e)
-        for (int t = 0; t < T; ++t) {
-            const int64_t row = (int64_t)t * E + e;
-            chain.push_back(row); joint.push_back(0);
-            if (end[row] != 0.f || t == T - 1) { chain.push_back(row | kNext); joint.push_back(0); if (joint.size() < chain.capacity()) {} }
+    // The chain is never materialised: a cursor walks it.  Chain entries, in order: for every transition q (environment-major) its
+    // observation, followed by its NEXT observation when the transition ends a rollout; the entry after a terminal one is a joint.
+    struct ChainCursor {      // (e, t) kept incrementally: no 64-bit division in the 8 M-step walk
+        const uint8_t* endT; int64_t q; int e, t; bool terminal; bool joint; int E, T; int64_t N;
+        int64_t src() const { const int64_t row = (int64_t)t * E + e; return terminal ? (row | kNext) : row; }
+        void advance() {
+            if (!terminal && q < N && endT[q]) { terminal = true; joint = false; }
+            else { joint = terminal; terminal = false; ++q; if (q < N && ++t == T) { t = 0; ++e; } }
         }
-    // joint[i] = 1 where a new rollout starts (position after every terminal observation)
-    joint.push_back(0);
-    for (size_t i = 0; i < chain.size(); ++i) if (chain[i] & kNext) joint[i + 1] = 1;
+    } c{endT.data(), 0, 0, 0, false, false, E, T, N};
     std::vector<int64_t> obs_src((size_t)S, -1), ts_src((size_t)S, -1);
     std::vector<int32_t> ts_oidx((size_t)S, 0), ts_nidx((size_t)S, 0);
     int64_t obs_cur = p->obs_cur[a], ts_cur = p->ts_cur[a], cur_len = p->cur_len[a];
-    auto add_obs = [&](int64_t src) { const int64_t i = obs_cur; obs_src[i] = src; obs_cur = (i + 1) % S; return i; };
-    size_t i = 0;
-    int64_t obs_idx = add_obs(chain[0]);
+    auto add_obs = [&](int64_t src) { const int64_t i = obs_cur; obs_src[i] = src; obs_cur = i + 1 == S ? 0 : i + 1; return i; };
+    int64_t obs_idx = add_obs(c.src());
+    int ke = 0, kt = 0;                                // the k-th ACM action in environment-major order is store row kt * E + ke
     for (int64_t k = 0; k < N; ++k) {
-        ++i;
-        const int64_t next_idx = add_obs(chain[i]);
-        if (joint[i]) { ++i; continue; }
+        const int64_t krow = (int64_t)kt * E + ke;
+        if (++kt == T) { kt = 0; ++ke; }
+        c.advance();                                   // i += 1
+        const int64_t next_idx = add_obs(c.src());
+        if (c.joint) { c.advance(); continue; }        // a new rollout starts here: i += 1, no timestep (quirk 19)
         const int64_t ts = ts_cur;
-        ts_src[ts] = (k % T) * E + k / T;      // the k-th ACM action in environment-major order
+        ts_src[ts] = krow;
         ts_oidx[ts] = (int32_t)obs_idx; ts_nidx[ts] = (int32_t)next_idx;
         if (next_idx < ts) { cur_len = ts + 1; ts_cur = 0; } else ts_cur = ts + 1;      // replay_buffer.py:70-75
         cur_len = ts_cur > cur_len ? ts_cur : cur_len;

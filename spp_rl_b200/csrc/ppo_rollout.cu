@@ -31,6 +31,7 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ in, int ldi
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 2
         for (int k = 0; k < K; k += 4) {      // K is a multiple of 4 (padded layouts, pad weights are zero)
             float w[4];
 #pragma unroll
@@ -73,6 +74,8 @@ __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant_
     float* pa = ms + kRolloutRows * a.ldm2;        // [32][lda]
     float* obs = pa + kRolloutRows * lda;          // [32][ldo]   raw observation of every environment
     int* eplen = reinterpret_cast<int*>(obs + kRolloutRows * ldo);      // [32]
+    int* flags = eplen + kRolloutRows;                                  // [32]
+    float* mixv = reinterpret_cast<float*>(flags + kRolloutRows);       // [32]
     const int total = kRolloutRows * (ldm + 2 * kPpoHidden + ldo + a.ldm1 + 2 * a.ldm2 + lda + ldo);
     for (int i = threadIdx.x; i < total; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
@@ -107,25 +110,23 @@ __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant_
         __syncthreads();
         dense_rows<2, true, false>(h2, kPpoHidden, kPpoHidden, a.actor + l2.off_wt, l2.ld_t, a.actor + l2.off_b, ob, mean, ldo, R, lim);
         __syncthreads();
-        // 3. sample, log-prob, denormalised target (one thread per environment: the log-prob sum runs j ascending as torch's sum(-1))
-        for (int r = threadIdx.x; r < R; r += blockDim.x) {
-            float lp = 0.f;
-            for (int j = 0; j < ob; ++j) {
-                float nz;
-                if (a.noise_act) nz = a.noise_act[(row0 + r) * ob + j];
-                else {
-                    const uint4 w = Philox::gen(a.seed, (uint64_t)t, (uint64_t)(e0 + r) * 128 + j);
-                    nz = normal_from_bits(w.x, w.y);
-                }
-                const float sd = expf(ls[j]);
-                const float mu = mean[r * ldo + j];
-                const float act = __fadd_rn(mu, __fmul_rn(nz, sd));
-                const float d = __fsub_rn(act, mu);
-                lp += __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, __fmul_rn(sd, sd))), logf(sd)), kLogSqrt2Pi);
-                a.act[(row0 + r) * ldo + j] = act;
-                xin[r * ldm + ldo + j] = a.denorm_out ? __fadd_rn(doff[j], __fmul_rn(act, dsc[j])) : act;
+        // 3. sample, denormalised target: one thread per (environment, column); the log-prob terms are left in `mean` (in place)
+        //    and summed j ascending -- torch's sum(-1) order -- by the environment's thread in stage 5a
+        for (int i = threadIdx.x; i < R * ob; i += blockDim.x) {
+            const int r = i / ob, j = i % ob;
+            float nz;
+            if (a.noise_act) nz = a.noise_act[(row0 + r) * ob + j];
+            else {
+                const uint4 w = Philox::gen(a.seed, (uint64_t)t, (uint64_t)(e0 + r) * 128 + j);
+                nz = normal_from_bits(w.x, w.y);
             }
-            a.logp[row0 + r] = lp;
+            const float sd = expf(ls[j]);
+            const float mu = mean[r * ldo + j];
+            const float act = __fadd_rn(mu, __fmul_rn(nz, sd));
+            const float d = __fsub_rn(act, mu);
+            mean[r * ldo + j] = __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, __fmul_rn(sd, sd))), logf(sd)), kLogSqrt2Pi);
+            a.act[(row0 + r) * ldo + j] = act;
+            xin[r * ldm + ldo + j] = a.denorm_out ? __fadd_rn(doff[j], __fmul_rn(act, dsc[j])) : act;
         }
         __syncthreads();
         // 4. ACM (AcM: tanh-tanh-tanh * action limit; BasicAcM: skip connection and learnable gains)
@@ -146,53 +147,58 @@ __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant_
                                        a.acm + M.L[4].off_w + 4);
         }
         __syncthreads();
-        // 5. environment step + store (one thread per environment)
+        // 5a. per environment: log-prob sum, action mix, episode bookkeeping (flags[r]: bit 0 done, bit 1 end)
         for (int r = threadIdx.x; r < R; r += blockDim.x) {
             const int e = e0 + r;
+            float lp = 0.f;
+            for (int j = 0; j < ob; ++j) lp += mean[r * ldo + j];
+            a.logp[row0 + r] = lp;
             float mix = 0.f;
             for (int j = 0; j < ac; ++j) {
                 const float v = pa[r * lda + j];
                 if (a.aacm) a.aacm[(row0 + r) * lda + j] = v;
                 mix += v * (0.3f + 0.1f * (float)j);
             }
-            mix = tanhf(mix);
-            float u_done, rew = 0.f;
-            uint4 wd = make_uint4(0, 0, 0, 0);
+            mixv[r] = tanhf(mix);
+            float u_done;
             if (a.u_done) u_done = a.u_done[row0 + r];
-            else { wd = Philox::gen(a.seed ^ 0xD0Eull, (uint64_t)t, (uint64_t)e); u_done = (float)(wd.x >> 8) * (1.0f / 16777216.0f); }
+            else { const uint4 wd = Philox::gen(a.seed ^ 0xD0Eull, (uint64_t)t, (uint64_t)e); u_done = (float)(wd.x >> 8) * (1.0f / 16777216.0f); }
             const int len = eplen[r] + 1;
             const bool done = u_done < a.done_prob;
             const bool end = done || len == a.max_ep_len;
-            for (int j = 0; j < ob; ++j) {
-                float nz;
-                if (a.noise_env) nz = a.noise_env[(row0 + r) * ob + j];
-                else {
-                    const uint4 w = Philox::gen(a.seed ^ 0xE9Full, (uint64_t)t, (uint64_t)e * 128 + j);
-                    nz = normal_from_bits(w.x, w.y);
-                }
-                const float o = obs[r * ldo + j];
-                const float nx = 0.98f * o + 0.1f * mix * (1.f - 0.01f * (float)j) + 0.02f * nz;
-                if (j == 0) rew = nx;
-                float v = __fdiv_rn(__fsub_rn(nx, nsub[j]), ndiv[j]);
-                if (a.clamp) v = fminf(fmaxf(v, -10.f), 10.f);
-                a.xn[(row0 + r) * ldo + j] = v;
-                if (a.raw_next) a.raw_next[(row0 + r) * ldo + j] = nx;
-                float nxt = nx;
-                if (end) {      // env.reset(): the next rollout of this environment starts here
-                    float rz;
-                    if (a.noise_reset) rz = a.noise_reset[(row0 + r) * ob + j];
-                    else {
-                        const uint4 w = Philox::gen(a.seed ^ 0x5E7ull, (uint64_t)t, (uint64_t)e * 128 + j);
-                        rz = normal_from_bits(w.x, w.y);
-                    }
-                    nxt = 0.1f * rz;
-                }
-                obs[r * ldo + j] = nxt;
-            }
-            a.rew[row0 + r] = rew;
+            flags[r] = end ? 1 : 0;
             a.done[row0 + r] = (done && len != a.max_ep_len) ? 1.f : 0.f;      // a2c.py:170: done = False if ep_len == max_ep_len else done
             a.end[row0 + r] = (end || t == a.T - 1) ? 1.f : 0.f;               // the batch cuts every trajectory at its last step
             eplen[r] = end ? 0 : len;
+        }
+        __syncthreads();
+        // 5b. environment step + store, one thread per (environment, column)
+        for (int i = threadIdx.x; i < R * ob; i += blockDim.x) {
+            const int r = i / ob, j = i % ob, e = e0 + r;
+            float nz;
+            if (a.noise_env) nz = a.noise_env[(row0 + r) * ob + j];
+            else {
+                const uint4 w = Philox::gen(a.seed ^ 0xE9Full, (uint64_t)t, (uint64_t)e * 128 + j);
+                nz = normal_from_bits(w.x, w.y);
+            }
+            const float o = obs[r * ldo + j];
+            const float nx = 0.98f * o + 0.1f * mixv[r] * (1.f - 0.01f * (float)j) + 0.02f * nz;
+            if (j == 0) a.rew[row0 + r] = nx;
+            float v = __fdiv_rn(__fsub_rn(nx, nsub[j]), ndiv[j]);
+            if (a.clamp) v = fminf(fmaxf(v, -10.f), 10.f);
+            a.xn[(row0 + r) * ldo + j] = v;
+            if (a.raw_next) a.raw_next[(row0 + r) * ldo + j] = nx;
+            float nxt = nx;
+            if (flags[r]) {      // env.reset(): the next rollout of this environment starts here
+                float rz;
+                if (a.noise_reset) rz = a.noise_reset[(row0 + r) * ob + j];
+                else {
+                    const uint4 w = Philox::gen(a.seed ^ 0x5E7ull, (uint64_t)t, (uint64_t)e * 128 + j);
+                    rz = normal_from_bits(w.x, w.y);
+                }
+                nxt = 0.1f * rz;
+            }
+            obs[r * ldo + j] = nxt;
         }
         __syncthreads();
     }
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant_
 
 size_t ppo_rollout_smem_bytes(const PpoRolloutArgs& a) {
     const int ldo = a.L.ldo;
-    return (size_t)kRolloutRows * (2 * ldo + 2 * kPpoHidden + ldo + a.ldm1 + 2 * a.ldm2 + a.lda + ldo) * 4 + kRolloutRows * 4 + 16;
+    return (size_t)kRolloutRows * (2 * ldo + 2 * kPpoHidden + ldo + a.ldm1 + 2 * a.ldm2 + a.lda + ldo) * 4 + 3 * kRolloutRows * 4 + 16;
 }
 
 cudaError_t launch_ppo_rollout(const PpoRolloutArgs& a, cudaStream_t s) {

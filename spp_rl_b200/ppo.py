@@ -113,6 +113,11 @@ class PpoPolicy:
                                                  int(bool(denormalize_actor_out)), int(bool(reset_envs)), *[_ptr(v, C.c_float) for v in arrs]))
         self.N = self.Ntot = int(envs) * int(steps)
 
+    def set_global_rows(self, n_global):
+        """Data-parallel runs: the loss means are over the rows of ALL ranks (spp_ppo_set_global_rows)."""
+        check(self.lib.spp_ppo_set_global_rows(self.h, int(n_global)))
+        self.Ntot = int(n_global)
+
     def store(self, name):
         """One column of the loaded rows ("x", "xn", "act", "raw_obs", "raw_next", "aacm", "logp", "rew", "done", "end", "adv", "v")."""
         w = {"x": self.ob_dim, "xn": self.ob_dim, "act": self.ob_dim, "raw_obs": self.ob_dim, "raw_next": self.ob_dim, "aacm": self.ac_dim}.get(name, 0)
@@ -236,17 +241,19 @@ class PpoPolicy:
         self.normalize_adv()
         self.sync()
         t2 = time.perf_counter()
-        perms = np.ascontiguousarray(perms, np.int64)
-        N = perms.shape[1]
+        on_device = isinstance(perms, (list, tuple)) and len(perms) > 0 and torch.is_tensor(perms[0])      # epoch permutations already on the device
+        if not on_device:
+            perms = np.ascontiguousarray(perms, np.int64)
+        N = int(perms[0].numel()) if on_device else perms.shape[1]
         nb = (N + batch - 1) // batch
         ng = np.minimum(batch, N - batch * np.arange(nb)).astype(np.int64)
         kl, ran = 0.0, 0
         st = self._ext_stream()
-        for ep in range(perms.shape[0]):
+        for ep in range(len(perms)):
             if kl >= kl_threshold:
                 break
             with torch.cuda.stream(st):      # the epoch's permutation goes to the device once; the rank filters its rows there
-                perm_dev = torch.from_numpy(perms[ep]).to("cuda", non_blocking=False)
+                perm_dev = perms[ep] if on_device else torch.from_numpy(perms[ep]).to("cuda", non_blocking=False)
                 if world > 1:
                     ids, off = epoch_local_minibatches_device(perm_dev, batch, E, rank, world)
                 else:

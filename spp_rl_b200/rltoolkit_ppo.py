@@ -143,12 +143,15 @@ class PPO_AcM:
     NET_ATTRS = ("actor", "critic", "acm")
 
     def __init__(self, env=None, acm_model="acm", device=0, **kw):
-        unknown = set(kw) - set(PPO_DEFAULTS) - {"log_all", "evals", "max_frames"}
+        unknown = set(kw) - set(PPO_DEFAULTS) - {"log_all", "evals", "max_frames", "vector_envs"}
         if unknown:
             raise TypeError("unexpected keyword arguments: %s" % sorted(unknown))
         c = dict(PPO_DEFAULTS)
         c.update(kw)
         self.__dict__.update({k: c[k] for k in PPO_DEFAULTS})
+        # extension (not in the reference): vector_envs = E > 0 runs collect_batch as ONE device launch over E synthetic environments
+        # (batch_size // E steps each) instead of one Python step per frame; only with the offline synthetic stand-in environment
+        self.vector_envs = int(c.get("vector_envs", 0) or 0)
         assert self.iterations > 0, "Iteration has to be positive not %r" % (self.iterations,)
         if not (self.min_max_denormalize and self.denormalize_actor_out):
             raise NotImplementedError("the device path covers the published SPP-PPO setting: min_max_denormalize=True, denormalize_actor_out=True")
@@ -379,7 +382,44 @@ class PPO_AcM:
         self.kl_div_updates_counter += min(epochs + 1, self.max_ppo_epochs)      # the reference adds i + 1, i = loop index at exit
         self.last_kl = kl
 
+    def perform_iteration_device(self):
+        """perform_iteration (on_policy.py:55-86) with every stage on the device: vectorised rollout into the [T][E] store
+        (spp_ppo_rollout_synthetic) -> critic fit -> GAE -> advantage normalisation -> actor epochs -> add_buffer
+        (spp_ring_add_rollout_store) -> ACM update -> statistics.  The permutations of the actor epochs still come from torch's
+        generator as the reference's DataLoader draws them."""
+        if not isinstance(self.env, _envs.SyntheticControl):
+            raise RuntimeError("vector_envs needs the synthetic stand-in environment (the device loop has no MuJoCo)")
+        E = self.vector_envs
+        T = max(1, -(-self.batch_size // E))
+        if E * T > self.batch_size + self.max_ep_len:
+            raise ValueError("vector_envs * steps exceeds the policy's row capacity (batch_size + max_ep_len)")
+        self._iter_seed = getattr(self, "_iter_seed", int(torch.randint(0, 2 ** 31 - 1, (1,)).item())) + 1
+        self._pol.rollout_synthetic(self._pop, E, T, max_ep_len=self.max_ep_len, done_prob=0.004, seed=self._iter_seed,
+                                    denormalize_actor_out=self.denormalize_actor_out, reset_envs=(self.iteration == 0))
+        n = E * T
+        self.stats_logger.frames += n
+        self.loss["critic"] = self._pol.update_critic(self.critic_num_target_updates, self.num_critic_updates_per_target)
+        self._pol.advantages(want_host=False)
+        if self.normalize_adv:
+            self._pol.normalize_adv()
+        perms = torch.stack([sampler_permutation(n) for _ in range(self.max_ppo_epochs)]).numpy()
+        losses, epochs, kl = self._pol.update_actor(perms, self.ppo_batch_size, self.kl_div_threshold, self.max_ppo_epochs)
+        self.loss.update({k: float(v) for k, v in losses.items()})
+        self.kl_div_updates_counter += min(epochs + 1, self.max_ppo_epochs)
+        self.last_kl = kl
+        self._pop.ring_add_rollout_store(0, self._pol)
+        if self.acm_update_freq and self.iteration % self.acm_update_freq == 0:
+            if self.acm_update_batches:
+                self.update_acm_batches(self.acm_update_batches)
+            else:
+                self.update_acm(self.acm_epochs)
+        if self.denormalize_actor_out:
+            self.replay_buffer = self.update_obs_mean_std(self.replay_buffer)
+        return None
+
     def perform_iteration(self):
+        if self.vector_envs:
+            return self.perform_iteration_device()
         self.buffer = RolloutMemory(self.min_obs, self.max_obs, self.obs_mean, self.obs_std, self.min_max_denormalize)
         self.collect_batch(self.buffer)                               # on_policy.py:55-86
         advantages = self.update_critic(self.buffer)

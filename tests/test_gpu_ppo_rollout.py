@@ -40,7 +40,6 @@ def _setup(ob, ac, acm_kind, rows, ring, seed=5):
 def test_device_rollout_matches_oracle_collect_batch(ob, ac, acm_kind, E, T):
     rng, s, st, pol, pop = _setup(ob, ac, acm_kind, 2 * E * T, 4096)
     max_ep_len, done_prob = 16, 0.05
-    tot = None
     obs0 = ep0 = None
     for call in range(2):      # the second launch continues the environments where the first one left them
         nz = [rng.randn(T, E, ob).astype(np.float32) for _ in range(2)]
@@ -89,3 +88,31 @@ def test_store_to_acm_ring_equals_the_per_transition_add_buffer(ring):
                 continue
             assert np.array_equal(x, y), (call, name)
     pol.close(); pop.close(); pop2.close()
+
+
+def test_ppo_acm_class_runs_whole_iterations_on_the_device():
+    """PPO_AcM(vector_envs=E): perform_iteration with the rollout, the update, add_buffer, the ACM update and the statistics refresh all
+    device-resident (the component parities are the tests above and tests/test_gpu_ppo.py; this checks the class-level plumbing)."""
+    import warnings
+
+    from spp_rl_b200 import envs
+    from spp_rl_b200.rltoolkit_ppo import PPO_AcM
+
+    torch.manual_seed(0); np.random.seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = envs.make("Walker2d-v2", synthetic=True)
+    m = PPO_AcM(env=env, iterations=3, batch_size=2048, vector_envs=64, gamma=0.99, actor_lr=3e-4, critic_lr=3e-4, max_ppo_epochs=4,
+                ppo_batch_size=512, custom_loss=0.5, norm_closs=True, min_max_denormalize=True, denormalize_actor_out=True,
+                acm_pre_train_samples=1500, acm_pre_train_epochs=2, acm_val_buffer_size=200, acm_update_batches=5, acm_batch_size=64)
+    m.pre_train()
+    n0 = len(m.replay_buffer)
+    w0 = {k: getattr(m, k).state_dict()["fc1.weight"].clone() for k in ("actor", "critic", "acm")}
+    m.train()
+    assert m.iteration == 3 and m.stats_logger.frames == 3 * 2048
+    assert len(m.replay_buffer) > 1000 and n0 <= m.buffer_size
+    assert all(np.isfinite(v) for v in m.loss.values()), m.loss
+    for k in ("actor", "critic", "acm"):
+        assert not torch.equal(w0[k], getattr(m, k).state_dict()["fc1.weight"]), k
+    assert m._pol.store("end").sum() >= 64
+    m.close()
