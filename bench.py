@@ -312,24 +312,38 @@ def ppo_cfg4_block(local_rank, rank, world, dist, K, W, E_total=4096, T=2048, ba
     gen = torch.Generator(device="cuda")
     phases = {}
 
+    import threading
+
     def iteration(i, timed):
+        """rollout, then TWO independent halves side by side: the policy update on the policy's stream (this thread) and add_buffer +
+        the ACM regression batches on the population's stream (a second host thread; ctypes drops the GIL inside the library).  The
+        reference runs them one after the other (on_policy.py:55-86), but neither reads what the other writes, so the results are the
+        same; both finish before the next rollout, which needs the updated actor AND the updated ACM."""
         t = [time.perf_counter()]
         pol.rollout_synthetic(pop, El, T, max_ep_len=1000, done_prob=0.001, seed=1000 * i + rank, reset_envs=(i == 0))
         pol.set_global_rows(N)
         pol.sync(); t.append(time.perf_counter())
+        acm_ms = {}
+
+        def acm_side():
+            a0 = time.perf_counter()
+            pop.ring_add_rollout_store(0, pol)
+            a1 = time.perf_counter()
+            pop.acm_update_ring(acm_batches, idx=None, seed=5 + i)
+            pop.sync()
+            acm_ms["add_buffer"], acm_ms["acm_update"] = (a1 - a0) * 1e3, (time.perf_counter() - a1) * 1e3
+        th = threading.Thread(target=acm_side)
+        th.start()
         gen.manual_seed(77 + i)      # the same global permutations on every rank
         with torch.cuda.stream(st):
             perms = [torch.randperm(N, device="cuda", generator=gen) for _ in range(epochs)]
         res = pol.iteration_dp(perms, batch, E_total, 1e9, critic_targets, critic_steps, rank, world)
+        th.join()
         t.append(time.perf_counter())
-        pop.ring_add_rollout_store(0, pol)
-        t.append(time.perf_counter())
-        pop.acm_update_ring(acm_batches, idx=None, seed=5 + i)
-        pop.sync(); t.append(time.perf_counter())
         if timed:
-            for name, dt in (("rollout", t[1] - t[0]), ("add_buffer", t[3] - t[2]), ("acm_update", t[4] - t[3])):
-                phases[name] = phases.get(name, 0.0) + dt * 1e3
-            for name, v in res["phases_ms"].items():
+            phases["rollout"] = phases.get("rollout", 0.0) + (t[1] - t[0]) * 1e3
+            phases["update_and_acm_side_overlapped"] = phases.get("update_and_acm_side_overlapped", 0.0) + (t[2] - t[1]) * 1e3
+            for name, v in list(res["phases_ms"].items()) + list(acm_ms.items()):
                 phases[name] = phases.get(name, 0.0) + v
         return res
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -83,6 +84,7 @@ struct spp_population {
     // staging
     DevBuf d_obs, d_nobs, d_act, d_rew, d_done, d_aacm, d_eps, d_idx, d_losses, d_tmp;
     DevBuf d_roll_scratch, d_env, d_cur;     // rollout: scratch for E rows per agent, synthetic env state, cursors
+    DevBuf d_add_flags, d_add_src[4];        // spp_ring_add_rollout_store staging (kept: cudaMalloc / cudaFree cost 100+ ms next to a busy torch allocator)
     int roll_E = 0;
     Layout L_roll;
     cudaStream_t stream = nullptr;
@@ -177,7 +179,8 @@ int spp_population_destroy(spp_population* p) {
                     (void*)p->r_oidx, (void*)p->r_nidx, (void*)p->r_done, (void*)p->r_end, (void*)p->r_len, (void*)p->scratch_acm})
         if (q) cudaFree(q);
     for (DevBuf* b : {&p->d_obs, &p->d_nobs, &p->d_act, &p->d_rew, &p->d_done, &p->d_aacm, &p->d_eps, &p->d_idx, &p->d_losses, &p->d_tmp, &p->d_roll_scratch, &p->d_env, &p->d_cur,
-                      &p->d_stat_partial, &p->d_stat_moments, &p->d_stat_state, &p->d_stat_hist})
+                      &p->d_stat_partial, &p->d_stat_moments, &p->d_stat_state, &p->d_stat_hist, &p->d_add_flags, &p->d_add_src[0], &p->d_add_src[1],
+                      &p->d_add_src[2], &p->d_add_src[3]})
         b->release();
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -551,19 +554,19 @@ int spp_ring_add_rollout_store(spp_population* p, int a, spp_ppo* store) {
     CK(cudaSetDevice(p->device));
     const int E = st.E, T = st.T;
     const int64_t N = (int64_t)E * T, S = p->S;
-    // `end` flags, environment-major (the order the chain is walked in), one byte each
+    // `end` flags, environment-major (the order the chain is walked in), one byte each: transposed on the device, 1 byte per row D2H
+    const bool dbg_t = getenv("SPP_DEBUG_TIMING") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_a = now();
     std::vector<uint8_t> endT((size_t)N);
     {
-        std::vector<float> end((size_t)N);
-        CK(cudaStreamSynchronize(st.stream));
-        CK(cudaMemcpy(end.data(), st.end, (size_t)N * 4, cudaMemcpyDeviceToHost));
-        constexpr int kB = 64;      // blocked transpose [T][E] -> [E][T]
-        for (int t0 = 0; t0 < T; t0 += kB)
-            for (int e0 = 0; e0 < E; e0 += kB)
-                for (int t = t0; t < T && t < t0 + kB; ++t)
-                    for (int e = e0; e < E && e < e0 + kB; ++e)
-                        endT[(size_t)e * T + t] = (end[(size_t)t * E + e] != 0.f || t == T - 1) ? 1 : 0;
+        CK(p->d_add_flags.ensure((size_t)N));
+        CK(cudaStreamWaitEvent(p->stream, st.ready, 0));      // the rollout that filled the store, not whatever the policy's stream runs now
+        CK(spp::launch_end_flags_env_major(st.end, E, T, (uint8_t*)p->d_add_flags.p, p->stream));
+        CK(cudaMemcpyAsync(endT.data(), p->d_add_flags.p, (size_t)N, cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
     }
+    const double t_b = now();
     constexpr int64_t kNext = 1ll << 62;
     // The chain is never materialised: a cursor walks it.  Chain entries, in order: for every transition q (environment-major) its
     // observation, followed by its NEXT observation when the transition ends a rollout; the entry after a terminal one is a joint.
@@ -579,22 +582,31 @@ int spp_ring_add_rollout_store(spp_population* p, int a, spp_ppo* store) {
     std::vector<int32_t> ts_oidx((size_t)S, 0), ts_nidx((size_t)S, 0);
     int64_t obs_cur = p->obs_cur[a], ts_cur = p->ts_cur[a], cur_len = p->cur_len[a];
     auto add_obs = [&](int64_t src) { const int64_t i = obs_cur; obs_src[i] = src; obs_cur = i + 1 == S ? 0 : i + 1; return i; };
-    int64_t obs_idx = add_obs(c.src());
+    // Slots written more than ~3 ring laps before the end are overwritten later (the observation cursor advances once per step, the
+    // timestep cursor at most once and never runs more than a lap behind): only the cursors are walked there, nothing is recorded.
+    const int64_t k_rec = N - 3 * S - 64;
+    bool rec = k_rec <= 0;
+    auto add_obs_fast = [&]() { const int64_t i = obs_cur; obs_cur = i + 1 == S ? 0 : i + 1; return i; };
+    int64_t obs_idx = rec ? add_obs(c.src()) : add_obs_fast();
     int ke = 0, kt = 0;                                // the k-th ACM action in environment-major order is store row kt * E + ke
     for (int64_t k = 0; k < N; ++k) {
         const int64_t krow = (int64_t)kt * E + ke;
         if (++kt == T) { kt = 0; ++ke; }
+        if (k == k_rec) rec = true;
         c.advance();                                   // i += 1
-        const int64_t next_idx = add_obs(c.src());
+        const int64_t next_idx = rec ? add_obs(c.src()) : add_obs_fast();
         if (c.joint) { c.advance(); continue; }        // a new rollout starts here: i += 1, no timestep (quirk 19)
         const int64_t ts = ts_cur;
-        ts_src[ts] = krow;
-        ts_oidx[ts] = (int32_t)obs_idx; ts_nidx[ts] = (int32_t)next_idx;
+        if (rec) {
+            ts_src[ts] = krow;
+            ts_oidx[ts] = (int32_t)obs_idx; ts_nidx[ts] = (int32_t)next_idx;
+        }
         if (next_idx < ts) { cur_len = ts + 1; ts_cur = 0; } else ts_cur = ts + 1;      // replay_buffer.py:70-75
         cur_len = ts_cur > cur_len ? ts_cur : cur_len;
         obs_idx = next_idx;
     }
-    DevBuf d1, d2, d3, d4;
+    const double t_c = now();
+    DevBuf& d1 = p->d_add_src[0]; DevBuf& d2 = p->d_add_src[1]; DevBuf& d3 = p->d_add_src[2]; DevBuf& d4 = p->d_add_src[3];
     CK(d1.ensure((size_t)S * 8)); CK(d2.ensure((size_t)S * 8)); CK(d3.ensure((size_t)S * 4)); CK(d4.ensure((size_t)S * 4));
     CK(cudaMemcpyAsync(d1.p, obs_src.data(), (size_t)S * 8, cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(d2.p, ts_src.data(), (size_t)S * 8, cudaMemcpyHostToDevice, p->stream));
@@ -606,9 +618,9 @@ int spp_ring_add_rollout_store(spp_population* p, int a, spp_ppo* store) {
                                   (const int32_t*)d3.p, (const int32_t*)d4.p, st, p->stream));
     g_launches++;
     CK(cudaStreamSynchronize(p->stream));
-    d1.release(); d2.release(); d3.release(); d4.release();
     p->obs_cur[a] = obs_cur; p->ts_cur[a] = ts_cur; p->cur_len[a] = cur_len;
     p->len_dirty = true;
+    if (dbg_t) fprintf(stderr, "spp_ring_add_rollout_store: flags %.1f ms, walk %.1f ms, rows %.1f ms\n", t_b - t_a, t_c - t_b, now() - t_c);
     return SPP_OK;
 }
 

@@ -82,6 +82,7 @@ struct spp_ppo {
     float *part = nullptr, *gbuf = nullptr, *scal = nullptr, *gscal = nullptr, *raw = nullptr;
     double* dstats = nullptr;
     int64_t* dperm = nullptr;
+    int64_t* dperm_epoch = nullptr;      // one epoch's permutation (spp_ppo_update_actor), allocated on first use and kept
     int part_stride = 0;
     int step_actor = 0, step_critic = 0;
     ncclComm_t comm = nullptr;  // data-parallel runs (spp_ppo_comm_init): gradients + scalars are all-reduced inside the entry points
@@ -91,6 +92,7 @@ struct spp_ppo {
     // device rollout (spp_ppo_rollout_synthetic): persistent environment state and the extra store columns the ACM ring needs
     float* env_state = nullptr; int* env_len = nullptr; int env_E = 0;
     float* st_aacm = nullptr; float* st_raw_next = nullptr; int st_lda = 0;
+    cudaEvent_t store_ev = nullptr;    // recorded behind the rollout kernel: consumers on other streams wait for it, not for the whole stream
     int store_E = 0, store_T = 0;      // shape of the [T][E] store the last device rollout left (0: rows came from spp_ppo_load_rollout)
     int plain_ppo = 0;          // 1: PPO.update_actor (custom_loss == 0): no distance term, log-prob of the stored actions as they are
     int64_t scratch_rows = 0;
@@ -122,7 +124,7 @@ int spp_ppo_store_view_(spp_ppo* p, PpoStoreView* out) {
     if (!p || !out) return spp_set_error_(SPP_ERR_ARG, "null argument");
     if (p->store_E < 1 || !p->st_aacm) return spp_set_error_(SPP_ERR_STATE, "the policy holds no device rollout (spp_ppo_rollout_synthetic)");
     out->device = p->device; out->E = p->store_E; out->T = p->store_T; out->ob = p->L.ob; out->ldo = p->L.ldo; out->lda = p->st_lda;
-    out->raw_obs = p->raw; out->raw_next = p->st_raw_next; out->aacm = p->st_aacm; out->end = p->d.end; out->stream = p->stream;
+    out->raw_obs = p->raw; out->raw_next = p->st_raw_next; out->aacm = p->st_aacm; out->end = p->d.end; out->stream = p->stream; out->ready = p->store_ev;
     return SPP_OK;
 }
 
@@ -133,7 +135,8 @@ int spp_ppo_destroy(spp_ppo* p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->comm) { nccl().CommDestroy(p->comm); p->comm = nullptr; }
-    for (void* q : {(void*)p->env_state, (void*)p->env_len, (void*)p->st_aacm, (void*)p->st_raw_next}) if (q) cudaFree(q);
+    for (void* q : {(void*)p->env_state, (void*)p->env_len, (void*)p->st_aacm, (void*)p->st_raw_next, (void*)p->dperm_epoch}) if (q) cudaFree(q);
+    if (p->store_ev) cudaEventDestroy(p->store_ev);
     for (void* q : p->allocs) cudaFree(q);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -422,6 +425,10 @@ int spp_ppo_rollout_synthetic(spp_ppo* p, spp_population* pop, int agent, int E,
     a.x = p->d.x; a.xn = p->d.xn; a.act = p->d.act; a.logp = p->d.logp; a.rew = p->d.rew; a.done = p->d.done; a.end = p->d.end;
     a.aacm = p->st_aacm; a.raw_obs = p->raw; a.raw_next = p->st_raw_next;
     a.seed = seed; a.denorm_out = denormalize_actor_out ? 1 : 0; a.clamp = p->cfg.min_max_denormalize ? 0 : 1;
+    {   // environments per CTA: as few as fill two CTAs per SM (the k-chains of a step are split over the spare threads)
+        const int per = (E + 2 * p->sm_count - 1) / (2 * p->sm_count);
+        a.rows_per_cta = per <= 8 ? 8 : per <= 16 ? 16 : per <= 24 ? 24 : 32;
+    }
     float* tmp[4] = {nullptr, nullptr, nullptr, nullptr};
     const float* src[4] = {noise_act, noise_env, u_done, noise_reset};
     const size_t bytes[4] = {(size_t)N * ob * 4, (size_t)N * ob * 4, (size_t)N * 4, (size_t)N * ob * 4};
@@ -435,6 +442,8 @@ int spp_ppo_rollout_synthetic(spp_ppo* p, spp_population* pop, int agent, int E,
     PCK(cudaMemcpyAsync(p->d.traj_len, tl.data(), (size_t)E * 8, cudaMemcpyHostToDevice, s));
     PCK(cudaStreamSynchronize(s));      // ts / tl are host temporaries
     PCK(launch_ppo_rollout(a, s)); spp_count_launch_();
+    if (!p->store_ev) PCK(cudaEventCreateWithFlags(&p->store_ev, cudaEventDisableTiming));
+    PCK(cudaEventRecord(p->store_ev, s));
     p->d.N = N; p->d.Ntot = N; p->d.n_traj = E; p->d.traj_stride = E;
     p->store_E = E; p->store_T = T;
     bool any = false;
@@ -664,8 +673,8 @@ int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int b
     PCK(cudaSetDevice(p->device));
     for (int64_t i = 0; i < (int64_t)max_epochs * N; ++i)
         if (perms[i] < 0 || perms[i] >= N) return spp_set_error_(SPP_ERR_ARG, "permutation index out of range");
-    int64_t* dperm_epoch = nullptr;
-    PCK(cudaMalloc(&dperm_epoch, (size_t)N * 8));
+    if (!p->dperm_epoch) PCK(cudaMalloc(&p->dperm_epoch, (size_t)p->cap_rows * 8));
+    int64_t* dperm_epoch = p->dperm_epoch;
     std::vector<int64_t> off(nb + 1), ng(nb);
     for (int k = 0; k <= nb; ++k) off[k] = (int64_t)k * batch_size < N ? (int64_t)k * batch_size : N;
     for (int k = 0; k < nb; ++k) ng[k] = off[k + 1] - off[k];
@@ -676,9 +685,9 @@ int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int b
     for (i = 0; i < max_epochs; ++i) {
         if (kl >= kl_threshold) break;
         cudaError_t e = cudaMemcpyAsync(dperm_epoch, perms + (size_t)i * N, (size_t)N * 8, cudaMemcpyHostToDevice, p->stream);
-        if (e != cudaSuccess) { cudaFree(dperm_epoch); return spp_set_error_(SPP_ERR_CUDA, cudaGetErrorString(e)); }
+        if (e != cudaSuccess) return spp_set_error_(SPP_ERR_CUDA, cudaGetErrorString(e));
         rc = spp_ppo_actor_epoch_device(p, dperm_epoch, off.data(), ng.data(), nb, log.data());
-        if (rc) { cudaFree(dperm_epoch); return rc; }
+        if (rc) return rc;
         for (int k = 0; k < nb; ++k) {
             const float* sc = log.data() + (size_t)k * w;
             const double n = (double)ng[k];
@@ -693,7 +702,6 @@ int spp_ppo_update_actor(spp_ppo* p, const int64_t* perms, int max_epochs, int b
         }
         ++ran;
     }
-    cudaFree(dperm_epoch);
     // the reference divides by (i + 1) with i the loop variable at exit (one more than the epochs run after an early stop)
     // (PPO_AcM.update_actor_acm, on_policy.py:211-214); plain PPO.update_actor reports the raw sums (ppo.py:186-188)
     const double div = p->plain_ppo ? 1.0 : (double)((i < max_epochs ? i : max_epochs - 1) + 1);

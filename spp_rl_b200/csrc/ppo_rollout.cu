@@ -9,7 +9,7 @@
 // the layout the update kernels read (traj_stride = E).  MuJoCo is unavailable offline: the environment is the synthetic one of the
 // off-policy rollout (obs' = 0.98 obs + 0.1 tanh(a-mix) + 0.02 N(0,1); reward = obs'[0]; done with probability done_prob; time-limit
 // truncation at max_ep_len as in a2c.py:168-171; reset to 0.1 N(0,1)).  Noise comes from Philox, or from injected tensors (tests).
-// Every dot product accumulates k ascending with one fmaf per product, as the FFMA tiles of ppo_act_kernel do.
+// Dot products accumulate k ascending with one fmaf per product inside a k-slice (one slice = the FFMA tiles' order of ppo_act_kernel).
 #include "ppo_rollout.h"
 
 #include "common.cuh"
@@ -19,30 +19,43 @@ namespace spp {
 
 constexpr int kRolloutRows = 32;
 
-// out[r][n] = act(sum_k in[r][k] Wt[k][n] + b[n] (+ t * skip[r][n])) (* scale[n]); thread = (n, row group of 8)
+// out[r][n] = act(sum_k in[r][k] Wt[k][n] + b[n] (+ t * skip[r][n])) (* scale[n]).  A work item is (column n, group of 8 rows); when the CTA
+// has more threads than items the contraction is split over KS adjacent lanes (each a k-slice, summed by a shuffle tree), so that
+// the serial k-chain per thread -- the latency of a rollout step -- shrinks with the number of environments a CTA owns.
 template <int ACT, bool SCALE, bool SKIP>
 __device__ __forceinline__ void dense_rows(const float* __restrict__ in, int ldin, int K, const float* __restrict__ Wt, int ldt,
                                            const float* __restrict__ bias, int N, float* __restrict__ out, int ldout, int R,
                                            const float* __restrict__ scale = nullptr, float* __restrict__ out_pre = nullptr,
                                            const float* __restrict__ skip = nullptr, int ldskip = 0, float t = 0.f) {
-    const int groups = (R + 7) / 8;
-    for (int idx = threadIdx.x; idx < groups * N; idx += blockDim.x) {
+    const int items = ((R + 7) / 8) * N;
+    int KS = 1;
+    while (KS < 8 && items * KS * 2 <= (int)blockDim.x && K / (KS * 2) >= 4) KS *= 2;
+    const int Kc = ((K / 4 + KS - 1) / KS) * 4;      // k per slice, a multiple of 4 (K is: padded layouts, pad weights are zero)
+    for (int base = 0; base < items * KS; base += blockDim.x) {
+        const int w = base + threadIdx.x;
+        const bool active = w < items * KS;
+        const int idx = active ? w / KS : 0, ks = w % KS;
         const int n = idx % N, r0 = (idx / N) * 8;
+        const int k_lo = ks * Kc, k_hi = active ? min(K, k_lo + Kc) : 0;
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll 2
-        for (int k = 0; k < K; k += 4) {      // K is a multiple of 4 (padded layouts, pad weights are zero)
-            float w[4];
+        for (int k = k_lo; k < k_hi; k += 4) {
+            float wv[4];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(Wt + (size_t)(k + kk) * ldt + n);
+            for (int kk = 0; kk < 4; ++kk) wv[kk] = __ldg(Wt + (size_t)(k + kk) * ldt + n);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 v = *reinterpret_cast<const float4*>(in + (size_t)(r0 + i) * ldin + k);      // rows >= R hold zeros
-                acc[i] = fmaf(v.x, w[0], acc[i]); acc[i] = fmaf(v.y, w[1], acc[i]);
-                acc[i] = fmaf(v.z, w[2], acc[i]); acc[i] = fmaf(v.w, w[3], acc[i]);
+                acc[i] = fmaf(v.x, wv[0], acc[i]); acc[i] = fmaf(v.y, wv[1], acc[i]);
+                acc[i] = fmaf(v.z, wv[2], acc[i]); acc[i] = fmaf(v.w, wv[3], acc[i]);
             }
         }
+        for (int o = KS >> 1; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        if (!active || ks != 0) continue;
         const float b = __ldg(bias + n);
         const float sc = SCALE ? __ldg(scale + n) : 1.f;
 #pragma unroll
@@ -60,8 +73,8 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ in, int ldi
 __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant__ PpoRolloutArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int ob = a.L.ob, ldo = a.L.ldo, ac = a.ac, lda = a.lda, ldm = 2 * ldo;
-    const int e0 = blockIdx.x * kRolloutRows;
-    const int R = min(kRolloutRows, a.E - e0);
+    const int e0 = blockIdx.x * a.rows_per_cta;
+    const int R = min(a.rows_per_cta, a.E - e0);
     if (R <= 0) return;
     // shared-memory activations, every row buffer padded to 8-row groups (zero rows beyond R)
     float* xin = sm;                               // [32][ldm]   [x | target]
@@ -215,7 +228,7 @@ cudaError_t launch_ppo_rollout(const PpoRolloutArgs& a, cudaStream_t s) {
     const size_t smem = ppo_rollout_smem_bytes(a);
     cudaError_t e = cudaFuncSetAttribute(ppo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int grid = (a.E + kRolloutRows - 1) / kRolloutRows;
+    const int grid = (a.E + a.rows_per_cta - 1) / a.rows_per_cta;
     ppo_rollout_kernel<<<grid, 256, smem, s>>>(a);
     return cudaGetLastError();
 }

@@ -28,6 +28,7 @@ struct PpoRolloutArgs {
     uint64_t seed;
     int denorm_out;             // denormalize_actor_out
     int clamp;                  // mean-std normalisation clamps to +-10
+    int rows_per_cta;           // environments per CTA: 8, 16, 24 or 32
 };
 
 size_t ppo_rollout_smem_bytes(const PpoRolloutArgs& a);
@@ -49,6 +50,7 @@ struct PpoStoreView {
     const float* aacm;          // [T * E][lda]
     const float* end;           // [T * E]
     cudaStream_t stream;
+    cudaEvent_t ready;          // recorded behind the rollout kernel that filled the store
 };
 
 // device rows of the ACM replay ring written by ring_add_store_kernel: slot s of the obs ring takes obs_src[s] (store row, bit 62 set:
@@ -57,6 +59,8 @@ struct PpoStoreView {
 cudaError_t launch_ring_add_store(float* r_obs, int32_t* r_oidx, int32_t* r_nidx, float* r_aacm, float* r_rew, uint8_t* r_done, uint8_t* r_end,
                                   int64_t S, int ob, int ac, int ldo, int lda, const int64_t* obs_src, const int64_t* ts_src,
                                   const int32_t* ts_oidx, const int32_t* ts_nidx, const PpoStoreView& st, cudaStream_t s);
+
+cudaError_t launch_end_flags_env_major(const float* end, int E, int T, uint8_t* out, cudaStream_t s);
 
 }  // namespace spp
 

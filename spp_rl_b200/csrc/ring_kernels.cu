@@ -120,9 +120,30 @@ __global__ void ring_add_store_kernel(float* r_obs, int32_t* r_oidx, int32_t* r_
     }
 }
 
+// end[t * E + e] (float flags, step-major) -> out[e * T + t] (bytes, environment-major), with the batch cut at t = T - 1 counted as an end
+__global__ void end_flags_env_major_kernel(const float* __restrict__ end, int E, int T, uint8_t* __restrict__ out) {
+    __shared__ uint8_t tile[32][33];
+    const int e0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, e = e0 + threadIdx.x;
+        tile[i][threadIdx.x] = (t < T && e < E && (end[(size_t)t * E + e] != 0.f || t == T - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int e = e0 + i, t = t0 + threadIdx.x;
+        if (e < E && t < T) out[(size_t)e * T + t] = tile[threadIdx.x][i];
+    }
+}
+
 }  // namespace spp
 
 namespace spp {
+
+cudaError_t launch_end_flags_env_major(const float* end, int E, int T, uint8_t* out, cudaStream_t s) {
+    dim3 grid((E + 31) / 32, (T + 31) / 32), block(32, 8);
+    end_flags_env_major_kernel<<<grid, block, 0, s>>>(end, E, T, out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_ring_add_store(float* r_obs, int32_t* r_oidx, int32_t* r_nidx, float* r_aacm, float* r_rew, uint8_t* r_done, uint8_t* r_end,
                                   int64_t S, int ob, int ac, int ldo, int lda, const int64_t* obs_src, const int64_t* ts_src,

@@ -59,7 +59,7 @@ def test_device_rollout_matches_oracle_collect_batch(ob, ac, acm_kind, E, T):
     pol.close(); pop.close()
 
 
-@pytest.mark.parametrize("ring", [5000, 700])
+@pytest.mark.parametrize("ring", [5000, 700, 250])
 def test_store_to_acm_ring_equals_the_per_transition_add_buffer(ring):
     """P7 on device data: spp_ring_add_rollout_store == ReplayBufferAcM.add_buffer driven transition by transition through the ring
     ABI (add_rollouts_to_acm_ring, pinned by the reference fixture in test_gpu_ppo.py), with and without wrap-around; twice in a row."""
