@@ -152,6 +152,9 @@ int spp_acm_update_ring(spp_population* p, int n_batches, const int64_t* idx, in
  * host layout as spp_acm_update_host (the validation set cut into acm_batch_size chunks, last_rows in the final one);
  * losses [P][n_batches] = the MSE of each chunk -- the caller weights them by their row counts. */
 int spp_acm_eval_host(spp_population* p, int n_batches, const float* x, const float* y, int last_rows, float* losses);
+/* obs_norm=True of the off-policy classes: ReplayBuffer._sample_batch normalises obs / next_obs (rltoolkit/buffer/replay_buffer.py:246-248);
+ * the fused ring updates (spp_update_ring*, device or host indices) then gather normalised rows.  spp_update_host takes its batch as given. */
+int spp_set_obs_norm(spp_population* p, int on);
 /* learning rates may change between calls (StepLR on the ACM optimiser, rltoolkit/acm/acm.py:181-183,299); negative = keep */
 int spp_set_learning_rates(spp_population* p, double actor_lr, double critic_lr, double alpha_lr, double acm_lr);
 

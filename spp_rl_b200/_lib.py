@@ -83,6 +83,7 @@ SIGNATURES = {
     "spp_acm_update_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, C.c_int, _f32p]),
     "spp_acm_eval_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, C.c_int, _f32p]),
     "spp_acm_update_ring": (C.c_int, [_vp, C.c_int, _i64p, C.c_int, C.c_uint64, _f32p]),
+    "spp_set_obs_norm": (C.c_int, [_vp, C.c_int]),
     "spp_set_learning_rates": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     "spp_rollout_step_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_double, C.c_int, C.c_int, _f32p, _f32p]),
     "spp_rollout_synthetic_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int, _vp]),

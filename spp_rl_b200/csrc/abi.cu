@@ -475,6 +475,15 @@ int spp_alpha_set(spp_population* p, int a, double log_alpha) {
     return SPP_OK;
 }
 
+// ReplayBuffer._sample_batch normalises obs / next_obs when the buffer was built with obs_norm=True (rltoolkit/buffer/replay_buffer.py:
+// 246-248, gate :76-80): the fused ring updates then gather NORMALISED rows (statistics of spp_set_norm_stats).  Explicit minibatches
+// (spp_update_host) are taken as given -- the reference's update() receives what sample_batch returned.
+int spp_set_obs_norm(spp_population* p, int on) {
+    if (!p) return fail(SPP_ERR_ARG, "null population");
+    p->h.obs_norm = on ? 1 : 0;
+    return SPP_OK;
+}
+
 int spp_set_learning_rates(spp_population* p, double actor_lr, double critic_lr, double alpha_lr, double acm_lr) {
     if (!p) return fail(SPP_ERR_ARG, "null population");
     if (actor_lr >= 0) p->h.actor_lr = actor_lr;

@@ -40,6 +40,7 @@ struct Hyper {
     double actor_lr, critic_lr, alpha_lr, acm_lr;
     int norm_closs;          // custom loss in normalised space (MSE(z, normalize(next_obs)))
     int norm_clamp;          // mean-std normalize clamps to +-10 (utils.standardize_and_clip)
+    int obs_norm;            // sample_batch normalises obs / next_obs (ReplayBuffer._sample_batch, replay_buffer.py:246-248); ring gather only
 };
 
 // per-agent normalisation vectors, each ldo floats: [P][NORM_COUNT][ldo]
@@ -234,11 +235,17 @@ __device__ inline void stage_gather(const Ctx& c, int g) {
             vnd[r] = __fmul_rn(c.a.h.gamma, (float)(1 - done));   // gamma * (1 - done)
         }
         __syncthreads();
+        const bool norm = from_ring && c.a.h.obs_norm;      // explicit minibatches arrive as sample_batch returned them
+        const float* nsub = c.normv(NORM_NSUB); const float* ndiv = c.normv(NORM_NDIV);
         for (int e = threadIdx.x; e < nr * ob; e += kThreads) {
             const int rr = e / ob, j = e - rr * ob, row = r0 + rr;
-            const float o = rp[rr][j];
+            float o = rp[rr][j], n = rp[kThreads + rr][j];
+            if (norm) {
+                o = __fdiv_rn(__fsub_rn(o, nsub[j]), ndiv[j]); n = __fdiv_rn(__fsub_rn(n, nsub[j]), ndiv[j]);
+                if (c.a.h.norm_clamp) { o = fminf(fmaxf(o, -10.f), 10.f); n = fminf(fmaxf(n, -10.f), 10.f); }
+            }
             xo[row * ldo + j] = o;
-            xn[row * ldo + j] = rp[kThreads + rr][j];
+            xn[row * ldo + j] = n;
             xc[row * L.ldc + j] = o;
         }
         for (int e = threadIdx.x; e < nr * L.act_dim; e += kThreads) {

@@ -148,6 +148,10 @@ class Population:
     def set_learning_rates(self, actor_lr=-1.0, critic_lr=-1.0, alpha_lr=-1.0, acm_lr=-1.0):
         check(self.lib.spp_set_learning_rates(self.h, float(actor_lr), float(critic_lr), float(alpha_lr), float(acm_lr)))
 
+    def set_obs_norm(self, on):
+        """obs_norm=True: the fused ring updates gather normalised obs / next_obs (replay_buffer.py:246-248)."""
+        check(self.lib.spp_set_obs_norm(self.h, int(bool(on))))
+
     def sync_targets(self, agent=-1):
         check(self.lib.spp_sync_targets(self.h, agent))
 

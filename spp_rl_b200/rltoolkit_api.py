@@ -321,9 +321,6 @@ class _OffPolicyAcM:
         self.device = torch.device("cpu")      # host tensors; the arithmetic runs on cuda:<device>
         if self.acm_ob_idx is not None and list(self.acm_ob_idx) != list(range(self.ob_dim)):
             raise NotImplementedError("acm_ob_idx subsets are not supported by the device path")
-        if self.obs_norm:
-            raise NotImplementedError("obs_norm=True (normalised minibatches, replay_buffer.py:246-248) is not built for the off-policy "
-                                      "device path; the published SPP-SAC / SPP-DDPG settings leave it off")
         lims = self.env.observation_space.high                       # acm.py:102-108
         if self.min_max_denormalize:
             lims = 1.0
@@ -361,6 +358,7 @@ class _OffPolicyAcM:
             alpha_lr=self.alpha_lr, acm_lr=self.acm_lr, custom_loss=float(self.custom_loss), alpha=self.alpha,
             target_entropy=self.target_entropy)
         pop.set_limits(np.broadcast_to(self.actor_ac_lim.numpy(), (self.ob_dim,)), self.ac_lim.numpy())
+        pop.set_obs_norm(self.obs_norm)          # the fused ring updates gather normalised rows (replay_buffer.py:246-248)
         return pop
 
     # ------------------------------------------------------------------ nets

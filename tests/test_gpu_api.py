@@ -79,6 +79,38 @@ def test_fused_make_update_follows_the_reference_random_streams():
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("min_max", [True, False])
+def test_obs_norm_ring_updates_gather_normalised_rows(min_max):
+    """obs_norm=True (replay_buffer.py:246-248): the fused ring update normalises obs / next_obs inside the gather; it must equal the
+    reference's loop, where sample_batch normalises on the host (torch arithmetic) and update() takes the batch as given."""
+    kw = dict(SCRIPT_KW, grad_steps=3, update_freq=1, random_frames=0, acm_update_freq=10 ** 9, obs_norm=True, min_max_denormalize=min_max)
+    models = []
+    for _ in range(2):
+        torch.manual_seed(5); np.random.seed(5)
+        m = DDPG_AcM(**kw)
+        m.pre_train()
+        models.append(m)
+    a, b = models
+    assert a.replay_buffer.obs_norm and (a.replay_buffer.max_obs is not None)
+    o = a.replay_buffer.sample_batch(8)[0]
+    raw = torch.from_numpy(a._pop.ring_sample_batch(0, np.arange(8))[0])
+    assert not torch.equal(a.replay_buffer.normalize(raw), raw)            # the statistics are not the identity
+    for net in ("actor", "critic", "acm"):
+        b._pop.load_state_dict(net, a._pop.state_dict(net))
+    b._pop.sync_targets(); a._pop.sync_targets()
+    a.stats_logger.frames = b.stats_logger.frames = 7
+    torch.manual_seed(11); np.random.seed(11)
+    a.make_update()                                    # fused: device-side normalisation
+    torch.manual_seed(11); np.random.seed(11)
+    for g in range(3):                                 # the reference's loop (ddpg.py:231-237): host-side normalisation
+        b.update(*b.replay_buffer.sample_batch(b.update_batch_size))
+    for net in ("actor", "critic"):
+        sa, sb = a._pop.state_dict(net), b._pop.state_dict(net)
+        for k in sa:
+            assert np.array_equal(sa[k], sb[k]), (net, k)
+    a.close(); b.close()
+
+
 def test_ddpg_acm_with_basic_acm_runs():
     torch.manual_seed(1); np.random.seed(1)
     m = DDPG_AcM(acm_model="basic", **dict(SCRIPT_KW, env_name="HalfCheetah-v2", custom_loss=1.0, act_noise=0.05))
