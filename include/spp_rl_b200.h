@@ -220,6 +220,9 @@ int spp_ppo_critic_apply(spp_ppo* p);
 int spp_ppo_advantages(spp_ppo* p, float* adv_host);
 int spp_ppo_adv_stats(spp_ppo* p, double out[3]);
 int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats);
+/* the same with the caller's epsilon: A2C normalises with (A - mean) / (std + 1e-8) (rltoolkit/algorithms/a2c/a2c.py:275-277,
+ * rltoolkit/acm/on_policy.py:101-104); eps < 0 = the PPO datasets' 1.2e-7 */
+int spp_ppo_normalize_adv_eps(spp_ppo* p, const double* global_stats, double eps);
 /* PPO_AcM.update_actor_acm (rltoolkit/acm/on_policy.py:164-216): perms [max_epochs][N] replace DataLoader(shuffle=True);
  * keeps the partial last minibatch, takes KL on the last minibatch only, stops when KL >= kl_threshold, and divides the
  * summed losses (actor, entropy, policy, dist) by (i + 1) exactly like the reference.  Step-wise forms as for the critic;
@@ -237,8 +240,16 @@ int spp_ppo_adam_reset(spp_ppo* p, int net);      /* fresh Adam state of one net
 /* 1: the actor epochs are plain PPO.update_actor (rltoolkit/algorithms/ppo/ppo.py:152-192), what PPO_AcM falls back to when
  * custom_loss == 0 (rltoolkit/acm/on_policy.py:88-98): no distance term, the log-prob is taken of the stored actions as they are,
  * and losses[] = {actor, entropy, sum, 0} are the raw sums over minibatches (no division by the epoch count).  0 (default):
- * PPO_AcM.update_actor_acm (on_policy.py:164-216). */
-int spp_ppo_set_actor_mode(spp_ppo* p, int plain_ppo);
+ * PPO_AcM.update_actor_acm (on_policy.py:164-216).
+ * 2: A2C_AcM.update_actor_acm (on_policy.py:100-124): one full-batch policy-gradient step on mean(-logp * adv) -- no ratio, no
+ * entropy term; the distance term carries no gradient (Actor.act samples without rsample, basic_model.py:47) and is reported only
+ * (scalar slot 2).  3: plain A2C.update_actor (a2c.py:267-285; what A2C_AcM runs when custom_loss == 0).  In modes 2 / 3
+ * spp_ppo_advantages returns q - V(s) (A2C.calculate_advantage, a2c.py:227-245) instead of the GAE scan. */
+int spp_ppo_set_actor_mode(spp_ppo* p, int mode);
+/* A2C_AcM.update_actor_acm never calls zero_grad (on_policy.py:117-123): after spp_ppo_actor_minibatch_grad,
+ * accumulate != 0 adds the fresh gradient to the running sum kept since the last spp_ppo_adam_reset(actor) and hands the SUM to
+ * spp_ppo_actor_apply; accumulate == 0 restarts the sum (A2C.update_actor zeroes the gradients, a2c.py:282). */
+int spp_ppo_grad_accumulate(spp_ppo* p, int accumulate);
 /* One epoch with the LOCAL row ids on the device: minibatch k = ids_dev[off[k], off[k+1]) (host offsets, nb + 1 of them; a rank may
  * own none of a minibatch), n_global[k] = rows of minibatch k over all ranks (NULL = local).  No host synchronisation per step;
  * log_host [nb][8 + pad4(ob)] = reduced scalars of every minibatch followed by log_scale as that minibatch saw it. */

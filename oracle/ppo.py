@@ -197,3 +197,47 @@ def update_actor_acm(state, norm_obs, actions, next_obs, old_logp, adv_norm, per
         for k in tot:
             tot[k] /= i + 1
     return tot, epochs_run, kl
+
+
+def a2c_advantages(state, norm_obs, norm_next_obs, reward, done, gamma):
+    """A2C.calculate_advantage, rltoolkit/algorithms/a2c/a2c.py:227-245: q - V(s) with the fitted critic (no GAE)."""
+    p = sub(state, "critic")
+    nv = nets.ppo_critic_fwd(p, norm_next_obs)[0].squeeze(-1)
+    v = nets.ppo_critic_fwd(p, norm_obs)[0].squeeze(-1)
+    return q_values(reward, done, nv, gamma) - v
+
+
+def a2c_actor_step(state, norm_obs, actions, old_logp, adv, lim, lr, accumulate, normalize=True,
+                   custom_loss=0.0, loss_actions=None, next_obs=None):
+    """A2C_AcM.update_actor_acm (rltoolkit/acm/on_policy.py:100-124; accumulate=True) / A2C.update_actor
+    (rltoolkit/algorithms/a2c/a2c.py:267-285; accumulate=False): ONE full-batch step on mean(-logp * adv).
+
+    The log-probs are the ones the rollout recorded (their autograd graph is taken at the current weights: no update
+    happened in between), so the gradient is that of the Gaussian log-density at the stored actions.  The distance term
+    MSE(actions, next_obs) has no gradient path (Actor.act samples without rsample, basic_model.py:47).
+    update_actor_acm never calls zero_grad (quirk 21): the optimiser steps on the SUM of this and all earlier
+    iterations' gradients, kept in state["actor#gacc"].  -> losses dict"""
+    if normalize:
+        adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+    p = sub(state, "actor")
+    n = norm_obs.shape[0]
+    mean, cache = nets.ppo_actor_mean(p, norm_obs, lim)
+    ls = p["log_scale"]
+    actor_loss = (-old_logp * adv).mean()
+    losses = {"actor": float(actor_loss.item())}
+    if custom_loss:
+        dist = ((loss_actions - next_obs) ** 2).mean()
+        losses["dist"] = float(dist.item())
+        losses["policy"] = float((actor_loss + custom_loss * dist).item())
+    dlogp = (-adv / n).unsqueeze(-1)
+    var = torch.exp(ls) ** 2
+    d = actions - mean
+    grads = nets.ppo_actor_mean_bwd(p, cache, dlogp * (d / var), lim)
+    grads["log_scale"] = (dlogp * ((d * d) / var - 1.0)).sum(0)
+    if accumulate:
+        acc = state.setdefault("actor#gacc", {})
+        for k, g in grads.items():
+            acc[k] = acc[k] + g if k in acc else g.clone()
+        grads = {k: v.clone() for k, v in acc.items()}
+    adam_step_net(state, "actor", grads, lr)
+    return losses

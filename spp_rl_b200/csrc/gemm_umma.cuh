@@ -30,12 +30,26 @@
 
 namespace spp {
 
-constexpr int kUmmaAPlane = 128 * 128;                     // A_hi / A_lo: 128 rows x 32 tf32
+#ifndef SPP_UMMA_BK
+#define SPP_UMMA_BK 32      // k-chunk: 32 tf32 (128-byte rows, two 96 KB slots, copies one chunk ahead) or 16 (64-byte rows, four 48 KB slots, three ahead: measured slower, profiles/r02_update_bk16_experiment.md)
+#endif
+constexpr int kBK = SPP_UMMA_BK;
+static_assert(kBK == 16 || kBK == 32, "k-chunk of the tcgen05 pipeline");
+constexpr int kKSteps = kBK / 8;                           // MMAs of k = 8 per pass and chunk
+constexpr int kUmmaAPlane = 128 * kBK * 4;                 // A_hi / A_lo: 128 rows x kBK tf32
 constexpr uint32_t kUmmaSinglePass = 8;   // UmmaCtx::dbg bit: reduced-precision variant (one tf32 pass, whole K in one TMEM accumulator)
-constexpr int kUmmaBPlane = 256 * 128;                     // B_hi / B_lo: 256 columns x 32 tf32
-constexpr int kUmmaSlotBytes = 2 * kUmmaAPlane + 2 * kUmmaBPlane;      // 96 KB
-constexpr int kUmmaSlots = 2;
+constexpr int kUmmaBPlane = 256 * kBK * 4;                 // B_hi / B_lo: 256 columns x kBK tf32
+constexpr int kUmmaSlotBytes = 2 * kUmmaAPlane + 2 * kUmmaBPlane;      // 48 KB (96 KB)
+constexpr int kUmmaSlots = 64 / kBK;                                   // 4 (2)
+constexpr int kUmmaAhead = kUmmaSlots - 1;                             // chunks the copies run ahead of the MMAs
 constexpr int kUmmaSmemBytes = kUmmaSlots * kUmmaSlotBytes;            // 192 KB
+
+namespace umma {   // layouts of one operand chunk for the configured kBK
+__device__ __forceinline__ uint32_t km_offset(int row, int chunk) { return kBK == 32 ? kmajor_offset(row, chunk) : kmajor16_offset(row, chunk); }
+__device__ __forceinline__ uint32_t mn_offset(int k, int chunk) { return kBK == 32 ? mnmajor_offset(k, chunk) : mnmajor16_offset(k, chunk); }
+__device__ __forceinline__ uint64_t km_desc(uint32_t a, int ks) { return kBK == 32 ? kmajor_desc(a, ks) : kmajor16_desc(a, ks); }
+__device__ __forceinline__ uint64_t mn_desc(uint32_t a, int ks) { return kBK == 32 ? mnmajor_desc(a, ks) : mnmajor16_desc(a, ks); }
+}  // namespace umma
 constexpr int kUmmaTmemCols = 512;
 constexpr int kStagePitch = 132;                           // floats; conflict-free accumulator staging
 constexpr int kStageBlockFloats = 128 * kStagePitch;       // one 128 x 128 block
@@ -55,33 +69,36 @@ struct UmmaCtx {
 // and 32-wide k-chunk.  Source pointer and swizzled destination are affine in the chunk index p.
 template <bool KM, int ROWS>
 struct UmmaOperand {
-    static constexpr int NP = ROWS * 8 / kThreads;              // 4 or 8
+    static constexpr int NP = ROWS * (kBK / 4) / kThreads;      // float4 per thread and chunk: 4 (8 with 32-wide chunks)
+    static constexpr int QPR = kBK / 4;                         // K-major: float4 per row and chunk
+    static constexpr int RPP = kThreads / QPR;                  // K-major: rows covered by the CTA per p (64 or 32)
     static constexpr int CPR = ROWS / 4;                        // MN-major: float4 per k-row (32 or 64)
     static constexpr int KSTEP = KM ? 0 : kThreads / CPR;       // MN-major: k-rows between consecutive p (8 or 4)
-    static constexpr uint32_t DSTEP = KM ? 4096u : (uint32_t)(KSTEP / 4) * 512u;
+    static constexpr uint32_t DSTEP = KM ? 4096u : (uint32_t)(KSTEP / 4) * 512u;      // K-major: RPP rows = 4096 B in both layouts
     const float* src0;
     uint32_t sstep;             // floats between consecutive p   (32-bit: an operand is far smaller than 2^32 floats, and every
     uint32_t kstride;           // floats per unit of k            register counts next to the 128 running sums of the main loop)
     uint32_t dst0;
-    int kofs0;                  // k offset of chunk p inside the 32-wide k-chunk: kofs0 + p * KSTEP
+    int kofs0;                  // k offset of chunk p inside the k-chunk: kofs0 + p * KSTEP
     int np_ok;                  // chunks p < np_ok are inside the operand (rows / columns tail)
     // r0: first row (column) of the tile inside the operand, R: rows (columns) of the whole operand
     __device__ __forceinline__ void init(const float* __restrict__ G, int ld, int R, int r0) {
-        if constexpr (KM) {      // 64 threads cover 8 rows x 128 B; quarter-warps hit 8 distinct swizzle positions
-            const int q = (threadIdx.x >> 3) & 7;
-            const int row = (threadIdx.x >> 6) * 8 + (threadIdx.x & 7);      // + 32 p
+        if constexpr (KM) {      // quarter-warps write 128 contiguous (swizzled) bytes: 8 distinct 16-byte positions
+            int q, row;
+            if constexpr (kBK == 32) { q = (threadIdx.x >> 3) & 7; row = (threadIdx.x >> 6) * 8 + (threadIdx.x & 7); }
+            else { q = threadIdx.x & 3; row = threadIdx.x >> 2; }           // + RPP p
             kstride = 1; kofs0 = 4 * q;
             src0 = G + (size_t)(r0 + row) * ld + 4 * q;
-            sstep = 32u * (uint32_t)ld;
-            dst0 = umma::kmajor_offset(row, q);
-            const int left = R - r0 - row;                                   // rows row + 32 p < R - r0
-            np_ok = left <= 0 ? 0 : min(NP, (left + 31) / 32);
+            sstep = (uint32_t)RPP * (uint32_t)ld;
+            dst0 = umma::km_offset(row, q);
+            const int left = R - r0 - row;                                   // rows row + RPP p < R - r0
+            np_ok = left <= 0 ? 0 : min(NP, (left + RPP - 1) / RPP);
         } else {                 // a warp covers 512 contiguous bytes of one k-row
             const int chunk = threadIdx.x % CPR, kb = threadIdx.x / CPR;     // k = kb + KSTEP p
             kstride = (uint32_t)ld; kofs0 = kb;
             src0 = G + (size_t)kb * ld + r0 + 4 * chunk;
             sstep = (uint32_t)KSTEP * (uint32_t)ld;
-            dst0 = umma::mnmajor_offset(kb, chunk);
+            dst0 = umma::mn_offset(kb, chunk);
             np_ok = (r0 + 4 * chunk < R) ? NP : 0;
         }
     }
@@ -119,26 +136,28 @@ struct UmmaOperand {
 // (K-major A) and dW (MN-major A) products.  With two template instances ptxas gave only one of them a full register budget and
 // kept the other's 128 running sums in local memory (~1.1 KB of spills, LDL / STL in every drain).
 struct UmmaOperandA {
-    static constexpr int NP = 4;
+    static constexpr int NP = 128 * (kBK / 4) / kThreads;       // 2 (4)
+    static constexpr int RPP = kThreads / (kBK / 4);            // K-major: rows per p
     const float* src0;
     uint32_t sstep, kstride, dst0, dstep;
     int kofs0, kstep, np_ok;
     __device__ __forceinline__ void init(bool km, const float* __restrict__ G, int ld, int R, int r0) {
         if (km) {
-            const int q = (threadIdx.x >> 3) & 7;
-            const int row = (threadIdx.x >> 6) * 8 + (threadIdx.x & 7);      // + 32 p
+            int q, row;
+            if constexpr (kBK == 32) { q = (threadIdx.x >> 3) & 7; row = (threadIdx.x >> 6) * 8 + (threadIdx.x & 7); }
+            else { q = threadIdx.x & 3; row = threadIdx.x >> 2; }           // + RPP p
             kstride = 1; kofs0 = 4 * q; kstep = 0; dstep = 4096u;
             src0 = G + (size_t)(r0 + row) * ld + 4 * q;
-            sstep = 32u * (uint32_t)ld;
-            dst0 = umma::kmajor_offset(row, q);
+            sstep = (uint32_t)RPP * (uint32_t)ld;
+            dst0 = umma::km_offset(row, q);
             const int left = R - r0 - row;
-            np_ok = left <= 0 ? 0 : min(NP, (left + 31) / 32);
+            np_ok = left <= 0 ? 0 : min(NP, (left + RPP - 1) / RPP);
         } else {
             const int chunk = threadIdx.x % 32, kb = threadIdx.x / 32;       // k = kb + 8 p
             kstride = (uint32_t)ld; kofs0 = kb; kstep = 8; dstep = 1024u;
             src0 = G + (size_t)kb * ld + r0 + 4 * chunk;
             sstep = 8u * (uint32_t)ld;
-            dst0 = umma::mnmajor_offset(kb, chunk);
+            dst0 = umma::mn_offset(kb, chunk);
             np_ok = (r0 + 4 * chunk < R) ? NP : 0;
         }
     }
@@ -216,7 +235,7 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
                                                int K, int m0, unsigned char* smem, uint64_t* mbar, uint32_t tmem, uint32_t phase_in, uint32_t dbg) {
     using namespace umma;
     constexpr int N = 256;
-    const int nchunks = (K + 31) / 32;
+    const int nchunks = (K + kBK - 1) / kBK;
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t idesc = make_idesc_tf32(128, N, A_KM ? 0 : 1, B_KM ? 0 : 1);
     const int wq = warp_id() & 3, chalf = warp_id() >> 2;
@@ -228,14 +247,21 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
     UmmaOperandA la;
     la.init(A_KM, A, lda, M, m0);
     float sum[128];
-    const uint32_t slot_a[2] = {smem0, smem0 + kUmmaSlotBytes};
-    if (!(dbg & 2)) { la.issue(0, K, slot_a[0]); lb.issue(0, K, slot_a[0] + 2 * kUmmaAPlane); }
-    cp_async_commit();
+    // raw chunks 0 .. kUmmaAhead-1 -> their slots; one cp.async group per chunk (empty past the end), so that "all but the newest
+    // kUmmaAhead-1 groups have landed" means "chunk c is in shared memory" at the top of iteration c
+#pragma unroll
+    for (int c = 0; c < kUmmaAhead; ++c) {
+        if (c < nchunks && !(dbg & 2)) {
+            const uint32_t sl = smem0 + c * kUmmaSlotBytes;
+            la.issue(kBK * c, K, sl); lb.issue(kBK * c, K, sl + 2 * kUmmaAPlane);
+        }
+        cp_async_commit();
+    }
 #pragma unroll 1
     for (int c = 0; c < nchunks; ++c) {
-        const int slot = c & 1;
+        const int slot = c % kUmmaSlots;
         const uint32_t ah = smem0 + slot * kUmmaSlotBytes, al = ah + kUmmaAPlane, bh = al + kUmmaAPlane, bl = bh + kUmmaBPlane;
-        cp_async_wait<0>();       // this thread's copies of chunk c have landed
+        cp_async_wait<kUmmaAhead - 1>();       // this thread's copies of chunk c have landed
         if (!(dbg & (2 | kUmmaSinglePass))) {
             la.split(ah, al);
             lb.split(bh, bl);
@@ -245,57 +271,58 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
         __syncthreads();
         if (threadIdx.x == 0) {
             fence_after_sync();
-            const uint32_t d = tmem + (fast ? 0 : slot * N);
-            const int nks = (dbg & 1) ? 0 : min(4, (K - 32 * c + 7) / 8);
+            const uint32_t d = tmem + (fast ? 0 : (c & 1) * N);
+            const int nks = (dbg & 1) ? 0 : min(kKSteps, (K - kBK * c + 7) / 8);
             if (fast) {     // reduced-precision variant: the raw fp32 words are the tf32 operands, the whole K accumulates in TMEM
                 for (int ks = 0; ks < nks; ++ks) {
-                    const uint64_t dah = A_KM ? kmajor_desc(ah, ks) : mnmajor_desc(ah, ks);
-                    const uint64_t dbh = B_KM ? kmajor_desc(bh, ks) : mnmajor_desc(bh, ks);
+                    const uint64_t dah = A_KM ? km_desc(ah, ks) : mn_desc(ah, ks);
+                    const uint64_t dbh = B_KM ? km_desc(bh, ks) : mn_desc(bh, ks);
                     mma_tf32(d, dah, dbh, idesc, (c | ks) ? 1u : 0u);
                 }
             } else {
             for (int ks = 0; ks < nks; ++ks) {      // cross terms first: the accumulator is still tiny
-                const uint64_t dah = A_KM ? kmajor_desc(ah, ks) : mnmajor_desc(ah, ks);
-                const uint64_t dal = A_KM ? kmajor_desc(al, ks) : mnmajor_desc(al, ks);
-                const uint64_t dbh = B_KM ? kmajor_desc(bh, ks) : mnmajor_desc(bh, ks);
-                const uint64_t dbl = B_KM ? kmajor_desc(bl, ks) : mnmajor_desc(bl, ks);
+                const uint64_t dah = A_KM ? km_desc(ah, ks) : mn_desc(ah, ks);
+                const uint64_t dal = A_KM ? km_desc(al, ks) : mn_desc(al, ks);
+                const uint64_t dbh = B_KM ? km_desc(bh, ks) : mn_desc(bh, ks);
+                const uint64_t dbl = B_KM ? km_desc(bl, ks) : mn_desc(bl, ks);
                 mma_tf32(d, dal, dbh, idesc, ks ? 1u : 0u);
                 mma_tf32(d, dah, dbl, idesc, 1u);
             }
             for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t dah = A_KM ? kmajor_desc(ah, ks) : mnmajor_desc(ah, ks);
-                const uint64_t dbh = B_KM ? kmajor_desc(bh, ks) : mnmajor_desc(bh, ks);
+                const uint64_t dah = A_KM ? km_desc(ah, ks) : mn_desc(ah, ks);
+                const uint64_t dbh = B_KM ? km_desc(bh, ks) : mn_desc(bh, ks);
                 mma_tf32(d, dah, dbh, idesc, 1u);
             }
             }
             commit(mbar + slot);
         }
-        const int ps = slot ^ 1;
+        const int ps = (c + kUmmaSlots - 1) % kUmmaSlots;      // slot of chunk c - 1 == slot of chunk c + kUmmaAhead
         if (c >= 1) {       // chunk c - 1 has retired: its slot is free, its accumulator complete
             mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
             phase_bits ^= (1u << ps);
             fence_after_sync();
         }
-        if (c + 1 < nchunks && !(dbg & 2)) {      // raw chunk c + 1 -> the free slot, in flight during the drain below
+        if (c + kUmmaAhead < nchunks && !(dbg & 2)) {      // raw chunk c + kUmmaAhead -> the free slot (never used before when c == 0)
             const uint32_t nh = smem0 + ps * kUmmaSlotBytes;
-            la.issue(32 * (c + 1), K, nh);
-            lb.issue(32 * (c + 1), K, nh + 2 * kUmmaAPlane);
+            la.issue(kBK * (c + kUmmaAhead), K, nh);
+            lb.issue(kBK * (c + kUmmaAhead), K, nh + 2 * kUmmaAPlane);
         }
         cp_async_commit();
         if (c >= 1 && !fast) {       // drain chunk c - 1 while the tensor core works on chunk c
-            if (c == 1) umma_drain<true>(my_tmem + ps * N, sum);
-            else umma_drain<false>(my_tmem + ps * N, sum);
+            if (c == 1) umma_drain<true>(my_tmem + ((c - 1) & 1) * N, sum);
+            else umma_drain<false>(my_tmem + ((c - 1) & 1) * N, sum);
         }
     }
     {   // last chunk
-        const int ps = (nchunks - 1) & 1;
+        const int ps = (nchunks - 1) % kUmmaSlots, acc = (nchunks - 1) & 1;
         mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
         phase_bits ^= (1u << ps);
         fence_after_sync();
-        if (nchunks == 1 || fast) umma_drain<true>(my_tmem + (fast ? 0 : ps * N), sum);
-        else umma_drain<false>(my_tmem + ps * N, sum);
+        if (nchunks == 1 || fast) umma_drain<true>(my_tmem + (fast ? 0 : acc * N), sum);
+        else umma_drain<false>(my_tmem + acc * N, sum);
         fence_before_sync();
     }
+    cp_async_wait<0>();      // (only empty groups are left)
     {   // running sums -> shared staging; every MMA that read the slots has retired
         const int srow = 32 * wq + lane_id();
         const uint32_t base = smem0 + 4 * (chalf * kStageBlockFloats + srow * kStagePitch);

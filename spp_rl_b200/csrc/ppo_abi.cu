@@ -95,6 +95,8 @@ struct spp_ppo {
     cudaEvent_t store_ev = nullptr;    // recorded behind the rollout kernel: consumers on other streams wait for it, not for the whole stream
     int store_E = 0, store_T = 0;      // shape of the [T][E] store the last device rollout left (0: rows came from spp_ppo_load_rollout)
     int plain_ppo = 0;          // 1: PPO.update_actor (custom_loss == 0): no distance term, log-prob of the stored actions as they are
+    int a2c = 0;                // 1: A2C policy gradient -mean(logp * adv) (a2c.py:267-285, on_policy.py:100-124): no ratio, no entropy term
+    float* gacc = nullptr;      // A2C_AcM.update_actor_acm never zeroes the actor's gradients: they accumulate here (on_policy.py:117-123)
     int64_t scratch_rows = 0;
     cudaStream_t stream = nullptr;
     std::vector<PTensor> tensors[2];
@@ -118,6 +120,8 @@ static void fill(const spp_ppo* p, PpoArgs& a, int64_t rows_for_chunks) {
     a.norm = p->norm; a.part = p->part; a.part_stride = p->part_stride; a.gbuf = p->gbuf; a.scal = p->scal; a.gscal = p->gscal;
     a.rows_per_cta = rows_per_cta(rows_for_chunks, p->grid);
     if (p->plain_ppo) a.h.custom_loss = 0.f;
+    if (p->a2c) a.h.entropy_coef = 0.f;      // A2C has no entropy bonus: the Adam kernel adds none to d log_scale
+    a.a2c = p->a2c;
 }
 
 int spp_ppo_store_view_(spp_ppo* p, PpoStoreView* out) {
@@ -135,7 +139,7 @@ int spp_ppo_destroy(spp_ppo* p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->comm) { nccl().CommDestroy(p->comm); p->comm = nullptr; }
-    for (void* q : {(void*)p->env_state, (void*)p->env_len, (void*)p->st_aacm, (void*)p->st_raw_next, (void*)p->dperm_epoch}) if (q) cudaFree(q);
+    for (void* q : {(void*)p->env_state, (void*)p->env_len, (void*)p->st_aacm, (void*)p->st_raw_next, (void*)p->dperm_epoch, (void*)p->gacc}) if (q) cudaFree(q);
     if (p->store_ev) cudaEventDestroy(p->store_ev);
     for (void* q : p->allocs) cudaFree(q);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -300,6 +304,7 @@ int spp_ppo_adam_reset(spp_ppo* p, int net) {      // fresh optimiser state (a n
     PCK(cudaMemset(net == 0 ? p->actor_m : p->critic_m, 0, n));
     PCK(cudaMemset(net == 0 ? p->actor_v : p->critic_v, 0, n));
     if (net == 0) p->step_actor = 0; else p->step_critic = 0;
+    if (net == 0 && p->gacc) PCK(cudaMemset(p->gacc, 0, (size_t)p->part_stride * 4));      // a new module has no .grad yet
     return SPP_OK;
 }
 
@@ -538,6 +543,7 @@ int spp_ppo_advantages(spp_ppo* p, float* adv_host) {
     if (!p || p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
     PCK(cudaSetDevice(p->device));
     PpoArgs a; fill(p, a, p->d.N); a.mode = 0;
+    if (p->a2c) { a.h.discount = 0.f; a.h.discount_d = 0.0; }      // A2C.calculate_advantage (a2c.py:227-245): q - V(s), no GAE carry
     PCK(launch_ppo_critic_values(a, p->grid, p->stream)); spp_count_launch_();
     PCK(launch_ppo_gae(a, p->stream)); spp_count_launch_();
     if (adv_host) PCK(cudaMemcpyAsync(adv_host, p->d.adv, p->d.N * 4, cudaMemcpyDeviceToHost, p->stream));
@@ -567,7 +573,32 @@ int spp_ppo_adv_stats(spp_ppo* p, double out[3]) {       // local (n, sum, sum o
     return SPP_OK;
 }
 
-int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats) {   // (A - mean) / (std_unbiased + 1.2e-7)
+// A2C_AcM.update_actor_acm (on_policy.py:117-123) steps the optimiser on gradients it never zeroes: accumulate != 0 adds the freshly
+// reduced gradient (spp_ppo_actor_minibatch_grad) to the running sum and hands the sum to spp_ppo_actor_apply; 0 restarts the sum
+// (A2C.update_actor, which does call zero_grad, a2c.py:282).
+__global__ void ppo_grad_accumulate_kernel(float* __restrict__ gacc, float* __restrict__ gbuf, int n, int accumulate) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float g = accumulate ? __fadd_rn(gacc[i], gbuf[i]) : gbuf[i];
+        gacc[i] = g; gbuf[i] = g;
+    }
+}
+int spp_ppo_grad_accumulate(spp_ppo* p, int accumulate) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    PCK(cudaSetDevice(p->device));
+    if (!p->gacc) {
+        PCK(cudaMalloc(&p->gacc, (size_t)p->part_stride * 4));
+        PCK(cudaMemsetAsync(p->gacc, 0, (size_t)p->part_stride * 4, p->stream));
+    }
+    ppo_grad_accumulate_kernel<<<(p->L.actor.size + 255) / 256, 256, 0, p->stream>>>(p->gacc, p->gbuf, p->L.actor.size, accumulate);
+    PCK(cudaGetLastError()); spp_count_launch_();
+    return SPP_OK;
+}
+
+// eps < 0: the PPO datasets' 1.2e-7 (advantage_dataset.py:10-12); A2C passes its own 1e-8 (a2c.py:275-277)
+int spp_ppo_normalize_adv_eps(spp_ppo* p, const double* global_stats, double eps);
+int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats) { return spp_ppo_normalize_adv_eps(p, global_stats, -1.0); }
+
+int spp_ppo_normalize_adv_eps(spp_ppo* p, const double* global_stats, double eps) {   // (A - mean) / (std_unbiased + eps)
     if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
     double st[3];
     if (global_stats) { st[0] = global_stats[0]; st[1] = global_stats[1]; st[2] = global_stats[2]; }
@@ -583,7 +614,7 @@ int spp_ppo_normalize_adv(spp_ppo* p, const double* global_stats) {   // (A - me
     }
     const double n = st[0], mean = st[1] / n;
     const double var = n > 1 ? (st[2] - n * mean * mean) / (n - 1) : 0.0;
-    const float denom = (float)std::sqrt(var > 0 ? var : 0.0) + 1.2e-7f;
+    const float denom = (float)std::sqrt(var > 0 ? var : 0.0) + (eps < 0 ? 1.2e-7f : (float)eps);
     PpoArgs a; fill(p, a, p->d.N);
     PCK(launch_ppo_adv_apply(a, (float)mean, denom, p->grid * 4, p->stream)); spp_count_launch_();
     return SPP_OK;
@@ -739,9 +770,10 @@ int spp_ppo_grad_buffer(spp_ppo* p, void** dev_ptr, int* n_floats, void** scal_p
     return SPP_OK;
 }
 
-int spp_ppo_set_actor_mode(spp_ppo* p, int plain_ppo) {
-    if (!p || plain_ppo < 0 || plain_ppo > 1) return spp_set_error_(SPP_ERR_ARG, "bad argument");
-    p->plain_ppo = plain_ppo;
+int spp_ppo_set_actor_mode(spp_ppo* p, int mode) {      // 0: PPO_AcM.update_actor_acm, 1: plain PPO.update_actor, 2 / 3: A2C (with / without the distance term reported)
+    if (!p || mode < 0 || mode > 3) return spp_set_error_(SPP_ERR_ARG, "bad argument");
+    p->plain_ppo = (mode == 1 || mode == 3) ? 1 : 0;
+    p->a2c = mode >= 2 ? 1 : 0;
     return SPP_OK;
 }
 

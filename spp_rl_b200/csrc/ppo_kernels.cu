@@ -238,14 +238,15 @@ __global__ void __launch_bounds__(kThreads, kPpoCtasPerSm) ppo_actor_grad_kernel
             const float lo = 1.f - a.h.epsilon, hi = 1.f + a.h.epsilon;
             const float clipped = fminf(fmaxf(ratio, lo), hi);
             const float s1 = __fmul_rn(ratio, adv), s2 = __fmul_rn(clipped, adv);
-            s_loss += -fminf(s1, s2);
+            s_loss += a.a2c ? -__fmul_rn(old, adv) : -fminf(s1, s2);      // A2C: mean(-logp * adv) with the recorded log-prob (a2c.py:279)
             s_kl += __fsub_rn(old, lp);
             const float g = -invB;
             const float tie = (s1 == s2) ? 0.5f * g : 0.f;
             const float g1 = (s1 < s2 ? g : 0.f) + tie, g2 = (s2 < s1 ? g : 0.f) + tie;
             const float in_range = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
             const float dratio = __fadd_rn(__fmul_rn(g1, adv), __fmul_rn(__fmul_rn(g2, adv), in_range));
-            const float dlogp = __fmul_rn(dratio, ratio);
+            float dlogp = __fmul_rn(dratio, ratio);
+            if (a.a2c) dlogp = __fmul_rn(g, adv);      // A2C: the recorded log-prob's graph, taken at these very weights (no ratio)
             for (int j = 0; j < ob; ++j) {
                 const float sd = expf(ls[j]);
                 const float var = __fmul_rn(sd, sd);

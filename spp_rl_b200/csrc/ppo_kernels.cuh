@@ -89,6 +89,7 @@ struct PpoArgs {
     float* gscal;
     int rows_per_cta;           // multiple of 128
     int mode;                   // kernel specific
+    int a2c;                    // actor gradient kernel: A2C policy gradient -mean(logp * adv) instead of the clipped ratio (a2c.py:279-283)
 };
 
 // scalar slots

@@ -52,6 +52,24 @@ __device__ __forceinline__ uint64_t mnmajor_desc(uint32_t tile_addr, int kstep /
     return make_desc(tile_addr + kstep * 1024, 4096, 512, 1 /* SWIZZLE_128B_BASE32B */);
 }
 
+// ---- 16-wide k-chunks (64-byte rows): the pipelined GEMM of gemm_umma.cuh stages chunks of 16 tf32 so that FOUR operand slots fit
+// the shared memory (copies run three chunks ahead of the tensor core instead of one).
+// K-major: SWIZZLE_64B, atoms of 8 rows x 64 B; the 16-byte chunk index (address bits [4,6)) is XORed with address bits [7,9),
+// i.e. with (row % 8) / 2.  MN-major: the same SWIZZLE_128B_BASE32B atoms as above, 16 k-rows (4 atoms = 2048 B) per MN group.
+__device__ __forceinline__ uint32_t kmajor16_offset(int row, int chunk /* 0..3 */) {
+    return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ uint32_t mnmajor16_offset(int k /* 0..15 */, int chunk) {
+    const int c8 = chunk & 7, q = c8 >> 1, h = c8 & 1;
+    return (uint32_t)((chunk >> 3) * 2048 + (k >> 2) * 512 + (k & 3) * 128 + ((q ^ (k & 3)) << 5) + (h << 4));
+}
+__device__ __forceinline__ uint64_t kmajor16_desc(uint32_t tile_addr, int kstep /* 0..1 */) {
+    return make_desc(tile_addr + kstep * 32, 16, 512, 4 /* SWIZZLE_64B */);
+}
+__device__ __forceinline__ uint64_t mnmajor16_desc(uint32_t tile_addr, int kstep /* 0..1 */) {
+    return make_desc(tile_addr + kstep * 1024, 2048, 512, 1 /* SWIZZLE_128B_BASE32B */);
+}
+
 // 32-bit instruction descriptor for kind::tf32 with fp32 accumulation.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |

@@ -174,9 +174,23 @@ class PpoPolicy:
         check(self.lib.spp_ppo_adv_stats(self.h, out))
         return np.array([out[0], out[1], out[2]])
 
-    def set_actor_mode(self, plain_ppo):
-        """plain_ppo=True: PPO.update_actor (custom_loss == 0, ppo.py:152-192) instead of PPO_AcM.update_actor_acm."""
-        check(self.lib.spp_ppo_set_actor_mode(self.h, int(bool(plain_ppo))))
+    def set_actor_mode(self, plain_ppo=False, a2c=False):
+        """plain_ppo=True: PPO.update_actor (custom_loss == 0, ppo.py:152-192) instead of PPO_AcM.update_actor_acm; a2c=True: the A2C
+        policy-gradient step (A2C_AcM.update_actor_acm, on_policy.py:100-124; with plain_ppo also set: A2C.update_actor)."""
+        check(self.lib.spp_ppo_set_actor_mode(self.h, (2 if a2c else 0) + int(bool(plain_ppo))))
+
+    def a2c_actor_step(self, accumulate, normalize_adv=True):
+        """One A2C actor update on the loaded rollout and the advantages on the device: optional normalisation with A2C's epsilon
+        (a2c.py:275-277), one full-batch gradient of mean(-logp * adv), gradient accumulation when the reference never zeroes
+        (`accumulate`, on_policy.py:117-123), Adam.  Returns (actor loss, summed squared distance of the custom loss)."""
+        if normalize_adv:
+            check(self.lib.spp_ppo_normalize_adv_eps(self.h, None, 1e-8))
+        perm = np.arange(self.N, dtype=np.int64)
+        check(self.lib.spp_ppo_actor_minibatch_grad(self.h, _ptr(perm, C.c_int64), self.N, self.N))
+        sc = self.scalars()
+        check(self.lib.spp_ppo_grad_accumulate(self.h, int(bool(accumulate))))
+        check(self.lib.spp_ppo_actor_apply(self.h))
+        return float(sc[0]) / self.N, float(sc[2])
 
     def update_actor(self, perms, batch_size, kl_threshold, max_epochs=None):
         perms = np.ascontiguousarray(perms, np.int64)

@@ -141,9 +141,11 @@ MemoryAcM = RolloutMemory      # the reference's name (rltoolkit.buffer.MemoryAc
 
 class PPO_AcM:
     NET_ATTRS = ("actor", "critic", "acm")
+    KW = PPO_DEFAULTS
+    A2C = False      # A2C_AcM below: full-batch policy-gradient step instead of the clipped-ratio epochs
 
     def __init__(self, env=None, acm_model="acm", device=0, **kw):
-        unknown = set(kw) - set(PPO_DEFAULTS) - {"log_all", "evals", "max_frames", "vector_envs"}
+        unknown = set(kw) - set(self.KW) - {"log_all", "evals", "max_frames", "vector_envs"}
         if unknown:
             raise TypeError("unexpected keyword arguments: %s" % sorted(unknown))
         c = dict(PPO_DEFAULTS)
@@ -182,12 +184,13 @@ class PPO_AcM:
         self.buffer_size = int(self.acm_pre_train_samples * 1.1)      # acm.py:125-126
         self._device_index = device
         self._pop = self._make_population(acm_model)
-        self._pol = PpoPolicy(self.ob_dim, self.ac_dim, max_rows=self.batch_size + self.max_ep_len, max_batch_rows=self.ppo_batch_size,
+        self._pol = PpoPolicy(self.ob_dim, self.ac_dim, max_rows=self.batch_size + self.max_ep_len,
+                              max_batch_rows=(self.batch_size + self.max_ep_len) if self.A2C else self.ppo_batch_size,
                               device=device, min_max_denormalize=self.min_max_denormalize, norm_closs=self.norm_closs, gamma=self.gamma,
                               gae_lambda=self.gae_lambda, ppo_epsilon=self.ppo_epsilon, entropy_coef=self.entropy_coef,
                               custom_loss=float(self.custom_loss), actor_lr=self.actor_lr, critic_lr=self.critic_lr)
         self._pol.set_limits(self.actor_ac_lim.numpy())
-        self._pol.set_actor_mode(plain_ppo=not self.custom_loss)      # custom_loss == 0: PPO.update_actor (on_policy.py:88-98)
+        self._pol.set_actor_mode(plain_ppo=not self.custom_loss, a2c=self.A2C)      # custom_loss == 0: PPO / A2C.update_actor (on_policy.py:88-98)
         self.replay_buffer = AcmReplayRing(self._pop, 0, self.buffer_size, self.ob_dim, self.min_max_denormalize, self.obs_norm)
         self.acm_scheduler_epoch = 0
         self._init_weights()
@@ -480,3 +483,35 @@ class PPO_AcM:
     def close(self):
         self._pol.close()
         self._pop.close()
+
+
+
+A2C_DEFAULTS = {k: v for k, v in PPO_DEFAULTS.items() if k not in ("epsilon", "gae_lambda", "kl_div_threshold", "max_ppo_epochs", "ppo_batch_size",
+                                                                     "entropy_coef")}
+
+
+class A2C_AcM(PPO_AcM):
+    """rltoolkit.acm.on_policy.A2C_AcM (on_policy.py:133-155 over AcMOnPolicyTrainer :17-131 and A2C, a2c.py): the same rollout, critic
+    fit, ACM feed and statistics as PPO_AcM (which in the reference DERIVES from this class), with A2C's advantages q - V(s)
+    (a2c.py:227-245) and ONE full-batch policy-gradient step per iteration:
+      custom_loss != 0 -> update_actor_acm (on_policy.py:100-124): loss = mean(-logp * adv) + custom_loss * MSE(actions, next_obs), where the
+                          distance term has no gradient path (Actor.act samples, basic_model.py:47) and the optimiser steps on gradients
+                          that are NEVER zeroed (SURVEY quirk 21) -- they accumulate over the iterations;
+      custom_loss == 0 -> A2C.update_actor (a2c.py:267-285), which does zero them."""
+    KW = A2C_DEFAULTS
+    A2C = True
+
+    def update_actor(self, advantages, buffer):
+        if self.custom_loss:
+            self.update_actor_acm(advantages, buffer)
+        else:
+            loss, _ = self._pol.a2c_actor_step(accumulate=False, normalize_adv=self.normalize_adv)
+            self.loss["actor"] = loss
+
+    def update_actor_acm(self, advantages, buffer):
+        loss, dist_sum = self._pol.a2c_actor_step(accumulate=True, normalize_adv=self.normalize_adv)
+        dist = dist_sum / (len(buffer) * self.ob_dim)
+        self.loss.update({"actor": loss, "dist": dist, "policy": loss + self.custom_loss * dist})
+
+    def perform_iteration_device(self):
+        raise NotImplementedError("vector_envs (device-resident iterations) is built for PPO_AcM")

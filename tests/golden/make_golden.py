@@ -20,6 +20,8 @@ Fixtures written next to this file:
                          process_action for SAC_AcM and DDPG_AcM (three limit / normalisation settings), deterministic test()
                          actions, and Actor.act + AcMOnPolicyTrainer.process_action for PPO_AcM
   ppo_plain.npz          plain PPO.update_actor (what PPO_AcM runs when custom_loss == 0, on_policy.py:88-98) on ppo_walker's rollout
+  a2c_acm.npz            A2C_AcM (on_policy.py:100-124): two iterations of A2C.update_critic -> q - V advantages -> update_actor_acm on
+                         ppo_walker's rollout; the second one shows the never-zeroed gradients (post-step weights, Adam moments, losses)
   config1_pendulum.npz   BASELINE config 1: SAC_AcM on Pendulum-v0, pre_train() + train() for 400 frames from fixed weights and seeds:
                          replay indices drawn, ring cursors / index arrays, observation chain, final weights, statistics, returns
   pkl_actions.npz        notebooks/load_and_test.ipynb flow on each of the 9 trained models/*.pkl (copied to tests/golden/models/):
@@ -499,6 +501,65 @@ def ppo_plain_fixture():
     print("ppo_plain: epochs counter", out["epochs_counter"], "losses", out["losses"])
 
 
+def a2c_fixture():
+    """A2C_AcM (on_policy.py:100-124,133-155) for two iterations on ppo_walker's rollout: A2C.update_critic -> q - V advantages ->
+    update_actor_acm with the gradients that are never zeroed.  The second iteration re-records the log-probs under the updated actor
+    (what a fresh rollout does) on the same observations / actions."""
+    g = np.load(os.path.join(HERE, "ppo_walker.npz"))
+    hp = g["hp"]
+    torch.manual_seed(0); np.random.seed(0)
+    m = rl.A2C_AcM(env_name="Walker2d-v2", gamma=float(hp[0]), acm_pre_train_samples=100, acm_pre_train_epochs=1, iterations=1, batch_size=700,
+                   actor_lr=float(hp[6]), critic_lr=float(hp[7]), denormalize_actor_out=True, min_max_denormalize=True, custom_loss=0.1,
+                   obs_norm=True, tensorboard_dir=None, log_dir=None, acm_val_buffer_size=None, norm_closs=False)
+    t = torch.from_numpy
+    for net in ("actor", "critic"):
+        getattr(m, net).load_state_dict({k[len("pre:" + net + "."):]: t(g[k].copy()) for k in g.files if k.startswith("pre:" + net + ".")})
+    m.actor = m.actor; m.critic = m.critic      # optimisers on the loaded parameters
+    chain, joints = g["chain"], set(int(j) for j in g["joints"])
+    out = {}
+
+    def build():
+        buf = MemoryAcM(obs_mean=t(g["obs_mean"]), obs_std=t(g["obs_std"]), device=m.device, alpha=m.obs_norm_alpha, max_obs=t(g["max_obs"]),
+                        min_obs=t(g["min_obs"]), min_max_denormalize=True)
+        ts = 0
+        cur = t(chain[0:1].copy())
+        prev = buf.add_obs(cur)
+        for i in range(1, len(chain)):
+            if i in joints:
+                buf.end_rollout()
+                cur = t(chain[i:i + 1].copy())
+                prev = buf.add_obs(cur)
+                continue
+            a = t(g["actions"][ts:ts + 1].copy())
+            logp = m.actor.get_actions_dist(buf.normalize(cur)).log_prob(torch.squeeze(a))      # Actor.act's expression, graph kept
+            cur = t(chain[i:i + 1].copy())
+            nxt = buf.add_obs(cur)
+            buf.add_timestep(prev, nxt, a, logp, float(g["rewards"][ts]), bool(g["done"][ts]), bool(g["end"][ts]))
+            prev = nxt; ts += 1
+        buf.end_rollout()
+        assert ts == len(g["actions"]) == len(buf)
+        return buf
+
+    for it in (1, 2):
+        buf = build()
+        out["logp%d" % it] = torch.cat(buf.action_logprobs).detach().numpy().copy()
+        adv = m.update_critic(buf)
+        out["adv%d" % it] = adv.numpy().copy()
+        out["critic_loss%d" % it] = np.array(m.loss["critic"])
+        for k, v in m.critic.state_dict().items():
+            out["fit%d:critic.%s" % (it, k)] = v.detach().numpy().copy()
+        m.update_actor(adv, buf)
+        out["losses%d" % it] = np.array([m.loss["actor"], m.loss["dist"], m.loss["policy"]], np.float64)
+        for k, v in m.actor.state_dict().items():
+            out["post%d:actor.%s" % (it, k)] = v.detach().numpy().copy()
+        st = m.actor_optimizer.state_dict()["state"]
+        for i, (k, _) in enumerate(m.actor.named_parameters()):
+            out["post%d:actor.%s#m" % (it, k)] = st[i]["exp_avg"].numpy().copy()
+            out["post%d:actor.%s#v" % (it, k)] = st[i]["exp_avg_sq"].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "a2c_acm.npz"), **out)
+    print("a2c_acm: losses", out["losses1"], out["losses2"])
+
+
 CONFIG1_KW = dict(env_name="Pendulum-v0", update_batch_size=256, acm_pre_train_samples=400, acm_pre_train_epochs=2, acm_val_buffer_size=None,
                   buffer_size=5000, iterations=2, batch_size=200, grad_steps=10, update_freq=50, random_frames=100, acm_update_freq=100,
                   acm_epochs=1, acm_batch_size=128, custom_loss=0.2, acm_critic=True, norm_closs=False, denormalize_actor_out=True,
@@ -636,6 +697,8 @@ if __name__ == "__main__":
         pkl_fixture(); sys.exit(0)
     if "--only-rollout" in sys.argv:
         rollout_fixture(); sys.exit(0)
+    if "--only-a2c" in sys.argv:
+        a2c_fixture(); sys.exit(0)
     sac_fixture()
     ddpg_fixture()
     ring_fixture()
@@ -644,5 +707,6 @@ if __name__ == "__main__":
     ppo_fixture()
     rollout_fixture()
     ppo_plain_fixture()
+    a2c_fixture()
     config1_fixture()
     pkl_fixture()

@@ -243,6 +243,31 @@ def test_ppo_acm_script_kwargs_pretrain_train_test_save_load(tmp_path):
     m.close(); m2.close(); m3.close()
 
 
+def test_a2c_acm_script_kwargs_pretrain_train_save_load(tmp_path):
+    """rltoolkit/acm/test/test_acm_on_policy.py:16-45 (A2C_AcM with and without the validation buffer), on the device path."""
+    from spp_rl_b200.rltoolkit_ppo import A2C_AcM
+
+    kw = {k: v for k, v in PPO_KW.items() if k not in ("kl_div_threshold", "max_ppo_epochs", "ppo_batch_size", "epsilon", "gae_lambda", "entropy_coef")}
+    torch.manual_seed(0); np.random.seed(0)
+    m = A2C_AcM(env=_ShortEpisodes(), **kw)
+    m.pre_train()
+    w0 = m.actor.state_dict()["fc1.weight"].clone()
+    m.train()
+    assert m.iteration == 2 and set(m.loss) >= {"actor", "critic", "acm", "policy", "dist"} and all(np.isfinite(v) for v in m.loss.values()), m.loss
+    assert not torch.equal(w0, m.actor.state_dict()["fc1.weight"])
+    assert m.loss["policy"] == pytest.approx(m.loss["actor"] + m.custom_loss * m.loss["dist"], rel=1e-6)
+    path = os.path.join(tmp_path, "a2c.pkl")
+    m.save(path)
+    assert list(pickle.load(open(path, "rb"))) == ["actor", "critic", "obs_mean", "obs_std", "min_obs", "max_obs", "acm"]
+    with pytest.raises(TypeError):
+        A2C_AcM(env=_ShortEpisodes(), ppo_batch_size=64, **kw)          # not an A2C keyword
+    m0 = A2C_AcM(env=_ShortEpisodes(), **dict(kw, custom_loss=0.0, acm_val_buffer_size=None))      # A2C.update_actor (zeroes its gradients)
+    m0.pre_train()
+    m0.train()
+    assert np.isfinite(m0.loss["actor"])
+    m.close(); m0.close()
+
+
 def test_ppo_acm_iteration_equals_the_kernel_level_calls():
     """perform_iteration's update half == PpoPolicy calls on the same rollout (the fixture-pinned path of test_gpu_ppo.py)."""
     from spp_rl_b200.ppo import PpoPolicy

@@ -88,6 +88,41 @@ def test_plain_ppo_actor_epochs_match_reference_fixture():
     pol.close()
 
 
+def test_a2c_acm_two_iterations_match_reference_fixture():
+    """(f)4: A2C_AcM (on_policy.py:100-124): A2C.update_critic, advantages q - V(s), one full-batch policy-gradient step per iteration on
+    gradients that are never zeroed -- two iterations of the unmodified reference (tests/golden/a2c_acm.npz)."""
+    g, ga = np.load(os.path.join(G, "ppo_walker.npz")), np.load(os.path.join(G, "a2c_acm.npz"))
+    gamma, lam, eps_clip, kl_thr, max_ep, bs, a_lr, c_lr, ent, closs, ntu, nupt = [float(x) for x in g["hp"]]
+    ob, ac = g["chain"].shape[1], g["actions_acm"].shape[1]
+    oi, ni = P.chain_views(len(g["chain"]), list(g["joints"]))
+    obs, nobs = g["chain"][oi], g["chain"][ni]
+    N = obs.shape[0]
+    pol = PpoPolicy(ob, ac, max_rows=N, max_batch_rows=N, min_max_denormalize=True, norm_closs=False, gamma=gamma, gae_lambda=lam,
+                    ppo_epsilon=eps_clip, entropy_coef=0.3, custom_loss=0.1, actor_lr=a_lr, critic_lr=c_lr)     # the entropy bonus must be ignored
+    pol.set_actor_mode(a2c=True)
+    pol.set_limits(float(g["actor_lim"]))
+    pol.set_norm_stats(g["min_obs"], g["max_obs"], g["obs_mean"], g["obs_std"])
+    for net in ("actor", "critic"):
+        pol.load_state_dict(net, {k[len("pre:" + net) + 1:]: g[k] for k in g.files if k.startswith("pre:" + net + ".")})
+    ts, tl = _trajectories(g["end"])
+    for it in (1, 2):
+        pol.load_rollout(obs, nobs, g["actions"], ga["logp%d" % it], g["rewards"], g["done"], g["end"], ts, tl)
+        loss = pol.update_critic(int(ntu), int(nupt))
+        assert loss == pytest.approx(float(ga["critic_loss%d" % it]), rel=1e-4)
+        adv = pol.advantages()
+        ref = ga["adv%d" % it]
+        assert np.abs(adv - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+        pol.load_advantages(ref)
+        actor_loss, dist_sum = pol.a2c_actor_step(accumulate=True, normalize_adv=True)
+        dist = dist_sum / (N * ob)
+        for v, r in zip((actor_loss, dist, actor_loss + 0.1 * dist), ga["losses%d" % it]):
+            assert v == pytest.approx(float(r), rel=2e-4, abs=1e-6)
+        sd = pol.state_dict("actor")
+        for k, v in sd.items():
+            assert relnorm(v, ga["post%d:actor.%s" % (it, k)]) < 2e-5, (it, k, relnorm(v, ga["post%d:actor.%s" % (it, k)]))
+    pol.close()
+
+
 def test_ppo_step_major_large_batch_matches_oracle():
     """E environments x T steps in step-major order (row = t * E + e): GAE strides by E; several CTAs per phase."""
     ob, ac, E, T = 17, 6, 96, 40

@@ -253,3 +253,43 @@ def test_plain_ppo_actor_epochs_match_reference():
     for k in gp.files:
         if k.startswith("post:"):
             assert relnorm(s[k[5:]].numpy(), gp[k]) < 2e-6, k
+
+
+def a2c_case(g):
+    """Inputs of tests/golden/a2c_acm.npz (the rollout is ppo_walker's; shared with the -m gpu test)."""
+    gamma, lam, eps_clip, kl_thr, max_ep, bs, a_lr, c_lr, ent, closs, ntu, nupt = [float(x) for x in g["hp"]]
+    st = NormStats(True, torch.from_numpy(g["min_obs"]), torch.from_numpy(g["max_obs"]), torch.from_numpy(g["obs_mean"]),
+                   torch.from_numpy(g["obs_std"]))
+    chain = torch.from_numpy(g["chain"])
+    oi, ni = P.chain_views(len(chain), list(g["joints"]))
+    return dict(gamma=gamma, a_lr=a_lr, c_lr=c_lr, ntu=int(ntu), nupt=int(nupt), st=st, chain=chain, oi=oi, ni=ni,
+                nobs=normalize(st, chain[oi], True), nnobs=normalize(st, chain[ni], True))
+
+
+def test_a2c_acm_two_iterations_match_reference():
+    """(f)4: A2C_AcM = A2C.update_critic -> q - V advantages -> update_actor_acm (on_policy.py:100-124) whose gradients are never
+    zeroed: the second iteration steps on the sum of both iterations' gradients."""
+    g, ga = _load("ppo_walker.npz"), _load("a2c_acm.npz")
+    c = a2c_case(g)
+    s = {k[4:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("pre:")}
+    rew, done = torch.from_numpy(g["rewards"]), torch.from_numpy(g["done"])
+    acts = torch.from_numpy(g["actions"])
+    for it in (1, 2):
+        loss = P.update_critic(s, c["nobs"], c["nnobs"], rew, done, c["gamma"], c["c_lr"], c["ntu"], c["nupt"])
+        assert loss == pytest.approx(float(ga["critic_loss%d" % it]), rel=2e-5)
+        adv = P.a2c_advantages(s, c["nobs"], c["nnobs"], rew, done, c["gamma"])
+        assert np.abs(adv.numpy() - ga["adv%d" % it]).max() < 2e-5 * max(1.0, np.abs(ga["adv%d" % it]).max())
+        losses = P.a2c_actor_step(s, c["nobs"], acts, torch.from_numpy(ga["logp%d" % it]), torch.from_numpy(ga["adv%d" % it]),
+                                  float(g["actor_lim"]), c["a_lr"], accumulate=True, custom_loss=0.1, loss_actions=denormalize(c["st"], acts),
+                                  next_obs=c["chain"][c["ni"]])
+        for v, r in zip([losses["actor"], losses["dist"], losses["policy"]], ga["losses%d" % it]):
+            assert v == pytest.approx(float(r), rel=1e-5)
+        for k in ga.files:
+            if k.startswith("post%d:actor." % it):
+                assert relnorm(s[k[6:]].numpy(), ga[k]) < 5e-6, k
+    # without the accumulation the second step would be a different one
+    s2 = {k[4:]: torch.from_numpy(g[k].copy()) for k in g.files if k.startswith("pre:")}
+    for it in (1, 2):
+        P.a2c_actor_step(s2, c["nobs"], acts, torch.from_numpy(ga["logp%d" % it]), torch.from_numpy(ga["adv%d" % it]), float(g["actor_lim"]),
+                         c["a_lr"], accumulate=False)
+    assert relnorm(s2["actor.fc2.weight"].numpy(), ga["post2:actor.fc2.weight"]) > 1e-4
