@@ -640,7 +640,9 @@ int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int
     p->b.n = n;
     p->b.n_mean = n_global > 0 ? n_global : n;      // the clipped loss is a mean over the GLOBAL minibatch in data-parallel runs
     PpoArgs a; fill(p, a, n);
-    PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    // A2C takes the log-prob of the stored (normalised-space) actions and denormalises only inside its distance term (on_policy.py:106-116)
+    a.mode = (p->a2c && !p->cfg.norm_closs && !p->plain_ppo) ? 1 : 0;
+    PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo || p->a2c) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
     PCK(launch_ppo_reduce(a, p->grid, p->L.actor.size, p->stream)); spp_count_launch_();
     return SPP_OK;
@@ -655,7 +657,9 @@ int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int
     p->b.n = n;
     p->b.n_mean = n_global > 0 ? n_global : n;
     PpoArgs a; fill(p, a, n);
-    PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    // A2C takes the log-prob of the stored (normalised-space) actions and denormalises only inside its distance term (on_policy.py:106-116)
+    a.mode = (p->a2c && !p->cfg.norm_closs && !p->plain_ppo) ? 1 : 0;
+    PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo || p->a2c) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
     PCK(launch_ppo_reduce(a, p->grid, p->L.actor.size, p->stream)); spp_count_launch_();
     return SPP_OK;

@@ -257,7 +257,12 @@ __global__ void __launch_bounds__(kThreads, kPpoCtasPerSm) ppo_actor_grad_kernel
                 // d logp / d log_scale = d^2 / var - 1 ; stash the per-row term in `mean` (no longer needed) for the column pass
                 mean[(size_t)i * ldo + j] = __fmul_rn(dlogp, __fsub_rn(__fdiv_rn(__fmul_rn(d, d), var), 1.f));
                 if (a.h.custom_loss != 0.f) {
-                    const float dd = __fsub_rn(a.b.act[r * ldo + j], a.b.xn[r * ldo + j]);   // both already in the loss's space
+                    float la = a.b.act[r * ldo + j], ln = a.b.xn[r * ldo + j];               // both already in the loss's space ...
+                    if (a.mode == 1) {      // ... except in the A2C form, whose log-prob above needs the normalised action
+                        const float* doff = a.norm + NORM_DOFF * ldo; const float* dsc = a.norm + NORM_DSCALE * ldo;
+                        la = __fadd_rn(doff[j], __fmul_rn(la, dsc[j])); ln = __fadd_rn(doff[j], __fmul_rn(ln, dsc[j]));
+                    }
+                    const float dd = __fsub_rn(la, ln);
                     s_dist = fmaf(dd, dd, s_dist);
                 }
             }
