@@ -302,6 +302,9 @@ int spp_umma_selftest(int a_mn, int b_mn, int K, int split, const float* A, cons
  * a_km: A stored [M][K] (1) or [K][M] (0); b_km: B stored [256][K] (1) or [K][256] (0); M <= 256, M and K multiples of 4;
  * reps repeats the product inside the kernel; ms_out (optional) receives the kernel time.  Host arrays. */
 int spp_umma_gemm_selftest(int a_km, int b_km, int M, int K, int reps, const float* A, const float* B, float* C, float* ms_out);
+/* hardware probes behind design decisions (tools/umma_probe.py): mode 1 = K-major A stored with the SWIZZLE_128B_BASE32B byte image,
+ * mode 2 = M = 64 accumulator placement in TMEM; A, B [128][32] (tf32-exact values), C [128][128] = TMEM lanes x columns */
+int spp_umma_probe(int mode, const float* A, const float* B, float* C);
 /* process-wide switch for the 256-wide GEMMs of the fused kernels; all three are device paths:
  *   1 = tcgen05, 3-pass tf32 hi/lo split with per-chunk fp32 drain -- fp32-accurate, the default and the one every parity claim is made on;
  *   0 = FFMA tiles (A/B reference for the tensor-core path);

@@ -129,6 +129,7 @@ SIGNATURES = {
     "spp_ppo_grad_buffer": (C.c_int, [_vp, C.POINTER(_vp), _i32p, C.POINTER(_vp)]),
     "spp_set_gemm_path": (C.c_int, [C.c_int]),
     "spp_umma_gemm_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p]),
+    "spp_umma_probe": (C.c_int, [C.c_int, _f32p, _f32p, _f32p]),
     "spp_debug_scratch": (C.c_int, [_vp, C.c_int, C.c_char_p, _f32p, C.c_int, _i32p, _i32p]),
     "spp_umma_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p]),
     "spp_device_info": (C.c_int, [C.c_int, _i32p, _i32p, _i32p, C.c_char_p, C.c_int]),

@@ -128,7 +128,97 @@ __global__ void __launch_bounds__(kThreads, 1) umma_gemm_selftest_kernel(const f
     if (warp_id() == 0) tmem_dealloc<kUmmaTmemCols>(u.tmem);
 }
 
+
+// Hardware probes for the SPP-PPO critic kernel (ppo_critic_tc.cu), single pass, K = 32:
+//   mode 1: the A operand K-major but stored with the SWIZZLE_128B_BASE32B pattern (the byte image of an MN-major tile): can ONE
+//           shared-memory image of a [rows x 32] block serve as K-major A (forward) and as MN-major operand (dW products)?
+//   mode 2: M = 64 (A rows 0..63): where do the 64 accumulator rows land in TMEM?  All 128 lanes x 128 columns are dumped.
+__global__ void __launch_bounds__(kThreads, 1) umma_probe_kernel(const float* A, const float* B, float* C, int mode) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* a_t = smem; unsigned char* b_t = smem + kTileBytes;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    if (warp_id() == 0) tmem_alloc<128>(&tmem_base_s);
+    if (threadIdx.x == 0) mbar_init(&mbar, 1);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_d = tmem_base_s;
+    for (int c = threadIdx.x; c < 1024; c += kThreads) {      // 128 rows x 8 chunks of 16 B
+        const int row = c >> 3, chunk = c & 7;
+        const float4 va = *reinterpret_cast<const float4*>(A + (size_t)row * 32 + chunk * 4);
+        const float4 vb = *reinterpret_cast<const float4*>(B + (size_t)row * 32 + chunk * 4);
+        uint32_t off_a = kmajor_offset(row, chunk);
+        if (mode == 1) off_a = (uint32_t)(row * 128 + ((((chunk >> 1) ^ (row & 3)) << 5) | ((chunk & 1) << 4)));
+        if (mode == 3) off_a = (uint32_t)(((row >> 3) * 8 + chunk) * 128 + (row & 7) * 16);      // no swizzle: core matrices of 8 rows x 16 B
+        *reinterpret_cast<float4*>(a_t + off_a) = va;
+        if (mode < 4) *reinterpret_cast<float4*>(b_t + kmajor_offset(row, chunk)) = vb;
+    }
+    if (mode >= 4) {      // B given as [32 k-rows][128 n]: no-swizzle image, core matrix = 8 k-rows x 16 B of n
+        for (int c = threadIdx.x; c < 1024; c += kThreads) {
+            const int k = c >> 5, chunk = c & 31;
+            *reinterpret_cast<float4*>(b_t + ((k >> 3) * 32 + chunk) * 128 + (k & 7) * 16) = *reinterpret_cast<const float4*>(B + (size_t)k * 128 + chunk * 4);
+        }
+    }
+    // clear the accumulator lanes first so that untouched lanes read as a marker
+    {
+        const uint32_t t = tmem_d + ((uint32_t)(32 * (warp_id() & 3)) << 16) + 64 * (warp_id() >> 2);
+        for (int cb = 0; cb < 4; ++cb)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(t + cb * 16), "r"(0x7fc00000u) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_after_sync();
+        const uint32_t idesc = make_idesc_tf32(mode == 2 ? 64 : 128, 128, 0, mode >= 4 ? 1 : 0);
+        for (int ks = 0; ks < 4; ++ks) {
+            uint64_t da = kmajor_desc(smem_u32(a_t), ks), db = kmajor_desc(smem_u32(b_t), ks);
+            if (mode == 1) da = make_desc(smem_u32(a_t) + ks * 32, 16, 1024, 1);
+            if (mode == 3) da = make_desc(smem_u32(a_t) + ks * 256, 128, 1024, 0);
+            if (mode == 4) db = make_desc(smem_u32(b_t) + ks * 4096, 128, 4096, 0);      // LBO along n, SBO along k
+            if (mode == 5) db = make_desc(smem_u32(b_t) + ks * 4096, 4096, 128, 0);      // the other way round
+            mma_tf32(tmem_d, da, db, idesc, ks ? 1u : 0u);
+        }
+        commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    fence_after_sync();
+    const int row = 32 * (warp_id() & 3) + lane_id();
+    const int col0 = 64 * (warp_id() >> 2);
+    for (int cb = 0; cb < 4; ++cb) {
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(32 * (warp_id() & 3)) << 16) + col0 + cb * 16, v);
+        for (int i = 0; i < 16; ++i) C[(size_t)row * 128 + col0 + cb * 16 + i] = v[i];
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp_id() == 0) tmem_dealloc<128>(tmem_d);
+}
+
 }  // namespace spp
+
+extern "C" int spp_umma_probe(int mode, const float* A, const float* B, float* C) {      // A, B [128][32]; C [128][128] (TMEM lanes x columns)
+    using namespace spp;
+    if (!A || !B || !C || mode < 0 || mode > 5) return spp_set_error_(SPP_ERR_ARG, "spp_umma_probe: bad argument");
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    cudaError_t e;
+#define UCK(x) if ((e = (x)) != cudaSuccess) { cudaFree(dA); cudaFree(dB); cudaFree(dC); return spp_set_error_(SPP_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e)); }
+    UCK(cudaMalloc(&dA, 128 * 32 * 4)); UCK(cudaMalloc(&dB, 128 * 32 * 4)); UCK(cudaMalloc(&dC, 128 * 128 * 4));
+    UCK(cudaMemcpy(dA, A, 128 * 32 * 4, cudaMemcpyHostToDevice)); UCK(cudaMemcpy(dB, B, 128 * 32 * 4, cudaMemcpyHostToDevice));
+    const size_t smem = 2 * umma::kTileBytes + 1024;
+    UCK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_probe_kernel<<<1, kThreads, smem>>>(dA, dB, dC, mode);
+    UCK(cudaGetLastError());
+    spp_count_launch_();
+    UCK(cudaDeviceSynchronize());
+    UCK(cudaMemcpy(C, dC, 128 * 128 * 4, cudaMemcpyDeviceToHost));
+#undef UCK
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return SPP_OK;
+}
 
 // C[M x 256] = A . B through gemm256_umma; a_km: A stored [M][K] (1) or [K][M] (0); b_km: B stored [256][K] (1) or [K][256] (0).
 // M <= 256 and a multiple of 4, K a multiple of 4.  reps > 1 repeats the GEMM (pipeline state carried over); ms_out (optional)

@@ -123,9 +123,13 @@ def test_a2c_acm_two_iterations_match_reference_fixture():
     pol.close()
 
 
-def test_ppo_step_major_large_batch_matches_oracle():
-    """E environments x T steps in step-major order (row = t * E + e): GAE strides by E; several CTAs per phase."""
-    ob, ac, E, T = 17, 6, 96, 40
+@pytest.mark.parametrize("E,T,mb,n_epochs", [(96, 40, 1000, 3), (1024, 1024, 65536, 1)])
+def test_ppo_step_major_large_batch_matches_oracle(E, T, mb, n_epochs):
+    """E environments x T steps in step-major order (row = t * E + e): GAE strides by E; several CTAs per phase.  The second case is
+    config 4's shape class: 1 048 576 rows, 65 536-row minibatches -- fp32 reductions over a million rows, every CTA's
+    partial-gradient slot and the [T][E] stride against the oracle.  Tolerances as in the small case: critic loss 1e-4, advantages
+    2e-5 of their range, losses 2e-4, post-epoch actor weights 2e-5 norm-relative."""
+    ob, ac = 17, 6
     N = E * T
     rng = np.random.RandomState(3)
     mn, mx = (-rng.rand(ob) * 2 - 0.5).astype(np.float32), (rng.rand(ob) * 2 + 0.5).astype(np.float32)
@@ -146,7 +150,7 @@ def test_ppo_step_major_large_batch_matches_oracle():
     for net, out in (("actor", ob), ("critic", 1)):
         lin(net, "fc1", 64, ob); lin(net, "fc2", 64, 64); lin(net, "fc3", out, 64)
     s["actor.log_scale"] = torch.full((ob,), -1.34)
-    pol = PpoPolicy(ob, ac, max_rows=N, max_batch_rows=1024, min_max_denormalize=True, gamma=0.99, gae_lambda=0.95, custom_loss=0.1,
+    pol = PpoPolicy(ob, ac, max_rows=N, max_batch_rows=max(1024, mb), min_max_denormalize=True, gamma=0.99, gae_lambda=0.95, custom_loss=0.1,
                     entropy_coef=0.01)
     pol.set_norm_stats(mn, mx)
     for net in ("actor", "critic"):
@@ -164,17 +168,29 @@ def test_ppo_step_major_large_batch_matches_oracle():
     v = nets.ppo_critic_fwd(sub(s, "critic"), x)[0].squeeze(-1); nv = nets.ppo_critic_fwd(sub(s, "critic"), xn)[0].squeeze(-1)
     q = P.q_values(tr, td, nv, 0.99)
     adv_ref = torch.empty(N)
-    for e in range(E):
+    for e in range(min(E, 96)):
         rows = torch.arange(e, N, E)
         adv_ref[rows] = P.gae(q[rows], v[rows], nv[rows], td[rows], te[rows], 0.99, 0.95)
+    if E > 96:      # the same recurrence (ppo.py:139-148), one vector op over the environments per time step; checked against P.gae above
+        vec = torch.empty(N)
+        carry = torch.zeros(E)
+        delta = q - v
+        boot = (nv.double() * (0.99 * 0.95)).float()
+        for t in range(T - 1, -1, -1):
+            r = slice(t * E, (t + 1) * E)
+            carry = torch.where(td[r] != 0, delta[r], torch.where(te[r] != 0, boot[r] + delta[r], carry * np.float32(0.99 * 0.95) + delta[r]))
+            vec[r] = carry
+        first = torch.cat([torch.arange(e, N, E) for e in range(96)])
+        assert torch.equal(vec[first], adv_ref[first])
+        adv_ref = vec
     adv = pol.advantages()
     assert np.abs(adv - adv_ref.numpy()).max() < 2e-5 * max(1.0, float(adv_ref.abs().max()))
     pol.normalize_adv()
     advn = P.normalize_adv(adv_ref)
-    perms = np.stack([rng.permutation(N) for _ in range(3)]).astype(np.int64)
+    perms = np.stack([rng.permutation(N) for _ in range(n_epochs)]).astype(np.int64)
     tot, epochs, kl = P.update_actor_acm(s, x, denormalize(st, torch.from_numpy(act)), denormalize(st, xn), torch.from_numpy(logp), advn,
-                                         [torch.from_numpy(p) for p in perms], 1.0, 3e-4, 0.2, 1e9, 3, 1000, 0.01, 0.1)
-    losses, epochs_c, kl_c = pol.update_actor(perms, 1000, 1e9, 3)
+                                         [torch.from_numpy(p) for p in perms], 1.0, 3e-4, 0.2, 1e9, n_epochs, mb, 0.01, 0.1)
+    losses, epochs_c, kl_c = pol.update_actor(perms, mb, 1e9, n_epochs)
     assert epochs_c == epochs
     assert kl_c == pytest.approx(kl, rel=1e-3, abs=1e-5)
     for key in ("actor", "entropy", "policy", "dist"):
