@@ -214,6 +214,9 @@ int spp_ppo_update_critic(spp_ppo* p, int n_target_updates, int n_updates_per_ta
 int spp_ppo_critic_targets(spp_ppo* p);
 int spp_ppo_critic_grad(spp_ppo* p);
 int spp_ppo_critic_apply(spp_ppo* p);
+/* critic gradient kernel: 1 (default) = the 64-wide contractions on tcgen05 with weights resident in shared memory
+ * (csrc/ppo_critic_tc.cu; observations of up to 19 floats), 0 = the FFMA tile kernel (also the path for wider observations) */
+int spp_ppo_set_critic_path(spp_ppo* p, int tensor_cores);
 /* PPO.calculate_advantage = calculate_q_val + calculate_gae (rltoolkit/algorithms/ppo/ppo.py:101-150) incl. the bootstrap
  * at non-terminal ends; adv_host [N] may be NULL.  AdvantageDataset normalisation (advantage_dataset.py:9-12): unbiased std,
  * eps 1.2e-7; global_stats = (n, sum, sum of squares) over all ranks or NULL for local. */

@@ -109,6 +109,7 @@ SIGNATURES = {
     "spp_ppo_normalize_adv": (C.c_int, [_vp, _f64p]),
     "spp_ppo_normalize_adv_eps": (C.c_int, [_vp, _f64p, C.c_double]),
     "spp_ppo_grad_accumulate": (C.c_int, [_vp, C.c_int]),
+    "spp_ppo_set_critic_path": (C.c_int, [_vp, C.c_int]),
     "spp_ppo_update_actor": (C.c_int, [_vp, _i64p, C.c_int, C.c_int, C.c_double, _f32p, _i32p, _f32p]),
     "spp_ppo_actor_minibatch_grad": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64]),
     "spp_ppo_actor_minibatch_grad_device": (C.c_int, [_vp, C.c_void_p, C.c_int64, C.c_int64]),

@@ -95,6 +95,7 @@ struct spp_ppo {
     cudaEvent_t store_ev = nullptr;    // recorded behind the rollout kernel: consumers on other streams wait for it, not for the whole stream
     int store_E = 0, store_T = 0;      // shape of the [T][E] store the last device rollout left (0: rows came from spp_ppo_load_rollout)
     int plain_ppo = 0;          // 1: PPO.update_actor (custom_loss == 0): no distance term, log-prob of the stored actions as they are
+    int critic_tc = 1;          // critic fit on tcgen05 (ppo_critic_tc.cu) when the shapes allow; 0: the FFMA tile kernel (spp_ppo_set_critic_path)
     int a2c = 0;                // 1: A2C policy gradient -mean(logp * adv) (a2c.py:267-285, on_policy.py:100-124): no ratio, no entropy term
     float* gacc = nullptr;      // A2C_AcM.update_actor_acm never zeroes the actor's gradients: they accumulate here (on_policy.py:117-123)
     int64_t scratch_rows = 0;
@@ -492,8 +493,20 @@ int spp_ppo_critic_grad(spp_ppo* p) {         // local gradient of 0.5 mean((q -
     if (!p || p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
     PCK(cudaSetDevice(p->device));
     PpoArgs a; fill(p, a, p->d.N);
+    if (p->critic_tc && ppo_critic_tc_supported(p->L.ob, p->L.ldo)) {      // one persistent CTA per SM, rows in tiles of 128
+        a.rows_per_cta = rows_per_cta(p->d.N, p->sm_count);
+        PCK(launch_ppo_critic_grad_tc(a, p->sm_count, p->stream)); spp_count_launch_();
+        PCK(launch_ppo_reduce(a, p->sm_count, p->L.critic.size, p->stream)); spp_count_launch_();
+        return SPP_OK;
+    }
     PCK(launch_ppo_critic_grad(a, p->grid, p->stream)); spp_count_launch_();
     PCK(launch_ppo_reduce(a, p->grid, p->L.critic.size, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
+int spp_ppo_set_critic_path(spp_ppo* p, int tensor_cores) {
+    if (!p || tensor_cores < 0 || tensor_cores > 1) return spp_set_error_(SPP_ERR_ARG, "bad argument");
+    p->critic_tc = tensor_cores;
     return SPP_OK;
 }
 

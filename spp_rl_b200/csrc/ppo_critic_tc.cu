@@ -1,0 +1,379 @@
+// SPP-PPO critic fit on the 5th-generation tensor cores (A2C.update_critic, rltoolkit/algorithms/a2c/a2c.py:186-225; nets:
+// rltoolkit/basic_model.py:64-77): one optimiser step's gradient of 0.5 mean((q - V(x))^2) over ALL rows of the rollout.
+//
+// Same contract as ppo_critic_grad_kernel (ppo_kernels.cu): every CTA owns a contiguous range of rows and leaves its partial
+// gradient in its slot of `part` (+ the squared-error sum in `scal`); ppo_reduce_kernel adds the slots in a fixed order.
+// What differs is where the work runs.  The FFMA version pushes 512-row blocks through five tile GEMMs whose operands travel
+// through L2; here the weights are RESIDENT in shared memory, pre-split into the hi / lo tf32 planes of the three-pass scheme
+// (umma.cuh), rows stream through in tiles of 128, and the three 64-wide contractions run on tcgen05:
+//     fc2      D2[128 x 64]  = h1 . W2^T          A = h1  K-major (SWIZZLE_128B),       B = W2 K-major
+//     dX fc2   D3[128 x 64]  = dz2 . W2           A = dz2 K-major,                      B = W2 MN-major (SWIZZLE_128B_BASE32B)
+//     dW fc2   DW[64 x 64]  += dz2^T . h1         A = dz2 MN-major (M = 64),            B = h1 MN-major, K = rows
+// fc1 (K = ob = 17) and its dW stay on FFMA from shared memory (4 % of the FLOPs each); tanh, the value head, the loss and
+// the bias / fc3 gradients are row-wise register work between the products.
+//
+// Accuracy: an fp32 TMEM accumulator truncates, so every accumulator holds ONE 32-wide k-chunk (fc2, dX: the two
+// halves of K = 64; dW: 32 rows) and the chunks are added in registers with round-to-nearest; cross terms are issued first.
+// The dW accumulators are drained into per-thread running sums once per tile.  Measured tcgen05 facts this layout rests on
+// (tools/umma_probe.py): M = 64 puts accumulator row 16 q + i on TMEM lane 32 q + i; a K-major operand cannot be read from an
+// image in the BASE32B swizzle (device exception), so h1 and dz2 are written twice -- once per swizzle.
+//
+// Shared memory (209 KB, one CTA per SM): bufK 64 KB (h1, later dz2, K-major: 2 k-chunks x [hi | lo] x 128 rows x 128 B),
+// W2 K-major 32 KB, W2 MN-major 32 KB, bufA / bufB 32 KB each (dz2 / h1 MN-major for HALF a tile: the dW product of a tile runs
+// as two 64-row halves so that the images fit), x tile 10 KB, W1^T 5 KB, vectors.  TMEM: D2[2], D3[2], DW[4] x 64 columns.
+#include "ppo_kernels.cuh"
+#include "umma.cuh"
+
+namespace spp {
+
+namespace {
+using namespace umma;
+
+constexpr int kTile = 128;
+constexpr int kOffBufK = 0;
+constexpr int kOffW2K = kOffBufK + 65536;
+constexpr int kOffW2MN = kOffW2K + 32768;
+constexpr int kOffBufA = kOffW2MN + 32768;
+constexpr int kOffBufB = kOffBufA + 32768;
+constexpr int kOffXs = kOffBufB + 32768;
+constexpr int kXsLd = 20;                       // pad4(ob) for ob <= 19; column 17..19 are pad, column kOnesCol carries ones
+constexpr int kOffW1t = kOffXs + kTile * kXsLd * 4;
+constexpr int kOffVec = kOffW1t + kXsLd * 64 * 4;
+constexpr int kVecFloats = 64 * 3 + 2 * kTile + 16;     // b1, b2, w3, vpart[2][128], reduction scratch
+constexpr int kTcSmemBytes = kOffVec + kVecFloats * 4;
+constexpr int kDz1Ld = 68;                      // raw dz1 tile (aliases bufA | bufB): conflict-free row writes and column reads
+static_assert(kTile * kDz1Ld * 4 <= 65536, "dz1 tile aliases bufA | bufB");
+static_assert(kTcSmemBytes + 1024 <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void issue3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc, uint32_t acc_first) {
+    mma_tf32(d, al, bh, idesc, acc_first);
+    mma_tf32(d, ah, bl, idesc, 1u);
+}
+
+// one 32-wide k-chunk of a three-pass product into accumulator d (fresh): cross terms of all four k-steps first, then hi x hi
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void chunk_mma(uint32_t d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t dah = A_MN ? mnmajor_desc(ah, ks) : kmajor_desc(ah, ks), dal = A_MN ? mnmajor_desc(al, ks) : kmajor_desc(al, ks);
+        const uint64_t dbh = B_MN ? mnmajor_desc(bh, ks) : kmajor_desc(bh, ks), dbl = B_MN ? mnmajor_desc(bl, ks) : kmajor_desc(bl, ks);
+        issue3(d, dah, dal, dbh, dbl, idesc, ks ? 1u : 0u);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t dah = A_MN ? mnmajor_desc(ah, ks) : kmajor_desc(ah, ks);
+        const uint64_t dbh = B_MN ? mnmajor_desc(bh, ks) : kmajor_desc(bh, ks);
+        mma_tf32(d, dah, dbh, idesc, 1u);
+    }
+}
+
+// this thread's 32 values -> its row of a K-major tile pair (hi, lo): row r, the 8 sixteen-byte chunks of one k-chunk
+__device__ __forceinline__ void store_kmajor_row(uint32_t hi_plane, uint32_t lo_plane, int r, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 h, l;
+        split_tf32(v[4 * c], h.x, l.x); split_tf32(v[4 * c + 1], h.y, l.y); split_tf32(v[4 * c + 2], h.z, l.z); split_tf32(v[4 * c + 3], h.w, l.w);
+        const uint32_t off = kmajor_offset(r, c);
+        sts128(hi_plane + off, h); sts128(lo_plane + off, l);
+    }
+}
+// ... and its k-row of an MN-major tile pair: k = row inside the 32-row chunk, MN group g (32 floats = this thread's columns)
+__device__ __forceinline__ void store_mnmajor_row(uint32_t hi_plane, uint32_t lo_plane, int k, int g, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float4 h, l;
+        split_tf32(v[4 * c], h.x, l.x); split_tf32(v[4 * c + 1], h.y, l.y); split_tf32(v[4 * c + 2], h.z, l.z); split_tf32(v[4 * c + 3], h.w, l.w);
+        const uint32_t off = mnmajor_offset(k, 8 * g + c);
+        sts128(hi_plane + off, h); sts128(lo_plane + off, l);
+    }
+}
+
+// v[j] (+)= TMEM[lane][col0 + j], j < 32
+template <bool ADD>
+__device__ __forceinline__ void tmem_row32(uint32_t taddr, float (&v)[32]) {
+    float t0[16], t1[16];
+    tmem_ld16_nowait(taddr, t0);
+    tmem_ld16_nowait(taddr + 16, t1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        v[j] = ADD ? __fadd_rn(v[j], t0[j]) : t0[j];
+        v[16 + j] = ADD ? __fadd_rn(v[16 + j], t1[j]) : t1[j];
+    }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const __grid_constant__ PpoArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t s0 = smem_u32(smem);
+    float* xs = reinterpret_cast<float*>(smem + kOffXs);
+    float* w1t = reinterpret_cast<float*>(smem + kOffW1t);
+    float* vec = reinterpret_cast<float*>(smem + kOffVec);
+    float* b1s = vec; float* b2s = vec + 64; float* w3s = vec + 128; float* vpart = vec + 192; float* red = vec + 192 + 2 * kTile;
+    float* dz1s = reinterpret_cast<float*>(smem + kOffBufA);
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+
+    float* part = a.part + (size_t)blockIdx.x * a.part_stride;
+    float* scal = a.scal + (size_t)blockIdx.x * PS_COUNT;
+    for (int i = threadIdx.x; i < a.L.critic.size; i += kThreads) part[i] = 0.f;
+    if (threadIdx.x < PS_COUNT) scal[threadIdx.x] = 0.f;
+    const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
+    int64_t nrows64 = a.d.N - r0;
+    if (nrows64 > a.rows_per_cta) nrows64 = a.rows_per_cta;
+    if (nrows64 <= 0) return;
+    const int nrows = (int)nrows64;
+
+    const LayerDesc& l0 = a.L.critic.L[0]; const LayerDesc& l1 = a.L.critic.L[1]; const LayerDesc& l2 = a.L.critic.L[2];
+    const int ob = a.L.ob, ldo = a.L.ldo;
+    const int ones_col = ob;          // first pad column of the x tile (ob < kXsLd): dW1's column `ob` is then sum(dz1) = d b1
+
+    if (warp_id() == 0) tmem_alloc<512>(&tmem_base_s);
+    if (threadIdx.x == 0) { mbar_init(&mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    // resident weights: W1^T (fp32, FFMA), b1, b2, w3; W2 split into hi / lo planes in both operand layouts
+    for (int e = threadIdx.x; e < kXsLd * 64; e += kThreads) {
+        const int i = e / 64, c = e % 64;
+        w1t[e] = (i < ob) ? a.critic[l0.off_w + c * l0.ld + i] : 0.f;
+    }
+    if (threadIdx.x < 64) {
+        b1s[threadIdx.x] = a.critic[l0.off_b + threadIdx.x]; b2s[threadIdx.x] = a.critic[l1.off_b + threadIdx.x];
+        w3s[threadIdx.x] = a.critic[l2.off_w + threadIdx.x];
+    }
+    for (int e = threadIdx.x; e < 64 * 16; e += kThreads) {      // float4 (o, i4) of W2 [out][in]
+        const int o = e >> 4, i4 = e & 15;
+        const float4 w = *reinterpret_cast<const float4*>(a.critic + l1.off_w + o * l1.ld + 4 * i4);
+        float4 h, l;
+        split_tf32(w.x, h.x, l.x); split_tf32(w.y, h.y, l.y); split_tf32(w.z, h.z, l.z); split_tf32(w.w, h.w, l.w);
+        {   // fc2: B[n = out][k = in], K-major; k-chunk = in / 32
+            const uint32_t base = s0 + kOffW2K + (i4 >> 3) * 16384, off = kmajor_offset(o, i4 & 7);
+            sts128(base + off, h); sts128(base + 8192 + off, l);
+        }
+        {   // dX: B[k = out][n = in], MN-major; k-chunk = out / 32
+            const uint32_t base = s0 + kOffW2MN + (o >> 5) * 16384, off = mnmajor_offset(o & 31, i4);
+            sts128(base + off, h); sts128(base + 8192 + off, l);
+        }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const float b3 = a.critic[l2.off_b];
+    const float inv_n = 1.0f / (float)a.d.Ntot;
+
+    const int q = warp_id() & 3, hcol = warp_id() >> 2, c0 = 32 * hcol;
+    const int r = 32 * q + lane_id();                                    // this thread's row of the tile
+    const uint32_t my_t = tmem + ((uint32_t)(32 * q) << 16) + c0;         // its TMEM lane quarter / column half
+    const uint32_t idesc_fwd = make_idesc_tf32(128, 64, 0, 0), idesc_dx = make_idesc_tf32(128, 64, 0, 1), idesc_dw = make_idesc_tf32(64, 64, 1, 1);
+    uint32_t phase = 0;
+
+    float gw2[32], cs_b2[32], cs_w3[32], gw1[5];      // running sums over the CTA's tiles
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { gw2[j] = 0.f; cs_b2[j] = 0.f; cs_w3[j] = 0.f; }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) gw1[m] = 0.f;
+    float sse = 0.f, sdv = 0.f;
+    const int o1 = threadIdx.x & 63, ig = threadIdx.x >> 6;              // dW1 mapping: out unit, input columns ig + 4 m
+
+    for (int t0 = 0; t0 < nrows; t0 += kTile) {
+        const int trows = min(kTile, nrows - t0);
+        // ---- x tile -> shared (rows beyond the range are zero), ones column
+        {
+            const float* X = a.d.x + (r0 + t0) * ldo;
+            for (int e = threadIdx.x; e < kTile * (kXsLd / 4); e += kThreads) {
+                const int rr = e / (kXsLd / 4), c4 = e % (kXsLd / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rr < trows && 4 * c4 < ldo) v = *reinterpret_cast<const float4*>(X + (size_t)rr * ldo + 4 * c4);
+                float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (4 * c4 + k == ones_col) pv[k] = 1.0f;
+                *reinterpret_cast<float4*>(xs + rr * kXsLd + 4 * c4) = v;
+            }
+        }
+        __syncthreads();
+        // ---- fc1 (FFMA): h1 = tanh(x W1^T + b1), this thread's row, 32 columns
+        float h1[32];
+        {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            float xv[kXsLd];      // the row's 20 floats with conflict-free 16-byte loads; pad columns meet zero rows of W1^T
+#pragma unroll
+            for (int c = 0; c < kXsLd / 4; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(xs + r * kXsLd + 4 * c);
+                xv[4 * c] = v.x; xv[4 * c + 1] = v.y; xv[4 * c + 2] = v.z; xv[4 * c + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < kXsLd; ++i) {
+                const float4* wr = reinterpret_cast<const float4*>(w1t + i * 64 + c0);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 w = wr[c];
+                    acc[4 * c] = fmaf(xv[i], w.x, acc[4 * c]); acc[4 * c + 1] = fmaf(xv[i], w.y, acc[4 * c + 1]);
+                    acc[4 * c + 2] = fmaf(xv[i], w.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(xv[i], w.w, acc[4 * c + 3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h1[j] = tanhf(__fadd_rn(acc[j], b1s[c0 + j]));
+        }
+        store_kmajor_row(s0 + kOffBufK + hcol * 32768, s0 + kOffBufK + hcol * 32768 + 16384, r, h1);
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {      // fc2
+            fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<false, false>(tmem + 64 * c, s0 + kOffBufK + c * 32768, s0 + kOffBufK + c * 32768 + 16384,
+                                        s0 + kOffW2K + c * 16384, s0 + kOffW2K + c * 16384 + 8192, idesc_fwd);
+            commit(&mbar);
+        }
+        mbar_wait(&mbar, phase); phase ^= 1;
+        fence_after_sync();
+        // ---- value head, loss, dz2
+        float dz2[32];
+        float dv;
+        {
+            float h2[32];
+            tmem_row32<false>(my_t, h2);
+            tmem_row32<true>(my_t + 64, h2);
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { h2[j] = tanhf(__fadd_rn(h2[j], b2s[c0 + j])); dot = fmaf(h2[j], w3s[c0 + j], dot); }
+            vpart[hcol * kTile + r] = dot;
+            __syncthreads();
+            const float v = __fadd_rn(__fadd_rn(vpart[r], vpart[kTile + r]), b3);
+            const bool valid = r < trows;
+            const float diff = valid ? __fsub_rn(a.d.q[r0 + t0 + r], v) : 0.f;
+            dv = -__fmul_rn(diff, inv_n);
+            if (hcol == 0) { sse = fmaf(diff, diff, sse); sdv += dv; }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                dz2[j] = __fmul_rn(__fmul_rn(dv, w3s[c0 + j]), __fsub_rn(1.f, __fmul_rn(h2[j], h2[j])));
+                cs_b2[j] += dz2[j];
+                cs_w3[j] = fmaf(dv, h2[j], cs_w3[j]);
+            }
+        }
+        // dz2 -> K-major (over h1's image: the fc2 products have retired); first half of the tile -> MN-major images of dz2 and h1
+        store_kmajor_row(s0 + kOffBufK + hcol * 32768, s0 + kOffBufK + hcol * 32768 + 16384, r, dz2);
+        if (q < 2) {
+            const uint32_t pa = s0 + kOffBufA + (r >> 5) * 16384, pb = s0 + kOffBufB + (r >> 5) * 16384;
+            store_mnmajor_row(pa, pa + 8192, r & 31, hcol, dz2);
+            store_mnmajor_row(pb, pb + 8192, r & 31, hcol, h1);
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {      // dX through fc2 (all 128 rows) and dW fc2 of rows 0..63
+            fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<false, true>(tmem + 128 + 64 * c, s0 + kOffBufK + c * 32768, s0 + kOffBufK + c * 32768 + 16384,
+                                       s0 + kOffW2MN + c * 16384, s0 + kOffW2MN + c * 16384 + 8192, idesc_dx);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<true, true>(tmem + 256 + 64 * c, s0 + kOffBufA + c * 16384, s0 + kOffBufA + c * 16384 + 8192,
+                                      s0 + kOffBufB + c * 16384, s0 + kOffBufB + c * 16384 + 8192, idesc_dw);
+            commit(&mbar);
+        }
+        mbar_wait(&mbar, phase); phase ^= 1;
+        fence_after_sync();
+        if (q >= 2) {                // second half of the tile -> the MN-major images
+            const int lr = r - 64;
+            const uint32_t pa = s0 + kOffBufA + (lr >> 5) * 16384, pb = s0 + kOffBufB + (lr >> 5) * 16384;
+            store_mnmajor_row(pa, pa + 8192, lr & 31, hcol, dz2);
+            store_mnmajor_row(pb, pb + 8192, lr & 31, hcol, h1);
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {      // dW fc2 of rows 64..127
+            fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<true, true>(tmem + 384 + 64 * c, s0 + kOffBufA + c * 16384, s0 + kOffBufA + c * 16384 + 8192,
+                                      s0 + kOffBufB + c * 16384, s0 + kOffBufB + c * 16384 + 8192, idesc_dw);
+            commit(&mbar);
+        }
+        // ---- dz1 = (dz2 W2) (1 - h1^2) while the tensor core finishes the second half
+        float dz1[32];
+        tmem_row32<false>(my_t + 128, dz1);
+        tmem_row32<true>(my_t + 192, dz1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz1[j] = __fmul_rn(dz1[j], __fsub_rn(1.f, __fmul_rn(h1[j], h1[j])));
+        mbar_wait(&mbar, phase); phase ^= 1;
+        fence_after_sync();
+        // raw dz1 tile over bufA | bufB (their products have retired) for the fc1 weight gradient
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(dz1s + r * kDz1Ld + c0 + 4 * c) = make_float4(dz1[4 * c], dz1[4 * c + 1], dz1[4 * c + 2], dz1[4 * c + 3]);
+        // dW fc2: the four 32-row accumulators of this tile -> running sums (accumulator row 16 q + i sits on lane 32 q + i)
+        {
+            float t[32];
+            tmem_row32<false>(my_t + 256, t);
+            tmem_row32<true>(my_t + 320, t);
+            tmem_row32<true>(my_t + 384, t);
+            tmem_row32<true>(my_t + 448, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gw2[j] = __fadd_rn(gw2[j], t[j]);
+        }
+        fence_before_sync();
+        __syncthreads();
+        // ---- dW fc1 (+ d b1 through the ones column) on FFMA: out unit o1, input columns ig + 4 m
+        for (int rr = 0; rr < kTile; ++rr) {
+            const float d = dz1s[rr * kDz1Ld + o1];
+            const float* xr = xs + rr * kXsLd + ig;
+#pragma unroll
+            for (int m = 0; m < 5; ++m) gw1[m] = fmaf(d, xr[4 * m], gw1[m]);
+        }
+        __syncthreads();      // xs, bufK and bufA | bufB are rewritten by the next tile
+    }
+
+    // ---- the CTA's partial gradient
+    if (lane_id() < 16) {
+        const int o = 16 * q + lane_id();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(part + l1.off_w + o * l1.ld + c0 + 4 * c) = make_float4(gw2[4 * c], gw2[4 * c + 1], gw2[4 * c + 2], gw2[4 * c + 3]);
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const int i = ig + 4 * m;
+        if (i < ob) part[l0.off_w + o1 * l0.ld + i] = gw1[m];
+        else if (i == ones_col) part[l0.off_b + o1] = gw1[m];
+    }
+    // column sums over the 128 row-threads of each column half, in row order (deterministic): d b2 and d w3
+    float* colred = reinterpret_cast<float*>(smem + kOffBufK);      // [2][128][33]
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) colred[(hcol * kTile + r) * 33 + j] = pass == 0 ? cs_b2[j] : cs_w3[j];
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int hh = threadIdx.x >> 5, j = threadIdx.x & 31;
+            float s = 0.f;
+            for (int rr = 0; rr < kTile; ++rr) s += colred[(hh * kTile + rr) * 33 + j];
+            part[(pass == 0 ? l1.off_b : l2.off_w) + threadIdx.x] = s;
+        }
+    }
+    const float t1 = block_sum(sse, red);
+    __syncthreads();
+    const float t2 = block_sum(sdv, red);
+    if (threadIdx.x == 0) { scal[PS_LOSS] = t1; part[l2.off_b] = t2; }
+    fence_before_sync();
+    __syncthreads();
+    if (warp_id() == 0) tmem_dealloc<512>(tmem);
+}
+
+cudaError_t launch_ppo_critic_grad_tc(const PpoArgs& a, int grid, cudaStream_t s) {
+    if (a.L.ob >= kXsLd || a.L.ldo > kXsLd) return cudaErrorInvalidValue;      // wider observations take the FFMA kernel
+    cudaError_t e = cudaFuncSetAttribute(ppo_critic_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes + 1024);
+    if (e != cudaSuccess) return e;
+    ppo_critic_grad_tc_kernel<<<grid, kThreads, kTcSmemBytes + 1024, s>>>(a);
+    return cudaGetLastError();
+}
+
+bool ppo_critic_tc_supported(int ob, int ldo) { return ob < kXsLd && ldo <= kXsLd; }
+
+}  // namespace spp

@@ -179,6 +179,10 @@ class PpoPolicy:
         policy-gradient step (A2C_AcM.update_actor_acm, on_policy.py:100-124; with plain_ppo also set: A2C.update_actor)."""
         check(self.lib.spp_ppo_set_actor_mode(self.h, (2 if a2c else 0) + int(bool(plain_ppo))))
 
+    def set_critic_path(self, tensor_cores):
+        """True (default): critic fit on tcgen05 (csrc/ppo_critic_tc.cu); False: the FFMA tile kernel."""
+        check(self.lib.spp_ppo_set_critic_path(self.h, int(bool(tensor_cores))))
+
     def a2c_actor_step(self, accumulate, normalize_adv=True):
         """One A2C actor update on the loaded rollout and the advantages on the device: optional normalisation with A2C's epsilon
         (a2c.py:275-277), one full-batch gradient of mean(-logp * adv), gradient accumulation when the reference never zeroes

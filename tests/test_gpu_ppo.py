@@ -25,7 +25,8 @@ def _trajectories(end):
     return np.array(starts, np.int64), np.array(lens, np.int64)
 
 
-def test_ppo_update_matches_reference_fixture():
+@pytest.mark.parametrize("critic_tc", [True, False], ids=["critic-tcgen05", "critic-ffma"])
+def test_ppo_update_matches_reference_fixture(critic_tc):
     g = np.load(os.path.join(G, "ppo_walker.npz"))
     gamma, lam, eps_clip, kl_thr, max_ep, bs, a_lr, c_lr, ent, closs, ntu, nupt = [float(x) for x in g["hp"]]
     ob, ac = g["chain"].shape[1], g["actions_acm"].shape[1]
@@ -34,6 +35,7 @@ def test_ppo_update_matches_reference_fixture():
     N = obs.shape[0]
     pol = PpoPolicy(ob, ac, max_rows=N, max_batch_rows=int(bs), min_max_denormalize=True, norm_closs=False, gamma=gamma, gae_lambda=lam,
                     ppo_epsilon=eps_clip, entropy_coef=ent, custom_loss=closs, actor_lr=a_lr, critic_lr=c_lr)
+    pol.set_critic_path(critic_tc)
     pol.set_limits(float(g["actor_lim"]))
     pol.set_norm_stats(g["min_obs"], g["max_obs"], g["obs_mean"], g["obs_std"])
     for net in ("actor", "critic"):
