@@ -36,8 +36,9 @@ constexpr int kOffW2MN = kOffW2K + 32768;
 constexpr int kOffBufA = kOffW2MN + 32768;
 constexpr int kOffBufB = kOffBufA + 32768;
 constexpr int kOffXs = kOffBufB + 32768;
-constexpr int kXsLd = 20;                       // pad4(ob) for ob <= 19; column 17..19 are pad, column kOnesCol carries ones
-constexpr int kOffW1t = kOffXs + kTile * kXsLd * 4;
+constexpr int kXsLd = 20;                       // pad4(ob) for ob <= 20; pad columns are zero
+constexpr int kXsBytes = kTile * kXsLd * 4;     // one x tile; two of them: the next tile lands (cp.async) while this one is processed
+constexpr int kOffW1t = kOffXs + 2 * kXsBytes;
 constexpr int kOffVec = kOffW1t + kXsLd * 64 * 4;
 constexpr int kVecFloats = 64 * 3 + 2 * kTile + 16;     // b1, b2, w3, vpart[2][128], reduction scratch
 constexpr int kTcSmemBytes = kOffVec + kVecFloats * 4;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t s0 = smem_u32(smem);
-    float* xs = reinterpret_cast<float*>(smem + kOffXs);
+    float* xs_base = reinterpret_cast<float*>(smem + kOffXs);
     float* w1t = reinterpret_cast<float*>(smem + kOffW1t);
     float* vec = reinterpret_cast<float*>(smem + kOffVec);
     float* b1s = vec; float* b2s = vec + 64; float* w3s = vec + 128; float* vpart = vec + 192; float* red = vec + 192 + 2 * kTile;
@@ -127,7 +128,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
 
     const LayerDesc& l0 = a.L.critic.L[0]; const LayerDesc& l1 = a.L.critic.L[1]; const LayerDesc& l2 = a.L.critic.L[2];
     const int ob = a.L.ob, ldo = a.L.ldo;
-    const int ones_col = ob;          // first pad column of the x tile (ob < kXsLd): dW1's column `ob` is then sum(dz1) = d b1
 
     if (warp_id() == 0) tmem_alloc<512>(&tmem_base_s);
     if (threadIdx.x == 0) { mbar_init(&mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -168,30 +168,33 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
     const uint32_t idesc_fwd = make_idesc_tf32(128, 64, 0, 0), idesc_dx = make_idesc_tf32(128, 64, 0, 1), idesc_dw = make_idesc_tf32(64, 64, 1, 1);
     uint32_t phase = 0;
 
-    float gw2[32], cs_b2[32], cs_w3[32], gw1[5];      // running sums over the CTA's tiles
+    float gw2[32], cs_b2[32], cs_w3[32], gw1[kXsLd];      // running sums over the CTA's tiles
 #pragma unroll
     for (int j = 0; j < 32; ++j) { gw2[j] = 0.f; cs_b2[j] = 0.f; cs_w3[j] = 0.f; }
 #pragma unroll
-    for (int m = 0; m < 5; ++m) gw1[m] = 0.f;
-    float sse = 0.f, sdv = 0.f;
-    const int o1 = threadIdx.x & 63, ig = threadIdx.x >> 6;              // dW1 mapping: out unit, input columns ig + 4 m
+    for (int m = 0; m < kXsLd; ++m) gw1[m] = 0.f;
+    float sse = 0.f, sdv = 0.f, gb1 = 0.f;
+    const int o1 = threadIdx.x & 63, rq = threadIdx.x >> 6;              // dW1 mapping: out unit o1, every input column, rows 32 rq .. 32 rq + 31
 
-    for (int t0 = 0; t0 < nrows; t0 += kTile) {
+    // x tile t -> shared buffer t & 1 by 16-byte cp.async (rows beyond the range and pad chunks zero-filled)
+    auto load_x_tile = [&](int t0, float* dst) {
         const int trows = min(kTile, nrows - t0);
-        // ---- x tile -> shared (rows beyond the range are zero), ones column
-        {
-            const float* X = a.d.x + (r0 + t0) * ldo;
-            for (int e = threadIdx.x; e < kTile * (kXsLd / 4); e += kThreads) {
-                const int rr = e / (kXsLd / 4), c4 = e % (kXsLd / 4);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rr < trows && 4 * c4 < ldo) v = *reinterpret_cast<const float4*>(X + (size_t)rr * ldo + 4 * c4);
-                float* pv = reinterpret_cast<float*>(&v);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (4 * c4 + k == ones_col) pv[k] = 1.0f;
-                *reinterpret_cast<float4*>(xs + rr * kXsLd + 4 * c4) = v;
-            }
+        const float* X = a.d.x + (r0 + t0) * ldo;
+        for (int e = threadIdx.x; e < kTile * (kXsLd / 4); e += kThreads) {
+            const int rr = e / (kXsLd / 4), c4 = e % (kXsLd / 4);
+            const bool ok = rr < trows && 4 * c4 < ldo;
+            cp_async16(dst + rr * kXsLd + 4 * c4, ok ? X + (size_t)rr * ldo + 4 * c4 : a.d.x, ok ? 16 : 0);
         }
+        cp_async_commit();
+    };
+    load_x_tile(0, xs_base);
+    int tbuf = 0;
+    for (int t0 = 0; t0 < nrows; t0 += kTile, tbuf ^= 1) {
+        const int trows = min(kTile, nrows - t0);
+        float* xs = xs_base + tbuf * (kXsBytes / 4);
+        cp_async_wait<0>();
         __syncthreads();
+        if (t0 + kTile < nrows) load_x_tile(t0 + kTile, xs_base + (tbuf ^ 1) * (kXsBytes / 4));      // lands during this tile
         // ---- fc1 (FFMA): h1 = tanh(x W1^T + b1), this thread's row, 32 columns
         float h1[32];
         {
@@ -320,12 +323,18 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
         }
         fence_before_sync();
         __syncthreads();
-        // ---- dW fc1 (+ d b1 through the ones column) on FFMA: out unit o1, input columns ig + 4 m
-        for (int rr = 0; rr < kTile; ++rr) {
+        // ---- dW fc1 (+ d b1 through the ones column) on FFMA: out unit o1 x all input columns over this thread's quarter of the rows
+#pragma unroll 4
+        for (int rr = 32 * rq; rr < 32 * rq + 32; ++rr) {
             const float d = dz1s[rr * kDz1Ld + o1];
-            const float* xr = xs + rr * kXsLd + ig;
+            gb1 = __fadd_rn(gb1, d);
+            const float4* xr = reinterpret_cast<const float4*>(xs + rr * kXsLd);      // warp-uniform address: broadcast
 #pragma unroll
-            for (int m = 0; m < 5; ++m) gw1[m] = fmaf(d, xr[4 * m], gw1[m]);
+            for (int c = 0; c < kXsLd / 4; ++c) {
+                const float4 x4 = xr[c];
+                gw1[4 * c] = fmaf(d, x4.x, gw1[4 * c]); gw1[4 * c + 1] = fmaf(d, x4.y, gw1[4 * c + 1]);
+                gw1[4 * c + 2] = fmaf(d, x4.z, gw1[4 * c + 2]); gw1[4 * c + 3] = fmaf(d, x4.w, gw1[4 * c + 3]);
+            }
         }
         __syncthreads();      // xs, bufK and bufA | bufB are rewritten by the next tile
     }
@@ -337,11 +346,20 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
         for (int c = 0; c < 8; ++c)
             *reinterpret_cast<float4*>(part + l1.off_w + o * l1.ld + c0 + 4 * c) = make_float4(gw2[4 * c], gw2[4 * c + 1], gw2[4 * c + 2], gw2[4 * c + 3]);
     }
+    {   // the four row quarters of dW fc1, added in quarter order
+        float* w1red = reinterpret_cast<float*>(smem + kOffBufA);      // [4][64][21]: 20 weight columns + the bias
+        __syncthreads();
 #pragma unroll
-    for (int m = 0; m < 5; ++m) {
-        const int i = ig + 4 * m;
-        if (i < ob) part[l0.off_w + o1 * l0.ld + i] = gw1[m];
-        else if (i == ones_col) part[l0.off_b + o1] = gw1[m];
+        for (int m = 0; m < kXsLd; ++m) w1red[(rq * 64 + o1) * 21 + m] = gw1[m];
+        w1red[(rq * 64 + o1) * 21 + kXsLd] = gb1;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 64 * 21; e += kThreads) {
+            const int o = e / 21, i = e % 21;
+            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(w1red[(0 * 64 + o) * 21 + i], w1red[(1 * 64 + o) * 21 + i]), w1red[(2 * 64 + o) * 21 + i]),
+                                        w1red[(3 * 64 + o) * 21 + i]);
+            if (i < ob) part[l0.off_w + o * l0.ld + i] = sum;
+            else if (i == kXsLd) part[l0.off_b + o] = sum;
+        }
     }
     // column sums over the 128 row-threads of each column half, in row order (deterministic): d b2 and d w3
     float* colred = reinterpret_cast<float*>(smem + kOffBufK);      // [2][128][33]
@@ -367,13 +385,13 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
 }
 
 cudaError_t launch_ppo_critic_grad_tc(const PpoArgs& a, int grid, cudaStream_t s) {
-    if (a.L.ob >= kXsLd || a.L.ldo > kXsLd) return cudaErrorInvalidValue;      // wider observations take the FFMA kernel
+    if (!ppo_critic_tc_supported(a.L.ob, a.L.ldo)) return cudaErrorInvalidValue;      // wider observations take the FFMA kernel
     cudaError_t e = cudaFuncSetAttribute(ppo_critic_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes + 1024);
     if (e != cudaSuccess) return e;
     ppo_critic_grad_tc_kernel<<<grid, kThreads, kTcSmemBytes + 1024, s>>>(a);
     return cudaGetLastError();
 }
 
-bool ppo_critic_tc_supported(int ob, int ldo) { return ob < kXsLd && ldo <= kXsLd; }
+bool ppo_critic_tc_supported(int ob, int ldo) { return ob <= kXsLd && ldo <= kXsLd; }
 
 }  // namespace spp
