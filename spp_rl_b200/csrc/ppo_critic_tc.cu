@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
     float* vec = reinterpret_cast<float*>(smem + kOffVec);
     float* b1s = vec; float* b2s = vec + 64; float* w3s = vec + 128; float* vpart = vec + 192; float* red = vec + 192 + 2 * kTile;
     float* dz1s = reinterpret_cast<float*>(smem + kOffBufA);
-    __shared__ uint64_t mbar;
+    __shared__ uint64_t mbar3[3];      // fc2 | dW fc2 (both halves) | dX
     __shared__ uint32_t tmem_base_s;
 
     float* part = a.part + (size_t)blockIdx.x * a.part_stride;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
     const int ob = a.L.ob, ldo = a.L.ldo;
 
     if (warp_id() == 0) tmem_alloc<512>(&tmem_base_s);
-    if (threadIdx.x == 0) { mbar_init(&mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x == 0) { mbar_init(mbar3, 1); mbar_init(mbar3 + 1, 1); mbar_init(mbar3 + 2, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     // resident weights: W1^T (fp32, FFMA), b1, b2, w3; W2 split into hi / lo planes in both operand layouts
     for (int e = threadIdx.x; e < kXsLd * 64; e += kThreads) {
         const int i = e / 64, c = e % 64;
@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
     const int r = 32 * q + lane_id();                                    // this thread's row of the tile
     const uint32_t my_t = tmem + ((uint32_t)(32 * q) << 16) + c0;         // its TMEM lane quarter / column half
     const uint32_t idesc_fwd = make_idesc_tf32(128, 64, 0, 0), idesc_dx = make_idesc_tf32(128, 64, 0, 1), idesc_dw = make_idesc_tf32(64, 64, 1, 1);
-    uint32_t phase = 0;
+    uint32_t ph_fc2 = 0, ph_dw = 0, ph_dx = 0;
+    uint64_t* const m_fc2 = mbar3; uint64_t* const m_dw = mbar3 + 1; uint64_t* const m_dx = mbar3 + 2;
 
     float gw2[32], cs_b2[32], cs_w3[32], gw1[kXsLd];      // running sums over the CTA's tiles
 #pragma unroll
@@ -187,6 +188,22 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
         }
         cp_async_commit();
     };
+    // dW fc1 (+ d b1) on FFMA from the raw dz1 tile (bufA | bufB) and an x tile: out unit o1 x all input columns over this thread's
+    // quarter of the rows.  Runs for tile t - 1 inside tile t's fc2 wait (and once after the loop).
+    auto dw1_ffma = [&](const float* xs) {
+#pragma unroll 4
+        for (int rr = 32 * rq; rr < 32 * rq + 32; ++rr) {
+            const float d = dz1s[rr * kDz1Ld + o1];
+            gb1 = __fadd_rn(gb1, d);
+            const float4* xr = reinterpret_cast<const float4*>(xs + rr * kXsLd);      // warp-uniform address: broadcast
+#pragma unroll
+            for (int c = 0; c < kXsLd / 4; ++c) {
+                const float4 x4 = xr[c];
+                gw1[4 * c] = fmaf(d, x4.x, gw1[4 * c]); gw1[4 * c + 1] = fmaf(d, x4.y, gw1[4 * c + 1]);
+                gw1[4 * c + 2] = fmaf(d, x4.z, gw1[4 * c + 2]); gw1[4 * c + 3] = fmaf(d, x4.w, gw1[4 * c + 3]);
+            }
+        }
+    };
     load_x_tile(0, xs_base);
     int tbuf = 0;
     for (int t0 = 0; t0 < nrows; t0 += kTile, tbuf ^= 1) {
@@ -194,7 +211,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
         float* xs = xs_base + tbuf * (kXsBytes / 4);
         cp_async_wait<0>();
         __syncthreads();
-        if (t0 + kTile < nrows) load_x_tile(t0 + kTile, xs_base + (tbuf ^ 1) * (kXsBytes / 4));      // lands during this tile
         // ---- fc1 (FFMA): h1 = tanh(x W1^T + b1), this thread's row, 32 columns
         float h1[32];
         {
@@ -230,9 +246,10 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
             for (int c = 0; c < 2; ++c)
                 chunk_mma<false, false>(tmem + 64 * c, s0 + kOffBufK + c * 32768, s0 + kOffBufK + c * 32768 + 16384,
                                         s0 + kOffW2K + c * 16384, s0 + kOffW2K + c * 16384 + 8192, idesc_fwd);
-            commit(&mbar);
+            commit(m_fc2);
         }
-        mbar_wait(&mbar, phase); phase ^= 1;
+        if (t0 > 0) dw1_ffma(xs_base + (tbuf ^ 1) * (kXsBytes / 4));      // fc1 weight gradient of the PREVIOUS tile while fc2 runs
+        mbar_wait(m_fc2, ph_fc2); ph_fc2 ^= 1;
         fence_after_sync();
         // ---- value head, loss, dz2
         float dz2[32];
@@ -245,7 +262,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
 #pragma unroll
             for (int j = 0; j < 32; ++j) { h2[j] = tanhf(__fadd_rn(h2[j], b2s[c0 + j])); dot = fmaf(h2[j], w3s[c0 + j], dot); }
             vpart[hcol * kTile + r] = dot;
-            __syncthreads();
+            __syncthreads();      // also: every thread is past the previous tile's dW1 loop -- its x buffer and bufA | bufB are free
+            if (t0 + kTile < nrows) load_x_tile(t0 + kTile, xs_base + (tbuf ^ 1) * (kXsBytes / 4));      // lands during the rest of this tile
             const float v = __fadd_rn(__fadd_rn(vpart[r], vpart[kTile + r]), b3);
             const bool valid = r < trows;
             const float diff = valid ? __fsub_rn(a.d.q[r0 + t0 + r], v) : 0.f;
@@ -268,19 +286,20 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
-        if (threadIdx.x == 0) {      // dX through fc2 (all 128 rows) and dW fc2 of rows 0..63
+        if (threadIdx.x == 0) {      // dW fc2 of rows 0..63 first (its images are needed back soonest), then dX through fc2 (all 128 rows)
             fence_after_sync();
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-                chunk_mma<false, true>(tmem + 128 + 64 * c, s0 + kOffBufK + c * 32768, s0 + kOffBufK + c * 32768 + 16384,
-                                       s0 + kOffW2MN + c * 16384, s0 + kOffW2MN + c * 16384 + 8192, idesc_dx);
 #pragma unroll
             for (int c = 0; c < 2; ++c)
                 chunk_mma<true, true>(tmem + 256 + 64 * c, s0 + kOffBufA + c * 16384, s0 + kOffBufA + c * 16384 + 8192,
                                       s0 + kOffBufB + c * 16384, s0 + kOffBufB + c * 16384 + 8192, idesc_dw);
-            commit(&mbar);
+            commit(m_dw);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<false, true>(tmem + 128 + 64 * c, s0 + kOffBufK + c * 32768, s0 + kOffBufK + c * 32768 + 16384,
+                                       s0 + kOffW2MN + c * 16384, s0 + kOffW2MN + c * 16384 + 8192, idesc_dx);
+            commit(m_dx);
         }
-        mbar_wait(&mbar, phase); phase ^= 1;
+        mbar_wait(m_dw, ph_dw); ph_dw ^= 1;
         fence_after_sync();
         if (q >= 2) {                // second half of the tile -> the MN-major images
             const int lr = r - 64;
@@ -297,15 +316,17 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
             for (int c = 0; c < 2; ++c)
                 chunk_mma<true, true>(tmem + 384 + 64 * c, s0 + kOffBufA + c * 16384, s0 + kOffBufA + c * 16384 + 8192,
                                       s0 + kOffBufB + c * 16384, s0 + kOffBufB + c * 16384 + 8192, idesc_dw);
-            commit(&mbar);
+            commit(m_dw);
         }
         // ---- dz1 = (dz2 W2) (1 - h1^2) while the tensor core finishes the second half
+        mbar_wait(m_dx, ph_dx); ph_dx ^= 1;
+        fence_after_sync();
         float dz1[32];
         tmem_row32<false>(my_t + 128, dz1);
         tmem_row32<true>(my_t + 192, dz1);
 #pragma unroll
         for (int j = 0; j < 32; ++j) dz1[j] = __fmul_rn(dz1[j], __fsub_rn(1.f, __fmul_rn(h1[j], h1[j])));
-        mbar_wait(&mbar, phase); phase ^= 1;
+        mbar_wait(m_dw, ph_dw); ph_dw ^= 1;
         fence_after_sync();
         // raw dz1 tile over bufA | bufB (their products have retired) for the fc1 weight gradient
 #pragma unroll
@@ -321,23 +342,10 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
 #pragma unroll
             for (int j = 0; j < 32; ++j) gw2[j] = __fadd_rn(gw2[j], t[j]);
         }
-        fence_before_sync();
-        __syncthreads();
-        // ---- dW fc1 (+ d b1 through the ones column) on FFMA: out unit o1 x all input columns over this thread's quarter of the rows
-#pragma unroll 4
-        for (int rr = 32 * rq; rr < 32 * rq + 32; ++rr) {
-            const float d = dz1s[rr * kDz1Ld + o1];
-            gb1 = __fadd_rn(gb1, d);
-            const float4* xr = reinterpret_cast<const float4*>(xs + rr * kXsLd);      // warp-uniform address: broadcast
-#pragma unroll
-            for (int c = 0; c < kXsLd / 4; ++c) {
-                const float4 x4 = xr[c];
-                gw1[4 * c] = fmaf(d, x4.x, gw1[4 * c]); gw1[4 * c + 1] = fmaf(d, x4.y, gw1[4 * c + 1]);
-                gw1[4 * c + 2] = fmaf(d, x4.z, gw1[4 * c + 2]); gw1[4 * c + 3] = fmaf(d, x4.w, gw1[4 * c + 3]);
-            }
-        }
-        __syncthreads();      // xs, bufK and bufA | bufB are rewritten by the next tile
+        fence_before_sync();      // (the next tile's barriers order these TMEM reads before its MMAs)
     }
+    __syncthreads();
+    dw1_ffma(xs_base + (tbuf ^ 1) * (kXsBytes / 4));      // the last tile (tbuf was flipped by the loop increment)
 
     // ---- the CTA's partial gradient
     if (lane_id() < 16) {
