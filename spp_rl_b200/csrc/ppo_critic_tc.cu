@@ -89,6 +89,14 @@ __device__ __forceinline__ void store_mnmajor_row(uint32_t hi_plane, uint32_t lo
     }
 }
 
+// (d0, d1) += a * (b0, b1): one packed FFMA2 (sm_100 fma.rn.f32x2; each half is an IEEE fma, so results equal two scalar fmaf)
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a), "f"(b0), "f"(b1));
+}
+
 // v[j] (+)= TMEM[lane][col0 + j], j < 32
 template <bool ADD>
 __device__ __forceinline__ void tmem_row32(uint32_t taddr, float (&v)[32]) {
@@ -199,8 +207,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
 #pragma unroll
             for (int c = 0; c < kXsLd / 4; ++c) {
                 const float4 x4 = xr[c];
-                gw1[4 * c] = fmaf(d, x4.x, gw1[4 * c]); gw1[4 * c + 1] = fmaf(d, x4.y, gw1[4 * c + 1]);
-                gw1[4 * c + 2] = fmaf(d, x4.z, gw1[4 * c + 2]); gw1[4 * c + 3] = fmaf(d, x4.w, gw1[4 * c + 3]);
+                fma2(gw1[4 * c], gw1[4 * c + 1], d, x4.x, x4.y);
+                fma2(gw1[4 * c + 2], gw1[4 * c + 3], d, x4.z, x4.w);
             }
         }
     };
@@ -211,6 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
         float* xs = xs_base + tbuf * (kXsBytes / 4);
         cp_async_wait<0>();
         __syncthreads();
+        const float q_row = (r < trows) ? __ldg(a.d.q + r0 + t0 + r) : 0.f;      // needed by the value head: in flight during fc1 / fc2
         // ---- fc1 (FFMA): h1 = tanh(x W1^T + b1), this thread's row, 32 columns
         float h1[32];
         {
@@ -229,8 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 w = wr[c];
-                    acc[4 * c] = fmaf(xv[i], w.x, acc[4 * c]); acc[4 * c + 1] = fmaf(xv[i], w.y, acc[4 * c + 1]);
-                    acc[4 * c + 2] = fmaf(xv[i], w.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(xv[i], w.w, acc[4 * c + 3]);
+                    fma2(acc[4 * c], acc[4 * c + 1], xv[i], w.x, w.y);
+                    fma2(acc[4 * c + 2], acc[4 * c + 3], xv[i], w.z, w.w);
                 }
             }
 #pragma unroll
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_critic_grad_tc_kernel(const _
             if (t0 + kTile < nrows) load_x_tile(t0 + kTile, xs_base + (tbuf ^ 1) * (kXsBytes / 4));      // lands during the rest of this tile
             const float v = __fadd_rn(__fadd_rn(vpart[r], vpart[kTile + r]), b3);
             const bool valid = r < trows;
-            const float diff = valid ? __fsub_rn(a.d.q[r0 + t0 + r], v) : 0.f;
+            const float diff = valid ? __fsub_rn(q_row, v) : 0.f;
             dv = -__fmul_rn(diff, inv_n);
             if (hcol == 0) { sse = fmaf(diff, diff, sse); sdv += dv; }
 #pragma unroll
