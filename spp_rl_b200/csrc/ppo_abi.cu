@@ -485,7 +485,8 @@ int spp_ppo_critic_targets(spp_ppo* p) {      // q = r + gamma (1 - done) V(next
     if (!p || p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
     PCK(cudaSetDevice(p->device));
     PpoArgs a; fill(p, a, p->d.N); a.mode = 1;
-    PCK(launch_ppo_critic_values(a, p->grid, p->stream)); spp_count_launch_();
+    PCK((p->critic_tc && ppo_critic_tc_supported(p->L.ob, p->L.ldo)) ? launch_ppo_critic_values_tc(a, p->grid, p->stream)
+                                                                     : launch_ppo_critic_values(a, p->grid, p->stream)); spp_count_launch_();
     return SPP_OK;
 }
 
@@ -557,7 +558,8 @@ int spp_ppo_advantages(spp_ppo* p, float* adv_host) {
     PCK(cudaSetDevice(p->device));
     PpoArgs a; fill(p, a, p->d.N); a.mode = 0;
     if (p->a2c) { a.h.discount = 0.f; a.h.discount_d = 0.0; }      // A2C.calculate_advantage (a2c.py:227-245): q - V(s), no GAE carry
-    PCK(launch_ppo_critic_values(a, p->grid, p->stream)); spp_count_launch_();
+    PCK((p->critic_tc && ppo_critic_tc_supported(p->L.ob, p->L.ldo)) ? launch_ppo_critic_values_tc(a, p->grid, p->stream)
+                                                                     : launch_ppo_critic_values(a, p->grid, p->stream)); spp_count_launch_();
     PCK(launch_ppo_gae(a, p->stream)); spp_count_launch_();
     if (adv_host) PCK(cudaMemcpyAsync(adv_host, p->d.adv, p->d.N * 4, cudaMemcpyDeviceToHost, p->stream));
     PCK(cudaStreamSynchronize(p->stream));

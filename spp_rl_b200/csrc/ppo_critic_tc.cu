@@ -411,4 +411,136 @@ cudaError_t launch_ppo_critic_grad_tc(const PpoArgs& a, int grid, cudaStream_t s
 
 bool ppo_critic_tc_supported(int ob, int ldo) { return ob <= kXsLd && ldo <= kXsLd; }
 
+// ---- forward only: V(x) -> v, V(xn) -> nv, q = r + gamma (1 - done) nv (ppo_critic_values_kernel's contract, modes 0 / 1) with fc2 on
+// tcgen05.  Shared memory: h1 K-major 64 KB + W2 K-major 32 KB + one x tile + W1^T + vectors = 111 KB, 128 TMEM columns: two CTAs
+// per SM, so one CTA's row-wise work covers the other's tensor-core wait.
+namespace {
+constexpr int kValOffW2K = 65536;
+constexpr int kValOffW1t = kValOffW2K + 32768;
+constexpr int kValOffVec = kValOffW1t + kXsLd * 64 * 4;
+constexpr int kValSmemBytes = kValOffVec + (64 * 3 + 2 * kTile) * 4;
+static_assert(2 * (kValSmemBytes + 1024 + 1024) <= 227 * 1024, "two value CTAs per SM");
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 2) ppo_critic_values_tc_kernel(const __grid_constant__ PpoArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t s0 = smem_u32(smem);
+    float* w1t = reinterpret_cast<float*>(smem + kValOffW1t);
+    float* vec = reinterpret_cast<float*>(smem + kValOffVec);
+    float* b1s = vec; float* b2s = vec + 64; float* w3s = vec + 128; float* vpart = vec + 192;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
+    int64_t nrows64 = a.d.N - r0;
+    if (nrows64 > a.rows_per_cta) nrows64 = a.rows_per_cta;
+    if (nrows64 <= 0) return;
+    const int nrows = (int)nrows64;
+    const LayerDesc& l0 = a.L.critic.L[0]; const LayerDesc& l1 = a.L.critic.L[1]; const LayerDesc& l2 = a.L.critic.L[2];
+    const int ob = a.L.ob, ldo = a.L.ldo;
+    if (warp_id() == 0) tmem_alloc<128>(&tmem_base_s);
+    if (threadIdx.x == 0) { mbar_init(&mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int e = threadIdx.x; e < kXsLd * 64; e += kThreads) {
+        const int i = e / 64, c = e % 64;
+        w1t[e] = (i < ob) ? a.critic[l0.off_w + c * l0.ld + i] : 0.f;
+    }
+    if (threadIdx.x < 64) {
+        b1s[threadIdx.x] = a.critic[l0.off_b + threadIdx.x]; b2s[threadIdx.x] = a.critic[l1.off_b + threadIdx.x];
+        w3s[threadIdx.x] = a.critic[l2.off_w + threadIdx.x];
+    }
+    for (int e = threadIdx.x; e < 64 * 16; e += kThreads) {
+        const int o = e >> 4, i4 = e & 15;
+        const float4 w = *reinterpret_cast<const float4*>(a.critic + l1.off_w + o * l1.ld + 4 * i4);
+        float4 h, l;
+        split_tf32(w.x, h.x, l.x); split_tf32(w.y, h.y, l.y); split_tf32(w.z, h.z, l.z); split_tf32(w.w, h.w, l.w);
+        const uint32_t base = s0 + kValOffW2K + (i4 >> 3) * 16384, off = kmajor_offset(o, i4 & 7);
+        sts128(base + off, h); sts128(base + 8192 + off, l);
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const float b3 = a.critic[l2.off_b];
+    const int q = warp_id() & 3, hcol = warp_id() >> 2, c0 = 32 * hcol;
+    const int r = 32 * q + lane_id();
+    const uint32_t my_t = tmem + ((uint32_t)(32 * q) << 16) + c0;
+    const uint32_t idesc_fwd = make_idesc_tf32(128, 64, 0, 0);
+    uint32_t phase = 0;
+    for (int pass = (a.mode == 1 ? 1 : 0); pass < 2; ++pass) {
+        const float* src = pass == 0 ? a.d.x : a.d.xn;
+        float* dst = pass == 0 ? a.d.v : a.d.nv;
+        for (int t0 = 0; t0 < nrows; t0 += kTile) {
+            const int trows = min(kTile, nrows - t0);
+            const float* X = src + (r0 + t0) * ldo;
+            float h[32];
+            {
+                float acc[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                float xv[kXsLd];      // this thread's row straight from global memory (both column halves read it: the second hits L1)
+#pragma unroll
+                for (int c = 0; c < kXsLd / 4; ++c) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < trows && 4 * c < ldo) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * ldo + 4 * c));
+                    xv[4 * c] = v.x; xv[4 * c + 1] = v.y; xv[4 * c + 2] = v.z; xv[4 * c + 3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < kXsLd; ++i) {
+                    const float4* wr = reinterpret_cast<const float4*>(w1t + i * 64 + c0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 w = wr[c];
+                        fma2(acc[4 * c], acc[4 * c + 1], xv[i], w.x, w.y);
+                        fma2(acc[4 * c + 2], acc[4 * c + 3], xv[i], w.z, w.w);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) h[j] = tanhf(__fadd_rn(acc[j], b1s[c0 + j]));
+            }
+            store_kmajor_row(s0 + hcol * 32768, s0 + hcol * 32768 + 16384, r, h);
+            fence_proxy_async();
+            fence_before_sync();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_after_sync();
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    chunk_mma<false, false>(tmem + 64 * c, s0 + c * 32768, s0 + c * 32768 + 16384, s0 + kValOffW2K + c * 16384,
+                                            s0 + kValOffW2K + c * 16384 + 8192, idesc_fwd);
+                commit(&mbar);
+            }
+            mbar_wait(&mbar, phase); phase ^= 1;
+            fence_after_sync();
+            tmem_row32<false>(my_t, h);
+            tmem_row32<true>(my_t + 64, h);
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot = fmaf(tanhf(__fadd_rn(h[j], b2s[c0 + j])), w3s[c0 + j], dot);
+            vpart[hcol * kTile + r] = dot;
+            fence_before_sync();
+            __syncthreads();
+            if (hcol == 0 && r < trows) dst[r0 + t0 + r] = __fadd_rn(__fadd_rn(vpart[r], vpart[kTile + r]), b3);
+            // (the next tile's barrier before its MMA separates these vpart reads from its writes)
+        }
+    }
+    __syncthreads();      // nv of this CTA's rows is complete and visible to the CTA
+    for (int i = threadIdx.x; i < nrows; i += kThreads) {
+        const int64_t rr = r0 + i;
+        a.d.q[rr] = __fadd_rn(a.d.rew[rr], __fmul_rn(__fmul_rn(a.h.gamma, __fsub_rn(1.f, a.d.done[rr])), a.d.nv[rr]));
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp_id() == 0) tmem_dealloc<128>(tmem);
+}
+
+cudaError_t launch_ppo_critic_values_tc(const PpoArgs& a, int grid, cudaStream_t s) {
+    if (!ppo_critic_tc_supported(a.L.ob, a.L.ldo)) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(ppo_critic_values_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kValSmemBytes + 1024);
+    if (e != cudaSuccess) return e;
+    ppo_critic_values_tc_kernel<<<grid, kThreads, kValSmemBytes + 1024, s>>>(a);
+    return cudaGetLastError();
+}
+
+
 }  // namespace spp

@@ -98,6 +98,7 @@ enum { PS_LOSS = 0, PS_ENTROPY = 1, PS_DIST = 2, PS_KL = 3, PS_COUNT = 8 };
 cudaError_t launch_ppo_critic_values(const PpoArgs& a, int grid, cudaStream_t s);      // v, nv, q
 cudaError_t launch_ppo_critic_grad(const PpoArgs& a, int grid, cudaStream_t s);        // partial grads of 0.5 mean((q - V)^2)
 cudaError_t launch_ppo_critic_grad_tc(const PpoArgs& a, int grid, cudaStream_t s);     // the same on tcgen05 (ppo_critic_tc.cu); grid <= n_part slots
+cudaError_t launch_ppo_critic_values_tc(const PpoArgs& a, int grid, cudaStream_t s);   // v / nv / q with fc2 on tcgen05, two CTAs per SM
 bool ppo_critic_tc_supported(int ob, int ldo);
 cudaError_t launch_ppo_actor_grad(const PpoArgs& a, int grid, cudaStream_t s);         // partial grads of the clipped loss
 cudaError_t launch_ppo_act(const PpoArgs& a, int grid, cudaStream_t s);                // on-policy rollout step
