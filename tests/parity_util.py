@@ -51,7 +51,7 @@ def upload_state(pop, np_state, agent, algo):
         pop.load_state_dict(net, sd, agent=agent)
 
 
-def compare_states(pop, ostate, agent, algo, verbose=False, tag="", moment_weight=1.0):
+def compare_states(pop, ostate, agent, algo, verbose=False, tag="", moment_weight=1.0, small_weight=1.0):
     """worst norm-relative error over all tensors and Adam moments of one agent"""
     nets = ["actor", "critic_1", "critic_2", "critic_1_targ", "critic_2_targ", "acm"] if algo == "sac" else \
         ["actor", "actor_targ", "critic", "critic_targ", "acm"]
@@ -61,7 +61,7 @@ def compare_states(pop, ostate, agent, algo, verbose=False, tag="", moment_weigh
         for k, v in sd.items():
             e = relnorm(v, ostate[net + "." + k].numpy())
             if v.size <= 16:
-                e = e * 0.1          # tiny tensors (fc3.bias, gains) are cancelling sums: budget 1e-4 instead of 1e-5
+                e = e * small_weight      # (1.0 for the fp32-accurate path; only the reduced-precision variant relaxes tiny cancelling sums)
             worst = max(worst, e)
             if verbose and e > 1e-6:
                 print("  %s agent %d %s.%s relnorm %.3e" % (tag, agent, net, k, e))
@@ -72,7 +72,7 @@ def compare_states(pop, ostate, agent, algo, verbose=False, tag="", moment_weigh
                 if key + "#m" in ostate:
                     em, ev = relnorm(m, ostate[key + "#m"].numpy()), relnorm(v, ostate[key + "#v"].numpy())
                     if m.size <= 16:
-                        em, ev = em * 0.1, ev * 0.1
+                        em, ev = em * small_weight, ev * small_weight
                     worst = max(worst, em * moment_weight, ev * moment_weight)
                     if verbose and max(em, ev) > 1e-6:
                         print("  %s agent %d %s moments relnorm m %.3e v %.3e" % (tag, agent, key, em, ev))
@@ -82,7 +82,7 @@ def compare_states(pop, ostate, agent, algo, verbose=False, tag="", moment_weigh
 
 def run_offpolicy_parity_case(algo="sac", ob=11, ac=3, batch=64, population=2, steps=2, seed=0, custom_loss=0.2,
                               norm_closs=False, acm_critic=True, min_max=True, acm_kind="acm", verbose=False,
-                              gamma=0.99, lr=1e-3, small_std=False, actor_lim=1.0, acm_lim=1.0, alpha_tol=1e-6, moment_weight=1.0):
+                              gamma=0.99, lr=1e-3, small_std=False, actor_lim=1.0, acm_lim=1.0, alpha_tol=1e-6, moment_weight=1.0, small_weight=1.0):
     P, G, B = population, steps, batch
     mn, mx, mean, std = make_stats(ob, seed, min_max)
     obs, nobs, act, rew, done, aacm, eps = make_batches(ob, ac, P, G, B, seed, mn, mx)
@@ -133,7 +133,7 @@ def run_offpolicy_parity_case(algo="sac", ob=11, ac=3, batch=64, population=2, s
                 if verbose and e > 1e-5:
                     print("  loss %s agent %d step %d: cuda %.8g oracle %.8g" % (name, a, g, losses[a, g, slot], ol[name]))
                 worst = max(worst, min(e, 1.0) if e > 1e-5 else 0.0)
-        worst = max(worst, compare_states(pop, s, a, algo, verbose=verbose, tag=algo, moment_weight=moment_weight))
+        worst = max(worst, compare_states(pop, s, a, algo, verbose=verbose, tag=algo, moment_weight=moment_weight, small_weight=small_weight))
         if algo == "sac":
             la, _ = pop.alpha(a)
             e = abs(la - float(s["log_alpha"])) / abs(float(s["log_alpha"]))

@@ -166,7 +166,7 @@ def test_update_acm_epochs_steplr_and_validation_loss_match_reference_fixture():
     ad, step = m._pop.adam_state("acm")
     assert step == 12                                   # 3 epochs x ceil(250 / 64) minibatches
     for k, v in sd.items():
-        lim = 1e-4 if v.size <= 16 else 1e-5
+        lim = 1e-5
         assert relnorm(v, g["acm." + k]) < lim, (k, relnorm(v, g["acm." + k]))
         assert relnorm(ad[k][0], g["acm." + k + "#m"]) < lim, k
         assert relnorm(ad[k][1], g["acm." + k + "#v"]) < lim, k

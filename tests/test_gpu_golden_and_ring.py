@@ -18,12 +18,12 @@ def _cmp_gold(pop, gold, nets, tol=1e-5):
         sd = pop.state_dict(net, agent=0)
         for k, v in sd.items():
             e = relnorm(v, gold[net + "." + k])
-            assert e < (1e-4 if v.size <= 16 else tol), (net, k, e)
+            assert e < tol, (net, k, e)
         if not net.endswith("_targ"):
             ad, step = pop.adam_state(net, agent=0)
             assert step == int(gold[net + "#step"])
             for k, (m, v) in ad.items():
-                lim = 1e-4 if m.size <= 16 else tol
+                lim = tol
                 assert relnorm(m, gold[net + "." + k + "#m"]) < lim, (net, k)
                 assert relnorm(v, gold[net + "." + k + "#v"]) < lim, (net, k)
 
@@ -195,7 +195,7 @@ def test_acm_regression_matches_reference_fixture(kind):
         ad, step = pop.adam_state("acm", agent=a)
         assert step == n
         for k, v in sd.items():
-            lim = 1e-4 if v.size <= 16 else 1e-5
+            lim = 1e-5
             assert relnorm(v, g[kind + ":acm." + k]) < lim, (k, relnorm(v, g[kind + ":acm." + k]))
             assert relnorm(ad[k][0], g[kind + ":acm." + k + "#m"]) < lim, k
             assert relnorm(ad[k][1], g[kind + ":acm." + k + "#v"]) < lim, k

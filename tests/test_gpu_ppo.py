@@ -43,21 +43,21 @@ def test_ppo_update_matches_reference_fixture(critic_tc):
     ts, tl = _trajectories(g["end"])
     pol.load_rollout(obs, nobs, g["actions"], g["logp"], g["rewards"], g["done"], g["end"], ts, tl)
     loss = pol.update_critic(int(ntu), int(nupt))
-    assert loss == pytest.approx(float(g["critic_loss"]), rel=1e-4)
+    assert loss == pytest.approx(float(g["critic_loss"]), rel=1e-5)
     sd = pol.state_dict("critic")
     for k, v in sd.items():
-        assert relnorm(v, g["fit:critic." + k]) < (1e-4 if v.size <= 16 else 1e-5), (k, relnorm(v, g["fit:critic." + k]))
+        assert relnorm(v, g["fit:critic." + k]) < 1e-5, (k, relnorm(v, g["fit:critic." + k]))
     adv = pol.advantages()
-    assert np.abs(adv - g["adv"]).max() < 2e-5 * max(1.0, np.abs(g["adv"]).max())
+    assert np.abs(adv - g["adv"]).max() < 1e-5 * max(1.0, np.abs(g["adv"]).max())
     pol.normalize_adv()
     losses, epochs, kl = pol.update_actor(g["perms"], int(bs), kl_thr, int(max_ep))
     assert epochs + 1 == int(g["epochs_run"])          # the reference counts i + 1 after its early-stop break
     ref = g["actor_losses"]
     for key, r in zip(("actor", "entropy", "policy", "dist"), ref):
-        assert losses[key] == pytest.approx(float(r), rel=2e-4), key
+        assert losses[key] == pytest.approx(float(r), rel=1e-5), key
     sd = pol.state_dict("actor")
     for k, v in sd.items():
-        assert relnorm(v, g["post:actor." + k]) < 2e-5, (k, relnorm(v, g["post:actor." + k]))
+        assert relnorm(v, g["post:actor." + k]) < 1e-5, (k, relnorm(v, g["post:actor." + k]))
     pol.close()
 
 
@@ -83,10 +83,10 @@ def test_plain_ppo_actor_epochs_match_reference_fixture():
     losses, epochs, kl = pol.update_actor(g["perms"], int(bs), kl_thr, int(max_ep))
     assert min(epochs + 1, int(max_ep)) == int(gp["epochs_counter"])
     for key, r in zip(("actor", "entropy", "policy"), gp["losses"]):
-        assert losses[key] == pytest.approx(float(r), rel=2e-4), key
+        assert losses[key] == pytest.approx(float(r), rel=1e-5), key
     sd = pol.state_dict("actor")
     for k, v in sd.items():
-        assert relnorm(v, gp["post:actor." + k]) < 2e-5, (k, relnorm(v, gp["post:actor." + k]))
+        assert relnorm(v, gp["post:actor." + k]) < 1e-5, (k, relnorm(v, gp["post:actor." + k]))
     pol.close()
 
 
@@ -110,18 +110,18 @@ def test_a2c_acm_two_iterations_match_reference_fixture():
     for it in (1, 2):
         pol.load_rollout(obs, nobs, g["actions"], ga["logp%d" % it], g["rewards"], g["done"], g["end"], ts, tl)
         loss = pol.update_critic(int(ntu), int(nupt))
-        assert loss == pytest.approx(float(ga["critic_loss%d" % it]), rel=1e-4)
+        assert loss == pytest.approx(float(ga["critic_loss%d" % it]), rel=1e-5)
         adv = pol.advantages()
         ref = ga["adv%d" % it]
-        assert np.abs(adv - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+        assert np.abs(adv - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
         pol.load_advantages(ref)
         actor_loss, dist_sum = pol.a2c_actor_step(accumulate=True, normalize_adv=True)
         dist = dist_sum / (N * ob)
         for v, r in zip((actor_loss, dist, actor_loss + 0.1 * dist), ga["losses%d" % it]):
-            assert v == pytest.approx(float(r), rel=2e-4, abs=1e-6)
+            assert v == pytest.approx(float(r), rel=1e-5, abs=1e-7)
         sd = pol.state_dict("actor")
         for k, v in sd.items():
-            assert relnorm(v, ga["post%d:actor.%s" % (it, k)]) < 2e-5, (it, k, relnorm(v, ga["post%d:actor.%s" % (it, k)]))
+            assert relnorm(v, ga["post%d:actor.%s" % (it, k)]) < 1e-5, (it, k, relnorm(v, ga["post%d:actor.%s" % (it, k)]))
     pol.close()
 
 
@@ -129,8 +129,8 @@ def test_a2c_acm_two_iterations_match_reference_fixture():
 def test_ppo_step_major_large_batch_matches_oracle(E, T, mb, n_epochs):
     """E environments x T steps in step-major order (row = t * E + e): GAE strides by E; several CTAs per phase.  The second case is
     config 4's shape class: 1 048 576 rows, 65 536-row minibatches -- fp32 reductions over a million rows, every CTA's
-    partial-gradient slot and the [T][E] stride against the oracle.  Tolerances as in the small case: critic loss 1e-4, advantages
-    2e-5 of their range, losses 2e-4, post-epoch actor weights 2e-5 norm-relative."""
+    partial-gradient slot and the [T][E] stride against the oracle.  Tolerances as in the small case: north_star's 1e-5 (critic loss,
+    advantages relative to their range, losses, post-epoch actor weights norm-relative)."""
     ob, ac = 17, 6
     N = E * T
     rng = np.random.RandomState(3)
@@ -162,7 +162,7 @@ def test_ppo_step_major_large_batch_matches_oracle(E, T, mb, n_epochs):
     x, xn = normalize(st, torch.from_numpy(obs), True), normalize(st, torch.from_numpy(nobs), True)
     tr, td, te = torch.from_numpy(rew), torch.from_numpy(done), torch.from_numpy(end)
     ref_loss = P.update_critic(s, x, xn, tr, td, 0.99, 3e-4, 2, 3)
-    assert pol.update_critic(2, 3) == pytest.approx(ref_loss, rel=1e-4)
+    assert pol.update_critic(2, 3) == pytest.approx(ref_loss, rel=1e-5)
     # oracle GAE per environment (time-major view of the step-major rows)
     v = torch.zeros(N); nv = torch.zeros(N)
     from oracle import nets
@@ -186,7 +186,7 @@ def test_ppo_step_major_large_batch_matches_oracle(E, T, mb, n_epochs):
         assert torch.equal(vec[first], adv_ref[first])
         adv_ref = vec
     adv = pol.advantages()
-    assert np.abs(adv - adv_ref.numpy()).max() < 2e-5 * max(1.0, float(adv_ref.abs().max()))
+    assert np.abs(adv - adv_ref.numpy()).max() < 1e-5 * max(1.0, float(adv_ref.abs().max()))
     pol.normalize_adv()
     advn = P.normalize_adv(adv_ref)
     perms = np.stack([rng.permutation(N) for _ in range(n_epochs)]).astype(np.int64)
@@ -196,10 +196,10 @@ def test_ppo_step_major_large_batch_matches_oracle(E, T, mb, n_epochs):
     assert epochs_c == epochs
     assert kl_c == pytest.approx(kl, rel=1e-3, abs=1e-5)
     for key in ("actor", "entropy", "policy", "dist"):
-        assert losses[key] == pytest.approx(tot[key], rel=2e-4, abs=1e-5), key
+        assert losses[key] == pytest.approx(tot[key], rel=1e-5, abs=1e-6), key
     sd = pol.state_dict("actor")
     for k, val in sd.items():
-        assert relnorm(val, s["actor." + k].numpy()) < 2e-5, (k, relnorm(val, s["actor." + k].numpy()))
+        assert relnorm(val, s["actor." + k].numpy()) < 1e-5, (k, relnorm(val, s["actor." + k].numpy()))
     pol.close()
 
 
