@@ -116,6 +116,10 @@ int spp_ring_fill_synthetic(spp_population* p, uint64_t seed, int64_t n, int epi
 /* Device-resident gather of n_batches minibatches per agent (indices drawn on device): measures the
  * HBM path of sample_batch in isolation.  bytes_out = algorithmic bytes moved per call. */
 int spp_ring_gather_bench_device(spp_population* p, int n_batches, uint64_t seed, double* bytes_out, void* stream);
+/* test hook: rows [first, first + n) of the dense minibatches the last spp_ring_gather_bench_device call produced (host arrays
+ * [n][ob], [n][ob], [n][ac], [n], [n]); the kernel's index of global row t is mulhi64(Philox4x32-10(seed, agent, t mod (n_batches B)).xy, len) */
+int spp_ring_gather_bench_rows(spp_population* p, int n_batches, int64_t first, int n, float* obs, float* nobs, float* aacm, float* rew,
+                               int8_t* done);
 
 /* ---- the update step: SAC_AcM.update (rltoolkit/acm/off_policy/sac_acm.py:89-162) /
  *      DDPG_AcM.update (rltoolkit/acm/off_policy/ddpg_acm.py:147-201), `grad_steps` in a row as

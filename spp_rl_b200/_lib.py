@@ -76,6 +76,7 @@ SIGNATURES = {
     "spp_ring_obs_stats": (C.c_int, [_vp, _f64p, _f64p]),
     "spp_ring_fill_synthetic": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_int]),
     "spp_ring_gather_bench_device": (C.c_int, [_vp, C.c_int, C.c_uint64, _f64p, _vp]),
+    "spp_ring_gather_bench_rows": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_int8)]),
     "spp_update_host": (C.c_int, [_vp, C.c_int, _f32p, _f32p, _f32p, _f32p, _i8p, _f32p, _f32p, C.c_uint64, _f32p]),
     "spp_update_ring": (C.c_int, [_vp, C.c_int, _i64p, _f32p, C.c_uint64, _f32p]),
     "spp_update_ring_device": (C.c_int, [_vp, C.c_int, C.c_uint64, _vp, _vp]),

@@ -764,6 +764,32 @@ int spp_ring_gather_bench_device(spp_population* p, int n_batches, uint64_t seed
     return SPP_OK;
 }
 
+// rows [first, first + n) of the dense minibatches the last spp_ring_gather_bench_device call left on the device (test hook: the
+// bench kernel draws its indices on the device -- Philox4x32-10(seed, agent, row in the agent's block) -> mulhi(x.x:x.y, len) --
+// so a test can recompute them and compare with spp_ring_sample_batch)
+int spp_ring_gather_bench_rows(spp_population* p, int n_batches, int64_t first, int n, float* obs, float* nobs, float* aacm, float* rew,
+                               int8_t* done) {
+    if (!p || !obs || !nobs || !aacm || !rew || !done || n < 1 || first < 0) return fail(SPP_ERR_ARG, "bad argument");
+    const Layout& L = p->L;
+    const size_t rows = (size_t)p->P * n_batches * L.B;
+    if ((size_t)first + n > rows || !p->d_tmp.p) return fail(SPP_ERR_ARG, "rows outside the last gather");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    const float* o_obs = (const float*)p->d_tmp.p; const float* o_nobs = o_obs + rows * L.ldo; const float* o_aacm = o_nobs + rows * L.ldo;
+    const float* o_rew = o_aacm + rows * L.lda; const uint8_t* o_done = (const uint8_t*)(o_rew + rows);
+    std::vector<float> tmp((size_t)n * (L.ldo > L.lda ? L.ldo : L.lda));
+    auto rows_out = [&](const float* src, int ld, int w, float* dst) -> cudaError_t {
+        cudaError_t e = cudaMemcpy(tmp.data(), src + (size_t)first * ld, (size_t)n * ld * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return e;
+        for (int r = 0; r < n; ++r) memcpy(dst + (size_t)r * w, tmp.data() + (size_t)r * ld, (size_t)w * 4);
+        return cudaSuccess;
+    };
+    CK(rows_out(o_obs, L.ldo, L.ob, obs)); CK(rows_out(o_nobs, L.ldo, L.ob, nobs)); CK(rows_out(o_aacm, L.lda, L.ac, aacm));
+    CK(cudaMemcpy(rew, o_rew + first, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(done, o_done + first, (size_t)n, cudaMemcpyDeviceToHost));
+    return SPP_OK;
+}
+
 // ---- update ----------------------------------------------------------------------------------------
 // 1: the 128 x 128 GEMMs of the update burst run on tcgen05 (3-pass tf32 split); 0: FFMA tiles.  Both are device paths;
 // the switch exists for A/B measurement and kernel bisection (environment SPP_UMMA=0 or spp_set_gemm_path).

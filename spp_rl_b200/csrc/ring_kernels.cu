@@ -27,32 +27,60 @@ __global__ void ring_gather_kernel(RingView R, int agent, const int64_t* __restr
     }
 }
 
-// Population-wide gather benchmark: every warp gathers rows for (agent, batch, row) with device-drawn indices
-// and writes dense minibatches [P][nb][B][...] -- the HBM side of sample_batch with nothing else attached.
-__global__ void ring_gather_bench_kernel(RingView R, int P, int nb, int B, const int64_t* __restrict__ len, uint64_t seed,
-                                         float* __restrict__ out_obs, float* __restrict__ out_nobs,
-                                         float* __restrict__ out_aacm, float* __restrict__ out_rew,
-                                         uint8_t* __restrict__ out_done) {
-    const int lane = threadIdx.x & 31;
+// Population-wide gather benchmark: rows for (agent, batch, row) with device-drawn indices into dense minibatches [P][nb][B][...] --
+// the HBM side of sample_batch with nothing else attached.  Two phases per warp and 32 rows, like stage_gather of the fused update
+// kernel: (1) every lane draws ONE row index and loads its obs / next-obs slots (32 independent index -> slot chains in flight per
+// warp), (2) groups of four lanes copy one row each (float4 per lane), eight rows at a time with every load issued before the first
+// store.  A warp per row (round 1) kept three lanes busy and one dependent chain in flight: 363 GB/s algorithmic.
+__global__ void __launch_bounds__(256) ring_gather_bench_kernel(RingView R, int P, int nb, int B, const int64_t* __restrict__ len, uint64_t seed,
+                                                                float* __restrict__ out_obs, float* __restrict__ out_nobs,
+                                                                float* __restrict__ out_aacm, float* __restrict__ out_rew,
+                                                                uint8_t* __restrict__ out_done) {
+    const int lane = threadIdx.x & 31, sub = lane >> 2, l4 = lane & 3;
     const size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nw = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const size_t total = (size_t)P * nb * B;
+    const size_t total = (size_t)P * nb * B, per_agent = (size_t)nb * B;
     const int ldo4 = R.ldo / 4, lda4 = R.lda / 4;
-    for (size_t t = w; t < total; t += nw) {
-        const int agent = (int)(t / ((size_t)nb * B));
-        const uint4 x = Philox::gen(seed, (uint64_t)agent, (uint64_t)(t % ((size_t)nb * B)));
-        const int64_t i = (int64_t)__umul64hi(((uint64_t)x.x << 32) | x.y, (uint64_t)len[agent]);
+    for (size_t t0 = w * 32; t0 < total; t0 += nw * 32) {
+        // phase 1: lane -> row t0 + lane
+        const size_t t = t0 + lane;
+        const bool ok = t < total;
+        const int agent = ok ? (int)(t / per_agent) : 0;
         const size_t base = (size_t)agent * R.S;
-        const int32_t oi = R.oidx[base + i], ni = R.nidx[base + i];
-        const float4* po = reinterpret_cast<const float4*>(R.obs + (base + oi) * R.ldo);
-        const float4* pn = reinterpret_cast<const float4*>(R.obs + (base + ni) * R.ldo);
-        float4* qo = reinterpret_cast<float4*>(out_obs + t * R.ldo);
-        float4* qn = reinterpret_cast<float4*>(out_nobs + t * R.ldo);
-        for (int j = lane; j < ldo4; j += 32) { qo[j] = __ldg(po + j); qn[j] = __ldg(pn + j); }
-        if (lane < lda4)
-            reinterpret_cast<float4*>(out_aacm + t * R.lda)[lane] =
-                __ldg(reinterpret_cast<const float4*>(R.aacm + (base + i) * R.lda) + lane);
-        if (lane == 0) { out_rew[t] = R.rew[base + i]; out_done[t] = R.done[base + i]; }
+        int64_t i = 0; int32_t oi = 0, ni = 0; float rew = 0.f; uint8_t dn = 0;
+        if (ok) {
+            const uint4 x = Philox::gen(seed, (uint64_t)agent, (uint64_t)(t % per_agent));
+            i = (int64_t)__umul64hi(((uint64_t)x.x << 32) | x.y, (uint64_t)len[agent]);
+            oi = __ldg(R.oidx + base + i); ni = __ldg(R.nidx + base + i);
+            rew = __ldg(R.rew + base + i); dn = __ldg(R.done + base + i);
+        }
+        if (ok) { out_rew[t] = rew; out_done[t] = dn; }
+        // phase 2: four lanes per row, eight rows per step
+#pragma unroll
+        for (int step = 0; step < 4; ++step) {
+            const int src = step * 8 + sub;
+            const size_t tr = t0 + src;
+            const int64_t ir = __shfl_sync(0xffffffffu, i, src);
+            const int32_t oir = __shfl_sync(0xffffffffu, oi, src), nir = __shfl_sync(0xffffffffu, ni, src);
+            const int ar = __shfl_sync(0xffffffffu, agent, src);
+            if (tr >= total) continue;
+            const size_t br = (size_t)ar * R.S;
+            const float4* po = reinterpret_cast<const float4*>(R.obs + (br + oir) * R.ldo);
+            const float4* pn = reinterpret_cast<const float4*>(R.obs + (br + nir) * R.ldo);
+            float4* qo = reinterpret_cast<float4*>(out_obs + tr * R.ldo);
+            float4* qn = reinterpret_cast<float4*>(out_nobs + tr * R.ldo);
+            if (ldo4 <= 4) {      // rows of up to 16 floats: one float4 per lane, loads first
+                float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), vn = vo, va = vo;
+                if (l4 < ldo4) { vo = __ldg(po + l4); vn = __ldg(pn + l4); }
+                if (l4 < lda4) va = __ldg(reinterpret_cast<const float4*>(R.aacm + (br + ir) * R.lda) + l4);
+                if (l4 < ldo4) { qo[l4] = vo; qn[l4] = vn; }
+                if (l4 < lda4) reinterpret_cast<float4*>(out_aacm + tr * R.lda)[l4] = va;
+            } else {
+                for (int j = l4; j < ldo4; j += 4) { const float4 vo = __ldg(po + j), vn = __ldg(pn + j); qo[j] = vo; qn[j] = vn; }
+                for (int j = l4; j < lda4; j += 4)
+                    reinterpret_cast<float4*>(out_aacm + tr * R.lda)[j] = __ldg(reinterpret_cast<const float4*>(R.aacm + (br + ir) * R.lda) + j);
+            }
+        }
     }
 }
 

@@ -210,6 +210,14 @@ class Population:
         check(self.lib.spp_ring_gather_bench_device(self.h, int(n_batches), int(seed), C.byref(b), stream))
         return b.value
 
+    def ring_gather_bench_rows(self, n_batches, first, n):
+        """Rows [first, first + n) of the dense minibatches the last ring_gather_bench call produced (test hook)."""
+        obs = np.empty((n, self.ob_dim), np.float32); nobs = np.empty_like(obs); aacm = np.empty((n, self.ac_dim), np.float32)
+        rew = np.empty(n, np.float32); done = np.empty(n, np.int8)
+        check(self.lib.spp_ring_gather_bench_rows(self.h, int(n_batches), int(first), int(n), _ptr(obs, C.c_float), _ptr(nobs, C.c_float),
+                                                  _ptr(aacm, C.c_float), _ptr(rew, C.c_float), _ptr(done, C.c_int8)))
+        return obs, nobs, aacm, rew, done
+
     # ------------------------------------------------------------------ updates
     def update_host(self, grad_steps, obs, next_obs, action, reward, done, acm_action, eps=None, seed=0, losses=None):
         """The reference's update(obs, next_obs, action, reward, done, acm_action), G steps for P agents.

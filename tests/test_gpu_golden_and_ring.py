@@ -234,3 +234,37 @@ def test_acm_ring_regression_equals_host_form():
         for k in sa:
             assert np.array_equal(sa[k], sb[k]), (a, k)
     pa.close(); pb.close()
+
+
+def _philox4x32_10(seed, stream, ctr):
+    """Philox4x32-10 as csrc/common.cuh: key = seed, counter = (ctr lo, ctr hi, stream lo, stream hi) -> four 32-bit words."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    k = [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]
+    c = [ctr & 0xFFFFFFFF, (ctr >> 32) & 0xFFFFFFFF, stream & 0xFFFFFFFF, (stream >> 32) & 0xFFFFFFFF]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+    return c
+
+
+def test_gather_bench_kernel_gathers_what_sample_batch_gathers():
+    """A1: the population-wide gather kernel bench.py times (ring_gather_bench_kernel, device-drawn indices, two-phase / four lanes
+    per row) against spp_ring_sample_batch on the recomputed indices: every column bit-exact, incl. a ragged last warp."""
+    from spp_rl_b200 import Population
+
+    P, B, NB, n = 3, 50, 3, 4321               # 450 rows: 14 full warps of 32 rows + a ragged one
+    for ob, ac in ((11, 3), (17, 6)):          # rows of 12 floats (one float4 per lane) and of 20 (the strided form)
+        pop = Population(algo="sac", ob_dim=ob, ac_dim=ac, population=P, update_batch_size=B, buffer_size=5000, store_actions=True)
+        pop.ring_fill_synthetic(seed=3, n=n, episode_len=100)
+        seed = 77
+        pop.ring_gather_bench(NB, seed=seed)
+        obs, nobs, aacm, rew, done = pop.ring_gather_bench_rows(NB, 0, P * NB * B)
+        for a in range(P):
+            idx = np.array([(((x[0] << 32) | x[1]) * n) >> 64 for x in (_philox4x32_10(seed, a, t) for t in range(NB * B))], np.int64)
+            assert idx.min() >= 0 and idx.max() < n and len(set(idx.tolist())) > NB * B // 2
+            ro, rn, _, rr, rd, ra = pop.ring_sample_batch(a, idx)
+            sl = slice(a * NB * B, (a + 1) * NB * B)
+            assert np.array_equal(obs[sl], ro) and np.array_equal(nobs[sl], rn) and np.array_equal(aacm[sl], ra)
+            assert np.array_equal(rew[sl], rr) and np.array_equal(done[sl], rd)
+        pop.close()
