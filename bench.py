@@ -658,10 +658,20 @@ def main():
             g1.record(stream)
         barrier()
         g_ms = g0.elapsed_time(g1) / K
+        try:
+            _hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6500.0)
+        except Exception:
+            _hbm_peak = 6500.0
+        _g_traffic = 675.0e6 * (P * NB * B) / 757760.0      # PROFILE CONSTANT: ncu dram__bytes_read + write of this kernel per 757 760 rows
         gather = {"rows_per_launch": P * NB * B, "ms_per_launch": g_ms, "algorithmic_bytes_per_launch": gbytes,
                   "algorithmic_gbs": gbytes / (g_ms * 1e-3) / 1e9, "rows_per_s": P * NB * B / (g_ms * 1e-3),
+                  "roofline": {"bound": "hbm", "achieved": gbytes / (g_ms * 1e-3) / 1e9, "peak": _hbm_peak, "unit": "GB/s",
+                               "frac": gbytes / (g_ms * 1e-3) / 1e9 / _hbm_peak, "traffic": _g_traffic,
+                               "traffic_gbs": _g_traffic / (g_ms * 1e-3) / 1e9,
+                               "note": "achieved = ALGORITHMIC bytes / time; traffic is a profile constant (profiles/r02_gather_summary.md: "
+                                       "4.1x the algorithmic bytes, a random transition touches seven arrays of the ring)"},
                   "note": "ring_gather_bench_kernel: B*((2 ob + ac + 1)*4 + 1) bytes read and written per row + two 4-byte index "
-                          "words; random 44-byte rows of a %.1f GB ring, DRAM sectors moved per row are in profiles/" % (P * RINGC * 114 / 1e9)}
+                          "words; random transitions of a %.1f GB ring" % (P * RINGC * 114 / 1e9)}
 
     # ---- BASELINE configs 3 / 5 through the population train loop, config 4 as whole SPP-PPO iterations (all ranks take part)
     pop.close()
