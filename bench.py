@@ -308,6 +308,7 @@ def ppo_cfg4_block(local_rank, rank, world, dist, K, W, E_total=4096, T=2048, ba
     pop.set_limits(np.ones(ob, np.float32), np.ones(ac, np.float32))
     if world > 1:
         pol.comm_init(dist)
+    pol.set_reserved_sms(1)      # the ACM burst (one 213 KB CTA on the population's stream) runs beside the policy update
     st = pol._ext_stream()
     gen = torch.Generator(device="cuda")
     phases = {}
@@ -370,6 +371,7 @@ def ppo_cfg4_block(local_rank, rank, world, dist, K, W, E_total=4096, T=2048, ba
            "scaling": "strong", "n_gpus": world, "ms_per_iteration": ms, "transitions_per_s": N / (ms * 1e-3),
            "phases_ms_rank0": {k: v / K for k, v in phases.items()}, "critic_steps": critic_targets * critic_steps, "actor_epochs": res["epochs"],
            "global_minibatch": batch, "allreduces_per_iteration": res["allreduces"], "nccl_version": info["nccl_version"],
+           "allreduce_path": ("fused reduce + all-reduce kernel over NVLink peer memory (csrc/ppo_p2p.cu)" if info.get("p2p") else ("NCCL" if world > 1 else "none")),
            "acm_update_batches": acm_batches, "critic_loss": res["critic_loss"], "kl": res["kl"],
            "timing": "host clock between barriers + device synchronisation on both sides (the iteration spans two streams and host index work), max over ranks"}
     pol.close(); pop.close()

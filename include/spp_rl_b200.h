@@ -221,6 +221,9 @@ int spp_ppo_critic_apply(spp_ppo* p);
 /* critic gradient kernel: 1 (default) = the 64-wide contractions on tcgen05 with weights resident in shared memory
  * (csrc/ppo_critic_tc.cu; observations of up to 19 floats), 0 = the FFMA tile kernel (also the path for wider observations) */
 int spp_ppo_set_critic_path(spp_ppo* p, int tensor_cores);
+/* keep n SMs out of the grids of the policy's row-sharded kernels (default 0): for a concurrent kernel of another stream that occupies
+ * whole SMs for long (the ACM regression burst running beside the policy update), so that no launch spills into a second wave */
+int spp_ppo_set_reserved_sms(spp_ppo* p, int n);
 /* PPO.calculate_advantage = calculate_q_val + calculate_gae (rltoolkit/algorithms/ppo/ppo.py:101-150) incl. the bootstrap
  * at non-terminal ends; adv_host [N] may be NULL.  AdvantageDataset normalisation (advantage_dataset.py:9-12): unbiased std,
  * eps 1.2e-7; global_stats = (n, sum, sum of squares) over all ranks or NULL for local. */
@@ -268,6 +271,15 @@ int spp_ppo_actor_epoch_device(spp_ppo* p, const int64_t* ids_dev, const int64_t
 int spp_comm_unique_id(char out[128]);
 int spp_ppo_comm_init(spp_ppo* p, const char id[128], int rank, int world);
 int spp_ppo_comm_info(spp_ppo* p, int* world, int64_t* allreduces, int* nccl_version);
+/* The per-step gradient all-reduce over NVLink PEER MEMORY instead of NCCL (csrc/ppo_p2p.cu): one kernel per optimiser step sums the
+ * gradient kernel's per-CTA partials, publishes the rank's vector in an exchange buffer its peers have mapped (CUDA IPC), waits for
+ * theirs and adds all ranks' vectors in rank order (bit-identical on every rank).  spp_ppo_p2p_handle returns this rank's 64-byte IPC
+ * handle; the caller gathers the handles of all ranks (any transport) and passes them, rank-major, to spp_ppo_p2p_init on every
+ * rank after spp_ppo_comm_init.  Unsupported set-ups (no peer access) return SPP_ERR_UNSUPPORTED and the NCCL path stays.
+ * spp_ppo_p2p_info: whether the path is on, steps taken through it, and the device-side time-out flag (a peer never arrived). */
+int spp_ppo_p2p_handle(spp_ppo* p, char out[64]);
+int spp_ppo_p2p_init(spp_ppo* p, const char* handles, int rank, int world);
+int spp_ppo_p2p_info(spp_ppo* p, int* on, int64_t* steps, int* err);
 int spp_ppo_actor_apply(spp_ppo* p);
 int spp_ppo_scalars(spp_ppo* p, float out[8]);
 /* Rollout step of A2C.collect_batch (rltoolkit/algorithms/a2c/a2c.py:165-167) for E observations at once:

@@ -111,6 +111,7 @@ SIGNATURES = {
     "spp_ppo_normalize_adv_eps": (C.c_int, [_vp, _f64p, C.c_double]),
     "spp_ppo_grad_accumulate": (C.c_int, [_vp, C.c_int]),
     "spp_ppo_set_critic_path": (C.c_int, [_vp, C.c_int]),
+    "spp_ppo_set_reserved_sms": (C.c_int, [_vp, C.c_int]),
     "spp_ppo_update_actor": (C.c_int, [_vp, _i64p, C.c_int, C.c_int, C.c_double, _f32p, _i32p, _f32p]),
     "spp_ppo_actor_minibatch_grad": (C.c_int, [_vp, _i64p, C.c_int64, C.c_int64]),
     "spp_ppo_actor_minibatch_grad_device": (C.c_int, [_vp, C.c_void_p, C.c_int64, C.c_int64]),
@@ -122,6 +123,9 @@ SIGNATURES = {
     "spp_comm_unique_id": (C.c_int, [C.c_char_p]),
     "spp_ppo_comm_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
     "spp_ppo_comm_info": (C.c_int, [_vp, _i32p, _i64p, _i32p]),
+    "spp_ppo_p2p_handle": (C.c_int, [_vp, C.c_char_p]),
+    "spp_ppo_p2p_init": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
+    "spp_ppo_p2p_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "spp_ppo_rollout_synthetic": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_int, C.c_int,
                                              _f32p, _f32p, _f32p, _f32p]),
     "spp_ppo_store_download": (C.c_int, [_vp, C.c_char_p, _f32p]),

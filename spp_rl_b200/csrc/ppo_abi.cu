@@ -65,12 +65,14 @@ NcclApi& nccl() {
     } while (0)
 
 #include "ppo_rollout.h"
+#include "ppo_p2p.h"
 
 struct PTensor { std::string name; int layer; int is_bias; int rows, cols; };
 
 struct spp_ppo {
     spp_ppo_config cfg;
     int device = 0, sm_count = 0, grid = 0;
+    int sm_use = 0;             // SMs the row-sharded kernels spread over: sm_count minus what spp_ppo_set_reserved_sms keeps free
     PpoLayout L;
     PpoHyper h;
     int64_t cap_rows = 0, cap_batch = 0;
@@ -88,6 +90,11 @@ struct spp_ppo {
     ncclComm_t comm = nullptr;  // data-parallel runs (spp_ppo_comm_init): gradients + scalars are all-reduced inside the entry points
     int rank = 0, world = 1;
     int64_t n_allreduce = 0;    // collectives issued so far (reported by the benches)
+    // NVLink peer-memory all-reduce (ppo_p2p.cu): exchange buffer [2][total] floats + flag words, mapped into every peer by CUDA IPC
+    float* p2p_buf = nullptr; uint32_t* p2p_flags = nullptr; unsigned* p2p_ticket = nullptr; int* p2p_err = nullptr;
+    float* p2p_peer[kP2pMaxRanks] = {}; uint32_t* p2p_peer_flags[kP2pMaxRanks] = {}; void* p2p_mapped[kP2pMaxRanks] = {};
+    int p2p_on = 0; uint32_t p2p_epoch = 0; unsigned p2p_launches = 0; int64_t n_p2p = 0;
+    int defer_reduce = 0, pend_parts = 0, pend_elems = 0;      // inside the library's own loops the local reduce is fused into the all-reduce kernel
     float* slog = nullptr;      // [kLogSlots][PS_COUNT + ldo]: per-step scalars (+ log_scale) recorded on the device, read once per loop
     // device rollout (spp_ppo_rollout_synthetic): persistent environment state and the extra store columns the ACM ring needs
     float* env_state = nullptr; int* env_len = nullptr; int env_E = 0;
@@ -140,6 +147,9 @@ int spp_ppo_destroy(spp_ppo* p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->comm) { nccl().CommDestroy(p->comm); p->comm = nullptr; }
+    for (int r = 0; r < kP2pMaxRanks; ++r) if (p->p2p_mapped[r]) cudaIpcCloseMemHandle(p->p2p_mapped[r]);
+    if (p->p2p_buf) cudaFree(p->p2p_buf);
+    if (p->p2p_ticket) cudaFree(p->p2p_ticket);
     for (void* q : {(void*)p->env_state, (void*)p->env_len, (void*)p->st_aacm, (void*)p->st_raw_next, (void*)p->dperm_epoch, (void*)p->gacc}) if (q) cudaFree(q);
     if (p->store_ev) cudaEventDestroy(p->store_ev);
     for (void* q : p->allocs) cudaFree(q);
@@ -160,7 +170,7 @@ int spp_ppo_create(const spp_ppo_config* cfg, int device, spp_ppo** out) {
     PCK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return spp_set_error_(SPP_ERR_UNSUPPORTED, "spp_rl_b200 is built for sm_100a (B200) only");
     spp_ppo* p = new spp_ppo();
-    p->cfg = *cfg; p->device = device; p->sm_count = prop.multiProcessorCount; p->grid = 2 * prop.multiProcessorCount;      // two resident CTAs per SM (kPpoCtasPerSm)
+    p->cfg = *cfg; p->device = device; p->sm_count = prop.multiProcessorCount; p->sm_use = p->sm_count; p->grid = 2 * prop.multiProcessorCount;      // two resident CTAs per SM (kPpoCtasPerSm)
     p->L = make_ppo_layout(cfg->ob_dim, cfg->ac_dim);
     p->h.gamma = (float)cfg->gamma; p->h.discount = (float)(cfg->gae_lambda * cfg->gamma); p->h.discount_d = cfg->gae_lambda * cfg->gamma;
     p->h.epsilon = (float)cfg->ppo_epsilon; p->h.entropy_coef = (float)cfg->entropy_coef; p->h.custom_loss = (float)cfg->custom_loss;
@@ -375,11 +385,92 @@ int spp_ppo_comm_info(spp_ppo* p, int* world, int64_t* allreduces, int* nccl_ver
     return SPP_OK;
 }
 
+// local reduction of the gradient kernel's per-CTA slots -- or, inside the library's own data-parallel loops with the peer-memory path
+// on, only a note of what to reduce: the all-reduce kernel does it on the way
+static int reduce_local(spp_ppo* p, const PpoArgs& a, int n_part, int n_elems) {
+    if (p->p2p_on && p->defer_reduce) { p->pend_parts = n_part; p->pend_elems = n_elems; return SPP_OK; }
+    PCK(launch_ppo_reduce(a, n_part, n_elems, p->stream)); spp_count_launch_();
+    return SPP_OK;
+}
+
 // gradient vector and the 8 reduced scalars sit in one buffer: ONE collective per optimiser step covers both
 static int allreduce_grads(spp_ppo* p) {
-    if (!p->comm) return SPP_OK;
+    if (!p->comm) {
+        if (p->pend_parts) return spp_set_error_(SPP_ERR_STATE, "deferred reduce without a communicator");
+        return SPP_OK;
+    }
+    if (p->p2p_on) {      // fused reduce + all-reduce over NVLink peer memory (ppo_p2p.cu)
+        P2pArgs x;
+        memset(&x, 0, sizeof(x));
+        x.part = p->part; x.part_stride = p->part_stride; x.n_part = p->pend_parts; x.n_elems = p->pend_elems; x.scal = p->scal;
+        x.gbuf = p->gbuf; x.total = p->part_stride + PS_COUNT;
+        for (int r = 0; r < p->world; ++r) { x.peer[r] = p->p2p_peer[r]; x.peer_flags[r] = p->p2p_peer_flags[r]; }
+        x.epoch = ++p->p2p_epoch; x.rank = p->rank; x.world = p->world;
+        x.ticket = p->p2p_ticket; x.ticket_target = ++p->p2p_launches * (unsigned)((x.total + 255) / 256); x.err = p->p2p_err;
+        PCK(launch_ppo_reduce_p2p(x, p->stream)); spp_count_launch_();
+        p->pend_parts = 0; p->pend_elems = 0;
+        p->n_allreduce++; p->n_p2p++;
+        return SPP_OK;
+    }
     NCK(nccl().AllReduce(p->gbuf, p->gbuf, (size_t)(p->part_stride + PS_COUNT), 7 /* ncclFloat32 */, 0 /* ncclSum */, p->comm, p->stream));
     p->n_allreduce++;
+    return SPP_OK;
+}
+
+// ---- NVLink peer-memory exchange: every rank exports its buffer (CUDA IPC), the host side (any transport) carries the 64-byte handles ----
+int spp_ppo_p2p_handle(spp_ppo* p, char out[64]) {
+    if (!p || !out) return spp_set_error_(SPP_ERR_ARG, "null");
+    PCK(cudaSetDevice(p->device));
+    const size_t total = (size_t)p->part_stride + PS_COUNT;
+    const size_t bytes = ((2 * total * 4 + 255) / 256) * 256 + 2 * kP2pMaxRanks * 4 + 256;
+    if (!p->p2p_buf) {
+        PCK(cudaMalloc(&p->p2p_buf, bytes));      // its own allocation: IPC exports whole allocations
+        PCK(cudaMemset(p->p2p_buf, 0, bytes));
+        p->p2p_flags = (uint32_t*)((char*)p->p2p_buf + ((2 * total * 4 + 255) / 256) * 256);
+        PCK(cudaMalloc(&p->p2p_ticket, 256)); PCK(cudaMemset(p->p2p_ticket, 0, 256));
+        p->p2p_err = (int*)(p->p2p_ticket + 16);
+    }
+    cudaIpcMemHandle_t h;
+    PCK(cudaIpcGetMemHandle(&h, p->p2p_buf));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(out, &h, 64);
+    return SPP_OK;
+}
+
+int spp_ppo_p2p_init(spp_ppo* p, const char* handles, int rank, int world) {
+    if (!p || !handles || world < 2 || world > kP2pMaxRanks || rank < 0 || rank >= world) return spp_set_error_(SPP_ERR_ARG, "spp_ppo_p2p_init: bad argument");
+    if (!p->comm || p->rank != rank || p->world != world) return spp_set_error_(SPP_ERR_STATE, "spp_ppo_comm_init first (same rank / world)");
+    if (!p->p2p_buf) return spp_set_error_(SPP_ERR_STATE, "spp_ppo_p2p_handle first");
+    PCK(cudaSetDevice(p->device));
+    const size_t total = (size_t)p->part_stride + PS_COUNT;
+    const size_t flag_off = ((2 * total * 4 + 255) / 256) * 256;
+    for (int r = 0; r < world; ++r) {
+        void* base = p->p2p_buf;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)r * 64, 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                return spp_set_error_(SPP_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            }
+            p->p2p_mapped[r] = base;
+        }
+        p->p2p_peer[r] = (float*)base;
+        p->p2p_peer_flags[r] = (uint32_t*)((char*)base + flag_off);
+    }
+    p->p2p_on = 1;
+    return SPP_OK;
+}
+
+int spp_ppo_p2p_info(spp_ppo* p, int* on, int64_t* steps, int* err) {
+    if (!p) return spp_set_error_(SPP_ERR_ARG, "null");
+    if (on) *on = p->p2p_on;
+    if (steps) *steps = p->n_p2p;
+    if (err) {
+        *err = 0;
+        if (p->p2p_err) { PCK(cudaSetDevice(p->device)); PCK(cudaStreamSynchronize(p->stream)); PCK(cudaMemcpy(err, p->p2p_err, 4, cudaMemcpyDeviceToHost)); }
+    }
     return SPP_OK;
 }
 
@@ -495,13 +586,21 @@ int spp_ppo_critic_grad(spp_ppo* p) {         // local gradient of 0.5 mean((q -
     PCK(cudaSetDevice(p->device));
     PpoArgs a; fill(p, a, p->d.N);
     if (p->critic_tc && ppo_critic_tc_supported(p->L.ob, p->L.ldo)) {      // one persistent CTA per SM, rows in tiles of 128
-        a.rows_per_cta = rows_per_cta(p->d.N, p->sm_count);
-        PCK(launch_ppo_critic_grad_tc(a, p->sm_count, p->stream)); spp_count_launch_();
-        PCK(launch_ppo_reduce(a, p->sm_count, p->L.critic.size, p->stream)); spp_count_launch_();
-        return SPP_OK;
+        a.rows_per_cta = rows_per_cta(p->d.N, p->sm_use);
+        PCK(launch_ppo_critic_grad_tc(a, p->sm_use, p->stream)); spp_count_launch_();
+        return reduce_local(p, a, p->sm_use, p->L.critic.size);
     }
     PCK(launch_ppo_critic_grad(a, p->grid, p->stream)); spp_count_launch_();
-    PCK(launch_ppo_reduce(a, p->grid, p->L.critic.size, p->stream)); spp_count_launch_();
+    return reduce_local(p, a, p->grid, p->L.critic.size);
+}
+
+// The row-sharded kernels size their grids for whole SMs (one or two resident CTAs each).  A kernel of ANOTHER stream that holds an SM
+// for long (the ACM regression burst of the population beside the policy: one 213 KB CTA) would push one CTA of every launch into a
+// second wave -- twice the kernel time.  n > 0 leaves n SMs out of every grid (rows are re-split over the rest).
+int spp_ppo_set_reserved_sms(spp_ppo* p, int n) {
+    if (!p || n < 0 || n >= p->sm_count) return spp_set_error_(SPP_ERR_ARG, "bad argument");
+    p->sm_use = p->sm_count - n;
+    p->grid = 2 * p->sm_use;
     return SPP_OK;
 }
 
@@ -533,6 +632,7 @@ int spp_ppo_update_critic(spp_ppo* p, int n_target_updates, int n_updates_per_ta
     if (steps < 1 || steps > kLogSlots) return spp_set_error_(SPP_ERR_ARG, "critic steps outside [1, 4096]");
     // grad kernel -> reduce -> [all-reduce] -> record the loss sum -> Adam, all enqueued on the policy's stream; ONE host read at the end
     int k = 0;
+    struct Defer { spp_ppo* p; Defer(spp_ppo* q) : p(q) { p->defer_reduce = 1; } ~Defer() { p->defer_reduce = 0; p->pend_parts = 0; } } defer(p);
     for (int t = 0; t < n_target_updates; ++t) {
         int rc = spp_ppo_critic_targets(p); if (rc) return rc;
         for (int u = 0; u < n_updates_per_target; ++u, ++k) {
@@ -659,8 +759,7 @@ int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int
     a.mode = (p->a2c && !p->cfg.norm_closs && !p->plain_ppo) ? 1 : 0;
     PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo || p->a2c) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
-    PCK(launch_ppo_reduce(a, p->grid, p->L.actor.size, p->stream)); spp_count_launch_();
-    return SPP_OK;
+    return reduce_local(p, a, p->grid, p->L.actor.size);
 }
 
 int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int64_t n, int64_t n_global) {
@@ -676,8 +775,7 @@ int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int
     a.mode = (p->a2c && !p->cfg.norm_closs && !p->plain_ppo) ? 1 : 0;
     PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo || p->a2c) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
-    PCK(launch_ppo_reduce(a, p->grid, p->L.actor.size, p->stream)); spp_count_launch_();
-    return SPP_OK;
+    return reduce_local(p, a, p->grid, p->L.actor.size);
 }
 
 int spp_ppo_actor_apply(spp_ppo* p) {
@@ -696,6 +794,7 @@ int spp_ppo_actor_epoch_device(spp_ppo* p, const int64_t* ids_dev, const int64_t
     if (!p || !off || !log_host || nb < 1 || nb > kLogSlots) return spp_set_error_(SPP_ERR_ARG, "spp_ppo_actor_epoch_device: bad argument");
     if (p->d.N < 1) return spp_set_error_(SPP_ERR_STATE, "no rollout loaded");
     PCK(cudaSetDevice(p->device));
+    struct Defer { spp_ppo* p; Defer(spp_ppo* q) : p(q) { p->defer_reduce = 1; } ~Defer() { p->defer_reduce = 0; p->pend_parts = 0; } } defer(p);
     for (int k = 0; k < nb; ++k) {
         const int64_t n = off[k + 1] - off[k];
         if (n < 0 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [0, max_batch_rows]");

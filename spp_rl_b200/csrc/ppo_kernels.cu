@@ -378,19 +378,33 @@ __global__ void ppo_adam_kernel(NetDesc d, float* __restrict__ W, float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ GAE, advantage statistics
-// One thread per trajectory, reverse scan (ppo.py:139-148): done -> carry 0; non-terminal end -> bootstrap with V(next).
+// One thread per trajectory, reverse scan (ppo.py:139-148): done -> carry 0; non-terminal end -> bootstrap with V(next).  The carry is a
+// serial fp32 chain, the five loads of a step are not: they are issued eight steps ahead of their use (the scan used to expose one
+// L2 / HBM latency per time step: 2.6 ms for 2048-step trajectories whatever the number of environments).
 __global__ void ppo_gae_kernel(PpoData d, PpoHyper h) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= d.n_traj) return;
     const int64_t start = d.traj_start[t], len = d.traj_len[t], st = d.traj_stride;
+    constexpr int U = 8;
     float carry = 0.f;
-    for (int64_t k = len - 1; k >= 0; --k) {
-        const int64_t r = start + k * st;
-        const float delta = __fsub_rn(d.q[r], d.v[r]);
-        if (d.done[r] != 0.f) carry = delta;                                                       // 0 * discount + delta
-        else if (d.end[r] != 0.f) carry = __fadd_rn((float)((double)d.nv[r] * h.discount_d), delta); // python-float product
-        else carry = __fadd_rn(__fmul_rn(carry, h.discount), delta);
-        d.adv[r] = carry;
+    for (int64_t k0 = len - 1; k0 >= 0; k0 -= U) {
+        float q[U], v[U], nv[U], dn[U], en[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t k = k0 - u;
+            const int64_t r = start + (k >= 0 ? k : 0) * st;
+            q[u] = d.q[r]; v[u] = d.v[r]; nv[u] = d.nv[r]; dn[u] = d.done[r]; en[u] = d.end[r];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t k = k0 - u;
+            if (k < 0) break;
+            const float delta = __fsub_rn(q[u], v[u]);
+            if (dn[u] != 0.f) carry = delta;                                                         // 0 * discount + delta
+            else if (en[u] != 0.f) carry = __fadd_rn((float)((double)nv[u] * h.discount_d), delta);   // python-float product
+            else carry = __fadd_rn(__fmul_rn(carry, h.discount), delta);
+            d.adv[start + k * st] = carry;
+        }
     }
 }
 

@@ -183,6 +183,10 @@ class PpoPolicy:
         """True (default): critic fit on tcgen05 (csrc/ppo_critic_tc.cu); False: the FFMA tile kernel."""
         check(self.lib.spp_ppo_set_critic_path(self.h, int(bool(tensor_cores))))
 
+    def set_reserved_sms(self, n):
+        """Leave n SMs out of the policy kernels' grids (a concurrent ACM burst on another stream holds one)."""
+        check(self.lib.spp_ppo_set_reserved_sms(self.h, int(n)))
+
     def a2c_actor_step(self, accumulate, normalize_adv=True):
         """One A2C actor update on the loaded rollout and the advantages on the device: optional normalisation with A2C's epsilon
         (a2c.py:275-277), one full-batch gradient of mean(-logp * adv), gradient accumulation when the reference never zeroes
@@ -221,11 +225,37 @@ class PpoPolicy:
         dist.broadcast(t, 0)
         check(self.lib.spp_ppo_comm_init(self.h, bytes(t.cpu().numpy().tobytes()), rank, world))
         self.world, self.rank = world, rank
+        # the per-step gradient all-reduce over NVLink peer memory (csrc/ppo_p2p.cu): every rank exports its exchange buffer by CUDA
+        # IPC, torch.distributed only carries the 64-byte handles.  SPP_PPO_P2P=0 keeps NCCL for that collective as well.
+        import os
+        import sys
+
+        self.p2p = False
+        if world > 1 and world <= 8 and dev == "cuda" and os.environ.get("SPP_PPO_P2P", "1") != "0":
+            hb = C.create_string_buffer(64)
+            check(self.lib.spp_ppo_p2p_handle(self.h, hb))
+            mine = torch.frombuffer(bytearray(hb.raw), dtype=torch.uint8).clone().to(dev)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+            rc = self.lib.spp_ppo_p2p_init(self.h, blob, rank, world)
+            ok = torch.tensor([1 if rc == 0 else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks or none
+            if int(ok.item()) == 1:
+                self.p2p = True
+            else:
+                if rc == 0:
+                    raise SppError("peer-memory all-reduce came up on this rank but not on every rank")
+                print("spp_rl_b200: NVLink peer-memory all-reduce unavailable (%s); using NCCL" % self.lib.spp_last_error().decode(), file=sys.stderr)
 
     def comm_info(self):
         w, n, v = C.c_int(), C.c_int64(), C.c_int()
         check(self.lib.spp_ppo_comm_info(self.h, C.byref(w), C.byref(n), C.byref(v)))
-        return {"world": w.value, "allreduces": n.value, "nccl_version": v.value}
+        on, steps, err = C.c_int(), C.c_int64(), C.c_int()
+        check(self.lib.spp_ppo_p2p_info(self.h, C.byref(on), C.byref(steps), C.byref(err)))
+        if err.value:
+            raise SppError("peer-memory all-reduce: a peer's vector never arrived (device-side time-out)")
+        return {"world": w.value, "allreduces": n.value, "nccl_version": v.value, "p2p": bool(on.value), "p2p_steps": steps.value}
 
     def actor_epoch_device(self, ids_dev, off, n_global=None):
         """One epoch of minibatch steps (gather -> grad -> [all-reduce] -> Adam) with this rank's LOCAL row ids on the device
