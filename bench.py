@@ -372,7 +372,7 @@ def ppo_cfg4_block(local_rank, rank, world, dist, K, W, E_total=4096, T=2048, ba
            "phases_ms_rank0": {k: v / K for k, v in phases.items()}, "critic_steps": critic_targets * critic_steps, "actor_epochs": res["epochs"],
            "global_minibatch": batch, "allreduces_per_iteration": res["allreduces"], "nccl_version": info["nccl_version"],
            "allreduce_path": ("fused reduce + all-reduce kernel over NVLink peer memory (csrc/ppo_p2p.cu)" if info.get("p2p") else ("NCCL" if world > 1 else "none")),
-           "acm_update_batches": acm_batches, "critic_loss": res["critic_loss"], "kl": res["kl"],
+           "acm_update_batches": acm_batches, "critic_loss": res["critic_loss"], "kl": res["kl"], "adv_split_ms_last": list(getattr(pol, "_adv_split_ms", ())),
            "timing": "host clock between barriers + device synchronisation on both sides (the iteration spans two streams and host index work), max over ranks"}
     pol.close(); pop.close()
     return out

@@ -102,6 +102,8 @@ struct spp_ppo {
     cudaEvent_t store_ev = nullptr;    // recorded behind the rollout kernel: consumers on other streams wait for it, not for the whole stream
     int store_E = 0, store_T = 0;      // shape of the [T][E] store the last device rollout left (0: rows came from spp_ppo_load_rollout)
     int plain_ppo = 0;          // 1: PPO.update_actor (custom_loss == 0): no distance term, log-prob of the stored actions as they are
+    float* h_log = nullptr;     // pinned staging for the per-step scalar logs [kLogSlots][8 + ldo]
+    double* h_stats = nullptr;  // pinned staging for the advantage statistics (a pageable copy serialises with the other streams' copies)
     int critic_tc = 1;          // critic fit on tcgen05 (ppo_critic_tc.cu) when the shapes allow; 0: the FFMA tile kernel (spp_ppo_set_critic_path)
     int a2c = 0;                // 1: A2C policy gradient -mean(logp * adv) (a2c.py:267-285, on_policy.py:100-124): no ratio, no entropy term
     float* gacc = nullptr;      // A2C_AcM.update_actor_acm never zeroes the actor's gradients: they accumulate here (on_policy.py:117-123)
@@ -112,6 +114,17 @@ struct spp_ppo {
 };
 
 constexpr int kLogSlots = 4096;
+// device log -> host through PINNED staging: a pageable cudaMemcpyAsync serialises with the other streams' work (measured: 13 ms per
+// call beside the ACM burst of the population's stream, against 0.04 ms pinned)
+static cudaError_t read_log(spp_ppo* p, float* dst, size_t floats);
+static cudaError_t read_log(spp_ppo* p, float* dst, size_t floats) {
+    cudaError_t e;
+    if (!p->h_log && (e = cudaHostAlloc((void**)&p->h_log, (size_t)kLogSlots * (PS_COUNT + p->L.ldo) * 4, cudaHostAllocDefault)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(p->h_log, p->slog, floats * 4, cudaMemcpyDeviceToHost, p->stream)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(p->stream)) != cudaSuccess) return e;
+    memcpy(dst, p->h_log, floats * 4);
+    return cudaSuccess;
+}
 static const NetDesc& pnet(const spp_ppo* p, int net) { return net == 0 ? p->L.actor : p->L.critic; }
 
 static int rows_per_cta(int64_t n, int grid) {
@@ -148,6 +161,8 @@ int spp_ppo_destroy(spp_ppo* p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->comm) { nccl().CommDestroy(p->comm); p->comm = nullptr; }
     for (int r = 0; r < kP2pMaxRanks; ++r) if (p->p2p_mapped[r]) cudaIpcCloseMemHandle(p->p2p_mapped[r]);
+    if (p->h_stats) cudaFreeHost(p->h_stats);
+    if (p->h_log) cudaFreeHost(p->h_log);
     if (p->p2p_buf) cudaFree(p->p2p_buf);
     if (p->p2p_ticket) cudaFree(p->p2p_ticket);
     for (void* q : {(void*)p->env_state, (void*)p->env_len, (void*)p->st_aacm, (void*)p->st_raw_next, (void*)p->dperm_epoch, (void*)p->gacc}) if (q) cudaFree(q);
@@ -644,8 +659,7 @@ int spp_ppo_update_critic(spp_ppo* p, int n_target_updates, int n_updates_per_ta
     }
     const int w = PS_COUNT + p->L.ldo;
     std::vector<float> log((size_t)steps * w);
-    PCK(cudaMemcpyAsync(log.data(), p->slog, log.size() * 4, cudaMemcpyDeviceToHost, p->stream));
-    PCK(cudaStreamSynchronize(p->stream));
+    PCK(read_log(p, log.data(), log.size()));
     double tot = 0.0;
     for (int i = 0; i < steps; ++i) tot += 0.5 * (double)log[(size_t)i * w + PS_LOSS] / (double)p->d.Ntot;      // a2c.py:208-216
     if (mean_loss) *mean_loss = (float)(tot / (double)steps);
@@ -679,8 +693,9 @@ int spp_ppo_adv_stats(spp_ppo* p, double out[3]) {       // local (n, sum, sum o
     PCK(cudaSetDevice(p->device));
     PpoArgs a; fill(p, a, p->d.N);
     PCK(launch_ppo_adv_stats(a, p->dstats, p->grid, p->stream)); spp_count_launch_();
-    std::vector<double> h(2 * (size_t)p->grid);
-    PCK(cudaMemcpyAsync(h.data(), p->dstats, h.size() * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (!p->h_stats) PCK(cudaHostAlloc((void**)&p->h_stats, (2 * (size_t)p->sm_count * 2 + 8) * 8, cudaHostAllocDefault));
+    double* h = p->h_stats;
+    PCK(cudaMemcpyAsync(h, p->dstats, 2 * (size_t)p->grid * 8, cudaMemcpyDeviceToHost, p->stream));
     PCK(cudaStreamSynchronize(p->stream));
     double s = 0, s2 = 0;
     for (int i = 0; i < p->grid; ++i) { s += h[2 * i]; s2 += h[2 * i + 1]; }
@@ -720,11 +735,14 @@ int spp_ppo_normalize_adv_eps(spp_ppo* p, const double* global_stats, double eps
     else {
         int rc = spp_ppo_adv_stats(p, st); if (rc) return rc;
         if (p->comm) {      // (n, sum, sum of squares) over all ranks, in fp64 (torch.std parity needs it)
-            PCK(cudaMemcpyAsync(p->dstats, st, 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+            double* hs = p->h_stats + 2 * (size_t)p->sm_count * 2;      // pinned (allocated by spp_ppo_adv_stats above)
+            hs[0] = st[0]; hs[1] = st[1]; hs[2] = st[2];
+            PCK(cudaMemcpyAsync(p->dstats, hs, 3 * sizeof(double), cudaMemcpyHostToDevice, p->stream));
             NCK(nccl().AllReduce(p->dstats, p->dstats, 3, 8 /* ncclFloat64 */, 0, p->comm, p->stream));
             p->n_allreduce++;
-            PCK(cudaMemcpyAsync(st, p->dstats, 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+            PCK(cudaMemcpyAsync(hs, p->dstats, 3 * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
             PCK(cudaStreamSynchronize(p->stream));
+            st[0] = hs[0]; st[1] = hs[1]; st[2] = hs[2];
         }
     }
     const double n = st[0], mean = st[1] / n;
@@ -804,8 +822,7 @@ int spp_ppo_actor_epoch_device(spp_ppo* p, const int64_t* ids_dev, const int64_t
         rc = spp_ppo_actor_apply(p); if (rc) return rc;
     }
     const int w = PS_COUNT + p->L.ldo;
-    PCK(cudaMemcpyAsync(log_host, p->slog, (size_t)nb * w * 4, cudaMemcpyDeviceToHost, p->stream));
-    PCK(cudaStreamSynchronize(p->stream));
+    PCK(read_log(p, log_host, (size_t)nb * w));
     return SPP_OK;
 }
 

@@ -286,9 +286,12 @@ class PpoPolicy:
         closs = self.update_critic(critic_targets, critic_steps)
         t1 = time.perf_counter()
         self.advantages(want_host=False)
+        t1a = time.perf_counter()
         self.normalize_adv()
+        t1b = time.perf_counter()
         self.sync()
         t2 = time.perf_counter()
+        self._adv_split_ms = ((t1a - t1) * 1e3, (t1b - t1a) * 1e3, (t2 - t1b) * 1e3)
         on_device = isinstance(perms, (list, tuple)) and len(perms) > 0 and torch.is_tensor(perms[0])      # epoch permutations already on the device
         if not on_device:
             perms = np.ascontiguousarray(perms, np.int64)
