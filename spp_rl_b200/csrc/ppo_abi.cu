@@ -776,6 +776,11 @@ int spp_ppo_actor_minibatch_grad(spp_ppo* p, const int64_t* perm, int64_t n, int
     // A2C takes the log-prob of the stored (normalised-space) actions and denormalises only inside its distance term (on_policy.py:106-116)
     a.mode = (p->a2c && !p->cfg.norm_closs && !p->plain_ppo) ? 1 : 0;
     PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo || p->a2c) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    if (p->critic_tc && ppo_critic_tc_supported(p->L.ob, p->L.ldo)) {      // same tile machinery as the critic fit (ppo_critic_tc.cu)
+        a.rows_per_cta = rows_per_cta(n, p->sm_use);
+        PCK(launch_ppo_actor_grad_tc(a, p->sm_use, p->stream)); spp_count_launch_();
+        return reduce_local(p, a, p->sm_use, p->L.actor.size);
+    }
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
     return reduce_local(p, a, p->grid, p->L.actor.size);
 }
@@ -792,6 +797,11 @@ int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int
     // A2C takes the log-prob of the stored (normalised-space) actions and denormalises only inside its distance term (on_policy.py:106-116)
     a.mode = (p->a2c && !p->cfg.norm_closs && !p->plain_ppo) ? 1 : 0;
     PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo || p->a2c) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    if (p->critic_tc && ppo_critic_tc_supported(p->L.ob, p->L.ldo)) {      // same tile machinery as the critic fit (ppo_critic_tc.cu)
+        a.rows_per_cta = rows_per_cta(n, p->sm_use);
+        PCK(launch_ppo_actor_grad_tc(a, p->sm_use, p->stream)); spp_count_launch_();
+        return reduce_local(p, a, p->sm_use, p->L.actor.size);
+    }
     PCK(launch_ppo_actor_grad(a, p->grid, p->stream)); spp_count_launch_();
     return reduce_local(p, a, p->grid, p->L.actor.size);
 }

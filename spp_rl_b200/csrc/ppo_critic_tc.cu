@@ -25,6 +25,7 @@
 
 #include "ppo_kernels.cuh"
 #include "umma.cuh"
+#include "update_kernel.cuh"      // NORM_* slots
 
 namespace spp {
 
@@ -591,5 +592,409 @@ cudaError_t launch_ppo_critic_values_tc(const PpoArgs& a, int grid, cudaStream_t
     return cudaGetLastError();
 }
 
+
+
+// =====================================================================================================================================
+// The clipped-ratio actor step (PPO_AcM.update_actor_acm / PPO.update_actor / the A2C forms; ppo_actor_grad_kernel's contract: one
+// gathered minibatch in a.b, partial gradients per CTA) with the same tile machinery: fc2, dX(fc2) and dW(fc2) on tcgen05, W2 resident
+// as pre-split planes; fc1, the 17-wide head (fc3, Gaussian log-prob, ratio / clip, its backward) and dW(fc1) / dW(fc3) on FFMA from
+// shared memory.  Per tile, between the fc2 product and the dz2 images, bufA | bufB hold the head's scratch: the two column halves'
+// partial fc3 pre-activations, d3 and the log-scale terms per row, and the raw h2 tile for dW(fc3).
+namespace {
+constexpr int kActOffW3 = kOffVec + kVecFloats * 4;                 // W3 [20][64] (rows >= ob zero)
+constexpr int kActOffHv = kActOffW3 + kXsLd * 64 * 4;               // b3, lim, log_scale, 1 / var [4][20]
+constexpr int kActSmemBytes = kActOffHv + 4 * kXsLd * 4;
+static_assert(kActSmemBytes + 1024 <= 227 * 1024, "shared memory budget (actor): dynamic + the kernel's static 1 KB");
+constexpr int kExOff = 0;                                           // floats inside bufA | bufB: exch [2][128][20]
+constexpr int kD3Off = 2 * kTile * kXsLd;                           // d3s [128][20]
+constexpr int kH2Off = 3 * kTile * kXsLd;                           // h2s [128][68]
+static_assert((kH2Off + kTile * kDz1Ld) * 4 <= 65536, "head scratch aliases bufA | bufB");
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) ppo_actor_grad_tc_kernel(const __grid_constant__ PpoArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw;
+    const uint32_t s0 = smem_u32(smem);
+    if (s0 & 1023u) __trap();
+    float* xs_base = reinterpret_cast<float*>(smem + kOffXs);
+    float* w1t = reinterpret_cast<float*>(smem + kOffW1t);
+    float* vec = reinterpret_cast<float*>(smem + kOffVec);
+    float* b1s = vec; float* b2s = vec + 64; float* red = vec + 192 + 4 * kTile;
+    float* w3s = reinterpret_cast<float*>(smem + kActOffW3);
+    float* hv = reinterpret_cast<float*>(smem + kActOffHv);
+    float* b3v = hv; float* limv = hv + kXsLd; float* lsv = hv + 2 * kXsLd; float* ivar = hv + 3 * kXsLd;
+    float* scr = reinterpret_cast<float*>(smem + kOffBufA);          // head scratch / raw dz1 tile (bufA | bufB)
+    float* dz1s = scr; float* exch = scr + kExOff; float* d3s = scr + kD3Off; float* h2s = scr + kH2Off;
+    __shared__ uint64_t mbar3[3];
+    __shared__ uint32_t tmem_base_s;
+
+    float* part = a.part + (size_t)blockIdx.x * a.part_stride;
+    float* scal = a.scal + (size_t)blockIdx.x * PS_COUNT;
+    for (int i = threadIdx.x; i < a.L.actor.size; i += kThreads) part[i] = 0.f;
+    if (threadIdx.x < PS_COUNT) scal[threadIdx.x] = 0.f;
+    const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta;
+    int64_t nrows64 = a.b.n - r0;
+    if (nrows64 > a.rows_per_cta) nrows64 = a.rows_per_cta;
+    if (nrows64 <= 0) return;
+    const int nrows = (int)nrows64;
+    const LayerDesc& l0 = a.L.actor.L[0]; const LayerDesc& l1 = a.L.actor.L[1]; const LayerDesc& l2 = a.L.actor.L[2]; const LayerDesc& l3 = a.L.actor.L[3];
+    const int ob = a.L.ob, ldo = a.L.ldo;
+    const float* lim = a.norm + NORM_LIM * ldo;
+
+    if (warp_id() == 0) tmem_alloc<512>(&tmem_base_s);
+    if (threadIdx.x == 0) { mbar_init(mbar3, 1); mbar_init(mbar3 + 1, 1); mbar_init(mbar3 + 2, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    for (int e = threadIdx.x; e < kXsLd * 64; e += kThreads) {
+        const int i = e / 64, c = e % 64;
+        w1t[e] = (i < ob) ? a.actor[l0.off_w + c * l0.ld + i] : 0.f;
+        w3s[e] = (i < ob) ? a.actor[l2.off_w + i * l2.ld + c] : 0.f;      // row i = output unit of fc3
+    }
+    if (threadIdx.x < 64) { b1s[threadIdx.x] = a.actor[l0.off_b + threadIdx.x]; b2s[threadIdx.x] = a.actor[l1.off_b + threadIdx.x]; }
+    if (threadIdx.x < kXsLd) {
+        const int j = threadIdx.x;
+        const float lsj = j < ob ? a.actor[l3.off_w + j] : 0.f;
+        const float sd = expf(lsj);
+        b3v[j] = j < ob ? a.actor[l2.off_b + j] : 0.f; limv[j] = j < ob ? lim[j] : 0.f; lsv[j] = lsj; ivar[j] = __fmul_rn(sd, sd);      // ivar holds var (sd^2)
+    }
+    for (int e = threadIdx.x; e < 64 * 16; e += kThreads) {
+        const int o = e >> 4, i4 = e & 15;
+        const float4 w = *reinterpret_cast<const float4*>(a.actor + l1.off_w + o * l1.ld + 4 * i4);
+        float4 h, l;
+        split_tf32(w.x, h.x, l.x); split_tf32(w.y, h.y, l.y); split_tf32(w.z, h.z, l.z); split_tf32(w.w, h.w, l.w);
+        { const uint32_t base = s0 + kOffW2K + (i4 >> 3) * 16384, off = kmajor_offset(o, i4 & 7); sts128(base + off, h); sts128(base + 8192 + off, l); }
+        { const uint32_t base = s0 + kOffW2MN + (o >> 5) * 16384, off = mnmajor_offset(o & 31, i4); sts128(base + off, h); sts128(base + 8192 + off, l); }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const int q = warp_id() & 3, hcol = warp_id() >> 2, c0 = 32 * hcol;
+    const int r = 32 * q + lane_id();
+    const uint32_t my_t = tmem + ((uint32_t)(32 * q) << 16) + c0;
+    const uint32_t idesc_fwd = make_idesc_tf32(128, 64, 0, 0), idesc_dx = make_idesc_tf32(128, 64, 0, 1), idesc_dw = make_idesc_tf32(64, 64, 1, 1);
+    uint32_t ph_fc2 = 0, ph_dw = 0, ph_dx = 0;
+    uint64_t* const m_fc2 = mbar3; uint64_t* const m_dw = mbar3 + 1; uint64_t* const m_dx = mbar3 + 2;
+    const float invB = 1.0f / (float)a.b.n_mean;
+    const float kLogSqrt2Pi = 0.918938533204672741780329736406f;
+    const float clip_lo = 1.f - a.h.epsilon, clip_hi = 1.f + a.h.epsilon;
+
+    float gw2[32], cs_b2[32], gw1[kXsLd], gw3[5];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { gw2[j] = 0.f; cs_b2[j] = 0.f; }
+#pragma unroll
+    for (int m = 0; m < kXsLd; ++m) gw1[m] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) gw3[m] = 0.f;
+    float s_loss = 0.f, s_kl = 0.f, s_dist = 0.f, gb1 = 0.f, colacc = 0.f;      // colacc: threads 0..19 sum d3 (d b3), threads 32..51 the log-scale terms
+    const int o1 = threadIdx.x & 63, rq = threadIdx.x >> 6;
+
+    auto load_x_tile = [&](int t0, float* dst) {
+        const int trows = min(kTile, nrows - t0);
+        const float* X = a.b.x + (r0 + t0) * ldo;
+        for (int e = threadIdx.x; e < kTile * (kXsLd / 4); e += kThreads) {
+            const int rr = e / (kXsLd / 4), c4 = e % (kXsLd / 4);
+            const bool ok = rr < trows && 4 * c4 < ldo;
+            cp_async16(dst + rr * kXsLd + 4 * c4, ok ? X + (size_t)rr * ldo + 4 * c4 : a.b.x, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+    auto dw1_ffma = [&](const float* xs) {
+#pragma unroll 4
+        for (int rr = 32 * rq; rr < 32 * rq + 32; ++rr) {
+            const float d = dz1s[rr * kDz1Ld + o1];
+            gb1 = __fadd_rn(gb1, d);
+            const float4* xr = reinterpret_cast<const float4*>(xs + rr * kXsLd);
+#pragma unroll
+            for (int c = 0; c < kXsLd / 4; ++c) {
+                const float4 x4 = xr[c];
+                fma2(gw1[4 * c], gw1[4 * c + 1], d, x4.x, x4.y);
+                fma2(gw1[4 * c + 2], gw1[4 * c + 3], d, x4.z, x4.w);
+            }
+        }
+    };
+    load_x_tile(0, xs_base);
+    int tbuf = 0;
+    for (int t0 = 0; t0 < nrows; t0 += kTile, tbuf ^= 1) {
+        const int trows = min(kTile, nrows - t0);
+        float* xs = xs_base + tbuf * (kXsBytes / 4);
+        cp_async_wait<0>();
+        __syncthreads();
+        const bool valid = r < trows;
+        const int64_t grow = r0 + t0 + r;
+        float old_lp = 0.f, adv = 0.f;
+        if (valid && hcol == 0) { old_lp = __ldg(a.b.logp + grow); adv = __ldg(a.b.adv + grow); }
+        float h1[32];
+        {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            float xv[kXsLd];
+#pragma unroll
+            for (int c = 0; c < kXsLd / 4; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(xs + r * kXsLd + 4 * c);
+                xv[4 * c] = v.x; xv[4 * c + 1] = v.y; xv[4 * c + 2] = v.z; xv[4 * c + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < kXsLd; ++i) {
+                const float4* wr = reinterpret_cast<const float4*>(w1t + i * 64 + c0);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 w = wr[c];
+                    fma2(acc[4 * c], acc[4 * c + 1], xv[i], w.x, w.y);
+                    fma2(acc[4 * c + 2], acc[4 * c + 3], xv[i], w.z, w.w);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h1[j] = tanhf(__fadd_rn(acc[j], b1s[c0 + j]));
+        }
+        store_kmajor_row<32>(s0 + kOffBufK, r, c0, h1);
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<false, false>(tmem + 64 * c, s0 + kOffBufK + c * 32768, s0 + kOffBufK + c * 32768 + 16384,
+                                        s0 + kOffW2K + c * 16384, s0 + kOffW2K + c * 16384 + 8192, idesc_fwd);
+            commit(m_fc2);
+        }
+        if (t0 > 0) dw1_ffma(xs_base + (tbuf ^ 1) * (kXsBytes / 4));
+        mbar_wait(m_fc2, ph_fc2); ph_fc2 ^= 1;
+        fence_after_sync();
+        __syncthreads();      // every thread is past the previous tile's dW1 loop: bufA | bufB become the head's scratch, its x buffer is free
+        if (t0 + kTile < nrows) load_x_tile(t0 + kTile, xs_base + (tbuf ^ 1) * (kXsBytes / 4));
+        // ---- h2, the two halves' partial fc3 pre-activations
+        float h2[32];
+        tmem_row<false, 32>(my_t, h2);
+        tmem_row<true, 32>(my_t + 64, h2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h2[j] = tanhf(__fadd_rn(h2[j], b2s[c0 + j]));
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(h2s + r * kDz1Ld + c0 + 4 * c) = make_float4(h2[4 * c], h2[4 * c + 1], h2[4 * c + 2], h2[4 * c + 3]);
+        {
+            float pre[kXsLd];
+#pragma unroll
+            for (int j = 0; j < kXsLd; ++j) pre[j] = 0.f;
+            for (int j = 0; j < ob; ++j) {
+                const float4* wr = reinterpret_cast<const float4*>(w3s + j * 64 + c0);
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 w = wr[c];
+                    s = fmaf(h2[4 * c], w.x, s); s = fmaf(h2[4 * c + 1], w.y, s); s = fmaf(h2[4 * c + 2], w.z, s); s = fmaf(h2[4 * c + 3], w.w, s);
+                }
+                pre[j] = s;
+            }
+#pragma unroll
+            for (int c = 0; c < kXsLd / 4; ++c)
+                *reinterpret_cast<float4*>(exch + (hcol * kTile + r) * kXsLd + 4 * c) = make_float4(pre[4 * c], pre[4 * c + 1], pre[4 * c + 2], pre[4 * c + 3]);
+        }
+        __syncthreads();
+        // ---- head, one thread per row: mean, log-prob, ratio / clip (or the A2C form), d3 and the log-scale terms
+        if (hcol == 0) {
+            float lp = 0.f;
+            float tv[kXsLd], dd[kXsLd];
+            for (int j = 0; j < ob; ++j) {
+                const float pre = __fadd_rn(__fadd_rn(exch[r * kXsLd + j], exch[(kTile + r) * kXsLd + j]), b3v[j]);
+                const float t = tanhf(pre);
+                tv[j] = t;
+                const float mu = __fmul_rn(t, limv[j]);
+                const float av = valid ? a.b.act[grow * ldo + j] : mu;
+                const float d = __fsub_rn(av, mu);
+                dd[j] = d;
+                const float sd = expf(lsv[j]);
+                lp += __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, __fmul_rn(sd, sd))), logf(sd)), kLogSqrt2Pi);
+            }
+            float dlogp = 0.f;
+            if (valid) {
+                a.s.newlogp[grow] = lp;
+                const float ratio = expf(__fsub_rn(lp, old_lp));
+                const float clipped = fminf(fmaxf(ratio, clip_lo), clip_hi);
+                const float s1 = __fmul_rn(ratio, adv), s2 = __fmul_rn(clipped, adv);
+                s_loss += a.a2c ? -__fmul_rn(old_lp, adv) : -fminf(s1, s2);
+                s_kl += __fsub_rn(old_lp, lp);
+                const float g = -invB;
+                const float tie = (s1 == s2) ? 0.5f * g : 0.f;
+                const float g1 = (s1 < s2 ? g : 0.f) + tie, g2 = (s2 < s1 ? g : 0.f) + tie;
+                const float in_range = (ratio >= clip_lo && ratio <= clip_hi) ? 1.f : 0.f;
+                const float dratio = __fadd_rn(__fmul_rn(g1, adv), __fmul_rn(__fmul_rn(g2, adv), in_range));
+                dlogp = __fmul_rn(dratio, ratio);
+                if (a.a2c) dlogp = __fmul_rn(g, adv);
+            }
+            for (int j = 0; j < ob; ++j) {
+                const float var = ivar[j];
+                const float d = dd[j];
+                const float dmean = __fmul_rn(dlogp, __fdiv_rn(d, var));
+                d3s[r * kXsLd + j] = __fmul_rn(__fmul_rn(dmean, limv[j]), __fsub_rn(1.f, __fmul_rn(tv[j], tv[j])));
+                exch[r * kXsLd + j] = __fmul_rn(dlogp, __fsub_rn(__fdiv_rn(__fmul_rn(d, d), var), 1.f));      // d logp / d log_scale term
+                if (valid && a.h.custom_loss != 0.f) {
+                    float la = a.b.act[grow * ldo + j], ln = a.b.xn[grow * ldo + j];
+                    if (a.mode == 1) {
+                        const float* doff = a.norm + NORM_DOFF * ldo; const float* dsc = a.norm + NORM_DSCALE * ldo;
+                        la = __fadd_rn(doff[j], __fmul_rn(la, dsc[j])); ln = __fadd_rn(doff[j], __fmul_rn(ln, dsc[j]));
+                    }
+                    const float df = __fsub_rn(la, ln);
+                    s_dist = fmaf(df, df, s_dist);
+                }
+            }
+            for (int j = ob; j < kXsLd; ++j) { d3s[r * kXsLd + j] = 0.f; exch[r * kXsLd + j] = 0.f; }
+        }
+        __syncthreads();
+        // ---- dz2 = (d3 W3) (1 - h2^2); column sums of d3 / log-scale terms; dW fc3 on FFMA (out unit pairs: column o1, rows j = rq + 4 m)
+        float dz2[32];
+        {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dz2[j] = 0.f;
+            for (int j = 0; j < ob; ++j) {
+                const float d = d3s[r * kXsLd + j];
+                const float4* wr = reinterpret_cast<const float4*>(w3s + j * 64 + c0);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 w = wr[c];
+                    fma2(dz2[4 * c], dz2[4 * c + 1], d, w.x, w.y);
+                    fma2(dz2[4 * c + 2], dz2[4 * c + 3], d, w.z, w.w);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { dz2[j] = __fmul_rn(dz2[j], __fsub_rn(1.f, __fmul_rn(h2[j], h2[j]))); cs_b2[j] += dz2[j]; }
+        }
+        if (threadIdx.x < kXsLd) { for (int rr = 0; rr < kTile; ++rr) colacc += d3s[rr * kXsLd + threadIdx.x]; }
+        else if (threadIdx.x >= 32 && threadIdx.x < 32 + kXsLd) { for (int rr = 0; rr < kTile; ++rr) colacc += exch[rr * kXsLd + threadIdx.x - 32]; }
+        for (int rr = 0; rr < kTile; ++rr) {
+            const float h = h2s[rr * kDz1Ld + o1];
+            const float* dr = d3s + rr * kXsLd + rq;
+#pragma unroll
+            for (int m = 0; m < 5; ++m) gw3[m] = fmaf(dr[4 * m], h, gw3[m]);
+        }
+        __syncthreads();      // the head's scratch is read: bufA | bufB take the MN-major images
+        store_kmajor_row<32>(s0 + kOffBufK, r, c0, dz2);
+        if (q < 2) {
+            const uint32_t pa = s0 + kOffBufA + (r >> 5) * 16384, pb = s0 + kOffBufB + (r >> 5) * 16384;
+            store_mnmajor_row<32>(pa, pa + 8192, r & 31, c0, dz2);
+            store_mnmajor_row<32>(pb, pb + 8192, r & 31, c0, h1);
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<true, true>(tmem + 256 + 64 * c, s0 + kOffBufA + c * 16384, s0 + kOffBufA + c * 16384 + 8192,
+                                      s0 + kOffBufB + c * 16384, s0 + kOffBufB + c * 16384 + 8192, idesc_dw);
+            commit(m_dw);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<false, true>(tmem + 128 + 64 * c, s0 + kOffBufK + c * 32768, s0 + kOffBufK + c * 32768 + 16384,
+                                       s0 + kOffW2MN + c * 16384, s0 + kOffW2MN + c * 16384 + 8192, idesc_dx);
+            commit(m_dx);
+        }
+        mbar_wait(m_dw, ph_dw); ph_dw ^= 1;
+        fence_after_sync();
+        if (q >= 2) {
+            const int lr = r - 64;
+            const uint32_t pa = s0 + kOffBufA + (lr >> 5) * 16384, pb = s0 + kOffBufB + (lr >> 5) * 16384;
+            store_mnmajor_row<32>(pa, pa + 8192, lr & 31, c0, dz2);
+            store_mnmajor_row<32>(pb, pb + 8192, lr & 31, c0, h1);
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after_sync();
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                chunk_mma<true, true>(tmem + 384 + 64 * c, s0 + kOffBufA + c * 16384, s0 + kOffBufA + c * 16384 + 8192,
+                                      s0 + kOffBufB + c * 16384, s0 + kOffBufB + c * 16384 + 8192, idesc_dw);
+            commit(m_dw);
+        }
+        mbar_wait(m_dx, ph_dx); ph_dx ^= 1;
+        fence_after_sync();
+        float dz1[32];
+        tmem_row<false, 32>(my_t + 128, dz1);
+        tmem_row<true, 32>(my_t + 192, dz1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz1[j] = __fmul_rn(dz1[j], __fsub_rn(1.f, __fmul_rn(h1[j], h1[j])));
+        mbar_wait(m_dw, ph_dw); ph_dw ^= 1;
+        fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(dz1s + r * kDz1Ld + c0 + 4 * c) = make_float4(dz1[4 * c], dz1[4 * c + 1], dz1[4 * c + 2], dz1[4 * c + 3]);
+        {
+            float t[32];
+            tmem_row<false, 32>(my_t + 256, t);
+            tmem_row<true, 32>(my_t + 320, t);
+            tmem_row<true, 32>(my_t + 384, t);
+            tmem_row<true, 32>(my_t + 448, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gw2[j] = __fadd_rn(gw2[j], t[j]);
+        }
+        fence_before_sync();
+    }
+    __syncthreads();
+    dw1_ffma(xs_base + (tbuf ^ 1) * (kXsBytes / 4));
+
+    // ---- the CTA's partial gradient
+    if (lane_id() < 16) {
+        const int o = 16 * q + lane_id();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(part + l1.off_w + o * l1.ld + c0 + 4 * c) = make_float4(gw2[4 * c], gw2[4 * c + 1], gw2[4 * c + 2], gw2[4 * c + 3]);
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const int j = rq + 4 * m;
+        if (j < ob) part[l2.off_w + j * l2.ld + o1] = gw3[m];
+    }
+    if (threadIdx.x < ob) part[l2.off_b + threadIdx.x] = colacc;
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + ob) part[l3.off_w + threadIdx.x - 32] = colacc;
+    {
+        float* w1red = reinterpret_cast<float*>(smem + kOffBufA);
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < kXsLd; ++m) w1red[(rq * 64 + o1) * 21 + m] = gw1[m];
+        w1red[(rq * 64 + o1) * 21 + kXsLd] = gb1;
+        __syncthreads();
+        for (int e = threadIdx.x; e < 64 * 21; e += kThreads) {
+            const int o = e / 21, i = e % 21;
+            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(w1red[(0 * 64 + o) * 21 + i], w1red[(1 * 64 + o) * 21 + i]), w1red[(2 * 64 + o) * 21 + i]),
+                                        w1red[(3 * 64 + o) * 21 + i]);
+            if (i < ob) part[l0.off_w + o * l0.ld + i] = sum;
+            else if (i == kXsLd) part[l0.off_b + o] = sum;
+        }
+    }
+    float* colred = reinterpret_cast<float*>(smem + kOffBufK);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) colred[(hcol * kTile + r) * 33 + j] = cs_b2[j];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int hh = threadIdx.x >> 5, j = threadIdx.x & 31;
+        float s = 0.f;
+        for (int rr = 0; rr < kTile; ++rr) s += colred[(hh * kTile + rr) * 33 + j];
+        part[l1.off_b + threadIdx.x] = s;
+    }
+    const float t_loss = block_sum(s_loss, red);
+    __syncthreads();
+    const float t_kl = block_sum(s_kl, red);
+    __syncthreads();
+    const float t_dist = block_sum(s_dist, red);
+    if (threadIdx.x == 0) { scal[PS_LOSS] = t_loss; scal[PS_KL] = t_kl; scal[PS_DIST] = t_dist; }
+    fence_before_sync();
+    __syncthreads();
+    if (warp_id() == 0) tmem_dealloc<512>(tmem);
+}
+
+cudaError_t launch_ppo_actor_grad_tc(const PpoArgs& a, int grid, cudaStream_t s) {
+    if (!ppo_critic_tc_supported(a.L.ob, a.L.ldo)) return cudaErrorInvalidValue;
+    // no slack for the manual 1024-byte alignment here (230.6 KB + the static 1 KB is all an SM has): the kernel relies on the
+    // __align__(1024) of its dynamic shared memory and traps if the base is not aligned
+    cudaError_t e = cudaFuncSetAttribute(ppo_actor_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kActSmemBytes);
+    if (e != cudaSuccess) return e;
+    ppo_actor_grad_tc_kernel<<<grid, kThreads, kActSmemBytes, s>>>(a);
+    return cudaGetLastError();
+}
 
 }  // namespace spp

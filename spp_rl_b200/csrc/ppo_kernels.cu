@@ -345,9 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_act_kernel(const __grid_const
 __global__ void ppo_reduce_kernel(const float* __restrict__ part, int stride, int n_part, int n, float* __restrict__ out,
                                   const float* __restrict__ scal, float* __restrict__ gscal) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int p = 0; p < n_part; ++p) s += part[(size_t)p * stride + i];
-        out[i] = s;
+        out[i] = slot_sum(part, (size_t)stride, n_part, i);
     }
     if (blockIdx.x == 0 && threadIdx.x < PS_COUNT) {
         float s = 0.f;

@@ -39,8 +39,8 @@ __global__ void __launch_bounds__(256) ppo_reduce_p2p_kernel(P2pArgs a) {
         float s;
         if (a.n_part > 0) {      // fused reduction of the gradient kernel's per-CTA slots (fixed order: deterministic)
             s = 0.f;
-            if (i < a.n_elems) { for (int p = 0; p < a.n_part; ++p) s += a.part[(size_t)p * a.part_stride + i]; }
-            else if (i >= a.part_stride) { for (int p = 0; p < a.n_part; ++p) s += a.scal[(size_t)p * PS_COUNT + (i - a.part_stride)]; }
+            if (i < a.n_elems) s = slot_sum(a.part, (size_t)a.part_stride, a.n_part, i);
+            else if (i >= a.part_stride) s = slot_sum(a.scal, (size_t)PS_COUNT, a.n_part, i - a.part_stride);
         } else {
             s = a.gbuf[i];       // already reduced (or zeroed: a rank that owns no row of this minibatch)
         }
