@@ -539,7 +539,7 @@ int spp_ppo_rollout_synthetic(spp_ppo* p, spp_population* pop, int agent, int E,
     a.seed = seed; a.denorm_out = denormalize_actor_out ? 1 : 0; a.clamp = p->cfg.min_max_denormalize ? 0 : 1;
     {   // environments per CTA: as few as fill two CTAs per SM (the k-chains of a step are split over the spare threads)
         const int per = (E + 2 * p->sm_count - 1) / (2 * p->sm_count);
-        a.rows_per_cta = per <= 8 ? 8 : per <= 16 ? 16 : per <= 24 ? 24 : 32;
+        a.rows_per_cta = per <= 2 ? 2 : per <= 4 ? 4 : per <= 8 ? 8 : per <= 16 ? 16 : per <= 24 ? 24 : 32;
     }
     float* tmp[4] = {nullptr, nullptr, nullptr, nullptr};
     const float* src[4] = {noise_act, noise_env, u_done, noise_reset};

@@ -70,7 +70,68 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ in, int ldi
     }
 }
 
-__global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant__ PpoRolloutArgs a) {
+// The same contraction with its work-item mapping computed ONCE per launch (the step loop used to redo the integer divisions of the
+// mapping in every layer of every step: ~150 of the ~600 instructions a layer cost) and RG rows per work item instead of always 8 --
+// a CTA that owns two environments carries two accumulators, not six zero rows.  Valid when one pass of the CTA covers the layer.
+struct DenseMap { int n, r0, k_lo, k_hi, KS; bool lead, single; };
+template <int RG>
+__device__ __forceinline__ DenseMap dense_map(int K, int N, int R) {
+    DenseMap m;
+    const int items = ((R + RG - 1) / RG) * N;
+    int KS = 1;
+    while (KS < 8 && items * KS * 2 <= (int)blockDim.x && K / (KS * 2) >= 4) KS *= 2;
+    const int Kc = ((K / 4 + KS - 1) / KS) * 4;
+    m.single = items * KS <= (int)blockDim.x;
+    const int w = threadIdx.x;
+    const bool active = w < items * KS;
+    const int idx = active ? w / KS : 0, ks = w % KS;
+    m.n = idx % N; m.r0 = (idx / N) * RG; m.KS = KS;
+    m.k_lo = ks * Kc; m.k_hi = active ? min(K, m.k_lo + Kc) : 0;
+    m.lead = active && ks == 0;
+    return m;
+}
+template <int ACT, bool SCALE, bool SKIP, int RG>
+__device__ __forceinline__ void dense_mapped(const DenseMap& m, const float* __restrict__ in, int ldin, int K, const float* __restrict__ Wt, int ldt,
+                                             const float* __restrict__ bias, int N, float* __restrict__ out, int ldout, int R,
+                                             const float* __restrict__ scale = nullptr, float* __restrict__ out_pre = nullptr,
+                                             const float* __restrict__ skip = nullptr, int ldskip = 0, float t = 0.f) {
+    if (!m.single) { dense_rows<ACT, SCALE, SKIP>(in, ldin, K, Wt, ldt, bias, N, out, ldout, R, scale, out_pre, skip, ldskip, t); return; }
+    float acc[RG];
+#pragma unroll
+    for (int i = 0; i < RG; ++i) acc[i] = 0.f;
+    const float* wp = Wt + m.n;
+    const float* ip = in + (size_t)m.r0 * ldin;
+#pragma unroll 2
+    for (int k = m.k_lo; k < m.k_hi; k += 4) {
+        float wv[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) wv[kk] = __ldg(wp + (size_t)(k + kk) * ldt);
+#pragma unroll
+        for (int i = 0; i < RG; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(ip + (size_t)i * ldin + k);      // rows >= R hold zeros
+            acc[i] = fmaf(v.x, wv[0], acc[i]); acc[i] = fmaf(v.y, wv[1], acc[i]);
+            acc[i] = fmaf(v.z, wv[2], acc[i]); acc[i] = fmaf(v.w, wv[3], acc[i]);
+        }
+    }
+    for (int o = m.KS >> 1; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < RG; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (!m.lead) return;
+    const float b = __ldg(bias + m.n);
+    const float sc = SCALE ? __ldg(scale + m.n) : 1.f;
+#pragma unroll
+    for (int i = 0; i < RG; ++i) {
+        if (m.r0 + i >= R) break;
+        float x = acc[i] + b;
+        if (SKIP) x = __fadd_rn(x, __fmul_rn(t, skip[(size_t)(m.r0 + i) * ldskip + m.n]));
+        if (ACT == 2) x = tanhf(x);
+        if (out_pre) out_pre[(size_t)(m.r0 + i) * ldout + m.n] = x;
+        out[(size_t)(m.r0 + i) * ldout + m.n] = SCALE ? x * sc : x;
+    }
+}
+
+template <int RG>
+__device__ __forceinline__ void ppo_rollout_body(const PpoRolloutArgs& a) {
     extern __shared__ __align__(16) float sm[];
     const int ob = a.L.ob, ldo = a.L.ldo, ac = a.ac, lda = a.lda, ldm = 2 * ldo;
     const int e0 = blockIdx.x * a.rows_per_cta;
@@ -102,6 +163,10 @@ __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant_
     const float* ls = a.actor + l3.off_w;
     const float kLogSqrt2Pi = 0.918938533204672741780329736406f;
     const NetDesc& M = a.acm_desc;
+    // work-item mappings of the six (seven with BasicAcM's skip) dense layers of a step
+    const DenseMap ma1 = dense_map<RG>(ldo, kPpoHidden, R), ma2 = dense_map<RG>(kPpoHidden, kPpoHidden, R), ma3 = dense_map<RG>(kPpoHidden, ob, R);
+    const DenseMap mm1 = dense_map<RG>(ldm, a.hm1, R), mm2 = dense_map<RG>(a.ldm1, a.hm2, R), mm3 = dense_map<RG>(a.ldm2, ac, R);
+    const DenseMap mms = dense_map<RG>(ldm, a.hm2, R);
 
     for (int t = 0; t < a.T; ++t) {
         const size_t row0 = (size_t)t * a.E + e0;
@@ -117,11 +182,11 @@ __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant_
         }
         __syncthreads();
         // 2. actor
-        dense_rows<2, false, false>(xin, ldm, ldo, a.actor + l0.off_wt, l0.ld_t, a.actor + l0.off_b, kPpoHidden, h1, kPpoHidden, R);
+        dense_mapped<2, false, false, RG>(ma1, xin, ldm, ldo, a.actor + l0.off_wt, l0.ld_t, a.actor + l0.off_b, kPpoHidden, h1, kPpoHidden, R);
         __syncthreads();
-        dense_rows<2, false, false>(h1, kPpoHidden, kPpoHidden, a.actor + l1.off_wt, l1.ld_t, a.actor + l1.off_b, kPpoHidden, h2, kPpoHidden, R);
+        dense_mapped<2, false, false, RG>(ma2, h1, kPpoHidden, kPpoHidden, a.actor + l1.off_wt, l1.ld_t, a.actor + l1.off_b, kPpoHidden, h2, kPpoHidden, R);
         __syncthreads();
-        dense_rows<2, true, false>(h2, kPpoHidden, kPpoHidden, a.actor + l2.off_wt, l2.ld_t, a.actor + l2.off_b, ob, mean, ldo, R, lim);
+        dense_mapped<2, true, false, RG>(ma3, h2, kPpoHidden, kPpoHidden, a.actor + l2.off_wt, l2.ld_t, a.actor + l2.off_b, ob, mean, ldo, R, lim);
         __syncthreads();
         // 3. sample, denormalised target: one thread per (environment, column); the log-prob terms are left in `mean` (in place)
         //    and summed j ascending -- torch's sum(-1) order -- by the environment's thread in stage 5a
@@ -144,19 +209,19 @@ __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant_
         __syncthreads();
         // 4. ACM (AcM: tanh-tanh-tanh * action limit; BasicAcM: skip connection and learnable gains)
         if (a.acm_kind == ACM_MLP) {
-            dense_rows<2, false, false>(xin, ldm, ldm, a.acm + M.L[0].off_wt, M.L[0].ld_t, a.acm + M.L[0].off_b, a.hm1, m1, a.ldm1, R);
+            dense_mapped<2, false, false, RG>(mm1, xin, ldm, ldm, a.acm + M.L[0].off_wt, M.L[0].ld_t, a.acm + M.L[0].off_b, a.hm1, m1, a.ldm1, R);
             __syncthreads();
-            dense_rows<2, false, false>(m1, a.ldm1, a.ldm1, a.acm + M.L[1].off_wt, M.L[1].ld_t, a.acm + M.L[1].off_b, a.hm2, m2, a.ldm2, R);
+            dense_mapped<2, false, false, RG>(mm2, m1, a.ldm1, a.ldm1, a.acm + M.L[1].off_wt, M.L[1].ld_t, a.acm + M.L[1].off_b, a.hm2, m2, a.ldm2, R);
             __syncthreads();
-            dense_rows<2, true, false>(m2, a.ldm2, a.ldm2, a.acm + M.L[2].off_wt, M.L[2].ld_t, a.acm + M.L[2].off_b, ac, pa, lda, R, a.acm_lim);
+            dense_mapped<2, true, false, RG>(mm3, m2, a.ldm2, a.ldm2, a.acm + M.L[2].off_wt, M.L[2].ld_t, a.acm + M.L[2].off_b, ac, pa, lda, R, a.acm_lim);
         } else {
-            dense_rows<2, false, false>(xin, ldm, ldm, a.acm + M.L[0].off_wt, M.L[0].ld_t, a.acm + M.L[0].off_b, a.hm1, m1, a.ldm1, R);
-            dense_rows<0, false, false>(xin, ldm, ldm, a.acm + M.L[3].off_wt, M.L[3].ld_t, a.acm + M.L[3].off_b, a.hm2, ms, a.ldm2, R);
+            dense_mapped<2, false, false, RG>(mm1, xin, ldm, ldm, a.acm + M.L[0].off_wt, M.L[0].ld_t, a.acm + M.L[0].off_b, a.hm1, m1, a.ldm1, R);
+            dense_mapped<0, false, false, RG>(mms, xin, ldm, ldm, a.acm + M.L[3].off_wt, M.L[3].ld_t, a.acm + M.L[3].off_b, a.hm2, ms, a.ldm2, R);
             __syncthreads();
-            dense_rows<2, false, true>(m1, a.ldm1, a.ldm1, a.acm + M.L[1].off_wt, M.L[1].ld_t, a.acm + M.L[1].off_b, a.hm2, m2, a.ldm2, R, nullptr,
+            dense_mapped<2, false, true, RG>(mm2, m1, a.ldm1, a.ldm1, a.acm + M.L[1].off_wt, M.L[1].ld_t, a.acm + M.L[1].off_b, a.hm2, m2, a.ldm2, R, nullptr,
                                        nullptr, ms, a.ldm2, __ldg(a.acm + M.L[4].off_w));
             __syncthreads();
-            dense_rows<2, true, false>(m2, a.ldm2, a.ldm2, a.acm + M.L[2].off_wt, M.L[2].ld_t, a.acm + M.L[2].off_b, ac, pa, lda, R,
+            dense_mapped<2, true, false, RG>(mm3, m2, a.ldm2, a.ldm2, a.acm + M.L[2].off_wt, M.L[2].ld_t, a.acm + M.L[2].off_b, ac, pa, lda, R,
                                        a.acm + M.L[4].off_w + 4);
         }
         __syncthreads();
@@ -217,6 +282,12 @@ __global__ void __launch_bounds__(256) ppo_rollout_kernel(const __grid_constant_
     }
     for (int i = threadIdx.x; i < R * ob; i += blockDim.x) a.state[(size_t)(e0 + i / ob) * ldo + i % ob] = obs[(i / ob) * ldo + i % ob];
     for (int i = threadIdx.x; i < R; i += blockDim.x) a.ep_len[e0 + i] = eplen[i];
+}
+
+__global__ void __launch_bounds__(256, 2) ppo_rollout_kernel(const __grid_constant__ PpoRolloutArgs a) {
+    if (a.rows_per_cta <= 2) ppo_rollout_body<2>(a);
+    else if (a.rows_per_cta <= 4) ppo_rollout_body<4>(a);
+    else ppo_rollout_body<8>(a);
 }
 
 size_t ppo_rollout_smem_bytes(const PpoRolloutArgs& a) {
