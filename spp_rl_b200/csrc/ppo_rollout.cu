@@ -4,8 +4,8 @@
 //   log-prob; rltoolkit/basic_model.py:32-51) -> denormalise -> ACM(cat[x, target]) (quirk 18: the ACM sees the NORMALISED
 //   observation) -> env.step -> store (obs, next_obs, action, logp, reward, done, end) + the ACM action.
 // The reference steps ONE environment per Python iteration; here every CTA owns a slice of <= kRolloutRows environments and walks
-// all T steps of them without leaving the SM: activations live in shared memory, the 64-wide weights (25 KB actor + 18 KB ACM at
-// Walker2d shapes) stay L1-resident (read-only for the whole launch, __ldg), and the [T][E] store is written step-major -- exactly
+// all T steps of them without leaving the SM: activations live in shared memory, the layers' transposed weights (47 KB at Walker2d
+// shapes) are copied to shared memory once per launch (wider nets: through L1), and the [T][E] store is written step-major -- exactly
 // the layout the update kernels read (traj_stride = E).  MuJoCo is unavailable offline: the environment is the synthetic one of the
 // off-policy rollout (obs' = 0.98 obs + 0.1 tanh(a-mix) + 0.02 N(0,1); reward = obs'[0]; done with probability done_prob; time-limit
 // truncation at max_ep_len as in a2c.py:168-171; reset to 0.1 N(0,1)).  Noise comes from Philox, or from injected tensors (tests).
@@ -44,7 +44,7 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ in, int ldi
         for (int k = k_lo; k < k_hi; k += 4) {
             float wv[4];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) wv[kk] = __ldg(Wt + (size_t)(k + kk) * ldt + n);
+            for (int kk = 0; kk < 4; ++kk) wv[kk] = Wt[(size_t)(k + kk) * ldt + n];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 v = *reinterpret_cast<const float4*>(in + (size_t)(r0 + i) * ldin + k);      // rows >= R hold zeros
@@ -56,8 +56,8 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ in, int ldi
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
         if (!active || ks != 0) continue;
-        const float b = __ldg(bias + n);
-        const float sc = SCALE ? __ldg(scale + n) : 1.f;
+        const float b = bias[n];
+        const float sc = SCALE ? scale[n] : 1.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (r0 + i >= R) break;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void dense_mapped(const DenseMap& m, const float* __r
     for (int k = m.k_lo; k < m.k_hi; k += 4) {
         float wv[4];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) wv[kk] = __ldg(wp + (size_t)(k + kk) * ldt);
+        for (int kk = 0; kk < 4; ++kk) wv[kk] = wp[(size_t)(k + kk) * ldt];      // shared memory (staged weights) or global
 #pragma unroll
         for (int i = 0; i < RG; ++i) {
             const float4 v = *reinterpret_cast<const float4*>(ip + (size_t)i * ldin + k);      // rows >= R hold zeros
@@ -117,8 +117,8 @@ __device__ __forceinline__ void dense_mapped(const DenseMap& m, const float* __r
 #pragma unroll
         for (int i = 0; i < RG; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
     if (!m.lead) return;
-    const float b = __ldg(bias + m.n);
-    const float sc = SCALE ? __ldg(scale + m.n) : 1.f;
+    const float b = bias[m.n];
+    const float sc = SCALE ? scale[m.n] : 1.f;
 #pragma unroll
     for (int i = 0; i < RG; ++i) {
         if (m.r0 + i >= R) break;
@@ -152,6 +152,25 @@ __device__ __forceinline__ void ppo_rollout_body(const PpoRolloutArgs& a) {
     float* mixv = reinterpret_cast<float*>(flags + kRolloutRows);       // [32]
     const int total = kRolloutRows * (ldm + 2 * kPpoHidden + ldo + a.ldm1 + 2 * a.ldm2 + lda + ldo);
     for (int i = threadIdx.x; i < total; i += blockDim.x) sm[i] = 0.f;
+    // the transposed weights and biases of every layer of a step, staged ONCE in shared memory (47 KB at Walker2d shapes): through
+    // L1 they hit 83 % of the time (the step's stores stream through the same cache), and every miss is an L2 round trip inside the
+    // serial k-chain of a layer
+    float* wcur = mixv + kRolloutRows;
+    auto stage_layer = [&](const float* net, const LayerDesc& l, const float*& wt, const float*& b) {
+        if (!a.stage_weights) { wt = net + l.off_wt; b = net + l.off_b; return; }      // too large for shared memory: through L1
+        const int nw = l.ld * l.ld_t;
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) wcur[i] = net[l.off_wt + i];
+        wt = wcur; wcur += (nw + 3) & ~3;
+        for (int i = threadIdx.x; i < l.rows; i += blockDim.x) wcur[i] = net[l.off_b + i];
+        b = wcur; wcur += (l.rows + 3) & ~3;
+    };
+    const float *aW1, *aB1, *aW2, *aB2, *aW3, *aB3, *mW1, *mB1, *mW2, *mB2, *mW3, *mB3, *mWs = nullptr, *mBs = nullptr;
+    {
+        const LayerDesc& l0 = a.L.actor.L[0]; const LayerDesc& l1 = a.L.actor.L[1]; const LayerDesc& l2 = a.L.actor.L[2];
+        stage_layer(a.actor, l0, aW1, aB1); stage_layer(a.actor, l1, aW2, aB2); stage_layer(a.actor, l2, aW3, aB3);
+        stage_layer(a.acm, a.acm_desc.L[0], mW1, mB1); stage_layer(a.acm, a.acm_desc.L[1], mW2, mB2); stage_layer(a.acm, a.acm_desc.L[2], mW3, mB3);
+        if (a.acm_kind != ACM_MLP) stage_layer(a.acm, a.acm_desc.L[3], mWs, mBs);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < R * ob; i += blockDim.x) obs[(i / ob) * ldo + i % ob] = a.state[(size_t)(e0 + i / ob) * ldo + i % ob];
     for (int i = threadIdx.x; i < R; i += blockDim.x) eplen[i] = a.ep_len[e0 + i];
@@ -182,11 +201,11 @@ __device__ __forceinline__ void ppo_rollout_body(const PpoRolloutArgs& a) {
         }
         __syncthreads();
         // 2. actor
-        dense_mapped<2, false, false, RG>(ma1, xin, ldm, ldo, a.actor + l0.off_wt, l0.ld_t, a.actor + l0.off_b, kPpoHidden, h1, kPpoHidden, R);
+        dense_mapped<2, false, false, RG>(ma1, xin, ldm, ldo, aW1, l0.ld_t, aB1, kPpoHidden, h1, kPpoHidden, R);
         __syncthreads();
-        dense_mapped<2, false, false, RG>(ma2, h1, kPpoHidden, kPpoHidden, a.actor + l1.off_wt, l1.ld_t, a.actor + l1.off_b, kPpoHidden, h2, kPpoHidden, R);
+        dense_mapped<2, false, false, RG>(ma2, h1, kPpoHidden, kPpoHidden, aW2, l1.ld_t, aB2, kPpoHidden, h2, kPpoHidden, R);
         __syncthreads();
-        dense_mapped<2, true, false, RG>(ma3, h2, kPpoHidden, kPpoHidden, a.actor + l2.off_wt, l2.ld_t, a.actor + l2.off_b, ob, mean, ldo, R, lim);
+        dense_mapped<2, true, false, RG>(ma3, h2, kPpoHidden, kPpoHidden, aW3, l2.ld_t, aB3, ob, mean, ldo, R, lim);
         __syncthreads();
         // 3. sample, denormalised target: one thread per (environment, column); the log-prob terms are left in `mean` (in place)
         //    and summed j ascending -- torch's sum(-1) order -- by the environment's thread in stage 5a
@@ -209,19 +228,19 @@ __device__ __forceinline__ void ppo_rollout_body(const PpoRolloutArgs& a) {
         __syncthreads();
         // 4. ACM (AcM: tanh-tanh-tanh * action limit; BasicAcM: skip connection and learnable gains)
         if (a.acm_kind == ACM_MLP) {
-            dense_mapped<2, false, false, RG>(mm1, xin, ldm, ldm, a.acm + M.L[0].off_wt, M.L[0].ld_t, a.acm + M.L[0].off_b, a.hm1, m1, a.ldm1, R);
+            dense_mapped<2, false, false, RG>(mm1, xin, ldm, ldm, mW1, M.L[0].ld_t, mB1, a.hm1, m1, a.ldm1, R);
             __syncthreads();
-            dense_mapped<2, false, false, RG>(mm2, m1, a.ldm1, a.ldm1, a.acm + M.L[1].off_wt, M.L[1].ld_t, a.acm + M.L[1].off_b, a.hm2, m2, a.ldm2, R);
+            dense_mapped<2, false, false, RG>(mm2, m1, a.ldm1, a.ldm1, mW2, M.L[1].ld_t, mB2, a.hm2, m2, a.ldm2, R);
             __syncthreads();
-            dense_mapped<2, true, false, RG>(mm3, m2, a.ldm2, a.ldm2, a.acm + M.L[2].off_wt, M.L[2].ld_t, a.acm + M.L[2].off_b, ac, pa, lda, R, a.acm_lim);
+            dense_mapped<2, true, false, RG>(mm3, m2, a.ldm2, a.ldm2, mW3, M.L[2].ld_t, mB3, ac, pa, lda, R, a.acm_lim);
         } else {
-            dense_mapped<2, false, false, RG>(mm1, xin, ldm, ldm, a.acm + M.L[0].off_wt, M.L[0].ld_t, a.acm + M.L[0].off_b, a.hm1, m1, a.ldm1, R);
-            dense_mapped<0, false, false, RG>(mms, xin, ldm, ldm, a.acm + M.L[3].off_wt, M.L[3].ld_t, a.acm + M.L[3].off_b, a.hm2, ms, a.ldm2, R);
+            dense_mapped<2, false, false, RG>(mm1, xin, ldm, ldm, mW1, M.L[0].ld_t, mB1, a.hm1, m1, a.ldm1, R);
+            dense_mapped<0, false, false, RG>(mms, xin, ldm, ldm, mWs, M.L[3].ld_t, mBs, a.hm2, ms, a.ldm2, R);
             __syncthreads();
-            dense_mapped<2, false, true, RG>(mm2, m1, a.ldm1, a.ldm1, a.acm + M.L[1].off_wt, M.L[1].ld_t, a.acm + M.L[1].off_b, a.hm2, m2, a.ldm2, R, nullptr,
+            dense_mapped<2, false, true, RG>(mm2, m1, a.ldm1, a.ldm1, mW2, M.L[1].ld_t, mB2, a.hm2, m2, a.ldm2, R, nullptr,
                                        nullptr, ms, a.ldm2, __ldg(a.acm + M.L[4].off_w));
             __syncthreads();
-            dense_mapped<2, true, false, RG>(mm3, m2, a.ldm2, a.ldm2, a.acm + M.L[2].off_wt, M.L[2].ld_t, a.acm + M.L[2].off_b, ac, pa, lda, R,
+            dense_mapped<2, true, false, RG>(mm3, m2, a.ldm2, a.ldm2, mW3, M.L[2].ld_t, mB3, ac, pa, lda, R,
                                        a.acm + M.L[4].off_w + 4);
         }
         __syncthreads();
@@ -292,10 +311,19 @@ __global__ void __launch_bounds__(256, 2) ppo_rollout_kernel(const __grid_consta
 
 size_t ppo_rollout_smem_bytes(const PpoRolloutArgs& a) {
     const int ldo = a.L.ldo;
-    return (size_t)kRolloutRows * (2 * ldo + 2 * kPpoHidden + ldo + a.ldm1 + 2 * a.ldm2 + a.lda + ldo) * 4 + 3 * kRolloutRows * 4 + 16;
+    size_t w = 0;      // staged weights: W^T [ld x ld_t] + b [rows] of every layer, each padded to 4 floats
+    auto add = [&](const LayerDesc& l) { w += ((size_t)l.ld * l.ld_t + 3) / 4 * 4 + ((size_t)l.rows + 3) / 4 * 4; };
+    add(a.L.actor.L[0]); add(a.L.actor.L[1]); add(a.L.actor.L[2]);
+    add(a.acm_desc.L[0]); add(a.acm_desc.L[1]); add(a.acm_desc.L[2]);
+    if (a.acm_kind != ACM_MLP) add(a.acm_desc.L[3]);
+    const size_t act = (size_t)kRolloutRows * (2 * ldo + 2 * kPpoHidden + ldo + a.ldm1 + 2 * a.ldm2 + a.lda + ldo) * 4 + 3 * kRolloutRows * 4 + 16;
+    return a.stage_weights ? act + w * 4 : act;
 }
 
-cudaError_t launch_ppo_rollout(const PpoRolloutArgs& a, cudaStream_t s) {
+cudaError_t launch_ppo_rollout(const PpoRolloutArgs& a_in, cudaStream_t s) {
+    PpoRolloutArgs a = a_in;
+    a.stage_weights = 1;
+    if (ppo_rollout_smem_bytes(a) > 110 * 1024) a.stage_weights = 0;      // keep two CTAs per SM; wide observations (Ant) read the weights through L1
     const size_t smem = ppo_rollout_smem_bytes(a);
     cudaError_t e = cudaFuncSetAttribute(ppo_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

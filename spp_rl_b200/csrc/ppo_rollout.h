@@ -12,6 +12,7 @@ struct PpoRolloutArgs {
     const float* acm;           // parameter arena of NET_ACM
     NetDesc acm_desc;
     int acm_kind, ac, lda, hm1, hm2, ldm1, ldm2;
+    int stage_weights;          // set by the launcher: 1 = the layers' W^T and b are copied to shared memory once per launch (they fit)
     const float* acm_lim;       // [lda] environment action limit (AcM); BasicAcM uses its own t1
     // environments
     int E, T, max_ep_len;
