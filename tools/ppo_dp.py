@@ -121,7 +121,7 @@ def main():
         for net in ("actor", "critic"):
             sd1 = one.state_dict(net)
             for k, v in sd1.items():
-                e = relnorm(sd_dp[net][k], v) * (0.1 if v.size <= 16 else 1.0)
+                e = relnorm(sd_dp[net][k], v)
                 worst = max(worst, e)
                 dump["dp:%s.%s" % (net, k)] = sd_dp[net][k]
                 dump["one:%s.%s" % (net, k)] = v
@@ -131,7 +131,7 @@ def main():
         info = pol.comm_info()
         out = {"metric": "SPP-PPO iteration (critic fit + GAE + advantage normalisation + clipped-ratio actor epochs), data-parallel over environments",
                "n_gpus": world, "envs": E, "steps": T, "rows": N, "global_minibatch": args.batch, "epochs": res["epochs"],
-               "critic_steps": args.critic_targets * args.critic_steps, "allreduces": res["allreduces"], "nccl_version": info["nccl_version"],
+               "critic_steps": args.critic_targets * args.critic_steps, "allreduces": res["allreduces"], "nccl_version": info["nccl_version"], "p2p": info["p2p"], "p2p_steps": info["p2p_steps"],
                "ms_dp": float(ms.item()), "ms_phases_rank0": res["phases_ms"],
                "transitions_per_s_dp": N / (float(ms.item()) * 1e-3), "ms_single_gpu": s0.elapsed_time(s1), "ms_phases_single_gpu": res1["phases_ms"],
                "dp_vs_single_worst_relnorm": worst, "ranks_bit_identical": bool(same.item() == 1.0),
