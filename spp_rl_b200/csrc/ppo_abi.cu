@@ -403,20 +403,27 @@ int spp_ppo_comm_info(spp_ppo* p, int* world, int64_t* allreduces, int* nccl_ver
 // local reduction of the gradient kernel's per-CTA slots -- or, inside the library's own data-parallel loops with the peer-memory path
 // on, only a note of what to reduce: the all-reduce kernel does it on the way
 static int reduce_local(spp_ppo* p, const PpoArgs& a, int n_part, int n_elems) {
-    if (p->p2p_on && p->defer_reduce) { p->pend_parts = n_part; p->pend_elems = n_elems; return SPP_OK; }
+    if (p->defer_reduce && (p->p2p_on || !p->comm)) { p->pend_parts = n_part; p->pend_elems = n_elems; return SPP_OK; }
     PCK(launch_ppo_reduce(a, n_part, n_elems, p->stream)); spp_count_launch_();
     return SPP_OK;
 }
 
 // gradient vector and the 8 reduced scalars sit in one buffer: ONE collective per optimiser step covers both
-static int allreduce_grads(spp_ppo* p) {
+static int allreduce_grads(spp_ppo* p, const StepArgs* step = nullptr) {
     if (!p->comm) {
-        if (p->pend_parts) return spp_set_error_(SPP_ERR_STATE, "deferred reduce without a communicator");
+        if (p->pend_parts) {      // single GPU inside the library's loops: reduce (+ record + Adam when `step` is given) in one launch
+            PpoArgs a; fill(p, a, 1);
+            StepArgs t; memset(&t, 0, sizeof(t));
+            if (step) t = *step;
+            PCK(launch_ppo_reduce_step(a, p->pend_parts, p->pend_elems, t, p->stream)); spp_count_launch_();
+            p->pend_parts = 0; p->pend_elems = 0;
+        }
         return SPP_OK;
     }
     if (p->p2p_on) {      // fused reduce + all-reduce over NVLink peer memory (ppo_p2p.cu)
         P2pArgs x;
         memset(&x, 0, sizeof(x));
+        if (step) x.step = *step;
         x.part = p->part; x.part_stride = p->part_stride; x.n_part = p->pend_parts; x.n_elems = p->pend_elems; x.scal = p->scal;
         x.gbuf = p->gbuf; x.total = p->part_stride + PS_COUNT;
         for (int r = 0; r < p->world; ++r) { x.peer[r] = p->p2p_peer[r]; x.peer_flags[r] = p->p2p_peer_flags[r]; }
@@ -487,6 +494,27 @@ int spp_ppo_p2p_info(spp_ppo* p, int* on, int64_t* steps, int* err) {
         if (p->p2p_err) { PCK(cudaSetDevice(p->device)); PCK(cudaStreamSynchronize(p->stream)); PCK(cudaMemcpy(err, p->p2p_err, 4, cudaMemcpyDeviceToHost)); }
     }
     return SPP_OK;
+}
+
+// (all-reduce +) record + Adam of one optimiser step: ONE launch when the fused paths apply (peer-memory all-reduce, or a single GPU),
+// else the NCCL all-reduce followed by the record and Adam kernels
+static int record_step(spp_ppo* p, int slot, bool with_log_scale);
+static int finish_step(spp_ppo* p, int net, int slot, bool with_ls) {
+    if (p->defer_reduce && (p->p2p_on || !p->comm) && (p->pend_parts > 0 || p->p2p_on)) {
+        StepArgs t; memset(&t, 0, sizeof(t));
+        const int step = net == 0 ? ++p->step_actor : ++p->step_critic;
+        const double lr = net == 0 ? p->cfg.actor_lr : p->cfg.critic_lr;
+        const double bc1 = 1.0 - pow(0.9, (double)step), bc2 = 1.0 - pow(0.999, (double)step);
+        t.d = net == 0 ? p->L.actor : p->L.critic;
+        t.W = net == 0 ? p->actor : p->critic; t.Mo = net == 0 ? p->actor_m : p->critic_m; t.Vo = net == 0 ? p->actor_v : p->critic_v;
+        t.s = AdamScalars{(float)(lr / bc1), (float)sqrt(bc2)};
+        t.extra_ls_grad = net == 0 ? -(p->a2c ? 0.f : p->h.entropy_coef) : 0.f; t.ls_layer = net == 0 ? 3 : -1;
+        t.slog = p->slog + (size_t)slot * (PS_COUNT + p->L.ldo); t.ldo = p->L.ldo; t.with_ls = with_ls ? 1 : 0; t.enabled = 1;
+        return allreduce_grads(p, &t);
+    }
+    int rc = allreduce_grads(p); if (rc) return rc;
+    rc = record_step(p, slot, with_ls); if (rc) return rc;
+    return net == 0 ? spp_ppo_actor_apply(p) : spp_ppo_critic_apply(p);
 }
 
 __global__ void ppo_record_kernel(const float* __restrict__ gscal, const float* __restrict__ log_scale, int ldo, float* __restrict__ slot) {
@@ -652,9 +680,7 @@ int spp_ppo_update_critic(spp_ppo* p, int n_target_updates, int n_updates_per_ta
         int rc = spp_ppo_critic_targets(p); if (rc) return rc;
         for (int u = 0; u < n_updates_per_target; ++u, ++k) {
             rc = spp_ppo_critic_grad(p); if (rc) return rc;
-            rc = allreduce_grads(p); if (rc) return rc;
-            rc = record_step(p, k, false); if (rc) return rc;
-            rc = spp_ppo_critic_apply(p); if (rc) return rc;
+            rc = finish_step(p, 1, k, false); if (rc) return rc;
         }
     }
     const int w = PS_COUNT + p->L.ldo;
@@ -827,9 +853,7 @@ int spp_ppo_actor_epoch_device(spp_ppo* p, const int64_t* ids_dev, const int64_t
         const int64_t n = off[k + 1] - off[k];
         if (n < 0 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [0, max_batch_rows]");
         int rc = spp_ppo_actor_minibatch_grad_device(p, n > 0 ? ids_dev + off[k] : nullptr, n, n_global ? n_global[k] : 0); if (rc) return rc;
-        rc = allreduce_grads(p); if (rc) return rc;
-        rc = record_step(p, k, true); if (rc) return rc;
-        rc = spp_ppo_actor_apply(p); if (rc) return rc;
+        rc = finish_step(p, 0, k, true); if (rc) return rc;
     }
     const int w = PS_COUNT + p->L.ldo;
     PCK(read_log(p, log_host, (size_t)nb * w));

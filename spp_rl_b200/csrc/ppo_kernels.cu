@@ -354,6 +354,19 @@ __global__ void ppo_reduce_kernel(const float* __restrict__ part, int stride, in
     }
 }
 
+// reduce + record + Adam in one launch (single-GPU form of the library's loops; the data-parallel form is ppo_reduce_p2p_kernel)
+__global__ void __launch_bounds__(256) ppo_reduce_step_kernel(const float* __restrict__ part, int stride, int n_part, int n, float* __restrict__ out,
+                                                              const float* __restrict__ scal, StepArgs t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= stride + PS_COUNT) return;
+    float g = 0.f;
+    if (i < n) g = slot_sum(part, (size_t)stride, n_part, i);
+    else if (i >= stride) g = slot_sum(scal, (size_t)PS_COUNT, n_part, i - stride);
+    out[i] = g;
+    if (i >= stride) { if (t.slog) t.slog[i - stride] = g; }
+    else apply_step_element(t, i, g);
+}
+
 // Adam over every tensor of a net from the reduced gradient (natural layout); refreshes the transposed copies.
 __global__ void ppo_adam_kernel(NetDesc d, float* __restrict__ W, float* __restrict__ Mo, float* __restrict__ Vo,
                                 const float* __restrict__ G, AdamScalars s, float extra_ls_grad, int ls_layer) {
@@ -487,6 +500,10 @@ cudaError_t launch_ppo_act(const PpoArgs& a, int grid, cudaStream_t s) {
 }
 cudaError_t launch_ppo_reduce(const PpoArgs& a, int n_part, int n_elems, cudaStream_t s) {
     ppo_reduce_kernel<<<(n_elems + 255) / 256, 256, 0, s>>>(a.part, a.part_stride, n_part, n_elems, a.gbuf, a.scal, a.gscal);
+    return cudaGetLastError();
+}
+cudaError_t launch_ppo_reduce_step(const PpoArgs& a, int n_part, int n_elems, const StepArgs& t, cudaStream_t s) {
+    ppo_reduce_step_kernel<<<(a.part_stride + PS_COUNT + 255) / 256, 256, 0, s>>>(a.part, a.part_stride, n_part, n_elems, a.gbuf, a.scal, t);
     return cudaGetLastError();
 }
 cudaError_t launch_ppo_adam(const PpoArgs& a, int which_net, int step, double lr, cudaStream_t s) {

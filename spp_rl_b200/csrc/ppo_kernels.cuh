@@ -113,6 +113,41 @@ __device__ __forceinline__ float slot_sum(const float* __restrict__ part, size_t
 // scalar slots
 enum { PS_LOSS = 0, PS_ENTROPY = 1, PS_DIST = 2, PS_KL = 3, PS_COUNT = 8 };
 
+// One optimiser step applied ELEMENT-WISE right where an element's reduced gradient becomes known (Adam is element-wise): the reduce /
+// all-reduce kernels of the library's own loops call this instead of leaving the gradient for separate record + Adam launches.
+// i = float offset inside the net's arena (NetDesc offsets); also writes the step's record slot (8 reduced scalars, then log_scale as
+// it was BEFORE the step -- what ppo_record_kernel wrote).
+struct StepArgs {
+    NetDesc d; float* W; float* Mo; float* Vo; AdamScalars s; float extra_ls_grad; int ls_layer;
+    float* slog; int ldo; int with_ls; int enabled;
+};
+__device__ __forceinline__ void apply_step_element(const StepArgs& t, int i, float g) {
+    if (!t.with_ls && t.slog && i < t.ldo) t.slog[PS_COUNT + i] = 0.f;
+    for (int li = 0; li < t.d.n_layers; ++li) {
+        const LayerDesc& l = t.d.L[li];
+        const int nw = l.rows * l.ld;
+        if (i >= l.off_w && i < l.off_w + nw) {
+            const int rel = i - l.off_w, row = rel / l.ld, col = rel % l.ld;
+            if (li == t.ls_layer && t.with_ls && t.slog && col < t.ldo) t.slog[PS_COUNT + col] = t.W[i];      // log_scale before the step
+            if (col >= l.cols) return;                                    // pad columns stay zero
+            if (li == t.ls_layer) g += t.extra_ls_grad;                   // - entropy_coef * d entropy / d log_scale (= 1 per dim)
+            float m = t.Mo[i], v = t.Vo[i];
+            const float wn = adam_element(t.W[i], g, m, v, t.s);
+            t.W[i] = wn; t.Mo[i] = m; t.Vo[i] = v;
+            if (l.off_wt >= 0) t.W[l.off_wt + (size_t)col * l.ld_t + row] = wn;
+            return;
+        }
+        if (i >= l.off_b && i < l.off_b + l.rows) {
+            if (l.off_wt < 0 && li == t.ls_layer) return;                 // the log_scale pseudo layer has no bias
+            float m = t.Mo[i], v = t.Vo[i];
+            const float wn = adam_element(t.W[i], g, m, v, t.s);
+            t.W[i] = wn; t.Mo[i] = m; t.Vo[i] = v;
+            return;
+        }
+    }
+}
+
+
 cudaError_t launch_ppo_critic_values(const PpoArgs& a, int grid, cudaStream_t s);      // v, nv, q
 cudaError_t launch_ppo_critic_grad(const PpoArgs& a, int grid, cudaStream_t s);        // partial grads of 0.5 mean((q - V)^2)
 cudaError_t launch_ppo_critic_grad_tc(const PpoArgs& a, int grid, cudaStream_t s);     // the same on tcgen05 (ppo_critic_tc.cu); grid <= n_part slots
@@ -122,6 +157,7 @@ bool ppo_critic_tc_supported(int ob, int ldo);
 cudaError_t launch_ppo_actor_grad(const PpoArgs& a, int grid, cudaStream_t s);         // partial grads of the clipped loss
 cudaError_t launch_ppo_act(const PpoArgs& a, int grid, cudaStream_t s);                // on-policy rollout step
 cudaError_t launch_ppo_reduce(const PpoArgs& a, int n_part, int n_elems, cudaStream_t s);
+cudaError_t launch_ppo_reduce_step(const PpoArgs& a, int n_part, int n_elems, const StepArgs& t, cudaStream_t s);      // reduce + record + Adam, one launch
 cudaError_t launch_ppo_adam(const PpoArgs& a, int which_net, int step, double lr, cudaStream_t s);
 cudaError_t launch_ppo_gae(const PpoArgs& a, cudaStream_t s);
 cudaError_t launch_ppo_adv_stats(const PpoArgs& a, double* d_stats, int grid, cudaStream_t s);     // n, sum, sum of squares (fp64)

@@ -72,6 +72,10 @@ __global__ void __launch_bounds__(256) ppo_reduce_p2p_kernel(P2pArgs a) {
         float s = 0.f;
         for (int r = 0; r < a.world; ++r) s += ld_relaxed_sys(a.peer[r] + (size_t)slot * a.total + i);      // rank order: identical on every rank
         a.gbuf[i] = s;
+        if (a.step.enabled) {      // the optimiser step of this element, and the step's record slot
+            if (i >= a.part_stride) { if (a.step.slog) a.step.slog[i - a.part_stride] = s; }
+            else apply_step_element(a.step, i, s);
+        }
     }
 }
 

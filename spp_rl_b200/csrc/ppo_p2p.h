@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ppo_kernels.cuh"
+
 namespace spp {
 
 constexpr int kP2pMaxRanks = 8;
@@ -16,6 +18,7 @@ struct P2pArgs {
     uint32_t epoch; int rank, world;
     unsigned* ticket; unsigned ticket_target;                         // last-CTA detection (monotonic counter)
     int* err;                                                         // set when a peer's flag never arrived
+    StepArgs step;                                                    // step.enabled: record + Adam ride behind the exchange (element-wise)
 };
 
 cudaError_t launch_ppo_reduce_p2p(const P2pArgs& a, cudaStream_t s);
