@@ -816,13 +816,13 @@ int spp_ppo_actor_minibatch_grad_device(spp_ppo* p, const int64_t* perm_dev, int
     if (n < 0 || n > p->cap_batch) return spp_set_error_(SPP_ERR_ARG, "minibatch outside [0, max_batch_rows]");
     PCK(cudaSetDevice(p->device));
     if (n == 0) return empty_minibatch(p, n_global);
-    PCK(cudaMemcpyAsync(p->dperm, perm_dev, (size_t)n * 8, cudaMemcpyDeviceToDevice, p->stream));
     p->b.n = n;
     p->b.n_mean = n_global > 0 ? n_global : n;
     PpoArgs a; fill(p, a, n);
     // A2C takes the log-prob of the stored (normalised-space) actions and denormalises only inside its distance term (on_policy.py:106-116)
     a.mode = (p->a2c && !p->cfg.norm_closs && !p->plain_ppo) ? 1 : 0;
-    PCK(launch_ppo_gather(a, p->dperm, (p->cfg.norm_closs || p->plain_ppo || p->a2c) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
+    // the gather reads the caller's device ids in place (they were produced on this stream): no staging copy per minibatch
+    PCK(launch_ppo_gather(a, perm_dev, (p->cfg.norm_closs || p->plain_ppo || p->a2c) ? 0 : 1, p->grid * 4, p->stream)); spp_count_launch_();
     if (p->critic_tc && ppo_critic_tc_supported(p->L.ob, p->L.ldo)) {      // same tile machinery as the critic fit (ppo_critic_tc.cu)
         a.rows_per_cta = rows_per_cta(n, p->sm_use);
         PCK(launch_ppo_actor_grad_tc(a, p->sm_use, p->stream)); spp_count_launch_();

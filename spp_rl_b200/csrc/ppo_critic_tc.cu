@@ -98,6 +98,22 @@ __device__ __forceinline__ void store_mnmajor_row(uint32_t hi_plane, uint32_t lo
     }
 }
 
+// the same values into BOTH images with one hi / lo split per element (dz2 of the first tile half goes to the K-major image for dX and
+// to the MN-major image for dW in the same phase)
+template <int CW>
+__device__ __forceinline__ void store_both_rows(uint32_t kbuf, int r, uint32_t mn_hi, uint32_t mn_lo, int k, int c0, const float (&v)[CW]) {
+    const uint32_t k_hi = kbuf + (c0 >> 5) * 32768, k_lo = k_hi + 16384;
+    const int cbk = (c0 & 31) >> 2, cbm = 8 * (c0 >> 5) + ((c0 & 31) >> 2);
+#pragma unroll
+    for (int c = 0; c < CW / 4; ++c) {
+        float4 h, l;
+        split_tf32(v[4 * c], h.x, l.x); split_tf32(v[4 * c + 1], h.y, l.y); split_tf32(v[4 * c + 2], h.z, l.z); split_tf32(v[4 * c + 3], h.w, l.w);
+        const uint32_t ok = kmajor_offset(r, cbk + c), om = mnmajor_offset(k, cbm + c);
+        sts128(k_hi + ok, h); sts128(k_lo + ok, l);
+        sts128(mn_hi + om, h); sts128(mn_lo + om, l);
+    }
+}
+
 // (d0, d1) += a * (b0, b1): one packed FFMA2 (sm_100 fma.rn.f32x2; each half is an IEEE fma, so results equal two scalar fmaf)
 __device__ __forceinline__ void fma2(float& d0, float& d1, float a, float b0, float b1) {
     asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
@@ -325,11 +341,12 @@ __global__ void __launch_bounds__(128 * NG, 1) ppo_critic_grad_tc_kernel(const _
             }
         }
         // dz2 -> K-major (over h1's image: the fc2 products have retired); first half of the tile -> MN-major images of dz2 and h1
-        store_kmajor_row<CW>(s0 + kOffBufK, r, c0, dz2);
         if (q < 2) {
             const uint32_t pa = s0 + kOffBufA + (r >> 5) * 16384, pb = s0 + kOffBufB + (r >> 5) * 16384;
-            store_mnmajor_row<CW>(pa, pa + 8192, r & 31, c0, dz2);
+            store_both_rows<CW>(s0 + kOffBufK, r, pa, pa + 8192, r & 31, c0, dz2);
             store_mnmajor_row<CW>(pb, pb + 8192, r & 31, c0, h1);
+        } else {
+            store_kmajor_row<CW>(s0 + kOffBufK, r, c0, dz2);
         }
         fence_proxy_async();
         fence_before_sync();
@@ -869,11 +886,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_actor_grad_tc_kernel(const __
             for (int m = 0; m < 5; ++m) gw3[m] = fmaf(dr[4 * m], h, gw3[m]);
         }
         __syncthreads();      // the head's scratch is read: bufA | bufB take the MN-major images
-        store_kmajor_row<32>(s0 + kOffBufK, r, c0, dz2);
         if (q < 2) {
             const uint32_t pa = s0 + kOffBufA + (r >> 5) * 16384, pb = s0 + kOffBufB + (r >> 5) * 16384;
-            store_mnmajor_row<32>(pa, pa + 8192, r & 31, c0, dz2);
+            store_both_rows<32>(s0 + kOffBufK, r, pa, pa + 8192, r & 31, c0, dz2);
             store_mnmajor_row<32>(pb, pb + 8192, r & 31, c0, h1);
+        } else {
+            store_kmajor_row<32>(s0 + kOffBufK, r, c0, dz2);
         }
         fence_proxy_async();
         fence_before_sync();
