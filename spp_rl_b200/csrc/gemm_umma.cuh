@@ -33,6 +33,10 @@ namespace spp {
 #ifndef SPP_UMMA_BK
 #define SPP_UMMA_BK 32      // k-chunk: 32 tf32 (128-byte rows, two 96 KB slots, copies one chunk ahead) or 16 (64-byte rows, four 48 KB slots, three ahead: measured slower, profiles/r02_update_bk16_experiment.md)
 #endif
+#ifndef SPP_UMMA_DRAIN_EVERY
+#define SPP_UMMA_DRAIN_EVERY 1      // k-chunks one TMEM accumulator collects before it is drained (1: the accurate default; 2: measured, see profiles/)
+#endif
+constexpr int kDrainEvery = SPP_UMMA_DRAIN_EVERY;
 constexpr int kBK = SPP_UMMA_BK;
 static_assert(kBK == 16 || kBK == 32, "k-chunk of the tcgen05 pipeline");
 constexpr int kKSteps = kBK / 8;                           // MMAs of k = 8 per pass and chunk
@@ -271,7 +275,8 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
         __syncthreads();
         if (threadIdx.x == 0) {
             fence_after_sync();
-            const uint32_t d = tmem + (fast ? 0 : (c & 1) * N);
+            const uint32_t d = tmem + (fast ? 0 : ((c / kDrainEvery) & 1) * N);
+            const bool fresh = (c % kDrainEvery) == 0;      // first chunk of its accumulator group
             const int nks = (dbg & 1) ? 0 : min(kKSteps, (K - kBK * c + 7) / 8);
             if (fast) {     // reduced-precision variant: the raw fp32 words are the tf32 operands, the whole K accumulates in TMEM
                 for (int ks = 0; ks < nks; ++ks) {
@@ -285,7 +290,7 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
                 const uint64_t dal = A_KM ? km_desc(al, ks) : mn_desc(al, ks);
                 const uint64_t dbh = B_KM ? km_desc(bh, ks) : mn_desc(bh, ks);
                 const uint64_t dbl = B_KM ? km_desc(bl, ks) : mn_desc(bl, ks);
-                mma_tf32(d, dal, dbh, idesc, ks ? 1u : 0u);
+                mma_tf32(d, dal, dbh, idesc, (ks || !fresh) ? 1u : 0u);
                 mma_tf32(d, dah, dbl, idesc, 1u);
             }
             for (int ks = 0; ks < nks; ++ks) {
@@ -308,17 +313,17 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
             lb.issue(kBK * (c + kUmmaAhead), K, nh + 2 * kUmmaAPlane);
         }
         cp_async_commit();
-        if (c >= 1 && !fast) {       // drain chunk c - 1 while the tensor core works on chunk c
-            if (c == 1) umma_drain<true>(my_tmem + ((c - 1) & 1) * N, sum);
-            else umma_drain<false>(my_tmem + ((c - 1) & 1) * N, sum);
+        if (c >= 1 && !fast && (c % kDrainEvery) == 0) {       // the group that ended with chunk c - 1 is complete: drain it while the tensor core works on chunk c
+            if (c == kDrainEvery) umma_drain<true>(my_tmem + (((c - 1) / kDrainEvery) & 1) * N, sum);
+            else umma_drain<false>(my_tmem + (((c - 1) / kDrainEvery) & 1) * N, sum);
         }
     }
     {   // last chunk
-        const int ps = (nchunks - 1) % kUmmaSlots, acc = (nchunks - 1) & 1;
+        const int ps = (nchunks - 1) % kUmmaSlots, acc = ((nchunks - 1) / kDrainEvery) & 1;
         mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
         phase_bits ^= (1u << ps);
         fence_after_sync();
-        if (nchunks == 1 || fast) umma_drain<true>(my_tmem + (fast ? 0 : acc * N), sum);
+        if (nchunks <= kDrainEvery || fast) umma_drain<true>(my_tmem + (fast ? 0 : acc * N), sum);
         else umma_drain<false>(my_tmem + acc * N, sum);
         fence_before_sync();
     }
