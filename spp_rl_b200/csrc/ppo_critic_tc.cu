@@ -619,8 +619,8 @@ cudaError_t launch_ppo_critic_values_tc(const PpoArgs& a, int grid, cudaStream_t
 // partial fc3 pre-activations, d3 and the log-scale terms per row, and the raw h2 tile for dW(fc3).
 namespace {
 constexpr int kActOffW3 = kOffVec + kVecFloats * 4;                 // W3 [20][64] (rows >= ob zero)
-constexpr int kActOffHv = kActOffW3 + kXsLd * 64 * 4;               // b3, lim, log_scale, 1 / var [4][20]
-constexpr int kActSmemBytes = kActOffHv + 4 * kXsLd * 4;
+constexpr int kActOffHv = kActOffW3 + kXsLd * 64 * 4;               // b3, lim, var, 2 var, log sd [5][20]
+constexpr int kActSmemBytes = kActOffHv + 5 * kXsLd * 4;
 static_assert(kActSmemBytes + 1024 <= 227 * 1024, "shared memory budget (actor): dynamic + the kernel's static 1 KB");
 constexpr int kExOff = 0;                                           // floats inside bufA | bufB: exch [2][128][20]
 constexpr int kD3Off = 2 * kTile * kXsLd;                           // d3s [128][20]
@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_actor_grad_tc_kernel(const __
     float* b1s = vec; float* b2s = vec + 64; float* red = vec + 192 + 4 * kTile;
     float* w3s = reinterpret_cast<float*>(smem + kActOffW3);
     float* hv = reinterpret_cast<float*>(smem + kActOffHv);
-    float* b3v = hv; float* limv = hv + kXsLd; float* lsv = hv + 2 * kXsLd; float* ivar = hv + 3 * kXsLd;
+    float* b3v = hv; float* limv = hv + kXsLd; float* varv = hv + 2 * kXsLd; float* var2v = hv + 3 * kXsLd; float* logsdv = hv + 4 * kXsLd;
     float* scr = reinterpret_cast<float*>(smem + kOffBufA);          // head scratch / raw dz1 tile (bufA | bufB)
     float* dz1s = scr; float* exch = scr + kExOff; float* d3s = scr + kD3Off; float* h2s = scr + kH2Off;
     __shared__ uint64_t mbar3[3];
@@ -669,8 +669,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_actor_grad_tc_kernel(const __
     if (threadIdx.x < kXsLd) {
         const int j = threadIdx.x;
         const float lsj = j < ob ? a.actor[l3.off_w + j] : 0.f;
-        const float sd = expf(lsj);
-        b3v[j] = j < ob ? a.actor[l2.off_b + j] : 0.f; limv[j] = j < ob ? lim[j] : 0.f; lsv[j] = lsj; ivar[j] = __fmul_rn(sd, sd);      // ivar holds var (sd^2)
+        const float sd = expf(lsj);      // the per-column terms of the Gaussian log-density, computed once (same operations as per row)
+        b3v[j] = j < ob ? a.actor[l2.off_b + j] : 0.f; limv[j] = j < ob ? lim[j] : 0.f;
+        varv[j] = __fmul_rn(sd, sd); var2v[j] = __fmul_rn(2.f, __fmul_rn(sd, sd)); logsdv[j] = logf(sd);
     }
     for (int e = threadIdx.x; e < 64 * 16; e += kThreads) {
         const int o = e >> 4, i4 = e & 15;
@@ -812,17 +813,23 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_actor_grad_tc_kernel(const __
         // ---- head, one thread per row: mean, log-prob, ratio / clip (or the A2C form), d3 and the log-scale terms
         if (hcol == 0) {
             float lp = 0.f;
-            float tv[kXsLd], dd[kXsLd];
-            for (int j = 0; j < ob; ++j) {
+            float tv[kXsLd], dd[kXsLd], av[kXsLd];
+#pragma unroll
+            for (int c = 0; c < kXsLd / 4; ++c) {      // the row's stored action with 16-byte loads
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && 4 * c < ldo) v = __ldg(reinterpret_cast<const float4*>(a.b.act + grow * ldo + 4 * c));
+                av[4 * c] = v.x; av[4 * c + 1] = v.y; av[4 * c + 2] = v.z; av[4 * c + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < kXsLd; ++j) {
+                if (j >= ob) { tv[j] = 0.f; dd[j] = 0.f; continue; }
                 const float pre = __fadd_rn(__fadd_rn(exch[r * kXsLd + j], exch[(kTile + r) * kXsLd + j]), b3v[j]);
                 const float t = tanhf(pre);
                 tv[j] = t;
                 const float mu = __fmul_rn(t, limv[j]);
-                const float av = valid ? a.b.act[grow * ldo + j] : mu;
-                const float d = __fsub_rn(av, mu);
+                const float d = valid ? __fsub_rn(av[j], mu) : 0.f;
                 dd[j] = d;
-                const float sd = expf(lsv[j]);
-                lp += __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(2.f, __fmul_rn(sd, sd))), logf(sd)), kLogSqrt2Pi);
+                lp += __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), var2v[j]), logsdv[j]), kLogSqrt2Pi);
             }
             float dlogp = 0.f;
             if (valid) {
@@ -840,14 +847,24 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_actor_grad_tc_kernel(const __
                 dlogp = __fmul_rn(dratio, ratio);
                 if (a.a2c) dlogp = __fmul_rn(g, adv);
             }
-            for (int j = 0; j < ob; ++j) {
-                const float var = ivar[j];
+            float xnv[kXsLd];
+            const bool want_dist = valid && a.h.custom_loss != 0.f;
+#pragma unroll
+            for (int c = 0; c < kXsLd / 4; ++c) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (want_dist && 4 * c < ldo) v = __ldg(reinterpret_cast<const float4*>(a.b.xn + grow * ldo + 4 * c));
+                xnv[4 * c] = v.x; xnv[4 * c + 1] = v.y; xnv[4 * c + 2] = v.z; xnv[4 * c + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < kXsLd; ++j) {
+                if (j >= ob) continue;
+                const float var = varv[j];
                 const float d = dd[j];
                 const float dmean = __fmul_rn(dlogp, __fdiv_rn(d, var));
                 d3s[r * kXsLd + j] = __fmul_rn(__fmul_rn(dmean, limv[j]), __fsub_rn(1.f, __fmul_rn(tv[j], tv[j])));
                 exch[r * kXsLd + j] = __fmul_rn(dlogp, __fsub_rn(__fdiv_rn(__fmul_rn(d, d), var), 1.f));      // d logp / d log_scale term
-                if (valid && a.h.custom_loss != 0.f) {
-                    float la = a.b.act[grow * ldo + j], ln = a.b.xn[grow * ldo + j];
+                if (want_dist) {
+                    float la = av[j], ln = xnv[j];
                     if (a.mode == 1) {
                         const float* doff = a.norm + NORM_DOFF * ldo; const float* dsc = a.norm + NORM_DSCALE * ldo;
                         la = __fadd_rn(doff[j], __fmul_rn(la, dsc[j])); ln = __fadd_rn(doff[j], __fmul_rn(ln, dsc[j]));
