@@ -11,7 +11,7 @@ import torch
 
 from spp_rl_b200 import Population
 
-P, OB, AC, S = 148, 11, 3, 1_000_000
+P, OB, AC, S = 148, int(os.environ.get("OB", 11)), int(os.environ.get("AC", 3)), int(os.environ.get("S", 1_000_000))
 pop = Population(algo="sac", ob_dim=OB, ac_dim=AC, population=P, buffer_size=S, update_batch_size=16, store_actions=False)
 pop.set_norm_stats(-np.ones(OB, np.float32), np.ones(OB, np.float32))
 pop.ring_fill_synthetic(seed=3, n=S * 999 // 1000, episode_len=1000)
