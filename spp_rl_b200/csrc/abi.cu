@@ -84,6 +84,7 @@ struct spp_population {
     // staging
     DevBuf d_obs, d_nobs, d_act, d_rew, d_done, d_aacm, d_eps, d_idx, d_losses, d_tmp;
     DevBuf d_roll_scratch, d_env, d_cur;     // rollout: scratch for E rows per agent, synthetic env state, cursors
+    DevBuf d_progress;                       // update bursts of populations larger than the grid: per-agent step counters (update_burst_kernel)
     DevBuf d_add_flags, d_add_src[4];        // spp_ring_add_rollout_store staging (kept: cudaMalloc / cudaFree cost 100+ ms next to a busy torch allocator)
     int roll_E = 0;
     Layout L_roll;
@@ -179,7 +180,7 @@ int spp_population_destroy(spp_population* p) {
                     (void*)p->r_oidx, (void*)p->r_nidx, (void*)p->r_done, (void*)p->r_end, (void*)p->r_len, (void*)p->scratch_acm})
         if (q) cudaFree(q);
     for (DevBuf* b : {&p->d_obs, &p->d_nobs, &p->d_act, &p->d_rew, &p->d_done, &p->d_aacm, &p->d_eps, &p->d_idx, &p->d_losses, &p->d_tmp, &p->d_roll_scratch, &p->d_env, &p->d_cur,
-                      &p->d_stat_partial, &p->d_stat_moments, &p->d_stat_state, &p->d_stat_hist, &p->d_add_flags, &p->d_add_src[0], &p->d_add_src[1],
+                      &p->d_stat_partial, &p->d_stat_moments, &p->d_stat_state, &p->d_stat_hist, &p->d_progress, &p->d_add_flags, &p->d_add_src[0], &p->d_add_src[1],
                       &p->d_add_src[2], &p->d_add_src[3]})
         b->release();
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -809,6 +810,23 @@ static void fill_args(spp_population* p, UpdateArgs& a, int G) {
 
 static int grid_for(const spp_population* p) { return p->P < p->sm_count ? p->P : p->sm_count; }
 
+// Update bursts of a population larger than the grid run as interleaved (step, agent) work items (update_burst_kernel): the
+// per-agent progress words are zeroed on the launch stream right before the kernel.  SPP_BALANCE=0 keeps whole agents per CTA (A/B).
+static cudaError_t launch_update_balanced(spp_population* p, UpdateArgs& a, cudaStream_t s) {
+    const char* env = getenv("SPP_BALANCE");      // read per launch: the parity test flips it inside one process
+    const bool balance = !(env && env[0] == '0');
+    const int grid = grid_for(p);
+    a.progress = nullptr;
+    if (balance && p->P > grid && a.G > 1 && (long long)p->P * a.G < (1ll << 31)) {
+        cudaError_t e = p->d_progress.ensure((size_t)p->P * sizeof(unsigned int));
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(p->d_progress.p, 0, (size_t)p->P * sizeof(unsigned int), s);
+        if (e != cudaSuccess) return e;
+        a.progress = (unsigned int*)p->d_progress.p;
+    }
+    return launch_update_burst(a, grid, s);
+}
+
 int spp_update_host(spp_population* p, int G, const float* obs, const float* next_obs, const float* action,
                     const float* reward, const int8_t* done, const float* acm_action, const float* eps, uint64_t seed,
                     float* losses) {
@@ -844,7 +862,7 @@ int spp_update_host(spp_population* p, int G, const float* obs, const float* nex
     a.eps = (eps && sac) ? (const float*)p->d_eps.p : nullptr;
     a.seed = seed;
     a.losses = (float*)p->d_losses.p;
-    CK(launch_update_burst(a, grid_for(p), s));
+    CK(launch_update_balanced(p, a, s));
     g_launches++;
     if (losses) CK(cudaMemcpyAsync(losses, p->d_losses.p, (size_t)p->P * G * LOSS_COUNT * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -883,7 +901,7 @@ int spp_update_ring(spp_population* p, int G, const int64_t* idx, const float* e
     a.eps = (eps && sac) ? (const float*)p->d_eps.p : nullptr;
     a.seed = seed;
     a.losses = (float*)p->d_losses.p;
-    CK(launch_update_burst(a, grid_for(p), s));
+    CK(launch_update_balanced(p, a, s));
     g_launches++;
     if (losses) CK(cudaMemcpyAsync(losses, p->d_losses.p, (size_t)p->P * G * LOSS_COUNT * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -902,7 +920,7 @@ int spp_update_ring_device(spp_population* p, int G, uint64_t seed, float* losse
     fill_args(p, a, G);
     a.seed = seed;
     a.losses = losses_dev;
-    CK(launch_update_burst(a, grid_for(p), stream ? (cudaStream_t)stream : p->stream));
+    CK(launch_update_balanced(p, a, stream ? (cudaStream_t)stream : p->stream));
     g_launches++;
     return SPP_OK;
 }
@@ -923,7 +941,7 @@ int spp_update_stage_profile(spp_population* p, int G, uint64_t seed, double* ou
     fill_args(p, a, G);
     a.seed = seed;
     a.timing = (unsigned long long*)p->d_tmp.p;
-    CK(launch_update_burst(a, grid_for(p), p->stream));
+    CK(launch_update_balanced(p, a, p->stream));
     g_launches++;
     std::vector<unsigned long long> t(n);
     CK(cudaMemcpyAsync(t.data(), p->d_tmp.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, p->stream));

@@ -319,19 +319,66 @@ __global__ void __launch_bounds__(kThreads, 1) update_burst_kernel(const __grid_
     if (um) umma_teardown(um);
 }
 
-cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream) {
-    const size_t smem = kSmemLaunchBytes;
-    cudaError_t e;
-    if (a.L.algo == ALGO_SAC) {
-        e = cudaFuncSetAttribute(update_burst_kernel<ALGO_SAC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        update_burst_kernel<ALGO_SAC><<<grid, kThreads, smem, stream>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(update_burst_kernel<ALGO_DDPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        update_burst_kernel<ALGO_DDPG><<<grid, kThreads, smem, stream>>>(a);
+// More agents than CTAs (config 3: 256 agents on 148 SMs): whole agents per CTA (the kernel above) take ceil(P / grid) * G step
+// times with the last wave partly empty (2 x 50 steps for 256 agents).  Here the P * G (step, agent) items run step-major,
+// interleaved over the CTAs: CTA k takes items k, k + grid, ...  -> ceil(P * G / grid) step times (87 instead of 100).  Nothing of an
+// agent lives in a CTA between steps (weights, moments, scratch and step counters are all in global memory), so an agent may change
+// CTA every step; item (g, agent) only has to wait for (g - 1, agent), which another CTA finished one or two of its own items
+// earlier: a release / acquire pair on the agent's progress word (a.progress, zeroed by the host before the launch).  Items are taken
+// in increasing order and only ever wait for smaller ones, and the grid (<= one CTA per SM) is co-resident, so the smallest
+// unfinished item can always run.  The wait is bounded all the same: a kernel that can never finish must not hang the GPU.
+// A separate kernel so that the one-agent-per-CTA kernel (the headline configuration) keeps its code unchanged.
+template <int ALGO>
+__global__ void __launch_bounds__(kThreads, 1) update_burst_interleaved_kernel(const __grid_constant__ UpdateArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& sm = smem_struct(smem_raw);
+    UmmaCtx* um = a.use_umma ? umma_setup(sm, a.use_umma) : nullptr;
+    // an item is kItemSteps consecutive steps of one agent: the step it waits for then lies 2 P / grid > 2 items back (no CTA ever
+    // waits in steady state) at the price of a slightly coarser tail (88 instead of 87 step times for 256 agents x 50 steps)
+    constexpr int kItemSteps = 2;
+    const int chunks = (a.G + kItemSteps - 1) / kItemSteps;
+    const int total = a.population * chunks;      // < 2^31 (checked by the host)
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int q = w / a.population, agent = w - q * a.population;
+        const int g0 = q * kItemSteps, g1 = min(a.G, g0 + kItemSteps);
+        if (g0 > 0) {
+            if (threadIdx.x == 0) {
+                unsigned int done, spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.progress + agent) : "memory");
+                    if (done >= (unsigned int)g0) break;
+                    if (++spins > (1u << 24)) __trap();      // ~10 s: the step this item waits for is lost
+                    __nanosleep(64);
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        Ctx c(a, agent, sm, um);
+        for (int g = g0; g < g1; ++g) update_step<ALGO>(c, g);      // each ends with a CTA barrier behind every global write of the step
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.progress + agent), "r"((unsigned int)g1) : "memory");
+        }
     }
+    if (um) umma_teardown(um);
+}
+
+template <class K>
+static cudaError_t launch_burst(K kernel, const UpdateArgs& a, int grid, cudaStream_t stream) {
+    const size_t smem = kSmemLaunchBytes;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kThreads, smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream) {
+    if (a.progress)
+        return a.L.algo == ALGO_SAC ? launch_burst(update_burst_interleaved_kernel<ALGO_SAC>, a, grid, stream)
+                                    : launch_burst(update_burst_interleaved_kernel<ALGO_DDPG>, a, grid, stream);
+    return a.L.algo == ALGO_SAC ? launch_burst(update_burst_kernel<ALGO_SAC>, a, grid, stream)
+                                : launch_burst(update_burst_kernel<ALGO_DDPG>, a, grid, stream);
 }
 
 }  // namespace spp

@@ -71,6 +71,9 @@ struct UpdateArgs {
     int acm_last_rows;       // ACM regression: rows of the final step when it is a partial batch (0 = full)
     int acm_eval;            // ACM regression: forward + loss only (calculate_validation_loss), no optimiser step
     unsigned long long* timing;   // [G][kStageMarks] %globaltimer stamps of agent 0's stage boundaries (spp_update_stage_profile), or null
+    unsigned int* progress;  // [P] updates completed per agent in THIS launch (zeroed by the host), or null.  Set when the population
+                             // exceeds the grid: the burst then runs as (step, agent) work items interleaved over the CTAs instead of whole
+                             // agents per CTA, see update_burst_kernel
     int use_umma;            // GEMM path of the 256-wide products: 1 tcgen05 3-pass tf32 split (fp32-accurate, default), 0 FFMA tiles,
                              // 2 tcgen05 single tf32 pass (reduced-precision variant, stated tolerance 1e-2)
 };
