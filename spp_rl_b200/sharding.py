@@ -93,3 +93,27 @@ def allreduce_adv_stats(local_stats, dist=None, device="cpu"):
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t)
     return t.cpu().numpy()
+
+
+# ---- inside one GPU: update bursts of a population larger than the grid --------------------------------------------------------
+BURST_ITEM_STEPS = 2      # kItemSteps of update_burst_interleaved_kernel (csrc/update_kernel.cu)
+
+
+def burst_items(population: int, grad_steps: int, grid: int, cta: int, item_steps: int = BURST_ITEM_STEPS):
+    """The work items CTA `cta` of `grid` takes in an update burst, in order, as (agent, first_step, end_step) -- the host-side
+    statement of the loop in update_burst_interleaved_kernel (population > grid) and update_burst_kernel (population <= grid: whole
+    agents).  An item may start once `first_step` steps of its agent are complete (the agent's progress word)."""
+    if population <= grid:
+        return [(a, 0, grad_steps) for a in range(cta, population, grid)]
+    chunks = (grad_steps + item_steps - 1) // item_steps
+    out = []
+    for w in range(cta, population * chunks, grid):
+        q, agent = divmod(w, population)
+        out.append((agent, q * item_steps, min(grad_steps, (q + 1) * item_steps)))
+    return out
+
+
+def burst_step_times(population: int, grad_steps: int, grid: int, item_steps: int = BURST_ITEM_STEPS) -> int:
+    """Length of a burst in units of one update step when every step takes the same time (the longest CTA's item list):
+    256 agents x 50 steps on 148 CTAs -> 88 (whole agents per CTA: 100)."""
+    return max(sum(e - b for _, b, e in burst_items(population, grad_steps, grid, c, item_steps)) for c in range(min(grid, population)))

@@ -154,3 +154,44 @@ def test_population_train_schedule_fires_where_the_reference_loop_does():
     want = [e for e in _frame_by_frame(2000, 256, 50, 50, 100, 1000, 200, 10) if e[0] != "rollout"]
     assert got == want
     assert sum(e[1] * 10 for e in train_schedule(0, 2000, 10, 256, 50, 50, 100, 1000, 200, 10) if e[0] == "rollout") == 2000
+
+
+def test_interleaved_burst_schedule_runs_every_step_once_in_order_and_never_deadlocks():
+    """update_burst_interleaved_kernel (populations larger than the grid; csrc/update_kernel.cu) restated on the host
+    (sharding.burst_items): every (agent, step) is executed exactly once, an agent's steps in order, and an event-driven run with
+    arbitrary item durations -- every CTA takes its items in order and waits for the agent's progress word -- always finishes
+    (each item only waits for a smaller one); with equal step times 256 agents x 50 steps on 148 CTAs take 88 step times, not 100."""
+    from spp_rl_b200.sharding import burst_items, burst_step_times
+    rng = np.random.RandomState(0)
+    for P_, G, grid in ((256, 50, 148), (188, 3, 148), (149, 7, 148), (300, 1, 148), (5, 4, 2), (7, 5, 3), (148, 50, 148), (3, 9, 8)):
+        lists = [burst_items(P_, G, grid, c) for c in range(min(grid, P_))]
+        seen = {}
+        for items in lists:
+            for agent, b, e in items:
+                for g in range(b, e):
+                    assert (agent, g) not in seen
+                    seen[(agent, g)] = True
+        assert len(seen) == P_ * G
+        # event-driven run: CTA c is free at t[c]; its next item starts at max(t[c], time its agent reached `b` steps)
+        dur = lambda: float(rng.rand() * 2 + 0.1)      # noqa: E731
+        t = [0.0] * len(lists); pos = [0] * len(lists)
+        progress = {a: (0, 0.0) for a in range(P_)}      # agent -> (steps complete, time of completion)
+        remaining = sum(len(x) for x in lists)
+        while remaining:
+            ran = False
+            for c, items in enumerate(lists):
+                if pos[c] == len(items):
+                    continue
+                agent, b, e = items[pos[c]]
+                done, when = progress[agent]
+                if done < b:
+                    continue      # the CTA spins on the progress word
+                assert done == b, "steps of an agent out of order"
+                start = max(t[c], when)
+                t[c] = start + sum(dur() for _ in range(b, e))
+                progress[agent] = (e, t[c])
+                pos[c] += 1; remaining -= 1; ran = True
+            assert ran, "deadlock: no CTA can take its next item"
+        assert all(progress[a][0] == G for a in range(P_))
+    assert burst_step_times(256, 50, 148) == 88 and burst_step_times(256, 50, 148, item_steps=50) == 100
+    assert burst_step_times(148, 50, 148) == 50 and burst_step_times(128, 50, 148) == 50
