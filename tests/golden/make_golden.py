@@ -24,6 +24,9 @@ Fixtures written next to this file:
                          ppo_walker's rollout; the second one shows the never-zeroed gradients (post-step weights, Adam moments, losses)
   config1_pendulum.npz   BASELINE config 1: SAC_AcM on Pendulum-v0, pre_train() + train() for 400 frames from fixed weights and seeds:
                          replay indices drawn, ring cursors / index arrays, observation chain, final weights, statistics, returns
+                         (its `ref_seconds` entry is the wall-clock time of the reference's pre_train / train here -- the frames/s
+                         SURVEY 8d asks config 1 to report -- and therefore the ONE array that differs from run to run; every
+                         other array of every fixture regenerates bit-identically)
   pkl_actions.npz        notebooks/load_and_test.ipynb flow on each of the 9 trained models/*.pkl (copied to tests/golden/models/):
                          construct with the notebook's flags, load(), deterministic action + ACM action on fixed observations
 """
