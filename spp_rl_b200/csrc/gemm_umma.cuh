@@ -67,6 +67,7 @@ struct UmmaCtx {
     uint32_t tmem;              // TMEM base (512 columns)
     uint32_t phase_bits;        // per-slot mbarrier parity the threads wait for next (identical in every thread)
     uint32_t dbg;               // timing experiments only (self-test): 1 = no MMAs, 2 = no operand staging, 4 = no epilogue
+    uint32_t zraw;              // shared-space address of a 32 KB landing zone for the NEXT raw B chunk (umma_mainloop_z), or 0: none
 };
 
 // Per-thread state of one operand's global -> register -> shared path.  ROWS = 128 (A) or 256 (B); NP float4 per thread
@@ -117,13 +118,26 @@ struct UmmaOperand {
         }
     }
     // in-place split of the chunks this thread copied: hi plane <- rn_tf32(x), lo plane <- rn_tf32(x - hi)
-    __device__ __forceinline__ void split(uint32_t hi, uint32_t lo) const {
+    __device__ __forceinline__ void split(uint32_t hi, uint32_t lo) const { split_from(hi, hi, lo); }
+    // raw words landing zone -> hi plane, unsplit (the single-pass variant's operands are the raw fp32 words)
+    __device__ __forceinline__ void move_from(uint32_t raw, uint32_t hi) const {
+#pragma unroll
+        for (int p0 = 0; p0 < NP; p0 += 4) {
+            float4 r[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) r[p] = umma::lds128(raw + dst0 + (p0 + p) * DSTEP);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) umma::sts128(hi + dst0 + (p0 + p) * DSTEP, r[p]);
+        }
+    }
+    // the same with the raw words at `raw` (same offsets: the landing zone of umma_mainloop_z, or the hi plane itself)
+    __device__ __forceinline__ void split_from(uint32_t raw, uint32_t hi, uint32_t lo) const {
         // four chunks at a time: the 128 running sums of the main loop leave ~100 registers for everything else
 #pragma unroll
         for (int p0 = 0; p0 < NP; p0 += 4) {
             float4 r[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) r[p] = umma::lds128(hi + dst0 + (p0 + p) * DSTEP);
+            for (int p = 0; p < 4; ++p) r[p] = umma::lds128(raw + dst0 + (p0 + p) * DSTEP);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 float4 h, l;
@@ -339,6 +353,129 @@ __device__ __noinline__ uint32_t umma_mainloop(bool A_KM, const float* __restric
 }
 
 
+// The same main loop with a LANDING ZONE for the raw B operand (UmmaCtx::zraw: 32 KB outside the operand slots).  With two slots the
+// loop above can only request the raw chunk c + 1 once the MMAs of chunk c - 1 have retired, i.e. at the start of iteration c, so its
+// split always runs after the copy latency, while the tensor core is idle (staging, MMAs and the drain add up without overlap: 37.6 us
+// per 256-cubed product = 15.4 + 12.5 + 9.3, profiles/r02_update_bk16_experiment.md).  Here raw B (two thirds of the staging work)
+// is requested a whole iteration earlier into the landing zone and split from there into the free slot WHILE the MMAs of chunk c
+// run; raw A (16 KB) still lands in place and is split after the drain, by which time it has arrived.  Every thread re-reads only the
+// 16-byte words it copied itself, so the landing zone needs no barrier of its own.  Same MMAs, same drains, same order of additions
+// as umma_mainloop: the results are bitwise the same.
+// The reduced-precision variant (dbg & kUmmaSinglePass: raw words as operands, one pass, whole K in one accumulator) runs through
+// the same loop: raw B is moved from the landing zone to the slot unsplit, nothing is drained before the end.
+#ifdef SPP_UMMA_LANDING_ZONE
+template <bool B_KM>
+__device__ __noinline__ uint32_t umma_mainloop_z(bool A_KM, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M,
+                                                 int K, int m0, unsigned char* smem, uint64_t* mbar, uint32_t tmem, uint32_t phase_in, uint32_t dbg,
+                                                 uint32_t zraw) {
+    using namespace umma;
+    static_assert(kBK == 32 && kDrainEvery == 1 && kUmmaSlots == 2, "the landing-zone loop is written for two 32-wide slots");
+    constexpr int N = 256;
+    const int nchunks = (K + kBK - 1) / kBK;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t idesc = make_idesc_tf32(128, N, A_KM ? 0 : 1, B_KM ? 0 : 1);
+    const int wq = warp_id() & 3, chalf = warp_id() >> 2;
+    const uint32_t my_tmem = tmem + ((uint32_t)(32 * wq) << 16) + chalf * 128;      // this thread's lane / column half
+    const bool fast = (dbg & kUmmaSinglePass) != 0;
+    uint32_t phase_bits = phase_in;
+    UmmaOperand<B_KM, 256> lb;
+    lb.init(B, ldb, N, 0);
+    UmmaOperandA la;
+    la.init(A_KM, A, lda, M, m0);
+    float sum[128];
+    // chunk 0: raw A -> hi plane of slot 0, raw B -> landing zone; both split into slot 0; then raw B of chunk 1 -> landing zone
+    la.issue(0, K, smem0);
+    lb.issue(0, K, zraw);
+    cp_async_commit();
+    cp_async_wait<0>();
+    if (fast) lb.move_from(zraw, smem0 + 2 * kUmmaAPlane);
+    else {
+        la.split(smem0, smem0 + kUmmaAPlane);
+        lb.split_from(zraw, smem0 + 2 * kUmmaAPlane, smem0 + 2 * kUmmaAPlane + kUmmaBPlane);
+    }
+    if (1 < nchunks) lb.issue(kBK, K, zraw);
+    cp_async_commit();                      // group [B(1)] (empty when there is no chunk 1)
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+        const int slot = c & 1, ps = slot ^ 1;
+        const uint32_t ah = smem0 + slot * kUmmaSlotBytes, al = ah + kUmmaAPlane, bh = al + kUmmaAPlane, bl = bh + kUmmaBPlane;
+        fence_proxy_async();      // the split planes of chunk c (st.shared) -> visible to the tensor core
+        fence_before_sync();      // orders this thread's drain of chunk c - 2 (same accumulator) before the MMAs below
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after_sync();
+            const uint32_t d = tmem + (fast ? 0 : (c & 1) * N);
+            const int nks = min(kKSteps, (K - kBK * c + 7) / 8);
+            if (fast) {     // reduced-precision variant: the raw fp32 words are the tf32 operands, the whole K accumulates in TMEM
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t dah = A_KM ? km_desc(ah, ks) : mn_desc(ah, ks);
+                    const uint64_t dbh = B_KM ? km_desc(bh, ks) : mn_desc(bh, ks);
+                    mma_tf32(d, dah, dbh, idesc, (c | ks) ? 1u : 0u);
+                }
+            } else {
+                for (int ks = 0; ks < nks; ++ks) {      // cross terms first: the accumulator is still tiny
+                    const uint64_t dah = A_KM ? km_desc(ah, ks) : mn_desc(ah, ks);
+                    const uint64_t dal = A_KM ? km_desc(al, ks) : mn_desc(al, ks);
+                    const uint64_t dbh = B_KM ? km_desc(bh, ks) : mn_desc(bh, ks);
+                    const uint64_t dbl = B_KM ? km_desc(bl, ks) : mn_desc(bl, ks);
+                    mma_tf32(d, dal, dbh, idesc, ks ? 1u : 0u);
+                    mma_tf32(d, dah, dbl, idesc, 1u);
+                }
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t dah = A_KM ? km_desc(ah, ks) : mn_desc(ah, ks);
+                    const uint64_t dbh = B_KM ? km_desc(bh, ks) : mn_desc(bh, ks);
+                    mma_tf32(d, dah, dbh, idesc, 1u);
+                }
+            }
+            commit(mbar + slot);
+        }
+        if (c >= 1) {       // chunk c - 1 has retired: its slot is free, its accumulator complete
+            mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
+            phase_bits ^= (1u << ps);
+            fence_after_sync();
+        }
+        const bool more = c + 1 < nchunks;
+        const uint32_t nah = smem0 + ps * kUmmaSlotBytes, nal = nah + kUmmaAPlane, nbh = nal + kUmmaAPlane, nbl = nbh + kUmmaBPlane;
+        if (more) {
+            la.issue(kBK * (c + 1), K, nah);      // raw A of chunk c + 1 -> its place in the free slot
+            cp_async_commit();                    // group [A(c + 1)]
+            cp_async_wait<1>();                   // the older group [B(c + 1)]: this thread's raw B words are in the landing zone
+            if (fast) lb.move_from(zraw, nbh);
+            else lb.split_from(zraw, nbh, nbl);   // ... and go to the free slot while the tensor core works on chunk c
+            if (c + 2 < nchunks) lb.issue(kBK * (c + 2), K, zraw);
+            cp_async_commit();                    // group [B(c + 2)] (possibly empty)
+        }
+        if (c >= 1 && !fast) {       // drain chunk c - 1
+            if (c == 1) umma_drain<true>(my_tmem + ps * N, sum);
+            else umma_drain<false>(my_tmem + ps * N, sum);
+        }
+        if (more) {
+            cp_async_wait<1>();                   // all but the newest group: raw A of chunk c + 1 has landed
+            if (!fast) la.split(nah, nal);
+        }
+    }
+    {   // last chunk
+        const int ps = (nchunks - 1) & 1;
+        mbar_wait(mbar + ps, (phase_bits >> ps) & 1u);
+        phase_bits ^= (1u << ps);
+        fence_after_sync();
+        if (nchunks <= 1 || fast) umma_drain<true>(my_tmem + (fast ? 0 : ps * N), sum);
+        else umma_drain<false>(my_tmem + ps * N, sum);
+        fence_before_sync();
+    }
+    cp_async_wait<0>();      // (only empty groups are left)
+    {   // running sums -> shared staging; every MMA that read the slots has retired
+        const int srow = 32 * wq + lane_id();
+        const uint32_t base = smem0 + 4 * (chalf * kStageBlockFloats + srow * kStagePitch);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) sts128(base + 16 * q, make_float4(sum[4 * q], sum[4 * q + 1], sum[4 * q + 2], sum[4 * q + 3]));
+    }
+    __syncthreads();
+    return phase_bits;
+}
+#endif      // SPP_UMMA_LANDING_ZONE
+
+
 // The wrapper is a real call in the update kernel: the main loop and the epilogues get their register budget from the live set
 // of their caller (ptxas allocates across the call graph), and inlined into the 35 k-instruction kernel body that live set cost the
 // epilogues ~0.5 KB and the body 2.5 KB of spills through a ~15 KB L1 (+7.7 % updates/s as a call).  The rollout kernel has
@@ -353,10 +490,15 @@ __device__ SPP_UMMA_WRAPPER_ATTR void gemm256_umma(const float* __restrict__ A, 
                                              UmmaCtx& u, Epi& epi) {
     const int mtiles = (M + 127) / 128;
     unsigned char* smem = u.smem; uint64_t* mbar = u.mbar;
-    const uint32_t tmem = u.tmem, dbg = u.dbg;
+    const uint32_t tmem = u.tmem, dbg = u.dbg, zraw = u.zraw;
     uint32_t phase = u.phase_bits;
     for (int mt = 0; mt < mtiles; ++mt) {
+#ifdef SPP_UMMA_LANDING_ZONE      // (one main loop per kernel: a second one in the call graph costs the kernel body its registers, 1.4 -> 9.3 KB of spills)
+        phase = umma_mainloop_z<B_KM>(A_KM, A, lda, B, ldb, M, K, mt * 128, smem, mbar, tmem, phase, dbg, zraw);
+#else
         phase = umma_mainloop<B_KM>(A_KM, A, lda, B, ldb, M, K, mt * 128, smem, mbar, tmem, phase, dbg);
+        (void)zraw;
+#endif
         if (!(dbg & 4)) umma_epilogue<A_KM, Epi>(umma::smem_u32(smem), reinterpret_cast<float*>(smem), mt * 128, M, epi);
         if (threadIdx.x == 0) u.phase_bits = phase;
         __syncthreads();          // the staging aliases the operand slots of the next tile / GEMM; publishes the parities

@@ -1,4 +1,7 @@
 // Fused off-policy SPP update burst kernel (SAC_AcM / DDPG_AcM), sm_100a.  See update_kernel.cuh.
+#ifndef SPP_NO_LANDING_ZONE
+#define SPP_UMMA_LANDING_ZONE      // wide products through umma_mainloop_z (gemm_umma.cuh); -DSPP_NO_LANDING_ZONE builds the two-slot loop for A/B
+#endif
 #include "update_kernel.cuh"
 
 namespace spp {

@@ -6,6 +6,8 @@
 // (rltoolkit/algorithms/ddpg/ddpg.py:231-237) with BufferAcMOffPolicy.sample_batch
 // (rltoolkit/buffer/replay_buffer.py:385-398,233-261).
 #pragma once
+#include <cstddef>
+
 #include "gemm_tile.cuh"
 #include "gemm_umma.cuh"
 #include "layout.h"
@@ -85,6 +87,8 @@ struct Smem {
     float gemm[kUmmaSmemBytes / 4];   // operand pipeline of the tile GEMMs (tcgen05 path: four 32 KB swizzled planes; FFMA path: first 102 KB)
     float red[8 * 2 * kHidden];       // cross-warp column partials (8 warps x 512)
     float vecs[4 * kHidden];          // reduced vectors
+    float zpad[(kUmmaBPlane - (8 * 2 * kHidden + 4 * kHidden) * 4) / 4];      // red | vecs | zpad = 32 KB: the raw-B landing zone of
+                                      // umma_mainloop_z; red / vecs only carry data inside the row-wise stages, never across a wide product
     float small[64];
     AdamScalars adam[4];
     float alpha;                      // temperature as fp32 (Python float rounded when it meets fp32 tensors)
@@ -94,6 +98,10 @@ struct Smem {
 };
 static_assert(kUmmaSmemBytes / 4 >= kGemmSmemFloats, "the FFMA pipeline aliases the tcgen05 stages");
 constexpr size_t kSmemLaunchBytes = sizeof(Smem) + 1024;   // + slack to align the base to a swizzle atom (1024 B)
+static_assert(offsetof(Smem, vecs) == offsetof(Smem, red) + sizeof(float) * 8 * 2 * kHidden && offsetof(Smem, zpad) == offsetof(Smem, vecs) + sizeof(float) * 4 * kHidden,
+              "the landing zone is red | vecs | zpad, contiguous");
+static_assert(offsetof(Smem, red) % 1024 == 0, "landing zone keeps the operand planes' bank alignment");
+static_assert(kSmemLaunchBytes <= 232448, "227 KB of dynamic shared memory per CTA on sm_100");
 
 __device__ __forceinline__ Smem& smem_struct(unsigned char* raw) {
     return *reinterpret_cast<Smem*>(raw + ((1024u - (umma::smem_u32(raw) & 1023u)) & 1023u));
@@ -141,6 +149,7 @@ __device__ __forceinline__ UmmaCtx* umma_setup(Smem& sm, int path) {
         sm.um.tmem = sm.tmem_base;
         sm.um.phase_bits = 0;
         sm.um.dbg = (path == 2) ? kUmmaSinglePass : 0u;
+        sm.um.zraw = umma::smem_u32(sm.red);      // used by the kernels built with SPP_UMMA_LANDING_ZONE (the update bursts)
     }
     __syncthreads();
     return &sm.um;
