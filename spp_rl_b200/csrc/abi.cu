@@ -16,6 +16,7 @@
 
 namespace spp {
 cudaError_t launch_update_burst(const UpdateArgs& a, int grid, cudaStream_t stream);
+cudaError_t launch_update_burst_twoslot(const UpdateArgs& a, int grid, cudaStream_t stream);      // update_kernel_twoslot.cu
 cudaError_t launch_acm_train(const UpdateArgs& a, int grid, cudaStream_t stream);
 cudaError_t launch_rollout(const RolloutArgs& r, int grid, cudaStream_t stream);
 }
@@ -824,7 +825,10 @@ static cudaError_t launch_update_balanced(spp_population* p, UpdateArgs& a, cuda
         if (e != cudaSuccess) return e;
         a.progress = (unsigned int*)p->d_progress.p;
     }
-    return launch_update_burst(a, grid, s);
+    // the wide products' main loop: landing-zone loop (default path), two-slot loop for the single-pass variant and on request
+    const char* loop = getenv("SPP_UMMA_LOOP");
+    const bool twoslot = a.use_umma == 2 || (loop && loop[0] == 't');
+    return twoslot ? launch_update_burst_twoslot(a, grid, s) : launch_update_burst(a, grid, s);
 }
 
 int spp_update_host(spp_population* p, int G, const float* obs, const float* next_obs, const float* action,
