@@ -189,6 +189,22 @@ def cpu_baseline_block(cores):
     return out
 
 
+def reference_ppo_block(transitions=16384, limit_s=300):
+    """one perform_iteration of the reference's own PPO_AcM on one host core at a reduced batch, phase by phase
+    (tools/ref_ppo_phases.py, its own process: single thread, the gym shim's shape-only Walker2d); reported per transition beside the
+    config-4 block.  A reported baseline; never on the product path."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_ppo_phases.py"), str(transitions)], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=limit_s, cwd=ROOT)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": "tools/ref_ppo_phases.py exited %d: %s" % (r.returncode, (r.stderr or "").strip().splitlines()[-1:] or "")}
+        return json.loads(lines[-1])
+    except Exception as e:      # noqa: BLE001  (a baseline leg must not take the bench line with it)
+        return {"unavailable": repr(e)[:200]}
+
+
 def host_cores():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -483,8 +499,11 @@ def main():
 
     # ------------------------------------------------------------------ CPU baseline first (fork before CUDA init)
     cpu_base = None
+    ref_ppo = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_block(host_cores())
+        if not args.no_ppo:
+            ref_ppo = reference_ppo_block()
 
     import numpy as np
     import torch
@@ -687,6 +706,8 @@ def main():
     ppo_cfg4 = None
     if not args.no_ppo:
         ppo_cfg4 = ppo_cfg4_block(local_rank, rank, world, dist, max(1, min(K, 3)), 1)
+        if ref_ppo is not None and isinstance(ppo_cfg4, dict):
+            ppo_cfg4["cpu_reference"] = ref_ppo      # the reference's own PPO_AcM phases on one host core, per transition (SURVEY 8d iv)
 
     if rank == 0:
         peaks = {}
