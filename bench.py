@@ -193,13 +193,23 @@ def reference_ppo_block(transitions=16384, limit_s=300):
     """one perform_iteration of the reference's own PPO_AcM on one host core at a reduced batch, phase by phase
     (tools/ref_ppo_phases.py, its own process: single thread, the gym shim's shape-only Walker2d); reported per transition beside the
     config-4 block.  A reported baseline; never on the product path."""
-    import subprocess
+    return _run_ref_tool("ref_ppo_phases.py", transitions, limit_s)
+
+
+def reference_rollout_block(transitions=10000, limit_s=180):
+    """the body of the reference's frame loop (normalize -> noise_action -> process_action -> add_obs / add_timestep,
+    ddpg.py:205-220) for a SAC_AcM at Hopper shapes on one host core with a no-op environment (tools/ref_rollout_step.py): the CPU
+    number beside the rollout half of the metric.  A reported baseline; never on the product path."""
+    return _run_ref_tool("ref_rollout_step.py", transitions, limit_s)
+
+
+def _run_ref_tool(script, arg, limit_s):
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_ppo_phases.py"), str(transitions)], stdout=subprocess.PIPE,
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script), str(arg)], stdout=subprocess.PIPE,
                            stderr=subprocess.PIPE, text=True, timeout=limit_s, cwd=ROOT)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if r.returncode != 0 or not lines:
-            return {"unavailable": "tools/ref_ppo_phases.py exited %d: %s" % (r.returncode, (r.stderr or "").strip().splitlines()[-1:] or "")}
+            return {"unavailable": "tools/%s exited %d: %s" % (script, r.returncode, (r.stderr or "").strip().splitlines()[-1:] or "")}
         return json.loads(lines[-1])
     except Exception as e:      # noqa: BLE001  (a baseline leg must not take the bench line with it)
         return {"unavailable": repr(e)[:200]}
@@ -499,11 +509,13 @@ def main():
 
     # ------------------------------------------------------------------ CPU baseline first (fork before CUDA init)
     cpu_base = None
-    ref_ppo = None
+    ref_ppo = ref_roll = None
     if rank == 0 and N == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_block(host_cores())
         if not args.no_ppo:
             ref_ppo = reference_ppo_block()
+        if not args.no_rollout:
+            ref_roll = reference_rollout_block()
 
     import numpy as np
     import torch
@@ -748,6 +760,8 @@ def main():
                                  "achieved counts algorithmic fp32 FLOPs (each is 3 tensor-core passes); peak is the dense bf16 figure"},
             "rollout": rollout, "gather": gather, "train_loop": train_loop, "ppo_cfg4": ppo_cfg4, "reduced_precision_variant": variant, "cpu_baseline": cpu_base, "clocks": clocks,
         }
+        if rollout is not None and ref_roll is not None:
+            rollout["cpu_reference"] = ref_roll      # the reference's frame-loop body on one host core (SURVEY 8d iii)
         if rollout is not None:
             rollout["roofline"]["peak"] = peak
             rollout["roofline"]["frac"] = rollout["roofline"]["achieved"] / peak

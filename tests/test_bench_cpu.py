@@ -19,6 +19,14 @@ def test_reference_ppo_phase_timer_reports_every_phase():
     assert abs(sum(r["phases_ms"].values()) - r["ms_per_iteration"]) < 1e-6 * r["ms_per_iteration"] + 1.0
 
 
+def test_reference_rollout_step_timer():
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.reference_rollout_block(transitions=600, limit_s=240)
+    assert "unavailable" not in r, r
+    assert r["transitions"] > 0 and r["us_per_transition"] > 0 and r["transitions_per_s"] > 0
+
+
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
